@@ -1,0 +1,483 @@
+// b200_gemm: C[M,N] = A[M,K] * B[N,K]^T on tcgen05 tensor cores (sm_100a).
+//
+// Replaces every nn.Linear / conv-as-GEMM on the DINOv2 hot path of the reference
+// (qkv/proj: layers/attention.py:44-63, Mlp fc1/fc2: layers/mlp.py:31-42, PatchEmbed.proj:
+// layers/patch_embed.py:77-110, DINOv2ProjectionHead: _methods/dinov2/dinov2_head.py:66-95)
+// and their autograd backward (dgrad / wgrad), which the reference leaves to cuBLASLt.
+//
+// Design (one persistent CTA per SM, warp-specialised):
+//   warp 0      : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx)
+//   warp 1      : tcgen05.mma issuer (single thread), accumulators in TMEM, double-buffered
+//   warps 2..9  : epilogue (tcgen05.ld -> registers -> fused bias/GELU/LayerScale+residual/
+//                 dGELU/atomic split-K) with vectorised global stores
+// bf16 operands, fp32 accumulate. Either operand may be K-major (row-major [rows,K]) or
+// MN-major (stored [K,rows]); the latter feeds wgrad (contraction over tokens) without
+// materialising transposes.
+#include <cuda.h>
+#include "common.cuh"
+#include "../../include/b200dino.h"
+
+namespace b200 {
+
+static constexpr int BLOCK_M = 128;
+static constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle-128B row
+static constexpr int UMMA_K = 16;
+static constexpr int NUM_EPI_WARPS = 8;
+static constexpr int NUM_THREADS = (2 + NUM_EPI_WARPS) * 32;
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BLOCK_N <= 128) ? 6 : (BLOCK_N <= 192 ? 5 : 4);
+  static constexpr int ACC_STRIDE = 256;  // TMEM columns between the two accumulator buffers
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct GemmDev {
+  int M, N, K;
+  int a_mn, b_mn;
+  int splits;
+  int epi;
+  float alpha;
+  void* C;
+  long long ldc;
+  void* C2;
+  long long ldc2;
+  const void* aux;
+  long long ldaux;
+  const float* bias;
+  const float* gamma;
+  const float* rowscale;
+  int rows_per_scale;
+};
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                   uint32_t sbo_bytes) {
+  // cute::UMMA::SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start>>4 [0,14), LBO>>4 [16,30),
+  // SBO>>4 [32,46), version=1 [46,48), layout_type=SWIZZLE_128B(2) [61,64)
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__device__ __forceinline__ uint32_t make_idesc(int n, int a_mn, int b_mn) {
+  // cute::UMMA::InstrDescriptor: c_format F32(1)@[4,6), a/b_format BF16(1)@[7,10)/[10,13),
+  // a_major@15, b_major@16, N>>3@[17,23), M>>4@[24,29)
+  uint32_t d = 0;
+  d |= 1u << 4;
+  d |= 1u << 7;
+  d |= 1u << 10;
+  d |= (uint32_t)(a_mn ? 1 : 0) << 15;
+  d |= (uint32_t)(b_mn ? 1 : 0) << 16;
+  d |= (uint32_t)(n >> 3) << 17;
+  d |= (uint32_t)(BLOCK_M >> 4) << 24;
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue for one 32-column chunk of one output row held in registers.
+__device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t (&acc)[32], int row,
+                                               int col0) {
+  if (row >= p.M || col0 >= p.N) return;
+  const int ncols = min(32, p.N - col0);  // multiple of 8 (N % 8 == 0 enforced on host)
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) * p.alpha;
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      if (i < ncols) {
+        float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+      }
+    }
+  }
+  switch (p.epi) {
+    case B200_EPI_BF16: {
+      __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        if (i < ncols) {
+          uint4 o;
+          o.x = pack_bf16x2(v[i], v[i + 1]); o.y = pack_bf16x2(v[i + 2], v[i + 3]);
+          o.z = pack_bf16x2(v[i + 4], v[i + 5]); o.w = pack_bf16x2(v[i + 6], v[i + 7]);
+          *reinterpret_cast<uint4*>(c + i) = o;
+        }
+      }
+    } break;
+    case B200_EPI_F32: {
+      float* c = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        if (i < ncols) *reinterpret_cast<float4*>(c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+    } break;
+    case B200_EPI_F32_ATOMIC: {
+      float* c = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        if (i < ncols) atomicAdd(reinterpret_cast<float4*>(c + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+      }
+    } break;
+    case B200_EPI_BIAS_GELU: {
+      // u = bf16(acc + bias) (what nn.Linear returns under bf16 autocast); h = bf16(gelu(u))
+      __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0;
+      __nv_bfloat16* c2 = p.C2 ? reinterpret_cast<__nv_bfloat16*>(p.C2) + (size_t)row * p.ldc2 + col0 : nullptr;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        if (i < ncols) {
+          float u[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) u[j] = bf16_round(v[i + j]);
+          if (c2) {
+            uint4 o;
+            o.x = pack_bf16x2(u[0], u[1]); o.y = pack_bf16x2(u[2], u[3]);
+            o.z = pack_bf16x2(u[4], u[5]); o.w = pack_bf16x2(u[6], u[7]);
+            *reinterpret_cast<uint4*>(c2 + i) = o;
+          }
+          uint4 o;
+          o.x = pack_bf16x2(gelu_erf(u[0]), gelu_erf(u[1])); o.y = pack_bf16x2(gelu_erf(u[2]), gelu_erf(u[3]));
+          o.z = pack_bf16x2(gelu_erf(u[4]), gelu_erf(u[5])); o.w = pack_bf16x2(gelu_erf(u[6]), gelu_erf(u[7]));
+          *reinterpret_cast<uint4*>(c + i) = o;
+        }
+      }
+    } break;
+    case B200_EPI_RESIDUAL: {
+      // o = bf16(acc + bias); x_out = x_in + gamma * o * rowscale   (fp32 residual stream)
+      float* c = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
+      const float* xin = reinterpret_cast<const float*>(p.aux) + (size_t)row * p.ldaux + col0;
+      __nv_bfloat16* c2 = p.C2 ? reinterpret_cast<__nv_bfloat16*>(p.C2) + (size_t)row * p.ldc2 + col0 : nullptr;
+      const float rs = p.rowscale ? __ldg(p.rowscale + row / p.rows_per_scale) : 1.0f;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        if (i < ncols) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = bf16_round(v[i + j]);
+          if (c2) {
+            uint4 ob;
+            ob.x = pack_bf16x2(o[0], o[1]); ob.y = pack_bf16x2(o[2], o[3]);
+            ob.z = pack_bf16x2(o[4], o[5]); ob.w = pack_bf16x2(o[6], o[7]);
+            *reinterpret_cast<uint4*>(c2 + i) = ob;
+          }
+          float4 g0 = make_float4(1.f, 1.f, 1.f, 1.f), g1 = g0;
+          if (p.gamma) {
+            g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + col0 + i));
+            g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + col0 + i + 4));
+          }
+          float4 x0 = *reinterpret_cast<const float4*>(xin + i);
+          float4 x1 = *reinterpret_cast<const float4*>(xin + i + 4);
+          x0.x += (o[0] * g0.x) * rs; x0.y += (o[1] * g0.y) * rs; x0.z += (o[2] * g0.z) * rs; x0.w += (o[3] * g0.w) * rs;
+          x1.x += (o[4] * g1.x) * rs; x1.y += (o[5] * g1.y) * rs; x1.z += (o[6] * g1.z) * rs; x1.w += (o[7] * g1.w) * rs;
+          *reinterpret_cast<float4*>(c + i) = x0;
+          *reinterpret_cast<float4*>(c + i + 4) = x1;
+        }
+      }
+    } break;
+    case B200_EPI_DGELU: {
+      // dU = bf16( bf16(acc) * gelu'(u) ), u = aux (bf16 pre-activation saved by the forward)
+      __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0;
+      const __nv_bfloat16* up = reinterpret_cast<const __nv_bfloat16*>(p.aux) + (size_t)row * p.ldaux + col0;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        if (i < ncols) {
+          uint4 ub = *reinterpret_cast<const uint4*>(up + i);
+          float2 u0 = unpack_bf16x2(ub.x), u1 = unpack_bf16x2(ub.y), u2 = unpack_bf16x2(ub.z), u3 = unpack_bf16x2(ub.w);
+          uint4 o;
+          o.x = pack_bf16x2(bf16_round(v[i]) * gelu_erf_grad(u0.x), bf16_round(v[i + 1]) * gelu_erf_grad(u0.y));
+          o.y = pack_bf16x2(bf16_round(v[i + 2]) * gelu_erf_grad(u1.x), bf16_round(v[i + 3]) * gelu_erf_grad(u1.y));
+          o.z = pack_bf16x2(bf16_round(v[i + 4]) * gelu_erf_grad(u2.x), bf16_round(v[i + 5]) * gelu_erf_grad(u2.y));
+          o.w = pack_bf16x2(bf16_round(v[i + 6]) * gelu_erf_grad(u3.x), bf16_round(v[i + 7]) * gelu_erf_grad(u3.y));
+          *reinterpret_cast<uint4*>(c + i) = o;
+        }
+      }
+    } break;
+    default: break;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int BLOCK_N>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmDev p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  // swizzle-128B operand tiles need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int kb_total = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int kb_per_split = (kb_total + p.splits - 1) / p.splits;
+  const int n_splits = (kb_total + kb_per_split - 1) / kb_per_split;  // effective, no empty splits
+  const int total_work = tiles_m * tiles_n * n_splits;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], NUM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_base_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int split = w % n_splits;
+      const int tile = w / n_splits;
+      const int m0 = (tile % tiles_m) * BLOCK_M;
+      const int n0 = (tile / tiles_m) * BLOCK_N;
+      const int kb0 = split * kb_per_split;
+      const int kb1 = min(kb_total, kb0 + kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (lane == 0) {
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          const int k0 = kb * BLOCK_K;
+          if (!p.a_mn) {
+            tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);
+          } else {
+#pragma unroll
+            for (int a = 0; a < BLOCK_M / 64; ++a)
+              tma_load_2d(sa + a * (BLOCK_K * 128), &tmA, &full_bar[stage], m0 + a * 64, k0);
+          }
+          if (!p.b_mn) {
+            tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);
+          } else {
+#pragma unroll
+            for (int a = 0; a < BLOCK_N / 64; ++a)
+              tma_load_2d(sb + a * (BLOCK_K * 128), &tmB, &full_bar[stage], n0 + a * 64, k0);
+          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc(BLOCK_N, p.a_mn, p.b_mn);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int split = w % n_splits;
+      const int kb0 = split * kb_per_split;
+      const int kb1 = min(kb_total, kb0 + kb_per_split);
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * Cfg::ACC_STRIDE;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          // K-major:  SBO = 8 rows * 128 B;                         K-step = 32 B inside the atom
+          // MN-major: LBO = BLOCK_K*128 B between 64-wide MN atoms, SBO = 8 k-rows * 128 B,
+          //           K-step = 16 k-rows * 128 B
+          const uint64_t adesc0 = p.a_mn ? make_smem_desc(sa, BLOCK_K * 128, 1024) : make_smem_desc(sa, 16, 1024);
+          const uint64_t bdesc0 = p.b_mn ? make_smem_desc(sb, BLOCK_K * 128, 1024) : make_smem_desc(sb, 16, 1024);
+          const uint32_t a_step = p.a_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+          const uint32_t b_step = p.b_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            umma_f16(tmem_d, adesc0 + (uint64_t)(k * a_step), bdesc0 + (uint64_t)(k * b_step), idesc,
+                     (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when the MMAs above retire
+          if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if ((acc ^= 1) == 0) acc_phase ^= 1;
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int half = ew >> 2;      // which half of the tile's columns
+    constexpr int COLS_PER_WARP = BLOCK_N / 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int tile = w / n_splits;
+      const int m0 = (tile % tiles_m) * BLOCK_M;
+      const int n0 = (tile / tiles_m) * BLOCK_N;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = m0 + quarter * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < COLS_PER_WARP; c += 32) {
+        const int col_in_tile = half * COLS_PER_WARP + c;
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * Cfg::ACC_STRIDE + col_in_tile, v);
+        tmem_ld_wait();
+        epilogue_chunk(p, v, row, n0 + col_in_tile);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if ((acc ^= 1) == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess) return nullptr;
+  if (qres != cudaDriverEntryPointSuccess) return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  return fn;
+}
+
+// rows x cols bf16 matrix, cols contiguous, leading dimension ld (elements); box = box_cols x box_rows
+static int make_tmap(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int box_cols,
+                     int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return B200_ERR_DRIVER;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? B200_OK : B200_ERR_DRIVER;
+}
+
+static int g_num_sms = 0;
+
+template <int BLOCK_N>
+static int launch_gemm(const b200_gemm_args* a, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!a->a_mn) rc = make_tmap(&tmA, a->A, a->M, a->K, a->lda, BLOCK_K, BLOCK_M);
+  else rc = make_tmap(&tmA, a->A, a->K, a->M, a->lda, 64, BLOCK_K);
+  if (rc) return rc;
+  if (!a->b_mn) rc = make_tmap(&tmB, a->B, a->N, a->K, a->ldb, BLOCK_K, BLOCK_N);
+  else rc = make_tmap(&tmB, a->B, a->K, a->N, a->ldb, 64, BLOCK_K);
+  if (rc) return rc;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             Cfg::SMEM_BYTES) != cudaSuccess)
+      return B200_ERR_CUDA;
+    attr_set = true;
+  }
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  GemmDev p;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.a_mn = a->a_mn; p.b_mn = a->b_mn;
+  p.splits = a->splits < 1 ? 1 : a->splits;
+  p.epi = a->epi;
+  p.alpha = a->alpha;
+  p.C = a->C; p.ldc = a->ldc;
+  p.C2 = a->C2; p.ldc2 = a->ldc2;
+  p.aux = a->aux; p.ldaux = a->ldaux;
+  p.bias = a->bias; p.gamma = a->gamma;
+  p.rowscale = a->rowscale; p.rows_per_scale = a->rows_per_scale > 0 ? a->rows_per_scale : 1;
+
+  const int tiles = ((a->M + BLOCK_M - 1) / BLOCK_M) * ((a->N + BLOCK_N - 1) / BLOCK_N);
+  const int kb_total = (a->K + BLOCK_K - 1) / BLOCK_K;
+  int splits = p.splits > kb_total ? kb_total : p.splits;
+  p.splits = splits;
+  long long work = (long long)tiles * splits;
+  int grid = (int)(work < g_num_sms ? work : g_num_sms);
+  if (grid < 1) grid = 1;
+  gemm_tcgen05_kernel<BLOCK_N><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+}  // namespace b200
+
+extern "C" int b200_gemm(const b200_gemm_args* a, void* stream) {
+  using namespace b200;
+  if (!a || !a->A || !a->B || !a->C) return B200_ERR_INVALID_ARG;
+  if (a->M <= 0 || a->N <= 0 || a->K <= 0) return B200_ERR_INVALID_ARG;
+  // TMA: 16-byte aligned bases and row pitches; vectorised epilogue: N, ldc multiples of 8
+  if ((a->lda % 8) || (a->ldb % 8) || (a->N % 8) || (a->ldc % 8)) return B200_ERR_UNSUPPORTED;
+  if (((uintptr_t)a->A & 15) || ((uintptr_t)a->B & 15) || ((uintptr_t)a->C & 15)) return B200_ERR_UNSUPPORTED;
+  if (a->epi < 0 || a->epi > B200_EPI_DGELU) return B200_ERR_INVALID_ARG;
+  if (a->splits > 1 && a->epi != B200_EPI_F32_ATOMIC) return B200_ERR_INVALID_ARG;
+  if ((a->epi == B200_EPI_RESIDUAL || a->epi == B200_EPI_DGELU) && (!a->aux || (a->ldaux % 8))) return B200_ERR_INVALID_ARG;
+  if (a->C2 && (a->ldc2 % 8)) return B200_ERR_UNSUPPORTED;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int bn = a->block_n;
+  if (bn == 0) {
+    // tile-N heuristic: minimise padded columns, prefer wider tiles (fewer smem bytes per MMA)
+    const int cand[3] = {256, 192, 128};
+    long long best = -1;
+    for (int i = 0; i < 3; ++i) {
+      long long padded = (long long)((a->N + cand[i] - 1) / cand[i]) * cand[i];
+      if (best < 0 || padded < best) { best = padded; bn = cand[i]; }
+    }
+  }
+  switch (bn) {
+    case 128: return launch_gemm<128>(a, s);
+    case 192: return launch_gemm<192>(a, s);
+    case 256: return launch_gemm<256>(a, s);
+    default: return B200_ERR_INVALID_ARG;
+  }
+}
