@@ -1,0 +1,143 @@
+"""Pin the CPU oracle (oracle/dinov2_oracle.py) against
+  (a) the known-answer values of the reference's own tests, and
+  (b) fixtures produced by the reference's own modules (tools/make_golden.py -> tests/golden/*.pt).
+CPU only; bit-level agreement is not expected (different op order), tolerances are fp32-level.
+"""
+import json
+
+import pytest
+import torch
+
+from oracle import dinov2_oracle as O
+from tests.golden import recipes as R
+
+
+def _close(a, b, rtol=1e-4, atol=1e-5):
+    torch.testing.assert_close(a, b, rtol=rtol, atol=atol)
+
+
+def test_reference_known_answers(golden_dir):
+    """tests/_methods/dinov2/test_dinov2_loss.py:84-103,:179-211,:63-82; tests/test__torch_helpers.py:38-50."""
+    kat = json.loads((golden_dir / "ref_kats.json").read_text())
+    assert kat["dino_forward"] == pytest.approx(1.5565, rel=1e-4)       # the reference test's own constant
+    assert kat["ibot_forward_masked"] == pytest.approx(0.4057, rel=1e-4)
+    t = torch.tensor([[0.1, 0.2], [0.3, 0.4], [0.5, 0.6]])
+    s = torch.tensor([[0.7, 0.8], [0.9, 1.0], [1.1, 1.2]])
+    center = torch.zeros(1, 2)
+    p = O.softmax_center_teacher(t, center, 0.04)
+    loss = O.dino_loss([s, s], [p, p], student_temp=0.1)
+    assert float(loss) == pytest.approx(1.5565, rel=1e-4)
+    assert float(loss) == pytest.approx(kat["dino_forward"], rel=1e-6)
+    c = O.center_ema(center, O.center_batch_sum_dino(t), 3, 0.9)
+    _close(c.flatten(), torch.tensor(kat["dino_center_after"]))
+
+    mask = torch.tensor([[True, False, True, False], [False, False, False, True], [False, False, False, False]])
+    p = O.softmax_center_teacher(t.unsqueeze(0), torch.zeros(1, 1, 2), 0.1).squeeze(0)
+    w = O.masks_weight_from_masks(mask)
+    li = O.ibot_loss_masked(s, p, w, n_images=mask.shape[0], student_temp=0.2)
+    assert float(li) == pytest.approx(0.4057, rel=1e-4)
+    assert float(li) == pytest.approx(kat["ibot_forward_masked"], rel=1e-6)
+
+    c2 = O.center_ema(torch.zeros(1, 2), O.center_batch_sum_dino(torch.ones(4, 2) * 2), 4, 0.9)
+    _close(c2.flatten(), torch.tensor([0.2, 0.2]))
+
+    a = torch.tensor([[3.0, 4.0], [5.0, 6.0]])
+    e = torch.tensor([[1.0, 2.0], [3.0, 4.0]])
+    O.update_ema([a], [e], 0.25)
+    assert torch.equal(e, torch.tensor([[2.5, 3.5], [4.5, 5.5]]))
+    assert torch.equal(e, torch.tensor(kat["ema"]))
+    got = [O.linear_warmup_schedule(s_, 37500, 0.04, 0.07) for s_ in (0, 100, 37500, 50000)]
+    assert got == pytest.approx(kat["linear_warmup"])
+
+
+def test_softmax_and_sinkhorn_rows_sum_to_one():
+    """tests/_methods/dinov2/test_dinov2_loss.py:26-61,:108-154."""
+    t = torch.randn(4, 2)
+    assert torch.allclose(O.softmax_center_teacher(t, torch.zeros(1, 2), 0.04).sum(-1), torch.ones(4))
+    assert torch.allclose(O.sinkhorn_knopp(t, 0.04, 4.0, n_iterations=4).sum(-1), torch.ones(4))
+    assert torch.allclose(O.sinkhorn_knopp(t, 0.04, 3.0).sum(-1), torch.ones(4))
+
+
+def test_vit_forward_matches_reference(golden_dir):
+    ref = torch.load(golden_dir / "vit_tiny.pt")
+    cfg = R.VIT_TINY
+    sd = R.det_vit_state(cfg, seed=11)
+    xg, xl, masks = R.vit_case_inputs()
+    g = O.vit_forward_features(sd, cfg, xg, masks)
+    _close(g["cls"], ref["g_cls"], rtol=1e-4, atol=2e-5)
+    _close(g["patch"], ref["g_patch"], rtol=1e-4, atol=2e-5)
+    _close(g["prenorm"], ref["g_prenorm"], rtol=1e-4, atol=2e-5)
+    _close(O.vit_forward_features(sd, cfg, xg, None)["cls"], ref["g_nomask_cls"], rtol=1e-4, atol=2e-5)
+    l = O.vit_forward_features(sd, cfg, xl, None)
+    _close(l["cls"], ref["l_cls"], rtol=1e-4, atol=2e-5)
+    _close(l["patch"], ref["l_patch"], rtol=1e-4, atol=2e-5)
+    _close(O.interpolate_pos_encoding(sd, cfg, 36, 96, 96), ref["pos_embed_96"])
+
+
+def test_vit_register_tokens_antialias_matches_reference(golden_dir):
+    ref = torch.load(golden_dir / "vit_tiny_reg.pt")
+    cfg = R.VIT_TINY_REG
+    sd = R.det_vit_state(cfg, seed=12)
+    xg, xl, masks = R.vit_case_inputs()
+    _close(O.vit_forward_features(sd, cfg, xl, None)["cls"], ref["l_cls"], rtol=1e-4, atol=2e-5)
+    g = O.vit_forward_features(sd, cfg, xg, masks)
+    _close(g["cls"], ref["g_cls"], rtol=1e-4, atol=2e-5)
+    _close(g["patch"], ref["g_patch"], rtol=1e-4, atol=2e-5)
+
+
+def test_head_forward_backward_matches_reference(golden_dir):
+    ref = torch.load(golden_dir / "head_tiny.pt")
+    sd = {k: v.clone().requires_grad_(True) for k, v in R.det_head_state(R.HEAD_TINY, seed=21).items()}
+    x = R.head_case_input().requires_grad_(True)
+    y = O.head_forward(sd, x)
+    _close(y, ref["logits"], rtol=1e-4, atol=1e-6)
+    (y * R.head_case_cotangent()).sum().backward()
+    _close(x.grad, ref["dx"], rtol=1e-3, atol=1e-6)
+    for k, p in sd.items():
+        _close(p.grad, ref["grad." + k], rtol=1e-3, atol=1e-6)
+
+
+def test_losses_match_reference(golden_dir):
+    ref = torch.load(golden_dir / "loss_case.pt")
+    B = ref["t_cls"].shape[0] // 2
+    p_cls = O.softmax_center_teacher(ref["t_cls"], ref["center_dino"], 0.05)
+    p_patch = O.softmax_center_teacher(ref["t_patch"].unsqueeze(0), ref["center_ibot"], 0.05).squeeze(0)
+    _close(p_cls, ref["p_cls"]); _close(p_patch, ref["p_patch"])
+    _close(O.dino_loss([ref["s_g"]], [p_cls]), ref["loss_global"])
+    _close(O.dino_loss(ref["s_l"].chunk(4), list(p_cls.view(2, B, -1))), ref["loss_local"])
+    _close(O.ibot_loss_masked(ref["s_patch"], p_patch, ref["w"], n_images=2 * B), ref["loss_ibot"])
+    c = O.center_ema(ref["center_dino"], O.center_batch_sum_dino(ref["t_cls"]), 2 * B, 0.9)
+    _close(c, ref["center_dino_after"])
+    c = O.center_ema(ref["center_ibot"], O.center_batch_sum_ibot(ref["t_patch"].unsqueeze(0)), 1, 0.9)
+    _close(c, ref["center_ibot_after"])
+    _close(O.sinkhorn_knopp(ref["t_cls"], 0.05, float(2 * B)), ref["sk_cls"], rtol=1e-4, atol=1e-8)
+    _close(O.sinkhorn_knopp(ref["t_patch"], 0.05, float(ref["t_patch"].shape[0])), ref["sk_patch"], rtol=1e-4, atol=1e-8)
+
+
+@pytest.mark.parametrize("center_method,separate", [("softmax", False), ("sinkhorn_knopp", True)])
+def test_training_step_matches_reference(golden_dir, center_method, separate):
+    ref = torch.load(golden_dir / f"step_{center_method}_{'sep' if separate else 'shared'}.pt")
+    cfg = R.step_config(center_method, separate)
+    st = R.det_step_state(cfg, seed=41)
+    student = {k: v.clone().requires_grad_(True) for k, v in st["student"].items()}
+    views, masks, idx, w = R.step_case_inputs(cfg)
+    taps = {}
+    out = O.training_step(cfg, student, st["teacher"], st["centers"], views, masks, idx, w, teacher_temp=0.05, taps=taps)
+    for k in ("loss", "dino_global_loss", "dino_local_loss", "ibot_loss", "koleo_loss"):
+        _close(out[k], ref[k], rtol=1e-5, atol=1e-6)
+    _close(taps["t_cls_logits"], ref["t_cls_logits"], rtol=1e-4, atol=1e-5)
+    _close(taps["t_patch_logits"], ref["t_patch_logits"], rtol=1e-4, atol=1e-5)
+    _close(taps["s_cls_logits_g"], ref["s_cls_logits_g"], rtol=1e-4, atol=1e-5)
+    _close(taps["s_patch_logits"], ref["s_patch_logits"], rtol=1e-4, atol=1e-5)
+    out["loss"].backward()
+    worst = 0.0
+    for k, p in student.items():
+        gref = ref["grad." + k]
+        g = p.grad if p.grad is not None else torch.zeros_like(p)
+        denom = gref.abs().max().item() + 1e-8
+        worst = max(worst, (g - gref).abs().max().item() / denom)
+    assert worst < 2e-3, worst
+    if center_method == "softmax":
+        B2 = views[0].shape[0] * 2
+        _close(O.center_ema(st["centers"]["dino"], out["dino_center_sum"], B2, 0.9), ref["center_dino_after"])
+        _close(O.center_ema(st["centers"]["ibot"], out["ibot_center_sum"], 1, 0.9), ref["center_ibot_after"])
