@@ -66,6 +66,119 @@ typedef struct b200_gemm_args {
 
 int b200_gemm(const b200_gemm_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Attention core for short sequences (head_dim 64), forward and backward.
+ * Replaces LT/_models/dinov2_vit/dinov2_vit_src/layers/attention.py:55-63 (q*scale @ k^T, softmax, @ v) and
+ * its autograd backward.  qkv: bf16 [B, N, 3, h, 64] with token pitch ld_tok; out/dout: bf16 [B, N, h*64]
+ * with token pitch ld_out; lse: f32 [B*h, N] (log-sum-exp of the scaled, bf16-rounded scores).
+ * dqkv has the layout of qkv (token pitch ld_dtok).  N <= 272.
+ */
+int b200_attention_fwd(const void* qkv, long long ld_tok, int B, int N, int h, int head_dim, float scale,
+                       void* out, long long ld_out, float* lse, void* stream);
+int b200_attention_bwd(const void* qkv, long long ld_tok, const void* out, const void* dout, long long ld_out,
+                       const float* lse, int B, int N, int h, int head_dim, float scale, void* dqkv,
+                       long long ld_dtok, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Row-wise kernels around the GEMMs.
+ */
+/* nn.LayerNorm(eps) forward (vision_transformer.py:138,377; block.py:92,95). x f32 [T,D] -> y bf16|f32. */
+int b200_layernorm_fwd(const float* x, long long ldx, int T, int D, const float* w, const float* b, float eps,
+                       void* y, long long ldy, int out_bf16, float* mean, float* rstd, void* stream);
+/* LayerNorm backward: dx (+)= LN'(dy); dw/db += column sums (may be NULL). dy bf16|f32. */
+int b200_layernorm_bwd(const void* dy, long long lddy, int dy_bf16, const float* x, long long ldx, int T, int D,
+                       const float* w, const float* mean, const float* rstd, float* dx, long long lddx,
+                       int accumulate, float* dw, float* db, void* stream);
+/* im2col for PatchEmbed.proj = Conv2d(k=s=p) (patch_embed.py:77-79,108): x f32 [B,C,H,W] -> bf16 [B*Np, C*p*p]. */
+int b200_im2col(const float* x, int B, int C, int H, int W, int p, void* cols, long long ldc, void* stream);
+/* prepare_tokens_with_masks (vision_transformer.py:307-329): mask-token select, cls/register concat, +pos. */
+int b200_assemble_tokens(const void* tok, long long ldt, const unsigned char* masks, const float* mask_token,
+                         const float* cls, const float* reg, const float* pos, int B, int Np, int R, int D,
+                         float* x, void* stream);
+int b200_assemble_tokens_bwd(const float* dx, const unsigned char* masks, int B, int Np, int R, int D, void* dtok,
+                             long long lddt, float* dpos, float* dcls, float* dreg, float* dmask_token,
+                             void* stream);
+/* LayerScale (+DropPath) backward (layer_scale.py:27-28, block.py:109-114): do = bf16(dx*rowscale*gamma),
+ * dgamma += sum dx*rowscale*o, dbias += sum do. */
+int b200_layerscale_bwd(const float* dx, long long lddx, const void* o, long long ldo, const float* gamma,
+                        const float* rowscale, int rows_per_scale, int T, int D, void* dout, long long lddo,
+                        float* dgamma, float* dbias, void* stream);
+/* torch.index_select of token rows (dinov2.py:427-431,496-500) and its backward (scatter).
+ * Row index = Np>0 ? (idx/Np)*N + off + idx%Np : idx. */
+int b200_gather_rows(const float* src, long long lds, const long long* idx, int M, int D, int Np, int N, int off,
+                     void* out, long long ldo, int out_bf16, void* stream);
+int b200_scatter_rows(const void* in, long long ldi, int in_bf16, const long long* idx, int M, int D, int Np,
+                      int N, int off, float* dst, long long ldd, int accumulate, void* stream);
+/* F.normalize(p=2, eps) on bf16 rows (dinov2_head.py:68-69) and backward. */
+int b200_l2norm_fwd(const void* x, long long ldx, int R, int D, float eps, void* y, long long ldy, float* nrm,
+                    void* stream);
+int b200_l2norm_bwd(const void* dy, long long lddy, const void* x, long long ldx, const float* nrm, int R, int D,
+                    void* dx, long long lddx, void* stream);
+/* parametrizations.weight_norm (dinov2_head.py:54-58): w bf16 [O,I] = g*v/||v||; backward dg, dv +=. */
+int b200_weightnorm_fwd(const float* g, const float* v, int O, int I, void* w, float* vnorm, void* stream);
+int b200_weightnorm_bwd(const float* dW, const float* g, const float* v, int O, int I, float* dg, float* dv,
+                        void* stream);
+/* tiny fp32 matmul C (+)= op(A) * B, B row-major [K,N]; positional-embedding resampling operator
+ * (interpolate_pos_encoding, vision_transformer.py:251-305, as a fixed linear map and its transpose). */
+int b200_small_matmul(const float* A, long long lda, int a_trans, const float* B, long long ldb, int M, int N,
+                      int K, float* C, long long ldc, int accumulate, void* stream);
+int b200_cast_bf16(const float* x, void* y, long long n, void* stream);
+int b200_fill_f32(float* x, long long n, float v, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * DINO / iBOT loss path (LT/_methods/dinov2/dinov2_loss.py). Teacher probabilities are represented as
+ *   p[b,k] = exp(t[b,k]*t_scale + colterm[k] + rowterm[b])   and never materialised.
+ */
+/* rowterm[r] = -logsumexp_k(x[r,k]*scale + colterm[k]); x bf16 [R,K]. (softmax_center_teacher :76-82,
+ * last column normalisation of sinkhorn_knopp_teacher :109-113) */
+int b200_row_lse(const void* x, long long ld, int R, int K, const float* colterm, float scale, float* rowterm,
+                 void* stream);
+/* out[k] += sum_r x[r,k]*rowvec[r] (mode 0; center batch sums :135-145, bias grads) or
+ * out[k] += sum_r exp(x[r,k]*scale + rowvec[r]) (mode 1; Sinkhorn prototype sums :100-104). */
+int b200_col_reduce(const void* x, long long ld, int R, int K, const float* rowvec, float scale, int mode,
+                    float* out, void* stream);
+/* K-vector helpers: op0 y=a*x+b*y (center EMA :148-160), op1 y=-a*x (colterm from center),
+ * op2 y=-log(x)-a (Sinkhorn log-scaling). */
+int b200_vec_op(float* y, const float* x, int n, float a, float b, int op, void* stream);
+/* Fused CE forward+backward, one student row per CTA (DINOLoss.forward :117-133, forward_masked :246-268):
+ * loss_rows[r] = w*(n_t*LSE_s - s_scale*sum_k p_t[k]*s[k]); ds = w*s_scale*(n_t*softmax_s - p_t)*gscale. */
+int b200_dino_ce(const void* s, long long lds, int Rs, int K, const void* t, long long ldt, const float* colterm,
+                 const float* t_rowterm, const int* t_idx0, const int* t_idx1, const float* weight,
+                 float s_scale, float t_scale, float gscale, float* loss_rows, void* ds, long long ldds,
+                 void* stream);
+int b200_segment_sum(const float* x, const int* offsets, int n_segments, const float* scale, float* out,
+                     void* stream);
+/* KoLeoLoss forward+backward (lightly.loss.KoLeoLoss; call site dinov2.py:377-380), `groups` independent
+ * sets of n rows. dx += gscale * dloss/dx. */
+int b200_koleo(const float* x, long long ldx, int groups, int n, int D, float eps, int bf16_sim, float gscale,
+               float* loss_out, float* dx, long long lddx, int* nn_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Parameter sweeps over flat fp32 arenas.
+ */
+/* update_momentum (LT/_torch_helpers.py:75-96): teacher = teacher*m + student*(1-m), in place. */
+int b200_ema(float* teacher, const float* student, long long n, float m, void* teacher_bf16, void* stream);
+int b200_sumsq(const float* x, long long n, float* out, void* stream);
+
+typedef struct b200_adamw_args {
+  float* p; const float* g; float* m; float* v;
+  float* t;                   /* teacher (EMA) arena or NULL                                         */
+  void* p_bf16; void* t_bf16; /* optional bf16 shadows refreshed in the same pass                    */
+  long long n; int chunk;     /* hyper-parameters are constant per `chunk` elements                  */
+  const float* lr_scale;      /* [n/chunk] layer-wise lr decay * patch-embed multiplier              */
+  const float* wd_scale;      /* [n/chunk] 1 = decayed, 0 = bias/norm/gamma                          */
+  const unsigned char* flags; /* [n/chunk] bit0 last_layer, bit1 backbone                            */
+  float lr, wd, beta1, beta2, eps;
+  int step;                   /* 1-based                                                             */
+  float ema_m;
+  const float* gradnorm_sq;   /* device scalar (sum of squares of g) or NULL = no clipping           */
+  float max_norm;
+  float grad_scale;           /* multiplies g (e.g. 1/world_size)                                    */
+  int freeze_last_layer, freeze_backbone;
+} b200_adamw_args;
+/* clip_grad_norm_ + AdamW.step + update_momentum in one sweep (dinov2.py:588-660, utils.py:191-273). */
+int b200_adamw_ema(const b200_adamw_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,373 @@
+// DINO / iBOT loss path: teacher centering (softmax or Sinkhorn-Knopp), student cross-entropy forward +
+// analytic backward, KoLeo regulariser.  HBM-bound kernels: every logit is read from HBM once.
+//
+// Reference arithmetic replaced (LT = src/lightly_train):
+//   LT/_methods/dinov2/dinov2_loss.py:76-82,178-186   softmax_center_teacher
+//   LT/_methods/dinov2/dinov2_loss.py:84-115,188-224  sinkhorn_knopp_teacher
+//   LT/_methods/dinov2/dinov2_loss.py:117-133         DINOLoss.forward
+//   LT/_methods/dinov2/dinov2_loss.py:246-268,55-56   IBOTPatchLoss.forward_masked / lossfunc
+//   LT/_methods/dinov2/dinov2_loss.py:135-160,270-297 center update
+//   lightly.loss.KoLeoLoss (call site LT/_methods/dinov2/dinov2.py:377-380)
+//
+// Representation: teacher probabilities are never materialised.  For both centering methods
+//     p[b,k] = exp(t[b,k]*t_scale + colterm[k] + rowterm[b])
+//   softmax-centering: colterm = -center*t_scale,           rowterm = -LSE_k(t*t_scale + colterm)
+//   Sinkhorn-Knopp   : colterm = log u (3 scaling iters),    rowterm = -LSE_k(t*t_scale + colterm)
+// (Sinkhorn is a diagonal scaling Q = diag(u) E diag(v); the last column normalisation *is* the softmax
+//  normalisation, so both methods share the CE kernel.)
+#include "common.cuh"
+#include "../../include/b200dino.h"
+
+namespace b200 {
+
+static constexpr int LOSS_THREADS = 512;
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ void load8f(const float* p, float (&f)[8]) {
+  float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// Online (max, sum-exp) merge helpers
+struct MaxSum {
+  float m, s;
+};
+__device__ __forceinline__ MaxSum ms_merge(MaxSum a, MaxSum b) {
+  float m = fmaxf(a.m, b.m);
+  if (m == -INFINITY) return {m, 0.f};
+  return {m, a.s * __expf(a.m - m) + b.s * __expf(b.m - m)};
+}
+__device__ __forceinline__ MaxSum block_maxsum(MaxSum v, MaxSum* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    MaxSum w{__shfl_xor_sync(0xffffffffu, v.m, o), __shfl_xor_sync(0xffffffffu, v.s, o)};
+    v = ms_merge(v, w);
+  }
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  MaxSum r = (lane < nw) ? red[lane] : MaxSum{-INFINITY, 0.f};
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    MaxSum w{__shfl_xor_sync(0xffffffffu, r.m, o), __shfl_xor_sync(0xffffffffu, r.s, o)};
+    r = ms_merge(r, w);
+  }
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// rowterm[r] = -LSE_k( x[r,k]*scale + colterm[k] )      one CTA per row
+__global__ void __launch_bounds__(LOSS_THREADS) row_lse_kernel(const __nv_bfloat16* __restrict__ x, long long ld,
+                                                                int R, int K, const float* __restrict__ colterm,
+                                                                float scale, float* __restrict__ rowterm) {
+  __shared__ MaxSum red[32];
+  const int r = blockIdx.x;
+  const __nv_bfloat16* xr = x + (size_t)r * ld;
+  MaxSum acc{-INFINITY, 0.f};
+  for (int k = threadIdx.x * 8; k < K; k += blockDim.x * 8) {
+    float v[8], c[8];
+    load8(xr + k, v);
+    if (colterm) load8f(colterm + k, c);
+    float z[8];
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      z[i] = v[i] * scale + (colterm ? c[i] : 0.f);
+      m = fmaxf(m, z[i]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += __expf(z[i] - m);
+    acc = ms_merge(acc, MaxSum{m, s});
+  }
+  MaxSum t = block_maxsum(acc, red);
+  if (threadIdx.x == 0) rowterm[r] = -(t.m + __logf(t.s));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Column reductions over rows.  mode 0: out[k] += sum_r x[r,k] * rowweight[r]   (rowweight NULL -> 1)
+//                               mode 1: out[k] += sum_r exp(x[r,k]*scale + rowterm[r])
+// grid = (ceil(K / (256*8)), row_splits); each thread owns 8 columns; atomicAdd at the end.
+__global__ void __launch_bounds__(256) col_reduce_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int R, int K,
+                                                         const float* __restrict__ rowvec, float scale, int mode,
+                                                         float* __restrict__ out) {
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (k >= K) return;
+  const int rows_per = (R + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per;
+  const int r1 = min(R, r0 + rows_per);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int r = r0; r < r1; ++r) {
+    float v[8];
+    load8(x + (size_t)r * ld + k, v);
+    if (mode == 0) {
+      const float w = rowvec ? __ldg(rowvec + r) : 1.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v[i] * w;
+    } else {
+      const float rt = rowvec ? __ldg(rowvec + r) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += __expf(v[i] * scale + rt);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) atomicAdd(out + k + i, acc[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Small vector helpers for the centering state (K-length fp32 vectors).
+// op 0: y = a*x + b*y          (center EMA: center = center*m + mean*(1-m))
+// op 1: y = -a * x             (colterm = -center * t_scale)
+// op 2: y = -log(x) - a        (Sinkhorn: log u = -log(sum) - log K)
+__global__ void vec_op_kernel(float* __restrict__ y, const float* __restrict__ x, int n, float a, float b, int op) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (op == 0) y[i] = a * x[i] + b * y[i];
+  else if (op == 1) y[i] = -a * x[i];
+  else y[i] = -__logf(x[i]) - a;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused cross-entropy forward + backward, one CTA per student row.
+//   n_t   = number of paired teacher rows (1 or 2)
+//   loss  = w * ( n_t * LSE_s - s_scale * sum_k p_t[k] * s[k] )
+//   dS[k] = w * s_scale * ( n_t * softmax_s[k] - p_t[k] ) * gscale     (bf16, optional)
+// Pass 1 streams the student row (HBM) for (max,sum); pass 2 re-reads it (L2-resident: 128 KB/row),
+// streams the teacher row(s) once and writes the gradient row once.
+__global__ void __launch_bounds__(LOSS_THREADS)
+dino_ce_kernel(const __nv_bfloat16* __restrict__ s, long long lds, int Rs, int K, const __nv_bfloat16* __restrict__ t,
+               long long ldt, const float* __restrict__ colterm, const float* __restrict__ t_rowterm,
+               const int* __restrict__ t_idx0, const int* __restrict__ t_idx1, const float* __restrict__ weight,
+               float s_scale, float t_scale, float gscale, float* __restrict__ loss_rows, __nv_bfloat16* __restrict__ ds,
+               long long ldds) {
+  __shared__ MaxSum red[32];
+  __shared__ float redf[32];
+  const int r = blockIdx.x;
+  const float w = weight ? __ldg(weight + r) : 1.f;
+  const int i0 = t_idx0[r];
+  const int i1 = t_idx1 ? t_idx1[r] : -1;
+  const float n_t = (i1 >= 0) ? 2.f : 1.f;
+  const __nv_bfloat16* sr = s + (size_t)r * lds;
+  const __nv_bfloat16* t0 = t + (size_t)i0 * ldt;
+  const __nv_bfloat16* t1 = (i1 >= 0) ? t + (size_t)i1 * ldt : nullptr;
+  const float rt0 = __ldg(t_rowterm + i0);
+  const float rt1 = (i1 >= 0) ? __ldg(t_rowterm + i1) : 0.f;
+
+  // pass 1: student log-sum-exp
+  MaxSum acc{-INFINITY, 0.f};
+  for (int k = threadIdx.x * 8; k < K; k += blockDim.x * 8) {
+    float v[8];
+    load8(sr + k, v);
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[i] *= s_scale; m = fmaxf(m, v[i]); }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += __expf(v[i] - m);
+    acc = ms_merge(acc, MaxSum{m, sum});
+  }
+  MaxSum st = block_maxsum(acc, red);
+  const float lse = st.m + __logf(st.s);
+
+  // pass 2: dot(p_t, s) and gradient
+  float dot = 0.f;
+  const float gw = w * s_scale * gscale;
+  for (int k = threadIdx.x * 8; k < K; k += blockDim.x * 8) {
+    float sv[8], tv[8], c[8], p[8];
+    load8(sr + k, sv);
+    load8(t0 + k, tv);
+    if (colterm) load8f(colterm + k, c);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (!colterm) c[i] = 0.f;
+      p[i] = __expf(tv[i] * t_scale + c[i] + rt0);
+    }
+    if (t1) {
+      load8(t1 + k, tv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) p[i] += __expf(tv[i] * t_scale + c[i] + rt1);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dot += p[i] * sv[i];
+    if (ds) {
+      float g[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = gw * (n_t * __expf(sv[i] * s_scale - lse) - p[i]);
+      uint4 o;
+      o.x = pack_bf16x2(g[0], g[1]); o.y = pack_bf16x2(g[2], g[3]);
+      o.z = pack_bf16x2(g[4], g[5]); o.w = pack_bf16x2(g[6], g[7]);
+      *reinterpret_cast<uint4*>(ds + (size_t)r * ldds + k) = o;
+    }
+  }
+  dot = block_sum(dot, redf);
+  if (threadIdx.x == 0) loss_rows[r] = w * (n_t * lse - s_scale * dot);
+}
+
+// ------------------------------------------------------------------------------------------------
+// out[j] = sum_{i in segment j} x[i];  segments given by offsets[j]..offsets[j+1]. One CTA per segment,
+// fixed summation order (deterministic).
+__global__ void __launch_bounds__(256) segment_sum_kernel(const float* __restrict__ x, const int* __restrict__ offsets,
+                                                          float* __restrict__ out, const float* __restrict__ scale) {
+  __shared__ float red[32];
+  const int j = blockIdx.x;
+  const int a = offsets[j], b = offsets[j + 1];
+  float acc = 0.f;
+  for (int i = a + threadIdx.x; i < b; i += blockDim.x) acc += x[i];
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) out[j] = acc * (scale ? scale[j] : 1.f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// KoLeo forward + backward for one group of n <= 256 rows of dimension D (single CTA per group).
+//   xn = x / max(||x||, eps); sim = round_bf16?(xn xn^T), diag = -2; j(i) = argmax_k sim[i,k] (first index)
+//   d_i = || xn_i - xn_j + eps ||_2 ; loss = -(1/n) sum_i log(d_i + eps)
+// dx (fp32, accumulated with +=) = gscale * dloss/dx, argmax treated as constant (as autograd does).
+__global__ void __launch_bounds__(256) koleo_kernel(const float* __restrict__ x, long long ldx, int n, int D, float eps,
+                                                    int bf16_sim, float gscale, float* __restrict__ loss_out,
+                                                    float* __restrict__ dx, long long lddx, int* __restrict__ nn_out) {
+  extern __shared__ float sm[];
+  float* xn = sm;                        // [n, D]
+  float* gxn = xn + (size_t)n * D;       // [n, D] grad wrt xn
+  float* nrm = gxn + (size_t)n * D;      // [n]
+  int* nn = reinterpret_cast<int*>(nrm + n);  // [n]
+  float* dist = reinterpret_cast<float*>(nn + n);  // [n]
+  const int g = blockIdx.x;
+  x += (size_t)g * n * ldx;
+  if (dx) dx += (size_t)g * n * lddx;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+
+  for (int i = warp; i < n; i += nwarps) {
+    float ss = 0.f;
+    for (int d = lane; d < D; d += 32) { float v = x[(size_t)i * ldx + d]; ss += v * v; }
+    ss = warp_sum(ss);
+    float nr = fmaxf(sqrtf(ss), eps);
+    if (lane == 0) nrm[i] = nr;
+    for (int d = lane; d < D; d += 32) { xn[i * D + d] = x[(size_t)i * ldx + d] / nr; gxn[i * D + d] = 0.f; }
+  }
+  __syncthreads();
+  // nearest neighbour (one warp per row i)
+  for (int i = warp; i < n; i += nwarps) {
+    float best = -INFINITY; int bi = 0;
+    for (int k = 0; k < n; ++k) {
+      float dot = 0.f;
+      if (bf16_sim) {
+        for (int d = lane; d < D; d += 32) dot += bf16_round(xn[i * D + d]) * bf16_round(xn[k * D + d]);
+      } else {
+        for (int d = lane; d < D; d += 32) dot += xn[i * D + d] * xn[k * D + d];
+      }
+      dot = warp_sum(dot);
+      if (bf16_sim) dot = bf16_round(dot);
+      if (k == i) dot = -2.f;
+      if (dot > best) { best = dot; bi = k; }
+    }
+    float ss = 0.f;
+    for (int d = lane; d < D; d += 32) { float df = xn[i * D + d] - xn[bi * D + d] + eps; ss += df * df; }
+    ss = warp_sum(ss);
+    if (lane == 0) { nn[i] = bi; dist[i] = sqrtf(ss); if (nn_out) nn_out[g * n + i] = bi; }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float l = 0.f;
+    for (int i = lane; i < n; i += 32) l += -__logf(dist[i] + eps);
+    l = warp_sum(l);
+    if (lane == 0) loss_out[g] = l / n;
+  }
+  if (!dx) return;
+  // grad wrt xn: i gets +c_i * diff, j(i) gets -c_i * diff, c_i = -(1/n)/(d_i+eps)/d_i ; serial over i per column
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    for (int i = 0; i < n; ++i) {
+      const int j = nn[i];
+      const float di = dist[i];
+      const float c = -(1.f / n) / (di + eps) / fmaxf(di, 1e-30f);
+      const float df = xn[i * D + d] - xn[j * D + d] + eps;
+      gxn[i * D + d] += c * df;
+      gxn[j * D + d] -= c * df;
+    }
+  }
+  __syncthreads();
+  // through the normalisation: dx = (g - xn * <xn, g>) / max(||x||, eps)
+  for (int i = warp; i < n; i += nwarps) {
+    float dot = 0.f;
+    for (int d = lane; d < D; d += 32) dot += xn[i * D + d] * gxn[i * D + d];
+    dot = warp_sum(dot);
+    for (int d = lane; d < D; d += 32)
+      dx[(size_t)i * lddx + d] += gscale * (gxn[i * D + d] - xn[i * D + d] * dot) / nrm[i];
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_row_lse(const void* x, long long ld, int R, int K, const float* colterm, float scale,
+                            float* rowterm, void* stream) {
+  if (!x || !rowterm || R <= 0 || K <= 0 || (K % 8) || (ld % 8)) return B200_ERR_INVALID_ARG;
+  row_lse_kernel<<<R, LOSS_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ld, R, K, colterm, scale, rowterm);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+extern "C" int b200_col_reduce(const void* x, long long ld, int R, int K, const float* rowvec, float scale, int mode,
+                               float* out, void* stream) {
+  if (!x || !out || R <= 0 || K <= 0 || (K % 8) || (ld % 8) || mode < 0 || mode > 1) return B200_ERR_INVALID_ARG;
+  dim3 grid((K / 8 + 255) / 256, 1);
+  int target = 148 * 4;
+  int splits = (target + grid.x - 1) / grid.x;
+  if (splits > R) splits = R;
+  if (splits < 1) splits = 1;
+  grid.y = splits;
+  col_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ld, R, K, rowvec, scale, mode, out);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+extern "C" int b200_vec_op(float* y, const float* x, int n, float a, float b, int op, void* stream) {
+  if (!y || !x || n <= 0 || op < 0 || op > 2) return B200_ERR_INVALID_ARG;
+  vec_op_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(y, x, n, a, b, op);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+extern "C" int b200_dino_ce(const void* s, long long lds, int Rs, int K, const void* t, long long ldt,
+                            const float* colterm, const float* t_rowterm, const int* t_idx0, const int* t_idx1,
+                            const float* weight, float s_scale, float t_scale, float gscale, float* loss_rows,
+                            void* ds, long long ldds, void* stream) {
+  if (!s || !t || !t_rowterm || !t_idx0 || !loss_rows || Rs <= 0 || K <= 0) return B200_ERR_INVALID_ARG;
+  if ((K % 8) || (lds % 8) || (ldt % 8) || (ds && (ldds % 8))) return B200_ERR_INVALID_ARG;
+  dino_ce_kernel<<<Rs, LOSS_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)s, lds, Rs, K,
+                                                                 (const __nv_bfloat16*)t, ldt, colterm, t_rowterm, t_idx0,
+                                                                 t_idx1, weight, s_scale, t_scale, gscale, loss_rows,
+                                                                 (__nv_bfloat16*)ds, ldds);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+extern "C" int b200_segment_sum(const float* x, const int* offsets, int n_segments, const float* scale, float* out,
+                                void* stream) {
+  if (!x || !offsets || !out || n_segments <= 0) return B200_ERR_INVALID_ARG;
+  segment_sum_kernel<<<n_segments, 256, 0, (cudaStream_t)stream>>>(x, offsets, out, scale);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+extern "C" int b200_koleo(const float* x, long long ldx, int groups, int n, int D, float eps, int bf16_sim, float gscale,
+                          float* loss_out, float* dx, long long lddx, int* nn_out, void* stream) {
+  if (!x || !loss_out || groups <= 0 || n <= 1 || n > 256 || D <= 0) return B200_ERR_INVALID_ARG;
+  size_t smem = (size_t)(2 * n * D + 3 * n) * sizeof(float);
+  if (smem > 220 * 1024) return B200_ERR_UNSUPPORTED;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(koleo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
+      return B200_ERR_CUDA;
+    attr = true;
+  }
+  koleo_kernel<<<groups, 256, smem, (cudaStream_t)stream>>>(x, ldx, n, D, eps, bf16_sim, gscale, loss_out, dx, lddx, nn_out);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}

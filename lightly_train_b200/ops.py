@@ -66,3 +66,183 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn: bool = Fa
     args.rows_per_scale = rows_per_scale
     check(_lib.lib().b200_gemm(C.byref(args), _stream()), "b200_gemm")
     return out
+
+
+class AdamWArgs(C.Structure):
+    _fields_ = [
+        ("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("t", C.c_void_p),
+        ("p_bf16", C.c_void_p), ("t_bf16", C.c_void_p),
+        ("n", C.c_longlong), ("chunk", C.c_int),
+        ("lr_scale", C.c_void_p), ("wd_scale", C.c_void_p), ("flags", C.c_void_p),
+        ("lr", C.c_float), ("wd", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+        ("step", C.c_int), ("ema_m", C.c_float),
+        ("gradnorm_sq", C.c_void_p), ("max_norm", C.c_float), ("grad_scale", C.c_float),
+        ("freeze_last_layer", C.c_int), ("freeze_backbone", C.c_int),
+    ]
+
+
+def _L():
+    return _lib.lib()
+
+
+def attention_fwd(qkv: torch.Tensor, B: int, N: int, h: int, out: torch.Tensor, lse: torch.Tensor | None,
+                  scale: float) -> None:
+    """qkv bf16 [B*N, 3*h*64]; out bf16 [B*N, h*64]; lse f32 [B*h, N]."""
+    _req_cuda(qkv, out, lse)
+    check(_L().b200_attention_fwd(qkv.data_ptr(), qkv.stride(0), B, N, h, 64, scale, out.data_ptr(), out.stride(0),
+                                  _ptr(lse), _stream()), "b200_attention_fwd")
+
+
+def attention_bwd(qkv, out, dout, lse, B: int, N: int, h: int, dqkv, scale: float) -> None:
+    _req_cuda(qkv, out, dout, lse, dqkv)
+    assert out.stride(0) == dout.stride(0)
+    check(_L().b200_attention_bwd(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), dout.data_ptr(), dout.stride(0),
+                                  lse.data_ptr(), B, N, h, 64, scale, dqkv.data_ptr(), dqkv.stride(0), _stream()),
+          "b200_attention_bwd")
+
+
+def layernorm_fwd(x, w, b, eps: float, y, mean=None, rstd=None) -> None:
+    """x f32 [T,D] -> y (bf16 or f32) [T,D]."""
+    _req_cuda(x, w, b, y)
+    T, D = x.shape
+    check(_L().b200_layernorm_fwd(x.data_ptr(), x.stride(0), T, D, w.data_ptr(), b.data_ptr(), eps, y.data_ptr(),
+                                  y.stride(0), int(y.dtype == torch.bfloat16), _ptr(mean), _ptr(rstd), _stream()),
+          "b200_layernorm_fwd")
+
+
+def layernorm_bwd(dy, x, w, mean, rstd, dx, accumulate: bool, dw=None, db=None) -> None:
+    _req_cuda(dy, x, w, mean, rstd, dx)
+    T, D = x.shape
+    check(_L().b200_layernorm_bwd(dy.data_ptr(), dy.stride(0), int(dy.dtype == torch.bfloat16), x.data_ptr(),
+                                  x.stride(0), T, D, w.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(),
+                                  dx.stride(0), int(accumulate), _ptr(dw), _ptr(db), _stream()), "b200_layernorm_bwd")
+
+
+def im2col(x, p: int, cols) -> None:
+    _req_cuda(x, cols)
+    B, Cc, H, W = x.shape
+    assert x.is_contiguous() and x.dtype == torch.float32
+    check(_L().b200_im2col(x.data_ptr(), B, Cc, H, W, p, cols.data_ptr(), cols.stride(0), _stream()), "b200_im2col")
+
+
+def assemble_tokens(tok, masks_u8, mask_token, cls, reg, pos, B: int, Np: int, R: int, D: int, x) -> None:
+    check(_L().b200_assemble_tokens(tok.data_ptr(), tok.stride(0), _ptr(masks_u8), _ptr(mask_token), cls.data_ptr(),
+                                    _ptr(reg), pos.data_ptr(), B, Np, R, D, x.data_ptr(), _stream()),
+          "b200_assemble_tokens")
+
+
+def assemble_tokens_bwd(dx, masks_u8, B: int, Np: int, R: int, D: int, dtok, dpos, dcls, dreg, dmask_token) -> None:
+    check(_L().b200_assemble_tokens_bwd(dx.data_ptr(), _ptr(masks_u8), B, Np, R, D, dtok.data_ptr(), dtok.stride(0),
+                                        dpos.data_ptr(), dcls.data_ptr(), _ptr(dreg), _ptr(dmask_token), _stream()),
+          "b200_assemble_tokens_bwd")
+
+
+def layerscale_bwd(dx, o, gamma, rowscale, rows_per_scale: int, dout, dgamma, dbias) -> None:
+    T, D = dx.shape
+    check(_L().b200_layerscale_bwd(dx.data_ptr(), dx.stride(0), o.data_ptr(), o.stride(0), _ptr(gamma), _ptr(rowscale),
+                                   rows_per_scale, T, D, dout.data_ptr(), dout.stride(0), _ptr(dgamma), _ptr(dbias),
+                                   _stream()), "b200_layerscale_bwd")
+
+
+def gather_rows(src, idx, out, Np: int = 0, N: int = 0, off: int = 0) -> None:
+    """out[m] = src[map(idx[m])]; src f32 2-D; idx int64."""
+    M, D = out.shape
+    check(_L().b200_gather_rows(src.data_ptr(), src.stride(0), idx.data_ptr(), M, D, Np, N, off, out.data_ptr(),
+                                out.stride(0), int(out.dtype == torch.bfloat16), _stream()), "b200_gather_rows")
+
+
+def scatter_rows(inp, idx, dst, Np: int = 0, N: int = 0, off: int = 0, accumulate: bool = False) -> None:
+    M, D = inp.shape
+    check(_L().b200_scatter_rows(inp.data_ptr(), inp.stride(0), int(inp.dtype == torch.bfloat16), _ptr(idx), M, D, Np, N,
+                                 off, dst.data_ptr(), dst.stride(0), int(accumulate), _stream()), "b200_scatter_rows")
+
+
+def l2norm_fwd(x, y, nrm, eps: float = 1e-12) -> None:
+    R, D = x.shape
+    check(_L().b200_l2norm_fwd(x.data_ptr(), x.stride(0), R, D, eps, y.data_ptr(), y.stride(0), nrm.data_ptr(), _stream()),
+          "b200_l2norm_fwd")
+
+
+def l2norm_bwd(dy, x, nrm, dx) -> None:
+    R, D = x.shape
+    check(_L().b200_l2norm_bwd(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), nrm.data_ptr(), R, D, dx.data_ptr(),
+                               dx.stride(0), _stream()), "b200_l2norm_bwd")
+
+
+def weightnorm_fwd(g, v, w_bf16, vnorm=None) -> None:
+    O, I = v.shape
+    check(_L().b200_weightnorm_fwd(g.data_ptr(), v.data_ptr(), O, I, w_bf16.data_ptr(), _ptr(vnorm), _stream()),
+          "b200_weightnorm_fwd")
+
+
+def weightnorm_bwd(dW, g, v, dg, dv) -> None:
+    O, I = v.shape
+    check(_L().b200_weightnorm_bwd(dW.data_ptr(), g.data_ptr(), v.data_ptr(), O, I, dg.data_ptr(), dv.data_ptr(), _stream()),
+          "b200_weightnorm_bwd")
+
+
+def small_matmul(A, Bm, Cm, a_trans: bool = False, accumulate: bool = False) -> None:
+    """C[M,N] (+)= op(A) @ B ; B row-major [K,N]."""
+    K, N = Bm.shape
+    M = A.shape[1] if a_trans else A.shape[0]
+    check(_L().b200_small_matmul(A.data_ptr(), A.stride(0), int(a_trans), Bm.data_ptr(), Bm.stride(0), M, N, K,
+                                 Cm.data_ptr(), Cm.stride(0), int(accumulate), _stream()), "b200_small_matmul")
+
+
+def cast_bf16(x, y) -> None:
+    check(_L().b200_cast_bf16(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "b200_cast_bf16")
+
+
+def fill_f32(x, v: float = 0.0) -> None:
+    check(_L().b200_fill_f32(x.data_ptr(), x.numel(), v, _stream()), "b200_fill_f32")
+
+
+def row_lse(x, colterm, scale: float, rowterm) -> None:
+    R, K = x.shape
+    check(_L().b200_row_lse(x.data_ptr(), x.stride(0), R, K, _ptr(colterm), scale, rowterm.data_ptr(), _stream()),
+          "b200_row_lse")
+
+
+def col_reduce(x, out, rowvec=None, scale: float = 1.0, mode: int = 0) -> None:
+    R, K = x.shape
+    check(_L().b200_col_reduce(x.data_ptr(), x.stride(0), R, K, _ptr(rowvec), scale, mode, out.data_ptr(), _stream()),
+          "b200_col_reduce")
+
+
+def vec_op(y, x, a: float, b: float, op: int) -> None:
+    check(_L().b200_vec_op(y.data_ptr(), x.data_ptr(), y.numel(), a, b, op, _stream()), "b200_vec_op")
+
+
+def dino_ce(s, t, colterm, t_rowterm, t_idx0, t_idx1, weight, s_scale: float, t_scale: float, loss_rows, ds=None,
+            gscale: float = 1.0) -> None:
+    Rs, K = s.shape
+    check(_L().b200_dino_ce(s.data_ptr(), s.stride(0), Rs, K, t.data_ptr(), t.stride(0), _ptr(colterm),
+                            t_rowterm.data_ptr(), t_idx0.data_ptr(), _ptr(t_idx1), _ptr(weight), s_scale, t_scale, gscale,
+                            loss_rows.data_ptr(), _ptr(ds), ds.stride(0) if ds is not None else 0, _stream()),
+          "b200_dino_ce")
+
+
+def segment_sum(x, offsets_i32, out, scale=None) -> None:
+    check(_L().b200_segment_sum(x.data_ptr(), offsets_i32.data_ptr(), out.numel(), _ptr(scale), out.data_ptr(), _stream()),
+          "b200_segment_sum")
+
+
+def koleo(x, groups: int, n: int, loss_out, dx=None, gscale: float = 1.0, eps: float = 1e-8, bf16_sim: bool = True,
+          nn_out=None) -> None:
+    D = x.shape[1]
+    check(_L().b200_koleo(x.data_ptr(), x.stride(0), groups, n, D, eps, int(bf16_sim), gscale, loss_out.data_ptr(),
+                          _ptr(dx), dx.stride(0) if dx is not None else 0, _ptr(nn_out), _stream()), "b200_koleo")
+
+
+def ema(teacher_flat, student_flat, m: float, teacher_bf16=None) -> None:
+    _req_cuda(teacher_flat, student_flat)
+    check(_L().b200_ema(teacher_flat.data_ptr(), student_flat.data_ptr(), teacher_flat.numel(), m, _ptr(teacher_bf16),
+                        _stream()), "b200_ema")
+
+
+def sumsq(x, out) -> None:
+    check(_L().b200_sumsq(x.data_ptr(), x.numel(), out.data_ptr(), _stream()), "b200_sumsq")
+
+
+def adamw_ema(args: AdamWArgs) -> None:
+    check(_L().b200_adamw_ema(C.byref(args), _stream()), "b200_adamw_ema")
