@@ -41,6 +41,7 @@ class B200Error(RuntimeError):
 
 
 _lib = None
+LAUNCHES = 0  # number of C-ABI kernel launches issued (bench.py reports it as gpu_launches)
 
 
 def lib() -> C.CDLL:
@@ -68,6 +69,8 @@ def _declare(L: C.CDLL) -> None:
 
 
 def check(rc: int, what: str) -> None:
+    global LAUNCHES
+    LAUNCHES += 1
     if rc != 0:
         code = rc
         extra = ""

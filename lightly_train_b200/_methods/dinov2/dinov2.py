@@ -1,0 +1,438 @@
+"""DINOv2 method on B200 kernels.
+
+Mirror of LT/_methods/dinov2/dinov2.py: `DINOv2Args` / `DINOv2AdamWViTArgs` (:70-164), `DINOv2Head` (:167-174)
+and the `DINOv2` method (:176-692) -- teacher/student ViTs + projection heads, DINO / iBOT / KoLeo losses,
+layer-wise-decay AdamW with cosine weight decay, last-layer lr freeze, gradient clipping and the EMA teacher
+update.  The public surface keeps the reference's names (`training_step_impl`, `on_before_optimizer_step`,
+`on_train_batch_end`, `TrainingStepResult`, the `train_loss/*` log keys, parameter/buffer names under
+`teacher_embedding_model.*`, `student_embedding_model.*`, `{teacher,student}_head.{dino_head,ibot_head}.*`,
+`dino_loss.center`, `ibot_loss.center`).
+
+Execution model (B200-first, not the reference's autograd graph): one training step is an explicit schedule
+of sm_100a kernel launches -- teacher forward, student forward (global, local), fused CE forward+backward,
+head and ViT backward into a flat gradient arena -- followed by ONE fused sweep doing gradient clipping,
+AdamW, the EMA teacher update and the bf16 weight-shadow refresh.  `training_step_impl` therefore returns the
+loss with gradients already accumulated in `param.grad` (views of the arena); `loss_for_autograd()` offers a
+torch.autograd bridge for trainers that insist on calling `loss.backward()`.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Literal, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import Tensor, nn
+
+from ... import ops
+from ..._arena import CHUNK, Arena
+from ..._models.dinov2_vit import DinoVisionTransformer, vit_param_shapes
+from .dinov2_head import DINOv2ProjectionHead, head_param_shapes
+from .dinov2_loss import DINOLoss, IBOTPatchLoss, sinkhorn_colterm
+from .scheduler import cosine_schedule, cosine_warmup_factor, linear_warmup_schedule
+from .utils import MaskingGenerator, create_collated_masks, param_group_settings
+
+
+@dataclass
+class DINOv2Args:
+    """LT/_methods/dinov2/dinov2.py:70-153 (same field names and defaults)."""
+
+    ibot_separate_head: bool = False
+    hidden_dim: int = 2048
+    dino_bottleneck_dim: int = 256
+    ibot_bottleneck_dim: int = 256
+    output_dim: int = 65536
+    batch_norm: bool = False
+    student_freeze_last_layer_steps: int = 1250
+    student_freeze_backbone_steps: int = 0
+    dino_loss_weight: float = 1.0
+    ibot_loss_weight: float = 1.0
+    koleo_loss_weight: float = 0.1
+    center_method: Literal["softmax", "sinkhorn_knopp"] = "softmax"
+    center_momentum: float = 0.9
+    momentum_start: float = 0.992
+    momentum_end: float = 1.0
+    student_temp: float = 0.1
+    teacher_temp_start: float = 0.04
+    teacher_temp_end: float = 0.07
+    teacher_temp_warmup_steps: int = 37500
+    mask_ratio_min: float = 0.1
+    mask_ratio_max: float = 0.5
+    mask_probability: float = 0.5
+    min_lr: float = 1.0e-06
+    warmup_steps: int = 12500
+    layerwise_decay: float = 0.9
+    patch_embed_lr_multiplier: float = 0.2
+    lr_scale_method: Literal["linear", "sqrt"] = "sqrt"
+    reference_batch_size: int = 1024
+    weight_decay_start: float | Literal["auto"] = "auto"
+    weight_decay_end: float = 0.4
+    gradient_clip_val: float = 3.0
+
+
+@dataclass
+class DINOv2AdamWViTArgs:
+    """LT/_methods/dinov2/dinov2.py:156-164."""
+
+    lr: float = 0.004
+    betas: Tuple[float, float] = (0.9, 0.999)
+    eps: float = 1e-8
+    weight_decay: float = 0.04
+
+
+@dataclass
+class TrainingStepResult:
+    """LT/_methods/method.py:41-44."""
+
+    loss: Tensor
+    log_dict: Dict[str, Any] = field(default_factory=dict)
+
+
+class _TrainerState:
+    """The three Trainer attributes the reference method reads (tests mock exactly these, test_dinov2.py:54-59)."""
+
+    def __init__(self, max_steps: int) -> None:
+        self.global_step = 0
+        self.estimated_stepping_batches = max_steps
+        self.max_epochs = 1
+
+
+class DINOv2Head(nn.Module):
+    def __init__(self, dino_head: DINOv2ProjectionHead, ibot_head: DINOv2ProjectionHead) -> None:
+        super().__init__()
+        self.dino_head = dino_head
+        self.ibot_head = ibot_head
+
+
+class _Wrapped(nn.Module):
+    """EmbeddingModel.wrapped_model / DINOv2ViTModelWrapper._model naming shell."""
+
+    def __init__(self, model: DinoVisionTransformer) -> None:
+        super().__init__()
+        self._model = model
+
+    def get_model(self) -> DinoVisionTransformer:
+        return self._model
+
+    @torch.no_grad()
+    def forward_features(self, x: Tensor, masks: Optional[Tensor] = None) -> Dict[str, Tensor]:
+        """DINOv2ViTModelWrapper.forward_features (LT/_models/dinov2_vit/dinov2_vit.py:67-97)."""
+        rt = self._model.forward_features(x, masks)
+        pt = rt["x_norm_patchtokens"]
+        b, _, d = pt.shape
+        hh, ww = x.shape[2] // self._model.patch_size, x.shape[3] // self._model.patch_size
+        return {"features": pt.permute(0, 2, 1).reshape(b, d, hh, ww), "cls_token": rt["x_norm_clstoken"]}
+
+
+class _Embedding(nn.Module):
+    def __init__(self, model: DinoVisionTransformer) -> None:
+        super().__init__()
+        self.wrapped_model = _Wrapped(model)
+
+
+class DINOv2(nn.Module):
+    def __init__(self, method_args: DINOv2Args, optimizer_args: DINOv2AdamWViTArgs, model_kwargs: Dict[str, Any],
+                 global_batch_size: int, num_input_channels: int = 3, max_steps: int = 125_000,
+                 device: str = "cuda") -> None:
+        """model_kwargs: DinoVisionTransformer constructor arguments (embed_dim, depth, num_heads, patch_size,
+        init_values, drop_path_rate, num_register_tokens, ...) -- what `dinov2/vits14-noreg` etc. resolve to."""
+        super().__init__()
+        if method_args.batch_norm:
+            raise NotImplementedError("batch_norm heads are not implemented on the B200 path")
+        self.method_args = method_args
+        self.optimizer_args = optimizer_args
+        self.global_batch_size = global_batch_size
+        self.trainer = _TrainerState(max_steps)
+        self.device_ = torch.device(device)
+        a = method_args
+        mk = dict(model_kwargs)
+        mk.setdefault("in_chans", num_input_channels)
+        probe = dict(img_size=mk.get("img_size", 224), patch_size=mk.get("patch_size", 16), embed_dim=mk["embed_dim"],
+                     depth=mk["depth"], mlp_ratio=mk.get("mlp_ratio", 4.0))
+        D = probe["embed_dim"]
+        n_patches = (probe["img_size"] // probe["patch_size"]) ** 2
+        shapes: Dict[str, Tuple[int, ...]] = {}
+        for k, v in vit_param_shapes(D, probe["depth"], probe["patch_size"], mk["in_chans"], n_patches,
+                                     int(D * probe["mlp_ratio"]), mk.get("num_register_tokens", 0),
+                                     bool(mk.get("init_values"))).items():
+            shapes["backbone." + k] = v
+        hs = head_param_shapes(D, a.hidden_dim, a.dino_bottleneck_dim, a.output_dim)
+        for k, v in hs.items():
+            shapes["dino_head." + k] = v
+        if a.ibot_separate_head:
+            for k, v in hs.items():
+                shapes["ibot_head." + k] = v
+        self.s_arena = Arena(shapes, device, with_grad=True, with_optim_state=True)
+        self.t_arena = Arena(shapes, device, with_grad=False, with_optim_state=False)
+
+        def build(arena: Arena, train: bool):
+            mkk = dict(mk)
+            if not train:
+                mkk["drop_path_rate"] = 0.0  # make_teacher(): teacher has no stochastic depth (dinov2_vit.py:108-151)
+            vit = DinoVisionTransformer(**mkk, arena=arena, prefix="backbone.", requires_grad=train)
+            dino = DINOv2ProjectionHead(D, a.output_dim, hidden_dim=a.hidden_dim, bottleneck_dim=a.dino_bottleneck_dim,
+                                        arena=arena, prefix="dino_head.", requires_grad=train)
+            ibot = dino
+            if a.ibot_separate_head:
+                ibot = DINOv2ProjectionHead(D, a.output_dim, hidden_dim=a.hidden_dim, bottleneck_dim=a.dino_bottleneck_dim,
+                                            arena=arena, prefix="ibot_head.", requires_grad=train)
+            return vit, dino, ibot
+
+        s_vit, s_dino, s_ibot = build(self.s_arena, True)
+        t_vit, t_dino, t_ibot = build(self.t_arena, False)
+        # student = deepcopy(teacher) in the reference (dinov2.py:197-198); heads are initialised independently
+        off, n = self.s_arena.offsets["dino_head.mlp.0.weight"]
+        self.s_arena.fp32[:off].copy_(self.t_arena.fp32[:off])
+        self.teacher_embedding_model = _Embedding(t_vit)
+        self.student_embedding_model = _Embedding(s_vit)
+        self.teacher_head = DINOv2Head(t_dino, t_ibot)
+        self.student_head = DINOv2Head(s_dino, s_ibot)
+        self._patch_size = s_vit.patch_size
+        self.dino_loss = DINOLoss(a.output_dim, a.student_temp, a.center_momentum).to(device)
+        self.ibot_loss = IBOTPatchLoss(a.output_dim, a.student_temp, a.center_momentum).to(device)
+        self._opt_step = 0
+        self._build_optimizer_tables()
+        self._grad_ready = False
+
+    # ------------------------------------------------------------------ accessors
+    @property
+    def s_vit(self) -> DinoVisionTransformer:
+        return self.student_embedding_model.wrapped_model._model
+
+    @property
+    def t_vit(self) -> DinoVisionTransformer:
+        return self.teacher_embedding_model.wrapped_model._model
+
+    # ------------------------------------------------------------------ optimizer tables (configure_optimizers :550-586)
+    def _build_optimizer_tables(self) -> None:
+        a = self.method_args
+        lr_scale = a.reference_batch_size and self.global_batch_size / a.reference_batch_size
+        if a.lr_scale_method == "sqrt":
+            lr_scale = math.sqrt(lr_scale)
+        self.base_lr = self.optimizer_args.lr * lr_scale
+        nl = self.s_vit.n_blocks
+        lr_t, wd_t, fl_t = {}, {}, {}
+        for name in self.s_arena.names():
+            if name.startswith("backbone."):
+                st = param_group_settings(name[len("backbone."):], True, nl, a.layerwise_decay, a.patch_embed_lr_multiplier)
+                flags = 2  # bit1: "head" not in group name -> frozen by student_freeze_backbone_steps
+            else:
+                # parameters of DINOv2Head are named "dino_head.*" / "ibot_head.*" inside trainable_modules()
+                st = param_group_settings(name, False, nl, a.layerwise_decay, a.patch_embed_lr_multiplier)
+                flags = 1 if st["last_layer"] else 0
+            lr_t[name], wd_t[name], fl_t[name] = st["lr_scale"], st["wd_scale"], flags
+        self.lr_table = self.s_arena.chunk_table(lr_t)
+        self.wd_table = self.s_arena.chunk_table(wd_t)
+        self.flag_table = self.s_arena.chunk_table(fl_t, dtype=torch.uint8)
+        self.weight_decay_start = (self.optimizer_args.weight_decay if a.weight_decay_start == "auto"
+                                   else float(a.weight_decay_start))
+        self.gradnorm_sq = torch.zeros(1, device=self.device_, dtype=torch.float32)
+
+    # ------------------------------------------------------------------ the step
+    def _masks(self, n_crops: int, h: int, w: int):
+        a = self.method_args
+        gen = MaskingGenerator(input_size=(h, w), max_num_patches=int(0.5 * h * w))
+        return create_collated_masks(a.mask_ratio_min, a.mask_ratio_max, int(n_crops * a.mask_probability), n_crops, gen)
+
+    def training_step_impl(self, batch: Dict[str, Any], batch_idx: int = 0) -> TrainingStepResult:
+        a = self.method_args
+        dev = self.device_
+        teacher_temp = linear_warmup_schedule(self.trainer.global_step, a.teacher_temp_warmup_steps,
+                                              a.teacher_temp_start, a.teacher_temp_end)
+        views: List[Tensor] = batch["views"]
+        n_global = 2
+        n_local = len(views) - n_global
+        g_terms = (n_global - 1) * n_global
+        l_terms = max(n_local * n_global, 1)
+        gv = torch.cat(views[:n_global])
+        n_crops = gv.shape[0]
+        B = n_crops // n_global
+        p = self._patch_size
+        hh, ww = gv.shape[2] // p, gv.shape[3] // p
+        masks = batch.get("masks")
+        if masks is None:
+            masks = self._masks(n_crops, hh, ww)  # host python RNG, same stream as the reference
+        collated = masks["collated_masks"].to(dev, non_blocking=True)
+        mask_idx = masks["mask_indices_list"].to(dev, non_blocking=True)
+        masks_weight = masks["masks_weight"].to(dev, torch.float32, non_blocking=True)
+        M = int(mask_idx.shape[0])
+
+        s_vit, t_vit = self.s_vit, self.t_vit
+        s_dino, s_ibot = self.student_head.dino_head, self.student_head.ibot_head
+        t_dino, t_ibot = self.teacher_head.dino_head, self.teacher_head.ibot_head
+        separate = a.ibot_separate_head
+        D, K = s_vit.embed_dim, a.output_dim
+        R = s_vit.num_register_tokens
+        bf, f32 = torch.bfloat16, torch.float32
+        for arena in (self.s_arena, self.t_arena):
+            if not arena.bf16_valid:
+                arena.refresh_bf16()
+        for hd in {id(x): x for x in (s_dino, s_ibot, t_dino, t_ibot)}.values():
+            hd.refresh_last_layer()
+        self.s_arena.zero_grad()
+
+        # ---------------- teacher (dinov2.py:399-472)
+        tctx = t_vit._fwd(gv, None, save=False)
+        Ng = tctx.dims[3]
+        cls_rows = torch.arange(n_crops, device=dev, dtype=torch.int64) * Ng
+        cls_rows_swapped = torch.cat([cls_rows[B:], cls_rows[:B]])  # A<->B swap (:415-417)
+        t_in = torch.empty(n_crops + M, D, device=dev, dtype=bf)
+        ops.gather_rows(tctx.xnorm, cls_rows_swapped, t_in[:n_crops])
+        ops.gather_rows(tctx.xnorm, mask_idx, t_in[n_crops:], Np=hh * ww, N=Ng, off=1 + R)
+        t_logits = torch.empty(n_crops + M, K, device=dev, dtype=bf)
+        if separate:
+            t_dino._fwd(t_in[:n_crops], save=False, logits=t_logits[:n_crops])
+            if M:
+                t_ibot._fwd(t_in[n_crops:], save=False, logits=t_logits[n_crops:])
+        else:
+            t_dino._fwd(t_in, save=False, logits=t_logits)
+        del tctx
+        t_scale = 1.0 / teacher_temp
+        t_rowterm = torch.empty(n_crops + M, device=dev, dtype=f32)
+        colterm_d = torch.empty(K, device=dev, dtype=f32)
+        colterm_i = torch.empty(K, device=dev, dtype=f32)
+        if a.center_method == "softmax":
+            self.dino_loss.apply_center_update()
+            self.ibot_loss.apply_center_update()
+            ops.vec_op(colterm_d, self.dino_loss.center.view(-1), t_scale, 0.0, 1)
+            ops.vec_op(colterm_i, self.ibot_loss.center.view(-1), t_scale, 0.0, 1)
+            self.dino_loss.reduce_center_update(t_logits[:n_crops])
+            if M:
+                self.ibot_loss.reduce_center_update(t_logits[n_crops:].unsqueeze(0))
+        elif a.center_method == "sinkhorn_knopp":
+            colterm_d = sinkhorn_colterm(t_logits[:n_crops], t_scale)
+            if M:
+                colterm_i = sinkhorn_colterm(t_logits[n_crops:], t_scale)
+        else:
+            raise ValueError(f"Unknown centering method: {a.center_method}")
+        ops.row_lse(t_logits[:n_crops], colterm_d, t_scale, t_rowterm[:n_crops])
+        if M:
+            ops.row_lse(t_logits[n_crops:], colterm_i, t_scale, t_rowterm[n_crops:])
+
+        # ---------------- student forward (dinov2.py:474-519)
+        sg = s_vit._fwd(gv, collated, save=True, drop_path=True)
+        sl = None
+        LB = 0
+        if n_local > 0:
+            lv = torch.cat(views[n_global:])
+            LB = lv.shape[0]
+            sl = s_vit._fwd(lv, None, save=True, drop_path=True)
+        Rs = n_crops + LB + M
+        s_in = torch.empty(Rs, D, device=dev, dtype=bf)
+        ops.gather_rows(sg.xnorm, cls_rows, s_in[:n_crops])
+        if sl is not None:
+            Nl = sl.dims[3]
+            lcls_rows = torch.arange(LB, device=dev, dtype=torch.int64) * Nl
+            ops.gather_rows(sl.xnorm, lcls_rows, s_in[n_crops:n_crops + LB])
+        ops.gather_rows(sg.xnorm, mask_idx, s_in[n_crops + LB:], Np=hh * ww, N=Ng, off=1 + R)
+        s_logits = torch.empty(Rs, K, device=dev, dtype=bf)
+        nd = n_crops + LB
+        if separate:
+            hc_d = s_dino._fwd(s_in[:nd], save=True, logits=s_logits[:nd])
+            hc_i = s_ibot._fwd(s_in[nd:], save=True, logits=s_logits[nd:]) if M else None
+        else:
+            hc_d = s_dino._fwd(s_in, save=True, logits=s_logits)
+            hc_i = None
+
+        # ---------------- fused CE forward + backward
+        terms = g_terms + l_terms
+        idx0 = torch.empty(Rs, device=dev, dtype=torch.int32)
+        idx1 = torch.full((Rs,), -1, device=dev, dtype=torch.int32)
+        wrow = torch.empty(Rs, device=dev, dtype=f32)
+        ar = torch.arange(n_crops, device=dev, dtype=torch.int32)
+        idx0[:n_crops] = ar
+        wrow[:n_crops] = (1.0 / n_crops) * 2.0 / terms
+        if LB:
+            bidx = torch.arange(LB, device=dev, dtype=torch.int32) % B
+            idx0[n_crops:nd] = bidx
+            idx1[n_crops:nd] = bidx + B
+            wrow[n_crops:nd] = (1.0 / B) / terms
+        if M:
+            idx0[nd:] = torch.arange(M, device=dev, dtype=torch.int32)
+            wrow[nd:] = masks_weight / n_crops
+        loss_rows = torch.empty(Rs, device=dev, dtype=f32)
+        ds = torch.empty(Rs, K, device=dev, dtype=bf)
+        s_scale = 1.0 / a.student_temp
+        ops.dino_ce(s_logits[:nd], t_logits[:n_crops], colterm_d, t_rowterm[:n_crops], idx0[:nd], idx1[:nd], wrow[:nd],
+                    s_scale, t_scale, loss_rows[:nd], ds[:nd], gscale=a.dino_loss_weight)
+        if M:
+            ops.dino_ce(s_logits[nd:], t_logits[n_crops:], colterm_i, t_rowterm[n_crops:], idx0[nd:], None, wrow[nd:],
+                        s_scale, t_scale, loss_rows[nd:], ds[nd:], gscale=a.ibot_loss_weight)
+        seg = torch.tensor([0, n_crops, nd, Rs], device=dev, dtype=torch.int32)
+        loss_terms = torch.zeros(3, device=dev, dtype=f32)
+        ops.segment_sum(loss_rows, seg, loss_terms)
+        del s_logits, t_logits
+
+        # ---------------- head backward -> gradient wrt the backbone outputs
+        dxn_g = torch.zeros(sg.dims[4], D, device=dev, dtype=f32)
+        if separate:
+            dx_d = s_dino._bwd(hc_d, ds[:nd])
+            dx_i = s_ibot._bwd(hc_i, ds[nd:]) if M else None
+        else:
+            dx_all = s_dino._bwd(hc_d, ds)
+            dx_d, dx_i = dx_all[:nd], dx_all[nd:]
+        ops.scatter_rows(dx_d[:n_crops], cls_rows, dxn_g)
+        if M:
+            ops.scatter_rows(dx_i, mask_idx, dxn_g, Np=hh * ww, N=Ng, off=1 + R)
+        # KoLeo on the pre-head global cls tokens (:377-380): forward value + gradient (+=) into dxn_g
+        koleo = torch.zeros(2, device=dev, dtype=f32)
+        ops.koleo(sg.xnorm.view(n_crops, Ng, D)[:, 0], 2, B, koleo, dxn_g.view(n_crops, Ng, D)[:, 0],
+                  gscale=a.koleo_loss_weight)
+        if sl is not None:
+            dxn_l = torch.zeros(sl.dims[4], D, device=dev, dtype=f32)
+            ops.scatter_rows(dx_d[n_crops:], lcls_rows, dxn_l)
+            s_vit._bwd(sl, dxn_l)
+            del sl, dxn_l
+        s_vit._bwd(sg, dxn_g)
+        self._grad_ready = True
+
+        dino_global, dino_local, ibot = loss_terms[0], loss_terms[1], loss_terms[2]
+        koleo_loss = koleo.sum()
+        loss = (a.dino_loss_weight * dino_global + a.dino_loss_weight * dino_local + a.ibot_loss_weight * ibot
+                + a.koleo_loss_weight * koleo_loss)
+        return TrainingStepResult(loss=loss, log_dict={
+            "train_loss/dino_global_loss": dino_global, "train_loss/dino_local_loss": dino_local,
+            "train_loss/ibot_loss": ibot, "train_loss/koleo_loss": koleo_loss})
+
+    # ------------------------------------------------------------------ optimizer (+ hooks :588-660) in one sweep
+    def optimizer_step(self) -> None:
+        """all-reduce(grad) -> clip_grad_norm_(3.0) -> AdamW (per-chunk lr/wd, freezes) -> EMA teacher -> bf16 shadows."""
+        if not self._grad_ready:
+            raise RuntimeError("optimizer_step() called without gradients; call training_step_impl first")
+        a = self.method_args
+        step = self.trainer.global_step
+        max_steps = self.trainer.estimated_stepping_batches
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        if world > 1:
+            dist.all_reduce(self.s_arena.grad)  # DDP gradient all-reduce (sum); mean applied via grad_scale
+        ops.fill_f32(self.gradnorm_sq, 0.0)
+        ops.sumsq(self.s_arena.grad, self.gradnorm_sq)
+        weight_decay = cosine_schedule(step, max_steps, self.weight_decay_start, a.weight_decay_end)
+        warmup = min(max_steps - 1, a.warmup_steps)
+        lr = self.base_lr * cosine_warmup_factor(step, int(warmup), int(max_steps), a.min_lr / self.base_lr)
+        momentum = cosine_schedule(step, max_steps, a.momentum_start, a.momentum_end)
+        self._opt_step += 1
+        args = ops.AdamWArgs()
+        sa, ta = self.s_arena, self.t_arena
+        args.p, args.g, args.m, args.v, args.t = (sa.fp32.data_ptr(), sa.grad.data_ptr(), sa.exp_avg.data_ptr(),
+                                                  sa.exp_avg_sq.data_ptr(), ta.fp32.data_ptr())
+        args.p_bf16, args.t_bf16 = sa.bf16.data_ptr(), ta.bf16.data_ptr()
+        args.n, args.chunk = sa.total, CHUNK
+        args.lr_scale, args.wd_scale, args.flags = self.lr_table.data_ptr(), self.wd_table.data_ptr(), self.flag_table.data_ptr()
+        args.lr, args.wd = lr, weight_decay
+        args.beta1, args.beta2, args.eps = self.optimizer_args.betas[0], self.optimizer_args.betas[1], self.optimizer_args.eps
+        args.step, args.ema_m = self._opt_step, momentum
+        args.gradnorm_sq, args.max_norm, args.grad_scale = self.gradnorm_sq.data_ptr(), a.gradient_clip_val, 1.0 / world
+        args.freeze_last_layer = int(step < a.student_freeze_last_layer_steps)
+        args.freeze_backbone = int(step < a.student_freeze_backbone_steps)
+        ops.adamw_ema(args)
+        sa.bf16_valid = ta.bf16_valid = True
+        self._grad_ready = False
+        self.trainer.global_step += 1
+
+    def train_step(self, batch: Dict[str, Any]) -> TrainingStepResult:
+        """One full optimisation step: what Lightning's fit loop does around training_step."""
+        res = self.training_step_impl(batch, 0)
+        self.optimizer_step()
+        return res

@@ -1,0 +1,353 @@
+"""DinoVisionTransformer on B200 kernels.
+
+Mirror of LT/_models/dinov2_vit/dinov2_vit_src/models/vision_transformer.py:83-487 (class DinoVisionTransformer,
+non-chunked blocks, ffn_layer="mlp"): same constructor arguments, same parameter names / shapes
+(`cls_token`, `pos_embed`, `mask_token`, `register_tokens`, `patch_embed.proj.*`, `blocks.{i}.{norm1,attn.qkv,
+attn.proj,ls1,norm2,mlp.fc1,mlp.fc2,ls2}.*`, `norm.*`) so reference checkpoints load unchanged, and the same
+`forward_features` contract.  The arithmetic runs on the sm_100a kernels of libb200dino.so; forward and
+backward are explicit schedules of kernel launches (no autograd graph): `_fwd` returns a context of saved
+activations, `_bwd` consumes it and accumulates into the gradient arena.
+
+Rounding points follow torch.autocast("cuda", bfloat16): bf16 GEMM operands/outputs
+with fp32 accumulation, fp32 residual stream / LayerNorm / softmax.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import Tensor, nn
+
+from .. import ops
+from .._arena import Arena
+from .pos_embed import pos_embed_operator
+
+
+def vit_param_shapes(embed_dim: int, depth: int, patch_size: int, in_chans: int, num_patches: int, hidden: int,
+                     num_register_tokens: int, layerscale: bool) -> Dict[str, Tuple[int, ...]]:
+    D, p = embed_dim, patch_size
+    s: Dict[str, Tuple[int, ...]] = {"cls_token": (1, 1, D), "pos_embed": (1, 1 + num_patches, D)}
+    if num_register_tokens:
+        s["register_tokens"] = (1, num_register_tokens, D)
+    s["patch_embed.proj.weight"] = (D, in_chans, p, p)
+    s["patch_embed.proj.bias"] = (D,)
+    for i in range(depth):
+        b = f"blocks.{i}."
+        s[b + "norm1.weight"] = (D,); s[b + "norm1.bias"] = (D,)
+        s[b + "attn.qkv.weight"] = (3 * D, D); s[b + "attn.qkv.bias"] = (3 * D,)
+        s[b + "attn.proj.weight"] = (D, D); s[b + "attn.proj.bias"] = (D,)
+        if layerscale:
+            s[b + "ls1.gamma"] = (D,)
+        s[b + "norm2.weight"] = (D,); s[b + "norm2.bias"] = (D,)
+        s[b + "mlp.fc1.weight"] = (hidden, D); s[b + "mlp.fc1.bias"] = (hidden,)
+        s[b + "mlp.fc2.weight"] = (D, hidden); s[b + "mlp.fc2.bias"] = (D,)
+        if layerscale:
+            s[b + "ls2.gamma"] = (D,)
+    s["norm.weight"] = (D,); s["norm.bias"] = (D,)
+    s["mask_token"] = (1, D)
+    return s
+
+
+def attach_params(root: nn.Module, arena: Arena, prefix: str, names, requires_grad: bool) -> None:
+    """Register arena views as nn.Parameters under `root` following the dotted reference names."""
+    for full in names:
+        if not full.startswith(prefix):
+            continue
+        name = full[len(prefix):]
+        mod = root
+        parts = name.split(".")
+        for part in parts[:-1]:
+            if not hasattr(mod, part) or not isinstance(getattr(mod, part), nn.Module):
+                mod.add_module(part, nn.Module())
+            mod = getattr(mod, part)
+        param = nn.Parameter(arena.p(full), requires_grad=requires_grad)
+        if requires_grad and arena.grad is not None:
+            param.grad = arena.g(full)
+        mod.register_parameter(parts[-1], param)
+
+
+class VitCtx:
+    """Saved activations of one forward pass (everything the explicit backward needs)."""
+
+    def __init__(self) -> None:
+        self.blocks: List[dict] = []
+
+
+class DinoVisionTransformer(nn.Module):
+    def __init__(self, img_size: int = 224, patch_size: int = 16, in_chans: int = 3, embed_dim: int = 768,
+                 depth: int = 12, num_heads: int = 12, mlp_ratio: float = 4.0, qkv_bias: bool = True,
+                 ffn_bias: bool = True, proj_bias: bool = True, drop_path_rate: float = 0.0,
+                 drop_path_uniform: bool = False, init_values: Optional[float] = None, ffn_layer: str = "mlp",
+                 block_chunks: int = 0, num_register_tokens: int = 0, interpolate_antialias: bool = False,
+                 interpolate_offset: float = 0.1, *, arena: Optional[Arena] = None, prefix: str = "",
+                 device: str = "cuda", requires_grad: bool = True) -> None:
+        super().__init__()
+        if ffn_layer != "mlp" or block_chunks not in (0,) or not (qkv_bias and ffn_bias and proj_bias):
+            raise NotImplementedError("b200 DinoVisionTransformer: ffn_layer='mlp', block_chunks=0, biases on")
+        if embed_dim % num_heads or embed_dim // num_heads != 64:
+            raise NotImplementedError("b200 attention kernels are specialised for head_dim 64")
+        self.num_features = self.embed_dim = embed_dim
+        self.n_blocks = depth
+        self.num_heads = num_heads
+        self.patch_size = patch_size
+        self.in_chans = in_chans
+        self.img_size = img_size
+        self.num_register_tokens = num_register_tokens
+        self.interpolate_antialias = interpolate_antialias
+        self.interpolate_offset = interpolate_offset
+        self.hidden_dim = int(embed_dim * mlp_ratio)
+        self.chunked_blocks = False
+        self.layerscale = bool(init_values)
+        self.ln_eps = 1e-6
+        self.num_patches = (img_size // patch_size) ** 2
+        if drop_path_uniform:
+            self.dpr = [drop_path_rate] * depth
+        else:
+            self.dpr = [x.item() for x in torch.linspace(0, drop_path_rate, depth)]  # vision_transformer.py:161-166
+        self.prefix = prefix
+        shapes = vit_param_shapes(embed_dim, depth, patch_size, in_chans, self.num_patches, self.hidden_dim,
+                                  num_register_tokens, self.layerscale)
+        if arena is None:
+            arena = Arena({prefix + k: v for k, v in shapes.items()}, device, with_grad=requires_grad,
+                          with_optim_state=False)
+        self.arena = arena
+        attach_params(self, arena, prefix, [prefix + k for k in shapes], requires_grad)
+        self._pos_ops: Dict[Tuple[int, int], Tensor] = {}
+        self.init_weights(init_values)
+
+    # ------------------------------------------------------------------ init (vision_transformer.py:244-249,574+)
+    @torch.no_grad()
+    def init_weights(self, init_values: Optional[float]) -> None:
+        for name, prm in self.named_parameters():
+            if name == "pos_embed":
+                nn.init.trunc_normal_(prm, std=0.02)
+            elif name in ("cls_token", "register_tokens"):
+                nn.init.normal_(prm, std=1e-6)
+            elif name == "mask_token":
+                prm.zero_()
+            elif name == "patch_embed.proj.weight":
+                nn.init.kaiming_uniform_(prm, a=math.sqrt(5))  # nn.Conv2d default
+            elif name == "patch_embed.proj.bias":
+                bound = 1.0 / math.sqrt(self.in_chans * self.patch_size ** 2)
+                nn.init.uniform_(prm, -bound, bound)
+            elif name.endswith("gamma"):
+                prm.fill_(init_values)
+            elif "norm" in name and name.endswith("weight"):
+                prm.fill_(1.0)
+            elif name.endswith("bias"):
+                prm.zero_()
+            else:
+                nn.init.trunc_normal_(prm, std=0.02)
+        self.arena.bf16_valid = False
+
+    # ------------------------------------------------------------------ helpers
+    def _P(self, name: str) -> Tensor:
+        return self.arena.p(self.prefix + name)
+
+    def _W(self, name: str) -> Tensor:
+        return self.arena.w(self.prefix + name)
+
+    def _G(self, name: str) -> Tensor:
+        return self.arena.g(self.prefix + name)
+
+    def _pos_operator(self, w0: int, h0: int) -> Tensor:
+        key = (w0, h0)
+        if key not in self._pos_ops:
+            M = int(math.sqrt(self.num_patches))
+            W = pos_embed_operator(M, w0, h0, self.interpolate_offset, self.interpolate_antialias)
+            self._pos_ops[key] = torch.from_numpy(W).to(self.arena.device)
+        return self._pos_ops[key]
+
+    def _pos_for(self, Np: int, H: int, W: int) -> Tuple[Tensor, bool]:
+        """[1+Np, D] positional embedding for this crop size (interpolate_pos_encoding, :251-305)."""
+        pos = self._P("pos_embed")[0]
+        if Np == self.num_patches and H == W:
+            return pos, False
+        w0, h0 = H // self.patch_size, W // self.patch_size  # reference names (new_H, new_W) as (w, h)
+        op = self._pos_operator(w0, h0)
+        out = torch.empty(1 + Np, self.embed_dim, device=pos.device, dtype=torch.float32)
+        out[0].copy_(pos[0])
+        ops.small_matmul(op, pos[1:], out[1:])
+        return out, True
+
+    # ------------------------------------------------------------------ forward
+    def _fwd(self, x: Tensor, masks: Optional[Tensor], save: bool, drop_path: bool = False) -> VitCtx:
+        if not self.arena.bf16_valid:
+            self.arena.refresh_bf16()
+        dev = x.device
+        Bc, Cin, H, Wimg = x.shape
+        p, D, Hd, h = self.patch_size, self.embed_dim, self.hidden_dim, self.num_heads
+        Np = (H // p) * (Wimg // p)
+        R = self.num_register_tokens
+        N = 1 + R + Np
+        T = Bc * N
+        bf, f32 = torch.bfloat16, torch.float32
+        ctx = VitCtx()
+        ctx.dims = (Bc, Np, R, N, T, H, Wimg)
+        E = lambda *s, dt=bf: torch.empty(*s, device=dev, dtype=dt)  # noqa: E731
+
+        cols = E(Bc * Np, Cin * p * p)
+        ops.im2col(x.contiguous(), p, cols)
+        tok = E(Bc * Np, D)
+        ops.gemm(cols, self._W("patch_embed.proj.weight").view(D, -1), tok, bias=self._P("patch_embed.proj.bias"))
+        pos, interp = self._pos_for(Np, H, Wimg)
+        masks_u8 = masks.to(torch.uint8).contiguous() if masks is not None else None
+        xs = E(Bc, N, D, dt=f32)
+        ops.assemble_tokens(tok, masks_u8, self._P("mask_token") if masks is not None else None,
+                            self._P("cls_token").view(D), self._P("register_tokens").view(R, D) if R else None, pos,
+                            Bc, Np, R, D, xs)
+        xcur = xs.view(T, D)
+        if save:
+            ctx.cols, ctx.masks_u8, ctx.interp = cols, masks_u8, interp
+        scale = 64 ** -0.5
+        for i in range(self.n_blocks):
+            b = f"blocks.{i}."
+            sv: dict = {}
+            rs1 = rs2 = None
+            if drop_path and self.dpr[i] > 0.0:
+                keep = 1.0 - self.dpr[i]
+                rs1 = torch.empty(Bc, device=dev, dtype=f32).bernoulli_(keep).div_(keep)  # drop_path.py:23-27
+                rs2 = torch.empty(Bc, device=dev, dtype=f32).bernoulli_(keep).div_(keep)
+            mean1, rstd1 = (E(T, dt=f32), E(T, dt=f32)) if save else (None, None)
+            xn = E(T, D)
+            ops.layernorm_fwd(xcur, self._P(b + "norm1.weight"), self._P(b + "norm1.bias"), self.ln_eps, xn, mean1, rstd1)
+            qkv = E(T, 3 * D)
+            ops.gemm(xn, self._W(b + "attn.qkv.weight"), qkv, bias=self._P(b + "attn.qkv.bias"))
+            att = E(T, D)
+            lse = E(Bc * h, N, dt=f32) if save else None
+            ops.attention_fwd(qkv, Bc, N, h, att, lse, scale)
+            o1 = E(T, D) if save else None
+            xmid = E(T, D, dt=f32)
+            ops.gemm(att, self._W(b + "attn.proj.weight"), xmid, epi=ops.EPI_RESIDUAL, bias=self._P(b + "attn.proj.bias"),
+                     out2=o1, aux=xcur, gamma=self._P(b + "ls1.gamma") if self.layerscale else None,
+                     rowscale=rs1, rows_per_scale=N)
+            mean2, rstd2 = (E(T, dt=f32), E(T, dt=f32)) if save else (None, None)
+            xn2 = E(T, D)
+            ops.layernorm_fwd(xmid, self._P(b + "norm2.weight"), self._P(b + "norm2.bias"), self.ln_eps, xn2, mean2, rstd2)
+            hh = E(T, Hd)
+            u = E(T, Hd) if save else None
+            ops.gemm(xn2, self._W(b + "mlp.fc1.weight"), hh, epi=ops.EPI_BIAS_GELU, bias=self._P(b + "mlp.fc1.bias"), out2=u)
+            o2 = E(T, D) if save else None
+            xout = E(T, D, dt=f32)
+            ops.gemm(hh, self._W(b + "mlp.fc2.weight"), xout, epi=ops.EPI_RESIDUAL, bias=self._P(b + "mlp.fc2.bias"),
+                     out2=o2, aux=xmid, gamma=self._P(b + "ls2.gamma") if self.layerscale else None,
+                     rowscale=rs2, rows_per_scale=N)
+            if save:
+                sv.update(x_in=xcur, mean1=mean1, rstd1=rstd1, xn=xn, qkv=qkv, att=att, lse=lse, o1=o1, x_mid=xmid,
+                          mean2=mean2, rstd2=rstd2, xn2=xn2, u=u, h=hh, o2=o2, rs1=rs1, rs2=rs2)
+                ctx.blocks.append(sv)
+            xcur = xout
+        meanf, rstdf = (E(T, dt=f32), E(T, dt=f32)) if save else (None, None)
+        xnorm = E(T, D, dt=f32)
+        ops.layernorm_fwd(xcur, self._P("norm.weight"), self._P("norm.bias"), self.ln_eps, xnorm, meanf, rstdf)
+        ctx.x_prenorm, ctx.xnorm = xcur, xnorm
+        if save:
+            ctx.meanf, ctx.rstdf = meanf, rstdf
+        return ctx
+
+    # ------------------------------------------------------------------ backward
+    def _bwd(self, ctx: VitCtx, d_xnorm: Tensor, wgrad_splits: int = 0) -> None:
+        """d_xnorm: f32 [T, D] gradient wrt the final-LayerNorm output. Accumulates into the gradient arena."""
+        Bc, Np, R, N, T, H, Wimg = ctx.dims
+        D, Hd, h = self.embed_dim, self.hidden_dim, self.num_heads
+        dev = d_xnorm.device
+        bf, f32 = torch.bfloat16, torch.float32
+        E = lambda *s, dt=bf: torch.empty(*s, device=dev, dtype=dt)  # noqa: E731
+        if wgrad_splits <= 0:
+            wgrad_splits = max(1, min(32, T // 2048))
+        scale = 64 ** -0.5
+
+        def wgrad(dy: Tensor, xin: Tensor, name: str) -> None:
+            # dW[out,in] += dy^T x : contraction over tokens, both operands MN-major, split-K + fp32 atomics
+            ops.gemm(dy, xin, self._G(name).view(dy.shape[1], xin.shape[1]), a_mn=True, b_mn=True,
+                     epi=ops.EPI_F32_ATOMIC, splits=wgrad_splits)
+
+        dx = E(T, D, dt=f32)
+        ops.layernorm_bwd(d_xnorm, ctx.x_prenorm, self._P("norm.weight"), ctx.meanf, ctx.rstdf, dx, False,
+                          self._G("norm.weight"), self._G("norm.bias"))
+        for i in reversed(range(self.n_blocks)):
+            b = f"blocks.{i}."
+            sv = ctx.blocks[i]
+            ls = self.layerscale
+            # ---- MLP branch
+            do2 = E(T, D)
+            ops.layerscale_bwd(dx, sv["o2"], self._P(b + "ls2.gamma") if ls else None, sv["rs2"], N, do2,
+                               self._G(b + "ls2.gamma") if ls else None, self._G(b + "mlp.fc2.bias"))
+            dU = E(T, Hd)
+            ops.gemm(do2, self._W(b + "mlp.fc2.weight"), dU, b_mn=True, epi=ops.EPI_DGELU, aux=sv["u"])
+            wgrad(do2, sv["h"], b + "mlp.fc2.weight")
+            ops.col_reduce(dU, self._G(b + "mlp.fc1.bias"))
+            wgrad(dU, sv["xn2"], b + "mlp.fc1.weight")
+            dxn2 = E(T, D)
+            ops.gemm(dU, self._W(b + "mlp.fc1.weight"), dxn2, b_mn=True)
+            ops.layernorm_bwd(dxn2, sv["x_mid"], self._P(b + "norm2.weight"), sv["mean2"], sv["rstd2"], dx, True,
+                              self._G(b + "norm2.weight"), self._G(b + "norm2.bias"))
+            # ---- attention branch
+            do1 = E(T, D)
+            ops.layerscale_bwd(dx, sv["o1"], self._P(b + "ls1.gamma") if ls else None, sv["rs1"], N, do1,
+                               self._G(b + "ls1.gamma") if ls else None, self._G(b + "attn.proj.bias"))
+            datt = E(T, D)
+            ops.gemm(do1, self._W(b + "attn.proj.weight"), datt, b_mn=True)
+            wgrad(do1, sv["att"], b + "attn.proj.weight")
+            dqkv = E(T, 3 * D)
+            ops.attention_bwd(sv["qkv"], sv["att"], datt, sv["lse"], Bc, N, h, dqkv, scale)
+            ops.col_reduce(dqkv, self._G(b + "attn.qkv.bias"))
+            wgrad(dqkv, sv["xn"], b + "attn.qkv.weight")
+            dxn = E(T, D)
+            ops.gemm(dqkv, self._W(b + "attn.qkv.weight"), dxn, b_mn=True)
+            ops.layernorm_bwd(dxn, sv["x_in"], self._P(b + "norm1.weight"), sv["mean1"], sv["rstd1"], dx, True,
+                              self._G(b + "norm1.weight"), self._G(b + "norm1.bias"))
+            ctx.blocks[i] = None  # free activations early
+        # ---- embeddings
+        dtok = E(Bc * Np, D)
+        gpos = self._G("pos_embed")[0]
+        if ctx.interp:
+            dpos = torch.zeros(1 + Np, D, device=dev, dtype=f32)
+        else:
+            dpos = gpos
+        ops.assemble_tokens_bwd(dx.view(Bc, N, D), ctx.masks_u8, Bc, Np, R, D, dtok, dpos, self._G("cls_token").view(D),
+                                self._G("register_tokens").view(R, D) if R else None,
+                                self._G("mask_token").view(D) if ctx.masks_u8 is not None else None)
+        if ctx.interp:
+            w0, h0 = H // self.patch_size, Wimg // self.patch_size
+            ops.small_matmul(self._pos_operator(w0, h0), dpos[1:], gpos[1:], a_trans=True, accumulate=True)
+            gpos[0].add_(dpos[0])
+        ops.col_reduce(dtok, self._G("patch_embed.proj.bias"))
+        ops.gemm(dtok, ctx.cols, self._G("patch_embed.proj.weight").view(D, -1), a_mn=True, b_mn=True,
+                 epi=ops.EPI_F32_ATOMIC, splits=max(1, min(32, (Bc * Np) // 2048)))
+
+    # ------------------------------------------------------------------ reference-facing API
+    @torch.no_grad()
+    def forward_features(self, x: Tensor, masks: Optional[Tensor] = None) -> Dict[str, Tensor]:
+        """DinoVisionTransformer.forward_features (vision_transformer.py:361-384); inference schedule (nothing saved)."""
+        ctx = self._fwd(x, masks, save=False)
+        Bc, Np, R, N, T, _, _ = ctx.dims
+        xn = ctx.xnorm.view(Bc, N, self.embed_dim)
+        return {"x_norm_clstoken": xn[:, 0], "x_norm_regtokens": xn[:, 1:R + 1], "x_norm_patchtokens": xn[:, R + 1:],
+                "x_prenorm": ctx.x_prenorm.view(Bc, N, self.embed_dim), "masks": masks}
+
+    def forward(self, *args, is_training: bool = False, **kwargs):
+        ret = self.forward_features(*args, **kwargs)
+        return ret if is_training else ret["x_norm_clstoken"]
+
+
+def vit_small(patch_size=16, num_register_tokens=0, **kw) -> DinoVisionTransformer:
+    return DinoVisionTransformer(patch_size=patch_size, embed_dim=384, depth=12, num_heads=6, mlp_ratio=4,
+                                 num_register_tokens=num_register_tokens, **kw)
+
+
+def vit_base(patch_size=16, num_register_tokens=0, **kw) -> DinoVisionTransformer:
+    return DinoVisionTransformer(patch_size=patch_size, embed_dim=768, depth=12, num_heads=12, mlp_ratio=4,
+                                 num_register_tokens=num_register_tokens, **kw)
+
+
+def vit_large(patch_size=16, num_register_tokens=0, **kw) -> DinoVisionTransformer:
+    return DinoVisionTransformer(patch_size=patch_size, embed_dim=1024, depth=24, num_heads=16, mlp_ratio=4,
+                                 num_register_tokens=num_register_tokens, **kw)
+
+
+def vit_tiny(patch_size=16, num_register_tokens=0, **kw) -> DinoVisionTransformer:
+    """ViT-T/16 (BASELINE.json cfg1): embed 192, 3 heads of 64."""
+    return DinoVisionTransformer(patch_size=patch_size, embed_dim=192, depth=12, num_heads=3, mlp_ratio=4,
+                                 num_register_tokens=num_register_tokens, **kw)

@@ -1,0 +1,79 @@
+"""CPU tests of the host-side mirror of the reference interface (no GPU, no kernels)."""
+import random
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from lightly_train_b200._methods.dinov2 import scheduler, utils
+from lightly_train_b200._models.pos_embed import pos_embed_operator
+from oracle import dinov2_oracle as O
+
+
+def test_masks_reproduce_reference_bit_for_bit(golden_dir):
+    ref = torch.load(golden_dir / "masks.pt")
+    for case in ref.values():
+        random.seed(case["seed"])
+        hw = case["hw"]
+        gen = utils.MaskingGenerator(input_size=(hw, hw), max_num_patches=int(0.5 * hw * hw))
+        got = utils.create_collated_masks(0.1, 0.5, int(case["n_crops"] * 0.5), case["n_crops"], gen)
+        assert torch.equal(got["collated_masks"], case["collated_masks"])
+        assert torch.equal(got["mask_indices_list"], case["mask_indices_list"])
+        assert torch.equal(got["masks_weight"], case["masks_weight"])
+
+
+def test_mask_generator_invariants():
+    """tests/_methods/dinov2/test_utils.py style invariants."""
+    random.seed(0)
+    gen = utils.MaskingGenerator(input_size=(14, 14), max_num_patches=98)
+    for n in (0, 4, 20, 60, 98):
+        m = gen(n)
+        assert m.shape == (14, 14) and m.dtype == bool and m.sum() <= max(n, 0)
+    res = utils.create_collated_masks(0.1, 0.5, 4, 8, gen)
+    assert res["collated_masks"].shape == (8, 196)
+    assert res["mask_indices_list"].numel() == int(res["collated_masks"].sum())
+    per_img = res["collated_masks"].sum(-1)
+    assert (per_img == 0).sum() >= 4
+
+
+def test_lr_decay_and_groups_follow_reference_rules():
+    """get_vit_lr_decay_rate / get_optimizer_with_decay (utils.py:155-250) vs the oracle restatement."""
+    names = ["cls_token", "pos_embed", "mask_token", "patch_embed.proj.weight", "patch_embed.proj.bias",
+             "blocks.0.norm1.weight", "blocks.3.attn.qkv.weight", "blocks.11.mlp.fc2.bias", "blocks.5.ls1.gamma",
+             "norm.weight", "norm.bias"]
+    for n in names:
+        s = utils.param_group_settings(n, True, 12, 0.9, 0.2)
+        o = O.param_hparams(n, True, 1.0, 1.0, 12, 0.9, 0.2)
+        assert s["lr_scale"] == pytest.approx(o["lr"]) and s["wd_scale"] == pytest.approx(o["weight_decay"])
+    assert utils.param_group_settings("blocks.0.attn.qkv.weight", True, 12, 0.9, 0.2)["lr_scale"] == pytest.approx(0.9 ** 12)
+    assert utils.param_group_settings("patch_embed.proj.weight", True, 12, 0.9, 0.2)["lr_scale"] == pytest.approx(0.2 * 0.9 ** 13)
+    assert utils.param_group_settings("norm.weight", True, 12, 0.9, 0.2)["lr_scale"] == pytest.approx(1.0)
+    h = utils.param_group_settings("dino_head.last_layer.parametrizations.weight.original1", False, 12, 0.9, 0.2)
+    assert h["lr_scale"] == 1.0 and h["wd_scale"] == 1.0 and h["last_layer"] == 1.0 and h["head"] == 1.0
+    assert utils.param_group_settings("dino_head.mlp.0.bias", False, 12, 0.9, 0.2)["wd_scale"] == 0.0
+
+
+def test_schedules():
+    assert scheduler.linear_warmup_schedule(0, 37500, 0.04, 0.07) == 0.04
+    assert scheduler.linear_warmup_schedule(37500, 37500, 0.04, 0.07) == 0.07
+    with pytest.raises(ValueError):
+        scheduler.linear_warmup_schedule(-1, 10, 0.04, 0.07)
+    assert scheduler.cosine_schedule(0, 100, 0.992, 1.0) == pytest.approx(0.992)
+    assert scheduler.cosine_schedule(100, 100, 0.992, 1.0) == 1.0
+    assert scheduler.cosine_schedule(99, 100, 0.992, 1.0) == pytest.approx(1.0)
+    for s in (0, 1, 7, 50, 99):
+        assert scheduler.cosine_schedule(s, 100, 0.04, 0.4) == pytest.approx(O.cosine_schedule(s, 100, 0.04, 0.4))
+    # reference test (tests/_methods/dinov2/test_dinov2.py:137-224): warmup 2 -> lr/2 after the first step
+    assert scheduler.cosine_warmup_factor(0, 2, 10, 0.01) == pytest.approx(0.5)
+    assert scheduler.cosine_warmup_factor(1, 2, 10, 0.01) == pytest.approx(1.0)
+    assert scheduler.cosine_warmup_factor(10, 2, 10, 0.01) == pytest.approx(0.01)
+
+
+@pytest.mark.parametrize("M,w0,off,aa", [(14, 6, 0.1, False), (16, 7, 0.1, False), (14, 6, 0.0, True), (37, 7, 0.1, True)])
+def test_pos_embed_operator_matches_interpolate(M, w0, off, aa):
+    x = torch.randn(1, 5, M, M)
+    kw = dict(scale_factor=((w0 + off) / M, (w0 + off) / M)) if off else dict(size=(w0, w0))
+    y = F.interpolate(x, mode="bicubic", antialias=aa, **kw)
+    W = torch.from_numpy(pos_embed_operator(M, w0, w0, off, aa))
+    y2 = (W @ x.reshape(5, M * M).t()).t().reshape(1, 5, w0, w0)
+    torch.testing.assert_close(y2, y, rtol=1e-4, atol=1e-5)
