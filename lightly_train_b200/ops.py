@@ -14,6 +14,9 @@ from ._lib import (EPI_BF16, EPI_BIAS_GELU, EPI_DGELU, EPI_F32, EPI_F32_ATOMIC, 
                    EPI_RESIDUAL, GemmArgs, check)
 
 
+GEMM_PROFILE = None  # bench.py sets this to a list: (flops, start_event, end_event) per b200_gemm launch
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -64,6 +67,13 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn: bool = Fa
     args.gamma = _ptr(gamma)
     args.rowscale = _ptr(rowscale)
     args.rows_per_scale = rows_per_scale
+    if GEMM_PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(_lib.lib().b200_gemm(C.byref(args), _stream()), "b200_gemm")
+        e1.record()
+        GEMM_PROFILE.append((2.0 * M * N * K, e0, e1))
+        return out
     check(_lib.lib().b200_gemm(C.byref(args), _stream()), "b200_gemm")
     return out
 
