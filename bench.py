@@ -127,11 +127,21 @@ def cpu_reference_step_time(batch: int, steps: int, warmup: int, threads: int):
     return sum(times) / len(times)
 
 
+def host_threads() -> int:
+    """Threads the CPU arm uses: the cores this process may run on, capped at 16 (the oracle's small-matrix torch
+    ops slow down badly when oversubscribed across a 128-core host)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, min(n, 16))
+
+
 def run_reference_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     batch = 4
     sec = cpu_reference_step_time(batch, args.steps, args.warmup, threads)
     value = batch / sec
@@ -157,6 +167,8 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="launch every kernel from the host instead of CUDA-graph replay")
+    ap.add_argument("--gemm-profile", default="", help="write the per-shape GEMM timing table of one step to this file")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -183,6 +195,7 @@ def main() -> None:
     random.seed(1000 + rank)
     torch.manual_seed(0)
     method = DINOv2(DINOv2Args(), DINOv2AdamWViTArgs(), VIT_S16, global_batch_size=B * world, max_steps=125_000, device=str(dev))
+    method.use_cuda_graph = not args.eager
     if world > 1:  # identical initial weights on every rank
         dist.broadcast(method.s_arena.fp32, 0)
         dist.broadcast(method.t_arena.fp32, 0)
@@ -264,9 +277,21 @@ def main() -> None:
     roofline = None
     if rank == 0:
         ops.GEMM_PROFILE = []
+        method.use_cuda_graph = False  # events cannot be recorded inside a graph replay: time the eager schedule
         method.train_step(batches[0])
         torch.cuda.synchronize()
+        method.use_cuda_graph = not args.eager
         prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
+        if args.gemm_profile:
+            table = {}
+            for (f, a, b), key in zip(prof, ops.GEMM_PROFILE_KEYS):
+                t = table.setdefault(key, [0, 0.0, 0.0])
+                t[0] += 1; t[1] += a.elapsed_time(b); t[2] += f
+            rows = sorted(((k, v) for k, v in table.items()), key=lambda kv: -kv[1][1])
+            with open(args.gemm_profile, "w") as fh:
+                fh.write("M,N,K,a_mn,b_mn,epi,splits,launches,total_ms,TFLOP/s\n")
+                for k, v in rows:
+                    fh.write(",".join(map(str, k)) + f",{v[0]},{v[1]:.4f},{v[2] / (v[1] * 1e-3) / 1e12:.1f}\n")
         flops = sum(f for f, _, _ in prof)
         gemm_ms = sum(a.elapsed_time(b) for _, a, b in prof)
         peaks = {}
@@ -278,11 +303,12 @@ def main() -> None:
         roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all launches of one step)", "achieved": ach,
                     "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
+                    "timed": "CUDA events around every b200_gemm launch of one eagerly launched step (same kernels as the graph replay)",
                     "gemm_launches": len(prof), "gemm_ms_per_step": gemm_ms, "gemm_tflop_per_step": flops / 1e12}
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        threads = host_threads()
         sec = cpu_reference_step_time(2, 1, 1, threads)
         cpu_baseline = {"value": 2 / sec, "unit": "images/s", "cores": threads, "kind": "port",
                         "sample": "full step (fwd+bwd+AdamW+EMA) of ViT-S/16 + K=65536 heads at bs=2, oracle/ on torch CPU fp32, 1 warm-up + 1 timed"}

@@ -108,7 +108,8 @@ int b200_layerscale_bwd(const float* dx, long long lddx, const void* o, long lon
 int b200_gather_rows(const float* src, long long lds, const long long* idx, int M, int D, int Np, int N, int off,
                      void* out, long long ldo, int out_bf16, void* stream);
 int b200_scatter_rows(const void* in, long long ldi, int in_bf16, const long long* idx, int M, int D, int Np,
-                      int N, int off, float* dst, long long ldd, int accumulate, void* stream);
+                      int N, int off, float* dst, long long ldd, int accumulate, const int* count_dev,
+                      void* stream); /* count_dev: optional device int; rows m >= *count_dev are skipped */
 /* F.normalize(p=2, eps) on bf16 rows (dinov2_head.py:68-69) and backward. */
 int b200_l2norm_fwd(const void* x, long long ldx, int R, int D, float eps, void* y, long long ldy, float* nrm,
                     void* stream);
@@ -128,24 +129,26 @@ int b200_fill_f32(float* x, long long n, float v, void* stream);
 /* ------------------------------------------------------------------------------------------------
  * DINO / iBOT loss path (LT/_methods/dinov2/dinov2_loss.py). Teacher probabilities are represented as
  *   p[b,k] = exp(t[b,k]*t_scale + colterm[k] + rowterm[b])   and never materialised.
+ * `*_dev` arguments: optional DEVICE scalar overriding the by-value scalar of the same name (lets a captured
+ * CUDA graph follow the teacher-temperature schedule without re-capture); NULL = use the by-value argument.
  */
 /* rowterm[r] = -logsumexp_k(x[r,k]*scale + colterm[k]); x bf16 [R,K]. (softmax_center_teacher :76-82,
  * last column normalisation of sinkhorn_knopp_teacher :109-113) */
-int b200_row_lse(const void* x, long long ld, int R, int K, const float* colterm, float scale, float* rowterm,
-                 void* stream);
+int b200_row_lse(const void* x, long long ld, int R, int K, const float* colterm, float scale,
+                 const float* scale_dev, float* rowterm, void* stream);
 /* out[k] += sum_r x[r,k]*rowvec[r] (mode 0; center batch sums :135-145, bias grads) or
  * out[k] += sum_r exp(x[r,k]*scale + rowvec[r]) (mode 1; Sinkhorn prototype sums :100-104). */
-int b200_col_reduce(const void* x, long long ld, int R, int K, const float* rowvec, float scale, int mode,
-                    float* out, void* stream);
+int b200_col_reduce(const void* x, long long ld, int R, int K, const float* rowvec, float scale,
+                    const float* scale_dev, int mode, float* out, void* stream);
 /* K-vector helpers: op0 y=a*x+b*y (center EMA :148-160), op1 y=-a*x (colterm from center),
  * op2 y=-log(x)-a (Sinkhorn log-scaling). */
-int b200_vec_op(float* y, const float* x, int n, float a, float b, int op, void* stream);
+int b200_vec_op(float* y, const float* x, int n, float a, float b, int op, const float* a_dev, void* stream);
 /* Fused CE forward+backward, one student row per CTA (DINOLoss.forward :117-133, forward_masked :246-268):
  * loss_rows[r] = w*(n_t*LSE_s - s_scale*sum_k p_t[k]*s[k]); ds = w*s_scale*(n_t*softmax_s - p_t)*gscale. */
 int b200_dino_ce(const void* s, long long lds, int Rs, int K, const void* t, long long ldt, const float* colterm,
                  const float* t_rowterm, const int* t_idx0, const int* t_idx1, const float* weight,
-                 float s_scale, float t_scale, float gscale, float* loss_rows, void* ds, long long ldds,
-                 void* stream);
+                 float s_scale, float t_scale, const float* t_scale_dev, float gscale, float* loss_rows, void* ds,
+                 long long ldds, void* stream);
 int b200_segment_sum(const float* x, const int* offsets, int n_segments, const float* scale, float* out,
                      void* stream);
 /* KoLeoLoss forward+backward (lightly.loss.KoLeoLoss; call site dinov2.py:377-380), `groups` independent
@@ -172,6 +175,8 @@ typedef struct b200_adamw_args {
   int step;                   /* 1-based                                                             */
   float ema_m;
   const float* gradnorm_sq;   /* device scalar (sum of squares of g) or NULL = no clipping           */
+  const float* dyn;           /* optional device [7]: lr, wd, 1-b1^t, sqrt(1-b2^t), ema_m, freeze_last,
+                                 freeze_backbone -- overrides the by-value fields (CUDA-graph replay)  */
   float max_norm;
   float grad_scale;           /* multiplies g (e.g. 1/world_size)                                    */
   int freeze_last_layer, freeze_backbone;

@@ -194,6 +194,9 @@ class DINOv2(nn.Module):
         self._opt_step = 0
         self._build_optimizer_tables()
         self._grad_ready = False
+        self._seg_cache: Dict[Tuple[int, int, int], Tensor] = {}
+        self._static: Optional[Dict[str, Any]] = None
+        self.use_cuda_graph = False
 
     # ------------------------------------------------------------------ accessors
     @property
@@ -236,28 +239,65 @@ class DINOv2(nn.Module):
         return create_collated_masks(a.mask_ratio_min, a.mask_ratio_max, int(n_crops * a.mask_probability), n_crops, gen)
 
     def training_step_impl(self, batch: Dict[str, Any], batch_idx: int = 0) -> TrainingStepResult:
+        """Loss evaluation + explicit backward (gradients land in the arena / `param.grad`). Eager launch schedule."""
         a = self.method_args
         dev = self.device_
         teacher_temp = linear_warmup_schedule(self.trainer.global_step, a.teacher_temp_warmup_steps,
                                               a.teacher_temp_start, a.teacher_temp_end)
         views: List[Tensor] = batch["views"]
-        n_global = 2
-        n_local = len(views) - n_global
-        g_terms = (n_global - 1) * n_global
-        l_terms = max(n_local * n_global, 1)
-        gv = torch.cat(views[:n_global])
-        n_crops = gv.shape[0]
-        B = n_crops // n_global
+        gv = torch.cat(views[:2])
+        lv = torch.cat(views[2:]) if len(views) > 2 else None
         p = self._patch_size
-        hh, ww = gv.shape[2] // p, gv.shape[3] // p
         masks = batch.get("masks")
         if masks is None:
-            masks = self._masks(n_crops, hh, ww)  # host python RNG, same stream as the reference
+            masks = self._masks(gv.shape[0], gv.shape[2] // p, gv.shape[3] // p)  # host python RNG, reference stream
         collated = masks["collated_masks"].to(dev, non_blocking=True)
         mask_idx = masks["mask_indices_list"].to(dev, non_blocking=True)
         masks_weight = masks["masks_weight"].to(dev, torch.float32, non_blocking=True)
-        M = int(mask_idx.shape[0])
+        for arena in (self.s_arena, self.t_arena):
+            if not arena.bf16_valid:
+                arena.refresh_bf16()
+        if a.center_method == "softmax":
+            self.dino_loss.apply_center_update()
+            self.ibot_loss.apply_center_update()
+        out = self._core(gv, lv, collated.to(torch.uint8), mask_idx, masks_weight, 1.0 / teacher_temp, None, None, None)
+        if a.center_method == "softmax":
+            self.dino_loss._launch_reduce(out["dino_center_sum"], gv.shape[0])
+            if mask_idx.shape[0]:
+                self.ibot_loss._launch_reduce(out["ibot_center_sum"], 1)
+        return self._result(out)
 
+    def _result(self, out: Dict[str, Tensor]) -> TrainingStepResult:
+        a = self.method_args
+        lt, koleo = out["loss_terms"], out["koleo"]
+        dino_global, dino_local, ibot = lt[0], lt[1], lt[2]
+        koleo_loss = koleo.sum()
+        loss = (a.dino_loss_weight * dino_global + a.dino_loss_weight * dino_local + a.ibot_loss_weight * ibot
+                + a.koleo_loss_weight * koleo_loss)
+        self._grad_ready = True
+        return TrainingStepResult(loss=loss, log_dict={
+            "train_loss/dino_global_loss": dino_global, "train_loss/dino_local_loss": dino_local,
+            "train_loss/ibot_loss": ibot, "train_loss/koleo_loss": koleo_loss})
+
+    def _core(self, gv: Tensor, lv: Optional[Tensor], masks_u8: Tensor, mask_idx: Tensor, masks_weight: Tensor,
+              t_scale: float, t_scale_dev: Optional[Tensor], ibot_rowvec: Optional[Tensor],
+              m_valid_dev: Optional[Tensor]) -> Dict[str, Tensor]:
+        """The device schedule of one step.  Shapes depend only on the arguments' shapes, every per-step scalar is
+        either a kernel argument (eager) or read from device memory (`*_dev`), and no host<->device traffic or
+        synchronisation happens inside -- so the whole function can be captured into a CUDA graph.
+        With padding (graph mode) rows >= *m_valid_dev of mask_idx/masks_weight are inert (weight 0)."""
+        a = self.method_args
+        dev = self.device_
+        n_global = 2
+        n_crops = gv.shape[0]
+        B = n_crops // n_global
+        LB = lv.shape[0] if lv is not None else 0
+        n_local = LB // B
+        g_terms = (n_global - 1) * n_global
+        l_terms = max(n_local * n_global, 1)
+        p = self._patch_size
+        hh, ww = gv.shape[2] // p, gv.shape[3] // p
+        M = int(mask_idx.shape[0])
         s_vit, t_vit = self.s_vit, self.t_vit
         s_dino, s_ibot = self.student_head.dino_head, self.student_head.ibot_head
         t_dino, t_ibot = self.teacher_head.dino_head, self.teacher_head.ibot_head
@@ -265,12 +305,10 @@ class DINOv2(nn.Module):
         D, K = s_vit.embed_dim, a.output_dim
         R = s_vit.num_register_tokens
         bf, f32 = torch.bfloat16, torch.float32
-        for arena in (self.s_arena, self.t_arena):
-            if not arena.bf16_valid:
-                arena.refresh_bf16()
         for hd in {id(x): x for x in (s_dino, s_ibot, t_dino, t_ibot)}.values():
             hd.refresh_last_layer()
         self.s_arena.zero_grad()
+        out: Dict[str, Tensor] = {}
 
         # ---------------- teacher (dinov2.py:399-472)
         tctx = t_vit._fwd(gv, None, save=False)
@@ -288,35 +326,35 @@ class DINOv2(nn.Module):
         else:
             t_dino._fwd(t_in, save=False, logits=t_logits)
         del tctx
-        t_scale = 1.0 / teacher_temp
         t_rowterm = torch.empty(n_crops + M, device=dev, dtype=f32)
         colterm_d = torch.empty(K, device=dev, dtype=f32)
         colterm_i = torch.empty(K, device=dev, dtype=f32)
         if a.center_method == "softmax":
-            self.dino_loss.apply_center_update()
-            self.ibot_loss.apply_center_update()
-            ops.vec_op(colterm_d, self.dino_loss.center.view(-1), t_scale, 0.0, 1)
-            ops.vec_op(colterm_i, self.ibot_loss.center.view(-1), t_scale, 0.0, 1)
-            self.dino_loss.reduce_center_update(t_logits[:n_crops])
+            ops.vec_op(colterm_d, self.dino_loss.center.view(-1), t_scale, 0.0, 1, a_dev=t_scale_dev)
+            ops.vec_op(colterm_i, self.ibot_loss.center.view(-1), t_scale, 0.0, 1, a_dev=t_scale_dev)
+            # per-rank center batch sums (reduce_center_update, dinov2_loss.py:139-145 / :274-282)
+            out["dino_center_sum"] = torch.zeros(K, device=dev, dtype=f32)
+            ops.col_reduce(t_logits[:n_crops], out["dino_center_sum"])
+            out["ibot_center_sum"] = torch.zeros(K, device=dev, dtype=f32)
             if M:
-                self.ibot_loss.reduce_center_update(t_logits[n_crops:].unsqueeze(0))
+                rv = ibot_rowvec if ibot_rowvec is not None else torch.full((M,), 1.0 / M, device=dev, dtype=f32)
+                ops.col_reduce(t_logits[n_crops:], out["ibot_center_sum"], rowvec=rv)
         elif a.center_method == "sinkhorn_knopp":
+            if t_scale_dev is not None:
+                raise NotImplementedError("Sinkhorn-Knopp centering runs on the eager schedule (needs mid-step all-reduce)")
             colterm_d = sinkhorn_colterm(t_logits[:n_crops], t_scale)
             if M:
                 colterm_i = sinkhorn_colterm(t_logits[n_crops:], t_scale)
         else:
             raise ValueError(f"Unknown centering method: {a.center_method}")
-        ops.row_lse(t_logits[:n_crops], colterm_d, t_scale, t_rowterm[:n_crops])
+        ops.row_lse(t_logits[:n_crops], colterm_d, t_scale, t_rowterm[:n_crops], scale_dev=t_scale_dev)
         if M:
-            ops.row_lse(t_logits[n_crops:], colterm_i, t_scale, t_rowterm[n_crops:])
+            ops.row_lse(t_logits[n_crops:], colterm_i, t_scale, t_rowterm[n_crops:], scale_dev=t_scale_dev)
 
         # ---------------- student forward (dinov2.py:474-519)
-        sg = s_vit._fwd(gv, collated, save=True, drop_path=True)
+        sg = s_vit._fwd(gv, masks_u8, save=True, drop_path=True)
         sl = None
-        LB = 0
-        if n_local > 0:
-            lv = torch.cat(views[n_global:])
-            LB = lv.shape[0]
+        if lv is not None:
             sl = s_vit._fwd(lv, None, save=True, drop_path=True)
         Rs = n_crops + LB + M
         s_in = torch.empty(Rs, D, device=dev, dtype=bf)
@@ -340,8 +378,7 @@ class DINOv2(nn.Module):
         idx0 = torch.empty(Rs, device=dev, dtype=torch.int32)
         idx1 = torch.full((Rs,), -1, device=dev, dtype=torch.int32)
         wrow = torch.empty(Rs, device=dev, dtype=f32)
-        ar = torch.arange(n_crops, device=dev, dtype=torch.int32)
-        idx0[:n_crops] = ar
+        idx0[:n_crops] = torch.arange(n_crops, device=dev, dtype=torch.int32)
         wrow[:n_crops] = (1.0 / n_crops) * 2.0 / terms
         if LB:
             bidx = torch.arange(LB, device=dev, dtype=torch.int32) % B
@@ -355,11 +392,11 @@ class DINOv2(nn.Module):
         ds = torch.empty(Rs, K, device=dev, dtype=bf)
         s_scale = 1.0 / a.student_temp
         ops.dino_ce(s_logits[:nd], t_logits[:n_crops], colterm_d, t_rowterm[:n_crops], idx0[:nd], idx1[:nd], wrow[:nd],
-                    s_scale, t_scale, loss_rows[:nd], ds[:nd], gscale=a.dino_loss_weight)
+                    s_scale, t_scale, loss_rows[:nd], ds[:nd], gscale=a.dino_loss_weight, t_scale_dev=t_scale_dev)
         if M:
             ops.dino_ce(s_logits[nd:], t_logits[n_crops:], colterm_i, t_rowterm[n_crops:], idx0[nd:], None, wrow[nd:],
-                        s_scale, t_scale, loss_rows[nd:], ds[nd:], gscale=a.ibot_loss_weight)
-        seg = torch.tensor([0, n_crops, nd, Rs], device=dev, dtype=torch.int32)
+                        s_scale, t_scale, loss_rows[nd:], ds[nd:], gscale=a.ibot_loss_weight, t_scale_dev=t_scale_dev)
+        seg = self._segments(n_crops, nd, Rs)
         loss_terms = torch.zeros(3, device=dev, dtype=f32)
         ops.segment_sum(loss_rows, seg, loss_terms)
         del s_logits, t_logits
@@ -374,7 +411,7 @@ class DINOv2(nn.Module):
             dx_d, dx_i = dx_all[:nd], dx_all[nd:]
         ops.scatter_rows(dx_d[:n_crops], cls_rows, dxn_g)
         if M:
-            ops.scatter_rows(dx_i, mask_idx, dxn_g, Np=hh * ww, N=Ng, off=1 + R)
+            ops.scatter_rows(dx_i, mask_idx, dxn_g, Np=hh * ww, N=Ng, off=1 + R, count_dev=m_valid_dev)
         # KoLeo on the pre-head global cls tokens (:377-380): forward value + gradient (+=) into dxn_g
         koleo = torch.zeros(2, device=dev, dtype=f32)
         ops.koleo(sg.xnorm.view(n_crops, Ng, D)[:, 0], 2, B, koleo, dxn_g.view(n_crops, Ng, D)[:, 0],
@@ -385,15 +422,87 @@ class DINOv2(nn.Module):
             s_vit._bwd(sl, dxn_l)
             del sl, dxn_l
         s_vit._bwd(sg, dxn_g)
-        self._grad_ready = True
+        out["loss_terms"], out["koleo"] = loss_terms, koleo
+        return out
 
-        dino_global, dino_local, ibot = loss_terms[0], loss_terms[1], loss_terms[2]
-        koleo_loss = koleo.sum()
-        loss = (a.dino_loss_weight * dino_global + a.dino_loss_weight * dino_local + a.ibot_loss_weight * ibot
-                + a.koleo_loss_weight * koleo_loss)
-        return TrainingStepResult(loss=loss, log_dict={
-            "train_loss/dino_global_loss": dino_global, "train_loss/dino_local_loss": dino_local,
-            "train_loss/ibot_loss": ibot, "train_loss/koleo_loss": koleo_loss})
+    def _segments(self, n_crops: int, nd: int, Rs: int) -> Tensor:
+        key = (n_crops, nd, Rs)
+        if key not in self._seg_cache:
+            self._seg_cache[key] = torch.tensor([0, n_crops, nd, Rs], device=self.device_, dtype=torch.int32)
+        return self._seg_cache[key]
+
+    # ------------------------------------------------------------------ CUDA-graph replay of the step
+    def _graphed_step(self, batch: Dict[str, Any]) -> TrainingStepResult:
+        """Same arithmetic as training_step_impl, replayed from a captured CUDA graph (one graph per padded
+        masked-token count, bucketed to 512): ~1000 kernel launches per step leave the host's critical path."""
+        a = self.method_args
+        dev = self.device_
+        views: List[Tensor] = batch["views"]
+        B = views[0].shape[0]
+        n_local = len(views) - 2
+        p = self._patch_size
+        hh, ww = views[0].shape[2] // p, views[0].shape[3] // p
+        st = self._static
+        if st is None or st["key"] != (B, n_local, tuple(views[0].shape[1:]), tuple(views[-1].shape[1:])):
+            cap_max = max(512, -(-(int(2 * B * a.mask_probability) * int(0.5 * hh * ww)) // 512) * 512)
+            st = self._static = {
+                "key": (B, n_local, tuple(views[0].shape[1:]), tuple(views[-1].shape[1:])),
+                "gv": torch.empty(2 * B, *views[0].shape[1:], device=dev),
+                "lv": torch.empty(n_local * B, *views[-1].shape[1:], device=dev) if n_local else None,
+                "masks_u8": torch.zeros(2 * B, hh * ww, device=dev, dtype=torch.uint8),
+                "idx": torch.zeros(cap_max, device=dev, dtype=torch.int64),
+                "mw": torch.zeros(cap_max, device=dev, dtype=torch.float32),
+                "iw": torch.zeros(cap_max, device=dev, dtype=torch.float32),
+                "m_valid": torch.zeros(1, device=dev, dtype=torch.int32),
+                "t_scale": torch.zeros(1, device=dev, dtype=torch.float32),
+                "graphs": {}, "pool": None,
+            }
+        teacher_temp = linear_warmup_schedule(self.trainer.global_step, a.teacher_temp_warmup_steps,
+                                              a.teacher_temp_start, a.teacher_temp_end)
+        masks = batch.get("masks")
+        if masks is None:
+            masks = self._masks(2 * B, hh, ww)
+        M = int(masks["mask_indices_list"].shape[0])
+        cap = max(512, -(-M // 512) * 512)
+        # stage the step's inputs into the static buffers (device copies for resident views, H2D otherwise)
+        for i in range(2):
+            st["gv"][i * B:(i + 1) * B].copy_(views[i], non_blocking=True)
+        for i in range(n_local):
+            st["lv"][i * B:(i + 1) * B].copy_(views[2 + i], non_blocking=True)
+        st["masks_u8"].copy_(masks["collated_masks"].to(torch.uint8), non_blocking=True)
+        idx_h = torch.zeros(cap, dtype=torch.int64); idx_h[:M] = masks["mask_indices_list"]
+        mw_h = torch.zeros(cap, dtype=torch.float32); mw_h[:M] = masks["masks_weight"]
+        iw_h = torch.zeros(cap, dtype=torch.float32); iw_h[:M] = 1.0 / max(M, 1)
+        st["idx"][:cap].copy_(idx_h, non_blocking=True)
+        st["mw"][:cap].copy_(mw_h, non_blocking=True)
+        st["iw"][:cap].copy_(iw_h, non_blocking=True)
+        st["m_valid"].fill_(M)
+        st["t_scale"].fill_(1.0 / teacher_temp)
+        for arena in (self.s_arena, self.t_arena):
+            if not arena.bf16_valid:
+                arena.refresh_bf16()
+        self.dino_loss.apply_center_update()
+        self.ibot_loss.apply_center_update()
+
+        def run() -> Dict[str, Tensor]:
+            return self._core(st["gv"], st["lv"], st["masks_u8"], st["idx"][:cap], st["mw"][:cap], 0.0, st["t_scale"],
+                              st["iw"][:cap], st["m_valid"])
+
+        entry = st["graphs"].get(cap)
+        if entry is None:
+            run()  # eager warm-up at this shape (also the result of this step)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=st["pool"]):
+                outs = run()
+            if st["pool"] is None:
+                st["pool"] = g.pool()
+            entry = st["graphs"][cap] = (g, outs)
+        g, outs = entry
+        g.replay()
+        self.dino_loss._launch_reduce(outs["dino_center_sum"], 2 * B)
+        self.ibot_loss._launch_reduce(outs["ibot_center_sum"], 1)
+        return self._result(outs)
 
     # ------------------------------------------------------------------ optimizer (+ hooks :588-660) in one sweep
     def optimizer_step(self) -> None:
@@ -433,6 +542,9 @@ class DINOv2(nn.Module):
 
     def train_step(self, batch: Dict[str, Any]) -> TrainingStepResult:
         """One full optimisation step: what Lightning's fit loop does around training_step."""
-        res = self.training_step_impl(batch, 0)
+        if self.use_cuda_graph and self.method_args.center_method == "softmax":
+            res = self._graphed_step(batch)
+        else:
+            res = self.training_step_impl(batch, 0)
         self.optimizer_step()
         return res

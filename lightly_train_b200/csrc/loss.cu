@@ -65,8 +65,10 @@ __device__ __forceinline__ MaxSum block_maxsum(MaxSum v, MaxSum* red) {
 // rowterm[r] = -LSE_k( x[r,k]*scale + colterm[k] )      one CTA per row
 __global__ void __launch_bounds__(LOSS_THREADS) row_lse_kernel(const __nv_bfloat16* __restrict__ x, long long ld,
                                                                 int R, int K, const float* __restrict__ colterm,
-                                                                float scale, float* __restrict__ rowterm) {
+                                                                float scale, const float* __restrict__ scale_dev,
+                                                                float* __restrict__ rowterm) {
   __shared__ MaxSum red[32];
+  if (scale_dev) scale = __ldg(scale_dev);
   const int r = blockIdx.x;
   const __nv_bfloat16* xr = x + (size_t)r * ld;
   MaxSum acc{-INFINITY, 0.f};
@@ -95,8 +97,10 @@ __global__ void __launch_bounds__(LOSS_THREADS) row_lse_kernel(const __nv_bfloat
 //                               mode 1: out[k] += sum_r exp(x[r,k]*scale + rowterm[r])
 // grid = (ceil(K / (256*8)), row_splits); each thread owns 8 columns; atomicAdd at the end.
 __global__ void __launch_bounds__(256) col_reduce_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int R, int K,
-                                                         const float* __restrict__ rowvec, float scale, int mode,
+                                                         const float* __restrict__ rowvec, float scale,
+                                                         const float* __restrict__ scale_dev, int mode,
                                                          float* __restrict__ out) {
+  if (scale_dev) scale = __ldg(scale_dev);
   const int k = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (k >= K) return;
   const int rows_per = (R + gridDim.y - 1) / gridDim.y;
@@ -125,7 +129,9 @@ __global__ void __launch_bounds__(256) col_reduce_kernel(const __nv_bfloat16* __
 // op 0: y = a*x + b*y          (center EMA: center = center*m + mean*(1-m))
 // op 1: y = -a * x             (colterm = -center * t_scale)
 // op 2: y = -log(x) - a        (Sinkhorn: log u = -log(sum) - log K)
-__global__ void vec_op_kernel(float* __restrict__ y, const float* __restrict__ x, int n, float a, float b, int op) {
+__global__ void vec_op_kernel(float* __restrict__ y, const float* __restrict__ x, int n, float a, float b, int op,
+                              const float* __restrict__ a_dev) {
+  if (a_dev) a = __ldg(a_dev);
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (op == 0) y[i] = a * x[i] + b * y[i];
@@ -144,10 +150,11 @@ __global__ void __launch_bounds__(LOSS_THREADS)
 dino_ce_kernel(const __nv_bfloat16* __restrict__ s, long long lds, int Rs, int K, const __nv_bfloat16* __restrict__ t,
                long long ldt, const float* __restrict__ colterm, const float* __restrict__ t_rowterm,
                const int* __restrict__ t_idx0, const int* __restrict__ t_idx1, const float* __restrict__ weight,
-               float s_scale, float t_scale, float gscale, float* __restrict__ loss_rows, __nv_bfloat16* __restrict__ ds,
-               long long ldds) {
+               float s_scale, float t_scale, const float* __restrict__ t_scale_dev, float gscale,
+               float* __restrict__ loss_rows, __nv_bfloat16* __restrict__ ds, long long ldds) {
   __shared__ MaxSum red[32];
   __shared__ float redf[32];
+  if (t_scale_dev) t_scale = __ldg(t_scale_dev);
   const int r = blockIdx.x;
   const float w = weight ? __ldg(weight + r) : 1.f;
   const int i0 = t_idx0[r];
@@ -306,15 +313,15 @@ __global__ void __launch_bounds__(256) koleo_kernel(const float* __restrict__ x,
 using namespace b200;
 
 extern "C" int b200_row_lse(const void* x, long long ld, int R, int K, const float* colterm, float scale,
-                            float* rowterm, void* stream) {
+                            const float* scale_dev, float* rowterm, void* stream) {
   if (!x || !rowterm || R <= 0 || K <= 0 || (K % 8) || (ld % 8)) return B200_ERR_INVALID_ARG;
-  row_lse_kernel<<<R, LOSS_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ld, R, K, colterm, scale, rowterm);
+  row_lse_kernel<<<R, LOSS_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ld, R, K, colterm, scale, scale_dev, rowterm);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
 
-extern "C" int b200_col_reduce(const void* x, long long ld, int R, int K, const float* rowvec, float scale, int mode,
-                               float* out, void* stream) {
+extern "C" int b200_col_reduce(const void* x, long long ld, int R, int K, const float* rowvec, float scale,
+                               const float* scale_dev, int mode, float* out, void* stream) {
   if (!x || !out || R <= 0 || K <= 0 || (K % 8) || (ld % 8) || mode < 0 || mode > 1) return B200_ERR_INVALID_ARG;
   dim3 grid((K / 8 + 255) / 256, 1);
   int target = 148 * 4;
@@ -322,28 +329,28 @@ extern "C" int b200_col_reduce(const void* x, long long ld, int R, int K, const 
   if (splits > R) splits = R;
   if (splits < 1) splits = 1;
   grid.y = splits;
-  col_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ld, R, K, rowvec, scale, mode, out);
+  col_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ld, R, K, rowvec, scale, scale_dev, mode, out);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
 
-extern "C" int b200_vec_op(float* y, const float* x, int n, float a, float b, int op, void* stream) {
+extern "C" int b200_vec_op(float* y, const float* x, int n, float a, float b, int op, const float* a_dev, void* stream) {
   if (!y || !x || n <= 0 || op < 0 || op > 2) return B200_ERR_INVALID_ARG;
-  vec_op_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(y, x, n, a, b, op);
+  vec_op_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(y, x, n, a, b, op, a_dev);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
 
 extern "C" int b200_dino_ce(const void* s, long long lds, int Rs, int K, const void* t, long long ldt,
                             const float* colterm, const float* t_rowterm, const int* t_idx0, const int* t_idx1,
-                            const float* weight, float s_scale, float t_scale, float gscale, float* loss_rows,
-                            void* ds, long long ldds, void* stream) {
+                            const float* weight, float s_scale, float t_scale, const float* t_scale_dev, float gscale,
+                            float* loss_rows, void* ds, long long ldds, void* stream) {
   if (!s || !t || !t_rowterm || !t_idx0 || !loss_rows || Rs <= 0 || K <= 0) return B200_ERR_INVALID_ARG;
   if ((K % 8) || (lds % 8) || (ldt % 8) || (ds && (ldds % 8))) return B200_ERR_INVALID_ARG;
   dino_ce_kernel<<<Rs, LOSS_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)s, lds, Rs, K,
                                                                  (const __nv_bfloat16*)t, ldt, colterm, t_rowterm, t_idx0,
-                                                                 t_idx1, weight, s_scale, t_scale, gscale, loss_rows,
-                                                                 (__nv_bfloat16*)ds, ldds);
+                                                                 t_idx1, weight, s_scale, t_scale, t_scale_dev, gscale,
+                                                                 loss_rows, (__nv_bfloat16*)ds, ldds);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

@@ -59,10 +59,15 @@ struct AdamDev {
   const float* lr_scale; const float* wd_scale; const unsigned char* flags;
   float lr, wd, beta1, beta2, eps, bc1, bc2_sqrt, ema_m, max_norm, grad_scale;
   const float* gradnorm_sq;
+  const float* dyn;
   int freeze_last_layer, freeze_backbone;
 };
 
-__global__ void __launch_bounds__(256) adamw_ema_kernel(const AdamDev a) {
+__global__ void __launch_bounds__(256) adamw_ema_kernel(AdamDev a) {
+  if (a.dyn) {  // per-step scalars from device memory (CUDA-graph replay): see b200_adamw_args.dyn
+    a.lr = a.dyn[0]; a.wd = a.dyn[1]; a.bc1 = a.dyn[2]; a.bc2_sqrt = a.dyn[3]; a.ema_m = a.dyn[4];
+    a.freeze_last_layer = a.dyn[5] != 0.f; a.freeze_backbone = a.dyn[6] != 0.f;
+  }
   float coef = a.grad_scale;
   if (a.gradnorm_sq) {
     // torch.nn.utils.clip_grad_norm_: clip_coef = max_norm / (total_norm + 1e-6), clamped to 1
@@ -155,6 +160,7 @@ extern "C" int b200_adamw_ema(const b200_adamw_args* a, void* stream) {
   d.bc2_sqrt = (float)sqrt(1.0 - pow((double)a->beta2, (double)a->step));
   d.ema_m = a->ema_m; d.max_norm = a->max_norm; d.grad_scale = a->grad_scale;
   d.gradnorm_sq = a->gradnorm_sq;
+  d.dyn = a->dyn;
   d.freeze_last_layer = a->freeze_last_layer; d.freeze_backbone = a->freeze_backbone;
   adamw_ema_kernel<<<sweep_grid(a->n), 256, 0, (cudaStream_t)stream>>>(d);
   B200_CHECK_LAUNCH();

@@ -335,9 +335,10 @@ template <bool IN_BF16>
 __global__ void __launch_bounds__(ROW_THREADS) scatter_rows_kernel(const void* __restrict__ in, long long ldi,
                                                                    const long long* __restrict__ idx, int M, int D, int Np,
                                                                    int N, int off, float* __restrict__ dst, long long ldd,
-                                                                   int accumulate) {
+                                                                   int accumulate, const int* __restrict__ count_dev) {
   const int m = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
   if (m >= M) return;
+  if (count_dev && m >= __ldg(count_dev)) return;  // padded rows of a static-shape (CUDA graph) step
   const int lane = threadIdx.x & 31;
   long long i = idx ? idx[m] : m;
   long long row = Np > 0 ? (i / Np) * N + off + (i % Np) : i;
@@ -568,12 +569,12 @@ extern "C" int b200_gather_rows(const float* src, long long lds, const long long
 }
 
 extern "C" int b200_scatter_rows(const void* in, long long ldi, int in_bf16, const long long* idx, int M, int D, int Np, int N,
-                                 int off, float* dst, long long ldd, int accumulate, void* stream) {
+                                 int off, float* dst, long long ldd, int accumulate, const int* count_dev, void* stream) {
   if (!in || !dst || M < 0 || (D % 4) || (ldi % 4) || (ldd % 4)) return B200_ERR_INVALID_ARG;
   if (M == 0) return B200_OK;
   dim3 grid((M + 7) / 8);
-  if (in_bf16) scatter_rows_kernel<true><<<grid, ROW_THREADS, 0, (cudaStream_t)stream>>>(in, ldi, idx, M, D, Np, N, off, dst, ldd, accumulate);
-  else scatter_rows_kernel<false><<<grid, ROW_THREADS, 0, (cudaStream_t)stream>>>(in, ldi, idx, M, D, Np, N, off, dst, ldd, accumulate);
+  if (in_bf16) scatter_rows_kernel<true><<<grid, ROW_THREADS, 0, (cudaStream_t)stream>>>(in, ldi, idx, M, D, Np, N, off, dst, ldd, accumulate, count_dev);
+  else scatter_rows_kernel<false><<<grid, ROW_THREADS, 0, (cudaStream_t)stream>>>(in, ldi, idx, M, D, Np, N, off, dst, ldd, accumulate, count_dev);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

@@ -15,6 +15,7 @@ from ._lib import (EPI_BF16, EPI_BIAS_GELU, EPI_DGELU, EPI_F32, EPI_F32_ATOMIC, 
 
 
 GEMM_PROFILE = None  # bench.py sets this to a list: (flops, start_event, end_event) per b200_gemm launch
+GEMM_PROFILE_KEYS = []
 
 
 def _stream() -> int:
@@ -73,6 +74,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn: bool = Fa
         check(_lib.lib().b200_gemm(C.byref(args), _stream()), "b200_gemm")
         e1.record()
         GEMM_PROFILE.append((2.0 * M * N * K, e0, e1))
+        GEMM_PROFILE_KEYS.append((M, N, K, int(a_mn), int(b_mn), epi, splits))
         return out
     check(_lib.lib().b200_gemm(C.byref(args), _stream()), "b200_gemm")
     return out
@@ -86,7 +88,7 @@ class AdamWArgs(C.Structure):
         ("lr_scale", C.c_void_p), ("wd_scale", C.c_void_p), ("flags", C.c_void_p),
         ("lr", C.c_float), ("wd", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
         ("step", C.c_int), ("ema_m", C.c_float),
-        ("gradnorm_sq", C.c_void_p), ("max_norm", C.c_float), ("grad_scale", C.c_float),
+        ("gradnorm_sq", C.c_void_p), ("dyn", C.c_void_p), ("max_norm", C.c_float), ("grad_scale", C.c_float),
         ("freeze_last_layer", C.c_int), ("freeze_backbone", C.c_int),
     ]
 
@@ -161,10 +163,11 @@ def gather_rows(src, idx, out, Np: int = 0, N: int = 0, off: int = 0) -> None:
                                 out.stride(0), int(out.dtype == torch.bfloat16), _stream()), "b200_gather_rows")
 
 
-def scatter_rows(inp, idx, dst, Np: int = 0, N: int = 0, off: int = 0, accumulate: bool = False) -> None:
+def scatter_rows(inp, idx, dst, Np: int = 0, N: int = 0, off: int = 0, accumulate: bool = False, count_dev=None) -> None:
     M, D = inp.shape
     check(_L().b200_scatter_rows(inp.data_ptr(), inp.stride(0), int(inp.dtype == torch.bfloat16), _ptr(idx), M, D, Np, N,
-                                 off, dst.data_ptr(), dst.stride(0), int(accumulate), _stream()), "b200_scatter_rows")
+                                 off, dst.data_ptr(), dst.stride(0), int(accumulate), _ptr(count_dev), _stream()),
+          "b200_scatter_rows")
 
 
 def l2norm_fwd(x, y, nrm, eps: float = 1e-12) -> None:
@@ -207,27 +210,27 @@ def fill_f32(x, v: float = 0.0) -> None:
     check(_L().b200_fill_f32(x.data_ptr(), x.numel(), v, _stream()), "b200_fill_f32")
 
 
-def row_lse(x, colterm, scale: float, rowterm) -> None:
+def row_lse(x, colterm, scale: float, rowterm, scale_dev=None) -> None:
     R, K = x.shape
-    check(_L().b200_row_lse(x.data_ptr(), x.stride(0), R, K, _ptr(colterm), scale, rowterm.data_ptr(), _stream()),
-          "b200_row_lse")
+    check(_L().b200_row_lse(x.data_ptr(), x.stride(0), R, K, _ptr(colterm), scale, _ptr(scale_dev), rowterm.data_ptr(),
+                            _stream()), "b200_row_lse")
 
 
-def col_reduce(x, out, rowvec=None, scale: float = 1.0, mode: int = 0) -> None:
+def col_reduce(x, out, rowvec=None, scale: float = 1.0, mode: int = 0, scale_dev=None) -> None:
     R, K = x.shape
-    check(_L().b200_col_reduce(x.data_ptr(), x.stride(0), R, K, _ptr(rowvec), scale, mode, out.data_ptr(), _stream()),
-          "b200_col_reduce")
+    check(_L().b200_col_reduce(x.data_ptr(), x.stride(0), R, K, _ptr(rowvec), scale, _ptr(scale_dev), mode, out.data_ptr(),
+                               _stream()), "b200_col_reduce")
 
 
-def vec_op(y, x, a: float, b: float, op: int) -> None:
-    check(_L().b200_vec_op(y.data_ptr(), x.data_ptr(), y.numel(), a, b, op, _stream()), "b200_vec_op")
+def vec_op(y, x, a: float, b: float, op: int, a_dev=None) -> None:
+    check(_L().b200_vec_op(y.data_ptr(), x.data_ptr(), y.numel(), a, b, op, _ptr(a_dev), _stream()), "b200_vec_op")
 
 
 def dino_ce(s, t, colterm, t_rowterm, t_idx0, t_idx1, weight, s_scale: float, t_scale: float, loss_rows, ds=None,
-            gscale: float = 1.0) -> None:
+            gscale: float = 1.0, t_scale_dev=None) -> None:
     Rs, K = s.shape
     check(_L().b200_dino_ce(s.data_ptr(), s.stride(0), Rs, K, t.data_ptr(), t.stride(0), _ptr(colterm),
-                            t_rowterm.data_ptr(), t_idx0.data_ptr(), _ptr(t_idx1), _ptr(weight), s_scale, t_scale, gscale,
+                            t_rowterm.data_ptr(), t_idx0.data_ptr(), _ptr(t_idx1), _ptr(weight), s_scale, t_scale, _ptr(t_scale_dev), gscale,
                             loss_rows.data_ptr(), _ptr(ds), ds.stride(0) if ds is not None else 0, _stream()),
           "b200_dino_ce")
 
