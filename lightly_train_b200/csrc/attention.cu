@@ -16,7 +16,6 @@
 
 namespace b200 {
 
-static constexpr int ATT_THREADS = 128;
 static constexpr int HD = 64;
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int bytes) {
@@ -66,7 +65,7 @@ __device__ __forceinline__ uint32_t addr_Bt(uint32_t tile, int k0, int dp, int l
 
 // load a [N x 64] bf16 panel (row pitch ld) into a swizzled smem tile of NP rows, zero-filling rows >= N
 __device__ __forceinline__ void load_panel(uint32_t tile, const __nv_bfloat16* src, long long ld, int N, int NP) {
-  for (int i = threadIdx.x; i < NP * 8; i += ATT_THREADS) {
+  for (int i = threadIdx.x; i < NP * 8; i += blockDim.x) {
     const int row = i >> 3, chunk = i & 7;
     const bool ok = row < N;
     cp_async16(tile + tile_off(row, chunk), ok ? (const void*)(src + (size_t)row * ld + chunk * 8) : (const void*)src, ok ? 16 : 0);
@@ -96,8 +95,8 @@ __device__ __forceinline__ void store_tile(const float (&o)[8][4], float mul, ui
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int NKV16>
-__global__ void __launch_bounds__(ATT_THREADS)
+template <int NKV16, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, int N, int h, float scale,
                 __nv_bfloat16* __restrict__ out, long long ld_out, float* __restrict__ lse) {
   constexpr int NP = NKV16 * 16;
@@ -114,7 +113,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, int N, 
   __syncthreads();
 
   const int nqt = (N + 15) / 16;
-  for (int qt = warp; qt < nqt; qt += ATT_THREADS / 32) {
+  for (int qt = warp; qt < nqt; qt += WARPS) {
     uint32_t aq[4][4];
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) ldsm_x4(aq[ks], addr_A(sQ, qt * 16, ks, lane));
@@ -186,8 +185,8 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, int N, 
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int NKV16>
-__global__ void __launch_bounds__(ATT_THREADS)
+template <int NKV16, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
 attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, const __nv_bfloat16* __restrict__ o,
                 const __nv_bfloat16* __restrict__ dout, long long ld_out, const float* __restrict__ lse, int N, int h,
                 float scale, __nv_bfloat16* __restrict__ dqkv, long long ld_dtok) {
@@ -195,7 +194,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, const _
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sQ = smem_u32(smem), sK = sQ + NP * 128, sV = sK + NP * 128, sDO = sV + NP * 128;
   uint8_t* stage_base = smem + 4 * NP * 128;
-  float* sL = reinterpret_cast<float*>(stage_base + 4 * 2048);
+  float* sL = reinterpret_cast<float*>(stage_base + WARPS * 2048);
   float* sD = sL + NP;
   const int bh = blockIdx.x, b = bh / h, head = bh % h;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -207,7 +206,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, const _
   load_panel(sV, base + (size_t)2 * h * HD, ld_tok, N, NP);
   load_panel(sDO, dob, ld_out, N, NP);
   // D_i = sum_d dO[i,d] * O[i,d]  (== sum_j dP_ij P_ij), one warp per row, 2 elements per lane
-  for (int r = warp; r < NP; r += ATT_THREADS / 32) {
+  for (int r = warp; r < NP; r += WARPS) {
     float acc = 0.f;
     if (r < N) {
       float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dob + (size_t)r * ld_out + lane * 2));
@@ -227,7 +226,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, const _
   uint8_t* stage = stage_base + warp * 2048;
 
   // ---------------- phase A: dQ, one 16-row query tile per warp iteration ----------------
-  for (int qt = warp; qt < nt; qt += ATT_THREADS / 32) {
+  for (int qt = warp; qt < nt; qt += WARPS) {
     uint32_t aq[4][4], ado[4][4];
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
@@ -278,7 +277,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, const _
   }
 
   // ---------------- phase B: dK, dV, one 16-row key tile per warp iteration ----------------
-  for (int kt = warp; kt < nt; kt += ATT_THREADS / 32) {
+  for (int kt = warp; kt < nt; kt += WARPS) {
     uint32_t ak[4][4], av[4][4];
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
@@ -337,34 +336,34 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, const _
   }
 }
 
-template <int NKV16>
+template <int NKV16, int WARPS>
 static int launch_fwd(const void* qkv, long long ld_tok, int B, int N, int h, float scale, void* out, long long ld_out,
                       float* lse, cudaStream_t s) {
   constexpr int NP = NKV16 * 16;
-  const int smem = 3 * NP * 128 + 4 * 2048;
+  const int smem = 3 * NP * 128 + WARPS * 2048;
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(attn_fwd_kernel<NKV16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(attn_fwd_kernel<NKV16, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return B200_ERR_CUDA;
     attr = true;
   }
-  attn_fwd_kernel<NKV16><<<B * h, ATT_THREADS, smem, s>>>((const __nv_bfloat16*)qkv, ld_tok, N, h, scale,
+  attn_fwd_kernel<NKV16, WARPS><<<B * h, WARPS * 32, smem, s>>>((const __nv_bfloat16*)qkv, ld_tok, N, h, scale,
                                                           (__nv_bfloat16*)out, ld_out, lse);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
-template <int NKV16>
+template <int NKV16, int WARPS>
 static int launch_bwd(const void* qkv, long long ld_tok, const void* o, const void* dout, long long ld_out, const float* lse,
                       int B, int N, int h, float scale, void* dqkv, long long ld_dtok, cudaStream_t s) {
   constexpr int NP = NKV16 * 16;
-  const int smem = 4 * NP * 128 + 4 * 2048 + 2 * NP * 4;
+  const int smem = 4 * NP * 128 + WARPS * 2048 + 2 * NP * 4;
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(attn_bwd_kernel<NKV16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(attn_bwd_kernel<NKV16, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return B200_ERR_CUDA;
     attr = true;
   }
-  attn_bwd_kernel<NKV16><<<B * h, ATT_THREADS, smem, s>>>((const __nv_bfloat16*)qkv, ld_tok, (const __nv_bfloat16*)o,
+  attn_bwd_kernel<NKV16, WARPS><<<B * h, WARPS * 32, smem, s>>>((const __nv_bfloat16*)qkv, ld_tok, (const __nv_bfloat16*)o,
                                                           (const __nv_bfloat16*)dout, ld_out, lse, N, h, scale,
                                                           (__nv_bfloat16*)dqkv, ld_dtok);
   B200_CHECK_LAUNCH();
@@ -381,10 +380,10 @@ extern "C" int b200_attention_fwd(const void* qkv, long long ld_tok, int B, int 
   if (head_dim != HD || (ld_tok % 8) || (ld_out % 8)) return B200_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
   const int nb = (N + 15) / 16;
-  if (nb <= 3) return launch_fwd<3>(qkv, ld_tok, B, N, h, scale, out, ld_out, lse, s);
-  if (nb <= 4) return launch_fwd<4>(qkv, ld_tok, B, N, h, scale, out, ld_out, lse, s);
-  if (nb <= 13) return launch_fwd<13>(qkv, ld_tok, B, N, h, scale, out, ld_out, lse, s);
-  if (nb <= 17) return launch_fwd<17>(qkv, ld_tok, B, N, h, scale, out, ld_out, lse, s);
+  if (nb <= 3) return launch_fwd<3, 4>(qkv, ld_tok, B, N, h, scale, out, ld_out, lse, s);
+  if (nb <= 4) return launch_fwd<4, 4>(qkv, ld_tok, B, N, h, scale, out, ld_out, lse, s);
+  if (nb <= 13) return launch_fwd<13, 4>(qkv, ld_tok, B, N, h, scale, out, ld_out, lse, s);
+  if (nb <= 17) return launch_fwd<17, 4>(qkv, ld_tok, B, N, h, scale, out, ld_out, lse, s);
   return B200_ERR_UNSUPPORTED;
 }
 
@@ -395,9 +394,9 @@ extern "C" int b200_attention_bwd(const void* qkv, long long ld_tok, const void*
   if (head_dim != HD || (ld_tok % 8) || (ld_out % 8) || (ld_dtok % 8)) return B200_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
   const int nb = (N + 15) / 16;
-  if (nb <= 3) return launch_bwd<3>(qkv, ld_tok, out, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
-  if (nb <= 4) return launch_bwd<4>(qkv, ld_tok, out, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
-  if (nb <= 13) return launch_bwd<13>(qkv, ld_tok, out, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
-  if (nb <= 17) return launch_bwd<17>(qkv, ld_tok, out, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
+  if (nb <= 3) return launch_bwd<3, 4>(qkv, ld_tok, out, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
+  if (nb <= 4) return launch_bwd<4, 4>(qkv, ld_tok, out, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
+  if (nb <= 13) return launch_bwd<13, 8>(qkv, ld_tok, out, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
+  if (nb <= 17) return launch_bwd<17, 8>(qkv, ld_tok, out, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
   return B200_ERR_UNSUPPORTED;
 }

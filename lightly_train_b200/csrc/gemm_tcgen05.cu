@@ -30,10 +30,11 @@ struct GemmCfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BLOCK_N <= 128) ? 6 : (BLOCK_N <= 192 ? 5 : 4);
+  static constexpr int STAGES = (BLOCK_N <= 128) ? 5 : 4;
   static constexpr int ACC_STRIDE = 256;  // TMEM columns between the two accumulator buffers
   static constexpr int TMEM_COLS = 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int EPI_STAGING_BYTES = NUM_EPI_WARPS * 32 * 32 * 4;  // one 32x32 fp32 transpose tile per warp
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct GemmDev {
@@ -82,122 +83,53 @@ __device__ __forceinline__ uint32_t make_idesc(int n, int a_mn, int b_mn) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Epilogue for one 32-column chunk of one output row held in registers.
-__device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t (&acc)[32], int row,
-                                               int col0) {
-  if (row >= p.M || col0 >= p.N) return;
-  const int ncols = min(32, p.N - col0);  // multiple of 8 (N % 8 == 0 enforced on host)
-  float v[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) * p.alpha;
-  if (p.bias != nullptr) {
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      if (i < ncols) {
-        float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
-        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-      }
-    }
-  }
+// Epilogue for 4 consecutive columns of one output row (after the smem transpose: a warp instruction covers
+// 4 rows x 32 columns, i.e. full 128-byte lines of fp32 or 64-byte runs of bf16 -- coalesced loads and stores).
+__device__ __forceinline__ void epilogue_vec4(const GemmDev& p, float4 acc, int row, int col, const float4& bias4,
+                                              const float4& gamma4) {
+  float v0 = acc.x * p.alpha + bias4.x, v1 = acc.y * p.alpha + bias4.y, v2 = acc.z * p.alpha + bias4.z,
+        v3 = acc.w * p.alpha + bias4.w;
   switch (p.epi) {
     case B200_EPI_BF16: {
-      __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0;
-#pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        if (i < ncols) {
-          uint4 o;
-          o.x = pack_bf16x2(v[i], v[i + 1]); o.y = pack_bf16x2(v[i + 2], v[i + 3]);
-          o.z = pack_bf16x2(v[i + 4], v[i + 5]); o.w = pack_bf16x2(v[i + 6], v[i + 7]);
-          *reinterpret_cast<uint4*>(c + i) = o;
-        }
-      }
+      uint2 o; o.x = pack_bf16x2(v0, v1); o.y = pack_bf16x2(v2, v3);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col) = o;
     } break;
     case B200_EPI_F32: {
-      float* c = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
-#pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        if (i < ncols) *reinterpret_cast<float4*>(c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-      }
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col) = make_float4(v0, v1, v2, v3);
     } break;
     case B200_EPI_F32_ATOMIC: {
-      float* c = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
-#pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        if (i < ncols) atomicAdd(reinterpret_cast<float4*>(c + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
-      }
+      atomicAdd(reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col), make_float4(v0, v1, v2, v3));
     } break;
     case B200_EPI_BIAS_GELU: {
       // u = bf16(acc + bias) (what nn.Linear returns under bf16 autocast); h = bf16(gelu(u))
-      __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0;
-      __nv_bfloat16* c2 = p.C2 ? reinterpret_cast<__nv_bfloat16*>(p.C2) + (size_t)row * p.ldc2 + col0 : nullptr;
-#pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        if (i < ncols) {
-          float u[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) u[j] = bf16_round(v[i + j]);
-          if (c2) {
-            uint4 o;
-            o.x = pack_bf16x2(u[0], u[1]); o.y = pack_bf16x2(u[2], u[3]);
-            o.z = pack_bf16x2(u[4], u[5]); o.w = pack_bf16x2(u[6], u[7]);
-            *reinterpret_cast<uint4*>(c2 + i) = o;
-          }
-          uint4 o;
-          o.x = pack_bf16x2(gelu_erf(u[0]), gelu_erf(u[1])); o.y = pack_bf16x2(gelu_erf(u[2]), gelu_erf(u[3]));
-          o.z = pack_bf16x2(gelu_erf(u[4]), gelu_erf(u[5])); o.w = pack_bf16x2(gelu_erf(u[6]), gelu_erf(u[7]));
-          *reinterpret_cast<uint4*>(c + i) = o;
-        }
+      const float u0 = bf16_round(v0), u1 = bf16_round(v1), u2 = bf16_round(v2), u3 = bf16_round(v3);
+      if (p.C2) {
+        uint2 o; o.x = pack_bf16x2(u0, u1); o.y = pack_bf16x2(u2, u3);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C2) + (size_t)row * p.ldc2 + col) = o;
       }
+      uint2 o; o.x = pack_bf16x2(gelu_erf(u0), gelu_erf(u1)); o.y = pack_bf16x2(gelu_erf(u2), gelu_erf(u3));
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col) = o;
     } break;
     case B200_EPI_RESIDUAL: {
       // o = bf16(acc + bias); x_out = x_in + gamma * o * rowscale   (fp32 residual stream)
-      float* c = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
-      const float* xin = reinterpret_cast<const float*>(p.aux) + (size_t)row * p.ldaux + col0;
-      __nv_bfloat16* c2 = p.C2 ? reinterpret_cast<__nv_bfloat16*>(p.C2) + (size_t)row * p.ldc2 + col0 : nullptr;
-      const float rs = p.rowscale ? __ldg(p.rowscale + row / p.rows_per_scale) : 1.0f;
-#pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        if (i < ncols) {
-          float o[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = bf16_round(v[i + j]);
-          if (c2) {
-            uint4 ob;
-            ob.x = pack_bf16x2(o[0], o[1]); ob.y = pack_bf16x2(o[2], o[3]);
-            ob.z = pack_bf16x2(o[4], o[5]); ob.w = pack_bf16x2(o[6], o[7]);
-            *reinterpret_cast<uint4*>(c2 + i) = ob;
-          }
-          float4 g0 = make_float4(1.f, 1.f, 1.f, 1.f), g1 = g0;
-          if (p.gamma) {
-            g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + col0 + i));
-            g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + col0 + i + 4));
-          }
-          float4 x0 = *reinterpret_cast<const float4*>(xin + i);
-          float4 x1 = *reinterpret_cast<const float4*>(xin + i + 4);
-          x0.x += (o[0] * g0.x) * rs; x0.y += (o[1] * g0.y) * rs; x0.z += (o[2] * g0.z) * rs; x0.w += (o[3] * g0.w) * rs;
-          x1.x += (o[4] * g1.x) * rs; x1.y += (o[5] * g1.y) * rs; x1.z += (o[6] * g1.z) * rs; x1.w += (o[7] * g1.w) * rs;
-          *reinterpret_cast<float4*>(c + i) = x0;
-          *reinterpret_cast<float4*>(c + i + 4) = x1;
-        }
+      const float o0 = bf16_round(v0), o1 = bf16_round(v1), o2 = bf16_round(v2), o3 = bf16_round(v3);
+      if (p.C2) {
+        uint2 o; o.x = pack_bf16x2(o0, o1); o.y = pack_bf16x2(o2, o3);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C2) + (size_t)row * p.ldc2 + col) = o;
       }
+      const float rs = p.rowscale ? __ldg(p.rowscale + row / p.rows_per_scale) : 1.0f;
+      float4 x = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) + (size_t)row * p.ldaux + col);
+      x.x += (o0 * gamma4.x) * rs; x.y += (o1 * gamma4.y) * rs; x.z += (o2 * gamma4.z) * rs; x.w += (o3 * gamma4.w) * rs;
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col) = x;
     } break;
     case B200_EPI_DGELU: {
       // dU = bf16( bf16(acc) * gelu'(u) ), u = aux (bf16 pre-activation saved by the forward)
-      __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0;
-      const __nv_bfloat16* up = reinterpret_cast<const __nv_bfloat16*>(p.aux) + (size_t)row * p.ldaux + col0;
-#pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        if (i < ncols) {
-          uint4 ub = *reinterpret_cast<const uint4*>(up + i);
-          float2 u0 = unpack_bf16x2(ub.x), u1 = unpack_bf16x2(ub.y), u2 = unpack_bf16x2(ub.z), u3 = unpack_bf16x2(ub.w);
-          uint4 o;
-          o.x = pack_bf16x2(bf16_round(v[i]) * gelu_erf_grad(u0.x), bf16_round(v[i + 1]) * gelu_erf_grad(u0.y));
-          o.y = pack_bf16x2(bf16_round(v[i + 2]) * gelu_erf_grad(u1.x), bf16_round(v[i + 3]) * gelu_erf_grad(u1.y));
-          o.z = pack_bf16x2(bf16_round(v[i + 4]) * gelu_erf_grad(u2.x), bf16_round(v[i + 5]) * gelu_erf_grad(u2.y));
-          o.w = pack_bf16x2(bf16_round(v[i + 6]) * gelu_erf_grad(u3.x), bf16_round(v[i + 7]) * gelu_erf_grad(u3.y));
-          *reinterpret_cast<uint4*>(c + i) = o;
-        }
-      }
+      const uint2 ub = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + (size_t)row * p.ldaux + col);
+      const float2 ua = unpack_bf16x2(ub.x), uc = unpack_bf16x2(ub.y);
+      uint2 o;
+      o.x = pack_bf16x2(bf16_round(v0) * gelu_erf_grad(ua.x), bf16_round(v1) * gelu_erf_grad(ua.y));
+      o.y = pack_bf16x2(bf16_round(v2) * gelu_erf_grad(uc.x), bf16_round(v3) * gelu_erf_grad(uc.y));
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col) = o;
     } break;
     default: break;
   }
@@ -213,7 +145,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   // swizzle-128B operand tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  float* epi_staging = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_STAGING_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -344,14 +277,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int n0 = (tile / tiles_m) * BLOCK_N;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int row = m0 + quarter * 32 + lane;
+      float* stg = epi_staging + ew * (32 * 32);
+      const int sub_row = lane >> 3;        // 0..3 : row within a 4-row group after the transpose
+      const int g4 = lane & 7;              // 0..7 : which float4 (4 columns) of the 32-column chunk
 #pragma unroll 1
       for (int c = 0; c < COLS_PER_WARP; c += 32) {
         const int col_in_tile = half * COLS_PER_WARP + c;
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * Cfg::ACC_STRIDE + col_in_tile, v);
         tmem_ld_wait();
-        epilogue_chunk(p, v, row, n0 + col_in_tile);
+        // transpose through smem: thread (= row `lane`) writes its 32 columns; XOR swizzle keeps both the
+        // row-wise float4 writes and the column-group reads bank-conflict free
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        const int col = n0 + col_in_tile + g4 * 4;
+        if (col < p.N) {  // N % 8 == 0 and col % 4 == 0 -> the 4 columns are all valid
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), gamma4 = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+          if (p.gamma) gamma4 = __ldg(reinterpret_cast<const float4*>(p.gamma + col));
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + sub_row;
+            const int row = m0 + quarter * 32 + r;
+            const float4 a4 = *reinterpret_cast<const float4*>(stg + r * 32 + ((g4 ^ (r & 7)) << 2));
+            if (row < p.M) epilogue_vec4(p, a4, row, col, bias4, gamma4);
+          }
+        }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();

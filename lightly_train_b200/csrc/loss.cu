@@ -95,33 +95,56 @@ __global__ void __launch_bounds__(LOSS_THREADS) row_lse_kernel(const __nv_bfloat
 // ------------------------------------------------------------------------------------------------
 // Column reductions over rows.  mode 0: out[k] += sum_r x[r,k] * rowweight[r]   (rowweight NULL -> 1)
 //                               mode 1: out[k] += sum_r exp(x[r,k]*scale + rowterm[r])
-// grid = (ceil(K / (256*8)), row_splits); each thread owns 8 columns; atomicAdd at the end.
-__global__ void __launch_bounds__(256) col_reduce_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int R, int K,
-                                                         const float* __restrict__ rowvec, float scale,
-                                                         const float* __restrict__ scale_dev, int mode,
-                                                         float* __restrict__ out) {
+// A CTA owns a slab of `cg` column groups (8 columns = one 16-byte load each) and a contiguous range of rows;
+// its threads are arranged [row lanes][column groups] so every warp load is a run of consecutive 16-byte
+// pieces of one or two rows (coalesced), 4 rows in flight per thread.  Row lanes are combined through smem,
+// then one atomicAdd per column per CTA.
+static constexpr int CR_THREADS = 512;
+__global__ void __launch_bounds__(CR_THREADS) col_reduce_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int R, int K,
+                                                                int cg, int rows_per_cta, const float* __restrict__ rowvec,
+                                                                float scale, const float* __restrict__ scale_dev, int mode,
+                                                                float* __restrict__ out) {
+  extern __shared__ float cr_sm[];  // [lanes][cg*8]
   if (scale_dev) scale = __ldg(scale_dev);
-  const int k = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
-  if (k >= K) return;
-  const int rows_per = (R + gridDim.y - 1) / gridDim.y;
-  const int r0 = blockIdx.y * rows_per;
-  const int r1 = min(R, r0 + rows_per);
+  const int lanes = CR_THREADS / cg;
+  const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
+  const int k = (blockIdx.x * cg + g) * 8;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(R, r0 + rows_per_cta);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int r = r0; r < r1; ++r) {
-    float v[8];
-    load8(x + (size_t)r * ld + k, v);
-    if (mode == 0) {
-      const float w = rowvec ? __ldg(rowvec + r) : 1.f;
+  if (lane < lanes && k < K) {
+    int r = r0 + lane;
+    for (; r + 3 * lanes < r1; r += 4 * lanes) {
+      float v[4][8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += v[i] * w;
-    } else {
-      const float rt = rowvec ? __ldg(rowvec + r) : 0.f;
+      for (int u = 0; u < 4; ++u) load8(x + (size_t)(r + u * lanes) * ld + k, v[u]);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += __expf(v[i] * scale + rt);
+      for (int u = 0; u < 4; ++u) {
+        const float w = rowvec ? __ldg(rowvec + r + u * lanes) : (mode == 0 ? 1.f : 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += (mode == 0) ? v[u][i] * w : __expf(v[u][i] * scale + w);
+      }
+    }
+    for (; r < r1; r += lanes) {
+      float v[8];
+      load8(x + (size_t)r * ld + k, v);
+      const float w = rowvec ? __ldg(rowvec + r) : (mode == 0 ? 1.f : 0.f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += (mode == 0) ? v[i] * w : __expf(v[i] * scale + w);
     }
   }
+  if (lane < lanes) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) atomicAdd(out + k + i, acc[i]);
+    for (int i = 0; i < 8; ++i) cr_sm[(size_t)lane * cg * 8 + g * 8 + i] = acc[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < cg * 8; c += CR_THREADS) {
+    const int kk = blockIdx.x * cg * 8 + c;
+    if (kk < K) {
+      float t = 0.f;
+      for (int l = 0; l < lanes; ++l) t += cr_sm[(size_t)l * cg * 8 + c];
+      atomicAdd(out + kk, t);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -323,13 +346,19 @@ extern "C" int b200_row_lse(const void* x, long long ld, int R, int K, const flo
 extern "C" int b200_col_reduce(const void* x, long long ld, int R, int K, const float* rowvec, float scale,
                                const float* scale_dev, int mode, float* out, void* stream) {
   if (!x || !out || R <= 0 || K <= 0 || (K % 8) || (ld % 8) || mode < 0 || mode > 1) return B200_ERR_INVALID_ARG;
-  dim3 grid((K / 8 + 255) / 256, 1);
-  int target = 148 * 4;
-  int splits = (target + grid.x - 1) / grid.x;
-  if (splits > R) splits = R;
-  if (splits < 1) splits = 1;
-  grid.y = splits;
-  col_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ld, R, K, rowvec, scale, scale_dev, mode, out);
+  const int groups = K / 8;
+  const int gx = (groups + 127) / 128;            // <= 128 column groups (1024 columns) per CTA, evenly split
+  const int cg = (groups + gx - 1) / gx;
+  int gy = (148 * 2 + gx - 1) / gx;                // ~2 CTAs per SM in total
+  const int lanes = CR_THREADS / cg;
+  const int min_rows = lanes * 8;
+  if ((long long)gy * min_rows > R) gy = (R + min_rows - 1) / min_rows;
+  if (gy < 1) gy = 1;
+  const int rows_per_cta = (R + gy - 1) / gy;
+  gy = (R + rows_per_cta - 1) / rows_per_cta;
+  const size_t smem = (size_t)lanes * cg * 8 * sizeof(float);
+  col_reduce_kernel<<<dim3(gx, gy), CR_THREADS, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ld, R, K, cg, rows_per_cta,
+                                                                                rowvec, scale, scale_dev, mode, out);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

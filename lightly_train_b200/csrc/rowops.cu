@@ -17,7 +17,7 @@ static constexpr int MAXV = 8;           // float4 chunks per lane -> D <= 1024
 
 // ------------------------------------------------------------------------------------------------
 // LayerNorm forward: x f32 [T,D] -> y (bf16 or f32) ; saves mean, rstd.
-template <bool OUT_BF16>
+template <bool OUT_BF16, int VMAX>
 __global__ void __launch_bounds__(ROW_THREADS) ln_fwd_kernel(const float* __restrict__ x, long long ldx, int T, int D,
                                                              const float* __restrict__ w, const float* __restrict__ b,
                                                              float eps, void* __restrict__ y, long long ldy,
@@ -27,17 +27,17 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_fwd_kernel(const float* __rest
   const int lane = threadIdx.x & 31;
   const int nv = D >> 2;
   const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ldx);
-  float4 v[MAXV];
+  float4 v[VMAX];
   float s = 0.f;
 #pragma unroll
-  for (int j = 0; j < MAXV; ++j) {
+  for (int j = 0; j < VMAX; ++j) {
     int c = lane + 32 * j;
     if (c < nv) { v[j] = xr[c]; s += v[j].x + v[j].y + v[j].z + v[j].w; }
   }
   const float mu = warp_sum(s) / D;
   float q = 0.f;
 #pragma unroll
-  for (int j = 0; j < MAXV; ++j) {
+  for (int j = 0; j < VMAX; ++j) {
     int c = lane + 32 * j;
     if (c < nv) {
       float a = v[j].x - mu, bb = v[j].y - mu, cc = v[j].z - mu, d = v[j].w - mu;
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_fwd_kernel(const float* __rest
   const float rs = rsqrtf(warp_sum(q) / D + eps);
   if (lane == 0) { if (mean) mean[row] = mu; if (rstd) rstd[row] = rs; }
 #pragma unroll
-  for (int j = 0; j < MAXV; ++j) {
+  for (int j = 0; j < VMAX; ++j) {
     int c = lane + 32 * j;
     if (c < nv) {
       float4 ww = __ldg(reinterpret_cast<const float4*>(w) + c);
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_fwd_kernel(const float* __rest
 
 // LayerNorm backward.  dy (bf16 or f32) = grad wrt LN output.  dx: f32, accumulate (+=) or assign.
 // dw/db: per-CTA partials reduced through smem, then atomicAdd into global [D].
-template <bool DY_BF16>
+template <bool DY_BF16, int VMAX>
 __global__ void __launch_bounds__(ROW_THREADS) ln_bwd_kernel(const void* __restrict__ dy, long long lddy,
                                                              const float* __restrict__ x, long long ldx, int T, int D,
                                                              const float* __restrict__ w, const float* __restrict__ mean,
@@ -79,16 +79,16 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_bwd_kernel(const void* __restr
   const int nv = D >> 2;
   for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
-  float4 aw[MAXV], ab[MAXV];
+  float4 aw[VMAX], ab[VMAX];
 #pragma unroll
-  for (int j = 0; j < MAXV; ++j) { aw[j] = make_float4(0, 0, 0, 0); ab[j] = make_float4(0, 0, 0, 0); }
+  for (int j = 0; j < VMAX; ++j) { aw[j] = make_float4(0, 0, 0, 0); ab[j] = make_float4(0, 0, 0, 0); }
   for (int row = blockIdx.x * (ROW_THREADS / 32) + warp; row < T; row += gridDim.x * (ROW_THREADS / 32)) {
     const float mu = mean[row], rs = rstd[row];
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ldx);
-    float4 g[MAXV], xh[MAXV];
+    float4 g[VMAX], xh[VMAX];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int j = 0; j < MAXV; ++j) {
+    for (int j = 0; j < VMAX; ++j) {
       int c = lane + 32 * j;
       if (c < nv) {
         float4 d;
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_bwd_kernel(const void* __restr
     s2 = warp_sum(s2) / D;
     float4* dxr = reinterpret_cast<float4*>(dx + (size_t)row * lddx);
 #pragma unroll
-    for (int j = 0; j < MAXV; ++j) {
+    for (int j = 0; j < VMAX; ++j) {
       int c = lane + 32 * j;
       if (c < nv) {
         float4 o;
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_bwd_kernel(const void* __restr
   }
   if (dw) {
 #pragma unroll
-    for (int j = 0; j < MAXV; ++j) {
+    for (int j = 0; j < VMAX; ++j) {
       int c = lane + 32 * j;
       if (c < nv) {
         atomicAdd(&sm[4 * c + 0], aw[j].x); atomicAdd(&sm[4 * c + 1], aw[j].y);
@@ -256,6 +256,7 @@ __global__ void assemble_tokens_bwd_kernel(const float* __restrict__ dx, const u
 // LayerScale backward: o bf16 [T,D] (branch output saved by the forward), dx f32 [T,D] (grad of the residual
 // stream), gamma [D], rowscale (per-sample DropPath scale) ->
 //   do bf16 = bf16(dx * rowscale * gamma) ; dgamma[d] += sum_t dx*rowscale*o ; dbias[d] += sum_t do
+template <int VMAX>
 __global__ void __launch_bounds__(ROW_THREADS) layerscale_bwd_kernel(const float* __restrict__ dx, long long lddx,
                                                                      const __nv_bfloat16* __restrict__ o, long long ldo,
                                                                      const float* __restrict__ gamma,
@@ -268,13 +269,13 @@ __global__ void __launch_bounds__(ROW_THREADS) layerscale_bwd_kernel(const float
   const int nv = D >> 2;
   for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
-  float4 ag[MAXV], ab[MAXV];
+  float4 ag[VMAX], ab[VMAX];
 #pragma unroll
-  for (int j = 0; j < MAXV; ++j) { ag[j] = make_float4(0, 0, 0, 0); ab[j] = make_float4(0, 0, 0, 0); }
+  for (int j = 0; j < VMAX; ++j) { ag[j] = make_float4(0, 0, 0, 0); ab[j] = make_float4(0, 0, 0, 0); }
   for (int row = blockIdx.x * (ROW_THREADS / 32) + warp; row < T; row += gridDim.x * (ROW_THREADS / 32)) {
     const float rs = rowscale ? __ldg(rowscale + row / rows_per_scale) : 1.f;
 #pragma unroll
-    for (int j = 0; j < MAXV; ++j) {
+    for (int j = 0; j < VMAX; ++j) {
       int c = lane + 32 * j;
       if (c < nv) {
         float4 g = reinterpret_cast<const float4*>(dx + (size_t)row * lddx)[c];
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(ROW_THREADS) layerscale_bwd_kernel(const float
     }
   }
 #pragma unroll
-  for (int j = 0; j < MAXV; ++j) {
+  for (int j = 0; j < VMAX; ++j) {
     int c = lane + 32 * j;
     if (c < nv) {
       atomicAdd(&sm[4 * c + 0], ag[j].x); atomicAdd(&sm[4 * c + 1], ag[j].y);
@@ -491,8 +492,14 @@ extern "C" int b200_layernorm_fwd(const float* x, long long ldx, int T, int D, c
                                   void* y, long long ldy, int out_bf16, float* mean, float* rstd, void* stream) {
   if (!x || !w || !b || !y || T <= 0 || !ok_dim(D) || (ldx % 4) || (ldy % 4)) return B200_ERR_INVALID_ARG;
   dim3 grid((T + 7) / 8);
-  if (out_bf16) ln_fwd_kernel<true><<<grid, ROW_THREADS, 0, (cudaStream_t)stream>>>(x, ldx, T, D, w, b, eps, y, ldy, mean, rstd);
-  else ln_fwd_kernel<false><<<grid, ROW_THREADS, 0, (cudaStream_t)stream>>>(x, ldx, T, D, w, b, eps, y, ldy, mean, rstd);
+  cudaStream_t st = (cudaStream_t)stream;
+#define B200_LN_FWD(V)                                                                                      \
+  do {                                                                                                      \
+    if (out_bf16) ln_fwd_kernel<true, V><<<grid, ROW_THREADS, 0, st>>>(x, ldx, T, D, w, b, eps, y, ldy, mean, rstd); \
+    else ln_fwd_kernel<false, V><<<grid, ROW_THREADS, 0, st>>>(x, ldx, T, D, w, b, eps, y, ldy, mean, rstd);         \
+  } while (0)
+  if (D <= 384) B200_LN_FWD(3); else if (D <= 768) B200_LN_FWD(6); else B200_LN_FWD(8);
+#undef B200_LN_FWD
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -503,10 +510,16 @@ extern "C" int b200_layernorm_bwd(const void* dy, long long lddy, int dy_bf16, c
   if (!dy || !x || !w || !mean || !rstd || !dx || T <= 0 || !ok_dim(D)) return B200_ERR_INVALID_ARG;
   if ((ldx % 4) || (lddx % 4) || (lddy % 4) || (dw && !db)) return B200_ERR_INVALID_ARG;
   int grid = (T + 7) / 8;
-  if (grid > 148 * 4) grid = 148 * 4;
+  if (grid > 148 * 8) grid = 148 * 8;
   size_t smem = 2 * D * sizeof(float);
-  if (dy_bf16) ln_bwd_kernel<true><<<grid, ROW_THREADS, smem, (cudaStream_t)stream>>>(dy, lddy, x, ldx, T, D, w, mean, rstd, dx, lddx, accumulate, dw, db);
-  else ln_bwd_kernel<false><<<grid, ROW_THREADS, smem, (cudaStream_t)stream>>>(dy, lddy, x, ldx, T, D, w, mean, rstd, dx, lddx, accumulate, dw, db);
+  cudaStream_t st = (cudaStream_t)stream;
+#define B200_LN_BWD(V)                                                                                                           \
+  do {                                                                                                                           \
+    if (dy_bf16) ln_bwd_kernel<true, V><<<grid, ROW_THREADS, smem, st>>>(dy, lddy, x, ldx, T, D, w, mean, rstd, dx, lddx, accumulate, dw, db); \
+    else ln_bwd_kernel<false, V><<<grid, ROW_THREADS, smem, st>>>(dy, lddy, x, ldx, T, D, w, mean, rstd, dx, lddx, accumulate, dw, db);        \
+  } while (0)
+  if (D <= 384) B200_LN_BWD(3); else if (D <= 768) B200_LN_BWD(6); else B200_LN_BWD(8);
+#undef B200_LN_BWD
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -549,10 +562,15 @@ extern "C" int b200_layerscale_bwd(const float* dx, long long lddx, const void* 
                                    float* dgamma, float* dbias, void* stream) {
   if (!dx || !o || !dout || T <= 0 || !ok_dim(D) || (lddx % 4) || (ldo % 4) || (lddo % 4)) return B200_ERR_INVALID_ARG;
   int grid = (T + 7) / 8;
-  if (grid > 148 * 4) grid = 148 * 4;
-  layerscale_bwd_kernel<<<grid, ROW_THREADS, 2 * D * sizeof(float), (cudaStream_t)stream>>>(
-      dx, lddx, (const __nv_bfloat16*)o, ldo, gamma, rowscale, rows_per_scale > 0 ? rows_per_scale : 1, T, D,
-      (__nv_bfloat16*)dout, lddo, dgamma, dbias);
+  if (grid > 148 * 8) grid = 148 * 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rps = rows_per_scale > 0 ? rows_per_scale : 1;
+#define B200_LS_BWD(V)                                                                                          \
+  layerscale_bwd_kernel<V><<<grid, ROW_THREADS, 2 * D * sizeof(float), st>>>(dx, lddx, (const __nv_bfloat16*)o, ldo, gamma, \
+                                                                            rowscale, rps, T, D, (__nv_bfloat16*)dout, lddo, \
+                                                                            dgamma, dbias)
+  if (D <= 384) B200_LS_BWD(3); else if (D <= 768) B200_LS_BWD(6); else B200_LS_BWD(8);
+#undef B200_LS_BWD
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
