@@ -26,7 +26,7 @@ class GemmArgs(C.Structure):
         ("A", C.c_void_p), ("lda", C.c_longlong), ("a_mn", C.c_int),
         ("B", C.c_void_p), ("ldb", C.c_longlong), ("b_mn", C.c_int),
         ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
-        ("splits", C.c_int), ("epi", C.c_int), ("block_n", C.c_int),
+        ("splits", C.c_int), ("epi", C.c_int), ("block_n", C.c_int), ("ws_mode", C.c_int),
         ("alpha", C.c_float),
         ("C", C.c_void_p), ("ldc", C.c_longlong),
         ("C2", C.c_void_p), ("ldc2", C.c_longlong),

@@ -85,53 +85,140 @@ __device__ __forceinline__ uint32_t make_idesc(int n, int a_mn, int b_mn) {
 // ---------------------------------------------------------------------------------------------
 // Epilogue for 4 consecutive columns of one output row (after the smem transpose: a warp instruction covers
 // 4 rows x 32 columns, i.e. full 128-byte lines of fp32 or 64-byte runs of bf16 -- coalesced loads and stores).
+// EPI is a template parameter so the per-element code is branch-free.
+template <int EPI>
 __device__ __forceinline__ void epilogue_vec4(const GemmDev& p, float4 acc, int row, int col, const float4& bias4,
-                                              const float4& gamma4) {
+                                              const float4& gamma4, const float4& aux4) {
   float v0 = acc.x * p.alpha + bias4.x, v1 = acc.y * p.alpha + bias4.y, v2 = acc.z * p.alpha + bias4.z,
         v3 = acc.w * p.alpha + bias4.w;
-  switch (p.epi) {
-    case B200_EPI_BF16: {
-      uint2 o; o.x = pack_bf16x2(v0, v1); o.y = pack_bf16x2(v2, v3);
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col) = o;
-    } break;
-    case B200_EPI_F32: {
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col) = make_float4(v0, v1, v2, v3);
-    } break;
-    case B200_EPI_F32_ATOMIC: {
-      atomicAdd(reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col), make_float4(v0, v1, v2, v3));
-    } break;
-    case B200_EPI_BIAS_GELU: {
-      // u = bf16(acc + bias) (what nn.Linear returns under bf16 autocast); h = bf16(gelu(u))
-      const float u0 = bf16_round(v0), u1 = bf16_round(v1), u2 = bf16_round(v2), u3 = bf16_round(v3);
-      if (p.C2) {
-        uint2 o; o.x = pack_bf16x2(u0, u1); o.y = pack_bf16x2(u2, u3);
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C2) + (size_t)row * p.ldc2 + col) = o;
+  if constexpr (EPI == B200_EPI_BF16) {
+    uint2 o; o.x = pack_bf16x2(v0, v1); o.y = pack_bf16x2(v2, v3);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col) = o;
+  } else if constexpr (EPI == B200_EPI_F32) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col) = make_float4(v0, v1, v2, v3);
+  } else if constexpr (EPI == B200_EPI_F32_ATOMIC) {
+    atomicAdd(reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col), make_float4(v0, v1, v2, v3));
+  } else if constexpr (EPI == B200_EPI_BIAS_GELU) {
+    // u = bf16(acc + bias) (what nn.Linear returns under bf16 autocast); h = bf16(gelu(u))
+    const float u0 = bf16_round(v0), u1 = bf16_round(v1), u2 = bf16_round(v2), u3 = bf16_round(v3);
+    if (p.C2) {
+      uint2 o; o.x = pack_bf16x2(u0, u1); o.y = pack_bf16x2(u2, u3);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C2) + (size_t)row * p.ldc2 + col) = o;
+    }
+    uint2 o; o.x = pack_bf16x2(gelu_erf(u0), gelu_erf(u1)); o.y = pack_bf16x2(gelu_erf(u2), gelu_erf(u3));
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col) = o;
+  } else if constexpr (EPI == B200_EPI_RESIDUAL) {
+    // o = bf16(acc + bias); x_out = x_in + gamma * o * rowscale   (fp32 residual stream)
+    const float o0 = bf16_round(v0), o1 = bf16_round(v1), o2 = bf16_round(v2), o3 = bf16_round(v3);
+    if (p.C2) {
+      uint2 o; o.x = pack_bf16x2(o0, o1); o.y = pack_bf16x2(o2, o3);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C2) + (size_t)row * p.ldc2 + col) = o;
+    }
+    const float rs = p.rowscale ? __ldg(p.rowscale + row / p.rows_per_scale) : 1.0f;
+    float4 x = aux4;
+    x.x += (o0 * gamma4.x) * rs; x.y += (o1 * gamma4.y) * rs; x.z += (o2 * gamma4.z) * rs; x.w += (o3 * gamma4.w) * rs;
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col) = x;
+  } else if constexpr (EPI == B200_EPI_DGELU) {
+    // dU = bf16( bf16(acc) * gelu'(u) ), u = aux (bf16 pre-activation saved by the forward)
+    const float2 ua = unpack_bf16x2(__float_as_uint(aux4.x)), uc = unpack_bf16x2(__float_as_uint(aux4.y));
+    uint2 o;
+    o.x = pack_bf16x2(bf16_round(v0) * gelu_erf_grad(ua.x), bf16_round(v1) * gelu_erf_grad(ua.y));
+    o.y = pack_bf16x2(bf16_round(v2) * gelu_erf_grad(uc.x), bf16_round(v3) * gelu_erf_grad(uc.y));
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col) = o;
+  }
+}
+
+// global reads an epilogue needs for one 32-column chunk (8 rows per lane): the fp32 residual stream or the
+// saved bf16 pre-activation.  They never alias the outputs, so they are issued a whole chunk ahead.
+template <int EPI>
+__device__ __forceinline__ void load_aux_chunk(const GemmDev& p, float4 (&aux4)[8], int row_base, int sub_row, int col) {
+  if constexpr (EPI == B200_EPI_RESIDUAL) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = row_base + it * 4 + sub_row;
+      aux4[it] = (row < p.M && col < p.N)
+                     ? __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) + (size_t)row * p.ldaux + col))
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  } else if constexpr (EPI == B200_EPI_DGELU) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = row_base + it * 4 + sub_row;
+      uint2 u = make_uint2(0u, 0u);
+      if (row < p.M && col < p.N)
+        u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + (size_t)row * p.ldaux + col));
+      aux4[it] = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), 0.f, 0.f);
+    }
+  }
+}
+
+// One 128 x BLOCK_N accumulator tile: TMEM -> registers -> smem transpose -> fused epilogue -> global.
+// Software pipeline per warp: bias/gamma and the first chunk's aux reads are issued before the accumulator is
+// ready; tcgen05.ld of chunk c+1 and the aux reads of chunk c+1 are in flight while chunk c is stored.
+template <int BLOCK_N, int EPI>
+__device__ __forceinline__ void epilogue_tile_t(const GemmDev& p, uint32_t tmem_acc, uint64_t* tmem_full_bar, uint32_t full_phase,
+                                                int m0, int n0, int quarter, int half, int lane, float* stg) {
+  constexpr int COLS_PER_WARP = BLOCK_N / 2;
+  constexpr int NC = COLS_PER_WARP / 32;
+  constexpr bool HAS_AUX = (EPI == B200_EPI_RESIDUAL || EPI == B200_EPI_DGELU);
+  const int sub_row = lane >> 3;  // 0..3 : row within a 4-row group after the transpose
+  const int g4 = lane & 7;        // 0..7 : which float4 (4 columns) of the 32-column chunk
+  const int row_base = m0 + quarter * 32;
+  const int col0 = n0 + half * COLS_PER_WARP + g4 * 4;
+  float4 bias4[NC], gamma4[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int col = col0 + c * 32;
+    bias4[c] = (p.bias && col < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    gamma4[c] = (EPI == B200_EPI_RESIDUAL && p.gamma && col < p.N) ? __ldg(reinterpret_cast<const float4*>(p.gamma + col))
+                                                                    : make_float4(1.f, 1.f, 1.f, 1.f);
+  }
+  float4 aux_cur[8], aux_nxt[8];
+  if constexpr (HAS_AUX) load_aux_chunk<EPI>(p, aux_nxt, row_base, sub_row, col0);
+
+  mbar_wait(tmem_full_bar, full_phase);
+  tc_fence_after();
+  const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16) + half * COLS_PER_WARP;
+  uint32_t v[32];
+  tmem_ld_32x32(taddr, v);
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    tmem_ld_wait();
+    // transpose through smem: thread (= row `lane`) writes its 32 columns; XOR swizzle keeps both the
+    // row-wise float4 writes and the column-group reads bank-conflict free
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    if (c + 1 < NC) tmem_ld_32x32(taddr + (c + 1) * 32, v);
+    __syncwarp();
+    if constexpr (HAS_AUX) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) aux_cur[it] = aux_nxt[it];
+      if (c + 1 < NC) load_aux_chunk<EPI>(p, aux_nxt, row_base, sub_row, col0 + (c + 1) * 32);
+    }
+    const int col = col0 + c * 32;
+    if (col < p.N) {  // N % 8 == 0 and col % 4 == 0 -> the 4 columns are all valid
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + sub_row;
+        const float4 a4 = *reinterpret_cast<const float4*>(stg + r * 32 + ((g4 ^ (r & 7)) << 2));
+        if (row_base + r < p.M) epilogue_vec4<EPI>(p, a4, row_base + r, col, bias4[c], gamma4[c], aux_cur[it]);
       }
-      uint2 o; o.x = pack_bf16x2(gelu_erf(u0), gelu_erf(u1)); o.y = pack_bf16x2(gelu_erf(u2), gelu_erf(u3));
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col) = o;
-    } break;
-    case B200_EPI_RESIDUAL: {
-      // o = bf16(acc + bias); x_out = x_in + gamma * o * rowscale   (fp32 residual stream)
-      const float o0 = bf16_round(v0), o1 = bf16_round(v1), o2 = bf16_round(v2), o3 = bf16_round(v3);
-      if (p.C2) {
-        uint2 o; o.x = pack_bf16x2(o0, o1); o.y = pack_bf16x2(o2, o3);
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C2) + (size_t)row * p.ldc2 + col) = o;
-      }
-      const float rs = p.rowscale ? __ldg(p.rowscale + row / p.rows_per_scale) : 1.0f;
-      float4 x = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) + (size_t)row * p.ldaux + col);
-      x.x += (o0 * gamma4.x) * rs; x.y += (o1 * gamma4.y) * rs; x.z += (o2 * gamma4.z) * rs; x.w += (o3 * gamma4.w) * rs;
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col) = x;
-    } break;
-    case B200_EPI_DGELU: {
-      // dU = bf16( bf16(acc) * gelu'(u) ), u = aux (bf16 pre-activation saved by the forward)
-      const uint2 ub = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + (size_t)row * p.ldaux + col);
-      const float2 ua = unpack_bf16x2(ub.x), uc = unpack_bf16x2(ub.y);
-      uint2 o;
-      o.x = pack_bf16x2(bf16_round(v0) * gelu_erf_grad(ua.x), bf16_round(v1) * gelu_erf_grad(ua.y));
-      o.y = pack_bf16x2(bf16_round(v2) * gelu_erf_grad(uc.x), bf16_round(v3) * gelu_erf_grad(uc.y));
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col) = o;
-    } break;
-    default: break;
+    }
+    __syncwarp();
+  }
+}
+
+template <int BLOCK_N>
+__device__ __forceinline__ void epilogue_tile(const GemmDev& p, uint32_t tmem_acc, uint64_t* tmem_full_bar, uint32_t full_phase,
+                                              int m0, int n0, int quarter, int half, int lane, float* stg) {
+  switch (p.epi) {  // warp-uniform, once per tile
+    case B200_EPI_BF16: epilogue_tile_t<BLOCK_N, B200_EPI_BF16>(p, tmem_acc, tmem_full_bar, full_phase, m0, n0, quarter, half, lane, stg); break;
+    case B200_EPI_F32: epilogue_tile_t<BLOCK_N, B200_EPI_F32>(p, tmem_acc, tmem_full_bar, full_phase, m0, n0, quarter, half, lane, stg); break;
+    case B200_EPI_F32_ATOMIC: epilogue_tile_t<BLOCK_N, B200_EPI_F32_ATOMIC>(p, tmem_acc, tmem_full_bar, full_phase, m0, n0, quarter, half, lane, stg); break;
+    case B200_EPI_BIAS_GELU: epilogue_tile_t<BLOCK_N, B200_EPI_BIAS_GELU>(p, tmem_acc, tmem_full_bar, full_phase, m0, n0, quarter, half, lane, stg); break;
+    case B200_EPI_RESIDUAL: epilogue_tile_t<BLOCK_N, B200_EPI_RESIDUAL>(p, tmem_acc, tmem_full_bar, full_phase, m0, n0, quarter, half, lane, stg); break;
+    default: epilogue_tile_t<BLOCK_N, B200_EPI_DGELU>(p, tmem_acc, tmem_full_bar, full_phase, m0, n0, quarter, half, lane, stg); break;
   }
 }
 
@@ -268,45 +355,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int ew = warp - 2;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int half = ew >> 2;      // which half of the tile's columns
-    constexpr int COLS_PER_WARP = BLOCK_N / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       const int tile = w / n_splits;
       const int m0 = (tile % tiles_m) * BLOCK_M;
       const int n0 = (tile / tiles_m) * BLOCK_N;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      float* stg = epi_staging + ew * (32 * 32);
-      const int sub_row = lane >> 3;        // 0..3 : row within a 4-row group after the transpose
-      const int g4 = lane & 7;              // 0..7 : which float4 (4 columns) of the 32-column chunk
-#pragma unroll 1
-      for (int c = 0; c < COLS_PER_WARP; c += 32) {
-        const int col_in_tile = half * COLS_PER_WARP + c;
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * Cfg::ACC_STRIDE + col_in_tile, v);
-        tmem_ld_wait();
-        // transpose through smem: thread (= row `lane`) writes its 32 columns; XOR swizzle keeps both the
-        // row-wise float4 writes and the column-group reads bank-conflict free
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        __syncwarp();
-        const int col = n0 + col_in_tile + g4 * 4;
-        if (col < p.N) {  // N % 8 == 0 and col % 4 == 0 -> the 4 columns are all valid
-          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), gamma4 = make_float4(1.f, 1.f, 1.f, 1.f);
-          if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-          if (p.gamma) gamma4 = __ldg(reinterpret_cast<const float4*>(p.gamma + col));
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int r = it * 4 + sub_row;
-            const int row = m0 + quarter * 32 + r;
-            const float4 a4 = *reinterpret_cast<const float4*>(stg + r * 32 + ((g4 ^ (r & 7)) << 2));
-            if (row < p.M) epilogue_vec4(p, a4, row, col, bias4, gamma4);
-          }
-        }
-        __syncwarp();
-      }
+      epilogue_tile<BLOCK_N>(p, tmem_base + acc * Cfg::ACC_STRIDE, &tmem_full[acc], acc_phase, m0, n0, quarter, half, lane,
+                             epi_staging + ew * (32 * 32));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -320,6 +376,170 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Weight-stationary variant for small K (K <= WS_KB_MAX*64, e.g. every D=384 GEMM of the ViT):
+// the [BLOCK_N x K] slab of B stays resident in shared memory while the CTA streams consecutive M tiles of A
+// through a short ring.  The generic kernel re-fetches the B slab for every output tile, which makes the
+// K=384 GEMMs L2->SM bandwidth bound (measured ~7 TB/s at 40 % tensor utilisation); here each CTA owns a
+// contiguous run of the n-major tile list, so B is fetched once (at most twice) per CTA.
+template <int BLOCK_N, int KB_MAX>
+struct GemmWsCfg {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;      // one k-block of the resident slab
+  static constexpr int PANEL_BYTES = KB_MAX * B_BYTES;
+  static constexpr int EPI_STAGING_BYTES = NUM_EPI_WARPS * 32 * 32 * 4;
+  static constexpr int BUDGET = 232448 - 1024 - 256 - PANEL_BYTES - EPI_STAGING_BYTES;
+  static constexpr int STAGES = BUDGET / A_BYTES > 6 ? 6 : BUDGET / A_BYTES;
+  static constexpr int ACC_STRIDE = 256;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int SMEM_BYTES = PANEL_BYTES + STAGES * A_BYTES + EPI_STAGING_BYTES + 1024 + 256;
+  static_assert(STAGES >= 2, "weight-stationary slab leaves no room for the A ring");
+};
+
+template <int BLOCK_N, int KB_MAX>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const GemmDev p) {
+  using Cfg = GemmWsCfg<BLOCK_N, KB_MAX>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* panel = smem;
+  uint8_t* ring = smem + Cfg::PANEL_BYTES;
+  float* epi_staging = reinterpret_cast<float*>(ring + STAGES * Cfg::A_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + STAGES * Cfg::A_BYTES + Cfg::EPI_STAGING_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* b_full = tmem_empty + 2;
+  uint64_t* b_empty = b_full + 1;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(b_empty + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int kb_total = (p.K + BLOCK_K - 1) / BLOCK_K;  // <= KB_MAX (checked on the host)
+  const int total_work = tiles_m * tiles_n;
+  const int per_cta = (total_work + gridDim.x - 1) / gridDim.x;
+  const int w0 = blockIdx.x * per_cta;
+  const int w1 = min(total_work, w0 + per_cta);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], NUM_EPI_WARPS); }
+    mbar_init(b_full, 1);
+    mbar_init(b_empty, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+  if (warp == 1) { tmem_alloc(tmem_base_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0, b_empty_phase = 0;
+    int cur_nt = -1;
+    for (int w = w0; w < w1; ++w) {
+      const int nt = w / tiles_m, mt = w % tiles_m;
+      const int m0 = mt * BLOCK_M, n0 = nt * BLOCK_N;
+      if (nt != cur_nt) {
+        if (cur_nt >= 0) { mbar_wait(b_empty, b_empty_phase); b_empty_phase ^= 1; }  // MMAs on the old slab retired
+        if (lane == 0) {
+          mbar_expect_tx(b_full, kb_total * Cfg::B_BYTES);
+          for (int kb = 0; kb < kb_total; ++kb) {
+            uint8_t* sb = panel + kb * Cfg::B_BYTES;
+            if (!p.b_mn) {
+              tma_load_2d(sb, &tmB, b_full, kb * BLOCK_K, n0);
+            } else {
+#pragma unroll
+              for (int a = 0; a < BLOCK_N / 64; ++a) tma_load_2d(sb + a * (BLOCK_K * 128), &tmB, b_full, n0 + a * 64, kb * BLOCK_K);
+            }
+          }
+        }
+        __syncwarp();
+        cur_nt = nt;
+      }
+      for (int kb = 0; kb < kb_total; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (lane == 0) {
+          uint8_t* sa = ring + stage * Cfg::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES);
+          if (!p.a_mn) {
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, m0);
+          } else {
+#pragma unroll
+            for (int a = 0; a < BLOCK_M / 64; ++a) tma_load_2d(sa + a * (BLOCK_K * 128), &tmA, &full_bar[stage], m0 + a * 64, kb * BLOCK_K);
+          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc(BLOCK_N, p.a_mn, p.b_mn);
+    int stage = 0;
+    uint32_t phase = 0, b_full_phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int cur_nt = -1;
+    for (int w = w0; w < w1; ++w) {
+      const int nt = w / tiles_m;
+      if (nt != cur_nt) { mbar_wait(b_full, b_full_phase); b_full_phase ^= 1; cur_nt = nt; }
+      const bool last_of_slab = (w + 1 == w1) || ((w + 1) / tiles_m != nt);
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * Cfg::ACC_STRIDE;
+      for (int kb = 0; kb < kb_total; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(ring + stage * Cfg::A_BYTES);
+          const uint32_t sb = smem_u32(panel + kb * Cfg::B_BYTES);
+          const uint64_t adesc0 = p.a_mn ? make_smem_desc(sa, BLOCK_K * 128, 1024) : make_smem_desc(sa, 16, 1024);
+          const uint64_t bdesc0 = p.b_mn ? make_smem_desc(sb, BLOCK_K * 128, 1024) : make_smem_desc(sb, 16, 1024);
+          const uint32_t a_step = p.a_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+          const uint32_t b_step = p.b_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_f16(tmem_d, adesc0 + (uint64_t)(k * a_step), bdesc0 + (uint64_t)(k * b_step), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (kb == kb_total - 1) {
+            umma_commit(&tmem_full[acc]);
+            if (last_of_slab) umma_commit(b_empty);
+          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if ((acc ^= 1) == 0) acc_phase ^= 1;
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = w0; w < w1; ++w) {
+      const int m0 = (w % tiles_m) * BLOCK_M, n0 = (w / tiles_m) * BLOCK_N;
+      epilogue_tile<BLOCK_N>(p, tmem_base + acc * Cfg::ACC_STRIDE, &tmem_full[acc], acc_phase, m0, n0, quarter, half, lane,
+                             epi_staging + ew * (32 * 32));
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if ((acc ^= 1) == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -404,6 +624,51 @@ static int launch_gemm(const b200_gemm_args* a, cudaStream_t stream) {
   return B200_OK;
 }
 
+
+template <int BLOCK_N, int KB_MAX>
+static int launch_gemm_ws(const b200_gemm_args* a, cudaStream_t stream) {
+  using Cfg = GemmWsCfg<BLOCK_N, KB_MAX>;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!a->a_mn) rc = make_tmap(&tmA, a->A, a->M, a->K, a->lda, BLOCK_K, BLOCK_M);
+  else rc = make_tmap(&tmA, a->A, a->K, a->M, a->lda, 64, BLOCK_K);
+  if (rc) return rc;
+  if (!a->b_mn) rc = make_tmap(&tmB, a->B, a->N, a->K, a->ldb, BLOCK_K, BLOCK_N);
+  else rc = make_tmap(&tmB, a->B, a->K, a->N, a->ldb, 64, BLOCK_K);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_tcgen05_ws_kernel<BLOCK_N, KB_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             Cfg::SMEM_BYTES) != cudaSuccess)
+      return B200_ERR_CUDA;
+    attr_set = true;
+  }
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  GemmDev p;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.a_mn = a->a_mn; p.b_mn = a->b_mn;
+  p.splits = 1;
+  p.epi = a->epi;
+  p.alpha = a->alpha;
+  p.C = a->C; p.ldc = a->ldc;
+  p.C2 = a->C2; p.ldc2 = a->ldc2;
+  p.aux = a->aux; p.ldaux = a->ldaux;
+  p.bias = a->bias; p.gamma = a->gamma;
+  p.rowscale = a->rowscale; p.rows_per_scale = a->rows_per_scale > 0 ? a->rows_per_scale : 1;
+  const long long tiles = (long long)((a->M + BLOCK_M - 1) / BLOCK_M) * ((a->N + BLOCK_N - 1) / BLOCK_N);
+  int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
+  // even out the contiguous runs: ceil(tiles/grid) tiles per CTA, drop CTAs that would get nothing
+  const long long per = (tiles + grid - 1) / grid;
+  grid = (int)((tiles + per - 1) / per);
+  gemm_tcgen05_ws_kernel<BLOCK_N, KB_MAX><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
 }  // namespace b200
 
 extern "C" int b200_gemm(const b200_gemm_args* a, void* stream) {
@@ -418,15 +683,29 @@ extern "C" int b200_gemm(const b200_gemm_args* a, void* stream) {
   if ((a->epi == B200_EPI_RESIDUAL || a->epi == B200_EPI_DGELU) && (!a->aux || (a->ldaux % 8))) return B200_ERR_INVALID_ARG;
   if (a->C2 && (a->ldc2 % 8)) return B200_ERR_UNSUPPORTED;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int kb_total = (a->K + BLOCK_K - 1) / BLOCK_K;
+  const int tiles_m = (a->M + BLOCK_M - 1) / BLOCK_M;
+  // weight-stationary schedule: small K (the B slab fits in smem next to the A ring) and enough M tiles to amortise it
+  const bool want_ws = a->ws_mode == 1 || (a->ws_mode == 0 && a->splits <= 1 && tiles_m >= 8 && kb_total <= 6);
   int bn = a->block_n;
   if (bn == 0) {
     // tile-N heuristic: minimise padded columns, prefer wider tiles (fewer smem bytes per MMA)
-    const int cand[3] = {256, 192, 128};
+    const int cand_any[3] = {256, 192, 128};
+    const int cand_ws6[2] = {192, 128};  // K <= 384: slabs of 256 columns do not fit
+    const int* cand = (want_ws && kb_total > 4) ? cand_ws6 : cand_any;
+    const int nc = (want_ws && kb_total > 4) ? 2 : 3;
     long long best = -1;
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < nc; ++i) {
       long long padded = (long long)((a->N + cand[i] - 1) / cand[i]) * cand[i];
       if (best < 0 || padded < best) { best = padded; bn = cand[i]; }
     }
+  }
+  if (want_ws) {
+    if (a->splits > 1) return B200_ERR_INVALID_ARG;
+    if (kb_total <= 4 && bn == 256) return launch_gemm_ws<256, 4>(a, s);
+    if (kb_total <= 6 && bn == 192) return launch_gemm_ws<192, 6>(a, s);
+    if (kb_total <= 6 && bn == 128) return launch_gemm_ws<128, 6>(a, s);
+    if (a->ws_mode == 1) return B200_ERR_UNSUPPORTED;
   }
   switch (bn) {
     case 128: return launch_gemm<128>(a, s);

@@ -36,7 +36,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn: bool = Fa
          epi: int = EPI_BF16, bias: torch.Tensor | None = None, out2: torch.Tensor | None = None,
          aux: torch.Tensor | None = None, gamma: torch.Tensor | None = None,
          rowscale: torch.Tensor | None = None, rows_per_scale: int = 1, alpha: float = 1.0,
-         splits: int = 1, block_n: int = 0) -> torch.Tensor:
+         splits: int = 1, block_n: int = 0, ws_mode: int = 0) -> torch.Tensor:
     """out[M,N] = epi(alpha * A[M,K] @ B[N,K]^T). a/b are bf16 2-D (last dim contiguous).
 
     a_mn / b_mn: the tensor passed is the TRANSPOSED operand, i.e. stored [K, M] / [K, N].
@@ -58,7 +58,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn: bool = Fa
     args.A, args.lda, args.a_mn = a.data_ptr(), a.stride(0), int(a_mn)
     args.B, args.ldb, args.b_mn = b.data_ptr(), b.stride(0), int(b_mn)
     args.M, args.N, args.K = M, N, K
-    args.splits, args.epi, args.block_n, args.alpha = splits, epi, block_n, alpha
+    args.splits, args.epi, args.block_n, args.alpha, args.ws_mode = splits, epi, block_n, alpha, ws_mode
     args.C, args.ldc = out.data_ptr(), out.stride(0)
     if out2 is not None:
         args.C2, args.ldc2 = out2.data_ptr(), out2.stride(0)

@@ -1,0 +1,40 @@
+"""Representative GEMM launches of the cfg2 step for `ncu --set full` (one launch per case after warm-up)."""
+import sys
+import torch
+sys.path.insert(0, ".")
+from lightly_train_b200 import ops
+
+dev = "cuda"
+T, D, H = 25216, 384, 1536
+bf = torch.bfloat16
+x = torch.randn(T, D, device=dev).to(bf)
+hid = torch.randn(T, H, device=dev).to(bf)
+wqkv = (torch.randn(3 * D, D, device=dev) * 0.02).to(bf)
+wproj = (torch.randn(D, D, device=dev) * 0.02).to(bf)
+w1 = (torch.randn(H, D, device=dev) * 0.02).to(bf)
+w2 = (torch.randn(D, H, device=dev) * 0.02).to(bf)
+b3, b1, bh = torch.randn(3 * D, device=dev), torch.randn(D, device=dev), torch.randn(H, device=dev)
+gamma = torch.randn(D, device=dev)
+res = torch.randn(T, D, device=dev)
+out_qkv = torch.empty(T, 3 * D, device=dev, dtype=bf)
+out_res, out_o = torch.empty(T, D, device=dev), torch.empty(T, D, device=dev, dtype=bf)
+out_h, out_u = torch.empty(T, H, device=dev, dtype=bf), torch.empty(T, H, device=dev, dtype=bf)
+out_du = torch.empty(T, H, device=dev, dtype=bf)
+
+
+def cases():
+    ops.gemm(x, wqkv, out_qkv, bias=b3)                                                      # qkv
+    ops.gemm(x, wproj, out_res, epi=ops.EPI_RESIDUAL, bias=b1, out2=out_o, aux=res, gamma=gamma)  # proj
+    ops.gemm(x, w1, out_h, epi=ops.EPI_BIAS_GELU, bias=bh, out2=out_u)                        # fc1
+    ops.gemm(hid, w2, out_res, epi=ops.EPI_RESIDUAL, bias=b1, out2=out_o, aux=res, gamma=gamma)   # fc2
+    ops.gemm(x, w2, out_du, b_mn=True, epi=ops.EPI_DGELU, aux=out_u)                          # dU dgrad
+
+
+for _ in range(3):
+    cases()
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStart()
+cases()
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStop()
+print("done")

@@ -16,13 +16,13 @@ def ref_mm(a, b, a_mn, b_mn):
     return A @ B.t()
 
 
-def run(M, N, K, a_mn=False, b_mn=False, epi=EPI_BF16, block_n=0, splits=1):
+def run(M, N, K, a_mn=False, b_mn=False, epi=EPI_BF16, block_n=0, splits=1, ws_mode=2):
     global fails
     a = torch.randn((K, M) if a_mn else (M, K), device=dev).bfloat16()
     b = torch.randn((K, N) if b_mn else (N, K), device=dev).bfloat16()
     ref = ref_mm(a, b, a_mn, b_mn) / 8.0
     bias = torch.randn(N, device=dev)
-    kw = dict(a_mn=a_mn, b_mn=b_mn, epi=epi, block_n=block_n, splits=splits, alpha=1 / 8.0)
+    kw = dict(a_mn=a_mn, b_mn=b_mn, epi=epi, block_n=block_n, splits=splits, alpha=1 / 8.0, ws_mode=ws_mode)
     if epi == EPI_BF16:
         out = torch.full((M, N), 7.0, device=dev, dtype=torch.bfloat16)
         ops.gemm(a, b, out, bias=bias, **kw)
@@ -65,7 +65,7 @@ def run(M, N, K, a_mn=False, b_mn=False, epi=EPI_BF16, block_n=0, splits=1):
     scale = want.abs().max().item()
     ok = err <= 0.02 * max(scale, 1.0)
     if not ok: fails += 1
-    print(f"{'OK ' if ok else 'BAD'} M={M} N={N} K={K} a_mn={int(a_mn)} b_mn={int(b_mn)} epi={epi} bn={block_n} splits={splits} err={err:.4g} scale={scale:.3g}", flush=True)
+    print(f"{'OK ' if ok else 'BAD'} M={M} N={N} K={K} a_mn={int(a_mn)} b_mn={int(b_mn)} epi={epi} bn={block_n} splits={splits} ws={ws_mode} err={err:.4g} scale={scale:.3g}", flush=True)
 
 
 print(lib().b200_version())
@@ -86,20 +86,36 @@ for a_mn in (False, True):
 # split-K atomic (wgrad-like)
 run(1152, 384, 25216, a_mn=True, b_mn=True, epi=EPI_F32_ATOMIC, splits=16, block_n=192)
 run(384, 1536, 5000, a_mn=True, b_mn=True, epi=EPI_F32_ATOMIC, splits=7)
+# weight-stationary schedule (auto for K<=384 and >= 8 M tiles; forced here on small/odd shapes too)
+for epi in (EPI_BF16, EPI_F32, EPI_BIAS_GELU, EPI_RESIDUAL, EPI_DGELU):
+    run(5000, 1152, 384, epi=epi, ws_mode=1)
+    run(3000, 1536, 384, epi=epi, ws_mode=1, block_n=128)
+run(4403, 4096, 256, ws_mode=1)                      # K=256 -> 256-wide slab
+run(1300, 392, 200, epi=EPI_F32, ws_mode=1)          # tails in M, N, K
+run(2500, 1536, 384, b_mn=True, epi=EPI_DGELU, ws_mode=1)
+run(2500, 384, 384, a_mn=True, b_mn=True, epi=EPI_F32, ws_mode=1)
+run(25216, 1152, 384, ws_mode=0)
 # fused epilogues
 run(1000, 1536, 384, epi=EPI_BIAS_GELU)
 run(1000, 384, 1536, epi=EPI_RESIDUAL)
 run(1000, 1536, 384, epi=EPI_DGELU)
 
 
-def bench(M, N, K, a_mn=False, b_mn=False, epi=EPI_BF16, splits=1, block_n=0, iters=20):
+def bench(M, N, K, a_mn=False, b_mn=False, epi=EPI_BF16, splits=1, block_n=0, iters=20, ws_mode=0):
     a = torch.randn((K, M) if a_mn else (M, K), device=dev).bfloat16()
     b = torch.randn((K, N) if b_mn else (N, K), device=dev).bfloat16()
-    out = torch.zeros((M, N), device=dev, dtype=torch.float32 if epi in (EPI_F32, EPI_F32_ATOMIC) else torch.bfloat16)
-    for _ in range(3): ops.gemm(a, b, out, a_mn=a_mn, b_mn=b_mn, epi=epi, splits=splits, block_n=block_n)
+    out = torch.zeros((M, N), device=dev, dtype=torch.float32 if epi in (EPI_F32, EPI_F32_ATOMIC, EPI_RESIDUAL) else torch.bfloat16)
+    extra = {}
+    if epi == EPI_RESIDUAL:
+        extra = dict(aux=torch.randn(M, N, device=dev), gamma=torch.randn(N, device=dev), out2=torch.empty(M, N, device=dev, dtype=torch.bfloat16), bias=torch.randn(N, device=dev))
+    if epi == EPI_BIAS_GELU:
+        extra = dict(out2=torch.empty(M, N, device=dev, dtype=torch.bfloat16), bias=torch.randn(N, device=dev))
+    if epi == EPI_DGELU:
+        extra = dict(aux=torch.randn(M, N, device=dev).bfloat16())
+    for _ in range(3): ops.gemm(a, b, out, a_mn=a_mn, b_mn=b_mn, epi=epi, splits=splits, block_n=block_n, ws_mode=ws_mode, **extra)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(iters): ops.gemm(a, b, out, a_mn=a_mn, b_mn=b_mn, epi=epi, splits=splits, block_n=block_n)
+    for _ in range(iters): ops.gemm(a, b, out, a_mn=a_mn, b_mn=b_mn, epi=epi, splits=splits, block_n=block_n, ws_mode=ws_mode, **extra)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     A = a.t() if a_mn else a
@@ -110,16 +126,20 @@ def bench(M, N, K, a_mn=False, b_mn=False, epi=EPI_BF16, splits=1, block_n=0, it
     e1.record(); torch.cuda.synchronize()
     ms_t = e0.elapsed_time(e1) / iters
     tf = 2.0 * M * N * K / ms / 1e9
-    print(f"bench M={M} N={N} K={K} a_mn={int(a_mn)} b_mn={int(b_mn)} epi={epi} splits={splits} bn={block_n}: {ms*1e3:.1f} us  {tf:.0f} TFLOP/s   (torch.matmul {ms_t*1e3:.1f} us, {2.0*M*N*K/ms_t/1e9:.0f} TF)", flush=True)
+    print(f"bench M={M} N={N} K={K} a_mn={int(a_mn)} b_mn={int(b_mn)} epi={epi} splits={splits} bn={block_n} ws={ws_mode}: {ms*1e3:.1f} us  {tf:.0f} TFLOP/s   (torch.matmul {ms_t*1e3:.1f} us, {2.0*M*N*K/ms_t/1e9:.0f} TF)", flush=True)
 
 
 if fails == 0:
-    for bn in (128, 192, 256):
-        bench(25216, 1152, 384, block_n=bn)
-    bench(25216, 384, 384, block_n=192)
-    bench(25216, 1536, 384)
+    for ws in (2, 0):
+        bench(25216, 1152, 384, ws_mode=ws)
+        bench(25216, 384, 384, ws_mode=ws)
+        bench(25216, 1536, 384, ws_mode=ws)
+        bench(25216, 384, 384, epi=EPI_RESIDUAL, ws_mode=ws)
+        bench(25216, 1536, 384, epi=EPI_BIAS_GELU, ws_mode=ws)
+        bench(25216, 1536, 384, b_mn=True, epi=EPI_DGELU, ws_mode=ws)
+        bench(4403, 65536, 256, ws_mode=ws)
     bench(25216, 384, 1536, block_n=192)
-    bench(4403, 65536, 256)
+    bench(25216, 384, 1536, epi=EPI_RESIDUAL)
     bench(8192, 8192, 8192)
     bench(1152, 384, 25216, a_mn=True, b_mn=True, epi=EPI_F32_ATOMIC, splits=8, block_n=192)
     bench(1152, 384, 25216, a_mn=True, b_mn=True, epi=EPI_F32_ATOMIC, splits=24, block_n=192)
