@@ -83,70 +83,70 @@ __device__ __forceinline__ uint32_t make_idesc(int n, int a_mn, int b_mn) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Epilogue for 4 consecutive columns of one output row (after the smem transpose: a warp instruction covers
-// 4 rows x 32 columns, i.e. full 128-byte lines of fp32 or 64-byte runs of bf16 -- coalesced loads and stores).
-// EPI is a template parameter so the per-element code is branch-free.
+// Epilogue.  After an smem transpose a warp instruction covers 4 rows x 32 columns (full 128-byte lines of fp32,
+// 64-byte runs of bf16): coalesced loads and stores.  EPI is a template parameter (branch-free per element) and
+// all global addresses are strength-reduced to one pointer bump per row group: the epilogue is issue-bound,
+// every instruction per element counts.
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+struct EpiPtrs {
+  char* c;         // primary output, positioned at (first row of this lane, col)
+  char* c2;        // secondary bf16 output or nullptr
+  const char* aux; // aux input or nullptr
+  long long c_step, c2_step, aux_step;  // bytes per 4-row group
+};
+
 template <int EPI>
-__device__ __forceinline__ void epilogue_vec4(const GemmDev& p, float4 acc, int row, int col, const float4& bias4,
+__device__ __forceinline__ void epilogue_vec4(const GemmDev& p, float4 acc, char* c, char* c2, float rs, const float4& bias4,
                                               const float4& gamma4, const float4& aux4) {
-  float v0 = acc.x * p.alpha + bias4.x, v1 = acc.y * p.alpha + bias4.y, v2 = acc.z * p.alpha + bias4.z,
-        v3 = acc.w * p.alpha + bias4.w;
+  const float v0 = fmaf(acc.x, p.alpha, bias4.x), v1 = fmaf(acc.y, p.alpha, bias4.y), v2 = fmaf(acc.z, p.alpha, bias4.z),
+              v3 = fmaf(acc.w, p.alpha, bias4.w);
   if constexpr (EPI == B200_EPI_BF16) {
-    uint2 o; o.x = pack_bf16x2(v0, v1); o.y = pack_bf16x2(v2, v3);
-    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col) = o;
+    *reinterpret_cast<uint2*>(c) = make_uint2(pack_bf16x2(v0, v1), pack_bf16x2(v2, v3));
   } else if constexpr (EPI == B200_EPI_F32) {
-    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col) = make_float4(v0, v1, v2, v3);
+    *reinterpret_cast<float4*>(c) = make_float4(v0, v1, v2, v3);
   } else if constexpr (EPI == B200_EPI_F32_ATOMIC) {
-    atomicAdd(reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col), make_float4(v0, v1, v2, v3));
+    atomicAdd(reinterpret_cast<float4*>(c), make_float4(v0, v1, v2, v3));
   } else if constexpr (EPI == B200_EPI_BIAS_GELU) {
     // u = bf16(acc + bias) (what nn.Linear returns under bf16 autocast); h = bf16(gelu(u))
-    const float u0 = bf16_round(v0), u1 = bf16_round(v1), u2 = bf16_round(v2), u3 = bf16_round(v3);
-    if (p.C2) {
-      uint2 o; o.x = pack_bf16x2(u0, u1); o.y = pack_bf16x2(u2, u3);
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C2) + (size_t)row * p.ldc2 + col) = o;
-    }
-    uint2 o; o.x = pack_bf16x2(gelu_erf(u0), gelu_erf(u1)); o.y = pack_bf16x2(gelu_erf(u2), gelu_erf(u3));
-    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col) = o;
+    const uint32_t p01 = pack_bf16x2(v0, v1), p23 = pack_bf16x2(v2, v3);
+    if (c2) *reinterpret_cast<uint2*>(c2) = make_uint2(p01, p23);
+    const float2 u01 = unpack_bf16x2(p01), u23 = unpack_bf16x2(p23);
+    *reinterpret_cast<uint2*>(c) = make_uint2(pack_bf16x2(gelu_erf(u01.x), gelu_erf(u01.y)), pack_bf16x2(gelu_erf(u23.x), gelu_erf(u23.y)));
   } else if constexpr (EPI == B200_EPI_RESIDUAL) {
     // o = bf16(acc + bias); x_out = x_in + gamma * o * rowscale   (fp32 residual stream)
-    const float o0 = bf16_round(v0), o1 = bf16_round(v1), o2 = bf16_round(v2), o3 = bf16_round(v3);
-    if (p.C2) {
-      uint2 o; o.x = pack_bf16x2(o0, o1); o.y = pack_bf16x2(o2, o3);
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C2) + (size_t)row * p.ldc2 + col) = o;
-    }
-    const float rs = p.rowscale ? __ldg(p.rowscale + row / p.rows_per_scale) : 1.0f;
+    const uint32_t p01 = pack_bf16x2(v0, v1), p23 = pack_bf16x2(v2, v3);
+    if (c2) *reinterpret_cast<uint2*>(c2) = make_uint2(p01, p23);
+    const float2 o01 = unpack_bf16x2(p01), o23 = unpack_bf16x2(p23);
     float4 x = aux4;
-    x.x += (o0 * gamma4.x) * rs; x.y += (o1 * gamma4.y) * rs; x.z += (o2 * gamma4.z) * rs; x.w += (o3 * gamma4.w) * rs;
-    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col) = x;
+    x.x += (o01.x * gamma4.x) * rs; x.y += (o01.y * gamma4.y) * rs; x.z += (o23.x * gamma4.z) * rs; x.w += (o23.y * gamma4.w) * rs;
+    *reinterpret_cast<float4*>(c) = x;
   } else if constexpr (EPI == B200_EPI_DGELU) {
     // dU = bf16( bf16(acc) * gelu'(u) ), u = aux (bf16 pre-activation saved by the forward)
     const float2 ua = unpack_bf16x2(__float_as_uint(aux4.x)), uc = unpack_bf16x2(__float_as_uint(aux4.y));
-    uint2 o;
-    o.x = pack_bf16x2(bf16_round(v0) * gelu_erf_grad(ua.x), bf16_round(v1) * gelu_erf_grad(ua.y));
-    o.y = pack_bf16x2(bf16_round(v2) * gelu_erf_grad(uc.x), bf16_round(v3) * gelu_erf_grad(uc.y));
-    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col) = o;
+    *reinterpret_cast<uint2*>(c) = make_uint2(pack_bf16x2(bf16_round(v0) * gelu_erf_grad(ua.x), bf16_round(v1) * gelu_erf_grad(ua.y)),
+                                              pack_bf16x2(bf16_round(v2) * gelu_erf_grad(uc.x), bf16_round(v3) * gelu_erf_grad(uc.y)));
   }
 }
 
-// global reads an epilogue needs for one 32-column chunk (8 rows per lane): the fp32 residual stream or the
+// global reads an epilogue needs for one 32-column chunk (8 row groups per lane): the fp32 residual stream or the
 // saved bf16 pre-activation.  They never alias the outputs, so they are issued a whole chunk ahead.
 template <int EPI>
-__device__ __forceinline__ void load_aux_chunk(const GemmDev& p, float4 (&aux4)[8], int row_base, int sub_row, int col) {
-  if constexpr (EPI == B200_EPI_RESIDUAL) {
+__device__ __forceinline__ void load_aux_chunk(float4 (&aux4)[8], const char* aux, long long step, int rows_valid, int sub_row, bool col_ok) {
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int row = row_base + it * 4 + sub_row;
-      aux4[it] = (row < p.M && col < p.N)
-                     ? __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) + (size_t)row * p.ldaux + col))
-                     : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  } else if constexpr (EPI == B200_EPI_DGELU) {
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int row = row_base + it * 4 + sub_row;
-      uint2 u = make_uint2(0u, 0u);
-      if (row < p.M && col < p.N)
-        u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + (size_t)row * p.ldaux + col));
+  for (int it = 0; it < 8; ++it) {
+    const bool ok = col_ok && (it * 4 + sub_row < rows_valid);
+    if constexpr (EPI == B200_EPI_RESIDUAL) {
+      aux4[it] = ok ? __ldg(reinterpret_cast<const float4*>(aux + it * step)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else if constexpr (EPI == B200_EPI_DGELU) {
+      const uint2 u = ok ? __ldg(reinterpret_cast<const uint2*>(aux + it * step)) : make_uint2(0u, 0u);
       aux4[it] = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), 0.f, 0.f);
     }
   }
@@ -161,9 +161,12 @@ __device__ __forceinline__ void epilogue_tile_t(const GemmDev& p, uint32_t tmem_
   constexpr int COLS_PER_WARP = BLOCK_N / 2;
   constexpr int NC = COLS_PER_WARP / 32;
   constexpr bool HAS_AUX = (EPI == B200_EPI_RESIDUAL || EPI == B200_EPI_DGELU);
+  constexpr int C_ESIZE = (EPI == B200_EPI_F32 || EPI == B200_EPI_F32_ATOMIC || EPI == B200_EPI_RESIDUAL) ? 4 : 2;
+  constexpr int AUX_ESIZE = (EPI == B200_EPI_RESIDUAL) ? 4 : 2;
   const int sub_row = lane >> 3;  // 0..3 : row within a 4-row group after the transpose
   const int g4 = lane & 7;        // 0..7 : which float4 (4 columns) of the 32-column chunk
-  const int row_base = m0 + quarter * 32;
+  const int row_first = m0 + quarter * 32 + sub_row;
+  const int rows_valid = p.M - (m0 + quarter * 32);  // rows r (0..31) of this warp are valid iff r < rows_valid
   const int col0 = n0 + half * COLS_PER_WARP + g4 * 4;
   float4 bias4[NC], gamma4[NC];
 #pragma unroll
@@ -173,36 +176,51 @@ __device__ __forceinline__ void epilogue_tile_t(const GemmDev& p, uint32_t tmem_
     gamma4[c] = (EPI == B200_EPI_RESIDUAL && p.gamma && col < p.N) ? __ldg(reinterpret_cast<const float4*>(p.gamma + col))
                                                                     : make_float4(1.f, 1.f, 1.f, 1.f);
   }
+  char* c_base = reinterpret_cast<char*>(p.C) + ((size_t)row_first * p.ldc + col0) * C_ESIZE;
+  char* c2_base = p.C2 ? reinterpret_cast<char*>(p.C2) + ((size_t)row_first * p.ldc2 + col0) * 2 : nullptr;
+  const char* aux_base = HAS_AUX ? reinterpret_cast<const char*>(p.aux) + ((size_t)row_first * p.ldaux + col0) * AUX_ESIZE : nullptr;
+  const long long c_step = 4 * p.ldc * C_ESIZE, c2_step = 8 * p.ldc2, aux_step = 4 * p.ldaux * AUX_ESIZE;
+  float rs[8];
+  if constexpr (EPI == B200_EPI_RESIDUAL) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it)
+      rs[it] = (p.rowscale && it * 4 + sub_row < rows_valid) ? __ldg(p.rowscale + (row_first + it * 4) / p.rows_per_scale) : 1.0f;
+  }
   float4 aux_cur[8], aux_nxt[8];
-  if constexpr (HAS_AUX) load_aux_chunk<EPI>(p, aux_nxt, row_base, sub_row, col0);
+  if constexpr (HAS_AUX) load_aux_chunk<EPI>(aux_nxt, aux_base, aux_step, rows_valid, sub_row, col0 < p.N);
 
   mbar_wait(tmem_full_bar, full_phase);
   tc_fence_after();
   const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16) + half * COLS_PER_WARP;
+  const uint32_t stg_w = smem_u32(stg) + lane * 128;                              // this lane's row (write side)
+  const uint32_t stg_r = smem_u32(stg) + sub_row * 128;                           // first row of the read side
   uint32_t v[32];
   tmem_ld_32x32(taddr, v);
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     tmem_ld_wait();
     // transpose through smem: thread (= row `lane`) writes its 32 columns; XOR swizzle keeps both the
-    // row-wise float4 writes and the column-group reads bank-conflict free
+    // row-wise 16-byte writes and the column-group reads bank-conflict free
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    for (int j = 0; j < 8; ++j) sts128(stg_w + ((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     if (c + 1 < NC) tmem_ld_32x32(taddr + (c + 1) * 32, v);
     __syncwarp();
+    const bool col_ok = col0 + c * 32 < p.N;  // N % 8 == 0 and col % 4 == 0 -> the 4 columns are all valid
     if constexpr (HAS_AUX) {
 #pragma unroll
       for (int it = 0; it < 8; ++it) aux_cur[it] = aux_nxt[it];
-      if (c + 1 < NC) load_aux_chunk<EPI>(p, aux_nxt, row_base, sub_row, col0 + (c + 1) * 32);
+      if (c + 1 < NC) load_aux_chunk<EPI>(aux_nxt, aux_base + (c + 1) * 32 * AUX_ESIZE, aux_step, rows_valid, sub_row, col0 + (c + 1) * 32 < p.N);
     }
-    const int col = col0 + c * 32;
-    if (col < p.N) {  // N % 8 == 0 and col % 4 == 0 -> the 4 columns are all valid
+    if (col_ok) {
+      char* cp = c_base + c * 32 * C_ESIZE;
+      char* c2p = c2_base ? c2_base + c * 64 : nullptr;
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const int r = it * 4 + sub_row;
-        const float4 a4 = *reinterpret_cast<const float4*>(stg + r * 32 + ((g4 ^ (r & 7)) << 2));
-        if (row_base + r < p.M) epilogue_vec4<EPI>(p, a4, row_base + r, col, bias4[c], gamma4[c], aux_cur[it]);
+        const float4 a4 = lds128(stg_r + it * 512 + ((g4 ^ (r & 7)) << 4));
+        if (r < rows_valid) epilogue_vec4<EPI>(p, a4, cp, c2p, (EPI == B200_EPI_RESIDUAL) ? rs[it] : 1.0f, bias4[c], gamma4[c], aux_cur[it]);
+        cp += c_step;
+        if (c2p) c2p += c2_step;
       }
     }
     __syncwarp();

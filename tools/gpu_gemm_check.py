@@ -93,7 +93,7 @@ for epi in (EPI_BF16, EPI_F32, EPI_BIAS_GELU, EPI_RESIDUAL, EPI_DGELU):
 run(4403, 4096, 256, ws_mode=1)                      # K=256 -> 256-wide slab
 run(1300, 392, 200, epi=EPI_F32, ws_mode=1)          # tails in M, N, K
 run(2500, 1536, 384, b_mn=True, epi=EPI_DGELU, ws_mode=1)
-run(2500, 384, 384, a_mn=True, b_mn=True, epi=EPI_F32, ws_mode=1)
+run(2504, 384, 384, a_mn=True, b_mn=True, epi=EPI_F32, ws_mode=1)
 run(25216, 1152, 384, ws_mode=0)
 # fused epilogues
 run(1000, 1536, 384, epi=EPI_BIAS_GELU)
