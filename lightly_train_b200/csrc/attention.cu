@@ -184,10 +184,25 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, int N, 
   }
 }
 
+// D[bh, n] = sum_d dO[b,n,h,d] * O[b,n,h,d]  (== sum_j dP_ij P_ij), one warp per token, all heads.
+__global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
+                                                            long long ld_out, int B, int N, int h, float* __restrict__ dvec) {
+  const long long tok = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (tok >= (long long)B * N) return;
+  const int lane = threadIdx.x & 31;
+  const int b = (int)(tok / N), n = (int)(tok % N);
+  for (int head = 0; head < h; ++head) {
+    const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dout + (size_t)tok * ld_out + head * HD + lane * 2));
+    const float2 c = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(o + (size_t)tok * ld_out + head * HD + lane * 2));
+    const float acc = warp_sum(a.x * c.x + a.y * c.y);
+    if (lane == 0) dvec[((size_t)b * h + head) * N + n] = acc;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 template <int NKV16, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
-attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, const __nv_bfloat16* __restrict__ o,
+attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, const float* __restrict__ dvec,
                 const __nv_bfloat16* __restrict__ dout, long long ld_out, const float* __restrict__ lse, int N, int h,
                 float scale, __nv_bfloat16* __restrict__ dqkv, long long ld_dtok) {
   constexpr int NP = NKV16 * 16;
@@ -200,21 +215,14 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, const _
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const __nv_bfloat16* base = qkv + (size_t)b * N * ld_tok + head * HD;
   const __nv_bfloat16* dob = dout + (size_t)b * N * ld_out + head * HD;
-  const __nv_bfloat16* ob = o + (size_t)b * N * ld_out + head * HD;
   load_panel(sQ, base, ld_tok, N, NP);
   load_panel(sK, base + (size_t)h * HD, ld_tok, N, NP);
   load_panel(sV, base + (size_t)2 * h * HD, ld_tok, N, NP);
   load_panel(sDO, dob, ld_out, N, NP);
-  // D_i = sum_d dO[i,d] * O[i,d]  (== sum_j dP_ij P_ij), one warp per row, 2 elements per lane
-  for (int r = warp; r < NP; r += WARPS) {
-    float acc = 0.f;
-    if (r < N) {
-      float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dob + (size_t)r * ld_out + lane * 2));
-      float2 c = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(ob + (size_t)r * ld_out + lane * 2));
-      acc = a.x * c.x + a.y * c.y;
-    }
-    acc = warp_sum(acc);
-    if (lane == 0) { sD[r] = acc; sL[r] = (r < N) ? lse[(size_t)bh * N + r] : 0.f; }
+  for (int r = threadIdx.x; r < NP; r += blockDim.x) {
+    const bool ok = r < N;
+    sD[r] = ok ? dvec[(size_t)bh * N + r] : 0.f;
+    sL[r] = ok ? lse[(size_t)bh * N + r] : 0.f;
   }
   cp_async_wait_all();
   __syncthreads();
@@ -353,7 +361,7 @@ static int launch_fwd(const void* qkv, long long ld_tok, int B, int N, int h, fl
   return B200_OK;
 }
 template <int NKV16, int WARPS>
-static int launch_bwd(const void* qkv, long long ld_tok, const void* o, const void* dout, long long ld_out, const float* lse,
+static int launch_bwd(const void* qkv, long long ld_tok, const float* dvec, const void* dout, long long ld_out, const float* lse,
                       int B, int N, int h, float scale, void* dqkv, long long ld_dtok, cudaStream_t s) {
   constexpr int NP = NKV16 * 16;
   const int smem = 4 * NP * 128 + WARPS * 2048 + 2 * NP * 4;
@@ -363,8 +371,8 @@ static int launch_bwd(const void* qkv, long long ld_tok, const void* o, const vo
       return B200_ERR_CUDA;
     attr = true;
   }
-  attn_bwd_kernel<NKV16, WARPS><<<B * h, WARPS * 32, smem, s>>>((const __nv_bfloat16*)qkv, ld_tok, (const __nv_bfloat16*)o,
-                                                          (const __nv_bfloat16*)dout, ld_out, lse, N, h, scale,
+  attn_bwd_kernel<NKV16, WARPS><<<B * h, WARPS * 32, smem, s>>>((const __nv_bfloat16*)qkv, ld_tok, dvec,
+                                                                 (const __nv_bfloat16*)dout, ld_out, lse, N, h, scale,
                                                           (__nv_bfloat16*)dqkv, ld_dtok);
   B200_CHECK_LAUNCH();
   return B200_OK;
@@ -389,14 +397,17 @@ extern "C" int b200_attention_fwd(const void* qkv, long long ld_tok, int B, int 
 
 extern "C" int b200_attention_bwd(const void* qkv, long long ld_tok, const void* out, const void* dout, long long ld_out,
                                   const float* lse, int B, int N, int h, int head_dim, float scale, void* dqkv,
-                                  long long ld_dtok, void* stream) {
-  if (!qkv || !out || !dout || !lse || !dqkv || B <= 0 || N <= 0 || h <= 0) return B200_ERR_INVALID_ARG;
+                                  long long ld_dtok, float* dvec_ws, void* stream) {
+  if (!qkv || !out || !dout || !lse || !dqkv || !dvec_ws || B <= 0 || N <= 0 || h <= 0) return B200_ERR_INVALID_ARG;
   if (head_dim != HD || (ld_tok % 8) || (ld_out % 8) || (ld_dtok % 8)) return B200_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
   const int nb = (N + 15) / 16;
-  if (nb <= 3) return launch_bwd<3, 4>(qkv, ld_tok, out, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
-  if (nb <= 4) return launch_bwd<4, 4>(qkv, ld_tok, out, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
-  if (nb <= 13) return launch_bwd<13, 8>(qkv, ld_tok, out, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
-  if (nb <= 17) return launch_bwd<17, 8>(qkv, ld_tok, out, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
+  if (nb > 17) return B200_ERR_UNSUPPORTED;
+  attn_bwd_prep_kernel<<<(unsigned)(((long long)B * N + 7) / 8), 256, 0, s>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, ld_out, B, N, h, dvec_ws);
+  B200_CHECK_LAUNCH();
+  if (nb <= 3) return launch_bwd<3, 4>(qkv, ld_tok, dvec_ws, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
+  if (nb <= 4) return launch_bwd<4, 4>(qkv, ld_tok, dvec_ws, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
+  if (nb <= 13) return launch_bwd<13, 8>(qkv, ld_tok, dvec_ws, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
+  if (nb <= 17) return launch_bwd<17, 8>(qkv, ld_tok, dvec_ws, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
   return B200_ERR_UNSUPPORTED;
 }

@@ -108,9 +108,10 @@ def attention_fwd(qkv: torch.Tensor, B: int, N: int, h: int, out: torch.Tensor, 
 def attention_bwd(qkv, out, dout, lse, B: int, N: int, h: int, dqkv, scale: float) -> None:
     _req_cuda(qkv, out, dout, lse, dqkv)
     assert out.stride(0) == dout.stride(0)
+    ws = torch.empty(B * h * N, device=qkv.device, dtype=torch.float32)
     check(_L().b200_attention_bwd(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), dout.data_ptr(), dout.stride(0),
-                                  lse.data_ptr(), B, N, h, 64, scale, dqkv.data_ptr(), dqkv.stride(0), _stream()),
-          "b200_attention_bwd")
+                                  lse.data_ptr(), B, N, h, 64, scale, dqkv.data_ptr(), dqkv.stride(0), ws.data_ptr(),
+                                  _stream()), "b200_attention_bwd")
 
 
 def layernorm_fwd(x, w, b, eps: float, y, mean=None, rstd=None) -> None:

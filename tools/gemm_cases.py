@@ -22,7 +22,18 @@ out_h, out_u = torch.empty(T, H, device=dev, dtype=bf), torch.empty(T, H, device
 out_du = torch.empty(T, H, device=dev, dtype=bf)
 
 
+B_, N_, h_ = 128, 197, 6
+qkv_att = torch.randn(B_ * N_, 3 * D, device=dev).to(bf)
+att_out = torch.empty(B_ * N_, D, device=dev, dtype=bf)
+att_lse = torch.empty(B_ * h_, N_, device=dev)
+datt = torch.randn(B_ * N_, D, device=dev).to(bf)
+dqkv = torch.empty_like(qkv_att)
+
+
 def cases():
+    ops.attention_fwd(qkv_att, B_, N_, h_, att_out, att_lse, 0.125)
+    ops.attention_bwd(qkv_att, att_out, datt, att_lse, B_, N_, h_, dqkv, 0.125)
+    ops.gemm(x, wqkv, out_qkv, bias=b3, ws_mode=2)                                           # qkv generic schedule
     ops.gemm(x, wqkv, out_qkv, bias=b3)                                                      # qkv
     ops.gemm(x, wproj, out_res, epi=ops.EPI_RESIDUAL, bias=b1, out2=out_o, aux=res, gamma=gamma)  # proj
     ops.gemm(x, w1, out_h, epi=ops.EPI_BIAS_GELU, bias=bh, out2=out_u)                        # fc1
