@@ -156,7 +156,7 @@ __device__ __forceinline__ void load_aux_chunk(float4 (&aux4)[8], const char* au
 // Software pipeline per warp: bias/gamma and the first chunk's aux reads are issued before the accumulator is
 // ready; tcgen05.ld of chunk c+1 and the aux reads of chunk c+1 are in flight while chunk c is stored.
 template <int BLOCK_N, int EPI>
-__device__ __forceinline__ void epilogue_tile_t(const GemmDev& p, uint32_t tmem_acc, uint64_t* tmem_full_bar, uint32_t full_phase,
+__device__ __noinline__ void epilogue_tile_t(const GemmDev& p, uint32_t tmem_acc, uint64_t* tmem_full_bar, uint32_t full_phase,
                                                 int m0, int n0, int quarter, int half, int lane, float* stg) {
   constexpr int COLS_PER_WARP = BLOCK_N / 2;
   constexpr int NC = COLS_PER_WARP / 32;
@@ -330,7 +330,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // every operand below is warp-uniform; one elected lane issues (keeps descriptors in uniform registers)
     const uint32_t idesc = make_idesc(BLOCK_N, p.a_mn, p.b_mn);
+    // K-major:  SBO = 8 rows * 128 B;                         K-step = 32 B inside the swizzle atom
+    // MN-major: LBO = BLOCK_K*128 B between 64-wide MN atoms, SBO = 8 k-rows * 128 B, K-step = 16 k-rows * 128 B
+    const uint32_t smem0 = smem_u32(smem);
+    const uint64_t adesc_base = p.a_mn ? make_smem_desc(smem0, BLOCK_K * 128, 1024) : make_smem_desc(smem0, 16, 1024);
+    const uint64_t bdesc_base = p.b_mn ? make_smem_desc(smem0 + Cfg::A_BYTES, BLOCK_K * 128, 1024)
+                                       : make_smem_desc(smem0 + Cfg::A_BYTES, 16, 1024);
+    const uint32_t a_step = p.a_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+    const uint32_t b_step = p.b_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -345,21 +354,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t sb = sa + Cfg::A_BYTES;
-          // K-major:  SBO = 8 rows * 128 B;                         K-step = 32 B inside the atom
-          // MN-major: LBO = BLOCK_K*128 B between 64-wide MN atoms, SBO = 8 k-rows * 128 B,
-          //           K-step = 16 k-rows * 128 B
-          const uint64_t adesc0 = p.a_mn ? make_smem_desc(sa, BLOCK_K * 128, 1024) : make_smem_desc(sa, 16, 1024);
-          const uint64_t bdesc0 = p.b_mn ? make_smem_desc(sb, BLOCK_K * 128, 1024) : make_smem_desc(sb, 16, 1024);
-          const uint32_t a_step = p.a_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
-          const uint32_t b_step = p.b_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            umma_f16(tmem_d, adesc0 + (uint64_t)(k * a_step), bdesc0 + (uint64_t)(k * b_step), idesc,
-                     (kb > kb0 || k > 0) ? 1u : 0u);
-          }
+        const uint64_t ad = adesc_base + (uint64_t)((stage * Cfg::STAGE_BYTES) >> 4);
+        const uint64_t bd = bdesc_base + (uint64_t)((stage * Cfg::STAGE_BYTES) >> 4);
+        if (elect_one_sync()) {
+          umma_f16(tmem_d, ad, bd, idesc, (kb > kb0) ? 1u : 0u);
+          umma_f16(tmem_d, ad + a_step, bd + b_step, idesc, 1u);
+          umma_f16(tmem_d, ad + 2 * a_step, bd + 2 * b_step, idesc, 1u);
+          umma_f16(tmem_d, ad + 3 * a_step, bd + 3 * b_step, idesc, 1u);
           umma_commit(&empty_bar[stage]);  // frees the smem slot when the MMAs above retire
           if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
         }
@@ -504,6 +505,10 @@ gemm_tcgen05_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = make_idesc(BLOCK_N, p.a_mn, p.b_mn);
+    const uint64_t adesc_base = p.a_mn ? make_smem_desc(smem_u32(ring), BLOCK_K * 128, 1024) : make_smem_desc(smem_u32(ring), 16, 1024);
+    const uint64_t bdesc_base = p.b_mn ? make_smem_desc(smem_u32(panel), BLOCK_K * 128, 1024) : make_smem_desc(smem_u32(panel), 16, 1024);
+    const uint32_t a_step = p.a_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+    const uint32_t b_step = p.b_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
     int stage = 0;
     uint32_t phase = 0, b_full_phase = 0;
     int acc = 0;
@@ -519,16 +524,13 @@ gemm_tcgen05_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       for (int kb = 0; kb < kb_total; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(ring + stage * Cfg::A_BYTES);
-          const uint32_t sb = smem_u32(panel + kb * Cfg::B_BYTES);
-          const uint64_t adesc0 = p.a_mn ? make_smem_desc(sa, BLOCK_K * 128, 1024) : make_smem_desc(sa, 16, 1024);
-          const uint64_t bdesc0 = p.b_mn ? make_smem_desc(sb, BLOCK_K * 128, 1024) : make_smem_desc(sb, 16, 1024);
-          const uint32_t a_step = p.a_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
-          const uint32_t b_step = p.b_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            umma_f16(tmem_d, adesc0 + (uint64_t)(k * a_step), bdesc0 + (uint64_t)(k * b_step), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        const uint64_t ad = adesc_base + (uint64_t)((stage * Cfg::A_BYTES) >> 4);
+        const uint64_t bd = bdesc_base + (uint64_t)((kb * Cfg::B_BYTES) >> 4);
+        if (elect_one_sync()) {
+          umma_f16(tmem_d, ad, bd, idesc, (kb > 0) ? 1u : 0u);
+          umma_f16(tmem_d, ad + a_step, bd + b_step, idesc, 1u);
+          umma_f16(tmem_d, ad + 2 * a_step, bd + 2 * b_step, idesc, 1u);
+          umma_f16(tmem_d, ad + 3 * a_step, bd + 3 * b_step, idesc, 1u);
           umma_commit(&empty_bar[stage]);
           if (kb == kb_total - 1) {
             umma_commit(&tmem_full[acc]);
