@@ -299,6 +299,13 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, const f
 #pragma unroll 1
     for (int i = 0; i < nt; ++i) {
       float st[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}}, dpt[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+      float2 Lv[2], Dv2[2];  // per-query-column log-sum-exp and D, fetched ahead of the MMAs
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int qc = i * 16 + t * 8 + (lane & 3) * 2;
+        Lv[t] = *reinterpret_cast<const float2*>(sL + qc);
+        Dv2[t] = *reinterpret_cast<const float2*>(sD + qc);
+      }
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         uint32_t bq[4], bdo[4];
@@ -319,9 +326,10 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, const f
           const int q = qc + (e & 1);
           const int kr = kr0 + ((e >> 1) ? 8 : 0);
           const bool valid = (q < N) && (kr < N);
-          const float p = valid ? __expf(bf16_round(st[t][e] * scale) - sL[q]) : 0.f;
+          const float Lq = (e & 1) ? Lv[t].y : Lv[t].x, Dq = (e & 1) ? Dv2[t].y : Dv2[t].x;
+          const float p = valid ? __expf(bf16_round(st[t][e] * scale) - Lq) : 0.f;
           pt[t][e] = p;
-          dst_[t][e] = p * (bf16_round(dpt[t][e]) - sD[q]);
+          dst_[t][e] = p * (bf16_round(dpt[t][e]) - Dq);
         }
       }
       apt[0] = pack_bf16x2(pt[0][0], pt[0][1]); apt[1] = pack_bf16x2(pt[0][2], pt[0][3]);
@@ -407,7 +415,7 @@ extern "C" int b200_attention_bwd(const void* qkv, long long ld_tok, const void*
   B200_CHECK_LAUNCH();
   if (nb <= 3) return launch_bwd<3, 4>(qkv, ld_tok, dvec_ws, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
   if (nb <= 4) return launch_bwd<4, 4>(qkv, ld_tok, dvec_ws, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
-  if (nb <= 13) return launch_bwd<13, 8>(qkv, ld_tok, dvec_ws, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
-  if (nb <= 17) return launch_bwd<17, 8>(qkv, ld_tok, dvec_ws, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
+  if (nb <= 13) return launch_bwd<13, 13>(qkv, ld_tok, dvec_ws, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
+  if (nb <= 17) return launch_bwd<17, 9>(qkv, ld_tok, dvec_ws, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
   return B200_ERR_UNSUPPORTED;
 }
