@@ -104,10 +104,10 @@ struct EpiPtrs {
 };
 
 template <int EPI>
-__device__ __forceinline__ void epilogue_vec4(const GemmDev& p, float4 acc, char* c, char* c2, float rs, const float4& bias4,
+__device__ __forceinline__ void epilogue_vec4(float alpha, float4 acc, char* c, char* c2, float rs, const float4& bias4,
                                               const float4& gamma4, const float4& aux4) {
-  const float v0 = fmaf(acc.x, p.alpha, bias4.x), v1 = fmaf(acc.y, p.alpha, bias4.y), v2 = fmaf(acc.z, p.alpha, bias4.z),
-              v3 = fmaf(acc.w, p.alpha, bias4.w);
+  const float v0 = fmaf(acc.x, alpha, bias4.x), v1 = fmaf(acc.y, alpha, bias4.y), v2 = fmaf(acc.z, alpha, bias4.z),
+              v3 = fmaf(acc.w, alpha, bias4.w);
   if constexpr (EPI == B200_EPI_BF16) {
     *reinterpret_cast<uint2*>(c) = make_uint2(pack_bf16x2(v0, v1), pack_bf16x2(v2, v3));
   } else if constexpr (EPI == B200_EPI_F32) {
@@ -152,91 +152,125 @@ __device__ __forceinline__ void load_aux_chunk(float4 (&aux4)[8], const char* au
   }
 }
 
-// One 128 x BLOCK_N accumulator tile: TMEM -> registers -> smem transpose -> fused epilogue -> global.
-// Software pipeline per warp: bias/gamma and the first chunk's aux reads are issued before the accumulator is
-// ready; tcgen05.ld of chunk c+1 and the aux reads of chunk c+1 are in flight while chunk c is stored.
+// The epilogue role of one warp, for the whole persistent loop over work items w = w_begin, w_begin+w_step, ...
+// (tile = w / n_splits, m-tile = tile % tiles_m, n-tile = tile / tiles_m in both schedules).
+// Per tile: TMEM -> registers -> smem transpose -> fused epilogue -> global.
+//  * __noinline__ + by-value arguments: each EPI variant gets its own register allocation and reads no kernel
+//    parameter from memory inside the loop;
+//  * bias / gamma live in registers across tiles and are re-read only when the n-tile changes;
+//  * software pipeline: the first chunk's aux reads are issued before the accumulator is ready; tcgen05.ld and the
+//    aux reads of chunk c+1 are in flight while chunk c is stored.
+struct EpiSched {
+  int w_begin, w_end, w_step, n_splits, tiles_m;
+};
+
 template <int BLOCK_N, int EPI>
-__device__ __noinline__ void epilogue_tile_t(const GemmDev& p, uint32_t tmem_acc, uint64_t* tmem_full_bar, uint32_t full_phase,
-                                                int m0, int n0, int quarter, int half, int lane, float* stg) {
+__device__ __noinline__ void epilogue_role(const GemmDev p, const EpiSched sc, const uint32_t tmem_base, uint64_t* tmem_full,
+                                           uint64_t* tmem_empty, const int quarter, const int half, const int lane, float* stg) {
   constexpr int COLS_PER_WARP = BLOCK_N / 2;
   constexpr int NC = COLS_PER_WARP / 32;
   constexpr bool HAS_AUX = (EPI == B200_EPI_RESIDUAL || EPI == B200_EPI_DGELU);
   constexpr int C_ESIZE = (EPI == B200_EPI_F32 || EPI == B200_EPI_F32_ATOMIC || EPI == B200_EPI_RESIDUAL) ? 4 : 2;
   constexpr int AUX_ESIZE = (EPI == B200_EPI_RESIDUAL) ? 4 : 2;
+  constexpr int ACC_STRIDE = 256;
+  // kernel parameters -> registers once (this function is not inlined: `p` arrives through the stack)
+  const int M = p.M, N = p.N, rows_per_scale = p.rows_per_scale;
+  const float alpha = p.alpha;
+  char* const C = reinterpret_cast<char*>(p.C);
+  char* const C2 = reinterpret_cast<char*>(p.C2);
+  const char* const AUX = reinterpret_cast<const char*>(p.aux);
+  const float* const bias = p.bias;
+  const float* const gamma = p.gamma;
+  const float* const rowscale = p.rowscale;
+  const long long ldc = p.ldc, ldc2 = p.ldc2, ldaux = p.ldaux;
   const int sub_row = lane >> 3;  // 0..3 : row within a 4-row group after the transpose
   const int g4 = lane & 7;        // 0..7 : which float4 (4 columns) of the 32-column chunk
-  const int row_first = m0 + quarter * 32 + sub_row;
-  const int rows_valid = p.M - (m0 + quarter * 32);  // rows r (0..31) of this warp are valid iff r < rows_valid
-  const int col0 = n0 + half * COLS_PER_WARP + g4 * 4;
+  const long long c_step = 4 * ldc * C_ESIZE, c2_step = 8 * ldc2, aux_step = 4 * ldaux * AUX_ESIZE;
+  const uint32_t stg_w = smem_u32(stg) + lane * 128;     // this lane's row (write side of the transpose)
+  const uint32_t stg_r = smem_u32(stg) + sub_row * 128;  // first row of the read side
   float4 bias4[NC], gamma4[NC];
+  int cur_n0 = -1;
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  for (int w = sc.w_begin; w < sc.w_end; w += sc.w_step) {
+    const int tile = w / sc.n_splits;
+    const int m0 = (tile % sc.tiles_m) * BLOCK_M, n0 = (tile / sc.tiles_m) * BLOCK_N;
+    const int row_first = m0 + quarter * 32 + sub_row;
+    const int rows_valid = M - (m0 + quarter * 32);  // rows r (0..31) of this warp are valid iff r < rows_valid
+    const int col0 = n0 + half * COLS_PER_WARP + g4 * 4;
+    if (n0 != cur_n0) {
+      cur_n0 = n0;
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    const int col = col0 + c * 32;
-    bias4[c] = (p.bias && col < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    gamma4[c] = (EPI == B200_EPI_RESIDUAL && p.gamma && col < p.N) ? __ldg(reinterpret_cast<const float4*>(p.gamma + col))
-                                                                    : make_float4(1.f, 1.f, 1.f, 1.f);
-  }
-  char* c_base = reinterpret_cast<char*>(p.C) + ((size_t)row_first * p.ldc + col0) * C_ESIZE;
-  char* c2_base = p.C2 ? reinterpret_cast<char*>(p.C2) + ((size_t)row_first * p.ldc2 + col0) * 2 : nullptr;
-  const char* aux_base = HAS_AUX ? reinterpret_cast<const char*>(p.aux) + ((size_t)row_first * p.ldaux + col0) * AUX_ESIZE : nullptr;
-  const long long c_step = 4 * p.ldc * C_ESIZE, c2_step = 8 * p.ldc2, aux_step = 4 * p.ldaux * AUX_ESIZE;
-  float rs[8];
-  if constexpr (EPI == B200_EPI_RESIDUAL) {
-#pragma unroll
-    for (int it = 0; it < 8; ++it)
-      rs[it] = (p.rowscale && it * 4 + sub_row < rows_valid) ? __ldg(p.rowscale + (row_first + it * 4) / p.rows_per_scale) : 1.0f;
-  }
-  float4 aux_cur[8], aux_nxt[8];
-  if constexpr (HAS_AUX) load_aux_chunk<EPI>(aux_nxt, aux_base, aux_step, rows_valid, sub_row, col0 < p.N);
-
-  mbar_wait(tmem_full_bar, full_phase);
-  tc_fence_after();
-  const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16) + half * COLS_PER_WARP;
-  const uint32_t stg_w = smem_u32(stg) + lane * 128;                              // this lane's row (write side)
-  const uint32_t stg_r = smem_u32(stg) + sub_row * 128;                           // first row of the read side
-  uint32_t v[32];
-  tmem_ld_32x32(taddr, v);
-#pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    tmem_ld_wait();
-    // transpose through smem: thread (= row `lane`) writes its 32 columns; XOR swizzle keeps both the
-    // row-wise 16-byte writes and the column-group reads bank-conflict free
-#pragma unroll
-    for (int j = 0; j < 8; ++j) sts128(stg_w + ((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    if (c + 1 < NC) tmem_ld_32x32(taddr + (c + 1) * 32, v);
-    __syncwarp();
-    const bool col_ok = col0 + c * 32 < p.N;  // N % 8 == 0 and col % 4 == 0 -> the 4 columns are all valid
-    if constexpr (HAS_AUX) {
-#pragma unroll
-      for (int it = 0; it < 8; ++it) aux_cur[it] = aux_nxt[it];
-      if (c + 1 < NC) load_aux_chunk<EPI>(aux_nxt, aux_base + (c + 1) * 32 * AUX_ESIZE, aux_step, rows_valid, sub_row, col0 + (c + 1) * 32 < p.N);
-    }
-    if (col_ok) {
-      char* cp = c_base + c * 32 * C_ESIZE;
-      char* c2p = c2_base ? c2_base + c * 64 : nullptr;
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int r = it * 4 + sub_row;
-        const float4 a4 = lds128(stg_r + it * 512 + ((g4 ^ (r & 7)) << 4));
-        if (r < rows_valid) epilogue_vec4<EPI>(p, a4, cp, c2p, (EPI == B200_EPI_RESIDUAL) ? rs[it] : 1.0f, bias4[c], gamma4[c], aux_cur[it]);
-        cp += c_step;
-        if (c2p) c2p += c2_step;
+      for (int c = 0; c < NC; ++c) {
+        const int col = col0 + c * 32;
+        bias4[c] = (bias && col < N) ? __ldg(reinterpret_cast<const float4*>(bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        gamma4[c] = (EPI == B200_EPI_RESIDUAL && gamma && col < N) ? __ldg(reinterpret_cast<const float4*>(gamma + col))
+                                                                        : make_float4(1.f, 1.f, 1.f, 1.f);
       }
     }
+    char* c_base = C + ((size_t)row_first * ldc + col0) * C_ESIZE;
+    char* c2_base = C2 ? C2 + ((size_t)row_first * ldc2 + col0) * 2 : nullptr;
+    const char* aux_base = HAS_AUX ? AUX + ((size_t)row_first * ldaux + col0) * AUX_ESIZE : nullptr;
+    float rs[8];
+    if constexpr (EPI == B200_EPI_RESIDUAL) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it)
+        rs[it] = (rowscale && it * 4 + sub_row < rows_valid) ? __ldg(rowscale + (row_first + it * 4) / rows_per_scale) : 1.0f;
+    }
+    float4 aux_cur[8], aux_nxt[8];
+    if constexpr (HAS_AUX) load_aux_chunk<EPI>(aux_nxt, aux_base, aux_step, rows_valid, sub_row, col0 < N);
+
+    mbar_wait(&tmem_full[acc], acc_phase);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16) + half * COLS_PER_WARP;
+    uint32_t v[32];
+    tmem_ld_32x32(taddr, v);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      tmem_ld_wait();
+      // transpose through smem: thread (= row `lane`) writes its 32 columns; XOR swizzle keeps both the
+      // row-wise 16-byte writes and the column-group reads bank-conflict free
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sts128(stg_w + ((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      if (c + 1 < NC) tmem_ld_32x32(taddr + (c + 1) * 32, v);
+      __syncwarp();
+      const bool col_ok = col0 + c * 32 < N;  // N % 8 == 0 and col % 4 == 0 -> the 4 columns are all valid
+      if constexpr (HAS_AUX) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) aux_cur[it] = aux_nxt[it];
+        if (c + 1 < NC) load_aux_chunk<EPI>(aux_nxt, aux_base + (c + 1) * 32 * AUX_ESIZE, aux_step, rows_valid, sub_row, col0 + (c + 1) * 32 < N);
+      }
+      if (col_ok) {
+        char* cp = c_base + c * 32 * C_ESIZE;
+        char* c2p = c2_base ? c2_base + c * 64 : nullptr;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + sub_row;
+          const float4 a4 = lds128(stg_r + it * 512 + ((g4 ^ (r & 7)) << 4));
+          if (r < rows_valid) epilogue_vec4<EPI>(alpha, a4, cp, c2p, (EPI == B200_EPI_RESIDUAL) ? rs[it] : 1.0f, bias4[c], gamma4[c], aux_cur[it]);
+          cp += c_step;
+          if (c2p) c2p += c2_step;
+        }
+      }
+      __syncwarp();
+    }
+    tc_fence_before();
     __syncwarp();
+    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    if ((acc ^= 1) == 0) acc_phase ^= 1;
   }
 }
 
 template <int BLOCK_N>
-__device__ __forceinline__ void epilogue_tile(const GemmDev& p, uint32_t tmem_acc, uint64_t* tmem_full_bar, uint32_t full_phase,
-                                              int m0, int n0, int quarter, int half, int lane, float* stg) {
-  switch (p.epi) {  // warp-uniform, once per tile
-    case B200_EPI_BF16: epilogue_tile_t<BLOCK_N, B200_EPI_BF16>(p, tmem_acc, tmem_full_bar, full_phase, m0, n0, quarter, half, lane, stg); break;
-    case B200_EPI_F32: epilogue_tile_t<BLOCK_N, B200_EPI_F32>(p, tmem_acc, tmem_full_bar, full_phase, m0, n0, quarter, half, lane, stg); break;
-    case B200_EPI_F32_ATOMIC: epilogue_tile_t<BLOCK_N, B200_EPI_F32_ATOMIC>(p, tmem_acc, tmem_full_bar, full_phase, m0, n0, quarter, half, lane, stg); break;
-    case B200_EPI_BIAS_GELU: epilogue_tile_t<BLOCK_N, B200_EPI_BIAS_GELU>(p, tmem_acc, tmem_full_bar, full_phase, m0, n0, quarter, half, lane, stg); break;
-    case B200_EPI_RESIDUAL: epilogue_tile_t<BLOCK_N, B200_EPI_RESIDUAL>(p, tmem_acc, tmem_full_bar, full_phase, m0, n0, quarter, half, lane, stg); break;
-    default: epilogue_tile_t<BLOCK_N, B200_EPI_DGELU>(p, tmem_acc, tmem_full_bar, full_phase, m0, n0, quarter, half, lane, stg); break;
+__device__ __forceinline__ void run_epilogue_role(const GemmDev& p, const EpiSched& sc, uint32_t tmem_base, uint64_t* tmem_full,
+                                                  uint64_t* tmem_empty, int quarter, int half, int lane, float* stg) {
+  switch (p.epi) {  // warp-uniform, once per kernel
+    case B200_EPI_BF16: epilogue_role<BLOCK_N, B200_EPI_BF16>(p, sc, tmem_base, tmem_full, tmem_empty, quarter, half, lane, stg); break;
+    case B200_EPI_F32: epilogue_role<BLOCK_N, B200_EPI_F32>(p, sc, tmem_base, tmem_full, tmem_empty, quarter, half, lane, stg); break;
+    case B200_EPI_F32_ATOMIC: epilogue_role<BLOCK_N, B200_EPI_F32_ATOMIC>(p, sc, tmem_base, tmem_full, tmem_empty, quarter, half, lane, stg); break;
+    case B200_EPI_BIAS_GELU: epilogue_role<BLOCK_N, B200_EPI_BIAS_GELU>(p, sc, tmem_base, tmem_full, tmem_empty, quarter, half, lane, stg); break;
+    case B200_EPI_RESIDUAL: epilogue_role<BLOCK_N, B200_EPI_RESIDUAL>(p, sc, tmem_base, tmem_full, tmem_empty, quarter, half, lane, stg); break;
+    default: epilogue_role<BLOCK_N, B200_EPI_DGELU>(p, sc, tmem_base, tmem_full, tmem_empty, quarter, half, lane, stg); break;
   }
 }
 
@@ -372,21 +406,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else {
     // ===================== epilogue warps =====================
     const int ew = warp - 2;
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    const int half = ew >> 2;      // which half of the tile's columns
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-      const int tile = w / n_splits;
-      const int m0 = (tile % tiles_m) * BLOCK_M;
-      const int n0 = (tile / tiles_m) * BLOCK_N;
-      epilogue_tile<BLOCK_N>(p, tmem_base + acc * Cfg::ACC_STRIDE, &tmem_full[acc], acc_phase, m0, n0, quarter, half, lane,
-                             epi_staging + ew * (32 * 32));
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      if ((acc ^= 1) == 0) acc_phase ^= 1;
-    }
+    EpiSched sc{(int)blockIdx.x, total_work, (int)gridDim.x, n_splits, tiles_m};
+    run_epilogue_role<BLOCK_N>(p, sc, tmem_base, tmem_full, tmem_empty, warp & 3, ew >> 2, lane, epi_staging + ew * (32 * 32));
   }
 
   tc_fence_before();
@@ -544,18 +565,9 @@ gemm_tcgen05_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
   } else {
     // ===================== epilogue warps =====================
-    const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int w = w0; w < w1; ++w) {
-      const int m0 = (w % tiles_m) * BLOCK_M, n0 = (w / tiles_m) * BLOCK_N;
-      epilogue_tile<BLOCK_N>(p, tmem_base + acc * Cfg::ACC_STRIDE, &tmem_full[acc], acc_phase, m0, n0, quarter, half, lane,
-                             epi_staging + ew * (32 * 32));
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      if ((acc ^= 1) == 0) acc_phase ^= 1;
-    }
+    const int ew = warp - 2;
+    EpiSched sc{w0, w1, 1, 1, tiles_m};
+    run_epilogue_role<BLOCK_N>(p, sc, tmem_base, tmem_full, tmem_empty, warp & 3, ew >> 2, lane, epi_staging + ew * (32 * 32));
   }
   tc_fence_before();
   __syncthreads();
