@@ -22,18 +22,28 @@ namespace b200 {
 static constexpr int BLOCK_M = 128;
 static constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle-128B row
 static constexpr int UMMA_K = 16;
-static constexpr int NUM_EPI_WARPS = 8;
-static constexpr int NUM_THREADS = (2 + NUM_EPI_WARPS) * 32;
+// Epilogue warps: TMEM lane quarter q is only reachable from warps with (warp % 4) == q, so the epilogue has a
+// multiple of 4 warps; each owns 32 rows x (BLOCK_N / (warps/4)) columns.  The fused epilogues are issue/latency
+// bound, so the 192-wide tile (every D=384 GEMM) gets 12 warps x 64 columns; 128 -> 8 x 64, 256 -> 8 x 128
+// (more warps would cap registers below what the aux-prefetching epilogues need).
+template <int BLOCK_N>
+struct EpiCfg {
+  static constexpr int WARPS = (BLOCK_N == 192) ? 12 : 8;
+  static constexpr int COLS_PER_WARP = BLOCK_N / (WARPS / 4);
+  static constexpr int THREADS = (2 + WARPS) * 32;
+  static constexpr int STAGING_BYTES = WARPS * 32 * 32 * 4;  // one 32x32 fp32 transpose tile per warp
+};
 
 template <int BLOCK_N>
 struct GemmCfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BLOCK_N <= 128) ? 5 : 4;
+  static constexpr int EPI_STAGING_BYTES = EpiCfg<BLOCK_N>::STAGING_BYTES;
+  static constexpr int STAGES_FIT = (232448 - 1024 - 256 - EPI_STAGING_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
   static constexpr int ACC_STRIDE = 256;  // TMEM columns between the two accumulator buffers
   static constexpr int TMEM_COLS = 512;
-  static constexpr int EPI_STAGING_BYTES = NUM_EPI_WARPS * 32 * 32 * 4;  // one 32x32 fp32 transpose tile per warp
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -167,7 +177,7 @@ struct EpiSched {
 template <int BLOCK_N, int EPI>
 __device__ __noinline__ void epilogue_role(const GemmDev p, const EpiSched sc, const uint32_t tmem_base, uint64_t* tmem_full,
                                            uint64_t* tmem_empty, const int quarter, const int half, const int lane, float* stg) {
-  constexpr int COLS_PER_WARP = BLOCK_N / 2;
+  constexpr int COLS_PER_WARP = EpiCfg<BLOCK_N>::COLS_PER_WARP;
   constexpr int NC = COLS_PER_WARP / 32;
   constexpr bool HAS_AUX = (EPI == B200_EPI_RESIDUAL || EPI == B200_EPI_DGELU);
   constexpr int C_ESIZE = (EPI == B200_EPI_F32 || EPI == B200_EPI_F32_ATOMIC || EPI == B200_EPI_RESIDUAL) ? 4 : 2;
@@ -276,7 +286,7 @@ __device__ __forceinline__ void run_epilogue_role(const GemmDev& p, const EpiSch
 
 // ---------------------------------------------------------------------------------------------
 template <int BLOCK_N>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(EpiCfg<BLOCK_N>::THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmDev p) {
   using Cfg = GemmCfg<BLOCK_N>;
@@ -308,7 +318,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], NUM_EPI_WARPS);
+      mbar_init(&tmem_empty[s], EpiCfg<BLOCK_N>::WARPS);
     }
     fence_barrier_init();
   }
@@ -430,7 +440,7 @@ struct GemmWsCfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;      // one k-block of the resident slab
   static constexpr int PANEL_BYTES = KB_MAX * B_BYTES;
-  static constexpr int EPI_STAGING_BYTES = NUM_EPI_WARPS * 32 * 32 * 4;
+  static constexpr int EPI_STAGING_BYTES = EpiCfg<BLOCK_N>::STAGING_BYTES;
   static constexpr int BUDGET = 232448 - 1024 - 256 - PANEL_BYTES - EPI_STAGING_BYTES;
   static constexpr int STAGES = BUDGET / A_BYTES > 6 ? 6 : BUDGET / A_BYTES;
   static constexpr int ACC_STRIDE = 256;
@@ -440,7 +450,7 @@ struct GemmWsCfg {
 };
 
 template <int BLOCK_N, int KB_MAX>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(EpiCfg<BLOCK_N>::THREADS, 1)
 gemm_tcgen05_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const GemmDev p) {
   using Cfg = GemmWsCfg<BLOCK_N, KB_MAX>;
@@ -470,7 +480,7 @@ gemm_tcgen05_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], NUM_EPI_WARPS); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EpiCfg<BLOCK_N>::WARPS); }
     mbar_init(b_full, 1);
     mbar_init(b_empty, 1);
     fence_barrier_init();
@@ -651,7 +661,7 @@ static int launch_gemm(const b200_gemm_args* a, cudaStream_t stream) {
   long long work = (long long)tiles * splits;
   int grid = (int)(work < g_num_sms ? work : g_num_sms);
   if (grid < 1) grid = 1;
-  gemm_tcgen05_kernel<BLOCK_N><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  gemm_tcgen05_kernel<BLOCK_N><<<grid, EpiCfg<BLOCK_N>::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -696,7 +706,7 @@ static int launch_gemm_ws(const b200_gemm_args* a, cudaStream_t stream) {
   // even out the contiguous runs: ceil(tiles/grid) tiles per CTA, drop CTAs that would get nothing
   const long long per = (tiles + grid - 1) / grid;
   grid = (int)((tiles + per - 1) / per);
-  gemm_tcgen05_ws_kernel<BLOCK_N, KB_MAX><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  gemm_tcgen05_ws_kernel<BLOCK_N, KB_MAX><<<grid, EpiCfg<BLOCK_N>::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -718,7 +728,9 @@ extern "C" int b200_gemm(const b200_gemm_args* a, void* stream) {
   const int kb_total = (a->K + BLOCK_K - 1) / BLOCK_K;
   const int tiles_m = (a->M + BLOCK_M - 1) / BLOCK_M;
   // weight-stationary schedule: small K (the B slab fits in smem next to the A ring) and enough M tiles to amortise it
-  const bool want_ws = a->ws_mode == 1 || (a->ws_mode == 0 && a->splits <= 1 && tiles_m >= 8 && kb_total <= 6);
+  // measured on B200 (profiles/r01_gemm_*.log): the slab schedule wins only for K <= 256 (projection-head last layer);
+  // for K = 384 the generic ring has more bytes in flight and is as fast or faster
+  const bool want_ws = a->ws_mode == 1 || (a->ws_mode == 0 && a->splits <= 1 && tiles_m >= 8 && kb_total <= 4);
   int bn = a->block_n;
   if (bn == 0) {
     // tile-N heuristic: minimise padded columns, prefer wider tiles (fewer smem bytes per MMA)
