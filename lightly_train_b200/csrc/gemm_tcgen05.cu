@@ -198,8 +198,6 @@ __device__ __noinline__ void epilogue_role(const GemmDev p, const EpiSched sc, c
   const long long c_step = 4 * ldc * C_ESIZE, c2_step = 8 * ldc2, aux_step = 4 * ldaux * AUX_ESIZE;
   const uint32_t stg_w = smem_u32(stg) + lane * 128;     // this lane's row (write side of the transpose)
   const uint32_t stg_r = smem_u32(stg) + sub_row * 128;  // first row of the read side
-  float4 bias4[NC], gamma4[NC];
-  int cur_n0 = -1;
   int acc = 0;
   uint32_t acc_phase = 0;
   for (int w = sc.w_begin; w < sc.w_end; w += sc.w_step) {
@@ -208,16 +206,10 @@ __device__ __noinline__ void epilogue_role(const GemmDev p, const EpiSched sc, c
     const int row_first = m0 + quarter * 32 + sub_row;
     const int rows_valid = M - (m0 + quarter * 32);  // rows r (0..31) of this warp are valid iff r < rows_valid
     const int col0 = n0 + half * COLS_PER_WARP + g4 * 4;
-    if (n0 != cur_n0) {
-      cur_n0 = n0;
-#pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        const int col = col0 + c * 32;
-        bias4[c] = (bias && col < N) ? __ldg(reinterpret_cast<const float4*>(bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        gamma4[c] = (EPI == B200_EPI_RESIDUAL && gamma && col < N) ? __ldg(reinterpret_cast<const float4*>(gamma + col))
+    // bias / gamma of the first chunk (later chunks are fetched one chunk ahead inside the loop)
+    float4 bias_nxt = (bias && col0 < N) ? __ldg(reinterpret_cast<const float4*>(bias + col0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 gamma_nxt = (EPI == B200_EPI_RESIDUAL && gamma && col0 < N) ? __ldg(reinterpret_cast<const float4*>(gamma + col0))
                                                                         : make_float4(1.f, 1.f, 1.f, 1.f);
-      }
-    }
     char* c_base = C + ((size_t)row_first * ldc + col0) * C_ESIZE;
     char* c2_base = C2 ? C2 + ((size_t)row_first * ldc2 + col0) * 2 : nullptr;
     const char* aux_base = HAS_AUX ? AUX + ((size_t)row_first * ldaux + col0) * AUX_ESIZE : nullptr;
@@ -235,20 +227,29 @@ __device__ __noinline__ void epilogue_role(const GemmDev p, const EpiSched sc, c
     const uint32_t taddr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16) + half * COLS_PER_WARP;
     uint32_t v[32];
     tmem_ld_32x32(taddr, v);
-#pragma unroll
+    // the chunk loop is deliberately NOT unrolled: the unrolled 8-row-group body below is already 1-2 K
+    // instructions for the GELU epilogues, and unrolling it NC times thrashed the instruction cache
+    // (stall_no_inst ~ 19 % of samples in profiles/r01_gemm_stalls.md)
+#pragma unroll 1
     for (int c = 0; c < NC; ++c) {
+      const float4 bias4 = bias_nxt, gamma4 = gamma_nxt;
       tmem_ld_wait();
       // transpose through smem: thread (= row `lane`) writes its 32 columns; XOR swizzle keeps both the
       // row-wise 16-byte writes and the column-group reads bank-conflict free
 #pragma unroll
       for (int j = 0; j < 8; ++j) sts128(stg_w + ((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-      if (c + 1 < NC) tmem_ld_32x32(taddr + (c + 1) * 32, v);
+      const int col_next = col0 + (c + 1) * 32;
+      if (c + 1 < NC) {
+        tmem_ld_32x32(taddr + (c + 1) * 32, v);
+        if (bias && col_next < N) bias_nxt = __ldg(reinterpret_cast<const float4*>(bias + col_next));
+        if (EPI == B200_EPI_RESIDUAL && gamma && col_next < N) gamma_nxt = __ldg(reinterpret_cast<const float4*>(gamma + col_next));
+      }
       __syncwarp();
       const bool col_ok = col0 + c * 32 < N;  // N % 8 == 0 and col % 4 == 0 -> the 4 columns are all valid
       if constexpr (HAS_AUX) {
 #pragma unroll
         for (int it = 0; it < 8; ++it) aux_cur[it] = aux_nxt[it];
-        if (c + 1 < NC) load_aux_chunk<EPI>(aux_nxt, aux_base + (c + 1) * 32 * AUX_ESIZE, aux_step, rows_valid, sub_row, col0 + (c + 1) * 32 < N);
+        if (c + 1 < NC) load_aux_chunk<EPI>(aux_nxt, aux_base + (c + 1) * 32 * AUX_ESIZE, aux_step, rows_valid, sub_row, col_next < N);
       }
       if (col_ok) {
         char* cp = c_base + c * 32 * C_ESIZE;
@@ -257,7 +258,7 @@ __device__ __noinline__ void epilogue_role(const GemmDev p, const EpiSched sc, c
         for (int it = 0; it < 8; ++it) {
           const int r = it * 4 + sub_row;
           const float4 a4 = lds128(stg_r + it * 512 + ((g4 ^ (r & 7)) << 4));
-          if (r < rows_valid) epilogue_vec4<EPI>(alpha, a4, cp, c2p, (EPI == B200_EPI_RESIDUAL) ? rs[it] : 1.0f, bias4[c], gamma4[c], aux_cur[it]);
+          if (r < rows_valid) epilogue_vec4<EPI>(alpha, a4, cp, c2p, (EPI == B200_EPI_RESIDUAL) ? rs[it] : 1.0f, bias4, gamma4, aux_cur[it]);
           cp += c_step;
           if (c2p) c2p += c2_step;
         }
