@@ -734,15 +734,21 @@ extern "C" int b200_gemm(const b200_gemm_args* a, void* stream) {
   const bool want_ws = a->ws_mode == 1 || (a->ws_mode == 0 && a->splits <= 1 && tiles_m >= 8 && kb_total <= 4);
   int bn = a->block_n;
   if (bn == 0) {
-    // tile-N heuristic: minimise padded columns, prefer wider tiles (fewer smem bytes per MMA)
-    const int cand_any[3] = {256, 192, 128};
-    const int cand_ws6[2] = {192, 128};  // K <= 384: slabs of 256 columns do not fit
-    const int* cand = (want_ws && kb_total > 4) ? cand_ws6 : cand_any;
-    const int nc = (want_ws && kb_total > 4) ? 2 : 3;
+    // tile-N heuristic: minimise (waves over the SMs) x (MMA time per tile ~ BLOCK_N), i.e. padding and wave
+    // quantisation together; ties go to 192 (12 epilogue warps), then to the wider tile
+    if (g_num_sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int cand[3] = {192, 256, 128};
+    const int splits = a->splits < 1 ? 1 : a->splits;
     long long best = -1;
-    for (int i = 0; i < nc; ++i) {
-      long long padded = (long long)((a->N + cand[i] - 1) / cand[i]) * cand[i];
-      if (best < 0 || padded < best) { best = padded; bn = cand[i]; }
+    for (int i = 0; i < 3; ++i) {
+      if (want_ws && kb_total > 4 && cand[i] == 256) continue;  // a 256 x 384 slab does not fit
+      const long long tiles = (long long)tiles_m * ((a->N + cand[i] - 1) / cand[i]) * splits;
+      const long long cost = ((tiles + g_num_sms - 1) / g_num_sms) * cand[i];
+      if (best < 0 || cost < best) { best = cost; bn = cand[i]; }
     }
   }
   if (want_ws) {
