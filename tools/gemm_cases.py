@@ -30,10 +30,19 @@ datt = torch.randn(B_ * N_, D, device=dev).to(bf)
 dqkv = torch.empty_like(qkv_att)
 
 
+import os
+ATT = os.environ.get("CASES", "all") in ("all", "att")
+GEMM_PLAIN = os.environ.get("CASES", "all") in ("all",)
+
+
 def cases():
-    ops.attention_fwd(qkv_att, B_, N_, h_, att_out, att_lse, 0.125)
-    ops.attention_bwd(qkv_att, att_out, datt, att_lse, B_, N_, h_, dqkv, 0.125)
-    ops.gemm(x, wqkv, out_qkv, bias=b3, ws_mode=2)                                           # qkv generic schedule
+    if ATT:
+        ops.attention_fwd(qkv_att, B_, N_, h_, att_out, att_lse, 0.125)
+        ops.attention_bwd(qkv_att, att_out, datt, att_lse, B_, N_, h_, dqkv, 0.125)
+    if os.environ.get("CASES", "all") == "att":
+        return
+    if GEMM_PLAIN:
+        ops.gemm(x, wqkv, out_qkv, bias=b3, ws_mode=2)                                       # qkv generic schedule
     ops.gemm(x, wqkv, out_qkv, bias=b3)                                                      # qkv
     ops.gemm(x, wproj, out_res, epi=ops.EPI_RESIDUAL, bias=b1, out2=out_o, aux=res, gamma=gamma)  # proj
     ops.gemm(x, w1, out_h, epi=ops.EPI_BIAS_GELU, bias=bh, out2=out_u)                        # fc1
