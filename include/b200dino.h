@@ -44,7 +44,9 @@ enum {
   B200_EPI_BIAS_GELU = 3,  /* u = bf16(acc+bias); C2(bf16)=u (optional); C(bf16) = gelu_erf(u)      */
   B200_EPI_RESIDUAL = 4,   /* o = bf16(acc+bias); C2(bf16)=o (optional);
                               C(f32) = aux(f32) + gamma[n]*o*rowscale[m / rows_per_scale]          */
-  B200_EPI_DGELU = 5       /* C(bf16) = bf16(acc) * gelu_erf'(aux(bf16))                           */
+  B200_EPI_DGELU = 5,      /* C(bf16) = bf16(acc) * gelu_erf'(aux(bf16))                           */
+  B200_EPI_BIAS_GELU_DG = 6, /* u = bf16(acc+bias); C(bf16) = gelu_erf(u); C2(bf16) = gelu_erf'(u)  */
+  B200_EPI_MUL_AUX = 7     /* C(bf16) = bf16(acc) * aux(bf16)   (dGELU with the saved derivative)  */
 };
 
 typedef struct b200_gemm_args {
@@ -90,6 +92,13 @@ int b200_layernorm_fwd(const float* x, long long ldx, int T, int D, const float*
 int b200_layernorm_bwd(const void* dy, long long lddy, int dy_bf16, const float* x, long long ldx, int T, int D,
                        const float* w, const float* mean, const float* rstd, float* dx, long long lddx,
                        int accumulate, float* dw, float* db, void* stream);
+/* LayerNorm backward fused with the LayerScale(+DropPath) backward that follows it in the block schedule:
+ * dx (+)= LN'(dy); dout = bf16(dx*rowscale*gamma); dgamma += sum dx*rowscale*o; dbias += sum dout. */
+int b200_layernorm_bwd_ls(const void* dy, long long lddy, int dy_bf16, const float* x, long long ldx, int T, int D,
+                          const float* w, const float* mean, const float* rstd, float* dx, long long lddx,
+                          int accumulate, float* dw, float* db, const void* o, long long ldo, const float* gamma,
+                          const float* rowscale, int rows_per_scale, void* dout, long long lddo, float* dgamma,
+                          float* dbias, void* stream);
 /* im2col for PatchEmbed.proj = Conv2d(k=s=p) (patch_embed.py:77-79,108): x f32 [B,C,H,W] -> bf16 [B*Np, C*p*p]. */
 int b200_im2col(const float* x, int B, int C, int H, int W, int p, void* cols, long long ldc, void* stream);
 /* prepare_tokens_with_masks (vision_transformer.py:307-329): mask-token select, cls/register concat, +pos. */

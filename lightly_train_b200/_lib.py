@@ -18,7 +18,7 @@ ERRORS = {
     -4: "B200_ERR_DRIVER",
 }
 
-EPI_BF16, EPI_F32, EPI_F32_ATOMIC, EPI_BIAS_GELU, EPI_RESIDUAL, EPI_DGELU = range(6)
+EPI_BF16, EPI_F32, EPI_F32_ATOMIC, EPI_BIAS_GELU, EPI_RESIDUAL, EPI_DGELU, EPI_BIAS_GELU_DG, EPI_MUL_AUX = range(8)
 
 
 class GemmArgs(C.Structure):

@@ -493,7 +493,7 @@ class DINOv2(nn.Module):
             run()  # eager warm-up at this shape (also the result of this step)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=st["pool"]):
+            with torch.cuda.graph(g, pool=st["pool"], capture_error_mode="thread_local"):  # NCCL watchdog thread may touch CUDA
                 outs = run()
             if st["pool"] is None:
                 st["pool"] = g.pool()
@@ -539,6 +539,13 @@ class DINOv2(nn.Module):
         sa.bf16_valid = ta.bf16_valid = True
         self._grad_ready = False
         self.trainer.global_step += 1
+
+    @staticmethod
+    def loss_for_autograd(result: TrainingStepResult) -> Tensor:
+        """Bridge for trainers that call `loss.backward()` themselves (Lightning automatic optimisation): the
+        gradients are already in `param.grad` when training_step_impl returns, so the returned leaf only has to
+        make `backward()` a no-op instead of an error ('autograd bridge')."""
+        return result.loss.detach().requires_grad_(True)
 
     def train_step(self, batch: Dict[str, Any]) -> TrainingStepResult:
         """One full optimisation step: what Lightning's fit loop does around training_step."""

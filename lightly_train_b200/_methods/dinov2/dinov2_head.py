@@ -87,9 +87,11 @@ class DINOv2ProjectionHead(nn.Module):
         ctx = HeadCtx()
         Hd, Bn, K = self.hidden_dim, self.bottleneck_dim, self.out_dim
         h0, u0 = E(R, Hd), (E(R, Hd) if save else None)
-        ops.gemm(x_bf16, self._W("mlp.0.weight"), h0, epi=ops.EPI_BIAS_GELU, bias=self._P("mlp.0.bias"), out2=u0)
+        ops.gemm(x_bf16, self._W("mlp.0.weight"), h0, epi=ops.EPI_BIAS_GELU_DG if save else ops.EPI_BIAS_GELU,
+                 bias=self._P("mlp.0.bias"), out2=u0)  # u0/u1 hold gelu'(pre-activation) for the backward
         h1, u1 = E(R, Hd), (E(R, Hd) if save else None)
-        ops.gemm(h0, self._W("mlp.2.weight"), h1, epi=ops.EPI_BIAS_GELU, bias=self._P("mlp.2.bias"), out2=u1)
+        ops.gemm(h0, self._W("mlp.2.weight"), h1, epi=ops.EPI_BIAS_GELU_DG if save else ops.EPI_BIAS_GELU,
+                 bias=self._P("mlp.2.bias"), out2=u1)
         z = E(R, Bn)
         ops.gemm(h1, self._W("mlp.4.weight"), z, bias=self._P("mlp.4.bias"))
         zn, nrm = E(R, Bn), E(R, dt=torch.float32)
@@ -127,10 +129,10 @@ class DINOv2ProjectionHead(nn.Module):
 
         lin_bwd(dz, ctx.h1, "mlp.4.weight", "mlp.4.bias")
         dU1 = E(R, Hd)
-        ops.gemm(dz, self._W("mlp.4.weight"), dU1, b_mn=True, epi=ops.EPI_DGELU, aux=ctx.u1)
+        ops.gemm(dz, self._W("mlp.4.weight"), dU1, b_mn=True, epi=ops.EPI_MUL_AUX, aux=ctx.u1)
         lin_bwd(dU1, ctx.h0, "mlp.2.weight", "mlp.2.bias")
         dU0 = E(R, Hd)
-        ops.gemm(dU1, self._W("mlp.2.weight"), dU0, b_mn=True, epi=ops.EPI_DGELU, aux=ctx.u0)
+        ops.gemm(dU1, self._W("mlp.2.weight"), dU0, b_mn=True, epi=ops.EPI_MUL_AUX, aux=ctx.u0)
         lin_bwd(dU0, ctx.x, "mlp.0.weight", "mlp.0.bias")
         dx = E(R, self.in_dim)
         ops.gemm(dU0, self._W("mlp.0.weight"), dx, b_mn=True)

@@ -227,7 +227,8 @@ class DinoVisionTransformer(nn.Module):
             ops.layernorm_fwd(xmid, self._P(b + "norm2.weight"), self._P(b + "norm2.bias"), self.ln_eps, xn2, mean2, rstd2)
             hh = E(T, Hd)
             u = E(T, Hd) if save else None
-            ops.gemm(xn2, self._W(b + "mlp.fc1.weight"), hh, epi=ops.EPI_BIAS_GELU, bias=self._P(b + "mlp.fc1.bias"), out2=u)
+            ops.gemm(xn2, self._W(b + "mlp.fc1.weight"), hh, epi=ops.EPI_BIAS_GELU_DG if save else ops.EPI_BIAS_GELU,
+                     bias=self._P(b + "mlp.fc1.bias"), out2=u)  # u holds gelu'(fc1 out) for the backward
             o2 = E(T, D) if save else None
             xout = E(T, D, dt=f32)
             ops.gemm(hh, self._W(b + "mlp.fc2.weight"), xout, epi=ops.EPI_RESIDUAL, bias=self._P(b + "mlp.fc2.bias"),
@@ -263,30 +264,35 @@ class DinoVisionTransformer(nn.Module):
             ops.gemm(dy, xin, self._G(name).view(dy.shape[1], xin.shape[1]), a_mn=True, b_mn=True,
                      epi=ops.EPI_F32_ATOMIC, splits=wgrad_splits)
 
+        ls = self.layerscale
+        nb = self.n_blocks
         dx = E(T, D, dt=f32)
-        ops.layernorm_bwd(d_xnorm, ctx.x_prenorm, self._P("norm.weight"), ctx.meanf, ctx.rstdf, dx, False,
-                          self._G("norm.weight"), self._G("norm.bias"))
-        for i in reversed(range(self.n_blocks)):
+        # final LayerNorm backward, fused with the LayerScale backward of the last block's MLP branch
+        last = ctx.blocks[nb - 1]
+        bl = f"blocks.{nb - 1}."
+        do2 = E(T, D)
+        ops.layernorm_bwd_ls(d_xnorm, ctx.x_prenorm, self._P("norm.weight"), ctx.meanf, ctx.rstdf, dx, False,
+                             self._G("norm.weight"), self._G("norm.bias"), last["o2"],
+                             self._P(bl + "ls2.gamma") if ls else None, last["rs2"], N, do2,
+                             self._G(bl + "ls2.gamma") if ls else None, self._G(bl + "mlp.fc2.bias"))
+        for i in reversed(range(nb)):
             b = f"blocks.{i}."
             sv = ctx.blocks[i]
-            ls = self.layerscale
-            # ---- MLP branch
-            do2 = E(T, D)
-            ops.layerscale_bwd(dx, sv["o2"], self._P(b + "ls2.gamma") if ls else None, sv["rs2"], N, do2,
-                               self._G(b + "ls2.gamma") if ls else None, self._G(b + "mlp.fc2.bias"))
+            # ---- MLP branch (do2 = gradient of the fc2 output, produced by the fused kernel above / below)
             dU = E(T, Hd)
-            ops.gemm(do2, self._W(b + "mlp.fc2.weight"), dU, b_mn=True, epi=ops.EPI_DGELU, aux=sv["u"])
+            ops.gemm(do2, self._W(b + "mlp.fc2.weight"), dU, b_mn=True, epi=ops.EPI_MUL_AUX, aux=sv["u"])
             wgrad(do2, sv["h"], b + "mlp.fc2.weight")
             ops.col_reduce(dU, self._G(b + "mlp.fc1.bias"))
             wgrad(dU, sv["xn2"], b + "mlp.fc1.weight")
             dxn2 = E(T, D)
             ops.gemm(dU, self._W(b + "mlp.fc1.weight"), dxn2, b_mn=True)
-            ops.layernorm_bwd(dxn2, sv["x_mid"], self._P(b + "norm2.weight"), sv["mean2"], sv["rstd2"], dx, True,
-                              self._G(b + "norm2.weight"), self._G(b + "norm2.bias"))
-            # ---- attention branch
+            # LN2 backward (dx += ...) fused with the LayerScale backward of this block's attention branch
             do1 = E(T, D)
-            ops.layerscale_bwd(dx, sv["o1"], self._P(b + "ls1.gamma") if ls else None, sv["rs1"], N, do1,
-                               self._G(b + "ls1.gamma") if ls else None, self._G(b + "attn.proj.bias"))
+            ops.layernorm_bwd_ls(dxn2, sv["x_mid"], self._P(b + "norm2.weight"), sv["mean2"], sv["rstd2"], dx, True,
+                                 self._G(b + "norm2.weight"), self._G(b + "norm2.bias"), sv["o1"],
+                                 self._P(b + "ls1.gamma") if ls else None, sv["rs1"], N, do1,
+                                 self._G(b + "ls1.gamma") if ls else None, self._G(b + "attn.proj.bias"))
+            # ---- attention branch
             datt = E(T, D)
             ops.gemm(do1, self._W(b + "attn.proj.weight"), datt, b_mn=True)
             wgrad(do1, sv["att"], b + "attn.proj.weight")
@@ -296,8 +302,18 @@ class DinoVisionTransformer(nn.Module):
             wgrad(dqkv, sv["xn"], b + "attn.qkv.weight")
             dxn = E(T, D)
             ops.gemm(dqkv, self._W(b + "attn.qkv.weight"), dxn, b_mn=True)
-            ops.layernorm_bwd(dxn, sv["x_in"], self._P(b + "norm1.weight"), sv["mean1"], sv["rstd1"], dx, True,
-                              self._G(b + "norm1.weight"), self._G(b + "norm1.bias"))
+            if i > 0:
+                # LN1 backward fused with the LayerScale backward of the PREVIOUS block's MLP branch
+                pv = ctx.blocks[i - 1]
+                bp = f"blocks.{i - 1}."
+                do2 = E(T, D)
+                ops.layernorm_bwd_ls(dxn, sv["x_in"], self._P(b + "norm1.weight"), sv["mean1"], sv["rstd1"], dx, True,
+                                     self._G(b + "norm1.weight"), self._G(b + "norm1.bias"), pv["o2"],
+                                     self._P(bp + "ls2.gamma") if ls else None, pv["rs2"], N, do2,
+                                     self._G(bp + "ls2.gamma") if ls else None, self._G(bp + "mlp.fc2.bias"))
+            else:
+                ops.layernorm_bwd(dxn, sv["x_in"], self._P(b + "norm1.weight"), sv["mean1"], sv["rstd1"], dx, True,
+                                  self._G(b + "norm1.weight"), self._G(b + "norm1.bias"))
             ctx.blocks[i] = None  # free activations early
         # ---- embeddings
         dtok = E(Bc * Np, D)

@@ -174,10 +174,11 @@ __device__ __forceinline__ float gelu_phi(float x) {
   return x < 0.f ? h : 1.0f - h;
 }
 __device__ __forceinline__ float gelu_erf(float x) { return x * gelu_phi(x); }
-__device__ __forceinline__ float gelu_erf_grad(float x) {
+__device__ __forceinline__ float gelu_grad_from_phi(float x, float phi) {
   const float kBeta = 0.39894228040143267794f;  // 1/sqrt(2*pi)
-  return fmaf(x * kBeta, __expf(-0.5f * x * x), gelu_phi(x));
+  return fmaf(x * kBeta, __expf(-0.5f * x * x), phi);
 }
+__device__ __forceinline__ float gelu_erf_grad(float x) { return gelu_grad_from_phi(x, gelu_phi(x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -130,6 +130,20 @@ __device__ __forceinline__ void epilogue_vec4(float alpha, float4 acc, char* c, 
     if (c2) *reinterpret_cast<uint2*>(c2) = make_uint2(p01, p23);
     const float2 u01 = unpack_bf16x2(p01), u23 = unpack_bf16x2(p23);
     *reinterpret_cast<uint2*>(c) = make_uint2(pack_bf16x2(gelu_erf(u01.x), gelu_erf(u01.y)), pack_bf16x2(gelu_erf(u23.x), gelu_erf(u23.y)));
+  } else if constexpr (EPI == B200_EPI_BIAS_GELU_DG) {
+    // like BIAS_GELU, but the second output is gelu'(u) (bf16) instead of u: the backward then only multiplies
+    const uint32_t p01 = pack_bf16x2(v0, v1), p23 = pack_bf16x2(v2, v3);
+    const float2 u01 = unpack_bf16x2(p01), u23 = unpack_bf16x2(p23);
+    const float f0 = gelu_phi(u01.x), f1 = gelu_phi(u01.y), f2 = gelu_phi(u23.x), f3 = gelu_phi(u23.y);
+    *reinterpret_cast<uint2*>(c) = make_uint2(pack_bf16x2(u01.x * f0, u01.y * f1), pack_bf16x2(u23.x * f2, u23.y * f3));
+    if (c2)
+      *reinterpret_cast<uint2*>(c2) = make_uint2(pack_bf16x2(gelu_grad_from_phi(u01.x, f0), gelu_grad_from_phi(u01.y, f1)),
+                                                 pack_bf16x2(gelu_grad_from_phi(u23.x, f2), gelu_grad_from_phi(u23.y, f3)));
+  } else if constexpr (EPI == B200_EPI_MUL_AUX) {
+    // C = bf16( bf16(acc) * aux ), aux bf16 (e.g. the gelu'(u) saved by BIAS_GELU_DG)
+    const float2 ga = unpack_bf16x2(__float_as_uint(aux4.x)), gc = unpack_bf16x2(__float_as_uint(aux4.y));
+    *reinterpret_cast<uint2*>(c) = make_uint2(pack_bf16x2(bf16_round(v0) * ga.x, bf16_round(v1) * ga.y),
+                                              pack_bf16x2(bf16_round(v2) * gc.x, bf16_round(v3) * gc.y));
   } else if constexpr (EPI == B200_EPI_RESIDUAL) {
     // o = bf16(acc + bias); x_out = x_in + gamma * o * rowscale   (fp32 residual stream)
     const uint32_t p01 = pack_bf16x2(v0, v1), p23 = pack_bf16x2(v2, v3);
@@ -155,7 +169,7 @@ __device__ __forceinline__ void load_aux_chunk(float4 (&aux4)[8], const char* au
     const bool ok = col_ok && (it * 4 + sub_row < rows_valid);
     if constexpr (EPI == B200_EPI_RESIDUAL) {
       aux4[it] = ok ? __ldg(reinterpret_cast<const float4*>(aux + it * step)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    } else if constexpr (EPI == B200_EPI_DGELU) {
+    } else if constexpr (EPI == B200_EPI_DGELU || EPI == B200_EPI_MUL_AUX) {
       const uint2 u = ok ? __ldg(reinterpret_cast<const uint2*>(aux + it * step)) : make_uint2(0u, 0u);
       aux4[it] = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), 0.f, 0.f);
     }
@@ -179,7 +193,7 @@ __device__ __noinline__ void epilogue_role(const GemmDev p, const EpiSched sc, c
                                            uint64_t* tmem_empty, const int quarter, const int half, const int lane, float* stg) {
   constexpr int COLS_PER_WARP = EpiCfg<BLOCK_N>::COLS_PER_WARP;
   constexpr int NC = COLS_PER_WARP / 32;
-  constexpr bool HAS_AUX = (EPI == B200_EPI_RESIDUAL || EPI == B200_EPI_DGELU);
+  constexpr bool HAS_AUX = (EPI == B200_EPI_RESIDUAL || EPI == B200_EPI_DGELU || EPI == B200_EPI_MUL_AUX);
   constexpr int C_ESIZE = (EPI == B200_EPI_F32 || EPI == B200_EPI_F32_ATOMIC || EPI == B200_EPI_RESIDUAL) ? 4 : 2;
   constexpr int AUX_ESIZE = (EPI == B200_EPI_RESIDUAL) ? 4 : 2;
   constexpr int ACC_STRIDE = 256;
@@ -282,6 +296,8 @@ __device__ __forceinline__ void run_epilogue_role(const GemmDev& p, const EpiSch
     case B200_EPI_F32_ATOMIC: epilogue_role<BLOCK_N, B200_EPI_F32_ATOMIC>(p, sc, tmem_base, tmem_full, tmem_empty, quarter, half, lane, stg); break;
     case B200_EPI_BIAS_GELU: epilogue_role<BLOCK_N, B200_EPI_BIAS_GELU>(p, sc, tmem_base, tmem_full, tmem_empty, quarter, half, lane, stg); break;
     case B200_EPI_RESIDUAL: epilogue_role<BLOCK_N, B200_EPI_RESIDUAL>(p, sc, tmem_base, tmem_full, tmem_empty, quarter, half, lane, stg); break;
+    case B200_EPI_BIAS_GELU_DG: epilogue_role<BLOCK_N, B200_EPI_BIAS_GELU_DG>(p, sc, tmem_base, tmem_full, tmem_empty, quarter, half, lane, stg); break;
+    case B200_EPI_MUL_AUX: epilogue_role<BLOCK_N, B200_EPI_MUL_AUX>(p, sc, tmem_base, tmem_full, tmem_empty, quarter, half, lane, stg); break;
     default: epilogue_role<BLOCK_N, B200_EPI_DGELU>(p, sc, tmem_base, tmem_full, tmem_empty, quarter, half, lane, stg); break;
   }
 }
@@ -724,9 +740,10 @@ extern "C" int b200_gemm(const b200_gemm_args* a, void* stream) {
   // TMA: 16-byte aligned bases and row pitches; vectorised epilogue: N, ldc multiples of 8
   if ((a->lda % 8) || (a->ldb % 8) || (a->N % 8) || (a->ldc % 8)) return B200_ERR_UNSUPPORTED;
   if (((uintptr_t)a->A & 15) || ((uintptr_t)a->B & 15) || ((uintptr_t)a->C & 15)) return B200_ERR_UNSUPPORTED;
-  if (a->epi < 0 || a->epi > B200_EPI_DGELU) return B200_ERR_INVALID_ARG;
+  if (a->epi < 0 || a->epi > B200_EPI_MUL_AUX) return B200_ERR_INVALID_ARG;
   if (a->splits > 1 && a->epi != B200_EPI_F32_ATOMIC) return B200_ERR_INVALID_ARG;
-  if ((a->epi == B200_EPI_RESIDUAL || a->epi == B200_EPI_DGELU) && (!a->aux || (a->ldaux % 8))) return B200_ERR_INVALID_ARG;
+  if ((a->epi == B200_EPI_RESIDUAL || a->epi == B200_EPI_DGELU || a->epi == B200_EPI_MUL_AUX) && (!a->aux || (a->ldaux % 8)))
+    return B200_ERR_INVALID_ARG;
   if (a->C2 && (a->ldc2 % 8)) return B200_ERR_UNSUPPORTED;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int kb_total = (a->K + BLOCK_K - 1) / BLOCK_K;
@@ -752,7 +769,8 @@ extern "C" int b200_gemm(const b200_gemm_args* a, void* stream) {
       const long long tiles = (long long)tiles_m * ((a->N + cand[i] - 1) / cand[i]) * splits;
       long long cost = ((tiles + g_num_sms - 1) / g_num_sms) * cand[i] * 8;
       // the GELU / dGELU epilogues are issue-bound: the 12-warp (192-wide) tile measured 10-15 % faster at equal cost
-      if ((a->epi == B200_EPI_BIAS_GELU || a->epi == B200_EPI_DGELU) && cand[i] != 192) cost += cost / 8;
+      if ((a->epi == B200_EPI_BIAS_GELU || a->epi == B200_EPI_DGELU || a->epi == B200_EPI_BIAS_GELU_DG) && cand[i] != 192)
+        cost += cost / 8;
       if (best < 0 || cost < best) { best = cost; bn = cand[i]; }
     }
   }

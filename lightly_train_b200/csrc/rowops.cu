@@ -140,6 +140,101 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_bwd_kernel(const void* __restr
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward fused with the LayerScale backward that always follows it in the block schedule:
+//   dx_new = dx_old + LN'(dy)                                   (residual-stream gradient, fp32, in place)
+//   dout   = bf16(dx_new * rowscale * gamma)                    (gradient of the NEXT branch output, toward its GEMM)
+//   dgamma += sum dx_new*rowscale*o ; dbias += sum dout ; dw_ln/db_ln += LayerNorm parameter gradients
+// One read of dx less and one launch less than ln_bwd + layerscale_bwd (18 instead of 22 bytes per element).
+template <bool DY_BF16, int VMAX>
+__global__ void __launch_bounds__(ROW_THREADS) ln_bwd_ls_kernel(
+    const void* __restrict__ dy, long long lddy, const float* __restrict__ x, long long ldx, int T, int D,
+    const float* __restrict__ w, const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dx,
+    long long lddx, int accumulate, float* __restrict__ dw, float* __restrict__ db, const __nv_bfloat16* __restrict__ o,
+    long long ldo, const float* __restrict__ gamma, const float* __restrict__ rowscale, int rows_per_scale,
+    __nv_bfloat16* __restrict__ dout, long long lddo, float* __restrict__ dgamma, float* __restrict__ dbias) {
+  extern __shared__ float sm[];  // [4][D]: dw, db, dgamma, dbias
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nv = D >> 2;
+  for (int i = threadIdx.x; i < 4 * D; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  float4 aw[VMAX], ab[VMAX], ag[VMAX], ao[VMAX];
+#pragma unroll
+  for (int j = 0; j < VMAX; ++j) { aw[j] = ab[j] = ag[j] = ao[j] = make_float4(0, 0, 0, 0); }
+  for (int row = blockIdx.x * (ROW_THREADS / 32) + warp; row < T; row += gridDim.x * (ROW_THREADS / 32)) {
+    const float mu = mean[row], rs = rstd[row];
+    const float dps = rowscale ? __ldg(rowscale + row / rows_per_scale) : 1.f;
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ldx);
+    float4* dxr = reinterpret_cast<float4*>(dx + (size_t)row * lddx);
+    float4 g[VMAX], xh[VMAX], dold[VMAX];
+    uint2 ob[VMAX];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < VMAX; ++j) {
+      int c = lane + 32 * j;
+      if (c < nv) {
+        float4 d;
+        if (DY_BF16) {
+          uint2 p = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(dy) + (size_t)row * lddy)[c];
+          float2 a = unpack_bf16x2(p.x), b2 = unpack_bf16x2(p.y);
+          d = make_float4(a.x, a.y, b2.x, b2.y);
+        } else {
+          d = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy) + (size_t)row * lddy)[c];
+        }
+        float4 xv = xr[c];
+        dold[j] = accumulate ? dxr[c] : make_float4(0, 0, 0, 0);
+        ob[j] = reinterpret_cast<const uint2*>(o + (size_t)row * ldo)[c];
+        float4 ww = __ldg(reinterpret_cast<const float4*>(w) + c);
+        xh[j] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        g[j] = make_float4(d.x * ww.x, d.y * ww.y, d.z * ww.z, d.w * ww.w);
+        s1 += g[j].x + g[j].y + g[j].z + g[j].w;
+        s2 += g[j].x * xh[j].x + g[j].y * xh[j].y + g[j].z * xh[j].z + g[j].w * xh[j].w;
+        aw[j].x += d.x * xh[j].x; aw[j].y += d.y * xh[j].y; aw[j].z += d.z * xh[j].z; aw[j].w += d.w * xh[j].w;
+        ab[j].x += d.x; ab[j].y += d.y; ab[j].z += d.z; ab[j].w += d.w;
+      }
+    }
+    s1 = warp_sum(s1) / D;
+    s2 = warp_sum(s2) / D;
+#pragma unroll
+    for (int j = 0; j < VMAX; ++j) {
+      int c = lane + 32 * j;
+      if (c < nv) {
+        float4 nx;
+        nx.x = dold[j].x + rs * (g[j].x - s1 - xh[j].x * s2); nx.y = dold[j].y + rs * (g[j].y - s1 - xh[j].y * s2);
+        nx.z = dold[j].z + rs * (g[j].z - s1 - xh[j].z * s2); nx.w = dold[j].w + rs * (g[j].w - s1 - xh[j].w * s2);
+        dxr[c] = nx;
+        const float4 gs = make_float4(nx.x * dps, nx.y * dps, nx.z * dps, nx.w * dps);
+        const float4 gm = gamma ? __ldg(reinterpret_cast<const float4*>(gamma) + c) : make_float4(1, 1, 1, 1);
+        const float2 o0 = unpack_bf16x2(ob[j].x), o1 = unpack_bf16x2(ob[j].y);
+        ag[j].x += gs.x * o0.x; ag[j].y += gs.y * o0.y; ag[j].z += gs.z * o1.x; ag[j].w += gs.w * o1.y;
+        const float4 dd = make_float4(bf16_round(gs.x * gm.x), bf16_round(gs.y * gm.y), bf16_round(gs.z * gm.z), bf16_round(gs.w * gm.w));
+        ao[j].x += dd.x; ao[j].y += dd.y; ao[j].z += dd.z; ao[j].w += dd.w;
+        uint2 pk; pk.x = pack_bf16x2(dd.x, dd.y); pk.y = pack_bf16x2(dd.z, dd.w);
+        reinterpret_cast<uint2*>(dout + (size_t)row * lddo)[c] = pk;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < VMAX; ++j) {
+    int c = lane + 32 * j;
+    if (c < nv) {
+      const float* srcs[4] = {&aw[j].x, &ab[j].x, &ag[j].x, &ao[j].x};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        atomicAdd(&sm[q * D + 4 * c + 0], srcs[q][0]); atomicAdd(&sm[q * D + 4 * c + 1], srcs[q][1]);
+        atomicAdd(&sm[q * D + 4 * c + 2], srcs[q][2]); atomicAdd(&sm[q * D + 4 * c + 3], srcs[q][3]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    if (dw) { atomicAdd(dw + i, sm[i]); atomicAdd(db + i, sm[D + i]); }
+    if (dgamma) atomicAdd(dgamma + i, sm[2 * D + i]);
+    if (dbias) atomicAdd(dbias + i, sm[3 * D + i]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // im2col for Conv2d(k=s=p): x f32 [B,C,H,W] -> cols bf16 [B*Np, C*p*p], column order (c, ky, kx).
 __global__ void im2col_kernel(const float* __restrict__ x, int B, int C, int H, int W, int p,
@@ -510,7 +605,7 @@ extern "C" int b200_layernorm_bwd(const void* dy, long long lddy, int dy_bf16, c
   if (!dy || !x || !w || !mean || !rstd || !dx || T <= 0 || !ok_dim(D)) return B200_ERR_INVALID_ARG;
   if ((ldx % 4) || (lddx % 4) || (lddy % 4) || (dw && !db)) return B200_ERR_INVALID_ARG;
   int grid = (T + 7) / 8;
-  if (grid > 148 * 8) grid = 148 * 8;
+  if (grid > 148 * 3) grid = 148 * 3;  // resident CTAs only: every CTA ends with 2*D global atomics
   size_t smem = 2 * D * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
 #define B200_LN_BWD(V)                                                                                                           \
@@ -520,6 +615,36 @@ extern "C" int b200_layernorm_bwd(const void* dy, long long lddy, int dy_bf16, c
   } while (0)
   if (D <= 384) B200_LN_BWD(3); else if (D <= 768) B200_LN_BWD(6); else B200_LN_BWD(8);
 #undef B200_LN_BWD
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+
+extern "C" int b200_layernorm_bwd_ls(const void* dy, long long lddy, int dy_bf16, const float* x, long long ldx, int T, int D,
+                                     const float* w, const float* mean, const float* rstd, float* dx, long long lddx,
+                                     int accumulate, float* dw, float* db, const void* o, long long ldo, const float* gamma,
+                                     const float* rowscale, int rows_per_scale, void* dout, long long lddo, float* dgamma,
+                                     float* dbias, void* stream) {
+  if (!dy || !x || !w || !mean || !rstd || !dx || !o || !dout || T <= 0 || !ok_dim(D)) return B200_ERR_INVALID_ARG;
+  if ((ldx % 4) || (lddx % 4) || (lddy % 4) || (ldo % 4) || (lddo % 4) || (dw && !db)) return B200_ERR_INVALID_ARG;
+  int grid = (T + 7) / 8;
+  if (grid > 148 * 3) grid = 148 * 3;
+  const size_t smem = 4 * D * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rps = rows_per_scale > 0 ? rows_per_scale : 1;
+#define B200_LN_BWD_LS(V)                                                                                                   \
+  do {                                                                                                                      \
+    if (dy_bf16)                                                                                                            \
+      ln_bwd_ls_kernel<true, V><<<grid, ROW_THREADS, smem, st>>>(dy, lddy, x, ldx, T, D, w, mean, rstd, dx, lddx, accumulate, dw, db, \
+                                                                 (const __nv_bfloat16*)o, ldo, gamma, rowscale, rps,       \
+                                                                 (__nv_bfloat16*)dout, lddo, dgamma, dbias);               \
+    else                                                                                                                    \
+      ln_bwd_ls_kernel<false, V><<<grid, ROW_THREADS, smem, st>>>(dy, lddy, x, ldx, T, D, w, mean, rstd, dx, lddx, accumulate, dw, db, \
+                                                                  (const __nv_bfloat16*)o, ldo, gamma, rowscale, rps,      \
+                                                                  (__nv_bfloat16*)dout, lddo, dgamma, dbias);              \
+  } while (0)
+  if (D <= 384) B200_LN_BWD_LS(3); else if (D <= 768) B200_LN_BWD_LS(6); else B200_LN_BWD_LS(8);
+#undef B200_LN_BWD_LS
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -562,7 +687,7 @@ extern "C" int b200_layerscale_bwd(const float* dx, long long lddx, const void* 
                                    float* dgamma, float* dbias, void* stream) {
   if (!dx || !o || !dout || T <= 0 || !ok_dim(D) || (lddx % 4) || (ldo % 4) || (lddo % 4)) return B200_ERR_INVALID_ARG;
   int grid = (T + 7) / 8;
-  if (grid > 148 * 8) grid = 148 * 8;
+  if (grid > 148 * 4) grid = 148 * 4;
   cudaStream_t st = (cudaStream_t)stream;
   const int rps = rows_per_scale > 0 ? rows_per_scale : 1;
 #define B200_LS_BWD(V)                                                                                          \

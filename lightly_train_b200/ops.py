@@ -10,8 +10,8 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (EPI_BF16, EPI_BIAS_GELU, EPI_DGELU, EPI_F32, EPI_F32_ATOMIC,  # noqa: F401
-                   EPI_RESIDUAL, GemmArgs, check)
+from ._lib import (EPI_BF16, EPI_BIAS_GELU, EPI_BIAS_GELU_DG, EPI_DGELU, EPI_F32, EPI_F32_ATOMIC,  # noqa: F401
+                   EPI_MUL_AUX, EPI_RESIDUAL, GemmArgs, check)
 
 
 GEMM_PROFILE = None  # bench.py sets this to a list: (flops, start_event, end_event) per b200_gemm launch
@@ -129,6 +129,17 @@ def layernorm_bwd(dy, x, w, mean, rstd, dx, accumulate: bool, dw=None, db=None) 
     check(_L().b200_layernorm_bwd(dy.data_ptr(), dy.stride(0), int(dy.dtype == torch.bfloat16), x.data_ptr(),
                                   x.stride(0), T, D, w.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(),
                                   dx.stride(0), int(accumulate), _ptr(dw), _ptr(db), _stream()), "b200_layernorm_bwd")
+
+
+def layernorm_bwd_ls(dy, x, w, mean, rstd, dx, accumulate: bool, dw, db, o, gamma, rowscale, rows_per_scale: int, dout,
+                     dgamma, dbias) -> None:
+    """ln_bwd fused with the layerscale_bwd that follows it (same dx)."""
+    T, D = x.shape
+    check(_L().b200_layernorm_bwd_ls(dy.data_ptr(), dy.stride(0), int(dy.dtype == torch.bfloat16), x.data_ptr(), x.stride(0),
+                                     T, D, w.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(), dx.stride(0),
+                                     int(accumulate), _ptr(dw), _ptr(db), o.data_ptr(), o.stride(0), _ptr(gamma),
+                                     _ptr(rowscale), rows_per_scale, dout.data_ptr(), dout.stride(0), _ptr(dgamma),
+                                     _ptr(dbias), _stream()), "b200_layernorm_bwd_ls")
 
 
 def im2col(x, p: int, cols) -> None:

@@ -57,6 +57,26 @@ def test_gemm_fused_epilogues():
     torch.testing.assert_close(d.float(), uf.grad, rtol=2e-2, atol=2e-2)
 
 
+def test_gemm_saved_derivative_gelu_epilogues():
+    """BIAS_GELU_DG stores gelu'(u) for the backward; MUL_AUX consumes it (same dU as the DGELU epilogue)."""
+    M, N, K = 777, 1536, 384
+    a, b = rnd(M, K, dtype=torch.bfloat16, scale=0.5, seed=3), rnd(N, K, dtype=torch.bfloat16, scale=0.05, seed=4)
+    bias = rnd(N, seed=5)
+    h, g = torch.empty(M, N, device=dev, dtype=torch.bfloat16), torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    ops.gemm(a, b, h, epi=ops.EPI_BIAS_GELU_DG, bias=bias, out2=g)
+    u = (a.float() @ b.float().t() + bias).bfloat16().float().requires_grad_(True)
+    hr = F.gelu(u)
+    hr.sum().backward()
+    torch.testing.assert_close(h.float(), hr.detach().bfloat16().float(), rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(g.float(), u.grad.bfloat16().float(), rtol=1e-2, atol=1e-2)
+    dy = rnd(M, K, dtype=torch.bfloat16, seed=6)
+    w = rnd(K, N, dtype=torch.bfloat16, scale=0.05, seed=7)  # [out=K... used as MN-major B: dU[M,N] = dy[M,K] @ w[K,N]
+    dU = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    ops.gemm(dy, w, dU, b_mn=True, epi=ops.EPI_MUL_AUX, aux=g)
+    want = (dy.float() @ w.float()).bfloat16().float() * g.float()
+    torch.testing.assert_close(dU.float(), want.bfloat16().float(), rtol=2e-2, atol=2e-2)
+
+
 def test_gemm_splitk_atomic_accumulates():
     M, N, K = 1152, 384, 9000
     a, b = rnd(K, M, dtype=torch.bfloat16, seed=8), rnd(K, N, dtype=torch.bfloat16, seed=9)
@@ -112,6 +132,32 @@ def test_layernorm_fwd_bwd(T, D):
     dx2 = torch.empty(T, D, device=dev)
     ops.layernorm_bwd(dy.bfloat16(), x.detach(), w.detach(), mean, rstd, dx2, False)
     torch.testing.assert_close(dx2, x.grad, rtol=5e-2, atol=5e-2)
+
+
+def test_layernorm_bwd_fused_with_layerscale_bwd():
+    T, D = 1003, 384
+    x = rnd(T, D, seed=50, scale=2.0)
+    w = 1 + 0.1 * rnd(D, seed=51)
+    mean, rstd = torch.empty(T, device=dev), torch.empty(T, device=dev)
+    y = torch.empty(T, D, device=dev)
+    ops.layernorm_fwd(x, w, rnd(D, seed=52), 1e-6, y, mean, rstd)
+    dy = rnd(T, D, dtype=torch.bfloat16, seed=53)
+    o = rnd(T, D, dtype=torch.bfloat16, seed=54)
+    gamma = rnd(D, seed=55)
+    rs = torch.rand(T // 59 + 1, device=dev)
+    dx0 = rnd(T, D, seed=56)
+    # reference: the two separate kernels
+    dx_ref = dx0.clone(); dw_r, db_r = torch.zeros(D, device=dev), torch.zeros(D, device=dev)
+    ops.layernorm_bwd(dy, x, w, mean, rstd, dx_ref, True, dw_r, db_r)
+    do_ref = torch.empty(T, D, device=dev, dtype=torch.bfloat16); dg_r, dbi_r = torch.zeros(D, device=dev), torch.zeros(D, device=dev)
+    ops.layerscale_bwd(dx_ref, o, gamma, rs, 59, do_ref, dg_r, dbi_r)
+    dx = dx0.clone(); dw, db = torch.zeros(D, device=dev), torch.zeros(D, device=dev)
+    do = torch.empty(T, D, device=dev, dtype=torch.bfloat16); dg, dbi = torch.zeros(D, device=dev), torch.zeros(D, device=dev)
+    ops.layernorm_bwd_ls(dy, x, w, mean, rstd, dx, True, dw, db, o, gamma, rs, 59, do, dg, dbi)
+    torch.testing.assert_close(dx, dx_ref, rtol=1e-5, atol=1e-5)
+    assert torch.equal(do, do_ref)
+    for a, b in ((dw, dw_r), (db, db_r), (dg, dg_r), (dbi, dbi_r)):
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-3)
 
 
 @pytest.mark.parametrize("p,H", [(16, 224), (16, 96), (14, 98)])
