@@ -275,13 +275,15 @@ def main() -> None:
 
     # ---- roofline: every tcgen05 GEMM launch of one step timed with CUDA events on the launch stream
     roofline = None
+    # every rank runs this extra step (it contains the gradient all-reduce); rank 0 reports
+    ops.GEMM_PROFILE = []
+    method.use_cuda_graph = False  # events cannot be recorded inside a graph replay: time the eager schedule
+    torch.cuda._sleep(int(8e7))    # ~40 ms head start for the host, so event pairs bracket kernels, not launch gaps
+    method.train_step(batches[0])
+    torch.cuda.synchronize()
+    method.use_cuda_graph = not args.eager
+    prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
     if rank == 0:
-        ops.GEMM_PROFILE = []
-        method.use_cuda_graph = False  # events cannot be recorded inside a graph replay: time the eager schedule
-        method.train_step(batches[0])
-        torch.cuda.synchronize()
-        method.use_cuda_graph = not args.eager
-        prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
         if args.gemm_profile:
             table = {}
             for (f, a, b), key in zip(prof, ops.GEMM_PROFILE_KEYS):
@@ -327,6 +329,7 @@ def main() -> None:
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
