@@ -53,7 +53,7 @@ typedef struct b200_gemm_args {
   const void* A; long long lda; int a_mn;
   const void* B; long long ldb; int b_mn;
   int M, N, K;
-  int splits;            /* split-K factor (>1 only with B200_EPI_F32_ATOMIC)                       */
+  int splits;            /* split-K factor (>1 only with B200_EPI_F32_ATOMIC; 0 there = choose automatically) */
   int epi;               /* B200_EPI_*                                                              */
   int block_n;           /* 0 = auto, or 128 / 192 / 256                                            */
   int ws_mode;           /* 0 = auto, 1 = force weight-stationary schedule (K <= 384), 2 = never     */

@@ -110,7 +110,7 @@ class DINOv2ProjectionHead(nn.Module):
         dev = dlogits.device
         Hd, Bn = self.hidden_dim, self.bottleneck_dim
         E = lambda *s, dt=torch.bfloat16: torch.empty(*s, device=dev, dtype=dt)  # noqa: E731
-        splits = max(1, min(16, R // 512))
+        splits = 0  # auto split-K
         # last layer: dW_eff = dlogits^T zn (fp32), then through the weight-norm parametrisation
         dW = E(K, Bn, dt=torch.float32)
         ops.gemm(dlogits, ctx.zn, dW, a_mn=True, b_mn=True, epi=ops.EPI_F32)

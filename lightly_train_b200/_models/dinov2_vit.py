@@ -255,8 +255,8 @@ class DinoVisionTransformer(nn.Module):
         dev = d_xnorm.device
         bf, f32 = torch.bfloat16, torch.float32
         E = lambda *s, dt=bf: torch.empty(*s, device=dev, dtype=dt)  # noqa: E731
-        if wgrad_splits <= 0:
-            wgrad_splits = max(1, min(32, T // 2048))
+        if wgrad_splits < 0:
+            wgrad_splits = 0  # 0 = let b200_gemm pick (tile width, split-K) for whole waves over the SMs
         scale = 64 ** -0.5
 
         def wgrad(dy: Tensor, xin: Tensor, name: str) -> None:
@@ -331,7 +331,7 @@ class DinoVisionTransformer(nn.Module):
             gpos[0].add_(dpos[0])
         ops.col_reduce(dtok, self._G("patch_embed.proj.bias"))
         ops.gemm(dtok, ctx.cols, self._G("patch_embed.proj.weight").view(D, -1), a_mn=True, b_mn=True,
-                 epi=ops.EPI_F32_ATOMIC, splits=max(1, min(32, (Bc * Np) // 2048)))
+                 epi=ops.EPI_F32_ATOMIC, splits=0)
 
     # ------------------------------------------------------------------ reference-facing API
     @torch.no_grad()

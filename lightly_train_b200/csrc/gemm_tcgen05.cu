@@ -742,6 +742,37 @@ extern "C" int b200_gemm(const b200_gemm_args* a, void* stream) {
   if (((uintptr_t)a->A & 15) || ((uintptr_t)a->B & 15) || ((uintptr_t)a->C & 15)) return B200_ERR_UNSUPPORTED;
   if (a->epi < 0 || a->epi > B200_EPI_MUL_AUX) return B200_ERR_INVALID_ARG;
   if (a->splits > 1 && a->epi != B200_EPI_F32_ATOMIC) return B200_ERR_INVALID_ARG;
+  b200_gemm_args tuned;
+  if (a->splits == 0 && a->epi == B200_EPI_F32_ATOMIC) {
+    // auto split-K (wgrad: few output tiles, very long K): pick (tile width, splits) so that tiles*splits fills whole
+    // waves of the 148 SMs; cost ~ rounds * k-blocks per split * tile width
+    if (g_num_sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int kbt = (a->K + BLOCK_K - 1) / BLOCK_K;
+    const int tm = (a->M + BLOCK_M - 1) / BLOCK_M;
+    const int cand[3] = {192, 256, 128};
+    long long best = -1;
+    int best_bn = 192, best_sp = 1;
+    for (int i = 0; i < 3; ++i) {
+      if (a->block_n != 0 && a->block_n != cand[i]) continue;
+      const int tiles = tm * ((a->N + cand[i] - 1) / cand[i]);
+      for (int r = 1; r <= 6; ++r) {
+        int sp = (g_num_sms * r) / tiles;
+        if (sp < 1) continue;
+        if (sp > kbt / 4) sp = kbt / 4 > 0 ? kbt / 4 : 1;
+        const int rounds = (tiles * sp + g_num_sms - 1) / g_num_sms;
+        const long long cost = (long long)rounds * ((kbt + sp - 1) / sp + 6) * cand[i];  // +6: per-item prologue/epilogue
+        if (best < 0 || cost < best) { best = cost; best_bn = cand[i]; best_sp = sp; }
+      }
+    }
+    tuned = *a;
+    tuned.block_n = best_bn;
+    tuned.splits = best_sp;
+    a = &tuned;
+  }
   if ((a->epi == B200_EPI_RESIDUAL || a->epi == B200_EPI_DGELU || a->epi == B200_EPI_MUL_AUX) && (!a->aux || (a->ldaux % 8)))
     return B200_ERR_INVALID_ARG;
   if (a->C2 && (a->ldc2 % 8)) return B200_ERR_UNSUPPORTED;

@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(256) segment_sum_kernel(const float* __restric
 //   xn = x / max(||x||, eps); sim = round_bf16?(xn xn^T), diag = -2; j(i) = argmax_k sim[i,k] (first index)
 //   d_i = || xn_i - xn_j + eps ||_2 ; loss = -(1/n) sum_i log(d_i + eps)
 // dx (fp32, accumulated with +=) = gscale * dloss/dx, argmax treated as constant (as autograd does).
+template <int DL>
 __global__ void __launch_bounds__(256) koleo_kernel(const float* __restrict__ x, long long ldx, int n, int D, float eps,
                                                     int bf16_sim, float gscale, float* __restrict__ loss_out,
                                                     float* __restrict__ dx, long long lddx, int* __restrict__ nn_out) {
@@ -281,26 +282,52 @@ __global__ void __launch_bounds__(256) koleo_kernel(const float* __restrict__ x,
     for (int d = lane; d < D; d += 32) { xn[i * D + d] = x[(size_t)i * ldx + d] / nr; gxn[i * D + d] = 0.f; }
   }
   __syncthreads();
-  // nearest neighbour (one warp per row i)
-  for (int i = warp; i < n; i += nwarps) {
-    float best = -INFINITY; int bi = 0;
+  // optional bf16 rounding of the similarity operands (the autocast reference runs x @ x.T in bf16): done once, in place
+  // in a copy that reuses gxn (zeroed again below)
+  float* xs = gxn;
+  for (int i = threadIdx.x; i < n * D; i += blockDim.x) xs[i] = bf16_sim ? bf16_round(xn[i]) : xn[i];
+  __syncthreads();
+  // nearest neighbour: a warp owns up to KR rows at a time (kept in registers) and streams every candidate row k once
+  constexpr int KR = 4;     // DL = D / 32 elements of a row per lane (template parameter -> registers)
+  for (int i0 = warp * KR; i0 < n; i0 += nwarps * KR) {
+    float r[KR][DL];
+#pragma unroll
+    for (int q = 0; q < KR; ++q)
+#pragma unroll
+      for (int e = 0; e < DL; ++e) r[q][e] = (i0 + q < n) ? xs[(i0 + q) * D + lane + 32 * e] : 0.f;
+    float best[KR]; int bi[KR];
+#pragma unroll
+    for (int q = 0; q < KR; ++q) { best[q] = -INFINITY; bi[q] = 0; }
     for (int k = 0; k < n; ++k) {
-      float dot = 0.f;
-      if (bf16_sim) {
-        for (int d = lane; d < D; d += 32) dot += bf16_round(xn[i * D + d]) * bf16_round(xn[k * D + d]);
-      } else {
-        for (int d = lane; d < D; d += 32) dot += xn[i * D + d] * xn[k * D + d];
+      float dot[KR];
+#pragma unroll
+      for (int q = 0; q < KR; ++q) dot[q] = 0.f;
+#pragma unroll
+      for (int e = 0; e < DL; ++e) {
+        const float xk = xs[k * D + lane + 32 * e];
+#pragma unroll
+        for (int q = 0; q < KR; ++q) dot[q] = fmaf(r[q][e], xk, dot[q]);
       }
-      dot = warp_sum(dot);
-      if (bf16_sim) dot = bf16_round(dot);
-      if (k == i) dot = -2.f;
-      if (dot > best) { best = dot; bi = k; }
+#pragma unroll
+      for (int q = 0; q < KR; ++q) {
+        float dsum = warp_sum(dot[q]);
+        if (bf16_sim) dsum = bf16_round(dsum);
+        if (k == i0 + q) dsum = -2.f;
+        if (dsum > best[q]) { best[q] = dsum; bi[q] = k; }
+      }
     }
-    float ss = 0.f;
-    for (int d = lane; d < D; d += 32) { float df = xn[i * D + d] - xn[bi * D + d] + eps; ss += df * df; }
-    ss = warp_sum(ss);
-    if (lane == 0) { nn[i] = bi; dist[i] = sqrtf(ss); if (nn_out) nn_out[g * n + i] = bi; }
+#pragma unroll
+    for (int q = 0; q < KR; ++q) {
+      const int i = i0 + q;
+      if (i >= n) continue;
+      float ss = 0.f;
+      for (int d = lane; d < D; d += 32) { float df = xn[i * D + d] - xn[bi[q] * D + d] + eps; ss += df * df; }
+      ss = warp_sum(ss);
+      if (lane == 0) { nn[i] = bi[q]; dist[i] = sqrtf(ss); if (nn_out) nn_out[g * n + i] = bi[q]; }
+    }
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n * D; i += blockDim.x) gxn[i] = 0.f;
   __syncthreads();
   if (warp == 0) {
     float l = 0.f;
@@ -394,16 +421,28 @@ extern "C" int b200_segment_sum(const float* x, const int* offsets, int n_segmen
 
 extern "C" int b200_koleo(const float* x, long long ldx, int groups, int n, int D, float eps, int bf16_sim, float gscale,
                           float* loss_out, float* dx, long long lddx, int* nn_out, void* stream) {
-  if (!x || !loss_out || groups <= 0 || n <= 1 || n > 256 || D <= 0) return B200_ERR_INVALID_ARG;
+  if (!x || !loss_out || groups <= 0 || n <= 1 || n > 256 || D <= 0 || (D % 32) || D > 1024) return B200_ERR_INVALID_ARG;
   size_t smem = (size_t)(2 * n * D + 3 * n) * sizeof(float);
   if (smem > 220 * 1024) return B200_ERR_UNSUPPORTED;
-  static bool attr = false;
-  if (!attr) {
-    if (cudaFuncSetAttribute(koleo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
-      return B200_ERR_CUDA;
-    attr = true;
+#define B200_KOLEO(DLV)                                                                                              \
+  do {                                                                                                               \
+    static bool attr = false;                                                                                        \
+    if (!attr) {                                                                                                     \
+      if (cudaFuncSetAttribute(koleo_kernel<DLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) \
+        return B200_ERR_CUDA;                                                                                        \
+      attr = true;                                                                                                   \
+    }                                                                                                                \
+    koleo_kernel<DLV><<<groups, 256, smem, (cudaStream_t)stream>>>(x, ldx, n, D, eps, bf16_sim, gscale, loss_out, dx, lddx, nn_out); \
+  } while (0)
+  switch (D / 32) {
+    case 4: B200_KOLEO(4); break;
+    case 6: B200_KOLEO(6); break;
+    case 12: B200_KOLEO(12); break;
+    case 24: B200_KOLEO(24); break;
+    case 32: B200_KOLEO(32); break;
+    default: return B200_ERR_UNSUPPORTED;
   }
-  koleo_kernel<<<groups, 256, smem, (cudaStream_t)stream>>>(x, ldx, n, D, eps, bf16_sim, gscale, loss_out, dx, lddx, nn_out);
+#undef B200_KOLEO
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

@@ -318,7 +318,9 @@ __global__ void assemble_tokens_bwd_kernel(const float* __restrict__ dx, const u
   if (i >= (long long)N * nd4) return;
   const int n = (int)(i / nd4), d = (int)(i % nd4) * 4;
   float4 acc = make_float4(0, 0, 0, 0), accm = make_float4(0, 0, 0, 0);
-  for (int b = 0; b < B; ++b) {
+  const int per = (B + gridDim.y - 1) / gridDim.y;  // the batch is split over blockIdx.y (partial sums meet in atomics)
+  const int b0 = blockIdx.y * per, b1 = min(B, b0 + per);
+  for (int b = b0; b < b1; ++b) {
     float4 g = *reinterpret_cast<const float4*>(dx + ((size_t)b * N + n) * D + d);
     if (n > R) {
       const int p = n - 1 - R;
@@ -676,7 +678,8 @@ extern "C" int b200_assemble_tokens_bwd(const float* dx, const unsigned char* ma
   if (!dx || !dtok || !dpos || !dcls || B <= 0 || Np <= 0 || (D % 4) || (lddt % 4)) return B200_ERR_INVALID_ARG;
   if ((masks && !dmask_token) || (R > 0 && !dreg)) return B200_ERR_INVALID_ARG;
   long long n = (long long)(1 + R + Np) * (D / 4);
-  assemble_tokens_bwd_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+  const int ysplit = B >= 64 ? 8 : (B >= 8 ? 4 : 1);
+  assemble_tokens_bwd_kernel<<<dim3((unsigned)((n + 127) / 128), ysplit), 128, 0, (cudaStream_t)stream>>>(
       dx, masks, B, Np, R, D, (__nv_bfloat16*)dtok, lddt, dpos, dcls, dreg, dmask_token);
   B200_CHECK_LAUNCH();
   return B200_OK;
