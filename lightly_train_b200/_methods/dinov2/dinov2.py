@@ -115,6 +115,11 @@ class _Wrapped(nn.Module):
     def get_model(self) -> DinoVisionTransformer:
         return self._model
 
+    def set_activation_checkpointing(self, enabled: bool, every_n_blocks: int = 1) -> None:
+        """DINOv2ViTModelWrapper.set_activation_checkpointing (LT/_models/dinov2_vit/dinov2_vit.py:55-59)."""
+        self._model._activation_checkpointing = enabled
+        self._model._activation_checkpointing_every_n_blocks = every_n_blocks
+
     @torch.no_grad()
     def forward_features(self, x: Tensor, masks: Optional[Tensor] = None) -> Dict[str, Tensor]:
         """DINOv2ViTModelWrapper.forward_features (LT/_models/dinov2_vit/dinov2_vit.py:67-97)."""

@@ -114,6 +114,9 @@ class DinoVisionTransformer(nn.Module):
         self.arena = arena
         attach_params(self, arena, prefix, [prefix + k for k in shapes], requires_grad)
         self._pos_ops: Dict[Tuple[int, int], Tensor] = {}
+        # configured post-instantiation, like DINOv2ViTModelWrapper.set_activation_checkpointing (dinov2_vit.py:55-59)
+        self._activation_checkpointing = False
+        self._activation_checkpointing_every_n_blocks = 1
         self.init_weights(init_values)
 
     # ------------------------------------------------------------------ init (vision_transformer.py:244-249,574+)
@@ -171,8 +174,49 @@ class DinoVisionTransformer(nn.Module):
         ops.small_matmul(op, pos[1:], out[1:])
         return out, True
 
+    # ------------------------------------------------------------------ one block forward (Block.forward, block.py:90-115)
+    def _block_fwd(self, i: int, xcur: Tensor, Bc: int, N: int, rs1: Optional[Tensor], rs2: Optional[Tensor], save: bool) -> dict:
+        dev = xcur.device
+        D, Hd, h = self.embed_dim, self.hidden_dim, self.num_heads
+        T = xcur.shape[0]
+        bf, f32 = torch.bfloat16, torch.float32
+        E = lambda *s, dt=bf: torch.empty(*s, device=dev, dtype=dt)  # noqa: E731
+        b = f"blocks.{i}."
+        scale = 64 ** -0.5
+        mean1, rstd1 = (E(T, dt=f32), E(T, dt=f32)) if save else (None, None)
+        xn = E(T, D)
+        ops.layernorm_fwd(xcur, self._P(b + "norm1.weight"), self._P(b + "norm1.bias"), self.ln_eps, xn, mean1, rstd1)
+        qkv = E(T, 3 * D)
+        ops.gemm(xn, self._W(b + "attn.qkv.weight"), qkv, bias=self._P(b + "attn.qkv.bias"))
+        att = E(T, D)
+        lse = E(Bc * h, N, dt=f32) if save else None
+        ops.attention_fwd(qkv, Bc, N, h, att, lse, scale)
+        o1 = E(T, D) if save else None
+        xmid = E(T, D, dt=f32)
+        ops.gemm(att, self._W(b + "attn.proj.weight"), xmid, epi=ops.EPI_RESIDUAL, bias=self._P(b + "attn.proj.bias"),
+                 out2=o1, aux=xcur, gamma=self._P(b + "ls1.gamma") if self.layerscale else None,
+                 rowscale=rs1, rows_per_scale=N)
+        mean2, rstd2 = (E(T, dt=f32), E(T, dt=f32)) if save else (None, None)
+        xn2 = E(T, D)
+        ops.layernorm_fwd(xmid, self._P(b + "norm2.weight"), self._P(b + "norm2.bias"), self.ln_eps, xn2, mean2, rstd2)
+        hh = E(T, Hd)
+        u = E(T, Hd) if save else None
+        ops.gemm(xn2, self._W(b + "mlp.fc1.weight"), hh, epi=ops.EPI_BIAS_GELU_DG if save else ops.EPI_BIAS_GELU,
+                 bias=self._P(b + "mlp.fc1.bias"), out2=u)  # u holds gelu'(fc1 out) for the backward
+        o2 = E(T, D) if save else None
+        xout = E(T, D, dt=f32)
+        ops.gemm(hh, self._W(b + "mlp.fc2.weight"), xout, epi=ops.EPI_RESIDUAL, bias=self._P(b + "mlp.fc2.bias"),
+                 out2=o2, aux=xmid, gamma=self._P(b + "ls2.gamma") if self.layerscale else None,
+                 rowscale=rs2, rows_per_scale=N)
+        sv = {"x_out": xout}
+        if save:
+            sv.update(x_in=xcur, mean1=mean1, rstd1=rstd1, xn=xn, qkv=qkv, att=att, lse=lse, o1=o1, x_mid=xmid,
+                      mean2=mean2, rstd2=rstd2, xn2=xn2, u=u, h=hh, o2=o2, rs1=rs1, rs2=rs2)
+        return sv
+
     # ------------------------------------------------------------------ forward
-    def _fwd(self, x: Tensor, masks: Optional[Tensor], save: bool, drop_path: bool = False) -> VitCtx:
+    def _fwd(self, x: Tensor, masks: Optional[Tensor], save: bool, drop_path: bool = False,
+             keep_scales: Optional[List[Tensor]] = None) -> VitCtx:
         if not self.arena.bf16_valid:
             self.arena.refresh_bf16()
         dev = x.device
@@ -200,43 +244,29 @@ class DinoVisionTransformer(nn.Module):
         xcur = xs.view(T, D)
         if save:
             ctx.cols, ctx.masks_u8, ctx.interp = cols, masks_u8, interp
-        scale = 64 ** -0.5
         for i in range(self.n_blocks):
-            b = f"blocks.{i}."
-            sv: dict = {}
             rs1 = rs2 = None
-            if drop_path and self.dpr[i] > 0.0:
+            if keep_scales is not None:
+                rs1, rs2 = keep_scales[i][0].contiguous(), keep_scales[i][1].contiguous()
+            elif drop_path and self.dpr[i] > 0.1:
+                # drop_add_residual_stochastic_depth (layers/block.py:118-141): the branch runs on a random subset of
+                # b' = max(int(b*(1-r)), 1) samples and is added back with alpha = b/b'.  Same arithmetic as a per-sample
+                # scale of b/b' on the subset and 0 elsewhere (the dropped samples' branch output is computed, then unused).
+                bsub = max(int(Bc * (1.0 - self.dpr[i])), 1)
+                rs1 = torch.zeros(Bc, device=dev, dtype=f32)
+                rs1[torch.randperm(Bc, device=dev)[:bsub]] = Bc / bsub
+                rs2 = torch.zeros(Bc, device=dev, dtype=f32)
+                rs2[torch.randperm(Bc, device=dev)[:bsub]] = Bc / bsub
+            elif drop_path and self.dpr[i] > 0.0:
                 keep = 1.0 - self.dpr[i]
                 rs1 = torch.empty(Bc, device=dev, dtype=f32).bernoulli_(keep).div_(keep)  # drop_path.py:23-27
                 rs2 = torch.empty(Bc, device=dev, dtype=f32).bernoulli_(keep).div_(keep)
-            mean1, rstd1 = (E(T, dt=f32), E(T, dt=f32)) if save else (None, None)
-            xn = E(T, D)
-            ops.layernorm_fwd(xcur, self._P(b + "norm1.weight"), self._P(b + "norm1.bias"), self.ln_eps, xn, mean1, rstd1)
-            qkv = E(T, 3 * D)
-            ops.gemm(xn, self._W(b + "attn.qkv.weight"), qkv, bias=self._P(b + "attn.qkv.bias"))
-            att = E(T, D)
-            lse = E(Bc * h, N, dt=f32) if save else None
-            ops.attention_fwd(qkv, Bc, N, h, att, lse, scale)
-            o1 = E(T, D) if save else None
-            xmid = E(T, D, dt=f32)
-            ops.gemm(att, self._W(b + "attn.proj.weight"), xmid, epi=ops.EPI_RESIDUAL, bias=self._P(b + "attn.proj.bias"),
-                     out2=o1, aux=xcur, gamma=self._P(b + "ls1.gamma") if self.layerscale else None,
-                     rowscale=rs1, rows_per_scale=N)
-            mean2, rstd2 = (E(T, dt=f32), E(T, dt=f32)) if save else (None, None)
-            xn2 = E(T, D)
-            ops.layernorm_fwd(xmid, self._P(b + "norm2.weight"), self._P(b + "norm2.bias"), self.ln_eps, xn2, mean2, rstd2)
-            hh = E(T, Hd)
-            u = E(T, Hd) if save else None
-            ops.gemm(xn2, self._W(b + "mlp.fc1.weight"), hh, epi=ops.EPI_BIAS_GELU_DG if save else ops.EPI_BIAS_GELU,
-                     bias=self._P(b + "mlp.fc1.bias"), out2=u)  # u holds gelu'(fc1 out) for the backward
-            o2 = E(T, D) if save else None
-            xout = E(T, D, dt=f32)
-            ops.gemm(hh, self._W(b + "mlp.fc2.weight"), xout, epi=ops.EPI_RESIDUAL, bias=self._P(b + "mlp.fc2.bias"),
-                     out2=o2, aux=xmid, gamma=self._P(b + "ls2.gamma") if self.layerscale else None,
-                     rowscale=rs2, rows_per_scale=N)
+            ckpt = save and self._activation_checkpointing and (i % self._activation_checkpointing_every_n_blocks == 0)
+            sv = self._block_fwd(i, xcur, Bc, N, rs1, rs2, save and not ckpt)
+            xout = sv.pop("x_out")
             if save:
-                sv.update(x_in=xcur, mean1=mean1, rstd1=rstd1, xn=xn, qkv=qkv, att=att, lse=lse, o1=o1, x_mid=xmid,
-                          mean2=mean2, rstd2=rstd2, xn2=xn2, u=u, h=hh, o2=o2, rs1=rs1, rs2=rs2)
+                if ckpt:  # keep only what the recomputation needs (LT/_activation_checkpointing.py:43-73)
+                    sv = {"ckpt": True, "x_in": xcur, "rs1": rs1, "rs2": rs2}
                 ctx.blocks.append(sv)
             xcur = xout
         meanf, rstdf = (E(T, dt=f32), E(T, dt=f32)) if save else (None, None)
@@ -268,7 +298,16 @@ class DinoVisionTransformer(nn.Module):
         nb = self.n_blocks
         dx = E(T, D, dt=f32)
         # final LayerNorm backward, fused with the LayerScale backward of the last block's MLP branch
-        last = ctx.blocks[nb - 1]
+        def materialise(j: int) -> dict:
+            """Recompute the activations of a checkpointed block from its saved input (same DropPath scales)."""
+            blk = ctx.blocks[j]
+            if blk.get("ckpt"):
+                blk = self._block_fwd(j, blk["x_in"], Bc, N, blk["rs1"], blk["rs2"], True)
+                blk.pop("x_out")
+                ctx.blocks[j] = blk
+            return blk
+
+        last = materialise(nb - 1)
         bl = f"blocks.{nb - 1}."
         do2 = E(T, D)
         ops.layernorm_bwd_ls(d_xnorm, ctx.x_prenorm, self._P("norm.weight"), ctx.meanf, ctx.rstdf, dx, False,
@@ -304,7 +343,7 @@ class DinoVisionTransformer(nn.Module):
             ops.gemm(dqkv, self._W(b + "attn.qkv.weight"), dxn, b_mn=True)
             if i > 0:
                 # LN1 backward fused with the LayerScale backward of the PREVIOUS block's MLP branch
-                pv = ctx.blocks[i - 1]
+                pv = materialise(i - 1)
                 bp = f"blocks.{i - 1}."
                 do2 = E(T, D)
                 ops.layernorm_bwd_ls(dxn, sv["x_in"], self._P(b + "norm1.weight"), sv["mean1"], sv["rstd1"], dx, True,

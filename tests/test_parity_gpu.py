@@ -217,3 +217,39 @@ def test_cuda_graph_replay_matches_eager_schedule():
     m1.ibot_loss.apply_center_update(); m2.ibot_loss.apply_center_update()
     torch.testing.assert_close(m1.dino_loss.center, m2.dino_loss.center, rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(m1.ibot_loss.center, m2.ibot_loss.center, rtol=1e-5, atol=1e-6)
+
+
+def test_activation_checkpointing_and_stochastic_depth_variants():
+    """(a) activation checkpointing (recompute in the backward) must give the same gradients as saving everything;
+    (b) explicit per-sample residual scales (DropPath / batch-subset stochastic depth, layers/block.py:104-141,
+    drop_path.py:16-27) must match the oracle's block with the same scales."""
+    cfg = R.VIT_TINY
+    sd = R.det_vit_state(cfg, seed=11)
+    xg, _, masks = R.vit_case_inputs()
+    g = torch.Generator().manual_seed(5)
+    # block 0: DropPath-style scales {0, 1/keep}; block 1: subset-style {0, b/b'}
+    ks = [torch.tensor([[0.0, 1 / 0.9], [1 / 0.9, 1 / 0.9]]), torch.tensor([[2.0, 0.0], [0.0, 2.0]])]
+
+    def run(ckpt: bool):
+        m = DinoVisionTransformer(img_size=cfg.img_size, patch_size=cfg.patch_size, embed_dim=cfg.embed_dim, depth=cfg.depth,
+                                  num_heads=cfg.num_heads, init_values=cfg.init_values, requires_grad=True)
+        m.load_state_dict(sd, strict=True)
+        m.arena.bf16_valid = False
+        m._activation_checkpointing = ckpt
+        m.arena.zero_grad()
+        ctx = m._fwd(xg.to(dev), masks.to(dev), save=True, keep_scales=[k.to(dev) for k in ks])
+        out = ctx.xnorm.clone()
+        cot = torch.randn(ctx.xnorm.shape, generator=g if False else torch.Generator().manual_seed(9)).to(dev)
+        m._bwd(ctx, cot)
+        torch.cuda.synchronize()
+        return out, m.arena.grad.clone()
+
+    out_a, grad_a = run(False)
+    out_b, grad_b = run(True)
+    torch.testing.assert_close(out_a, out_b, rtol=0, atol=0)
+    assert (grad_a - grad_b).abs().max().item() <= 2e-4 * grad_a.abs().max().item()
+    ref = O.vit_forward_features(sd, cfg, xg, masks, autocast=True, keep_scales=ks)
+    B, N = xg.shape[0], 197
+    xn = out_a.view(B, N, -1).float().cpu()
+    assert (xn[:, 0] - ref["cls"]).abs().max().item() < 3e-2
+    assert (xn[:, 1:] - ref["patch"]).abs().mean().item() < 3e-3
