@@ -253,10 +253,11 @@ class DinoVisionTransformer(nn.Module):
                 # b' = max(int(b*(1-r)), 1) samples and is added back with alpha = b/b'.  Same arithmetic as a per-sample
                 # scale of b/b' on the subset and 0 elsewhere (the dropped samples' branch output is computed, then unused).
                 bsub = max(int(Bc * (1.0 - self.dpr[i])), 1)
+                # (random subset = the bsub smallest of Bc uniform draws: graph-capturable, unlike randperm/index_put)
                 rs1 = torch.zeros(Bc, device=dev, dtype=f32)
-                rs1[torch.randperm(Bc, device=dev)[:bsub]] = Bc / bsub
+                rs1.index_fill_(0, torch.rand(Bc, device=dev).argsort()[:bsub], Bc / bsub)
                 rs2 = torch.zeros(Bc, device=dev, dtype=f32)
-                rs2[torch.randperm(Bc, device=dev)[:bsub]] = Bc / bsub
+                rs2.index_fill_(0, torch.rand(Bc, device=dev).argsort()[:bsub], Bc / bsub)
             elif drop_path and self.dpr[i] > 0.0:
                 keep = 1.0 - self.dpr[i]
                 rs1 = torch.empty(Bc, device=dev, dtype=f32).bernoulli_(keep).div_(keep)  # drop_path.py:23-27
