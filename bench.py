@@ -302,8 +302,13 @@ def main() -> None:
             peaks = json.loads(pk.read_text())
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
         ach = flops / (gemm_ms * 1e-3) / 1e12
+        traffic = None
+        tf = ROOT / "profiles" / "r01_gemm_traffic.json"  # dram bytes per launch from the committed `ncu --set full` capture
+        if tf.exists():
+            traffic = json.loads(tf.read_text()).get("mean_dram_bytes_per_launch")
         roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all launches of one step)", "achieved": ach,
-                    "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                    "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
+                    "traffic_source": "profiles/r01_gemm_traffic.json: mean dram read+write bytes per launch over the 5 block GEMMs",
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
                     "timed": "CUDA events around every b200_gemm launch of one eagerly launched step (same kernels as the graph replay)",
                     "gemm_launches": len(prof), "gemm_ms_per_step": gemm_ms, "gemm_tflop_per_step": flops / 1e12}
