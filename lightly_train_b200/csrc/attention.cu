@@ -40,6 +40,21 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// first MMA of an accumulation chain: C = 0 (ptxas maps the zero inputs to RZ, no accumulator clearing moves)
+__device__ __forceinline__ void mma16816_z(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+      : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
+}
+// round two fp32 values to bf16 precision (one F2FP + two bit ops instead of two F2F + two shifts)
+__device__ __forceinline__ void bf16_round2(float& a, float& b) {
+  const uint32_t u = pack_bf16x2(a, b);
+  a = __uint_as_float(u << 16);
+  b = __uint_as_float(u & 0xffff0000u);
+}
+static constexpr float kLog2e = 1.4426950408889634f;
+
 // byte offset of 16-byte chunk `chunk` of row `row` inside a [rows][64] bf16 tile (128 B rows, XOR swizzle)
 __device__ __forceinline__ uint32_t tile_off(int row, int chunk) {
   return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
@@ -95,7 +110,10 @@ __device__ __forceinline__ void store_tile(const float (&o)[8][4], float mul, ui
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int NKV16, int WARPS>
+// EXACT: N > (NKV16 - 1) * 16, i.e. only the last 16-column block can hold padded key columns (mask nothing else).
+// S is rounded to bf16 before the scale is applied: identical to the reference order for power-of-two scales
+// (head_dim 64 -> 0.125), and the scale then folds into the exponent FMA.
+template <int NKV16, int WARPS, bool EXACT>
 __global__ void __launch_bounds__(WARPS * 32)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, int N, int h, float scale,
                 __nv_bfloat16* __restrict__ out, long long ld_out, float* __restrict__ lse) {
@@ -112,45 +130,61 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, int N, 
   cp_async_wait_all();
   __syncthreads();
 
+  // per-lane ldmatrix offsets: the XOR swizzle only touches address bits 4-6, so a k-step is `^ (ks << 5)` and a
+  // 16-row block is `+ 2048` (folded into the instruction's immediate by ptxas)
+  const int mi = lane >> 3;
+  const uint32_t offA = tile_off((mi & 1) * 8 + (lane & 7), mi >> 1);  // A operand and transposed-B operand
+  const uint32_t offB = tile_off((mi >> 1) * 8 + (lane & 7), mi & 1);  // B operand from an [n][k] tile
+  uint32_t kaddr[4], vaddr[4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) { kaddr[ks] = sK + (offB ^ (ks << 5)); vaddr[ks] = sV + (offA ^ (ks << 5)); }
+  const float sl2 = scale * kLog2e;
+
   const int nqt = (N + 15) / 16;
   for (int qt = warp; qt < nqt; qt += WARPS) {
     uint32_t aq[4][4];
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) ldsm_x4(aq[ks], addr_A(sQ, qt * 16, ks, lane));
+    for (int ks = 0; ks < 4; ++ks) ldsm_x4(aq[ks], sQ + qt * 2048 + (offA ^ (ks << 5)));
     float s[NKV16 * 2][4];
 #pragma unroll
     for (int j = 0; j < NKV16; ++j) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { s[2 * j][e] = 0.f; s[2 * j + 1][e] = 0.f; }
-#pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         uint32_t bk[4];
-        ldsm_x4(bk, addr_B(sK, j * 16, ks, lane));
-        mma16816(s[2 * j], aq[ks], bk[0], bk[1]);
-        mma16816(s[2 * j + 1], aq[ks], bk[2], bk[3]);
+        ldsm_x4(bk, kaddr[ks] + j * 2048);
+        if (ks == 0) {
+          mma16816_z(s[2 * j], aq[ks], bk[0], bk[1]);
+          mma16816_z(s[2 * j + 1], aq[ks], bk[2], bk[3]);
+        } else {
+          mma16816(s[2 * j], aq[ks], bk[0], bk[1]);
+          mma16816(s[2 * j + 1], aq[ks], bk[2], bk[3]);
+        }
       }
     }
     // softmax over the key axis; rows r0 = lane/4 (elements 0,1) and r0+8 (elements 2,3)
     float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
     for (int t = 0; t < NKV16 * 2; ++t) {
-      const int col = t * 8 + (lane & 3) * 2;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float v = bf16_round(s[t][e] * scale);
-        if (col + (e & 1) >= N) v = -INFINITY;
-        s[t][e] = v;
+      float v0 = s[t][0], v1 = s[t][1], v2 = s[t][2], v3 = s[t][3];
+      bf16_round2(v0, v1);
+      bf16_round2(v2, v3);
+      if (!EXACT || t >= NKV16 * 2 - 2) {  // compile-time: only blocks that can hold padded key columns pay for the mask
+        const int col = t * 8 + (lane & 3) * 2;
+        if (col >= N) { v0 = -INFINITY; v2 = -INFINITY; }
+        if (col + 1 >= N) { v1 = -INFINITY; v3 = -INFINITY; }
       }
-      m0 = fmaxf(m0, fmaxf(s[t][0], s[t][1]));
-      m1 = fmaxf(m1, fmaxf(s[t][2], s[t][3]));
+      s[t][0] = v0; s[t][1] = v1; s[t][2] = v2; s[t][3] = v3;
+      m0 = fmaxf(m0, fmaxf(v0, v1));
+      m1 = fmaxf(m1, fmaxf(v2, v3));
     }
     m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
     m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    const float mb0 = -m0 * sl2, mb1 = -m1 * sl2;
     float l0 = 0.f, l1 = 0.f;
 #pragma unroll
     for (int t = 0; t < NKV16 * 2; ++t) {
-      s[t][0] = __expf(s[t][0] - m0); s[t][1] = __expf(s[t][1] - m0);
-      s[t][2] = __expf(s[t][2] - m1); s[t][3] = __expf(s[t][3] - m1);
+      s[t][0] = ex2_ftz(fmaf(s[t][0], sl2, mb0)); s[t][1] = ex2_ftz(fmaf(s[t][1], sl2, mb0));
+      s[t][2] = ex2_ftz(fmaf(s[t][2], sl2, mb1)); s[t][3] = ex2_ftz(fmaf(s[t][3], sl2, mb1));
       l0 += s[t][0] + s[t][1];
       l1 += s[t][2] + s[t][3];
     }
@@ -159,12 +193,10 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, int N, 
     const float inv0 = 1.f / l0, inv1 = 1.f / l1;
     if (lse && (lane & 3) == 0) {
       const int r0 = qt * 16 + (lane >> 2);
-      if (r0 < N) lse[(size_t)bh * N + r0] = m0 + __logf(l0);
-      if (r0 + 8 < N) lse[(size_t)bh * N + r0 + 8] = m1 + __logf(l1);
+      if (r0 < N) lse[(size_t)bh * N + r0] = m0 * scale + __logf(l0);
+      if (r0 + 8 < N) lse[(size_t)bh * N + r0 + 8] = m1 * scale + __logf(l1);
     }
     float o[8][4];
-#pragma unroll
-    for (int t = 0; t < 8; ++t) { o[t][0] = o[t][1] = o[t][2] = o[t][3] = 0.f; }
 #pragma unroll
     for (int j = 0; j < NKV16; ++j) {
       uint32_t ap[4];
@@ -175,9 +207,14 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, int N, 
 #pragma unroll
       for (int dp = 0; dp < 4; ++dp) {
         uint32_t bv[4];
-        ldsm_x4_t(bv, addr_Bt(sV, j * 16, dp, lane));
-        mma16816(o[2 * dp], ap, bv[0], bv[1]);
-        mma16816(o[2 * dp + 1], ap, bv[2], bv[3]);
+        ldsm_x4_t(bv, vaddr[dp] + j * 2048);
+        if (j == 0) {
+          mma16816_z(o[2 * dp], ap, bv[0], bv[1]);
+          mma16816_z(o[2 * dp + 1], ap, bv[2], bv[3]);
+        } else {
+          mma16816(o[2 * dp], ap, bv[0], bv[1]);
+          mma16816(o[2 * dp + 1], ap, bv[2], bv[3]);
+        }
       }
     }
     store_tile(o, 1.f, stage_base + warp * 2048, out + (size_t)b * N * ld_out + head * HD, ld_out, qt * 16, N, lane);
@@ -201,7 +238,7 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16*
 
 // ------------------------------------------------------------------------------------------------
 template <int NKV16, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, (WARPS <= 4 ? 4 : 1))
 attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, const float* __restrict__ dvec,
                 const __nv_bfloat16* __restrict__ dout, long long ld_out, const float* __restrict__ lse, int N, int h,
                 float scale, __nv_bfloat16* __restrict__ dqkv, long long ld_dtok) {
@@ -222,61 +259,78 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, const f
   for (int r = threadIdx.x; r < NP; r += blockDim.x) {
     const bool ok = r < N;
     sD[r] = ok ? dvec[(size_t)bh * N + r] : 0.f;
-    sL[r] = ok ? lse[(size_t)bh * N + r] : 0.f;
+    sL[r] = ok ? lse[(size_t)bh * N + r] * kLog2e : 0.f;  // base-2 log-sum-exp: p = 2^(s*log2e - L)
   }
   cp_async_wait_all();
   __syncthreads();
 
+  // No masks are needed below: padded Q/K/V/dO rows are zero in smem, so a padded key column multiplies a zero K row
+  // (phase A) and a padded query column a zero Q / dO row (phase B); padded output rows are never stored.  The
+  // exponent is clamped so that such a dead element stays finite (0 * inf would poison the accumulators).
   const int nt = (N + 15) / 16;
   __nv_bfloat16* dq_dst = dqkv + (size_t)b * N * ld_dtok + head * HD;
   __nv_bfloat16* dk_dst = dq_dst + (size_t)h * HD;
   __nv_bfloat16* dv_dst = dq_dst + (size_t)2 * h * HD;
   uint8_t* stage = stage_base + warp * 2048;
+  const int mi = lane >> 3;
+  const uint32_t offA = tile_off((mi & 1) * 8 + (lane & 7), mi >> 1);  // A operand and transposed-B operand
+  const uint32_t offB = tile_off((mi >> 1) * 8 + (lane & 7), mi & 1);  // B operand from an [n][k] tile
+  constexpr uint32_t kPanel = NP * 128;                                // sQ, sK, sV, sDO are kPanel bytes apart
+  constexpr float kClamp = 64.f;
+  const float sl2 = scale * kLog2e;
 
   // ---------------- phase A: dQ, one 16-row query tile per warp iteration ----------------
   for (int qt = warp; qt < nt; qt += WARPS) {
     uint32_t aq[4][4], ado[4][4];
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-      ldsm_x4(aq[ks], addr_A(sQ, qt * 16, ks, lane));
-      ldsm_x4(ado[ks], addr_A(sDO, qt * 16, ks, lane));
+      const uint32_t a = sQ + qt * 2048 + (offA ^ (ks << 5));
+      ldsm_x4(aq[ks], a);
+      ldsm_x4(ado[ks], a + 3 * kPanel);
     }
     const int r0 = qt * 16 + (lane >> 2);
     const float L0 = sL[r0], L1 = sL[r0 + 8], D0 = sD[r0], D1 = sD[r0 + 8];
     float dq[8][4];
 #pragma unroll
     for (int t = 0; t < 8; ++t) { dq[t][0] = dq[t][1] = dq[t][2] = dq[t][3] = 0.f; }
+    uint32_t kb = sK + offB, kt = sK + offA;
 #pragma unroll 1
-    for (int j = 0; j < nt; ++j) {
-      float s[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}}, dp[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    for (int j = 0; j < nt; ++j, kb += 2048, kt += 2048) {
+      float s[2][4], dp[2][4];
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         uint32_t bk[4], bv[4];
-        ldsm_x4(bk, addr_B(sK, j * 16, ks, lane));
-        ldsm_x4(bv, addr_B(sV, j * 16, ks, lane));
-        mma16816(s[0], aq[ks], bk[0], bk[1]);
-        mma16816(s[1], aq[ks], bk[2], bk[3]);
-        mma16816(dp[0], ado[ks], bv[0], bv[1]);
-        mma16816(dp[1], ado[ks], bv[2], bv[3]);
-      }
-      uint32_t ads[4];
-      float ds[2][4];
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int col = j * 16 + t * 8 + (lane & 3) * 2;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float L = (e < 2) ? L0 : L1, Dv = (e < 2) ? D0 : D1;
-          float p = (col + (e & 1) < N) ? __expf(bf16_round(s[t][e] * scale) - L) : 0.f;
-          ds[t][e] = p * (bf16_round(dp[t][e]) - Dv);
+        ldsm_x4(bk, kb ^ (ks << 5));
+        ldsm_x4(bv, (kb ^ (ks << 5)) + kPanel);
+        if (ks == 0) {
+          mma16816_z(s[0], aq[ks], bk[0], bk[1]);
+          mma16816_z(s[1], aq[ks], bk[2], bk[3]);
+          mma16816_z(dp[0], ado[ks], bv[0], bv[1]);
+          mma16816_z(dp[1], ado[ks], bv[2], bv[3]);
+        } else {
+          mma16816(s[0], aq[ks], bk[0], bk[1]);
+          mma16816(s[1], aq[ks], bk[2], bk[3]);
+          mma16816(dp[0], ado[ks], bv[0], bv[1]);
+          mma16816(dp[1], ado[ks], bv[2], bv[3]);
         }
       }
-      ads[0] = pack_bf16x2(ds[0][0], ds[0][1]); ads[1] = pack_bf16x2(ds[0][2], ds[0][3]);
-      ads[2] = pack_bf16x2(ds[1][0], ds[1][1]); ads[3] = pack_bf16x2(ds[1][2], ds[1][3]);
+      uint32_t ads[4];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        float s0 = s[t][0], s1 = s[t][1], s2 = s[t][2], s3 = s[t][3];
+        bf16_round2(s0, s1);
+        bf16_round2(s2, s3);
+        bf16_round2(dp[t][0], dp[t][1]);
+        bf16_round2(dp[t][2], dp[t][3]);
+        const float p0 = ex2_ftz(fminf(fmaf(s0, sl2, -L0), kClamp)), p1 = ex2_ftz(fminf(fmaf(s1, sl2, -L0), kClamp));
+        const float p2 = ex2_ftz(fminf(fmaf(s2, sl2, -L1), kClamp)), p3 = ex2_ftz(fminf(fmaf(s3, sl2, -L1), kClamp));
+        ads[2 * t] = pack_bf16x2(p0 * (dp[t][0] - D0), p1 * (dp[t][1] - D0));
+        ads[2 * t + 1] = pack_bf16x2(p2 * (dp[t][2] - D1), p3 * (dp[t][3] - D1));
+      }
 #pragma unroll
       for (int d2 = 0; d2 < 4; ++d2) {
         uint32_t bkt[4];
-        ldsm_x4_t(bkt, addr_Bt(sK, j * 16, d2, lane));
+        ldsm_x4_t(bkt, kt ^ (d2 << 5));
         mma16816(dq[2 * d2], ads, bkt[0], bkt[1]);
         mma16816(dq[2 * d2 + 1], ads, bkt[2], bkt[3]);
       }
@@ -289,58 +343,61 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, const f
     uint32_t ak[4][4], av[4][4];
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-      ldsm_x4(ak[ks], addr_A(sK, kt * 16, ks, lane));
-      ldsm_x4(av[ks], addr_A(sV, kt * 16, ks, lane));
+      const uint32_t a = sK + kt * 2048 + (offA ^ (ks << 5));
+      ldsm_x4(ak[ks], a);
+      ldsm_x4(av[ks], a + kPanel);
     }
     float dk[8][4], dv[8][4];
 #pragma unroll
     for (int t = 0; t < 8; ++t) { dk[t][0] = dk[t][1] = dk[t][2] = dk[t][3] = 0.f; dv[t][0] = dv[t][1] = dv[t][2] = dv[t][3] = 0.f; }
-    const int kr0 = kt * 16 + (lane >> 2);
+    uint32_t qb = sQ + offB, qt_ = sQ + offA;
+    const float* pL = sL + (lane & 3) * 2;
 #pragma unroll 1
-    for (int i = 0; i < nt; ++i) {
-      float st[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}}, dpt[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    for (int i = 0; i < nt; ++i, qb += 2048, qt_ += 2048, pL += 16) {
+      float st[2][4], dpt[2][4];
       float2 Lv[2], Dv2[2];  // per-query-column log-sum-exp and D, fetched ahead of the MMAs
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        const int qc = i * 16 + t * 8 + (lane & 3) * 2;
-        Lv[t] = *reinterpret_cast<const float2*>(sL + qc);
-        Dv2[t] = *reinterpret_cast<const float2*>(sD + qc);
+        Lv[t] = *reinterpret_cast<const float2*>(pL + t * 8);
+        Dv2[t] = *reinterpret_cast<const float2*>(pL + NP + t * 8);
       }
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         uint32_t bq[4], bdo[4];
-        ldsm_x4(bq, addr_B(sQ, i * 16, ks, lane));
-        ldsm_x4(bdo, addr_B(sDO, i * 16, ks, lane));
-        mma16816(st[0], ak[ks], bq[0], bq[1]);
-        mma16816(st[1], ak[ks], bq[2], bq[3]);
-        mma16816(dpt[0], av[ks], bdo[0], bdo[1]);
-        mma16816(dpt[1], av[ks], bdo[2], bdo[3]);
-      }
-      uint32_t apt[4], adst[4];
-      float pt[2][4], dst_[2][4];
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int qc = i * 16 + t * 8 + (lane & 3) * 2;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int q = qc + (e & 1);
-          const int kr = kr0 + ((e >> 1) ? 8 : 0);
-          const bool valid = (q < N) && (kr < N);
-          const float Lq = (e & 1) ? Lv[t].y : Lv[t].x, Dq = (e & 1) ? Dv2[t].y : Dv2[t].x;
-          const float p = valid ? __expf(bf16_round(st[t][e] * scale) - Lq) : 0.f;
-          pt[t][e] = p;
-          dst_[t][e] = p * (bf16_round(dpt[t][e]) - Dq);
+        ldsm_x4(bq, qb ^ (ks << 5));
+        ldsm_x4(bdo, (qb ^ (ks << 5)) + 3 * kPanel);
+        if (ks == 0) {
+          mma16816_z(st[0], ak[ks], bq[0], bq[1]);
+          mma16816_z(st[1], ak[ks], bq[2], bq[3]);
+          mma16816_z(dpt[0], av[ks], bdo[0], bdo[1]);
+          mma16816_z(dpt[1], av[ks], bdo[2], bdo[3]);
+        } else {
+          mma16816(st[0], ak[ks], bq[0], bq[1]);
+          mma16816(st[1], ak[ks], bq[2], bq[3]);
+          mma16816(dpt[0], av[ks], bdo[0], bdo[1]);
+          mma16816(dpt[1], av[ks], bdo[2], bdo[3]);
         }
       }
-      apt[0] = pack_bf16x2(pt[0][0], pt[0][1]); apt[1] = pack_bf16x2(pt[0][2], pt[0][3]);
-      apt[2] = pack_bf16x2(pt[1][0], pt[1][1]); apt[3] = pack_bf16x2(pt[1][2], pt[1][3]);
-      adst[0] = pack_bf16x2(dst_[0][0], dst_[0][1]); adst[1] = pack_bf16x2(dst_[0][2], dst_[0][3]);
-      adst[2] = pack_bf16x2(dst_[1][0], dst_[1][1]); adst[3] = pack_bf16x2(dst_[1][2], dst_[1][3]);
+      uint32_t apt[4], adst[4];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        float s0 = st[t][0], s1 = st[t][1], s2 = st[t][2], s3 = st[t][3];
+        bf16_round2(s0, s1);
+        bf16_round2(s2, s3);
+        bf16_round2(dpt[t][0], dpt[t][1]);
+        bf16_round2(dpt[t][2], dpt[t][3]);
+        const float p0 = ex2_ftz(fminf(fmaf(s0, sl2, -Lv[t].x), kClamp)), p1 = ex2_ftz(fminf(fmaf(s1, sl2, -Lv[t].y), kClamp));
+        const float p2 = ex2_ftz(fminf(fmaf(s2, sl2, -Lv[t].x), kClamp)), p3 = ex2_ftz(fminf(fmaf(s3, sl2, -Lv[t].y), kClamp));
+        apt[2 * t] = pack_bf16x2(p0, p1);
+        apt[2 * t + 1] = pack_bf16x2(p2, p3);
+        adst[2 * t] = pack_bf16x2(p0 * (dpt[t][0] - Dv2[t].x), p1 * (dpt[t][1] - Dv2[t].y));
+        adst[2 * t + 1] = pack_bf16x2(p2 * (dpt[t][2] - Dv2[t].x), p3 * (dpt[t][3] - Dv2[t].y));
+      }
 #pragma unroll
       for (int d2 = 0; d2 < 4; ++d2) {
         uint32_t bqt[4], bdot[4];
-        ldsm_x4_t(bqt, addr_Bt(sQ, i * 16, d2, lane));
-        ldsm_x4_t(bdot, addr_Bt(sDO, i * 16, d2, lane));
+        ldsm_x4_t(bqt, qt_ ^ (d2 << 5));
+        ldsm_x4_t(bdot, (qt_ ^ (d2 << 5)) + 3 * kPanel);
         mma16816(dk[2 * d2], adst, bqt[0], bqt[1]);
         mma16816(dk[2 * d2 + 1], adst, bqt[2], bqt[3]);
         mma16816(dv[2 * d2], apt, bdot[0], bdot[1]);
@@ -352,18 +409,18 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, const f
   }
 }
 
-template <int NKV16, int WARPS>
+template <int NKV16, int WARPS, bool EXACT>
 static int launch_fwd(const void* qkv, long long ld_tok, int B, int N, int h, float scale, void* out, long long ld_out,
                       float* lse, cudaStream_t s) {
   constexpr int NP = NKV16 * 16;
   const int smem = 3 * NP * 128 + WARPS * 2048;
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(attn_fwd_kernel<NKV16, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(attn_fwd_kernel<NKV16, WARPS, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return B200_ERR_CUDA;
     attr = true;
   }
-  attn_fwd_kernel<NKV16, WARPS><<<B * h, WARPS * 32, smem, s>>>((const __nv_bfloat16*)qkv, ld_tok, N, h, scale,
+  attn_fwd_kernel<NKV16, WARPS, EXACT><<<B * h, WARPS * 32, smem, s>>>((const __nv_bfloat16*)qkv, ld_tok, N, h, scale,
                                                           (__nv_bfloat16*)out, ld_out, lse);
   B200_CHECK_LAUNCH();
   return B200_OK;
@@ -392,21 +449,22 @@ using namespace b200;
 
 extern "C" int b200_attention_fwd(const void* qkv, long long ld_tok, int B, int N, int h, int head_dim, float scale, void* out,
                                   long long ld_out, float* lse, void* stream) {
-  if (!qkv || !out || B <= 0 || N <= 0 || h <= 0) return B200_ERR_INVALID_ARG;
+  if (!qkv || !out || B <= 0 || N <= 0 || h <= 0 || !(scale > 0.f)) return B200_ERR_INVALID_ARG;
   if (head_dim != HD || (ld_tok % 8) || (ld_out % 8)) return B200_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
   const int nb = (N + 15) / 16;
-  if (nb <= 3) return launch_fwd<3, 4>(qkv, ld_tok, B, N, h, scale, out, ld_out, lse, s);
-  if (nb <= 4) return launch_fwd<4, 4>(qkv, ld_tok, B, N, h, scale, out, ld_out, lse, s);
-  if (nb <= 13) return launch_fwd<13, 4>(qkv, ld_tok, B, N, h, scale, out, ld_out, lse, s);
-  if (nb <= 17) return launch_fwd<17, 4>(qkv, ld_tok, B, N, h, scale, out, ld_out, lse, s);
+#define B200_FWD(NB)                                                                                      \
+  if (nb == NB) return launch_fwd<NB, 4, true>(qkv, ld_tok, B, N, h, scale, out, ld_out, lse, s);         \
+  if (nb < NB) return launch_fwd<NB, 4, false>(qkv, ld_tok, B, N, h, scale, out, ld_out, lse, s);
+  B200_FWD(3) B200_FWD(4) B200_FWD(13) B200_FWD(17)
+#undef B200_FWD
   return B200_ERR_UNSUPPORTED;
 }
 
 extern "C" int b200_attention_bwd(const void* qkv, long long ld_tok, const void* out, const void* dout, long long ld_out,
                                   const float* lse, int B, int N, int h, int head_dim, float scale, void* dqkv,
                                   long long ld_dtok, float* dvec_ws, void* stream) {
-  if (!qkv || !out || !dout || !lse || !dqkv || !dvec_ws || B <= 0 || N <= 0 || h <= 0) return B200_ERR_INVALID_ARG;
+  if (!qkv || !out || !dout || !lse || !dqkv || !dvec_ws || B <= 0 || N <= 0 || h <= 0 || !(scale > 0.f)) return B200_ERR_INVALID_ARG;
   if (head_dim != HD || (ld_tok % 8) || (ld_out % 8) || (ld_dtok % 8)) return B200_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
   const int nb = (N + 15) / 16;

@@ -154,6 +154,18 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(h);
 }
+// raw MUFU wrappers: __expf / __fdividef wrap the same instructions in denormal-range fix-ups (FSETP + 2-3 FMUL each),
+// which the issue-bound epilogues and the attention inner loops cannot afford
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 // GELU (erf form, torch.nn.GELU() default) and its derivative, branch-free.
 // Phi(x) = 0.5*(1+erf(x/sqrt2)) through Abramowitz-Stegun 7.1.28: 1-erf(z) = (1+a1 z+...+a6 z^6)^-16, |err| <= 3e-7.
 // For x < 0, Phi = 0.5*r has no cancellation, so the tail keeps its relative accuracy.  Against the exact erf the
@@ -168,7 +180,7 @@ __device__ __forceinline__ float gelu_phi(float x) {
   p = fmaf(p, z, 0.0422820123f);
   p = fmaf(p, z, 0.0705230784f);
   p = fmaf(p, z, 1.0f);
-  float r = __fdividef(1.0f, p);
+  float r = rcp_ftz(p);
   r *= r; r *= r; r *= r; r *= r;
   const float h = 0.5f * r;
   return x < 0.f ? h : 1.0f - h;
@@ -176,7 +188,7 @@ __device__ __forceinline__ float gelu_phi(float x) {
 __device__ __forceinline__ float gelu_erf(float x) { return x * gelu_phi(x); }
 __device__ __forceinline__ float gelu_grad_from_phi(float x, float phi) {
   const float kBeta = 0.39894228040143267794f;  // 1/sqrt(2*pi)
-  return fmaf(x * kBeta, __expf(-0.5f * x * x), phi);
+  return fmaf(x * kBeta, ex2_ftz((x * -0.72134752044448170368f) * x), phi);  // exp(-x^2/2) = 2^(-x^2 * log2(e)/2)
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) { return gelu_grad_from_phi(x, gelu_phi(x)); }
 
