@@ -31,6 +31,7 @@ from ..._models.dinov2_vit import DinoVisionTransformer, vit_param_shapes
 from .dinov2_head import DINOv2ProjectionHead, head_param_shapes
 from .dinov2_loss import DINOLoss, IBOTPatchLoss, sinkhorn_colterm
 from .scheduler import cosine_schedule, cosine_warmup_factor, linear_warmup_schedule
+from ... import _lib
 from .utils import MaskingGenerator, create_collated_masks, param_group_settings
 
 
@@ -498,13 +499,17 @@ class DINOv2(nn.Module):
             run()  # eager warm-up at this shape (also the result of this step)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
+            n0 = _lib.LAUNCHES
             with torch.cuda.graph(g, pool=st["pool"], capture_error_mode="thread_local"):  # NCCL watchdog thread may touch CUDA
                 outs = run()
+            n_captured = _lib.LAUNCHES - n0
+            _lib.LAUNCHES = n0  # captured, not executed; every replay executes all of them
             if st["pool"] is None:
                 st["pool"] = g.pool()
-            entry = st["graphs"][cap] = (g, outs)
-        g, outs = entry
+            entry = st["graphs"][cap] = (g, outs, n_captured)
+        g, outs, n_captured = entry
         g.replay()
+        _lib.LAUNCHES += n_captured
         self.dino_loss._launch_reduce(outs["dino_center_sum"], 2 * B)
         self.ibot_loss._launch_reduce(outs["ibot_center_sum"], 1)
         return self._result(outs)

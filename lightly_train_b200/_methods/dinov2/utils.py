@@ -70,7 +70,11 @@ def create_collated_masks(mask_ratio_min: float, mask_ratio_max: float, n_masked
     random.shuffle(masks)
     collated = torch.stack(masks).flatten(1)
     indices = collated.flatten().nonzero().flatten()
-    weight = (1 / collated.sum(-1).clamp(min=1.0)).unsqueeze(-1).expand_as(collated)[collated]
+    # == (1 / collated.sum(-1).clamp(min=1.0)).unsqueeze(-1).expand_as(collated)[collated] of the reference (:149),
+    # in numpy: torch's boolean gather over the stride-0 expansion (and repeat_interleave) spin up the intra-op thread
+    # pool and cost tens of ms per step on the host, more than the whole device step
+    counts = collated.sum(-1).numpy()
+    weight = torch.from_numpy(np.repeat(np.float32(1) / np.maximum(counts, 1).astype(np.float32), counts))
     return {"collated_masks": collated, "mask_indices_list": indices, "masks_weight": weight}
 
 

@@ -89,6 +89,12 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 
+// Pull one 128-byte line into L2 ahead of its (single) use.  Costs no registers, so a warp that keeps only one
+// row / chunk of loads in flight can still cover DRAM latency for the next one.
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // ---------------------------------------------------------------- tcgen05
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -150,9 +156,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// two bit operations (the __bfloat1622float2 intrinsic compiles to two PRMT + two shifts per pair)
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
-  __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&u);
-  return __bfloat1622float2(h);
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
 // raw MUFU wrappers: __expf / __fdividef wrap the same instructions in denormal-range fix-ups (FSETP + 2-3 FMUL each),
 // which the issue-bound epilogues and the attention inner loops cannot afford
@@ -167,25 +173,29 @@ __device__ __forceinline__ float rcp_ftz(float x) {
   return y;
 }
 // GELU (erf form, torch.nn.GELU() default) and its derivative, branch-free.
-// Phi(x) = 0.5*(1+erf(x/sqrt2)) through Abramowitz-Stegun 7.1.28: 1-erf(z) = (1+a1 z+...+a6 z^6)^-16, |err| <= 3e-7.
-// For x < 0, Phi = 0.5*r has no cancellation, so the tail keeps its relative accuracy.  Against the exact erf the
-// bf16-rounded GELU differs by at most 1 bf16 ulp and only for x < -3.4 (|gelu| < 1e-3); 6 FMA + 1 MUFU.RCP + 4 FMUL
-// instead of erff()'s two divergent branches -- the GEMM epilogues that apply it are issue-bound.
-__device__ __forceinline__ float gelu_phi(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  float p = 0.0000430638f;
-  p = fmaf(p, z, 0.0002765672f);
-  p = fmaf(p, z, 0.0001520143f);
-  p = fmaf(p, z, 0.0092705272f);
-  p = fmaf(p, z, 0.0422820123f);
-  p = fmaf(p, z, 0.0705230784f);
+// Tail probability h(x) = 0.5*erfc(|x|/sqrt2) through Abramowitz-Stegun 7.1.28, erfc(z) = (1+a1 z+...+a6 z^6)^-16
+// (|err| <= 3e-7), with the 1/sqrt2 folded into the coefficients so the polynomial runs on |x| directly.
+//   Phi(x)  = x < 0 ? h : 1 - h          (no cancellation in the negative tail)
+//   gelu(x) = max(x, 0) - |x| * h        (== x * Phi(x); two instructions instead of compare + subtract + multiply)
+// Against the exact erf the bf16-rounded GELU differs by at most 1 bf16 ulp and only for x < -3.4 (|gelu| < 1e-3).
+// 6 FFMA + MUFU.RCP + 4 FMUL: the GEMM epilogues that apply it are issue-bound (profiles/r01_gemm_stalls.md).
+__device__ __forceinline__ float gelu_tail(float x) {
+  const float z = fabsf(x);
+  float p = 5.3829750000000024e-06f;
+  p = fmaf(p, z, 4.889063564344405e-05f);
+  p = fmaf(p, z, 3.800357500000001e-05f);
+  p = fmaf(p, z, 0.0032776263241471692f);
+  p = fmaf(p, z, 0.021141006150000002f);
+  p = fmaf(p, z, 0.049867346966790536f);
   p = fmaf(p, z, 1.0f);
   float r = rcp_ftz(p);
   r *= r; r *= r; r *= r; r *= r;
-  const float h = 0.5f * r;
-  return x < 0.f ? h : 1.0f - h;
+  return 0.5f * r;
 }
-__device__ __forceinline__ float gelu_erf(float x) { return x * gelu_phi(x); }
+__device__ __forceinline__ float gelu_from_tail(float x, float h) { return fmaf(-fabsf(x), h, fmaxf(x, 0.f)); }
+__device__ __forceinline__ float phi_from_tail(float x, float h) { return x < 0.f ? h : 1.0f - h; }
+__device__ __forceinline__ float gelu_phi(float x) { return phi_from_tail(x, gelu_tail(x)); }
+__device__ __forceinline__ float gelu_erf(float x) { return gelu_from_tail(x, gelu_tail(x)); }
 __device__ __forceinline__ float gelu_grad_from_phi(float x, float phi) {
   const float kBeta = 0.39894228040143267794f;  // 1/sqrt(2*pi)
   return fmaf(x * kBeta, ex2_ftz((x * -0.72134752044448170368f) * x), phi);  // exp(-x^2/2) = 2^(-x^2 * log2(e)/2)

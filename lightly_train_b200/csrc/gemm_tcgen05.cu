@@ -15,6 +15,7 @@
 // materialising transposes.
 #include <cuda.h>
 #include "common.cuh"
+#include <type_traits>
 #include "../../include/b200dino.h"
 
 namespace b200 {
@@ -113,9 +114,10 @@ struct EpiPtrs {
   long long c_step, c2_step, aux_step;  // bytes per 4-row group
 };
 
-template <int EPI>
-__device__ __forceinline__ void epilogue_vec4(float alpha, float4 acc, char* c, char* c2, float rs, const float4& bias4,
+template <int EPI, bool HAS_C2>
+__device__ __forceinline__ void epilogue_vec4(float alpha, float4 acc, char* c, char* c2_, float rs, const float4& bias4,
                                               const float4& gamma4, const float4& aux4) {
+  char* const c2 = HAS_C2 ? c2_ : nullptr;  // compile-time null: no per-store pointer test
   const float v0 = fmaf(acc.x, alpha, bias4.x), v1 = fmaf(acc.y, alpha, bias4.y), v2 = fmaf(acc.z, alpha, bias4.z),
               v3 = fmaf(acc.w, alpha, bias4.w);
   if constexpr (EPI == B200_EPI_BF16) {
@@ -134,16 +136,19 @@ __device__ __forceinline__ void epilogue_vec4(float alpha, float4 acc, char* c, 
     // like BIAS_GELU, but the second output is gelu'(u) (bf16) instead of u: the backward then only multiplies
     const uint32_t p01 = pack_bf16x2(v0, v1), p23 = pack_bf16x2(v2, v3);
     const float2 u01 = unpack_bf16x2(p01), u23 = unpack_bf16x2(p23);
-    const float f0 = gelu_phi(u01.x), f1 = gelu_phi(u01.y), f2 = gelu_phi(u23.x), f3 = gelu_phi(u23.y);
-    *reinterpret_cast<uint2*>(c) = make_uint2(pack_bf16x2(u01.x * f0, u01.y * f1), pack_bf16x2(u23.x * f2, u23.y * f3));
+    const float h0 = gelu_tail(u01.x), h1 = gelu_tail(u01.y), h2 = gelu_tail(u23.x), h3 = gelu_tail(u23.y);
+    *reinterpret_cast<uint2*>(c) = make_uint2(pack_bf16x2(gelu_from_tail(u01.x, h0), gelu_from_tail(u01.y, h1)),
+                                              pack_bf16x2(gelu_from_tail(u23.x, h2), gelu_from_tail(u23.y, h3)));
     if (c2)
-      *reinterpret_cast<uint2*>(c2) = make_uint2(pack_bf16x2(gelu_grad_from_phi(u01.x, f0), gelu_grad_from_phi(u01.y, f1)),
-                                                 pack_bf16x2(gelu_grad_from_phi(u23.x, f2), gelu_grad_from_phi(u23.y, f3)));
+      *reinterpret_cast<uint2*>(c2) = make_uint2(
+          pack_bf16x2(gelu_grad_from_phi(u01.x, phi_from_tail(u01.x, h0)), gelu_grad_from_phi(u01.y, phi_from_tail(u01.y, h1))),
+          pack_bf16x2(gelu_grad_from_phi(u23.x, phi_from_tail(u23.x, h2)), gelu_grad_from_phi(u23.y, phi_from_tail(u23.y, h3))));
   } else if constexpr (EPI == B200_EPI_MUL_AUX) {
     // C = bf16( bf16(acc) * aux ), aux bf16 (e.g. the gelu'(u) saved by BIAS_GELU_DG)
     const float2 ga = unpack_bf16x2(__float_as_uint(aux4.x)), gc = unpack_bf16x2(__float_as_uint(aux4.y));
-    *reinterpret_cast<uint2*>(c) = make_uint2(pack_bf16x2(bf16_round(v0) * ga.x, bf16_round(v1) * ga.y),
-                                              pack_bf16x2(bf16_round(v2) * gc.x, bf16_round(v3) * gc.y));
+    // (rounding through the packed F2FP: the scalar F2F.BF16 conversion runs on the quarter-rate XU pipe)
+    const float2 r01 = unpack_bf16x2(pack_bf16x2(v0, v1)), r23 = unpack_bf16x2(pack_bf16x2(v2, v3));
+    *reinterpret_cast<uint2*>(c) = make_uint2(pack_bf16x2(r01.x * ga.x, r01.y * ga.y), pack_bf16x2(r23.x * gc.x, r23.y * gc.y));
   } else if constexpr (EPI == B200_EPI_RESIDUAL) {
     // o = bf16(acc + bias); x_out = x_in + gamma * o * rowscale   (fp32 residual stream)
     const uint32_t p01 = pack_bf16x2(v0, v1), p23 = pack_bf16x2(v2, v3);
@@ -155,8 +160,9 @@ __device__ __forceinline__ void epilogue_vec4(float alpha, float4 acc, char* c, 
   } else if constexpr (EPI == B200_EPI_DGELU) {
     // dU = bf16( bf16(acc) * gelu'(u) ), u = aux (bf16 pre-activation saved by the forward)
     const float2 ua = unpack_bf16x2(__float_as_uint(aux4.x)), uc = unpack_bf16x2(__float_as_uint(aux4.y));
-    *reinterpret_cast<uint2*>(c) = make_uint2(pack_bf16x2(bf16_round(v0) * gelu_erf_grad(ua.x), bf16_round(v1) * gelu_erf_grad(ua.y)),
-                                              pack_bf16x2(bf16_round(v2) * gelu_erf_grad(uc.x), bf16_round(v3) * gelu_erf_grad(uc.y)));
+    const float2 r01 = unpack_bf16x2(pack_bf16x2(v0, v1)), r23 = unpack_bf16x2(pack_bf16x2(v2, v3));
+    *reinterpret_cast<uint2*>(c) = make_uint2(pack_bf16x2(r01.x * gelu_erf_grad(ua.x), r01.y * gelu_erf_grad(ua.y)),
+                                              pack_bf16x2(r23.x * gelu_erf_grad(uc.x), r23.y * gelu_erf_grad(uc.y)));
   }
 }
 
@@ -189,8 +195,8 @@ struct EpiSched {
 };
 
 template <int BLOCK_N, int EPI>
-__device__ __noinline__ void epilogue_role(const GemmDev p, const EpiSched sc, const uint32_t tmem_base, uint64_t* tmem_full,
-                                           uint64_t* tmem_empty, const int quarter, const int half, const int lane, float* stg) {
+__device__ __forceinline__ void epilogue_role(const GemmDev& p, const EpiSched& sc, const uint32_t tmem_base, uint64_t* tmem_full,
+                                              uint64_t* tmem_empty, const int quarter, const int half, const int lane, float* stg) {
   constexpr int COLS_PER_WARP = EpiCfg<BLOCK_N>::COLS_PER_WARP;
   constexpr int NC = COLS_PER_WARP / 32;
   constexpr bool HAS_AUX = (EPI == B200_EPI_RESIDUAL || EPI == B200_EPI_DGELU || EPI == B200_EPI_MUL_AUX);
@@ -236,6 +242,22 @@ __device__ __noinline__ void epilogue_role(const GemmDev p, const EpiSched sc, c
     }
     float4 aux_cur[8], aux_nxt[8];
     if constexpr (HAS_AUX) load_aux_chunk<EPI>(aux_nxt, aux_base, aux_step, rows_valid, sub_row, col0 < N);
+    if constexpr (HAS_AUX) {
+      // the NEXT tile's slice of aux (32 rows x COLS_PER_WARP of this warp) -> L2: aux is read exactly once, and with
+      // one chunk per warp in flight the fp32 residual stream was latency-bound (profiles/r01_gemm_stalls.md)
+      const int wn = w + sc.w_step;
+      if (wn < sc.w_end) {
+        const int tn = wn / sc.n_splits;
+        const int m0n = (sc.tiles_n > 0 ? tn / sc.tiles_n : tn % sc.tiles_m) * BLOCK_M + quarter * 32;
+        const int n0n = (sc.tiles_n > 0 ? tn % sc.tiles_n : tn / sc.tiles_m) * BLOCK_N + half * COLS_PER_WARP;
+        constexpr int LINES = COLS_PER_WARP * AUX_ESIZE / 128;  // 128-byte lines per row slice (>= 1)
+#pragma unroll
+        for (int i = 0; i < LINES; ++i) {
+          const int coln = n0n + i * (128 / AUX_ESIZE);
+          if (m0n + lane < M && coln < N) prefetch_l2(AUX + ((size_t)(m0n + lane) * ldaux + coln) * AUX_ESIZE);
+        }
+      }
+    }
 
     mbar_wait(&tmem_full[acc], acc_phase);
     tc_fence_after();
@@ -267,15 +289,26 @@ __device__ __noinline__ void epilogue_role(const GemmDev p, const EpiSched sc, c
         if (c + 1 < NC) load_aux_chunk<EPI>(aux_nxt, aux_base + (c + 1) * 32 * AUX_ESIZE, aux_step, rows_valid, sub_row, col_next < N);
       }
       if (col_ok) {
-        char* cp = c_base + c * 32 * C_ESIZE;
-        char* c2p = c2_base ? c2_base + c * 64 : nullptr;
+        // the 8 row groups of this chunk, specialised at compile time on (second output present, all 32 rows valid):
+        // per-store pointer tests and row predicates cost ~2 instructions per element in the issue-bound epilogues
+        auto rows = [&](auto has_c2, auto full) {
+          constexpr bool HC2 = decltype(has_c2)::value, FULL = decltype(full)::value;
+          char* cp = c_base + c * 32 * C_ESIZE;
+          char* c2p = HC2 ? c2_base + c * 64 : nullptr;
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int r = it * 4 + sub_row;
-          const float4 a4 = lds128(stg_r + it * 512 + ((g4 ^ (r & 7)) << 4));
-          if (r < rows_valid) epilogue_vec4<EPI>(alpha, a4, cp, c2p, (EPI == B200_EPI_RESIDUAL) ? rs[it] : 1.0f, bias4, gamma4, aux_cur[it]);
-          cp += c_step;
-          if (c2p) c2p += c2_step;
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + sub_row;
+            const float4 a4 = lds128(stg_r + it * 512 + ((g4 ^ (r & 7)) << 4));
+            if (FULL || r < rows_valid)
+              epilogue_vec4<EPI, HC2>(alpha, a4, cp, c2p, (EPI == B200_EPI_RESIDUAL) ? rs[it] : 1.0f, bias4, gamma4, aux_cur[it]);
+            cp += c_step;
+            if (HC2) c2p += c2_step;
+          }
+        };
+        if (rows_valid >= 32) {
+          if (c2_base) rows(std::true_type{}, std::true_type{}); else rows(std::false_type{}, std::true_type{});
+        } else {
+          if (c2_base) rows(std::true_type{}, std::false_type{}); else rows(std::false_type{}, std::false_type{});
         }
       }
       __syncwarp();
@@ -287,23 +320,8 @@ __device__ __noinline__ void epilogue_role(const GemmDev p, const EpiSched sc, c
   }
 }
 
-template <int BLOCK_N>
-__device__ __forceinline__ void run_epilogue_role(const GemmDev& p, const EpiSched& sc, uint32_t tmem_base, uint64_t* tmem_full,
-                                                  uint64_t* tmem_empty, int quarter, int half, int lane, float* stg) {
-  switch (p.epi) {  // warp-uniform, once per kernel
-    case B200_EPI_BF16: epilogue_role<BLOCK_N, B200_EPI_BF16>(p, sc, tmem_base, tmem_full, tmem_empty, quarter, half, lane, stg); break;
-    case B200_EPI_F32: epilogue_role<BLOCK_N, B200_EPI_F32>(p, sc, tmem_base, tmem_full, tmem_empty, quarter, half, lane, stg); break;
-    case B200_EPI_F32_ATOMIC: epilogue_role<BLOCK_N, B200_EPI_F32_ATOMIC>(p, sc, tmem_base, tmem_full, tmem_empty, quarter, half, lane, stg); break;
-    case B200_EPI_BIAS_GELU: epilogue_role<BLOCK_N, B200_EPI_BIAS_GELU>(p, sc, tmem_base, tmem_full, tmem_empty, quarter, half, lane, stg); break;
-    case B200_EPI_RESIDUAL: epilogue_role<BLOCK_N, B200_EPI_RESIDUAL>(p, sc, tmem_base, tmem_full, tmem_empty, quarter, half, lane, stg); break;
-    case B200_EPI_BIAS_GELU_DG: epilogue_role<BLOCK_N, B200_EPI_BIAS_GELU_DG>(p, sc, tmem_base, tmem_full, tmem_empty, quarter, half, lane, stg); break;
-    case B200_EPI_MUL_AUX: epilogue_role<BLOCK_N, B200_EPI_MUL_AUX>(p, sc, tmem_base, tmem_full, tmem_empty, quarter, half, lane, stg); break;
-    default: epilogue_role<BLOCK_N, B200_EPI_DGELU>(p, sc, tmem_base, tmem_full, tmem_empty, quarter, half, lane, stg); break;
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
-template <int BLOCK_N>
+template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(EpiCfg<BLOCK_N>::THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmDev p) {
@@ -437,7 +455,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ===================== epilogue warps =====================
     const int ew = warp - 2;
     EpiSched sc{(int)blockIdx.x, total_work, (int)gridDim.x, n_splits, tiles_m, tiles_n};
-    run_epilogue_role<BLOCK_N>(p, sc, tmem_base, tmem_full, tmem_empty, warp & 3, ew >> 2, lane, epi_staging + ew * (32 * 32));
+    epilogue_role<BLOCK_N, EPI>(p, sc, tmem_base, tmem_full, tmem_empty, warp & 3, ew >> 2, lane, epi_staging + ew * (32 * 32));
   }
 
   tc_fence_before();
@@ -469,7 +487,7 @@ struct GemmWsCfg {
   static_assert(STAGES >= 2, "weight-stationary slab leaves no room for the A ring");
 };
 
-template <int BLOCK_N, int KB_MAX>
+template <int BLOCK_N, int KB_MAX, int EPI>
 __global__ void __launch_bounds__(EpiCfg<BLOCK_N>::THREADS, 1)
 gemm_tcgen05_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const GemmDev p) {
@@ -597,7 +615,7 @@ gemm_tcgen05_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     // ===================== epilogue warps =====================
     const int ew = warp - 2;
     EpiSched sc{w0, w1, 1, 1, tiles_m, 0};
-    run_epilogue_role<BLOCK_N>(p, sc, tmem_base, tmem_full, tmem_empty, warp & 3, ew >> 2, lane, epi_staging + ew * (32 * 32));
+    epilogue_role<BLOCK_N, EPI>(p, sc, tmem_base, tmem_full, tmem_empty, warp & 3, ew >> 2, lane, epi_staging + ew * (32 * 32));
   }
   tc_fence_before();
   __syncthreads();
@@ -638,8 +656,8 @@ static int make_tmap(CUtensorMap* tm, const void* base, long long rows, long lon
 
 static int g_num_sms = 0;
 
-template <int BLOCK_N>
-static int launch_gemm(const b200_gemm_args* a, cudaStream_t stream) {
+template <int BLOCK_N, int EPI>
+static int launch_gemm_epi(const b200_gemm_args* a, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
   CUtensorMap tmA, tmB;
   int rc;
@@ -652,7 +670,7 @@ static int launch_gemm(const b200_gemm_args* a, cudaStream_t stream) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              Cfg::SMEM_BYTES) != cudaSuccess)
       return B200_ERR_CUDA;
     attr_set = true;
@@ -681,14 +699,14 @@ static int launch_gemm(const b200_gemm_args* a, cudaStream_t stream) {
   long long work = (long long)tiles * splits;
   int grid = (int)(work < g_num_sms ? work : g_num_sms);
   if (grid < 1) grid = 1;
-  gemm_tcgen05_kernel<BLOCK_N><<<grid, EpiCfg<BLOCK_N>::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  gemm_tcgen05_kernel<BLOCK_N, EPI><<<grid, EpiCfg<BLOCK_N>::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
 
 
-template <int BLOCK_N, int KB_MAX>
-static int launch_gemm_ws(const b200_gemm_args* a, cudaStream_t stream) {
+template <int BLOCK_N, int KB_MAX, int EPI>
+static int launch_gemm_ws_epi(const b200_gemm_args* a, cudaStream_t stream) {
   using Cfg = GemmWsCfg<BLOCK_N, KB_MAX>;
   CUtensorMap tmA, tmB;
   int rc;
@@ -700,7 +718,7 @@ static int launch_gemm_ws(const b200_gemm_args* a, cudaStream_t stream) {
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_tcgen05_ws_kernel<BLOCK_N, KB_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(gemm_tcgen05_ws_kernel<BLOCK_N, KB_MAX, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              Cfg::SMEM_BYTES) != cudaSuccess)
       return B200_ERR_CUDA;
     attr_set = true;
@@ -726,9 +744,36 @@ static int launch_gemm_ws(const b200_gemm_args* a, cudaStream_t stream) {
   // even out the contiguous runs: ceil(tiles/grid) tiles per CTA, drop CTAs that would get nothing
   const long long per = (tiles + grid - 1) / grid;
   grid = (int)((tiles + per - 1) / per);
-  gemm_tcgen05_ws_kernel<BLOCK_N, KB_MAX><<<grid, EpiCfg<BLOCK_N>::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  gemm_tcgen05_ws_kernel<BLOCK_N, KB_MAX, EPI><<<grid, EpiCfg<BLOCK_N>::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
   B200_CHECK_LAUNCH();
   return B200_OK;
+}
+
+// one kernel per (tile width, epilogue): the epilogue is inlined, its parameters stay in the constant bank and the
+// register allocation is the epilogue's own
+#define B200_EPI_SWITCH(CALL)                                              \
+  switch (a->epi) {                                                        \
+    case B200_EPI_BF16: return CALL(B200_EPI_BF16);                        \
+    case B200_EPI_F32: return CALL(B200_EPI_F32);                          \
+    case B200_EPI_F32_ATOMIC: return CALL(B200_EPI_F32_ATOMIC);            \
+    case B200_EPI_BIAS_GELU: return CALL(B200_EPI_BIAS_GELU);              \
+    case B200_EPI_RESIDUAL: return CALL(B200_EPI_RESIDUAL);                \
+    case B200_EPI_DGELU: return CALL(B200_EPI_DGELU);                      \
+    case B200_EPI_BIAS_GELU_DG: return CALL(B200_EPI_BIAS_GELU_DG);        \
+    case B200_EPI_MUL_AUX: return CALL(B200_EPI_MUL_AUX);                  \
+    default: return B200_ERR_INVALID_ARG;                                  \
+  }
+template <int BLOCK_N>
+static int launch_gemm(const b200_gemm_args* a, cudaStream_t stream) {
+#define B200_CALL(E) launch_gemm_epi<BLOCK_N, E>(a, stream)
+  B200_EPI_SWITCH(B200_CALL)
+#undef B200_CALL
+}
+template <int BLOCK_N, int KB_MAX>
+static int launch_gemm_ws(const b200_gemm_args* a, cudaStream_t stream) {
+#define B200_CALL(E) launch_gemm_ws_epi<BLOCK_N, KB_MAX, E>(a, stream)
+  B200_EPI_SWITCH(B200_CALL)
+#undef B200_CALL
 }
 
 }  // namespace b200
@@ -802,6 +847,9 @@ extern "C" int b200_gemm(const b200_gemm_args* a, void* stream) {
       // the GELU / dGELU epilogues are issue-bound: the 12-warp (192-wide) tile measured 10-15 % faster at equal cost
       if ((a->epi == B200_EPI_BIAS_GELU || a->epi == B200_EPI_DGELU || a->epi == B200_EPI_BIAS_GELU_DG) && cand[i] != 192)
         cost += cost / 8;
+      // the fp32 residual epilogue keeps two chunks of the stream in registers: it spills under the 128-register cap
+      // of the 12-warp (192-wide) configuration (ptxas: 164 B), so the 8-warp widths win at equal wave cost
+      if (a->epi == B200_EPI_RESIDUAL && cand[i] == 192) cost += cost / 8;
       if (best < 0 || cost < best) { best = cost; bn = cand[i]; }
     }
   }

@@ -163,6 +163,20 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_bwd_ls_kernel(
 #pragma unroll
   for (int j = 0; j < VMAX; ++j) { aw[j] = ab[j] = ag[j] = ao[j] = make_float4(0, 0, 0, 0); }
   for (int row = blockIdx.x * (ROW_THREADS / 32) + warp; row < T; row += gridDim.x * (ROW_THREADS / 32)) {
+    {  // this warp's next row -> L2 (each row is read exactly once; the loads below are the only ones in flight)
+      const int nrow = row + gridDim.x * (ROW_THREADS / 32);
+      if (nrow < T) {
+        const int b4 = lane * 128, b2 = lane * 128;
+        if (b4 < D * 4) {
+          prefetch_l2(reinterpret_cast<const char*>(x + (size_t)nrow * ldx) + b4);
+          if (accumulate) prefetch_l2(reinterpret_cast<const char*>(dx + (size_t)nrow * lddx) + b4);
+        }
+        if (b2 < D * 2) {
+          prefetch_l2(reinterpret_cast<const char*>(o + (size_t)nrow * ldo) + b2);
+          if (DY_BF16) prefetch_l2(reinterpret_cast<const char*>(reinterpret_cast<const __nv_bfloat16*>(dy) + (size_t)nrow * lddy) + b2);
+        }
+      }
+    }
     const float mu = mean[row], rs = rstd[row];
     const float dps = rowscale ? __ldg(rowscale + row / rows_per_scale) : 1.f;
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ldx);

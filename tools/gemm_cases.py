@@ -47,6 +47,10 @@ def cases():
     ops.gemm(x, wproj, out_res, epi=ops.EPI_RESIDUAL, bias=b1, out2=out_o, aux=res, gamma=gamma)  # proj
     ops.gemm(x, w1, out_h, epi=ops.EPI_BIAS_GELU, bias=bh, out2=out_u)                        # fc1
     ops.gemm(hid, w2, out_res, epi=ops.EPI_RESIDUAL, bias=b1, out2=out_o, aux=res, gamma=gamma)   # fc2
+    if os.environ.get("CASES", "all") == "epi":
+        ops.gemm(x, w1, out_h, epi=ops.EPI_BIAS_GELU_DG, bias=bh, out2=out_u)                 # fc1 student (h, gelu'(u))
+        ops.gemm(x, w2, out_du, b_mn=True, epi=ops.EPI_MUL_AUX, aux=out_u)                    # dU = dH * gelu'(u)
+        return
     ops.gemm(x, w2, out_du, b_mn=True, epi=ops.EPI_DGELU, aux=out_u)                          # dU dgrad
 
 
