@@ -790,7 +790,7 @@ extern "C" int b200_gemm(const b200_gemm_args* a, void* stream) {
   b200_gemm_args tuned;
   if (a->splits == 0 && a->epi == B200_EPI_F32_ATOMIC) {
     // auto split-K (wgrad: few output tiles, very long K): pick (tile width, splits) so that tiles*splits fills whole
-    // waves of the 148 SMs; cost ~ rounds * k-blocks per split * tile width
+    // waves of the 148 SMs; cost ~ rounds * k-blocks per split * operand bytes per k-block
     if (g_num_sms == 0) {
       int dev = 0;
       cudaGetDevice(&dev);
@@ -809,7 +809,9 @@ extern "C" int b200_gemm(const b200_gemm_args* a, void* stream) {
         if (sp < 1) continue;
         if (sp > kbt / 4) sp = kbt / 4 > 0 ? kbt / 4 : 1;
         const int rounds = (tiles * sp + g_num_sms - 1) / g_num_sms;
-        const long long cost = (long long)rounds * ((kbt + sp - 1) / sp + 6) * cand[i];  // +6: per-item prologue/epilogue
+        // per k-block a CTA pulls (BLOCK_M + BLOCK_N) x 128 B through L2: these long-K GEMMs run at the L2->SM
+        // bandwidth (~11 TB/s measured), not at the MMA rate, so the cost is bytes, not BLOCK_N; +6: per-item overhead
+        const long long cost = (long long)rounds * ((kbt + sp - 1) / sp + 6) * (BLOCK_M + cand[i]);
         if (best < 0 || cost < best) { best = cost; best_bn = cand[i]; best_sp = sp; }
       }
     }
@@ -830,8 +832,9 @@ extern "C" int b200_gemm(const b200_gemm_args* a, void* stream) {
   const bool want_ws = a->ws_mode == 1 || (a->ws_mode == 0 && a->splits <= 1 && tiles_m >= 8 && kb_total <= 4);
   int bn = a->block_n;
   if (bn == 0) {
-    // tile-N heuristic: minimise (waves over the SMs) x (MMA time per tile ~ BLOCK_N), i.e. padding and wave
-    // quantisation together; ties go to 192 (12 epilogue warps), then to the wider tile
+    // tile-N heuristic: minimise (waves over the SMs) x (operand bytes a CTA pulls through L2 per k-block, ~ BLOCK_M +
+    // BLOCK_N).  These K<=1536 GEMMs run at the L2->SM bandwidth (~11 TB/s measured: tools/gemm_sweep.py,
+    // profiles/r01_gemm_sweep.log), not at the MMA rate, so wider tiles win unless they add a wave or padding.
     if (g_num_sms == 0) {
       int dev = 0;
       cudaGetDevice(&dev);
@@ -843,13 +846,13 @@ extern "C" int b200_gemm(const b200_gemm_args* a, void* stream) {
     for (int i = 0; i < 3; ++i) {
       if (want_ws && kb_total > 4 && cand[i] == 256) continue;  // a 256 x 384 slab does not fit
       const long long tiles = (long long)tiles_m * ((a->N + cand[i] - 1) / cand[i]) * splits;
-      long long cost = ((tiles + g_num_sms - 1) / g_num_sms) * cand[i] * 8;
-      // the GELU / dGELU epilogues are issue-bound: the 12-warp (192-wide) tile measured 10-15 % faster at equal cost
+      long long cost = ((tiles + g_num_sms - 1) / g_num_sms) * (BLOCK_M + cand[i]) * 8;
+      // the GELU / dGELU epilogues are issue-bound: the 12-warp (192-wide) configuration measured 10-15 % faster
       if ((a->epi == B200_EPI_BIAS_GELU || a->epi == B200_EPI_DGELU || a->epi == B200_EPI_BIAS_GELU_DG) && cand[i] != 192)
-        cost += cost / 8;
-      // the fp32 residual epilogue keeps two chunks of the stream in registers: it spills under the 128-register cap
-      // of the 12-warp (192-wide) configuration (ptxas: 164 B), so the 8-warp widths win at equal wave cost
-      if (a->epi == B200_EPI_RESIDUAL && cand[i] == 192) cost += cost / 8;
+        cost += cost / 4;
+      // the fp32 residual epilogue keeps two chunks of the stream in registers: 128-wide tiles (8 warps, 168 registers,
+      // two chunks per warp) measured 29 / 43.5 us against 35 / 47-49 us for the wider ones (proj / fc2 shapes)
+      if (a->epi == B200_EPI_RESIDUAL && cand[i] != 128) cost += cost / 4;
       if (best < 0 || cost < best) { best = cost; bn = cand[i]; }
     }
   }
