@@ -56,7 +56,8 @@ typedef struct b200_gemm_args {
   int splits;            /* split-K factor (>1 only with B200_EPI_F32_ATOMIC; 0 there = choose automatically) */
   int epi;               /* B200_EPI_*                                                              */
   int block_n;           /* 0 = auto, or 128 / 192 / 256                                            */
-  int ws_mode;           /* 0 = auto, 1 = force weight-stationary schedule (K <= 384), 2 = never     */
+  int ws_mode;           /* schedule: 0 = auto, 1 = force weight-stationary (K <= 384), 2 = force the generic  */
+                         /* single-CTA ring, 3 = force the CTA-pair (cta_group::2, 256-row tile) kernel      */
   float alpha;
   void* C; long long ldc;
   void* C2; long long ldc2;

@@ -79,7 +79,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   return d;
 }
 
-__device__ __forceinline__ uint32_t make_idesc(int n, int a_mn, int b_mn) {
+__device__ __forceinline__ uint32_t make_idesc(int n, int a_mn, int b_mn, int m = BLOCK_M) {
   // cute::UMMA::InstrDescriptor: c_format F32(1)@[4,6), a/b_format BF16(1)@[7,10)/[10,13),
   // a_major@15, b_major@16, N>>3@[17,23), M>>4@[24,29)
   uint32_t d = 0;
@@ -89,7 +89,7 @@ __device__ __forceinline__ uint32_t make_idesc(int n, int a_mn, int b_mn) {
   d |= (uint32_t)(a_mn ? 1 : 0) << 15;
   d |= (uint32_t)(b_mn ? 1 : 0) << 16;
   d |= (uint32_t)(n >> 3) << 17;
-  d |= (uint32_t)(BLOCK_M >> 4) << 24;
+  d |= (uint32_t)(m >> 4) << 24;
   return d;
 }
 
@@ -192,9 +192,10 @@ __device__ __forceinline__ void load_aux_chunk(float4 (&aux4)[8], const char* au
 //    aux reads of chunk c+1 are in flight while chunk c is stored.
 struct EpiSched {
   int w_begin, w_end, w_step, n_splits, tiles_m, tiles_n;  // tiles_n > 0: n-fastest tile order (generic kernel)
+  int m_stride = BLOCK_M, m_off = 0;                       // CTA-pair kernel: 256-row tiles, this CTA's half at m_off
 };
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, bool TWO_SM = false>
 __device__ __forceinline__ void epilogue_role(const GemmDev& p, const EpiSched& sc, const uint32_t tmem_base, uint64_t* tmem_full,
                                               uint64_t* tmem_empty, const int quarter, const int half, const int lane, float* stg) {
   constexpr int COLS_PER_WARP = EpiCfg<BLOCK_N>::COLS_PER_WARP;
@@ -222,7 +223,7 @@ __device__ __forceinline__ void epilogue_role(const GemmDev& p, const EpiSched& 
   uint32_t acc_phase = 0;
   for (int w = sc.w_begin; w < sc.w_end; w += sc.w_step) {
     const int tile = w / sc.n_splits;
-    const int m0 = (sc.tiles_n > 0 ? tile / sc.tiles_n : tile % sc.tiles_m) * BLOCK_M;
+    const int m0 = (sc.tiles_n > 0 ? tile / sc.tiles_n : tile % sc.tiles_m) * sc.m_stride + sc.m_off;
     const int n0 = (sc.tiles_n > 0 ? tile % sc.tiles_n : tile / sc.tiles_m) * BLOCK_N;
     const int row_first = m0 + quarter * 32 + sub_row;
     const int rows_valid = M - (m0 + quarter * 32);  // rows r (0..31) of this warp are valid iff r < rows_valid
@@ -248,7 +249,7 @@ __device__ __forceinline__ void epilogue_role(const GemmDev& p, const EpiSched& 
       const int wn = w + sc.w_step;
       if (wn < sc.w_end) {
         const int tn = wn / sc.n_splits;
-        const int m0n = (sc.tiles_n > 0 ? tn / sc.tiles_n : tn % sc.tiles_m) * BLOCK_M + quarter * 32;
+        const int m0n = (sc.tiles_n > 0 ? tn / sc.tiles_n : tn % sc.tiles_m) * sc.m_stride + sc.m_off + quarter * 32;
         const int n0n = (sc.tiles_n > 0 ? tn % sc.tiles_n : tn / sc.tiles_m) * BLOCK_N + half * COLS_PER_WARP;
         constexpr int LINES = COLS_PER_WARP * AUX_ESIZE / 128;  // 128-byte lines per row slice (>= 1)
 #pragma unroll
@@ -295,14 +296,27 @@ __device__ __forceinline__ void epilogue_role(const GemmDev& p, const EpiSched& 
           constexpr bool HC2 = decltype(has_c2)::value, FULL = decltype(full)::value;
           char* cp = c_base + c * 32 * C_ESIZE;
           char* c2p = HC2 ? c2_base + c * 64 : nullptr;
+          // the transposed accumulators are read back in batches: the ld.shared are volatile (ordered against the
+          // st.shared of the transpose), so reading one row group at a time exposed the full smem latency 8 times per
+          // chunk (short-scoreboard stalls were 40 % of the epilogue's samples in profiles/r01_gemm_stalls.md)
+          constexpr int BATCH = (EPI == B200_EPI_RESIDUAL) ? 4 : 8;
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int r = it * 4 + sub_row;
-            const float4 a4 = lds128(stg_r + it * 512 + ((g4 ^ (r & 7)) << 4));
-            if (FULL || r < rows_valid)
-              epilogue_vec4<EPI, HC2>(alpha, a4, cp, c2p, (EPI == B200_EPI_RESIDUAL) ? rs[it] : 1.0f, bias4, gamma4, aux_cur[it]);
-            cp += c_step;
-            if (HC2) c2p += c2_step;
+          for (int b0 = 0; b0 < 8; b0 += BATCH) {
+            float4 a4[BATCH];
+#pragma unroll
+            for (int i = 0; i < BATCH; ++i) {
+              const int r = (b0 + i) * 4 + sub_row;
+              a4[i] = lds128(stg_r + (b0 + i) * 512 + ((g4 ^ (r & 7)) << 4));
+            }
+#pragma unroll
+            for (int i = 0; i < BATCH; ++i) {
+              const int it = b0 + i;
+              const int r = it * 4 + sub_row;
+              if (FULL || r < rows_valid)
+                epilogue_vec4<EPI, HC2>(alpha, a4[i], cp, c2p, (EPI == B200_EPI_RESIDUAL) ? rs[it] : 1.0f, bias4, gamma4, aux_cur[it]);
+              cp += c_step;
+              if (HC2) c2p += c2_step;
+            }
           }
         };
         if (rows_valid >= 32) {
@@ -315,7 +329,10 @@ __device__ __forceinline__ void epilogue_role(const GemmDev& p, const EpiSched& 
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    if (lane == 0) {
+      if constexpr (TWO_SM) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));  // the leader CTA's barrier
+      else mbar_arrive(&tmem_empty[acc]);
+    }
     if ((acc ^= 1) == 0) acc_phase ^= 1;
   }
 }
@@ -466,6 +483,171 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair variant (cluster of 2, tcgen05 cta_group::2): one 256 x BLOCK_N output tile per pair.  Each CTA stages its
+// own 128 rows of A and HALF of the B tile (BLOCK_N/2 rows); the leader CTA (cluster rank 0) issues M=256 MMAs that read
+// both CTAs' shared memory and write each CTA's 128 accumulator rows into its own TMEM.  Operand bytes pulled through
+// L2 per MAC drop by 1/3 (BLOCK_N = 256: 64 MAC/B against 42.7 for the single-CTA 128 x 256 tile) -- the K <= 1536 GEMMs
+// of this model run at the L2 throughput cap (~6300 B/clk), not at the MMA rate (profiles/r01_gemm_sweep.log).
+//   full[s]       : leader's barrier; the leader arms it for the bytes of BOTH CTAs, both CTAs' TMA complete on it
+//   empty[s]      : one per CTA, released by the leader's tcgen05.commit multicast to both CTAs
+//   tmem_full[a]  : one per CTA (commit multicast); tmem_empty[a]: leader's, counts the epilogue warps of both CTAs
+template <int BLOCK_N>
+struct Gemm2Cfg {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;  // this CTA's half of the B tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int EPI_STAGING_BYTES = EpiCfg<BLOCK_N>::STAGING_BYTES;
+  static constexpr int STAGES_FIT = (232448 - 1024 - 256 - EPI_STAGING_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+  static constexpr int ACC_STRIDE = 256;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGING_BYTES + 1024 + 256;
+};
+
+template <int BLOCK_N, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<BLOCK_N>::THREADS, 1)
+gemm_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const GemmDev p) {
+  using Cfg = Gemm2Cfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* epi_staging = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_STAGING_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  const int tiles_m = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int kb_total = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int kb_per_split = (kb_total + p.splits - 1) / p.splits;
+  const int n_splits = (kb_total + kb_per_split - 1) / kb_per_split;
+  const int total_work = tiles_m * tiles_n * n_splits;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 2 * EpiCfg<BLOCK_N>::WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(tmem_base_slot, Cfg::TMEM_COLS);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barrier inits and TMEM allocations of both CTAs are visible before any remote signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    const int m_off = rank * BLOCK_M, n_off = rank * (BLOCK_N / 2);
+    for (int w = pair; w < total_work; w += n_pairs) {
+      const int split = w % n_splits;
+      const int tile = w / n_splits;
+      const int m0 = (tile / tiles_n) * (2 * BLOCK_M) + m_off;
+      const int n0 = (tile % tiles_n) * BLOCK_N + n_off;
+      const int kb0 = split * kb_per_split;
+      const int kb1 = min(kb_total, kb0 + kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (lane == 0) {
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+          const uint32_t bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          const int k0 = kb * BLOCK_K;
+          if (!p.a_mn) {
+            tma_load_2d_2sm(sa, &tmA, bar, k0, m0);
+          } else {
+#pragma unroll
+            for (int a = 0; a < BLOCK_M / 64; ++a) tma_load_2d_2sm(sa + a * (BLOCK_K * 128), &tmA, bar, m0 + a * 64, k0);
+          }
+          if (!p.b_mn) {
+            tma_load_2d_2sm(sb, &tmB, bar, k0, n0);
+          } else {
+#pragma unroll
+            for (int a = 0; a < BLOCK_N / 128; ++a) tma_load_2d_2sm(sb + a * (BLOCK_K * 128), &tmB, bar, n0 + a * 64, k0);
+          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc(BLOCK_N, p.a_mn, p.b_mn, 2 * BLOCK_M);
+      const uint32_t smem0 = smem_u32(smem);
+      const uint64_t adesc_base = p.a_mn ? make_smem_desc(smem0, BLOCK_K * 128, 1024) : make_smem_desc(smem0, 16, 1024);
+      const uint64_t bdesc_base = p.b_mn ? make_smem_desc(smem0 + Cfg::A_BYTES, BLOCK_K * 128, 1024)
+                                         : make_smem_desc(smem0 + Cfg::A_BYTES, 16, 1024);
+      const uint32_t a_step = p.a_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+      const uint32_t b_step = p.b_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = pair; w < total_work; w += n_pairs) {
+        const int split = w % n_splits;
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb_total, kb0 + kb_per_split);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * Cfg::ACC_STRIDE;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t ad = adesc_base + (uint64_t)((stage * Cfg::STAGE_BYTES) >> 4);
+          const uint64_t bd = bdesc_base + (uint64_t)((stage * Cfg::STAGE_BYTES) >> 4);
+          if (elect_one_sync()) {
+            umma_f16_2sm(tmem_d, ad, bd, idesc, (kb > kb0) ? 1u : 0u);
+            umma_f16_2sm(tmem_d, ad + a_step, bd + b_step, idesc, 1u);
+            umma_f16_2sm(tmem_d, ad + 2 * a_step, bd + 2 * b_step, idesc, 1u);
+            umma_f16_2sm(tmem_d, ad + 3 * a_step, bd + 3 * b_step, idesc, 1u);
+            umma_commit_2sm(&empty_bar[stage], 3);  // frees the slot in both CTAs when the MMAs above retire
+            if (kb == kb1 - 1) umma_commit_2sm(&tmem_full[acc], 3);
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if ((acc ^= 1) == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue warps (both CTAs, own 128 rows) =====================
+    const int ew = warp - 2;
+    EpiSched sc{pair, total_work, n_pairs, n_splits, tiles_m, tiles_n, 2 * BLOCK_M, rank * BLOCK_M};
+    epilogue_role<BLOCK_N, EPI, true>(p, sc, tmem_base, tmem_full, tmem_empty, warp & 3, ew >> 2, lane, epi_staging + ew * (32 * 32));
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // no CTA of the pair leaves (or frees TMEM) while the other may still signal or read it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // Weight-stationary variant for small K (K <= WS_KB_MAX*64, e.g. every D=384 GEMM of the ViT):
@@ -749,6 +931,53 @@ static int launch_gemm_ws_epi(const b200_gemm_args* a, cudaStream_t stream) {
   return B200_OK;
 }
 
+template <int BLOCK_N, int EPI>
+static int launch_gemm_2sm_epi(const b200_gemm_args* a, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BLOCK_N>;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!a->a_mn) rc = make_tmap(&tmA, a->A, a->M, a->K, a->lda, BLOCK_K, BLOCK_M);
+  else rc = make_tmap(&tmA, a->A, a->K, a->M, a->lda, 64, BLOCK_K);
+  if (rc) return rc;
+  if (!a->b_mn) rc = make_tmap(&tmB, a->B, a->N, a->K, a->ldb, BLOCK_K, BLOCK_N / 2);
+  else rc = make_tmap(&tmB, a->B, a->K, a->N, a->ldb, 64, BLOCK_K);
+  if (rc) return rc;
+  if (a->b_mn && (BLOCK_N % 128) != 0) return B200_ERR_UNSUPPORTED;  // the B half must be whole 64-wide MN atoms
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_tcgen05_2sm_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             Cfg::SMEM_BYTES) != cudaSuccess)
+      return B200_ERR_CUDA;
+    attr_set = true;
+  }
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  GemmDev p;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.a_mn = a->a_mn; p.b_mn = a->b_mn;
+  p.splits = a->splits < 1 ? 1 : a->splits;
+  p.epi = a->epi;
+  p.alpha = a->alpha;
+  p.C = a->C; p.ldc = a->ldc;
+  p.C2 = a->C2; p.ldc2 = a->ldc2;
+  p.aux = a->aux; p.ldaux = a->ldaux;
+  p.bias = a->bias; p.gamma = a->gamma;
+  p.rowscale = a->rowscale; p.rows_per_scale = a->rows_per_scale > 0 ? a->rows_per_scale : 1;
+  const int tiles = ((a->M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((a->N + BLOCK_N - 1) / BLOCK_N);
+  const int kb_total = (a->K + BLOCK_K - 1) / BLOCK_K;
+  if (p.splits > kb_total) p.splits = kb_total;
+  const long long work = (long long)tiles * p.splits;
+  const int max_pairs = g_num_sms / 2;
+  int pairs = (int)(work < max_pairs ? work : max_pairs);
+  if (pairs < 1) pairs = 1;
+  gemm_tcgen05_2sm_kernel<BLOCK_N, EPI><<<2 * pairs, EpiCfg<BLOCK_N>::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
 // one kernel per (tile width, epilogue): the epilogue is inlined, its parameters stay in the constant bank and the
 // register allocation is the epilogue's own
 #define B200_EPI_SWITCH(CALL)                                              \
@@ -772,6 +1001,12 @@ static int launch_gemm(const b200_gemm_args* a, cudaStream_t stream) {
 template <int BLOCK_N, int KB_MAX>
 static int launch_gemm_ws(const b200_gemm_args* a, cudaStream_t stream) {
 #define B200_CALL(E) launch_gemm_ws_epi<BLOCK_N, KB_MAX, E>(a, stream)
+  B200_EPI_SWITCH(B200_CALL)
+#undef B200_CALL
+}
+template <int BLOCK_N>
+static int launch_gemm_2sm(const b200_gemm_args* a, cudaStream_t stream) {
+#define B200_CALL(E) launch_gemm_2sm_epi<BLOCK_N, E>(a, stream)
   B200_EPI_SWITCH(B200_CALL)
 #undef B200_CALL
 }
@@ -831,6 +1066,7 @@ extern "C" int b200_gemm(const b200_gemm_args* a, void* stream) {
   // for K = 384 the generic ring has more bytes in flight and is as fast or faster
   const bool want_ws = a->ws_mode == 1 || (a->ws_mode == 0 && a->splits <= 1 && tiles_m >= 8 && kb_total <= 4);
   int bn = a->block_n;
+  bool use_pair = false;
   if (bn == 0) {
     // tile-N heuristic: minimise (waves over the SMs) x (operand bytes a CTA pulls through L2 per k-block, ~ BLOCK_M +
     // BLOCK_N).  These K<=1536 GEMMs run at the L2->SM bandwidth (~11 TB/s measured: tools/gemm_sweep.py,
@@ -854,6 +1090,27 @@ extern "C" int b200_gemm(const b200_gemm_args* a, void* stream) {
       // two chunks per warp) measured 29 / 43.5 us against 35 / 47-49 us for the wider ones (proj / fc2 shapes)
       if (a->epi == B200_EPI_RESIDUAL && cand[i] != 128) cost += cost / 4;
       if (best < 0 || cost < best) { best = cost; bn = cand[i]; }
+    }
+    // CTA-pair kernel (256-row tiles): measured 4 % faster than the single-CTA kernel at equal wave counts and
+    // 10 % faster on large-K GEMMs (8192^3: 1.46 vs 1.33 PFLOP/s), but its waves are counted in pairs -- taken only
+    // when that does not add a round, for the plain epilogues, and for K-major B or whole 64-wide MN atoms per half
+    if (a->ws_mode == 0 && !want_ws && splits == 1 && (a->epi == B200_EPI_BF16 || a->epi == B200_EPI_F32)) {
+      const int pairs = g_num_sms / 2;
+      const int tiles_m2 = (a->M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+      for (int i = 0; i < 3; ++i) {
+        if (a->b_mn && (cand[i] % 128) != 0) continue;
+        const long long tiles2 = (long long)tiles_m2 * ((a->N + cand[i] - 1) / cand[i]);
+        const long long cost2 = ((tiles2 + pairs - 1) / pairs) * (BLOCK_M + cand[i]) * 8 * 19 / 20;
+        if (cost2 < best) { best = cost2; bn = cand[i]; use_pair = true; }
+      }
+    }
+  }
+  if (a->ws_mode == 3 || use_pair) {
+    switch (bn) {
+      case 128: return launch_gemm_2sm<128>(a, s);
+      case 192: return launch_gemm_2sm<192>(a, s);
+      case 256: return launch_gemm_2sm<256>(a, s);
+      default: return B200_ERR_INVALID_ARG;
     }
   }
   if (want_ws) {

@@ -68,37 +68,58 @@ def run(M, N, K, a_mn=False, b_mn=False, epi=EPI_BF16, block_n=0, splits=1, ws_m
     print(f"{'OK ' if ok else 'BAD'} M={M} N={N} K={K} a_mn={int(a_mn)} b_mn={int(b_mn)} epi={epi} bn={block_n} splits={splits} ws={ws_mode} err={err:.4g} scale={scale:.3g}", flush=True)
 
 
-print(lib().b200_version())
-# basic K-major, all tile widths
-for bn in (128, 192, 256):
-    run(256, 256, 64, block_n=bn)
-    run(256, 512, 384, block_n=bn)
-    run(1000, 1152, 384, block_n=bn)   # M tail
-run(128, 384, 64, epi=EPI_F32)
-run(130, 392, 72, epi=EPI_F32)         # M, N, K tails
-run(4403, 2048, 384)
-# majors
-for a_mn in (False, True):
-    for b_mn in (False, True):
-        run(384, 1152, 1000, a_mn=a_mn, b_mn=b_mn, epi=EPI_F32, block_n=192)
-        run(256, 256, 128, a_mn=a_mn, b_mn=b_mn, epi=EPI_F32, block_n=128)
-        run(256, 256, 128, a_mn=a_mn, b_mn=b_mn, epi=EPI_F32, block_n=256)
-# split-K atomic (wgrad-like)
-run(1152, 384, 25216, a_mn=True, b_mn=True, epi=EPI_F32_ATOMIC, splits=16, block_n=192)
-run(384, 1536, 5000, a_mn=True, b_mn=True, epi=EPI_F32_ATOMIC, splits=7)
-# weight-stationary schedule (auto for K<=384 and >= 8 M tiles; forced here on small/odd shapes too)
-for epi in (EPI_BF16, EPI_F32, EPI_BIAS_GELU, EPI_RESIDUAL, EPI_DGELU):
-    run(5000, 1152, 384, epi=epi, ws_mode=1)
-    run(3000, 1536, 384, epi=epi, ws_mode=1, block_n=128)
-run(4403, 4096, 256, ws_mode=1)                      # K=256 -> 256-wide slab
-run(1300, 392, 200, epi=EPI_F32, ws_mode=1)          # tails in M, N, K
-run(2500, 1536, 384, b_mn=True, epi=EPI_DGELU, ws_mode=1)
-run(2504, 384, 384, a_mn=True, b_mn=True, epi=EPI_F32, ws_mode=1)
-run(25216, 1152, 384, ws_mode=0)
-# fused epilogues
-run(1000, 1536, 384, epi=EPI_BIAS_GELU)
-run(1000, 384, 1536, epi=EPI_RESIDUAL)
-run(1000, 1536, 384, epi=EPI_DGELU)
+import os
+MODE = os.environ.get("CHECK", "all")
+if MODE == "all":
+    print(lib().b200_version())
+    # basic K-major, all tile widths
+    for bn in (128, 192, 256):
+        run(256, 256, 64, block_n=bn)
+        run(256, 512, 384, block_n=bn)
+        run(1000, 1152, 384, block_n=bn)   # M tail
+    run(128, 384, 64, epi=EPI_F32)
+    run(130, 392, 72, epi=EPI_F32)         # M, N, K tails
+    run(4403, 2048, 384)
+    # majors
+    for a_mn in (False, True):
+        for b_mn in (False, True):
+            run(384, 1152, 1000, a_mn=a_mn, b_mn=b_mn, epi=EPI_F32, block_n=192)
+            run(256, 256, 128, a_mn=a_mn, b_mn=b_mn, epi=EPI_F32, block_n=128)
+            run(256, 256, 128, a_mn=a_mn, b_mn=b_mn, epi=EPI_F32, block_n=256)
+    # split-K atomic (wgrad-like)
+    run(1152, 384, 25216, a_mn=True, b_mn=True, epi=EPI_F32_ATOMIC, splits=16, block_n=192)
+    run(384, 1536, 5000, a_mn=True, b_mn=True, epi=EPI_F32_ATOMIC, splits=7)
+    # weight-stationary schedule (auto for K<=384 and >= 8 M tiles; forced here on small/odd shapes too)
+    for epi in (EPI_BF16, EPI_F32, EPI_BIAS_GELU, EPI_RESIDUAL, EPI_DGELU):
+        run(5000, 1152, 384, epi=epi, ws_mode=1)
+        run(3000, 1536, 384, epi=epi, ws_mode=1, block_n=128)
+    run(4403, 4096, 256, ws_mode=1)                      # K=256 -> 256-wide slab
+    run(1300, 392, 200, epi=EPI_F32, ws_mode=1)          # tails in M, N, K
+    run(2500, 1536, 384, b_mn=True, epi=EPI_DGELU, ws_mode=1)
+    run(2504, 384, 384, a_mn=True, b_mn=True, epi=EPI_F32, ws_mode=1)
+    run(25216, 1152, 384, ws_mode=0)
+    # fused epilogues
+    run(1000, 1536, 384, epi=EPI_BIAS_GELU)
+    run(1000, 384, 1536, epi=EPI_RESIDUAL)
+    run(1000, 1536, 384, epi=EPI_DGELU)
+elif MODE == "2sm":
+    # CTA-pair kernel (ws_mode=3): 256-row tiles, B split across the pair
+    for bn in (128, 192, 256):
+        run(256, 256, 64, block_n=bn, ws_mode=3)
+        run(512, 512, 384, block_n=bn, ws_mode=3)
+        run(1000, 1152, 384, block_n=bn, ws_mode=3)   # M tail inside the second CTA's half
+        run(1100, 1152, 384, block_n=bn, ws_mode=3)   # M tail inside the first CTA's half (second half fully out of range)
+        run(130, 392, 72, epi=EPI_F32, block_n=bn, ws_mode=3)
+    for a_mn in (False, True):
+        for b_mn in (False, True):
+            run(384, 1152, 1000, a_mn=a_mn, b_mn=b_mn, epi=EPI_F32, block_n=256, ws_mode=3)
+            run(512, 256, 128, a_mn=a_mn, b_mn=b_mn, epi=EPI_F32, block_n=128, ws_mode=3)
+    run(1152, 384, 25216, a_mn=True, b_mn=True, epi=EPI_F32_ATOMIC, splits=16, block_n=128, ws_mode=3)
+    run(384, 1536, 5000, a_mn=True, b_mn=True, epi=EPI_F32_ATOMIC, splits=7, block_n=256, ws_mode=3)
+    for epi in (EPI_BF16, EPI_BIAS_GELU, EPI_RESIDUAL, EPI_DGELU):
+        run(5000, 1536, 384, epi=epi, block_n=192, ws_mode=3)
+        run(3000, 384, 1536, epi=epi, block_n=128, ws_mode=3)
+    run(25216, 1152, 384, block_n=192, ws_mode=3)
 
 
 def bench(M, N, K, a_mn=False, b_mn=False, epi=EPI_BF16, splits=1, block_n=0, iters=20, ws_mode=0):
@@ -129,7 +150,22 @@ def bench(M, N, K, a_mn=False, b_mn=False, epi=EPI_BF16, splits=1, block_n=0, it
     print(f"bench M={M} N={N} K={K} a_mn={int(a_mn)} b_mn={int(b_mn)} epi={epi} splits={splits} bn={block_n} ws={ws_mode}: {ms*1e3:.1f} us  {tf:.0f} TFLOP/s   (torch.matmul {ms_t*1e3:.1f} us, {2.0*M*N*K/ms_t/1e9:.0f} TF)", flush=True)
 
 
-if fails == 0:
+if fails == 0 and MODE == "2sm":
+    T = 25216
+    for bn in (128, 192, 256):
+        bench(T, 1152, 384, block_n=bn, ws_mode=3)
+        bench(T, 1536, 384, block_n=bn, ws_mode=3)
+        bench(T, 384, 1536, b_mn=True, block_n=bn, ws_mode=3) if bn != 192 else None
+        bench(T, 384, 384, epi=EPI_RESIDUAL, block_n=bn, ws_mode=3)
+        bench(T, 384, 1536, epi=EPI_RESIDUAL, block_n=bn, ws_mode=3)
+        bench(T, 1536, 384, epi=EPI_BIAS_GELU, block_n=bn, ws_mode=3)
+    for bn, sp in ((256, 12), (256, 6), (128, 6), (128, 8)):
+        bench(384, 1536, T, a_mn=True, b_mn=True, epi=EPI_F32_ATOMIC, splits=sp, block_n=bn, ws_mode=3)
+        bench(1536, 384, T, a_mn=True, b_mn=True, epi=EPI_F32_ATOMIC, splits=sp, block_n=bn, ws_mode=3)
+    bench(18944, 1152, 384, block_n=192, ws_mode=3)
+    bench(18944, 1152, 384, block_n=192, ws_mode=2)
+    bench(8192, 8192, 8192, block_n=256, ws_mode=3)
+if fails == 0 and MODE == "all":
     for ws in (2, 0):
         bench(25216, 1152, 384, ws_mode=ws)
         bench(25216, 384, 384, ws_mode=ws)
