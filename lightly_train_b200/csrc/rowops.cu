@@ -17,6 +17,24 @@ static constexpr int MAXV = 8;           // float4 chunks per lane -> D <= 1024
 
 // ------------------------------------------------------------------------------------------------
 // LayerNorm forward: x f32 [T,D] -> y (bf16 or f32) ; saves mean, rstd.
+// Per-lane column partials (VMAX float4 per lane, column c = lane + 32 j) -> one [D] vector in shared memory.  The warps
+// of the CTA take turns (plain read-modify-write, a __syncthreads between turns): shared-memory atomicAdd(float) is a
+// compare-and-swap loop on this architecture, and 8 warps hammering the same addresses made the tails of the LayerNorm
+// backward kernels cost more instructions than their row loops (ncu: 63 % of ln_bwd_ls's executed instructions).
+template <int VMAX>
+__device__ __forceinline__ void add_cols(float* sm_vec, const float4 (&a)[VMAX], int nv, int lane) {
+#pragma unroll
+  for (int j = 0; j < VMAX; ++j) {
+    const int c = lane + 32 * j;
+    if (c < nv) {
+      float4* p = reinterpret_cast<float4*>(sm_vec) + c;
+      float4 t = *p;
+      t.x += a[j].x; t.y += a[j].y; t.z += a[j].z; t.w += a[j].w;
+      *p = t;
+    }
+  }
+}
+
 template <bool OUT_BF16, int VMAX>
 __global__ void __launch_bounds__(ROW_THREADS) ln_fwd_kernel(const float* __restrict__ x, long long ldx, int T, int D,
                                                              const float* __restrict__ w, const float* __restrict__ b,
@@ -125,17 +143,10 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_bwd_kernel(const void* __restr
     }
   }
   if (dw) {
-#pragma unroll
-    for (int j = 0; j < VMAX; ++j) {
-      int c = lane + 32 * j;
-      if (c < nv) {
-        atomicAdd(&sm[4 * c + 0], aw[j].x); atomicAdd(&sm[4 * c + 1], aw[j].y);
-        atomicAdd(&sm[4 * c + 2], aw[j].z); atomicAdd(&sm[4 * c + 3], aw[j].w);
-        atomicAdd(&sm[D + 4 * c + 0], ab[j].x); atomicAdd(&sm[D + 4 * c + 1], ab[j].y);
-        atomicAdd(&sm[D + 4 * c + 2], ab[j].z); atomicAdd(&sm[D + 4 * c + 3], ab[j].w);
-      }
+    for (int w = 0; w < ROW_THREADS / 32; ++w) {
+      if (warp == w) { add_cols<VMAX>(sm, aw, nv, lane); add_cols<VMAX>(sm + D, ab, nv, lane); }
+      __syncthreads();
     }
-    __syncthreads();
     for (int i = threadIdx.x; i < D; i += blockDim.x) { atomicAdd(dw + i, sm[i]); atomicAdd(db + i, sm[D + i]); }
   }
 }
@@ -147,7 +158,8 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_bwd_kernel(const void* __restr
 //   dout   = bf16(dx_new * rowscale * gamma)                    (gradient of the NEXT branch output, toward its GEMM)
 //   dgamma += sum dx_new*rowscale*o ; dbias += sum dout ; dw_ln/db_ln += LayerNorm parameter gradients
 // One read of dx less and one launch less than ln_bwd + layerscale_bwd (18 instead of 22 bytes per element).
-template <bool DY_BF16, int VMAX>
+// EXACT: D == 128 * VMAX, i.e. every lane owns VMAX full float4 columns (no per-column bounds tests in the row loop).
+template <bool DY_BF16, int VMAX, bool EXACT>
 __global__ void __launch_bounds__(ROW_THREADS) ln_bwd_ls_kernel(
     const void* __restrict__ dy, long long lddy, const float* __restrict__ x, long long ldx, int T, int D,
     const float* __restrict__ w, const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dx,
@@ -187,7 +199,7 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_bwd_ls_kernel(
 #pragma unroll
     for (int j = 0; j < VMAX; ++j) {
       int c = lane + 32 * j;
-      if (c < nv) {
+      if (EXACT || c < nv) {
         float4 d;
         if (DY_BF16) {
           uint2 p = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(dy) + (size_t)row * lddy)[c];
@@ -213,7 +225,7 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_bwd_ls_kernel(
 #pragma unroll
     for (int j = 0; j < VMAX; ++j) {
       int c = lane + 32 * j;
-      if (c < nv) {
+      if (EXACT || c < nv) {
         float4 nx;
         nx.x = dold[j].x + rs * (g[j].x - s1 - xh[j].x * s2); nx.y = dold[j].y + rs * (g[j].y - s1 - xh[j].y * s2);
         nx.z = dold[j].z + rs * (g[j].z - s1 - xh[j].z * s2); nx.w = dold[j].w + rs * (g[j].w - s1 - xh[j].w * s2);
@@ -222,26 +234,20 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_bwd_ls_kernel(
         const float4 gm = gamma ? __ldg(reinterpret_cast<const float4*>(gamma) + c) : make_float4(1, 1, 1, 1);
         const float2 o0 = unpack_bf16x2(ob[j].x), o1 = unpack_bf16x2(ob[j].y);
         ag[j].x += gs.x * o0.x; ag[j].y += gs.y * o0.y; ag[j].z += gs.z * o1.x; ag[j].w += gs.w * o1.y;
-        const float4 dd = make_float4(bf16_round(gs.x * gm.x), bf16_round(gs.y * gm.y), bf16_round(gs.z * gm.z), bf16_round(gs.w * gm.w));
-        ao[j].x += dd.x; ao[j].y += dd.y; ao[j].z += dd.z; ao[j].w += dd.w;
-        uint2 pk; pk.x = pack_bf16x2(dd.x, dd.y); pk.y = pack_bf16x2(dd.z, dd.w);
+        uint2 pk; pk.x = pack_bf16x2(gs.x * gm.x, gs.y * gm.y); pk.y = pack_bf16x2(gs.z * gm.z, gs.w * gm.w);
+        const float2 d01 = unpack_bf16x2(pk.x), d23 = unpack_bf16x2(pk.y);  // the bf16-rounded values that are stored
+        ao[j].x += d01.x; ao[j].y += d01.y; ao[j].z += d23.x; ao[j].w += d23.y;
         reinterpret_cast<uint2*>(dout + (size_t)row * lddo)[c] = pk;
       }
     }
   }
-#pragma unroll
-  for (int j = 0; j < VMAX; ++j) {
-    int c = lane + 32 * j;
-    if (c < nv) {
-      const float* srcs[4] = {&aw[j].x, &ab[j].x, &ag[j].x, &ao[j].x};
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        atomicAdd(&sm[q * D + 4 * c + 0], srcs[q][0]); atomicAdd(&sm[q * D + 4 * c + 1], srcs[q][1]);
-        atomicAdd(&sm[q * D + 4 * c + 2], srcs[q][2]); atomicAdd(&sm[q * D + 4 * c + 3], srcs[q][3]);
-      }
+  for (int w = 0; w < ROW_THREADS / 32; ++w) {
+    if (warp == w) {
+      add_cols<VMAX>(sm, aw, nv, lane); add_cols<VMAX>(sm + D, ab, nv, lane);
+      add_cols<VMAX>(sm + 2 * D, ag, nv, lane); add_cols<VMAX>(sm + 3 * D, ao, nv, lane);
     }
+    __syncthreads();
   }
-  __syncthreads();
   for (int i = threadIdx.x; i < D; i += blockDim.x) {
     if (dw) { atomicAdd(dw + i, sm[i]); atomicAdd(db + i, sm[D + i]); }
     if (dgamma) atomicAdd(dgamma + i, sm[2 * D + i]);
@@ -402,17 +408,10 @@ __global__ void __launch_bounds__(ROW_THREADS) layerscale_bwd_kernel(const float
       }
     }
   }
-#pragma unroll
-  for (int j = 0; j < VMAX; ++j) {
-    int c = lane + 32 * j;
-    if (c < nv) {
-      atomicAdd(&sm[4 * c + 0], ag[j].x); atomicAdd(&sm[4 * c + 1], ag[j].y);
-      atomicAdd(&sm[4 * c + 2], ag[j].z); atomicAdd(&sm[4 * c + 3], ag[j].w);
-      atomicAdd(&sm[D + 4 * c + 0], ab[j].x); atomicAdd(&sm[D + 4 * c + 1], ab[j].y);
-      atomicAdd(&sm[D + 4 * c + 2], ab[j].z); atomicAdd(&sm[D + 4 * c + 3], ab[j].w);
-    }
+  for (int w = 0; w < ROW_THREADS / 32; ++w) {
+    if (warp == w) { add_cols<VMAX>(sm, ag, nv, lane); add_cols<VMAX>(sm + D, ab, nv, lane); }
+    __syncthreads();
   }
-  __syncthreads();
   for (int i = threadIdx.x; i < D; i += blockDim.x) {
     if (dgamma) atomicAdd(dgamma + i, sm[i]);
     if (dbias) atomicAdd(dbias + i, sm[D + i]);
@@ -648,18 +647,24 @@ extern "C" int b200_layernorm_bwd_ls(const void* dy, long long lddy, int dy_bf16
   const size_t smem = 4 * D * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
   const int rps = rows_per_scale > 0 ? rows_per_scale : 1;
-#define B200_LN_BWD_LS(V)                                                                                                   \
+#define B200_LN_BWD_LS_(V, E)                                                                                               \
   do {                                                                                                                      \
     if (dy_bf16)                                                                                                            \
-      ln_bwd_ls_kernel<true, V><<<grid, ROW_THREADS, smem, st>>>(dy, lddy, x, ldx, T, D, w, mean, rstd, dx, lddx, accumulate, dw, db, \
-                                                                 (const __nv_bfloat16*)o, ldo, gamma, rowscale, rps,       \
-                                                                 (__nv_bfloat16*)dout, lddo, dgamma, dbias);               \
+      ln_bwd_ls_kernel<true, V, E><<<grid, ROW_THREADS, smem, st>>>(dy, lddy, x, ldx, T, D, w, mean, rstd, dx, lddx, accumulate, dw, db, \
+                                                                    (const __nv_bfloat16*)o, ldo, gamma, rowscale, rps,    \
+                                                                    (__nv_bfloat16*)dout, lddo, dgamma, dbias);            \
     else                                                                                                                    \
-      ln_bwd_ls_kernel<false, V><<<grid, ROW_THREADS, smem, st>>>(dy, lddy, x, ldx, T, D, w, mean, rstd, dx, lddx, accumulate, dw, db, \
+      ln_bwd_ls_kernel<false, V, false><<<grid, ROW_THREADS, smem, st>>>(dy, lddy, x, ldx, T, D, w, mean, rstd, dx, lddx, accumulate, dw, db, \
                                                                   (const __nv_bfloat16*)o, ldo, gamma, rowscale, rps,      \
                                                                   (__nv_bfloat16*)dout, lddo, dgamma, dbias);              \
   } while (0)
+#define B200_LN_BWD_LS(V)                                   \
+  do {                                                      \
+    if (D == 128 * V) B200_LN_BWD_LS_(V, true);             \
+    else B200_LN_BWD_LS_(V, false);                         \
+  } while (0)
   if (D <= 384) B200_LN_BWD_LS(3); else if (D <= 768) B200_LN_BWD_LS(6); else B200_LN_BWD_LS(8);
+#undef B200_LN_BWD_LS_
 #undef B200_LN_BWD_LS
   B200_CHECK_LAUNCH();
   return B200_OK;
