@@ -237,6 +237,7 @@ class DINOv2(nn.Module):
         self.weight_decay_start = (self.optimizer_args.weight_decay if a.weight_decay_start == "auto"
                                    else float(a.weight_decay_start))
         self.gradnorm_sq = torch.zeros(1, device=self.device_, dtype=torch.float32)
+        self._side_stream = torch.cuda.Stream(device=self.device_) if self.device_.type == "cuda" else None
 
     # ------------------------------------------------------------------ the step
     def _masks(self, n_crops: int, h: int, w: int):
@@ -420,13 +421,22 @@ class DINOv2(nn.Module):
             ops.scatter_rows(dx_i, mask_idx, dxn_g, Np=hh * ww, N=Ng, off=1 + R, count_dev=m_valid_dev)
         # KoLeo on the pre-head global cls tokens (:377-380): forward value + gradient (+=) into dxn_g
         koleo = torch.zeros(2, device=dev, dtype=f32)
-        ops.koleo(sg.xnorm.view(n_crops, Ng, D)[:, 0], 2, B, koleo, dxn_g.view(n_crops, Ng, D)[:, 0],
-                  gscale=a.koleo_loss_weight)
+        # two CTAs of pure latency (~160 us): forked onto a side stream (a parallel branch of the captured graph) so it
+        # overlaps the local-crop backward; its += into dxn_g is only needed by the global-crop backward below
+        main = torch.cuda.current_stream()
+        side = self._side_stream if sl is not None else None
+        if side is not None:
+            side.wait_stream(main)
+        with torch.cuda.stream(side if side is not None else main):
+            ops.koleo(sg.xnorm.view(n_crops, Ng, D)[:, 0], 2, B, koleo, dxn_g.view(n_crops, Ng, D)[:, 0],
+                      gscale=a.koleo_loss_weight)
         if sl is not None:
             dxn_l = torch.zeros(sl.dims[4], D, device=dev, dtype=f32)
             ops.scatter_rows(dx_d[n_crops:], lcls_rows, dxn_l)
             s_vit._bwd(sl, dxn_l)
             del sl, dxn_l
+        if side is not None:
+            main.wait_stream(side)
         s_vit._bwd(sg, dxn_g)
         out["loss_terms"], out["koleo"] = loss_terms, koleo
         return out
