@@ -221,31 +221,17 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, int N, 
   }
 }
 
-// D[bh, n] = sum_d dO[b,n,h,d] * O[b,n,h,d]  (== sum_j dP_ij P_ij), one warp per token, all heads.
-__global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
-                                                            long long ld_out, int B, int N, int h, float* __restrict__ dvec) {
-  const long long tok = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (tok >= (long long)B * N) return;
-  const int lane = threadIdx.x & 31;
-  const int b = (int)(tok / N), n = (int)(tok % N);
-  for (int head = 0; head < h; ++head) {
-    const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dout + (size_t)tok * ld_out + head * HD + lane * 2));
-    const float2 c = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(o + (size_t)tok * ld_out + head * HD + lane * 2));
-    const float acc = warp_sum(a.x * c.x + a.y * c.y);
-    if (lane == 0) dvec[((size_t)b * h + head) * N + n] = acc;
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 template <int NKV16, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 4 ? 4 : 1))
-attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, const float* __restrict__ dvec,
+attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, const __nv_bfloat16* __restrict__ outp,
                 const __nv_bfloat16* __restrict__ dout, long long ld_out, const float* __restrict__ lse, int N, int h,
                 float scale, __nv_bfloat16* __restrict__ dqkv, long long ld_dtok) {
   constexpr int NP = NKV16 * 16;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sQ = smem_u32(smem), sK = sQ + NP * 128, sV = sK + NP * 128, sDO = sV + NP * 128;
-  uint8_t* stage_base = smem + 4 * NP * 128;
+  const uint32_t sO = sDO + NP * 128;  // forward output panel, only needed for D_i = sum_d dO_id * O_id
+  uint8_t* stage_base = smem + 5 * NP * 128;
   float* sL = reinterpret_cast<float*>(stage_base + WARPS * 2048);
   float* sD = sL + NP;
   const int bh = blockIdx.x, b = bh / h, head = bh % h;
@@ -256,12 +242,30 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, const f
   load_panel(sK, base + (size_t)h * HD, ld_tok, N, NP);
   load_panel(sV, base + (size_t)2 * h * HD, ld_tok, N, NP);
   load_panel(sDO, dob, ld_out, N, NP);
-  for (int r = threadIdx.x; r < NP; r += blockDim.x) {
-    const bool ok = r < N;
-    sD[r] = ok ? dvec[(size_t)bh * N + r] : 0.f;
-    sL[r] = ok ? lse[(size_t)bh * N + r] * kLog2e : 0.f;  // base-2 log-sum-exp: p = 2^(s*log2e - L)
-  }
+  load_panel(sO, outp + (size_t)b * N * ld_out + head * HD, ld_out, N, NP);
+  for (int r = threadIdx.x; r < NP; r += blockDim.x)
+    sL[r] = (r < N) ? lse[(size_t)bh * N + r] * kLog2e : 0.f;  // base-2 log-sum-exp: p = 2^(s*log2e - L)
   cp_async_wait_all();
+  __syncthreads();
+  // D_r = sum_d dO[r,d] * O[r,d] (== sum_j dP_rj P_rj), one thread per row straight from the two smem panels
+  // (replaces a separate prep kernel: 24 launches and a second pass over O / dO per step); padded rows give 0
+  for (int r = threadIdx.x; r < NP; r += blockDim.x) {
+    float acc = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+      const uint32_t off = tile_off(r, ch);
+      uint32_t a[4], c[4];
+      asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(sDO + off));
+      asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]) : "r"(sO + off));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 x = unpack_bf16x2(a[i]), y = unpack_bf16x2(c[i]);
+        acc = fmaf(x.x, y.x, acc);
+        acc = fmaf(x.y, y.y, acc);
+      }
+    }
+    sD[r] = acc;
+  }
   __syncthreads();
 
   // No masks are needed below: padded Q/K/V/dO rows are zero in smem, so a padded key column multiplies a zero K row
@@ -426,17 +430,17 @@ static int launch_fwd(const void* qkv, long long ld_tok, int B, int N, int h, fl
   return B200_OK;
 }
 template <int NKV16, int WARPS>
-static int launch_bwd(const void* qkv, long long ld_tok, const float* dvec, const void* dout, long long ld_out, const float* lse,
+static int launch_bwd(const void* qkv, long long ld_tok, const void* outp, const void* dout, long long ld_out, const float* lse,
                       int B, int N, int h, float scale, void* dqkv, long long ld_dtok, cudaStream_t s) {
   constexpr int NP = NKV16 * 16;
-  const int smem = 4 * NP * 128 + WARPS * 2048 + 2 * NP * 4;
+  const int smem = 5 * NP * 128 + WARPS * 2048 + 2 * NP * 4;
   static bool attr = false;
   if (!attr) {
     if (cudaFuncSetAttribute(attn_bwd_kernel<NKV16, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return B200_ERR_CUDA;
     attr = true;
   }
-  attn_bwd_kernel<NKV16, WARPS><<<B * h, WARPS * 32, smem, s>>>((const __nv_bfloat16*)qkv, ld_tok, dvec,
+  attn_bwd_kernel<NKV16, WARPS><<<B * h, WARPS * 32, smem, s>>>((const __nv_bfloat16*)qkv, ld_tok, (const __nv_bfloat16*)outp,
                                                                  (const __nv_bfloat16*)dout, ld_out, lse, N, h, scale,
                                                           (__nv_bfloat16*)dqkv, ld_dtok);
   B200_CHECK_LAUNCH();
@@ -464,16 +468,15 @@ extern "C" int b200_attention_fwd(const void* qkv, long long ld_tok, int B, int 
 extern "C" int b200_attention_bwd(const void* qkv, long long ld_tok, const void* out, const void* dout, long long ld_out,
                                   const float* lse, int B, int N, int h, int head_dim, float scale, void* dqkv,
                                   long long ld_dtok, float* dvec_ws, void* stream) {
-  if (!qkv || !out || !dout || !lse || !dqkv || !dvec_ws || B <= 0 || N <= 0 || h <= 0 || !(scale > 0.f)) return B200_ERR_INVALID_ARG;
+  if (!qkv || !out || !dout || !lse || !dqkv || B <= 0 || N <= 0 || h <= 0 || !(scale > 0.f)) return B200_ERR_INVALID_ARG;
   if (head_dim != HD || (ld_tok % 8) || (ld_out % 8) || (ld_dtok % 8)) return B200_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
   const int nb = (N + 15) / 16;
   if (nb > 17) return B200_ERR_UNSUPPORTED;
-  attn_bwd_prep_kernel<<<(unsigned)(((long long)B * N + 7) / 8), 256, 0, s>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, ld_out, B, N, h, dvec_ws);
-  B200_CHECK_LAUNCH();
-  if (nb <= 3) return launch_bwd<3, 4>(qkv, ld_tok, dvec_ws, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
-  if (nb <= 4) return launch_bwd<4, 4>(qkv, ld_tok, dvec_ws, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
-  if (nb <= 13) return launch_bwd<13, 13>(qkv, ld_tok, dvec_ws, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
-  if (nb <= 17) return launch_bwd<17, 9>(qkv, ld_tok, dvec_ws, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
+  (void)dvec_ws;  // D_i is computed inside the kernel since v10; the workspace argument is kept for ABI stability
+  if (nb <= 3) return launch_bwd<3, 4>(qkv, ld_tok, out, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
+  if (nb <= 4) return launch_bwd<4, 4>(qkv, ld_tok, out, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
+  if (nb <= 13) return launch_bwd<13, 13>(qkv, ld_tok, out, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
+  if (nb <= 17) return launch_bwd<17, 9>(qkv, ld_tok, out, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
   return B200_ERR_UNSUPPORTED;
 }
