@@ -105,6 +105,7 @@ class DinoVisionTransformer(nn.Module):
             self.dpr = [drop_path_rate] * depth
         else:
             self.dpr = [x.item() for x in torch.linspace(0, drop_path_rate, depth)]  # vision_transformer.py:161-166
+        self._dp_keep: dict = {}
         self.prefix = prefix
         shapes = vit_param_shapes(embed_dim, depth, patch_size, in_chans, self.num_patches, self.hidden_dim,
                                   num_register_tokens, self.layerscale)
@@ -244,10 +245,24 @@ class DinoVisionTransformer(nn.Module):
         xcur = xs.view(T, D)
         if save:
             ctx.cols, ctx.masks_u8, ctx.interp = cols, masks_u8, interp
+        # per-sample DropPath scales of every bernoulli block in four launches (rand, +keep, floor, /keep) instead of
+        # four per block: bernoulli(keep)/keep == floor(u + keep)/keep for u ~ U[0,1)  (drop_path.py:23-27)
+        bern = [i for i in range(self.n_blocks) if 0.0 < self.dpr[i] <= 0.1] if (drop_path and keep_scales is None) else []
+        bern_scales = None
+        if bern:
+            key = str(dev)
+            if key not in self._dp_keep:
+                self._dp_keep[key] = torch.tensor([1.0 - self.dpr[i] for i in bern for _ in range(2)], device=dev,
+                                                  dtype=f32).view(-1, 1)
+            keep2 = self._dp_keep[key]
+            bern_scales = torch.rand(2 * len(bern), Bc, device=dev, dtype=f32).add_(keep2).floor_().div_(keep2)
         for i in range(self.n_blocks):
             rs1 = rs2 = None
             if keep_scales is not None:
                 rs1, rs2 = keep_scales[i][0].contiguous(), keep_scales[i][1].contiguous()
+            elif bern_scales is not None and 0.0 < self.dpr[i] <= 0.1:
+                j = bern.index(i)
+                rs1, rs2 = bern_scales[2 * j], bern_scales[2 * j + 1]
             elif drop_path and self.dpr[i] > 0.1:
                 # drop_add_residual_stochastic_depth (layers/block.py:118-141): the branch runs on a random subset of
                 # b' = max(int(b*(1-r)), 1) samples and is added back with alpha = b/b'.  Same arithmetic as a per-sample
