@@ -238,8 +238,24 @@ class DINOv2(nn.Module):
                                    else float(a.weight_decay_start))
         self.gradnorm_sq = torch.zeros(1, device=self.device_, dtype=torch.float32)
         self._side_stream = torch.cuda.Stream(device=self.device_) if self.device_.type == "cuda" else None
+        self._comm_stream = torch.cuda.Stream(device=self.device_) if self.device_.type == "cuda" else None
+        self._head_ready = torch.cuda.Event() if self.device_.type == "cuda" else None
+        self._head_work = None
+        self._head_off = self.s_arena.offsets["dino_head.mlp.0.weight"][0]  # arena order: backbone.*, then the heads
 
     # ------------------------------------------------------------------ the step
+    def _allreduce_head_grads_async(self) -> None:
+        """Data-parallel runs: start the all-reduce of the projection-head gradients (the arena's tail, ~half of all
+        parameters; final once the head backward has run) on a communication stream, so that it overlaps the backbone
+        backward.  `optimizer_step` reduces the backbone part and waits for this one."""
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        main = torch.cuda.current_stream()
+        self._head_ready.record(main)
+        self._comm_stream.wait_event(self._head_ready)
+        with torch.cuda.stream(self._comm_stream):
+            self._head_work = dist.all_reduce(self.s_arena.grad[self._head_off:], async_op=True)
+
     def _masks(self, n_crops: int, h: int, w: int):
         a = self.method_args
         gen = MaskingGenerator(input_size=(h, w), max_num_patches=int(0.5 * h * w))
@@ -267,7 +283,9 @@ class DINOv2(nn.Module):
         if a.center_method == "softmax":
             self.dino_loss.apply_center_update()
             self.ibot_loss.apply_center_update()
-        out = self._core(gv, lv, collated.to(torch.uint8), mask_idx, masks_weight, 1.0 / teacher_temp, None, None, None)
+        st = self._core_a(gv, lv, collated.to(torch.uint8), mask_idx, masks_weight, 1.0 / teacher_temp, None, None, None)
+        self._allreduce_head_grads_async()
+        out = self._core_b(st)
         if a.center_method == "softmax":
             self.dino_loss._launch_reduce(out["dino_center_sum"], gv.shape[0])
             if mask_idx.shape[0]:
@@ -286,10 +304,12 @@ class DINOv2(nn.Module):
             "train_loss/dino_global_loss": dino_global, "train_loss/dino_local_loss": dino_local,
             "train_loss/ibot_loss": ibot, "train_loss/koleo_loss": koleo_loss})
 
-    def _core(self, gv: Tensor, lv: Optional[Tensor], masks_u8: Tensor, mask_idx: Tensor, masks_weight: Tensor,
-              t_scale: float, t_scale_dev: Optional[Tensor], ibot_rowvec: Optional[Tensor],
-              m_valid_dev: Optional[Tensor]) -> Dict[str, Tensor]:
-        """The device schedule of one step.  Shapes depend only on the arguments' shapes, every per-step scalar is
+    def _core_a(self, gv: Tensor, lv: Optional[Tensor], masks_u8: Tensor, mask_idx: Tensor, masks_weight: Tensor,
+                t_scale: float, t_scale_dev: Optional[Tensor], ibot_rowvec: Optional[Tensor],
+                m_valid_dev: Optional[Tensor]) -> Dict[str, Any]:
+        """First half of the device schedule of one step: teacher, student forward, losses, HEAD backward.  When it
+        returns, the gradients of the projection heads (the tail of the flat arena, half of all parameters) are final,
+        so their all-reduce can overlap `_core_b` (the backbone backward).  Shapes depend only on the arguments' shapes, every per-step scalar is
         either a kernel argument (eager) or read from device memory (`*_dev`), and no host<->device traffic or
         synchronisation happens inside -- so the whole function can be captured into a CUDA graph.
         With padding (graph mode) rows >= *m_valid_dev of mask_idx/masks_weight are inert (weight 0)."""
@@ -361,6 +381,7 @@ class DINOv2(nn.Module):
         # ---------------- student forward (dinov2.py:474-519)
         sg = s_vit._fwd(gv, masks_u8, save=True, drop_path=True)
         sl = None
+        lcls_rows = None
         if lv is not None:
             sl = s_vit._fwd(lv, None, save=True, drop_path=True)
         Rs = n_crops + LB + M
@@ -419,6 +440,20 @@ class DINOv2(nn.Module):
         ops.scatter_rows(dx_d[:n_crops], cls_rows, dxn_g)
         if M:
             ops.scatter_rows(dx_i, mask_idx, dxn_g, Np=hh * ww, N=Ng, off=1 + R, count_dev=m_valid_dev)
+        return dict(out=out, loss_terms=loss_terms, sg=sg, sl=sl, dx_d=dx_d, dxn_g=dxn_g, n_crops=n_crops, B=B, Ng=Ng,
+                    lcls_rows=lcls_rows)
+
+    def _core_b(self, st: Dict[str, Any]) -> Dict[str, Tensor]:
+        """Second half: KoLeo and the backbone backward (local crops, then global crops)."""
+        a = self.method_args
+        dev = self.device_
+        f32 = torch.float32
+        s_vit = self.s_vit
+        D = s_vit.embed_dim
+        # pop: the activation contexts must die with the local names below (the local-crop activations are released
+        # before the global-crop backward runs)
+        out, loss_terms, sg, sl, dx_d, dxn_g = (st.pop(k) for k in ("out", "loss_terms", "sg", "sl", "dx_d", "dxn_g"))
+        n_crops, B, Ng, lcls_rows = st["n_crops"], st["B"], st["Ng"], st["lcls_rows"]
         # KoLeo on the pre-head global cls tokens (:377-380): forward value + gradient (+=) into dxn_g
         koleo = torch.zeros(2, device=dev, dtype=f32)
         # two CTAs of pure latency (~160 us): forked onto a side stream (a parallel branch of the captured graph) so it
@@ -500,25 +535,31 @@ class DINOv2(nn.Module):
         self.dino_loss.apply_center_update()
         self.ibot_loss.apply_center_update()
 
-        def run() -> Dict[str, Tensor]:
-            return self._core(st["gv"], st["lv"], st["masks_u8"], st["idx"][:cap], st["mw"][:cap], 0.0, st["t_scale"],
-                              st["iw"][:cap], st["m_valid"])
+        def run_a() -> Dict[str, Any]:
+            return self._core_a(st["gv"], st["lv"], st["masks_u8"], st["idx"][:cap], st["mw"][:cap], 0.0, st["t_scale"],
+                                st["iw"][:cap], st["m_valid"])
 
         entry = st["graphs"].get(cap)
         if entry is None:
-            run()  # eager warm-up at this shape (also the result of this step)
+            self._core_b(run_a())  # eager warm-up at this shape (no collective: ranks reach new shapes at different steps)
             torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
+            # two graphs sharing one memory pool: [teacher, student fwd, losses, head bwd] and [backbone bwd]; the head
+            # gradients' all-reduce is issued between the two replays and overlaps the second
+            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             n0 = _lib.LAUNCHES
-            with torch.cuda.graph(g, pool=st["pool"], capture_error_mode="thread_local"):  # NCCL watchdog thread may touch CUDA
-                outs = run()
+            with torch.cuda.graph(g1, pool=st["pool"], capture_error_mode="thread_local"):  # NCCL watchdog thread may touch CUDA
+                mid = run_a()
+            if st["pool"] is None:
+                st["pool"] = g1.pool()
+            with torch.cuda.graph(g2, pool=st["pool"], capture_error_mode="thread_local"):
+                outs = self._core_b(mid)
             n_captured = _lib.LAUNCHES - n0
             _lib.LAUNCHES = n0  # captured, not executed; every replay executes all of them
-            if st["pool"] is None:
-                st["pool"] = g.pool()
-            entry = st["graphs"][cap] = (g, outs, n_captured)
-        g, outs, n_captured = entry
-        g.replay()
+            entry = st["graphs"][cap] = (g1, g2, outs, n_captured)
+        g1, g2, outs, n_captured = entry
+        g1.replay()
+        self._allreduce_head_grads_async()
+        g2.replay()
         _lib.LAUNCHES += n_captured
         self.dino_loss._launch_reduce(outs["dino_center_sum"], 2 * B)
         self.ibot_loss._launch_reduce(outs["ibot_center_sum"], 1)
@@ -533,8 +574,13 @@ class DINOv2(nn.Module):
         step = self.trainer.global_step
         max_steps = self.trainer.estimated_stepping_batches
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        if world > 1:
-            dist.all_reduce(self.s_arena.grad)  # DDP gradient all-reduce (sum); mean applied via grad_scale
+        if world > 1:  # DDP gradient all-reduce (sum); mean applied via grad_scale
+            if self._head_work is not None:
+                dist.all_reduce(self.s_arena.grad[:self._head_off])  # backbone part; the head part is already in flight
+                self._head_work.wait()                               # (stream-side wait, the host does not block)
+                self._head_work = None
+            else:
+                dist.all_reduce(self.s_arena.grad)
         ops.fill_f32(self.gradnorm_sq, 0.0)
         ops.sumsq(self.s_arena.grad, self.gradnorm_sq)
         weight_decay = cosine_schedule(step, max_steps, self.weight_decay_start, a.weight_decay_end)
