@@ -81,7 +81,7 @@ int b200_attention_fwd(const void* qkv, long long ld_tok, int B, int N, int h, i
                        void* out, long long ld_out, float* lse, void* stream);
 int b200_attention_bwd(const void* qkv, long long ld_tok, const void* out, const void* dout, long long ld_out,
                        const float* lse, int B, int N, int h, int head_dim, float scale, void* dqkv,
-                       long long ld_dtok, float* dvec_ws /* unused since the D_i pass moved into the kernel; kept for ABI stability (may be NULL) */, void* stream);
+                       long long ld_dtok, float* dqkv_colsum /* optional [3*h*64] f32: += column sums of dqkv (= the qkv bias gradient); NULL to skip */, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Row-wise kernels around the GEMMs.

@@ -352,8 +352,9 @@ class DinoVisionTransformer(nn.Module):
             ops.gemm(do1, self._W(b + "attn.proj.weight"), datt, b_mn=True)
             wgrad(do1, sv["att"], b + "attn.proj.weight")
             dqkv = E(T, 3 * D)
-            ops.attention_bwd(sv["qkv"], sv["att"], datt, sv["lse"], Bc, N, h, dqkv, scale)
-            ops.col_reduce(dqkv, self._G(b + "attn.qkv.bias"))
+            # the qkv bias gradient (column sums of dqkv) is accumulated by the attention backward from its registers
+            ops.attention_bwd(sv["qkv"], sv["att"], datt, sv["lse"], Bc, N, h, dqkv, scale,
+                              colsum=self._G(b + "attn.qkv.bias").view(-1))
             wgrad(dqkv, sv["xn"], b + "attn.qkv.weight")
             dxn = E(T, D)
             ops.gemm(dqkv, self._W(b + "attn.qkv.weight"), dxn, b_mn=True)

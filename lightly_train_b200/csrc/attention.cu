@@ -221,12 +221,34 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, int N, 
   }
 }
 
+// Column sums of one 16 x 64 accumulator tile (mma C layout) into this warp's 64-float slot: the bias gradient of the
+// qkv projection is the column sum of dqkv, taken here from registers instead of a second pass over dqkv in HBM.
+// Values are rounded to bf16 first (the reference sums the bf16 dqkv tensor); rows flagged invalid are skipped.
+__device__ __forceinline__ void colsum_tile(const float (&o)[8][4], float mul, bool v0, bool v1, float* slot, int lane) {
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    float a0 = o[t][0] * mul, a1 = o[t][1] * mul, b0 = o[t][2] * mul, b1 = o[t][3] * mul;
+    bf16_round2(a0, a1);
+    bf16_round2(b0, b1);
+    float s0 = (v0 ? a0 : 0.f) + (v1 ? b0 : 0.f), s1 = (v0 ? a1 : 0.f) + (v1 ? b1 : 0.f);
+#pragma unroll
+    for (int off = 4; off < 32; off <<= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, off);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+    }
+    if (lane < 4) {
+      slot[t * 8 + lane * 2] += s0;
+      slot[t * 8 + lane * 2 + 1] += s1;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 template <int NKV16, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 4 ? 4 : 1))
 attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, const __nv_bfloat16* __restrict__ outp,
                 const __nv_bfloat16* __restrict__ dout, long long ld_out, const float* __restrict__ lse, int N, int h,
-                float scale, __nv_bfloat16* __restrict__ dqkv, long long ld_dtok) {
+                float scale, __nv_bfloat16* __restrict__ dqkv, long long ld_dtok, float* __restrict__ colsum) {
   constexpr int NP = NKV16 * 16;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sQ = smem_u32(smem), sK = sQ + NP * 128, sV = sK + NP * 128, sDO = sV + NP * 128;
@@ -234,6 +256,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, const _
   uint8_t* stage_base = smem + 5 * NP * 128;
   float* sL = reinterpret_cast<float*>(stage_base + WARPS * 2048);
   float* sD = sL + NP;
+  float* sC = sD + NP;  // [WARPS][3][64] per-warp column sums of dq | dk | dv
   const int bh = blockIdx.x, b = bh / h, head = bh % h;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const __nv_bfloat16* base = qkv + (size_t)b * N * ld_tok + head * HD;
@@ -245,6 +268,8 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, const _
   load_panel(sO, outp + (size_t)b * N * ld_out + head * HD, ld_out, N, NP);
   for (int r = threadIdx.x; r < NP; r += blockDim.x)
     sL[r] = (r < N) ? lse[(size_t)bh * N + r] * kLog2e : 0.f;  // base-2 log-sum-exp: p = 2^(s*log2e - L)
+  if (colsum)
+    for (int i = threadIdx.x; i < WARPS * 192; i += blockDim.x) sC[i] = 0.f;
   cp_async_wait_all();
   __syncthreads();
   // D_r = sum_d dO[r,d] * O[r,d] (== sum_j dP_rj P_rj), one thread per row straight from the two smem panels
@@ -339,6 +364,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, const _
         mma16816(dq[2 * d2 + 1], ads, bkt[2], bkt[3]);
       }
     }
+    if (colsum) colsum_tile(dq, scale, qt * 16 + (lane >> 2) < N, qt * 16 + (lane >> 2) + 8 < N, sC + warp * 192, lane);
     store_tile(dq, scale, stage, dq_dst, ld_dtok, qt * 16, N, lane);
   }
 
@@ -354,6 +380,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, const _
     float dk[8][4], dv[8][4];
 #pragma unroll
     for (int t = 0; t < 8; ++t) { dk[t][0] = dk[t][1] = dk[t][2] = dk[t][3] = 0.f; dv[t][0] = dv[t][1] = dv[t][2] = dv[t][3] = 0.f; }
+    const int kr0 = kt * 16 + (lane >> 2);  // this lane's key rows: kr0 (elements 0,1) and kr0 + 8 (elements 2,3)
     uint32_t qb = sQ + offB, qt_ = sQ + offA;
     const float* pL = sL + (lane & 3) * 2;
 #pragma unroll 1
@@ -408,8 +435,21 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, const _
         mma16816(dv[2 * d2 + 1], apt, bdot[2], bdot[3]);
       }
     }
+    if (colsum) {  // padded key rows hold garbage (their scores are exp(-L), not 0): masked by the row flags
+      colsum_tile(dk, scale, kr0 < N, kr0 + 8 < N, sC + warp * 192 + 64, lane);
+      colsum_tile(dv, 1.f, kr0 < N, kr0 + 8 < N, sC + warp * 192 + 128, lane);
+    }
     store_tile(dk, scale, stage, dk_dst, ld_dtok, kt * 16, N, lane);
     store_tile(dv, 1.f, stage, dv_dst, ld_dtok, kt * 16, N, lane);
+  }
+  if (colsum) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 192; i += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) t += sC[w * 192 + i];
+      atomicAdd(colsum + (size_t)(i >> 6) * h * HD + head * HD + (i & 63), t);
+    }
   }
 }
 
@@ -431,9 +471,9 @@ static int launch_fwd(const void* qkv, long long ld_tok, int B, int N, int h, fl
 }
 template <int NKV16, int WARPS>
 static int launch_bwd(const void* qkv, long long ld_tok, const void* outp, const void* dout, long long ld_out, const float* lse,
-                      int B, int N, int h, float scale, void* dqkv, long long ld_dtok, cudaStream_t s) {
+                      int B, int N, int h, float scale, void* dqkv, long long ld_dtok, float* colsum, cudaStream_t s) {
   constexpr int NP = NKV16 * 16;
-  const int smem = 5 * NP * 128 + WARPS * 2048 + 2 * NP * 4;
+  const int smem = 5 * NP * 128 + WARPS * 2048 + 2 * NP * 4 + WARPS * 192 * 4;
   static bool attr = false;
   if (!attr) {
     if (cudaFuncSetAttribute(attn_bwd_kernel<NKV16, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
@@ -442,7 +482,7 @@ static int launch_bwd(const void* qkv, long long ld_tok, const void* outp, const
   }
   attn_bwd_kernel<NKV16, WARPS><<<B * h, WARPS * 32, smem, s>>>((const __nv_bfloat16*)qkv, ld_tok, (const __nv_bfloat16*)outp,
                                                                  (const __nv_bfloat16*)dout, ld_out, lse, N, h, scale,
-                                                          (__nv_bfloat16*)dqkv, ld_dtok);
+                                                          (__nv_bfloat16*)dqkv, ld_dtok, colsum);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -467,16 +507,15 @@ extern "C" int b200_attention_fwd(const void* qkv, long long ld_tok, int B, int 
 
 extern "C" int b200_attention_bwd(const void* qkv, long long ld_tok, const void* out, const void* dout, long long ld_out,
                                   const float* lse, int B, int N, int h, int head_dim, float scale, void* dqkv,
-                                  long long ld_dtok, float* dvec_ws, void* stream) {
+                                  long long ld_dtok, float* dqkv_colsum, void* stream) {
   if (!qkv || !out || !dout || !lse || !dqkv || B <= 0 || N <= 0 || h <= 0 || !(scale > 0.f)) return B200_ERR_INVALID_ARG;
   if (head_dim != HD || (ld_tok % 8) || (ld_out % 8) || (ld_dtok % 8)) return B200_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
   const int nb = (N + 15) / 16;
   if (nb > 17) return B200_ERR_UNSUPPORTED;
-  (void)dvec_ws;  // D_i is computed inside the kernel since v10; the workspace argument is kept for ABI stability
-  if (nb <= 3) return launch_bwd<3, 4>(qkv, ld_tok, out, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
-  if (nb <= 4) return launch_bwd<4, 4>(qkv, ld_tok, out, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
-  if (nb <= 13) return launch_bwd<13, 13>(qkv, ld_tok, out, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
-  if (nb <= 17) return launch_bwd<17, 9>(qkv, ld_tok, out, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, s);
+  if (nb <= 3) return launch_bwd<3, 4>(qkv, ld_tok, out, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, dqkv_colsum, s);
+  if (nb <= 4) return launch_bwd<4, 4>(qkv, ld_tok, out, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, dqkv_colsum, s);
+  if (nb <= 13) return launch_bwd<13, 13>(qkv, ld_tok, out, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, dqkv_colsum, s);
+  if (nb <= 17) return launch_bwd<17, 9>(qkv, ld_tok, out, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, dqkv_colsum, s);
   return B200_ERR_UNSUPPORTED;
 }

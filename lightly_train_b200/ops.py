@@ -105,12 +105,12 @@ def attention_fwd(qkv: torch.Tensor, B: int, N: int, h: int, out: torch.Tensor, 
                                   _ptr(lse), _stream()), "b200_attention_fwd")
 
 
-def attention_bwd(qkv, out, dout, lse, B: int, N: int, h: int, dqkv, scale: float) -> None:
+def attention_bwd(qkv, out, dout, lse, B: int, N: int, h: int, dqkv, scale: float, colsum=None) -> None:
+    """colsum (optional f32 [3*h*64]): += column sums of dqkv, i.e. the gradient of the qkv projection's bias."""
     _req_cuda(qkv, out, dout, lse, dqkv)
     assert out.stride(0) == dout.stride(0)
-    ws = torch.empty(B * h * N, device=qkv.device, dtype=torch.float32)
     check(_L().b200_attention_bwd(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), dout.data_ptr(), dout.stride(0),
-                                  lse.data_ptr(), B, N, h, 64, scale, dqkv.data_ptr(), dqkv.stride(0), ws.data_ptr(),
+                                  lse.data_ptr(), B, N, h, 64, scale, dqkv.data_ptr(), dqkv.stride(0), _ptr(colsum),
                                   _stream()), "b200_attention_bwd")
 
 

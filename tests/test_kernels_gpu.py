@@ -133,6 +133,13 @@ def test_attention_fwd_bwd(B, N, h):
     assert err < 0.05 * max(1.0, want.abs().max().item()), err
     rel = (dqkv.float() - want).norm() / want.norm()
     assert rel < 2e-2, rel
+    # fused qkv-bias gradient: += column sums of the (bf16) dqkv the kernel wrote, padded key rows excluded
+    cs = torch.ones(3 * D, device=dev)
+    dqkv2 = torch.empty_like(qkv)
+    ops.attention_bwd(qkv, out, do, lse, B, N, h, dqkv2, 0.125, colsum=cs)
+    assert torch.equal(dqkv2, dqkv)
+    ref = dqkv.float().sum(0) + 1
+    torch.testing.assert_close(cs, ref, rtol=1e-4, atol=1e-3 * max(1.0, float(ref.abs().max())))
 
 
 @pytest.mark.parametrize("T,D", [(1000, 384), (77, 128), (300, 1024), (64, 192)])
