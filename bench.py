@@ -146,10 +146,14 @@ def run_reference_arm(args) -> None:
     sec = cpu_reference_step_time(batch, args.steps, args.warmup, threads)
     value = batch / sec
     line = {
-        "impl": "reference", "metric": "images/sec ViT-S/16 DINOv2 training step (2g+8l crops)", "value": value,
+        "impl": "reference", "metric": "images/sec ViT-S/16 DINOv2 training step (2g+8l crops, bs64/GPU)", "value": value,
         "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": "ViT-S/16 DINOv2 step, 2x224^2 + 8x96^2 crops, K=65536 heads, bounded sample bs=4 on host cores"},
+        "config": {"workload": "cfg2: ViT-S/16 DINOv2, 2x224^2 + 8x96^2 crops, bs=64/GPU, K=65536 shared DINO/iBOT head, "
+                               "softmax centering, drop_path 0.1, full step incl. clip+AdamW+EMA",
+                   "global_batch": 64 * args.gpus, "parallelism": f"dp{args.gpus}",
+                   "sample": "each timed step is a bounded sample of that workload: %d images (of 64) through the same "
+                             "step on the host cores; images/s is batch-size independent on the CPU" % batch},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
                          "sample": f"full step at bs={batch} (reference algorithm restated in oracle/, torch CPU fp32)"},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
