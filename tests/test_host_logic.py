@@ -77,3 +77,31 @@ def test_pos_embed_operator_matches_interpolate(M, w0, off, aa):
     W = torch.from_numpy(pos_embed_operator(M, w0, w0, off, aa))
     y2 = (W @ x.reshape(5, M * M).t()).t().reshape(1, 5, w0, w0)
     torch.testing.assert_close(y2, y, rtol=1e-4, atol=1e-5)
+
+
+def _tiny_method(separate_ibot: bool = False):
+    from lightly_train_b200._methods.dinov2.dinov2 import DINOv2, DINOv2AdamWViTArgs, DINOv2Args
+    margs = DINOv2Args(hidden_dim=64, dino_bottleneck_dim=32, output_dim=128, ibot_separate_head=separate_ibot)
+    mk = dict(img_size=32, patch_size=16, embed_dim=64, depth=2, num_heads=1, init_values=1e-5, drop_path_rate=0.1)
+    return DINOv2(margs, DINOv2AdamWViTArgs(), mk, global_batch_size=8, max_steps=10, device="cpu")
+
+
+@pytest.mark.parametrize("separate_ibot", [False, True])
+def test_gradient_arena_splits_into_backbone_and_head_parts(separate_ibot):
+    """The data-parallel all-reduce goes out in two parts (heads early, backbone after the backward): the split offset
+    must separate exactly the backbone parameters from the head parameters, on a chunk boundary."""
+    from lightly_train_b200._arena import CHUNK
+    m = _tiny_method(separate_ibot)
+    off = m._head_off
+    assert 0 < off < m.s_arena.total and off % CHUNK == 0
+    for name, (o, n) in m.s_arena.offsets.items():
+        assert (o >= off) == name.startswith(("dino_head.", "ibot_head.")), name
+        assert o + n <= off or o >= off  # no parameter straddles the split
+
+
+def test_product_path_fails_loudly_without_a_gpu():
+    """No CPU / oracle fallback behind the public step: without CUDA the call raises instead of computing."""
+    m = _tiny_method()
+    views = [torch.randn(2, 3, 32, 32) for _ in range(2)]
+    with pytest.raises((RuntimeError, AssertionError)):
+        m.train_step({"views": views})
