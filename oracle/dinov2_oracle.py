@@ -50,6 +50,7 @@ class ViTConfig:
     interpolate_offset: float = 0.1
     interpolate_antialias: bool = False
     ln_eps: float = 1e-6
+    ffn_layer: str = "mlp"  # "mlp" | "swiglu" / "swiglufused" (vision_transformer.py:179-184)
 
     @property
     def num_patches(self) -> int:
@@ -57,7 +58,10 @@ class ViTConfig:
 
     @property
     def hidden_dim(self) -> int:
-        return int(self.embed_dim * self.mlp_ratio)
+        h = int(self.embed_dim * self.mlp_ratio)
+        if self.ffn_layer in ("swiglu", "swiglufused"):
+            h = (int(h * 2 / 3) + 7) // 8 * 8  # SwiGLUFFNFused, layers/swiglu_ffn.py:60-63
+        return h
 
 
 @dataclass
@@ -172,7 +176,13 @@ def attention(sd: Dict[str, Tensor], pre: str, cfg: ViTConfig, x: Tensor, autoca
 
 
 def mlp(sd: Dict[str, Tensor], pre: str, x: Tensor, autocast: bool) -> Tensor:
-    """layers/mlp.py:36-42."""
+    """layers/mlp.py:36-42, or SwiGLUFFN.forward (layers/swiglu_ffn.py:31-35) when the block carries w12/w3."""
+    if pre + "w12.weight" in sd:
+        x12 = linear(x, sd[pre + "w12.weight"], sd[pre + "w12.bias"], autocast)
+        x1, x2 = x12.chunk(2, dim=-1)
+        a = F.silu(x1)
+        hidden = _r(_r(a) * x2) if autocast else a * x2  # bf16 silu output, bf16 product under autocast
+        return linear(hidden, sd[pre + "w3.weight"], sd[pre + "w3.bias"], autocast)
     u = linear(x, sd[pre + "fc1.weight"], sd[pre + "fc1.bias"], autocast)
     return linear(gelu(u, autocast), sd[pre + "fc2.weight"], sd[pre + "fc2.bias"], autocast)
 

@@ -16,6 +16,8 @@ from oracle import dinov2_oracle as O
 VIT_TINY = O.ViTConfig(embed_dim=128, depth=2, num_heads=2, patch_size=16, img_size=224, init_values=1e-5)
 VIT_TINY_REG = O.ViTConfig(embed_dim=128, depth=2, num_heads=2, patch_size=16, img_size=224, init_values=1e-5,
                            num_register_tokens=4, interpolate_offset=0.0, interpolate_antialias=True)
+VIT_TINY_SWIGLU = O.ViTConfig(embed_dim=128, depth=2, num_heads=2, patch_size=16, img_size=224, init_values=1e-5,
+                              num_register_tokens=4, ffn_layer="swiglu")  # cfg3's zoo default FFN (hidden 344)
 HEAD_TINY = O.HeadConfig(in_dim=128, hidden_dim=256, bottleneck_dim=64, out_dim=512)
 
 
@@ -35,8 +37,14 @@ def vit_param_shapes(cfg: O.ViTConfig) -> Dict[str, Tuple[int, ...]]:
             b + "attn.proj.weight": (D, D), b + "attn.proj.bias": (D,),
             b + "ls1.gamma": (D,),
             b + "norm2.weight": (D,), b + "norm2.bias": (D,),
-            b + "mlp.fc1.weight": (H, D), b + "mlp.fc1.bias": (H,),
-            b + "mlp.fc2.weight": (D, H), b + "mlp.fc2.bias": (D,),
+        })
+        if cfg.ffn_layer == "mlp":
+            shapes.update({b + "mlp.fc1.weight": (H, D), b + "mlp.fc1.bias": (H,),
+                           b + "mlp.fc2.weight": (D, H), b + "mlp.fc2.bias": (D,)})
+        else:
+            shapes.update({b + "mlp.w12.weight": (2 * H, D), b + "mlp.w12.bias": (2 * H,),
+                           b + "mlp.w3.weight": (D, H), b + "mlp.w3.bias": (D,)})
+        shapes.update({
             b + "ls2.gamma": (D,),
         })
     shapes.update({"norm.weight": (D,), "norm.bias": (D,)})
@@ -92,6 +100,11 @@ def vit_case_inputs() -> Tuple[Tensor, Tensor, Tensor]:
     masks = torch.rand(2, 196, generator=g) < 0.3
     masks[1] = False
     return xg, xl, masks
+
+
+def vit_swiglu_cotangents() -> Tuple[Tensor, Tensor]:
+    g = torch.Generator().manual_seed(104)
+    return torch.randn(2, 196, VIT_TINY_SWIGLU.embed_dim, generator=g), torch.randn(2, VIT_TINY_SWIGLU.embed_dim, generator=g)
 
 
 def head_case_input() -> Tensor:

@@ -141,3 +141,24 @@ def test_training_step_matches_reference(golden_dir, center_method, separate):
         B2 = views[0].shape[0] * 2
         _close(O.center_ema(st["centers"]["dino"], out["dino_center_sum"], B2, 0.9), ref["center_dino_after"])
         _close(O.center_ema(st["centers"]["ibot"], out["ibot_center_sum"], 1, 0.9), ref["center_ibot_after"])
+
+
+def test_vit_swiglu_ffn_forward_and_gradients_match_reference(golden_dir):
+    """SwiGLU FFN blocks (the dinov2 zoo default for ViT-B/L reg4 models, layers/swiglu_ffn.py) + register tokens:
+    forward features and EVERY parameter gradient of the oracle vs the imported reference module."""
+    ref = torch.load(golden_dir / "vit_tiny_swiglu.pt")
+    cfg = R.VIT_TINY_SWIGLU
+    assert cfg.hidden_dim == 344  # round8(2/3 * 4 * 128)
+    sd = {k: v.clone().requires_grad_(True) for k, v in R.det_vit_state(cfg, seed=13).items()}
+    xg, _, masks = R.vit_case_inputs()
+    g = O.vit_forward_features(sd, cfg, xg, masks)
+    _close(g["cls"], ref["g_cls"], rtol=1e-4, atol=2e-5)
+    _close(g["patch"], ref["g_patch"], rtol=1e-4, atol=2e-5)
+    cot = R.vit_swiglu_cotangents()
+    ((g["patch"] * cot[0]).sum() + (g["cls"] * cot[1]).sum()).backward()
+    checked = 0
+    for k, v in sd.items():
+        if "grad." + k in ref:
+            _close(v.grad, ref["grad." + k], rtol=2e-3, atol=2e-4 * float(ref["grad." + k].abs().max() + 1e-6))
+            checked += 1
+    assert checked >= 30 and any("w12" in k for k in sd)

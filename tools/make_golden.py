@@ -68,7 +68,7 @@ def build_ref_vit(m, cfg: O.ViTConfig, sd):
         img_size=cfg.img_size, patch_size=cfg.patch_size, embed_dim=cfg.embed_dim, depth=cfg.depth,
         num_heads=cfg.num_heads, mlp_ratio=cfg.mlp_ratio, init_values=cfg.init_values, block_chunks=0,
         num_register_tokens=cfg.num_register_tokens, interpolate_offset=cfg.interpolate_offset,
-        interpolate_antialias=cfg.interpolate_antialias,
+        interpolate_antialias=cfg.interpolate_antialias, ffn_layer=cfg.ffn_layer,
         block_fn=__import__("functools").partial(m.vit.Block, attn_class=m.vit.MemEffAttention))
     missing = vit.load_state_dict(sd, strict=True)
     assert not missing.missing_keys and not missing.unexpected_keys
@@ -109,6 +109,20 @@ def vit_reg_case(m) -> dict:
         l = vit(xl, None, is_training=True)
         g = vit(xg, masks, is_training=True)
     return {"l_cls": l["x_norm_clstoken"], "g_cls": g["x_norm_clstoken"], "g_patch": g["x_norm_patchtokens"]}
+
+
+def vit_swiglu_case(m) -> dict:
+    """SwiGLU FFN (w12 / w3, hidden = round8(2/3 * 4D)) + register tokens: forward features and every parameter gradient."""
+    cfg = R.VIT_TINY_SWIGLU
+    sd = R.det_vit_state(cfg, seed=13)
+    vit = build_ref_vit(m, cfg, sd).train()  # drop_path_rate = 0: train() only enables the masks path
+    xg, xl, masks = R.vit_case_inputs()
+    g = vit(xg, masks, is_training=True)
+    cot = R.vit_swiglu_cotangents()
+    ((g["x_norm_patchtokens"] * cot[0]).sum() + (g["x_norm_clstoken"] * cot[1]).sum()).backward()
+    out = {"g_cls": g["x_norm_clstoken"].detach(), "g_patch": g["x_norm_patchtokens"].detach()}
+    out.update({"grad." + k: p.grad.clone() for k, p in vit.named_parameters() if p.grad is not None})
+    return out
 
 
 def head_case(m) -> dict:
@@ -252,6 +266,7 @@ def main() -> None:
     (OUT / "ref_kats.json").write_text(json.dumps(ref_kats(m), indent=1))
     torch.save(vit_case(m), OUT / "vit_tiny.pt")
     torch.save(vit_reg_case(m), OUT / "vit_tiny_reg.pt")
+    torch.save(vit_swiglu_case(m), OUT / "vit_tiny_swiglu.pt")
     torch.save(head_case(m), OUT / "head_tiny.pt")
     torch.save(masks_case(m), OUT / "masks.pt")
     torch.save(loss_case(m), OUT / "loss_case.pt")
