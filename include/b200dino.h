@@ -114,6 +114,13 @@ int b200_assemble_tokens_bwd(const float* dx, const unsigned char* masks, int B,
 int b200_layerscale_bwd(const float* dx, long long lddx, const void* o, long long ldo, const float* gamma,
                         const float* rowscale, int rows_per_scale, int T, int D, void* dout, long long lddo,
                         float* dgamma, float* dbias, void* stream);
+/* SwiGLU FFN gate (SwiGLUFFN.forward, LT/_models/dinov2_vit/dinov2_vit_src/layers/swiglu_ffn.py:31-35):
+ * x12 bf16 [T, 2H] = w12(x); hidden[t, j] = bf16( bf16(silu(x12[t, j])) * x12[t, H + j] ) -- the two roundings of the
+ * bf16-autocast reference.  Backward: dx12[:, :H] = bf16( bf16(dh * x2) * silu'(x1) ), dx12[:, H:] = bf16( dh * bf16(silu(x1)) ).
+ * H % 8 == 0, row pitches % 8 == 0. */
+int b200_swiglu_fwd(const void* x12, long long ld12, int T, int H, void* hidden, long long ldh, void* stream);
+int b200_swiglu_bwd(const void* x12, long long ld12, const void* dhidden, long long lddh, int T, int H, void* dx12,
+                    long long lddx12, void* stream);
 /* torch.index_select of token rows (dinov2.py:427-431,496-500) and its backward (scatter).
  * Row index = Np>0 ? (idx/Np)*N + off + idx%Np : idx. */
 int b200_gather_rows(const float* src, long long lds, const long long* idx, int M, int D, int Np, int N, int off,

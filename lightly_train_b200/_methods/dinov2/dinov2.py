@@ -159,9 +159,13 @@ class DINOv2(nn.Module):
         D = probe["embed_dim"]
         n_patches = (probe["img_size"] // probe["patch_size"]) ** 2
         shapes: Dict[str, Tuple[int, ...]] = {}
+        swiglu = mk.get("ffn_layer", "mlp") != "mlp"
+        hidden = int(D * probe["mlp_ratio"])
+        if swiglu:
+            hidden = (int(hidden * 2 / 3) + 7) // 8 * 8  # SwiGLUFFNFused hidden size (layers/swiglu_ffn.py:60-63)
         for k, v in vit_param_shapes(D, probe["depth"], probe["patch_size"], mk["in_chans"], n_patches,
-                                     int(D * probe["mlp_ratio"]), mk.get("num_register_tokens", 0),
-                                     bool(mk.get("init_values"))).items():
+                                     hidden, mk.get("num_register_tokens", 0),
+                                     bool(mk.get("init_values")), swiglu).items():
             shapes["backbone." + k] = v
         hs = head_param_shapes(D, a.hidden_dim, a.dino_bottleneck_dim, a.output_dim)
         for k, v in hs.items():

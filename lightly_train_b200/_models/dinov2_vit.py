@@ -1,7 +1,7 @@
 """DinoVisionTransformer on B200 kernels.
 
 Mirror of LT/_models/dinov2_vit/dinov2_vit_src/models/vision_transformer.py:83-487 (class DinoVisionTransformer,
-non-chunked blocks, ffn_layer="mlp"): same constructor arguments, same parameter names / shapes
+non-chunked blocks, ffn_layer "mlp" or "swiglu"/"swiglufused"): same constructor arguments, same parameter names / shapes
 (`cls_token`, `pos_embed`, `mask_token`, `register_tokens`, `patch_embed.proj.*`, `blocks.{i}.{norm1,attn.qkv,
 attn.proj,ls1,norm2,mlp.fc1,mlp.fc2,ls2}.*`, `norm.*`) so reference checkpoints load unchanged, and the same
 `forward_features` contract.  The arithmetic runs on the sm_100a kernels of libb200dino.so; forward and
@@ -25,7 +25,7 @@ from .pos_embed import pos_embed_operator
 
 
 def vit_param_shapes(embed_dim: int, depth: int, patch_size: int, in_chans: int, num_patches: int, hidden: int,
-                     num_register_tokens: int, layerscale: bool) -> Dict[str, Tuple[int, ...]]:
+                     num_register_tokens: int, layerscale: bool, swiglu: bool = False) -> Dict[str, Tuple[int, ...]]:
     D, p = embed_dim, patch_size
     s: Dict[str, Tuple[int, ...]] = {"cls_token": (1, 1, D), "pos_embed": (1, 1 + num_patches, D)}
     if num_register_tokens:
@@ -40,8 +40,12 @@ def vit_param_shapes(embed_dim: int, depth: int, patch_size: int, in_chans: int,
         if layerscale:
             s[b + "ls1.gamma"] = (D,)
         s[b + "norm2.weight"] = (D,); s[b + "norm2.bias"] = (D,)
-        s[b + "mlp.fc1.weight"] = (hidden, D); s[b + "mlp.fc1.bias"] = (hidden,)
-        s[b + "mlp.fc2.weight"] = (D, hidden); s[b + "mlp.fc2.bias"] = (D,)
+        if swiglu:  # SwiGLUFFN: w12 = Linear(D, 2H), w3 = Linear(H, D)  (layers/swiglu_ffn.py:28-29)
+            s[b + "mlp.w12.weight"] = (2 * hidden, D); s[b + "mlp.w12.bias"] = (2 * hidden,)
+            s[b + "mlp.w3.weight"] = (D, hidden); s[b + "mlp.w3.bias"] = (D,)
+        else:
+            s[b + "mlp.fc1.weight"] = (hidden, D); s[b + "mlp.fc1.bias"] = (hidden,)
+            s[b + "mlp.fc2.weight"] = (D, hidden); s[b + "mlp.fc2.bias"] = (D,)
         if layerscale:
             s[b + "ls2.gamma"] = (D,)
     s["norm.weight"] = (D,); s["norm.bias"] = (D,)
@@ -83,8 +87,11 @@ class DinoVisionTransformer(nn.Module):
                  interpolate_offset: float = 0.1, *, arena: Optional[Arena] = None, prefix: str = "",
                  device: str = "cuda", requires_grad: bool = True) -> None:
         super().__init__()
-        if ffn_layer != "mlp" or block_chunks not in (0,) or not (qkv_bias and ffn_bias and proj_bias):
-            raise NotImplementedError("b200 DinoVisionTransformer: ffn_layer='mlp', block_chunks=0, biases on")
+        if ffn_layer not in ("mlp", "swiglu", "swiglufused") or block_chunks not in (0,) or not (qkv_bias and ffn_bias and proj_bias):
+            raise NotImplementedError("b200 DinoVisionTransformer: ffn_layer in {mlp, swiglu, swiglufused}, block_chunks=0, biases on")
+        self.swiglu = ffn_layer != "mlp"
+        # parameter names of the FFN's input / output projections
+        self._ffn_in, self._ffn_out = ("mlp.w12.", "mlp.w3.") if self.swiglu else ("mlp.fc1.", "mlp.fc2.")
         if embed_dim % num_heads or embed_dim // num_heads != 64:
             raise NotImplementedError("b200 attention kernels are specialised for head_dim 64")
         self.num_features = self.embed_dim = embed_dim
@@ -97,6 +104,8 @@ class DinoVisionTransformer(nn.Module):
         self.interpolate_antialias = interpolate_antialias
         self.interpolate_offset = interpolate_offset
         self.hidden_dim = int(embed_dim * mlp_ratio)
+        if self.swiglu:
+            self.hidden_dim = (int(self.hidden_dim * 2 / 3) + 7) // 8 * 8  # SwiGLUFFNFused (layers/swiglu_ffn.py:60-63)
         self.chunked_blocks = False
         self.layerscale = bool(init_values)
         self.ln_eps = 1e-6
@@ -108,7 +117,7 @@ class DinoVisionTransformer(nn.Module):
         self._dp_keep: dict = {}
         self.prefix = prefix
         shapes = vit_param_shapes(embed_dim, depth, patch_size, in_chans, self.num_patches, self.hidden_dim,
-                                  num_register_tokens, self.layerscale)
+                                  num_register_tokens, self.layerscale, self.swiglu)
         if arena is None:
             arena = Arena({prefix + k: v for k, v in shapes.items()}, device, with_grad=requires_grad,
                           with_optim_state=False)
@@ -201,12 +210,19 @@ class DinoVisionTransformer(nn.Module):
         xn2 = E(T, D)
         ops.layernorm_fwd(xmid, self._P(b + "norm2.weight"), self._P(b + "norm2.bias"), self.ln_eps, xn2, mean2, rstd2)
         hh = E(T, Hd)
-        u = E(T, Hd) if save else None
-        ops.gemm(xn2, self._W(b + "mlp.fc1.weight"), hh, epi=ops.EPI_BIAS_GELU_DG if save else ops.EPI_BIAS_GELU,
-                 bias=self._P(b + "mlp.fc1.bias"), out2=u)  # u holds gelu'(fc1 out) for the backward
+        if self.swiglu:
+            u = E(T, 2 * Hd)  # x12 = w12(x): kept for the backward when saving
+            ops.gemm(xn2, self._W(b + "mlp.w12.weight"), u, bias=self._P(b + "mlp.w12.bias"))
+            ops.swiglu_fwd(u, hh)
+            if not save:
+                u = None
+        else:
+            u = E(T, Hd) if save else None
+            ops.gemm(xn2, self._W(b + "mlp.fc1.weight"), hh, epi=ops.EPI_BIAS_GELU_DG if save else ops.EPI_BIAS_GELU,
+                     bias=self._P(b + "mlp.fc1.bias"), out2=u)  # u holds gelu'(fc1 out) for the backward
         o2 = E(T, D) if save else None
         xout = E(T, D, dt=f32)
-        ops.gemm(hh, self._W(b + "mlp.fc2.weight"), xout, epi=ops.EPI_RESIDUAL, bias=self._P(b + "mlp.fc2.bias"),
+        ops.gemm(hh, self._W(b + self._ffn_out + "weight"), xout, epi=ops.EPI_RESIDUAL, bias=self._P(b + self._ffn_out + "bias"),
                  out2=o2, aux=xmid, gamma=self._P(b + "ls2.gamma") if self.layerscale else None,
                  rowscale=rs2, rows_per_scale=N)
         sv = {"x_out": xout}
@@ -329,18 +345,24 @@ class DinoVisionTransformer(nn.Module):
         ops.layernorm_bwd_ls(d_xnorm, ctx.x_prenorm, self._P("norm.weight"), ctx.meanf, ctx.rstdf, dx, False,
                              self._G("norm.weight"), self._G("norm.bias"), last["o2"],
                              self._P(bl + "ls2.gamma") if ls else None, last["rs2"], N, do2,
-                             self._G(bl + "ls2.gamma") if ls else None, self._G(bl + "mlp.fc2.bias"))
+                             self._G(bl + "ls2.gamma") if ls else None, self._G(bl + self._ffn_out + "bias"))
         for i in reversed(range(nb)):
             b = f"blocks.{i}."
             sv = ctx.blocks[i]
             # ---- MLP branch (do2 = gradient of the fc2 output, produced by the fused kernel above / below)
-            dU = E(T, Hd)
-            ops.gemm(do2, self._W(b + "mlp.fc2.weight"), dU, b_mn=True, epi=ops.EPI_MUL_AUX, aux=sv["u"])
-            wgrad(do2, sv["h"], b + "mlp.fc2.weight")
-            ops.col_reduce(dU, self._G(b + "mlp.fc1.bias"))
-            wgrad(dU, sv["xn2"], b + "mlp.fc1.weight")
+            if self.swiglu:
+                dH = E(T, Hd)
+                ops.gemm(do2, self._W(b + "mlp.w3.weight"), dH, b_mn=True)
+                dU = E(T, 2 * Hd)
+                ops.swiglu_bwd(sv["u"], dH, dU)
+            else:
+                dU = E(T, Hd)
+                ops.gemm(do2, self._W(b + "mlp.fc2.weight"), dU, b_mn=True, epi=ops.EPI_MUL_AUX, aux=sv["u"])
+            wgrad(do2, sv["h"], b + self._ffn_out + "weight")
+            ops.col_reduce(dU, self._G(b + self._ffn_in + "bias"))
+            wgrad(dU, sv["xn2"], b + self._ffn_in + "weight")
             dxn2 = E(T, D)
-            ops.gemm(dU, self._W(b + "mlp.fc1.weight"), dxn2, b_mn=True)
+            ops.gemm(dU, self._W(b + self._ffn_in + "weight"), dxn2, b_mn=True)
             # LN2 backward (dx += ...) fused with the LayerScale backward of this block's attention branch
             do1 = E(T, D)
             ops.layernorm_bwd_ls(dxn2, sv["x_mid"], self._P(b + "norm2.weight"), sv["mean2"], sv["rstd2"], dx, True,
@@ -366,7 +388,7 @@ class DinoVisionTransformer(nn.Module):
                 ops.layernorm_bwd_ls(dxn, sv["x_in"], self._P(b + "norm1.weight"), sv["mean1"], sv["rstd1"], dx, True,
                                      self._G(b + "norm1.weight"), self._G(b + "norm1.bias"), pv["o2"],
                                      self._P(bp + "ls2.gamma") if ls else None, pv["rs2"], N, do2,
-                                     self._G(bp + "ls2.gamma") if ls else None, self._G(bp + "mlp.fc2.bias"))
+                                     self._G(bp + "ls2.gamma") if ls else None, self._G(bp + self._ffn_out + "bias"))
             else:
                 ops.layernorm_bwd(dxn, sv["x_in"], self._P(b + "norm1.weight"), sv["mean1"], sv["rstd1"], dx, True,
                                   self._G(b + "norm1.weight"), self._G(b + "norm1.bias"))

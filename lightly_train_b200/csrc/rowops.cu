@@ -419,6 +419,57 @@ __global__ void __launch_bounds__(ROW_THREADS) layerscale_bwd_kernel(const float
 }
 
 // ------------------------------------------------------------------------------------------------
+// SwiGLU gate (layers/swiglu_ffn.py:31-35): 8 bf16 columns per thread, x1 = x12[:, :H], x2 = x12[:, H:].
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_ftz(1.0f + ex2_ftz(x * -1.4426950408889634f)); }
+
+__global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ x12, long long ld12, int T, int H,
+                                  __nv_bfloat16* __restrict__ hid, long long ldh) {
+  const int hv = H >> 3;
+  const long long total = (long long)T * hv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / hv;
+    const int c = (int)(i % hv) * 8;
+    const uint4 a = *reinterpret_cast<const uint4*>(x12 + row * ld12 + c);
+    const uint4 b = *reinterpret_cast<const uint4*>(x12 + row * ld12 + H + c);
+    const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+    uint32_t ov[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 x1 = unpack_bf16x2(av[k]), x2 = unpack_bf16x2(bv[k]);
+      const float2 s = unpack_bf16x2(pack_bf16x2(x1.x * sigmoid_fast(x1.x), x1.y * sigmoid_fast(x1.y)));  // bf16 silu
+      ov[k] = pack_bf16x2(s.x * x2.x, s.y * x2.y);
+    }
+    *reinterpret_cast<uint4*>(hid + row * ldh + c) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+  }
+}
+
+__global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ x12, long long ld12, const __nv_bfloat16* __restrict__ dh,
+                                  long long lddh, int T, int H, __nv_bfloat16* __restrict__ dx12, long long lddx) {
+  const int hv = H >> 3;
+  const long long total = (long long)T * hv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / hv;
+    const int c = (int)(i % hv) * 8;
+    const uint4 a = *reinterpret_cast<const uint4*>(x12 + row * ld12 + c);
+    const uint4 b = *reinterpret_cast<const uint4*>(x12 + row * ld12 + H + c);
+    const uint4 g = *reinterpret_cast<const uint4*>(dh + row * lddh + c);
+    const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w}, gv[4] = {g.x, g.y, g.z, g.w};
+    uint32_t o1[4], o2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 x1 = unpack_bf16x2(av[k]), x2 = unpack_bf16x2(bv[k]), d = unpack_bf16x2(gv[k]);
+      const float sx = sigmoid_fast(x1.x), sy = sigmoid_fast(x1.y);
+      const float2 s = unpack_bf16x2(pack_bf16x2(x1.x * sx, x1.y * sy));             // bf16 silu(x1), as saved by autograd
+      const float2 da = unpack_bf16x2(pack_bf16x2(d.x * x2.x, d.y * x2.y));          // grad wrt silu output (bf16)
+      o1[k] = pack_bf16x2(da.x * (sx * (1.0f + x1.x * (1.0f - sx))), da.y * (sy * (1.0f + x1.y * (1.0f - sy))));
+      o2[k] = pack_bf16x2(d.x * s.x, d.y * s.y);
+    }
+    *reinterpret_cast<uint4*>(dx12 + row * lddx + c) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+    *reinterpret_cast<uint4*>(dx12 + row * lddx + H + c) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Row gather / scatter of f32 rows.  src row index = map(idx[m]) with map(i) = (i / Np) * N + off + (i % Np)
 // (token index inside [B, N, D] from an index into the flattened patch grid; Np = 0 -> identity map).
 //   gather : out[m] = src[map(idx[m])]  (out f32 or bf16)
@@ -718,6 +769,30 @@ extern "C" int b200_layerscale_bwd(const float* dx, long long lddx, const void* 
                                                                             dgamma, dbias)
   if (D <= 384) B200_LS_BWD(3); else if (D <= 768) B200_LS_BWD(6); else B200_LS_BWD(8);
 #undef B200_LS_BWD
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+extern "C" int b200_swiglu_fwd(const void* x12, long long ld12, int T, int H, void* hidden, long long ldh, void* stream) {
+  if (!x12 || !hidden || T <= 0 || H <= 0) return B200_ERR_INVALID_ARG;
+  if ((H % 8) || (ld12 % 8) || (ldh % 8) || ((uintptr_t)x12 & 15) || ((uintptr_t)hidden & 15)) return B200_ERR_UNSUPPORTED;
+  const long long total = (long long)T * (H / 8);
+  const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  swiglu_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x12, ld12, T, H, (__nv_bfloat16*)hidden, ldh);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+extern "C" int b200_swiglu_bwd(const void* x12, long long ld12, const void* dhidden, long long lddh, int T, int H, void* dx12,
+                               long long lddx12, void* stream) {
+  if (!x12 || !dhidden || !dx12 || T <= 0 || H <= 0) return B200_ERR_INVALID_ARG;
+  if ((H % 8) || (ld12 % 8) || (lddh % 8) || (lddx12 % 8) || ((uintptr_t)x12 & 15) || ((uintptr_t)dhidden & 15) ||
+      ((uintptr_t)dx12 & 15))
+    return B200_ERR_UNSUPPORTED;
+  const long long total = (long long)T * (H / 8);
+  const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  swiglu_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x12, ld12, (const __nv_bfloat16*)dhidden, lddh, T, H,
+                                                            (__nv_bfloat16*)dx12, lddx12);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

@@ -168,6 +168,23 @@ def layerscale_bwd(dx, o, gamma, rowscale, rows_per_scale: int, dout, dgamma, db
                                    _stream()), "b200_layerscale_bwd")
 
 
+def swiglu_fwd(x12, hidden) -> None:
+    """hidden = silu(x12[:, :H]) * x12[:, H:]  (bf16, autocast rounding points)."""
+    _req_cuda(x12, hidden)
+    T, H = hidden.shape
+    assert x12.shape == (T, 2 * H) and x12.dtype == hidden.dtype == torch.bfloat16
+    check(_L().b200_swiglu_fwd(x12.data_ptr(), x12.stride(0), T, H, hidden.data_ptr(), hidden.stride(0), _stream()),
+          "b200_swiglu_fwd")
+
+
+def swiglu_bwd(x12, dhidden, dx12) -> None:
+    _req_cuda(x12, dhidden, dx12)
+    T, H = dhidden.shape
+    assert x12.shape == dx12.shape == (T, 2 * H)
+    check(_L().b200_swiglu_bwd(x12.data_ptr(), x12.stride(0), dhidden.data_ptr(), dhidden.stride(0), T, H, dx12.data_ptr(),
+                               dx12.stride(0), _stream()), "b200_swiglu_bwd")
+
+
 def gather_rows(src, idx, out, Np: int = 0, N: int = 0, off: int = 0) -> None:
     """out[m] = src[map(idx[m])]; src f32 2-D; idx int64."""
     M, D = out.shape

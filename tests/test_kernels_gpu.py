@@ -417,3 +417,22 @@ def test_ema_sumsq_adamw():
         torch.testing.assert_close(p, torch.cat([pa, pb]).detach(), rtol=1e-5, atol=1e-6)
         torch.testing.assert_close(teacher, t_ref, rtol=1e-5, atol=1e-6)
     assert torch.equal(pb16, p.bfloat16()) and torch.equal(tb16, teacher.bfloat16())
+
+
+@pytest.mark.parametrize("T,H", [(1000, 344), (77, 2048), (5, 8)])
+def test_swiglu_gate_fwd_bwd(T, H):
+    """b200_swiglu_fwd/bwd vs torch on bf16 tensors (the autocast reference: silu and the product each round to bf16)."""
+    x12 = rnd(T, 2 * H, dtype=torch.bfloat16, scale=2.0, seed=31)
+    hid = torch.empty(T, H, device=dev, dtype=torch.bfloat16)
+    ops.swiglu_fwd(x12, hid)
+    xr = x12.clone().requires_grad_(True)
+    x1, x2 = xr.chunk(2, dim=-1)
+    want = F.silu(x1) * x2
+    torch.testing.assert_close(hid.float(), want.float(), rtol=1.6e-2, atol=1e-3)  # <= 2 bf16 ulp (rcp/ex2.approx sigmoid)
+    dh = rnd(T, H, dtype=torch.bfloat16, scale=1.0, seed=32)
+    want.backward(dh)
+    dx = torch.empty_like(x12)
+    ops.swiglu_bwd(x12, dh, dx)
+    torch.testing.assert_close(dx.float(), xr.grad.float(), rtol=2.4e-2, atol=2e-3)
+    rel = (dx.float() - xr.grad.float()).norm() / xr.grad.float().norm()
+    assert rel < 5e-3, rel
