@@ -107,13 +107,6 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   return v;
 }
 
-struct EpiPtrs {
-  char* c;         // primary output, positioned at (first row of this lane, col)
-  char* c2;        // secondary bf16 output or nullptr
-  const char* aux; // aux input or nullptr
-  long long c_step, c2_step, aux_step;  // bytes per 4-row group
-};
-
 template <int EPI, bool HAS_C2>
 __device__ __forceinline__ void epilogue_vec4(float alpha, float4 acc, char* c, char* c2_, float rs, const float4& bias4,
                                               const float4& gamma4, const float4& aux4) {

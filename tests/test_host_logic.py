@@ -105,3 +105,23 @@ def test_product_path_fails_loudly_without_a_gpu():
     views = [torch.randn(2, 3, 32, 32) for _ in range(2)]
     with pytest.raises((RuntimeError, AssertionError)):
         m.train_step({"views": views})
+
+
+def test_state_dict_names_and_shapes_match_the_reference_modules(golden_dir):
+    """Drop-in boundary: the mirror classes expose exactly the reference's parameter names and
+    shapes (lists dumped from the imported reference modules by tools/make_golden.py), so its checkpoints load unchanged."""
+    import json
+    from lightly_train_b200._methods.dinov2.dinov2_head import DINOv2ProjectionHead
+    from lightly_train_b200._models.dinov2_vit import DinoVisionTransformer
+    ref = json.loads((golden_dir / "ref_state_dict_shapes.json").read_text())
+    mine = {
+        "vit_small_p16": DinoVisionTransformer(img_size=224, patch_size=16, embed_dim=384, depth=12, num_heads=6,
+                                               init_values=1e-5, device="cpu"),
+        "vit_base_p14_reg4_swiglu": DinoVisionTransformer(img_size=518, patch_size=14, embed_dim=768, depth=12, num_heads=12,
+                                                          init_values=1e-5, num_register_tokens=4, ffn_layer="swiglufused",
+                                                          interpolate_antialias=True, interpolate_offset=0.0, device="cpu"),
+        "head_384_65536": DINOv2ProjectionHead(384, 65536, hidden_dim=2048, bottleneck_dim=256, device="cpu"),
+    }
+    for name, mod in mine.items():
+        got = {k: list(v.shape) for k, v in mod.state_dict().items()}
+        assert got == ref[name], (name, set(got) ^ set(ref[name]))

@@ -125,6 +125,24 @@ def vit_swiglu_case(m) -> dict:
     return out
 
 
+def state_dict_shapes(m) -> dict:
+    """Parameter names and shapes of the reference modules (drop-in boundary)."""
+    import functools
+
+    def vit(**kw):
+        v = m.vit.DinoVisionTransformer(block_chunks=0, block_fn=functools.partial(m.vit.Block, attn_class=m.vit.MemEffAttention), **kw)
+        return {k: list(t.shape) for k, t in v.state_dict().items()}
+
+    h = m.head.DINOv2ProjectionHead(in_dim=384, out_dim=65536, hidden_dim=2048, bottleneck_dim=256)
+    return {
+        "vit_small_p16": vit(img_size=224, patch_size=16, embed_dim=384, depth=12, num_heads=6, init_values=1e-5),
+        "vit_base_p14_reg4_swiglu": vit(img_size=518, patch_size=14, embed_dim=768, depth=12, num_heads=12, init_values=1e-5,
+                                        num_register_tokens=4, ffn_layer="swiglufused", interpolate_antialias=True,
+                                        interpolate_offset=0.0),
+        "head_384_65536": {k: list(t.shape) for k, t in h.state_dict().items()},
+    }
+
+
 def head_case(m) -> dict:
     cfg = R.HEAD_TINY
     sd = R.det_head_state(cfg, seed=21)
@@ -266,6 +284,7 @@ def main() -> None:
     (OUT / "ref_kats.json").write_text(json.dumps(ref_kats(m), indent=1))
     torch.save(vit_case(m), OUT / "vit_tiny.pt")
     torch.save(vit_reg_case(m), OUT / "vit_tiny_reg.pt")
+    (OUT / "ref_state_dict_shapes.json").write_text(json.dumps(state_dict_shapes(m), indent=0))
     torch.save(vit_swiglu_case(m), OUT / "vit_tiny_swiglu.pt")
     torch.save(head_case(m), OUT / "head_tiny.pt")
     torch.save(masks_case(m), OUT / "masks.pt")
