@@ -150,3 +150,16 @@ def step_case_inputs(cfg: O.StepConfig, batch: int = 3, n_local: int = 2) -> Tup
     idx = masks.flatten().nonzero().flatten()
     w = O.masks_weight_from_masks(masks)
     return views, masks, idx, w
+
+
+def distill_case_inputs():
+    """(teacher_global, teacher_local, student_global, student_local, queue), all L2-normalised; B=4, M=9 tokens, D=16, C=32."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(301)
+    B, M, D, C = 4, 9, 16, 32
+    tg = F.normalize(torch.randn(B, D, generator=g), dim=-1)
+    tl = F.normalize(torch.randn(B, M, D, generator=g), dim=-1)
+    sg = F.normalize(torch.randn(B, D, generator=g), dim=-1)
+    sl = F.normalize(torch.randn(B, M, D, generator=g), dim=-1)
+    q = F.normalize(torch.randn(C, D, generator=g), dim=-1)
+    return tg, tl, sg, sl, q

@@ -162,3 +162,22 @@ def test_vit_swiglu_ffn_forward_and_gradients_match_reference(golden_dir):
             _close(v.grad, ref["grad." + k], rtol=2e-3, atol=2e-4 * float(ref["grad." + k].abs().max() + 1e-6))
             checked += 1
     assert checked >= 30 and any("w12" in k for k in sd)
+
+
+def test_distillation_v3_loss_matches_reference(golden_dir):
+    """oracle restatement of DistillationV3Loss vs the imported reference module (values and
+    gradients wrt the student features), plus the reference tests' own properties (zero when identical, non-negative)."""
+    from oracle import distillationv3_oracle as DO
+    ref = torch.load(golden_dir / "distill_v3_loss.pt")
+    tg, tl, sg, sl, q = R.distill_case_inputs()
+    sg.requires_grad_(True); sl.requires_grad_(True)
+    lg, ll = DO.distillation_v3_loss(tg, tl, sg, sl, q, 0.07, 0.05)
+    _close(lg.detach(), ref["loss_global"], rtol=1e-5, atol=1e-6)
+    _close(ll.detach(), ref["loss_local"], rtol=1e-4, atol=1e-8)
+    (lg + 2 * ll).backward()
+    _close(sg.grad, ref["d_student_global"], rtol=1e-4, atol=1e-6)
+    _close(sl.grad, ref["d_student_local"], rtol=1e-3, atol=1e-7)
+    # LT tests/_methods/distillation*/: identical teacher and student -> KL ~ 0 ; loss >= 0
+    z_g, z_l = DO.distillation_v3_loss(tg, tl, tg.clone(), tl.clone(), q, 0.07, 0.05)
+    assert abs(float(z_g)) < 1e-6 and abs(float(z_l)) < 1e-6
+    assert float(lg) >= 0 and float(ll) >= 0

@@ -143,6 +143,17 @@ def state_dict_shapes(m) -> dict:
     }
 
 
+def distill_v3_case() -> dict:
+    """DistillationV3Loss (temperatures 0.07 / 0.05): both KL terms and the gradients wrt the student features."""
+    from lightly_train._methods.distillationv3.distillationv3_loss import DistillationV3Loss  # type: ignore
+    tg, tl, sg, sl, q = R.distill_case_inputs()
+    sg.requires_grad_(True); sl.requires_grad_(True)
+    lg, ll = DistillationV3Loss(0.07, 0.05)(tg, tl, sg, sl, q)
+    (lg + 2 * ll).backward()
+    return {"loss_global": lg.detach(), "loss_local": ll.detach(), "d_student_global": sg.grad.clone(),
+            "d_student_local": sl.grad.clone()}
+
+
 def head_case(m) -> dict:
     cfg = R.HEAD_TINY
     sd = R.det_head_state(cfg, seed=21)
@@ -286,6 +297,7 @@ def main() -> None:
     torch.save(vit_reg_case(m), OUT / "vit_tiny_reg.pt")
     (OUT / "ref_state_dict_shapes.json").write_text(json.dumps(state_dict_shapes(m), indent=0))
     torch.save(vit_swiglu_case(m), OUT / "vit_tiny_swiglu.pt")
+    torch.save(distill_v3_case(), OUT / "distill_v3_loss.pt")
     torch.save(head_case(m), OUT / "head_tiny.pt")
     torch.save(masks_case(m), OUT / "masks.pt")
     torch.save(loss_case(m), OUT / "loss_case.pt")
