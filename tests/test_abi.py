@@ -43,3 +43,12 @@ def test_ops_refuse_cpu_tensors():
     a = torch.zeros(8, 8, dtype=torch.bfloat16)
     with pytest.raises(B200Error):
         ops.gemm(a, a, torch.zeros(8, 8, dtype=torch.bfloat16))
+
+
+def test_product_package_never_references_the_oracle():
+    """The oracle is test infrastructure: nothing under lightly_train_b200/ may import, call or mention it."""
+    import pathlib
+    root = pathlib.Path(__file__).resolve().parents[1] / "lightly_train_b200"
+    offenders = [str(p) for p in root.rglob("*.py") if "oracle" in p.read_text()]
+    offenders += [str(p) for p in (root / "csrc").glob("*.cu*") if "oracle" in p.read_text()]
+    assert not offenders, offenders
