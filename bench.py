@@ -347,7 +347,7 @@ def main() -> None:
                     "gemm_tflop_per_step": flops / 1e12}
 
     cpu_baseline = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:  # reported at N=1 only (the other ranks would idle)
         threads = host_threads()
         sec = cpu_reference_step_time(2, 1, 1, threads)
         cpu_baseline = {"value": 2 / sec, "unit": "images/s", "cores": threads, "kind": "port",
@@ -362,7 +362,7 @@ def main() -> None:
                                    "softmax centering, drop_path 0.1, full step incl. clip+AdamW+EMA" % B,
                        "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2_policy": "inputs (2 alternating 134 MB batches) and activations (>8 GB/step) exceed the 126 MB L2"},
-            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches, "host_ms_per_step": round(host_ms, 3), "loss": loss_val,
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches, "gpu_launches_scope": "library kernel launches of rank 0 (graph replays counted per captured launch)", "host_ms_per_step": round(host_ms, 3), "loss": loss_val,
             "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)
