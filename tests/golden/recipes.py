@@ -163,3 +163,47 @@ def distill_case_inputs():
     sl = F.normalize(torch.randn(B, M, D, generator=g), dim=-1)
     q = F.normalize(torch.randn(C, D, generator=g), dim=-1)
     return tg, tl, sg, sl, q
+
+
+# ---------------------------------------------------------------- DINOv3 teacher forward (distillation)
+def dinov3_tiny_cfg():
+    from oracle import dinov3_oracle as D3
+    return D3.Dinov3Config(embed_dim=128, depth=2, num_heads=2, patch_size=16)
+
+
+def dinov3_param_shapes(cfg) -> Dict[str, Tuple[int, ...]]:
+    D, p, H = cfg.embed_dim, cfg.patch_size, int(cfg.embed_dim * cfg.ffn_ratio)
+    shapes: Dict[str, Tuple[int, ...]] = {
+        "cls_token": (1, 1, D), "storage_tokens": (1, cfg.n_storage_tokens, D), "mask_token": (1, D),
+        "patch_embed.proj.weight": (D, 3, p, p), "patch_embed.proj.bias": (D,),
+    }
+    for i in range(cfg.depth):
+        b = f"blocks.{i}."
+        shapes.update({
+            b + "norm1.weight": (D,), b + "norm1.bias": (D,),
+            b + "attn.qkv.weight": (3 * D, D), b + "attn.qkv.bias": (3 * D,),
+            b + "attn.proj.weight": (D, D), b + "attn.proj.bias": (D,),
+            b + "ls1.gamma": (D,),
+            b + "norm2.weight": (D,), b + "norm2.bias": (D,),
+            b + "mlp.fc1.weight": (H, D), b + "mlp.fc1.bias": (H,),
+            b + "mlp.fc2.weight": (D, H), b + "mlp.fc2.bias": (D,),
+            b + "ls2.gamma": (D,),
+        })
+    shapes.update({"norm.weight": (D,), "norm.bias": (D,)})
+    return shapes
+
+
+def det_dinov3_state(cfg, seed: int) -> Dict[str, Tensor]:
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for k, shp in dinov3_param_shapes(cfg).items():
+        out[k] = _fill("register_tokens" if k == "storage_tokens" else k, shp, g)
+    return out
+
+
+def dinov3_case_inputs() -> Tuple[Tensor, Tensor]:
+    """Non-square image (14 x 6 patches) so that the axial RoPE's row / column roles are pinned, 30 % masked."""
+    g = torch.Generator().manual_seed(402)
+    x = torch.randn(2, 3, 224, 96, generator=g)
+    masks = torch.rand(2, 14 * 6, generator=g) < 0.3
+    return x, masks

@@ -181,3 +181,19 @@ def test_distillation_v3_loss_matches_reference(golden_dir):
     z_g, z_l = DO.distillation_v3_loss(tg, tl, tg.clone(), tl.clone(), q, 0.07, 0.05)
     assert abs(float(z_g)) < 1e-6 and abs(float(z_l)) < 1e-6
     assert float(lg) >= 0 and float(ll) >= 0
+
+
+def test_dinov3_teacher_forward_matches_reference(golden_dir):
+    """SURVEY 8a row a17 (cfg4 teacher): axial RoPE on the patch tokens only, storage tokens, masked k bias, eps 1e-5 --
+    oracle restatement vs the imported reference DINOv3 ViT on a non-square masked input."""
+    from oracle import dinov3_oracle as D3
+    ref = torch.load(golden_dir / "dinov3_tiny.pt")
+    cfg = R.dinov3_tiny_cfg()
+    sd = R.det_dinov3_state(cfg, seed=14)
+    x, masks = R.dinov3_case_inputs()
+    o = D3.forward_features(sd, cfg, x, masks)
+    for k in ("cls", "storage", "patch", "prenorm"):
+        _close(o[k], ref[k], rtol=1e-4, atol=2e-5)
+    # the rotation must actually matter: without RoPE the patch features move by far more than the tolerance
+    sin, cos = D3.rope_sincos(cfg, 14, 6)
+    assert sin.shape == (84, 64) and float(sin.abs().max()) > 0.5

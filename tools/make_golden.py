@@ -154,6 +154,28 @@ def distill_v3_case() -> dict:
             "d_student_local": sl.grad.clone()}
 
 
+def dinov3_case() -> dict:
+    """DINOv3 ViT (RoPE on patch tokens, 4 storage tokens, masked k bias, LayerNorm eps 1e-5) in eval mode = the teacher
+    forward of the distillation method: features of a non-square masked input."""
+    from lightly_train._models.dinov3.dinov3_src.models import vision_transformer as v3  # type: ignore
+    cfg = R.dinov3_tiny_cfg()
+    vit = v3.DinoVisionTransformer(img_size=224, patch_size=cfg.patch_size, embed_dim=cfg.embed_dim, depth=cfg.depth,
+                                   num_heads=cfg.num_heads, ffn_ratio=cfg.ffn_ratio, layerscale_init=cfg.layerscale_init,
+                                   norm_layer="layernormbf16", n_storage_tokens=cfg.n_storage_tokens, mask_k_bias=True,
+                                   pos_embed_rope_base=cfg.rope_base, pos_embed_rope_normalize_coords="separate",
+                                   pos_embed_rope_dtype="fp32", pos_embed_rope_rescale_coords=2.0)
+    vit.init_weights()  # fills rope periods and the k-bias mask
+    sd = R.det_dinov3_state(cfg, seed=14)
+    r = vit.load_state_dict(sd, strict=False)
+    assert not r.unexpected_keys and all(k.endswith("bias_mask") or k == "rope_embed.periods" for k in r.missing_keys), r
+    vit.eval()
+    x, masks = R.dinov3_case_inputs()
+    with torch.no_grad():
+        o = vit.forward_features(x, masks)
+    return {"cls": o["x_norm_clstoken"], "storage": o["x_storage_tokens"], "patch": o["x_norm_patchtokens"],
+            "prenorm": o["x_prenorm"]}
+
+
 def head_case(m) -> dict:
     cfg = R.HEAD_TINY
     sd = R.det_head_state(cfg, seed=21)
@@ -298,6 +320,7 @@ def main() -> None:
     (OUT / "ref_state_dict_shapes.json").write_text(json.dumps(state_dict_shapes(m), indent=0))
     torch.save(vit_swiglu_case(m), OUT / "vit_tiny_swiglu.pt")
     torch.save(distill_v3_case(), OUT / "distill_v3_loss.pt")
+    torch.save(dinov3_case(), OUT / "dinov3_tiny.pt")
     torch.save(head_case(m), OUT / "head_tiny.pt")
     torch.save(masks_case(m), OUT / "masks.pt")
     torch.save(loss_case(m), OUT / "loss_case.pt")
