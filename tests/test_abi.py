@@ -52,3 +52,25 @@ def test_product_package_never_references_the_oracle():
     offenders = [str(p) for p in root.rglob("*.py") if "oracle" in p.read_text()]
     offenders += [str(p) for p in (root / "csrc").glob("*.cu*") if "oracle" in p.read_text()]
     assert not offenders, offenders
+
+
+def test_error_convention_on_invalid_arguments(lib):
+    """entry points return a negative int on bad arguments and never throw, exit or touch the device --
+    these calls are rejected by the argument checks before any CUDA API is reached, so they run without a GPU."""
+    from lightly_train_b200._lib import GemmArgs
+    INVALID, UNSUPPORTED = -1, -2
+    g = GemmArgs()  # all-zero: null operands
+    assert lib.b200_gemm(ctypes.byref(g), None) == INVALID
+    dummy = ctypes.c_void_p(0x1000)  # never dereferenced: the shape checks fail first
+    g.A = g.B = g.C = 0x1000
+    g.M, g.N, g.K, g.lda, g.ldb, g.ldc = 128, 100, 64, 64, 64, 100  # N not a multiple of 8
+    assert lib.b200_gemm(ctypes.byref(g), None) == UNSUPPORTED
+    g.N, g.ldc, g.epi = 128, 128, 99  # unknown epilogue
+    assert lib.b200_gemm(ctypes.byref(g), None) == INVALID
+    # attention kernels are specialised for head_dim 64; sequences above 272 tokens are not supported
+    assert lib.b200_attention_fwd(dummy, 192, 1, 16, 1, 32, 0.125, dummy, 64, None, None) == UNSUPPORTED
+    assert lib.b200_attention_fwd(dummy, 192, 1, 300, 1, 64, 0.125, dummy, 64, None, None) == UNSUPPORTED
+    assert lib.b200_attention_fwd(dummy, 192, 1, 16, 1, 64, -1.0, dummy, 64, None, None) == INVALID
+    # SwiGLU gate: H must be a multiple of 8
+    assert lib.b200_swiglu_fwd(dummy, 24, 4, 12, dummy, 12, None) == UNSUPPORTED
+    assert lib.b200_swiglu_fwd(None, 16, 4, 8, dummy, 8, None) == INVALID
