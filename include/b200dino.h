@@ -70,6 +70,12 @@ typedef struct b200_gemm_args {
 
 int b200_gemm(const b200_gemm_args* args, void* stream);
 
+/* Same contract as b200_attention_fwd on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), N <= 256.
+ * BRING-UP: compiled and exported, not yet validated on hardware and not used by the product path
+ * (lightly_train_b200/csrc/attention_tc.cu).  P is rounded to bf16 before normalisation
+ * (flash-style), the other rounding points are those of b200_attention_fwd. */
+int b200_attention_fwd_tc(const void* qkv, long long ld_tok, int B, int N, int h, int head_dim, float scale, void* out,
+                          long long ld_out, float* lse, void* stream);
 /* ------------------------------------------------------------------------------------------------
  * Attention core for short sequences (head_dim 64), forward and backward.
  * Replaces LT/_models/dinov2_vit/dinov2_vit_src/layers/attention.py:55-63 (q*scale @ k^T, softmax, @ v) and

@@ -105,6 +105,13 @@ def attention_fwd(qkv: torch.Tensor, B: int, N: int, h: int, out: torch.Tensor, 
                                   _ptr(lse), _stream()), "b200_attention_fwd")
 
 
+def attention_fwd_tc(qkv, B: int, N: int, h: int, out, lse, scale: float) -> None:
+    """tcgen05 forward (bring-up, not used by the model: csrc/attention_tc.cu); same contract as attention_fwd, N <= 256."""
+    _req_cuda(qkv, out)
+    check(_L().b200_attention_fwd_tc(qkv.data_ptr(), qkv.stride(0), B, N, h, 64, scale, out.data_ptr(), out.stride(0),
+                                     _ptr(lse), _stream()), "b200_attention_fwd_tc")
+
+
 def attention_bwd(qkv, out, dout, lse, B: int, N: int, h: int, dqkv, scale: float, colsum=None) -> None:
     """colsum (optional f32 [3*h*64]): += column sums of dqkv, i.e. the gradient of the qkv projection's bias."""
     _req_cuda(qkv, out, dout, lse, dqkv)

@@ -142,6 +142,27 @@ def test_attention_fwd_bwd(B, N, h):
     torch.testing.assert_close(cs, ref, rtol=1e-4, atol=1e-3 * max(1.0, float(ref.abs().max())))
 
 
+@pytest.mark.skipif(__import__("os").environ.get("B200_TEST_TC_ATTENTION") != "1",
+                    reason="tcgen05 attention forward is a bring-up kernel (csrc/attention_tc.cu): opt in with B200_TEST_TC_ATTENTION=1")
+@pytest.mark.parametrize("B,N,h", [(3, 197, 6), (5, 37, 2), (2, 256, 3), (2, 130, 2), (1, 16, 1)])
+def test_attention_fwd_tcgen05(B, N, h):
+    """Gate for switching the product path to the tcgen05 forward: same checks as the mma.sync kernel, plus agreement
+    with it (P is rounded before normalisation here, so the two differ by bf16 rounding only)."""
+    D = h * 64
+    qkv = rnd(B * N, 3 * D, dtype=torch.bfloat16, scale=1.0, seed=10)
+    out, ref = (torch.empty(B * N, D, device=dev, dtype=torch.bfloat16) for _ in range(2))
+    lse, lse_ref = (torch.empty(B * h, N, device=dev) for _ in range(2))
+    ops.attention_fwd_tc(qkv, B, N, h, out, lse, 0.125)
+    ops.attention_fwd(qkv, B, N, h, ref, lse_ref, 0.125)
+    q5 = qkv.float().view(B, N, 3, h, 64).permute(2, 0, 3, 1, 4)
+    s = (q5[0] * 0.125) @ q5[1].transpose(-1, -2)
+    o = (s.softmax(-1) @ q5[2]).transpose(1, 2).reshape(B * N, D)
+    torch.testing.assert_close(out.float(), o, rtol=3e-2, atol=3e-2)
+    torch.testing.assert_close(lse.view(B, h, N), torch.logsumexp(s, -1), rtol=1e-2, atol=3e-2)
+    torch.testing.assert_close(out.float(), ref.float(), rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(lse, lse_ref, rtol=1e-5, atol=1e-4)
+
+
 @pytest.mark.parametrize("T,D", [(1000, 384), (77, 128), (300, 1024), (64, 192)])
 def test_layernorm_fwd_bwd(T, D):
     x = rnd(T, D, seed=12, scale=2.0).requires_grad_(True)
