@@ -197,3 +197,20 @@ def test_dinov3_teacher_forward_matches_reference(golden_dir):
     # the rotation must actually matter: without RoPE the patch features move by far more than the tolerance
     sin, cos = D3.rope_sincos(cfg, 14, 6)
     assert sin.shape == (84, 64) and float(sin.abs().max()) > 0.5
+
+
+@pytest.mark.parametrize("name,cfg,seed", [("mlp", R.VIT_TINY, 11), ("swiglu", R.VIT_TINY_SWIGLU, 13)])
+def test_autocast_emulation_tracks_real_bf16_autocast_of_the_reference(golden_dir, name, cfg, seed):
+    """The GPU parity bars compare against the oracle's autocast=True mode.  That emulation is pinned here against the
+    reference modules run under real bf16 autocast (CPU autocast, fixture from tools/make_golden.py): it must agree to
+    about one bf16 ulp of the O(3) LayerNorm outputs and be several times closer than the fp32 mode is."""
+    ref = torch.load(golden_dir / "vit_tiny_autocast_cpu.pt")
+    sd = R.det_vit_state(cfg, seed=seed)
+    xg, _, masks = R.vit_case_inputs()
+    emu = O.vit_forward_features(sd, cfg, xg, masks, autocast=True)
+    f32 = O.vit_forward_features(sd, cfg, xg, masks, autocast=False)
+    d_emu = (emu["patch"][0] - ref[name + "_patch0"]).abs()
+    d_f32 = (f32["patch"][0] - ref[name + "_patch0"]).abs()
+    assert float(d_emu.max()) < 3.2e-2 and float(d_emu.mean()) < 1e-3, (float(d_emu.max()), float(d_emu.mean()))
+    assert float(d_emu.mean()) < 0.4 * float(d_f32.mean())
+    assert float((emu["cls"] - ref[name + "_cls"]).abs().max()) < 3.2e-2

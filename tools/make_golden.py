@@ -176,6 +176,20 @@ def dinov3_case() -> dict:
             "prenorm": o["x_prenorm"]}
 
 
+def vit_autocast_case(m) -> dict:
+    """The reference ViTs under REAL bf16 autocast (torch.autocast("cpu", bfloat16): the same op policy family as the CUDA
+    autocast the training runs under) -- pins the oracle's autocast=True emulation, which the GPU parity bars rely on."""
+    out = {}
+    xg, _, masks = R.vit_case_inputs()
+    for name, cfg, seed in (("mlp", R.VIT_TINY, 11), ("swiglu", R.VIT_TINY_SWIGLU, 13)):
+        vit = build_ref_vit(m, cfg, R.det_vit_state(cfg, seed=seed)).eval()
+        with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+            g = vit(xg, masks, is_training=True)
+        out[name + "_cls"] = g["x_norm_clstoken"].float()
+        out[name + "_patch0"] = g["x_norm_patchtokens"][0].float()
+    return out
+
+
 def head_case(m) -> dict:
     cfg = R.HEAD_TINY
     sd = R.det_head_state(cfg, seed=21)
@@ -319,6 +333,7 @@ def main() -> None:
     torch.save(vit_reg_case(m), OUT / "vit_tiny_reg.pt")
     (OUT / "ref_state_dict_shapes.json").write_text(json.dumps(state_dict_shapes(m), indent=0))
     torch.save(vit_swiglu_case(m), OUT / "vit_tiny_swiglu.pt")
+    torch.save(vit_autocast_case(m), OUT / "vit_tiny_autocast_cpu.pt")
     torch.save(distill_v3_case(), OUT / "distill_v3_loss.pt")
     torch.save(dinov3_case(), OUT / "dinov3_tiny.pt")
     torch.save(head_case(m), OUT / "head_tiny.pt")
