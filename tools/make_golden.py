@@ -249,7 +249,14 @@ def loss_case(m) -> dict:
     return out
 
 
-def step_case(m, center_method: str, separate: bool) -> dict:
+def step_autocast_case(m) -> dict:
+    """Loss terms and logits of the softmax / shared-head step with the reference modules under real bf16 autocast (CPU)."""
+    full = step_case(m, "softmax", False, autocast=True)
+    keep = ("loss", "dino_global_loss", "dino_local_loss", "ibot_loss", "koleo_loss", "t_cls_logits", "s_cls_logits_g")
+    return {k: full[k].float() for k in keep}
+
+
+def step_case(m, center_method: str, separate: bool, autocast: bool = False) -> dict:
     """Full loss evaluation + backward with the reference modules, glue per dinov2.py:259-519."""
     cfg = R.step_config(center_method, separate)
     st = R.det_step_state(cfg, seed=41)
@@ -276,6 +283,8 @@ def step_case(m, center_method: str, separate: bool) -> dict:
     gv = torch.cat(views[:2])
     n_local = len(views) - 2
     g_terms, l_terms = 2, max(n_local * 2, 1)
+    ac = torch.autocast("cpu", dtype=torch.bfloat16, enabled=autocast)
+    ac.__enter__()  # the fit loop wraps training_step in the precision plugin's autocast context
     with torch.no_grad():
         tt = t_vit(gv, None, is_training=True)
         cls = tt["x_norm_clstoken"]
@@ -306,6 +315,7 @@ def step_case(m, center_method: str, separate: bool) -> dict:
                              masks_weight=w)
     koleo = sum(O.koleo_loss(c) for c in s_cls.chunk(2))  # lightly.KoLeoLoss restated (unpinned)
     loss = dino_global + dino_local + ibot + 0.1 * koleo
+    ac.__exit__(None, None, None)
     loss.backward()
     out = {"loss": loss.detach(), "dino_global_loss": dino_global.detach(), "dino_local_loss": dino_local.detach(),
            "ibot_loss": ibot.detach(), "koleo_loss": koleo.detach(),
@@ -334,6 +344,7 @@ def main() -> None:
     (OUT / "ref_state_dict_shapes.json").write_text(json.dumps(state_dict_shapes(m), indent=0))
     torch.save(vit_swiglu_case(m), OUT / "vit_tiny_swiglu.pt")
     torch.save(vit_autocast_case(m), OUT / "vit_tiny_autocast_cpu.pt")
+    torch.save(step_autocast_case(m), OUT / "step_softmax_shared_autocast_cpu.pt")
     torch.save(distill_v3_case(), OUT / "distill_v3_loss.pt")
     torch.save(dinov3_case(), OUT / "dinov3_tiny.pt")
     torch.save(head_case(m), OUT / "head_tiny.pt")
