@@ -31,6 +31,7 @@ from ..._models.dinov2_vit import DinoVisionTransformer, vit_param_shapes
 from .dinov2_head import DINOv2ProjectionHead, head_param_shapes
 from .dinov2_loss import DINOLoss, IBOTPatchLoss, sinkhorn_colterm
 from .scheduler import cosine_schedule, cosine_warmup_factor, linear_warmup_schedule
+from ..._torch_helpers import update_momentum
 from ... import _lib
 from .utils import MaskingGenerator, create_collated_masks, param_group_settings
 
@@ -137,13 +138,78 @@ class _Embedding(nn.Module):
         self.wrapped_model = _Wrapped(model)
 
 
+def _unwrap_backbone(embedding_model: Any) -> nn.Module:
+    """EmbeddingModel(wrapped_model=DINOv2ViTModelWrapper(model)) | wrapper | the ViT itself -> the ViT."""
+    m = embedding_model
+    if hasattr(m, "wrapped_model"):
+        m = m.wrapped_model
+    if hasattr(m, "get_model"):
+        m = m.get_model()
+    return m
+
+
+def backbone_kwargs_from_model(model: nn.Module) -> Dict[str, Any]:
+    """Constructor arguments of a DinoVisionTransformer (the reference's or this package's) read back from the module."""
+    blk0 = model.blocks[0]
+    chunked = bool(getattr(model, "chunked_blocks", False))
+    if chunked:  # BlockChunk(ModuleList): Identity padding then blocks (vision_transformer.py:215-226)
+        blk0 = [b for b in blk0 if not isinstance(b, nn.Identity)][0]
+    sd_names = [n for n, _ in model.named_parameters()]
+    swiglu = any(".mlp.w12." in n for n in sd_names)
+    ls = any(n.endswith("ls1.gamma") for n in sd_names)
+    pe_w = model.patch_embed.proj.weight
+    D = model.embed_dim
+    hidden = dict(model.named_parameters())[[n for n in sd_names if n.endswith("mlp.w12.weight" if swiglu else "mlp.fc1.weight")][0]].shape[0]
+    mlp_ratio = 4.0 if swiglu else hidden / D
+    n_patches = model.pos_embed.shape[1] - 1
+    # per-block stochastic-depth rates: reference Block keeps `sample_drop_ratio`, this package keeps `dpr`
+    if hasattr(model, "dpr"):
+        dpr = list(model.dpr)
+    else:
+        blocks = [b for c in model.blocks for b in (c if chunked else [c]) if not isinstance(b, nn.Identity)]
+        dpr = [float(getattr(b, "sample_drop_ratio", 0.0)) for b in blocks]
+    uniform = len(set(dpr)) == 1 and dpr[0] > 0
+    gamma0 = None
+    if ls:
+        gamma0 = float(dict(model.named_parameters())[[n for n in sd_names if n.endswith("ls1.gamma")][0]].detach().flatten()[0]) or 1e-5
+    return dict(img_size=int(round(n_patches ** 0.5)) * model.patch_size, patch_size=model.patch_size, in_chans=pe_w.shape[1],
+                embed_dim=D, depth=model.n_blocks, num_heads=model.num_heads, mlp_ratio=mlp_ratio,
+                drop_path_rate=max(dpr) if dpr else 0.0, drop_path_uniform=uniform, init_values=gamma0,
+                ffn_layer="swiglu" if swiglu else "mlp", num_register_tokens=model.num_register_tokens,
+                interpolate_antialias=model.interpolate_antialias, interpolate_offset=model.interpolate_offset)
+
+
+def _unchunk(name: str) -> str:
+    """`blocks.{chunk}.{i}.x` (block_chunks > 0 checkpoints) -> `blocks.{i}.x`."""
+    parts = name.split(".")
+    for j in range(len(parts) - 2):
+        if parts[j] == "blocks" and parts[j + 1].isdigit() and parts[j + 2].isdigit():
+            return ".".join(parts[:j + 1] + parts[j + 2:])
+    return name
+
+
 class DINOv2(nn.Module):
-    def __init__(self, method_args: DINOv2Args, optimizer_args: DINOv2AdamWViTArgs, model_kwargs: Dict[str, Any],
-                 global_batch_size: int, num_input_channels: int = 3, max_steps: int = 125_000,
-                 device: str = "cuda") -> None:
-        """model_kwargs: DinoVisionTransformer constructor arguments (embed_dim, depth, num_heads, patch_size,
-        init_values, drop_path_rate, num_register_tokens, ...) -- what `dinov2/vits14-noreg` etc. resolve to."""
+    def __init__(self, method_args: DINOv2Args, optimizer_args: DINOv2AdamWViTArgs, embedding_model: Any = None,
+                 global_batch_size: int = 1024, num_input_channels: int = 3, *, model_kwargs: Optional[Dict[str, Any]] = None,
+                 max_steps: int = 125_000, device: str = "cuda") -> None:
+        """Same leading arguments as the reference (LT/_methods/dinov2/dinov2.py:179-186).  `embedding_model` is either
+          * a pre-built backbone -- the reference's EmbeddingModel / DINOv2ViTModelWrapper / DinoVisionTransformer or this
+            package's DinoVisionTransformer: its architecture is read back and its weights initialise teacher and student
+            (the reference deep-copies the teacher into the student, :197-198), or
+          * a dict of DinoVisionTransformer constructor arguments (embed_dim, depth, num_heads, patch_size, init_values,
+            drop_path_rate, num_register_tokens, ...; what `dinov2/vits14-noreg` etc. resolve to); `model_kwargs=` is
+            the keyword spelling of the same."""
         super().__init__()
+        init_state = None
+        if model_kwargs is None:
+            if isinstance(embedding_model, dict):
+                model_kwargs = embedding_model
+            elif embedding_model is not None:
+                bb = _unwrap_backbone(embedding_model)
+                model_kwargs = backbone_kwargs_from_model(bb)
+                init_state = {_unchunk(k): v.detach() for k, v in bb.state_dict().items()}
+            else:
+                raise ValueError("DINOv2 needs an embedding_model (module) or model_kwargs (dict)")
         if method_args.batch_norm:
             raise NotImplementedError("batch_norm heads are not implemented on the B200 path")
         self.method_args = method_args
@@ -193,7 +259,13 @@ class DINOv2(nn.Module):
         t_vit, t_dino, t_ibot = build(self.t_arena, False)
         # student = deepcopy(teacher) in the reference (dinov2.py:197-198); heads are initialised independently
         off, n = self.s_arena.offsets["dino_head.mlp.0.weight"]
+        if init_state is not None:
+            for k, v in init_state.items():
+                if "backbone." + k in self.t_arena.offsets:
+                    self.t_arena.p("backbone." + k).copy_(v.to(device, torch.float32).view(self.t_arena.shapes["backbone." + k]))
+            self.t_arena.bf16_valid = False
         self.s_arena.fp32[:off].copy_(self.t_arena.fp32[:off])
+        self.s_arena.bf16_valid = False
         self.teacher_embedding_model = _Embedding(t_vit)
         self.student_embedding_model = _Embedding(s_vit)
         self.teacher_head = DINOv2Head(t_dino, t_ibot)
@@ -202,11 +274,25 @@ class DINOv2(nn.Module):
         self.dino_loss = DINOLoss(a.output_dim, a.student_temp, a.center_momentum).to(device)
         self.ibot_loss = IBOTPatchLoss(a.output_dim, a.student_temp, a.center_momentum).to(device)
         self._opt_step = 0
+        self._optimizer: Optional["FusedAdamWEMA"] = None
+        self._scheduler: Optional["CosineWarmupFactor"] = None
+        self._ema_done = False
+        self.logged: Dict[str, Any] = {}
+        self._last_result: Optional[TrainingStepResult] = None
         self._build_optimizer_tables()
+        # weights written through load_state_dict() land in the fp32 arenas: the bf16 GEMM shadows of BOTH sides are stale
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate_shadows())
+        # KoLeo runs one CTA per crop group with the group's features in shared memory (csrc/loss.cu)
+        D_ = s_vit.embed_dim
+        self._koleo_max_batch = (220 * 1024 // 4) // (2 * D_ + 3)
         self._grad_ready = False
         self._seg_cache: Dict[Tuple[int, int, int], Tensor] = {}
         self._static: Optional[Dict[str, Any]] = None
         self.use_cuda_graph = False
+
+    def _invalidate_shadows(self) -> None:
+        self.s_arena.bf16_valid = False
+        self.t_arena.bf16_valid = False
 
     # ------------------------------------------------------------------ accessors
     @property
@@ -460,6 +546,9 @@ class DINOv2(nn.Module):
         n_crops, B, Ng, lcls_rows = st["n_crops"], st["B"], st["Ng"], st["lcls_rows"]
         # KoLeo on the pre-head global cls tokens (:377-380): forward value + gradient (+=) into dxn_g
         koleo = torch.zeros(2, device=dev, dtype=f32)
+        if B > self._koleo_max_batch or B < 2:
+            raise _lib.B200Error(f"KoLeo kernel: per-GPU batch {B} outside [2, {self._koleo_max_batch}] for embed_dim {D} "
+                                 "(one CTA per crop group keeps the group's features in shared memory; csrc/loss.cu)")
         # two CTAs of pure latency (~160 us): forked onto a side stream (a parallel branch of the captured graph) so it
         # overlaps the local-crop backward; its += into dxn_g is only needed by the global-crop backward below
         main = torch.cuda.current_stream()
@@ -569,13 +658,91 @@ class DINOv2(nn.Module):
         self.ibot_loss._launch_reduce(outs["ibot_center_sum"], 1)
         return self._result(outs)
 
-    # ------------------------------------------------------------------ optimizer (+ hooks :588-660) in one sweep
-    def optimizer_step(self) -> None:
-        """all-reduce(grad) -> clip_grad_norm_(3.0) -> AdamW (per-chunk lr/wd, freezes) -> EMA teacher -> bf16 shadows."""
-        if not self._grad_ready:
-            raise RuntimeError("optimizer_step() called without gradients; call training_step_impl first")
+    # ------------------------------------------------------------------ Method surface (LT/_methods/method.py:131-148)
+    def training_step(self, batch: Dict[str, Any], batch_idx: int = 0) -> Tensor:
+        """Method.training_step: run the step, log `train_loss` + the log_dict with sync_dist=True semantics (cross-rank
+        mean; ONE tiny all-reduce for all five scalars), return the loss."""
+        if self.use_cuda_graph and self.method_args.center_method == "softmax":
+            res = self._graphed_step(batch)
+        else:
+            res = self.training_step_impl(batch, batch_idx)
+        self._last_result = res
+        names = ["train_loss"] + list(res.log_dict.keys())
+        vals = torch.stack([res.loss.reshape(())] + [v.reshape(()) for v in res.log_dict.values()])
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            vals = vals / dist.get_world_size()
+            dist.all_reduce(vals)
+        for k, v in zip(names, vals.unbind(0)):
+            self.log(k, v, sync_dist=False)
+        return res.loss
+
+    def log(self, name: str, value: Any, **kwargs: Any) -> None:
+        """Stand-in for LightningModule.log: keeps the latest value (a device scalar; no host sync) in `self.logged`."""
+        self.logged[name] = value
+
+    def log_dict(self, dictionary: Dict[str, Any], **kwargs: Any) -> None:
+        for k, v in dictionary.items():
+            self.log(k, v, **kwargs)
+
+    def trainable_modules(self) -> List[nn.Module]:
+        """LT/_methods/dinov2/dinov2.py:538-548."""
+        return [self.student_embedding_model.wrapped_model.get_model(), self.student_head]
+
+    # ------------------------------------------------------------------ optimizer + hooks (:550-660)
+    def configure_optimizers(self):
+        """([optimizer], [{"scheduler", "interval": "step"}]) like the reference (:550-586).  The optimizer is a shim over
+        the fused sweep (clip + AdamW + EMA teacher + bf16 shadows in one kernel); its param_groups list one group per
+        distinct (lr multiplier, weight-decay switch, freeze class), named after the group's first parameter as
+        get_fused_param_groups does (utils.py:253-273)."""
+        if self._optimizer is None:
+            self._optimizer = FusedAdamWEMA(self)
+            self._scheduler = CosineWarmupFactor(self)
+        return [self._optimizer], [{"scheduler": self._scheduler, "interval": "step"}]
+
+    def configure_gradient_clipping(self, optimizer: "FusedAdamWEMA", gradient_clip_val: Optional[float] = None,
+                                    gradient_clip_algorithm: Optional[str] = None) -> None:
+        """:588-598 -- clip_grad_norm_(method_args.gradient_clip_val); applied inside the sweep from the summed squares."""
+        optimizer.clip_val = self.method_args.gradient_clip_val
+
+    def on_before_optimizer_step(self, optimizer: "FusedAdamWEMA", *args: Any) -> None:
+        """:600-639 -- cosine weight-decay schedule, backbone / last-layer lr freeze for the step about to run."""
         a = self.method_args
         step = self.trainer.global_step
+        optimizer.weight_decay = cosine_schedule(step, self.trainer.estimated_stepping_batches, self.weight_decay_start,
+                                                 a.weight_decay_end)
+        optimizer.freeze_backbone = step < a.student_freeze_backbone_steps
+        optimizer.freeze_last_layer = step < a.student_freeze_last_layer_steps
+        optimizer.sync_param_groups()
+
+    def on_train_batch_end(self, outputs: Any = None, batch: Any = None, batch_idx: int = 0) -> None:
+        """:641-660 -- EMA teacher update with momentum cosine_schedule(trainer.global_step) (Lightning has already
+        incremented global_step when this hook runs).  The fused sweep normally did it with that same momentum
+        (`optimizer.step()`); this hook only does the work if the sweep ran without the EMA part."""
+        if self._ema_done:
+            self._ema_done = False
+            return
+        m = cosine_schedule(self.trainer.global_step, self.trainer.estimated_stepping_batches,
+                            self.method_args.momentum_start, self.method_args.momentum_end)
+        update_momentum(self.student_embedding_model, self.teacher_embedding_model, m)
+        update_momentum(self.student_head, self.teacher_head, m)
+
+    def optimizer_step(self) -> None:
+        """What Lightning's automatic optimisation does after backward, in its hook order: on_before_optimizer_step ->
+        configure_gradient_clipping -> optimizer.step -> scheduler.step -> global_step += 1 -> on_train_batch_end."""
+        if not self._grad_ready:
+            raise RuntimeError("optimizer_step() called without gradients; call training_step_impl first")
+        (opt,), (sch,) = self.configure_optimizers()
+        self.on_before_optimizer_step(opt)
+        self.configure_gradient_clipping(opt)
+        opt.step()
+        sch["scheduler"].step()
+        self.trainer.global_step += 1
+        self.on_train_batch_end(None, None, 0)
+
+    def _fused_sweep(self, opt: "FusedAdamWEMA", lr: float, fuse_ema: bool = True) -> None:
+        """all-reduce(grad) -> deterministic sum of squares -> ONE sweep: clip + AdamW (per-chunk lr/wd, freezes) + EMA
+        teacher + bf16 shadows of student and teacher."""
+        a = self.method_args
         max_steps = self.trainer.estimated_stepping_batches
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         if world > 1:  # DDP gradient all-reduce (sum); mean applied via grad_scale
@@ -587,28 +754,47 @@ class DINOv2(nn.Module):
                 dist.all_reduce(self.s_arena.grad)
         ops.fill_f32(self.gradnorm_sq, 0.0)
         ops.sumsq(self.s_arena.grad, self.gradnorm_sq)
-        weight_decay = cosine_schedule(step, max_steps, self.weight_decay_start, a.weight_decay_end)
-        warmup = min(max_steps - 1, a.warmup_steps)
-        lr = self.base_lr * cosine_warmup_factor(step, int(warmup), int(max_steps), a.min_lr / self.base_lr)
-        momentum = cosine_schedule(step, max_steps, a.momentum_start, a.momentum_end)
+        # on_train_batch_end runs after Lightning has incremented global_step: the momentum index is step + 1
+        momentum = cosine_schedule(self.trainer.global_step + 1, max_steps, a.momentum_start, a.momentum_end)
         self._opt_step += 1
         args = ops.AdamWArgs()
         sa, ta = self.s_arena, self.t_arena
-        args.p, args.g, args.m, args.v, args.t = (sa.fp32.data_ptr(), sa.grad.data_ptr(), sa.exp_avg.data_ptr(),
-                                                  sa.exp_avg_sq.data_ptr(), ta.fp32.data_ptr())
-        args.p_bf16, args.t_bf16 = sa.bf16.data_ptr(), ta.bf16.data_ptr()
+        args.p, args.g, args.m, args.v = sa.fp32.data_ptr(), sa.grad.data_ptr(), sa.exp_avg.data_ptr(), sa.exp_avg_sq.data_ptr()
+        args.p_bf16 = sa.bf16.data_ptr()
+        if fuse_ema:
+            args.t, args.t_bf16 = ta.fp32.data_ptr(), ta.bf16.data_ptr()
         args.n, args.chunk = sa.total, CHUNK
         args.lr_scale, args.wd_scale, args.flags = self.lr_table.data_ptr(), self.wd_table.data_ptr(), self.flag_table.data_ptr()
-        args.lr, args.wd = lr, weight_decay
+        args.lr, args.wd = lr, opt.weight_decay
         args.beta1, args.beta2, args.eps = self.optimizer_args.betas[0], self.optimizer_args.betas[1], self.optimizer_args.eps
         args.step, args.ema_m = self._opt_step, momentum
-        args.gradnorm_sq, args.max_norm, args.grad_scale = self.gradnorm_sq.data_ptr(), a.gradient_clip_val, 1.0 / world
-        args.freeze_last_layer = int(step < a.student_freeze_last_layer_steps)
-        args.freeze_backbone = int(step < a.student_freeze_backbone_steps)
+        args.gradnorm_sq = self.gradnorm_sq.data_ptr() if opt.clip_val is not None else None
+        args.max_norm = float(opt.clip_val or 0.0)
+        args.grad_scale = 1.0 / world
+        args.freeze_last_layer = int(opt.freeze_last_layer)
+        args.freeze_backbone = int(opt.freeze_backbone)
         ops.adamw_ema(args)
-        sa.bf16_valid = ta.bf16_valid = True
+        sa.bf16_valid = True
+        if fuse_ema:
+            ta.bf16_valid = True
+            self._ema_done = True
         self._grad_ready = False
-        self.trainer.global_step += 1
+
+    # ------------------------------------------------------------------ checkpoint (Lightning layout)
+    def checkpoint(self) -> Dict[str, Any]:
+        """{"state_dict", "optimizer_states", "lr_schedulers", "global_step"}: the keys of a Lightning checkpoint that
+        this path owns.  `state_dict` carries the reference's parameter / buffer names (loads into the reference module)."""
+        (opt,), (sch,) = self.configure_optimizers()
+        return {"state_dict": {k: v.detach().clone() for k, v in self.state_dict().items()},
+                "optimizer_states": [opt.state_dict()], "lr_schedulers": [sch["scheduler"].state_dict()],
+                "global_step": self.trainer.global_step}
+
+    def load_checkpoint(self, ckpt: Dict[str, Any]) -> None:
+        (opt,), (sch,) = self.configure_optimizers()
+        self.load_state_dict(ckpt["state_dict"])
+        opt.load_state_dict(ckpt["optimizer_states"][0])
+        sch["scheduler"].load_state_dict(ckpt["lr_schedulers"][0])
+        self.trainer.global_step = int(ckpt["global_step"])
 
     @staticmethod
     def loss_for_autograd(result: TrainingStepResult) -> Tensor:
@@ -625,3 +811,93 @@ class DINOv2(nn.Module):
             res = self.training_step_impl(batch, 0)
         self.optimizer_step()
         return res
+
+
+class FusedAdamWEMA:
+    """Optimizer shim handed to the trainer by DINOv2.configure_optimizers: `step()` runs the fused sweep over the flat
+    arenas.  `param_groups` mirror what get_optimizer_with_decay + get_fused_param_groups build (utils.py:191-273) so that
+    hooks / loggers that read or edit lr / weight_decay by group name keep working; the sweep itself reads the per-chunk
+    tables.  State (exp_avg, exp_avg_sq, step) round-trips through state_dict() like torch.optim.AdamW's."""
+
+    def __init__(self, method: DINOv2) -> None:
+        self.method = method
+        self.clip_val: Optional[float] = None
+        self.weight_decay = method.weight_decay_start
+        self.freeze_backbone = False
+        self.freeze_last_layer = False
+        self.defaults = dict(lr=method.base_lr, betas=method.optimizer_args.betas, eps=method.optimizer_args.eps,
+                             weight_decay=method.optimizer_args.weight_decay)
+        groups: Dict[Tuple[float, float, bool, bool], Dict[str, Any]] = {}
+        nl = method.s_vit.n_blocks
+        a = method.method_args
+        for full in method.s_arena.names():
+            is_bb = full.startswith("backbone.")
+            st = param_group_settings(full[len("backbone."):] if is_bb else full, is_bb, nl, a.layerwise_decay,
+                                      a.patch_embed_lr_multiplier)
+            key = (st["lr_scale"], st["wd_scale"], bool(st["last_layer"]), not is_bb)
+            g = groups.get(key)
+            if g is None:
+                # reference group names: parameter names inside trainable_modules() (the ViT itself, then DINOv2Head)
+                g = groups[key] = {"name": full[len("backbone."):] if is_bb else full, "params": [], "lr_scale": st["lr_scale"],
+                                   "wd_scale": st["wd_scale"], "lr": method.base_lr * st["lr_scale"],
+                                   "weight_decay": self.weight_decay * st["wd_scale"], "is_last_layer": bool(st["last_layer"]),
+                                   "is_head": not is_bb}
+            g["params"].append(method.s_arena.p(full))
+        self.param_groups: List[Dict[str, Any]] = list(groups.values())
+
+    def sync_param_groups(self, lr: Optional[float] = None) -> None:
+        lr = self.method.base_lr * self.method._scheduler.factor() if lr is None else lr
+        for g in self.param_groups:
+            frozen = (self.freeze_last_layer and g["is_last_layer"]) or (self.freeze_backbone and not g["is_head"])
+            g["lr"] = 0.0 if frozen else lr * g["lr_scale"]
+            g["weight_decay"] = self.weight_decay * g["wd_scale"]
+
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        """Gradients live in the flat arena and are zeroed by the step's first kernel."""
+
+    def step(self, closure: Any = None) -> None:
+        if closure is not None:
+            closure()
+        m = self.method
+        if not m._grad_ready:
+            raise RuntimeError("optimizer.step() without gradients; call training_step / training_step_impl first")
+        m._fused_sweep(self, m.base_lr * m._scheduler.factor())
+
+    def state_dict(self) -> Dict[str, Any]:
+        sa = self.method.s_arena
+        return {"exp_avg": sa.exp_avg.detach().clone(), "exp_avg_sq": sa.exp_avg_sq.detach().clone(),
+                "step": self.method._opt_step,
+                "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
+
+    def load_state_dict(self, sd: Dict[str, Any]) -> None:
+        sa = self.method.s_arena
+        sa.exp_avg.copy_(sd["exp_avg"])
+        sa.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.method._opt_step = int(sd["step"])
+
+
+class CosineWarmupFactor:
+    """lightly's CosineWarmupScheduler as the reference configures it (:576-583): `last_epoch` counts scheduler steps."""
+
+    def __init__(self, method: DINOv2) -> None:
+        self.method = method
+        self.last_epoch = 0
+
+    def factor(self) -> float:
+        m = self.method
+        max_steps = int(m.trainer.estimated_stepping_batches)
+        warmup = int(min(max_steps - 1, m.method_args.warmup_steps))
+        return cosine_warmup_factor(self.last_epoch, warmup, max_steps, m.method_args.min_lr / m.base_lr)
+
+    def step(self) -> None:
+        self.last_epoch += 1
+
+    def get_last_lr(self) -> List[float]:
+        f = self.factor()
+        return [self.method.base_lr * f * g["lr_scale"] for g in self.method._optimizer.param_groups]
+
+    def state_dict(self) -> Dict[str, Any]:
+        return {"last_epoch": self.last_epoch}
+
+    def load_state_dict(self, sd: Dict[str, Any]) -> None:
+        self.last_epoch = int(sd["last_epoch"])

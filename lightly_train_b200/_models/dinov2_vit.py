@@ -248,10 +248,20 @@ class DinoVisionTransformer(nn.Module):
         ctx.dims = (Bc, Np, R, N, T, H, Wimg)
         E = lambda *s, dt=bf: torch.empty(*s, device=dev, dtype=dt)  # noqa: E731
 
-        cols = E(Bc * Np, Cin * p * p)
+        # conv-as-GEMM K = Cin*p*p; TMA needs 16-byte row pitches, so K is padded to a multiple of 8 (patch 14: 588 -> 592)
+        # with zero columns in `cols` and zero columns in a padded bf16 copy of the weight shadow
+        Kc = Cin * p * p
+        Kp = (Kc + 7) // 8 * 8
+        if Kp != Kc:
+            cols = torch.zeros(Bc * Np, Kp, device=dev, dtype=bf)
+            wpe = torch.zeros(D, Kp, device=dev, dtype=bf)
+            wpe[:, :Kc].copy_(self._W("patch_embed.proj.weight").view(D, Kc))
+        else:
+            cols = E(Bc * Np, Kc)
+            wpe = self._W("patch_embed.proj.weight").view(D, Kc)
         ops.im2col(x.contiguous(), p, cols)
         tok = E(Bc * Np, D)
-        ops.gemm(cols, self._W("patch_embed.proj.weight").view(D, -1), tok, bias=self._P("patch_embed.proj.bias"))
+        ops.gemm(cols, wpe, tok, bias=self._P("patch_embed.proj.bias"))
         pos, interp = self._pos_for(Np, H, Wimg)
         masks_u8 = masks.to(torch.uint8).contiguous() if masks is not None else None
         xs = E(Bc, N, D, dt=f32)
@@ -408,8 +418,13 @@ class DinoVisionTransformer(nn.Module):
             ops.small_matmul(self._pos_operator(w0, h0), dpos[1:], gpos[1:], a_trans=True, accumulate=True)
             gpos[0].add_(dpos[0])
         ops.col_reduce(dtok, self._G("patch_embed.proj.bias"))
-        ops.gemm(dtok, ctx.cols, self._G("patch_embed.proj.weight").view(D, -1), a_mn=True, b_mn=True,
-                 epi=ops.EPI_F32_ATOMIC, splits=0)
+        gw = self._G("patch_embed.proj.weight").view(D, -1)
+        if ctx.cols.shape[1] != gw.shape[1]:  # padded K (patch 14): wgrad into a padded scratch, fold the real columns back
+            gpad = torch.zeros(D, ctx.cols.shape[1], device=dev, dtype=f32)
+            ops.gemm(dtok, ctx.cols, gpad, a_mn=True, b_mn=True, epi=ops.EPI_F32_ATOMIC, splits=0)
+            gw.add_(gpad[:, :gw.shape[1]])
+        else:
+            ops.gemm(dtok, ctx.cols, gw, a_mn=True, b_mn=True, epi=ops.EPI_F32_ATOMIC, splits=0)
 
     # ------------------------------------------------------------------ reference-facing API
     @torch.no_grad()

@@ -36,8 +36,18 @@ __global__ void __launch_bounds__(256) ema_kernel(float* __restrict__ t, const f
   }
 }
 
+// Sum of squares, DETERMINISTIC: every block writes its partial sum to a fixed slot, the last block to finish (ticket
+// counter) adds the slots in index order with a fixed reduction tree.  Data-parallel replicas compute the gradient norm
+// from bit-identical all-reduced gradients, so the clip coefficient -- and therefore the weights -- stay bit-identical
+// across ranks (a float atomicAdd per block would make the sum depend on block retirement order).
+// One launch in flight per device (the scratch below is per device, not per stream): the optimizer sweep is the only user.
+static constexpr int SUMSQ_MAX_BLOCKS = 4096;
+__device__ float g_sumsq_partials[SUMSQ_MAX_BLOCKS];
+__device__ unsigned int g_sumsq_ticket = 0;
+
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
   __shared__ float red[32];
+  __shared__ bool last;
   float acc = 0.f;
   const long long stride = (long long)gridDim.x * blockDim.x * 4;
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
@@ -49,7 +59,21 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x,
     }
   }
   acc = block_sum(acc, red);
-  if (threadIdx.x == 0) atomicAdd(out, acc);
+  if (threadIdx.x == 0) {
+    g_sumsq_partials[blockIdx.x] = acc;
+    __threadfence();
+    last = atomicAdd(&g_sumsq_ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float tot = 0.f;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) tot += __ldcg(&g_sumsq_partials[i]);
+  tot = block_sum(tot, red);
+  if (threadIdx.x == 0) {
+    *out += tot;
+    g_sumsq_ticket = 0;
+  }
 }
 
 struct AdamDev {
@@ -142,7 +166,9 @@ extern "C" int b200_ema(float* teacher, const float* student, long long n, float
 
 extern "C" int b200_sumsq(const float* x, long long n, float* out, void* stream) {
   if (!x || !out || n <= 0 || ((uintptr_t)x & 15)) return B200_ERR_INVALID_ARG;
-  sumsq_kernel<<<sweep_grid(n), 256, 0, (cudaStream_t)stream>>>(x, n, out);
+  int grid = sweep_grid(n);
+  if (grid > SUMSQ_MAX_BLOCKS) grid = SUMSQ_MAX_BLOCKS;
+  sumsq_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, out);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
