@@ -277,6 +277,7 @@ class DINOv2(nn.Module):
         self._optimizer: Optional["FusedAdamWEMA"] = None
         self._scheduler: Optional["CosineWarmupFactor"] = None
         self._ema_done = False
+        self.debug_taps: Optional[Dict[str, Any]] = None
         self.logged: Dict[str, Any] = {}
         self._last_result: Optional[TrainingStepResult] = None
         self._build_optimizer_tables()
@@ -517,6 +518,8 @@ class DINOv2(nn.Module):
         seg = self._segments(n_crops, nd, Rs)
         loss_terms = torch.zeros(3, device=dev, dtype=f32)
         ops.segment_sum(loss_rows, seg, loss_terms)
+        if self.debug_taps is not None:  # tests / bench parity read the head outputs (bf16 logits) of this step
+            self.debug_taps.update(t_logits=t_logits.clone(), s_logits=s_logits.clone(), n_crops=n_crops, n_local_rows=LB, n_masked=M)
         del s_logits, t_logits
 
         # ---------------- head backward -> gradient wrt the backbone outputs

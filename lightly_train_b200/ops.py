@@ -16,6 +16,19 @@ from ._lib import (EPI_BF16, EPI_BIAS_GELU, EPI_BIAS_GELU_DG, EPI_DGELU, EPI_F32
 
 GEMM_PROFILE = None  # bench.py sets this to a list: (flops, start_event, end_event) per b200_gemm launch
 GEMM_PROFILE_KEYS = []
+KERNEL_PROFILE = None  # bench.py sets this to a list: (kernel name, algorithmic bytes, start_event, end_event) per launch
+
+
+def _timed(name: str, nbytes: float, launch) -> None:
+    """Run `launch()`; when bench.py profiles, bracket it with a CUDA-event pair on the launch stream."""
+    if KERNEL_PROFILE is None:
+        launch()
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    launch()
+    e1.record()
+    KERNEL_PROFILE.append((name, float(nbytes), e0, e1))
 
 
 def _stream() -> int:
@@ -248,8 +261,8 @@ def fill_f32(x, v: float = 0.0) -> None:
 
 def row_lse(x, colterm, scale: float, rowterm, scale_dev=None) -> None:
     R, K = x.shape
-    check(_L().b200_row_lse(x.data_ptr(), x.stride(0), R, K, _ptr(colterm), scale, _ptr(scale_dev), rowterm.data_ptr(),
-                            _stream()), "b200_row_lse")
+    _timed("row_lse", 2.0 * R * K, lambda: check(_L().b200_row_lse(x.data_ptr(), x.stride(0), R, K, _ptr(colterm), scale,
+                                                                   _ptr(scale_dev), rowterm.data_ptr(), _stream()), "b200_row_lse"))
 
 
 def col_reduce(x, out, rowvec=None, scale: float = 1.0, mode: int = 0, scale_dev=None) -> None:
@@ -265,10 +278,10 @@ def vec_op(y, x, a: float, b: float, op: int, a_dev=None) -> None:
 def dino_ce(s, t, colterm, t_rowterm, t_idx0, t_idx1, weight, s_scale: float, t_scale: float, loss_rows, ds=None,
             gscale: float = 1.0, t_scale_dev=None) -> None:
     Rs, K = s.shape
-    check(_L().b200_dino_ce(s.data_ptr(), s.stride(0), Rs, K, t.data_ptr(), t.stride(0), _ptr(colterm),
-                            t_rowterm.data_ptr(), t_idx0.data_ptr(), _ptr(t_idx1), _ptr(weight), s_scale, t_scale, _ptr(t_scale_dev), gscale,
-                            loss_rows.data_ptr(), _ptr(ds), ds.stride(0) if ds is not None else 0, _stream()),
-          "b200_dino_ce")
+    _timed("dino_ce", (4.0 if ds is not None else 2.0) * Rs * K, lambda: check(
+        _L().b200_dino_ce(s.data_ptr(), s.stride(0), Rs, K, t.data_ptr(), t.stride(0), _ptr(colterm),
+                          t_rowterm.data_ptr(), t_idx0.data_ptr(), _ptr(t_idx1), _ptr(weight), s_scale, t_scale, _ptr(t_scale_dev), gscale,
+                          loss_rows.data_ptr(), _ptr(ds), ds.stride(0) if ds is not None else 0, _stream()), "b200_dino_ce"))
 
 
 def segment_sum(x, offsets_i32, out, scale=None) -> None:
@@ -290,8 +303,9 @@ def ema(teacher_flat, student_flat, m: float, teacher_bf16=None) -> None:
 
 
 def sumsq(x, out) -> None:
-    check(_L().b200_sumsq(x.data_ptr(), x.numel(), out.data_ptr(), _stream()), "b200_sumsq")
+    _timed("sumsq", 4.0 * x.numel(), lambda: check(_L().b200_sumsq(x.data_ptr(), x.numel(), out.data_ptr(), _stream()), "b200_sumsq"))
 
 
 def adamw_ema(args: AdamWArgs) -> None:
-    check(_L().b200_adamw_ema(C.byref(args), _stream()), "b200_adamw_ema")
+    nb = float(args.n) * ((20.0 + 20.0) if args.t else (16.0 + 14.0))
+    _timed("adamw_ema", nb, lambda: check(_L().b200_adamw_ema(C.byref(args), _stream()), "b200_adamw_ema"))

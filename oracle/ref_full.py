@@ -315,8 +315,7 @@ def build_dinov2(vit_kwargs: Dict[str, Any], method_overrides: Dict[str, Any], g
                num_input_channels=vit_kwargs.get("in_chans", 3))
     m.trainer = _Trainer(max_steps)
     if activation_checkpointing:
-        m.student_embedding_model.wrapped_model.set_activation_checkpointing(True) if hasattr(
-            m.student_embedding_model.wrapped_model, "set_activation_checkpointing") else None
+        m.student_embedding_model.wrapped_model.set_activation_checkpointing(True)
     m.to(device)
     (opt,), (sched,) = m.configure_optimizers()
     return m, opt, sched["scheduler"]

@@ -1,0 +1,202 @@
+"""-m gpu: the mirror driven the way Lightning drives the reference Method (LT/_methods/method.py:131-148,
+LT/_methods/dinov2/dinov2.py:550-660): a plain python loop standing in for the trainer calls the reference's hook names
+in automatic-optimisation order.  Also: checkpoint round trip into the reference's own modules, update_momentum with the
+reference signature, and the stochastic-depth code paths that draw their own random numbers."""
+import random
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():
+    pytest.skip("needs CUDA", allow_module_level=True)
+
+from lightly_train_b200._methods.dinov2.dinov2 import DINOv2, DINOv2AdamWViTArgs, DINOv2Args  # noqa: E402
+from lightly_train_b200._models.dinov2_vit import DinoVisionTransformer  # noqa: E402
+from lightly_train_b200._torch_helpers import update_momentum  # noqa: E402
+from oracle import dinov2_oracle as O  # noqa: E402
+from oracle import ref_full  # noqa: E402
+from tests import ref_cases as RC  # noqa: E402
+from tests.golden import recipes as R  # noqa: E402
+
+dev = "cuda"
+
+
+def _tiny_method(max_steps=10, **over) -> DINOv2:
+    cfg = R.step_config("softmax", False)
+    st = R.det_step_state(cfg, seed=41)
+    margs = DINOv2Args(hidden_dim=cfg.head.hidden_dim, dino_bottleneck_dim=cfg.head.bottleneck_dim, output_dim=cfg.head.out_dim,
+                       warmup_steps=2, student_freeze_last_layer_steps=1, **over)
+    mk = dict(img_size=224, patch_size=16, embed_dim=cfg.vit.embed_dim, depth=cfg.vit.depth, num_heads=cfg.vit.num_heads,
+              init_values=cfg.vit.init_values, drop_path_rate=0.0)
+    m = DINOv2(margs, DINOv2AdamWViTArgs(), mk, global_batch_size=1024, max_steps=max_steps, device=dev)
+    m.s_arena.load_from(st["student"]); m.t_arena.load_from(st["teacher"])
+    m.dino_loss.center.copy_(st["centers"]["dino"]); m.ibot_loss.center.copy_(st["centers"]["ibot"])
+    return m
+
+
+def _lightning_like_fit(m: DINOv2, batches, steps: int):
+    """What pytorch_lightning's fit loop does per batch under automatic optimisation, with the hook names the reference
+    method implements; `loss.backward()` goes through the autograd bridge (gradients are already in param.grad)."""
+    (opt,), (sch,) = m.configure_optimizers()
+    losses = []
+    for i in range(steps):
+        batch = batches[i % len(batches)]
+        opt.zero_grad()
+        loss = m.training_step(batch, i)                     # Method.training_step: step + log / log_dict(sync_dist)
+        DINOv2.loss_for_autograd(m._last_result).backward()  # trainer-side backward: a no-op on the bridge leaf
+        m.on_before_optimizer_step(opt)
+        m.configure_gradient_clipping(opt, gradient_clip_val=None, gradient_clip_algorithm=None)
+        opt.step()
+        sch["scheduler"].step()
+        m.trainer.global_step += 1
+        m.on_train_batch_end(loss, batch, i)
+        losses.append(float(loss))
+    return losses
+
+
+def test_lightning_shaped_loop_equals_train_step():
+    cfg = R.step_config("softmax", False)
+    views, masks, idx, w = R.step_case_inputs(cfg)
+    batch = {"views": [v.to(dev) for v in views], "masks": {"collated_masks": masks, "mask_indices_list": idx, "masks_weight": w}}
+    a, b = _tiny_method(), _tiny_method()
+    la = _lightning_like_fit(a, [batch], 3)
+    lb = [float(b.train_step(batch).loss) for _ in range(3)]
+    torch.cuda.synchronize()
+    assert la == pytest.approx(lb, rel=1e-5)
+    # fp32 split-K atomics reorder the wgrad sums run to run: weights agree to a few ulps of the lr-sized updates
+    assert (a.s_arena.fp32 - b.s_arena.fp32).abs().max().item() < 1e-5
+    assert (a.t_arena.fp32 - b.t_arena.fp32).abs().max().item() < 1e-6
+    assert a.trainer.global_step == b.trainer.global_step == 3
+    for k in ("train_loss", "train_loss/dino_global_loss", "train_loss/dino_local_loss", "train_loss/ibot_loss", "train_loss/koleo_loss"):
+        assert k in a.logged and torch.isfinite(a.logged[k]).item()
+    # hooks visible through the optimizer shim like through a torch optimizer
+    (opt,), (sch,) = a.configure_optimizers()
+    names = [g["name"] for g in opt.param_groups]
+    assert "cls_token" in names and any("last_layer" in n for n in names)
+    assert len(sch["scheduler"].get_last_lr()) == len(opt.param_groups)
+
+
+def test_ema_hook_order_and_unfused_update_momentum():
+    """The fused sweep applies the EMA with the momentum of global_step + 1 (Lightning increments before
+    on_train_batch_end); running the sweep without its EMA part and then the reference-signature update_momentum in the
+    hook must give the same teacher."""
+    cfg = R.step_config("softmax", False)
+    views, masks, idx, w = R.step_case_inputs(cfg)
+    batch = {"views": [v.to(dev) for v in views], "masks": {"collated_masks": masks, "mask_indices_list": idx, "masks_weight": w}}
+    a, b = _tiny_method(), _tiny_method()
+    t_before = a.t_arena.fp32.clone()
+    a.train_step(batch)
+    # b: same step, EMA through the hook
+    b.training_step_impl(batch, 0)
+    (opt,), (sch,) = b.configure_optimizers()
+    b.on_before_optimizer_step(opt); b.configure_gradient_clipping(opt)
+    b._fused_sweep(opt, b.base_lr * sch["scheduler"].factor(), fuse_ema=False)
+    sch["scheduler"].step(); b.trainer.global_step += 1
+    assert torch.equal(b.t_arena.fp32, t_before)  # teacher untouched so far
+    b.on_train_batch_end(None, batch, 0)
+    torch.cuda.synchronize()
+    assert (a.t_arena.fp32 - b.t_arena.fp32).abs().max().item() < 1e-6
+    m = O.cosine_schedule(1, 10, a.method_args.momentum_start, a.method_args.momentum_end)
+    want = t_before * m + a.s_arena.fp32 * (1 - m)
+    assert (a.t_arena.fp32 - want).abs().max().item() < 1e-6
+    # reference signature on arbitrary arena-backed modules (LT/_torch_helpers.py:89-96)
+    t2 = b.t_arena.fp32.clone()
+    update_momentum(b.student_head, b.teacher_head, 0.5)
+    off = b._head_off
+    assert torch.equal(b.t_arena.fp32[:off], t2[:off])
+    assert torch.allclose(b.t_arena.fp32[off:], 0.5 * t2[off:] + 0.5 * b.s_arena.fp32[off:], atol=1e-7)
+    assert torch.equal(b.t_arena.bf16[off:], b.t_arena.fp32[off:].bfloat16())
+
+
+def test_checkpoint_resume_is_exact():
+    """Optimizer moments, AdamW step count, scheduler epoch and global_step round-trip through the Lightning-layout
+    checkpoint: a resumed run continues exactly like the uninterrupted one (same graph-free schedule, same batch)."""
+    cfg = R.step_config("softmax", False)
+    views, masks, idx, w = R.step_case_inputs(cfg)
+    batch = {"views": [v.to(dev) for v in views], "masks": {"collated_masks": masks, "mask_indices_list": idx, "masks_weight": w}}
+    a = _tiny_method()
+    a.train_step(batch); a.train_step(batch)
+    a.dino_loss.apply_center_update(); a.ibot_loss.apply_center_update()
+    ck = a.checkpoint()
+    assert set(ck) == {"state_dict", "optimizer_states", "lr_schedulers", "global_step"} and ck["global_step"] == 2
+    b = _tiny_method()
+    b.load_checkpoint(ck)
+    assert not b.s_arena.bf16_valid and not b.t_arena.bf16_valid
+    assert b._opt_step == 2 and b.trainer.global_step == 2
+    assert torch.equal(a.s_arena.exp_avg, b.s_arena.exp_avg) and torch.equal(a.s_arena.fp32, b.s_arena.fp32)
+    ra, rb = a.train_step(batch), b.train_step(batch)
+    torch.cuda.synchronize()
+    assert abs(float(ra.loss) - float(rb.loss)) < 1e-5 * abs(float(ra.loss))
+    assert (a.s_arena.fp32 - b.s_arena.fp32).abs().max().item() < 1e-5
+
+
+@pytest.mark.skipif(not ref_full.available(), reason="reference copy (baseline/_ref) not on this box")
+def test_checkpoint_round_trip_into_reference_modules():
+    """1 optimisation step on CUDA -> state_dict() -> load_state_dict(strict=True) into the reference's own DINOv2 method
+    -> the reference ViT + head forward (fp32, host) reproduces the CUDA teacher/student features."""
+    case = RC.TINY
+    ref, _, _ = RC.build_reference(case)
+    m = DINOv2(DINOv2Args(**dict(dict(warmup_steps=2, student_freeze_last_layer_steps=1), **case.method)), DINOv2AdamWViTArgs(),
+               ref.teacher_embedding_model, case.batch, 3, max_steps=100, device=dev)
+    m.load_state_dict(ref.state_dict(), strict=True)
+    views = RC.make_views(case)
+    random.seed(3)
+    m.train_step({"views": [v.to(dev) for v in views]})
+    m.dino_loss.apply_center_update(); m.ibot_loss.apply_center_update()
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    res = ref.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    x = views[0]
+    with torch.no_grad():
+        for side in ("teacher", "student"):
+            emb = getattr(ref, f"{side}_embedding_model")
+            want = emb.wrapped_model.get_model().forward_features(x)["x_norm_clstoken"]
+            got = getattr(m, f"{side}_embedding_model").wrapped_model.get_model().forward_features(x.to(dev))["x_norm_clstoken"]
+            assert (got.float().cpu() - want).abs().max().item() < 5e-2, side  # bf16 GEMMs vs fp32, O(1) features
+            assert (got.float().cpu() - want).abs().mean().item() < 5e-3, side
+    # the step really moved the student away from the teacher-initialised weights
+    assert (sd["student_embedding_model.wrapped_model._model.blocks.0.attn.qkv.weight"]
+            - ref_full_state_before(case)).abs().max().item() > 0
+
+
+def ref_full_state_before(case):
+    ref0, _, _ = RC.build_reference(case)
+    return ref0.state_dict()["student_embedding_model.wrapped_model._model.blocks.0.attn.qkv.weight"]
+
+
+def test_stochastic_depth_rng_paths():
+    """The code that draws the stochastic-depth randomness itself (bench path): per-sample DropPath for rates <= 0.1
+    (`bern_scales`) and the batch-subset form for rates > 0.1 (layers/block.py:118-141).  Checks the scale statistics and
+    that a dropped sample receives NO gradient contribution from the dropped branch."""
+    torch.manual_seed(0)
+    Bc = 64
+    m = DinoVisionTransformer(img_size=32, patch_size=16, embed_dim=128, depth=4, num_heads=2, init_values=1.0,
+                              drop_path_rate=0.3, drop_path_uniform=False, requires_grad=True)
+    assert [round(r, 3) for r in m.dpr] == [0.0, 0.1, 0.2, 0.3]
+    x = torch.randn(Bc, 3, 32, 32, device=dev)
+    m.arena.zero_grad()
+    ctx = m._fwd(x, None, save=True, drop_path=True)
+    blocks = ctx.blocks
+    assert blocks[0]["rs1"] is None and blocks[0]["rs2"] is None            # rate 0: no scaling
+    rs = blocks[1]["rs1"]                                                   # rate 0.1: bernoulli(0.9) / 0.9
+    vals = set(round(v, 4) for v in rs.tolist())
+    assert vals <= {0.0, round(1 / 0.9, 4)} and len(vals) >= 1
+    for i, rate in ((2, 0.2), (3, 0.3)):                                   # subset form: b' = max(int(b(1-r)),1) kept at b/b'
+        for key in ("rs1", "rs2"):
+            r = blocks[i][key]
+            bsub = max(int(Bc * (1.0 - m.dpr[i])), 1)
+            assert int((r > 0).sum()) == bsub
+            assert torch.allclose(r[r > 0], torch.full((bsub,), Bc / bsub, device=dev))
+    assert not torch.equal(blocks[3]["rs1"], blocks[3]["rs2"])             # independent draws per branch
+    # gradient isolation: cotangent only on sample j's tokens; a block-3 branch dropped for sample j must not see it
+    N = ctx.dims[3]
+    j = int((blocks[3]["rs2"] == 0).nonzero()[0])
+    d = torch.zeros(Bc * N, 128, device=dev)
+    d[j * N:(j + 1) * N] = torch.randn(N, 128, device=dev)
+    g0 = m.arena.g("blocks.3.mlp.fc2.weight")
+    m._bwd(ctx, d)
+    torch.cuda.synchronize()
+    assert g0.abs().max().item() == 0.0, "dropped sample leaked gradient into its dropped MLP branch"
+    assert m.arena.g("blocks.0.mlp.fc2.weight").abs().max().item() > 0.0
