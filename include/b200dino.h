@@ -70,12 +70,16 @@ typedef struct b200_gemm_args {
 
 int b200_gemm(const b200_gemm_args* args, void* stream);
 
-/* Same contract as b200_attention_fwd on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), N <= 256.
- * BRING-UP: compiled and exported, not yet validated on hardware and not used by the product path
- * (lightly_train_b200/csrc/attention_tc.cu).  P is rounded to bf16 before normalisation
- * (flash-style), the other rounding points are those of b200_attention_fwd. */
+/* Attention on the 5th-generation tensor cores (tcgen05.mma, fp32 accumulators in TMEM, TMA-staged operands):
+ * same contracts as b200_attention_fwd / b200_attention_bwd below, for the global-crop sequence lengths
+ * (forward N <= 256, backward N <= 208; lightly_train_b200/csrc/attention_tc.cu).  Replaces
+ * LT/_models/dinov2_vit/dinov2_vit_src/layers/attention.py:49-66 and its autograd backward.  P is rounded to bf16
+ * before the 1/l normalisation (flash-style); the other rounding points are those of the warp-level kernels. */
 int b200_attention_fwd_tc(const void* qkv, long long ld_tok, int B, int N, int h, int head_dim, float scale, void* out,
                           long long ld_out, float* lse, void* stream);
+int b200_attention_bwd_tc(const void* qkv, long long ld_tok, const void* out, const void* dout, long long ld_out,
+                          const float* lse, int B, int N, int h, int head_dim, float scale, void* dqkv,
+                          long long ld_dtok, float* dqkv_colsum, void* stream);
 /* ------------------------------------------------------------------------------------------------
  * Attention core for short sequences (head_dim 64), forward and backward.
  * Replaces LT/_models/dinov2_vit/dinov2_vit_src/layers/attention.py:55-63 (q*scale @ k^T, softmax, @ v) and

@@ -1,22 +1,30 @@
-// Short-sequence attention FORWARD on the 5th-generation tensor cores (tcgen05 + TMEM + TMA) -- BRING-UP, NOT WIRED.
+// Short-sequence attention on the 5th-generation tensor cores: tcgen05.mma with fp32 accumulators in TMEM, operands
+// staged by TMA into 128B-swizzled shared memory.  Forward and backward for 128 < N <= 256 (forward) / N <= 208
+// (backward) tokens per image, head_dim 64 -- the global-crop sequences of the ViT (N = 197 / 201); shorter and longer
+// sequences stay on the warp-level kernels of attention.cu (b200_attention_fwd / _bwd dispatch).
 //
-// Status: compiles for sm_100a, exported as b200_attention_fwd_tc with the signature of b200_attention_fwd, but it is
-// not called by lightly_train_b200/ops.py and has not run on hardware yet (the round's GPU budget was spent); the
-// product path uses the mma.sync kernels of attention.cu.  tests/test_kernels_gpu.py::test_attention_fwd_tcgen05 is the
-// parity test that must pass before it is switched on (opt-in through B200_TEST_TC_ATTENTION=1 until then).
-// Design and expected gain: DESIGN.md section 7.
+// Replaces Attention.forward of LT/_models/dinov2_vit/dinov2_vit_src/layers/attention.py:49-66 and its autograd backward.
+// Rounding points of the bf16-autocast reference are kept: S = q k^T is rounded to bf16 before the fp32 softmax, P is
+// rounded to bf16 before P V (here BEFORE the 1/l normalisation, flash-style: same relative rounding error), dP and dS
+// are rounded to bf16 (autocast matmul outputs / operands), dq dk dv are written in bf16.
 //
-// Replaces (like attention.cu) Attention.forward of LT/_models/dinov2_vit/dinov2_vit_src/layers/attention.py:49-66.
+// One CTA per (image, head).  qkv: bf16 [B*N, 3*h*64] (row pitch ld_tok); out / dout: bf16 [B*N, h*64].
+// Rows past an image's N tokens inside a TMA box belong to the next image (or are zero-filled past the tensor): finite
+// data that is always MASKED (keys >= N get probability 0, query rows >= N are zeroed before they are contracted over
+// and never stored).
 //
-// One CTA per (image, head).  qkv: bf16 [B*N, 3*h*64] (row pitch ld_tok); out: bf16 [B*N, h*64].
-//   warp 4 (one elected lane): TMA loads of the pair's Q (two 128-row boxes), K and V rows (NKV = 16*ceil(N/16) rows;
-//            rows past the image's N tokens belong to the next image or are zero-filled by TMA: they are MASKED, never
-//            relied on), then per 128-row query tile  S = Q K^T  (4 x tcgen05.mma M128 x N=NKV x K16, fp32 in TMEM) and
-//            O = P V  (NKV/16 x tcgen05.mma M128 x N64 x K16, A = P from smem K-major, B = V from smem MN-major).
-//   warps 0-3: one query row per thread (TMEM lane = row): tcgen05.ld of the S row in 16-column chunks, row max and
-//            sum thread-local (no shuffles), P = 2^((s - m) * scale * log2e) rounded to bf16 UNNORMALISED into a
-//            128B-swizzled smem tile (flash-style: O is scaled by 1/l after the second MMA), then O row -> global.
-// S is rounded to bf16 before the softmax (autocast reference; the power-of-two scale commutes with the rounding).
+// FORWARD  (9 warps): warp 8 = control (TMA loads, all tcgen05.mma issues); warps 0-3 / 4-7 = the two 128-row query
+//   tiles, one query row per thread (TMEM lane = row, so row max / row sum are thread-local: no shuffles).
+//     S_t = Q_t K^T          M128 x N=NKV x K16 x4, fp32 -> TMEM columns [256 t, 256 t + NKV)
+//     P   = 2^((s - m) * scale * log2e) -> bf16 -> swizzled smem tile (A operand of the next MMA), l = sum p
+//     O_t = P V              M128 x N64 x K16 x NKV/16 -> TMEM columns [256 t, 256 t + 64) (S_t is dead by then)
+//     out = O / l, lse = m * scale + ln l
+// BACKWARD (9 warps): warp 8 = control; warps 0-3 / 4-7 = the key columns [0, NKV/2) / [NKV/2, NKV) of the current
+//   128-row query tile (LSE and D_i are known, so the row can be split across two threads without a reduction).
+//   Per query tile t:  S = Q_t K^T -> P (smem) ; dV += P^T dO_t ; dP = dO_t V^T (reuses S's TMEM columns) ->
+//   dS = P (dP - D) (smem, in place of P) ; dK += dS^T Q_t ; dQ_t = dS K (reuses the same TMEM columns) -> global.
+//   dK / dV accumulate in TMEM over the two query tiles (keys on the lanes: two 128-row M tiles x 64 columns each).
+//   The qkv-bias gradient (column sums of the bf16 dq | dk | dv) is accumulated from registers like attention.cu does.
 #include <cuda.h>
 #include "common.cuh"
 #include "../../include/b200dino.h"
@@ -26,11 +34,10 @@ namespace attn_tc {
 
 static constexpr int HD = 64;
 static constexpr int BLOCK_Q = 128;                 // query rows per MMA tile (= TMEM lanes)
-static constexpr int Q_BYTES = 2 * BLOCK_Q * 128;   // two query tiles
-static constexpr int P_SLAB = BLOCK_Q * 128;        // one 64-key slab of the P tile
-static constexpr int THREADS = 5 * 32;
+static constexpr int TILE_BYTES = BLOCK_Q * 128;    // one [128 x 64] bf16 tile (also one 64-key slab of a P tile)
+static constexpr float kLog2e = 1.4426950408889634f;
 
-// same encodings as gemm_tcgen05.cu (kept local: that file is hardware-verified and stays untouched)
+// same encodings as gemm_tcgen05.cu (hardware-verified there)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
@@ -40,53 +47,54 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t smem_addr, uint32_t lbo_b
   d |= (uint64_t)2 << 61;  // SWIZZLE_128B
   return d;
 }
-__device__ __forceinline__ uint32_t instr_desc(int m, int n, int b_mn) {
+__device__ __forceinline__ uint32_t instr_desc(int m, int n, int a_mn, int b_mn) {
   uint32_t d = 0;
   d |= 1u << 4;                    // D = f32
   d |= 1u << 7;                    // A = bf16
   d |= 1u << 10;                   // B = bf16
+  d |= (uint32_t)(a_mn ? 1 : 0) << 15;
   d |= (uint32_t)(b_mn ? 1 : 0) << 16;
   d |= (uint32_t)(n >> 3) << 17;
   d |= (uint32_t)(m >> 4) << 24;
   return d;
 }
-// TMEM -> registers: this warp's 32 lanes x 16 consecutive fp32 columns
-__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// 16-byte chunk `chunk` (8 bf16) of row `row` of a [rows][64] bf16 tile with 128-byte rows, 128B swizzle
+__device__ __forceinline__ uint32_t swz(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
 
+// ====================================================================================================================
+// forward
+// ====================================================================================================================
 template <int NKV16>
-struct Cfg {
-  static constexpr int NKV = NKV16 * 16;                   // padded key count (MMA N of S, K of P V), <= 256
+struct FwdCfg {
+  static constexpr int NKV = NKV16 * 16;                   // padded key count (MMA N of S, K of P V)
   static constexpr int KV_BYTES = NKV * 128;
   static constexpr int P_SLABS = (NKV + 63) / 64;
-  static constexpr int OFF_K = Q_BYTES;
+  static constexpr int OFF_K = 2 * TILE_BYTES;             // after the two query tiles
   static constexpr int OFF_V = OFF_K + KV_BYTES;
   static constexpr int OFF_P = (OFF_V + KV_BYTES + 1023) / 1024 * 1024;
-  static constexpr int OFF_BAR = OFF_P + P_SLABS * P_SLAB;
+  static constexpr int P_BYTES = P_SLABS * TILE_BYTES;     // per query tile
+  static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;  // barriers + TMEM slot, alignment slack
-  static constexpr int TM_S = 0, TM_O = NKV;               // TMEM columns: S [0, NKV), O [NKV, NKV + 64)
-  static_assert(NKV <= 256 && NKV + HD <= 512, "one S tile and one O tile must fit TMEM");
+  static constexpr int THREADS = 9 * 32;
+  static_assert(NKV <= 256, "one S tile per 256 TMEM columns");
+  static_assert(SMEM_BYTES <= 232448, "shared memory");
 };
 
 template <int NKV16>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(FwdCfg<NKV16>::THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, int N, int h,
                    float scale, __nv_bfloat16* __restrict__ out, long long ld_out, float* __restrict__ lse) {
-  using C = Cfg<NKV16>;
+  using C = FwdCfg<NKV16>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
   uint64_t* bar_load = bars + 0;  // TMA bytes landed
-  uint64_t* bar_s = bars + 1;     // S = Q K^T of the current tile is in TMEM
-  uint64_t* bar_p = bars + 2;     // P tile written to smem (4 worker warps)
-  uint64_t* bar_o = bars + 3;     // O = P V of the current tile is in TMEM
-  uint64_t* bar_free = bars + 4;  // workers are done with this tile's TMEM (4 worker warps)
+  uint64_t* bar_s = bars + 1;     // [2] S_t in TMEM
+  uint64_t* bar_p = bars + 3;     // [2] P_t in smem (4 worker warps each)
+  uint64_t* bar_o = bars + 5;     // [2] O_t in TMEM
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -95,13 +103,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   if (threadIdx.x == 0) {
     mbar_init(bar_load, 1);
-    mbar_init(bar_s, 1);
-    mbar_init(bar_p, 4);
-    mbar_init(bar_o, 1);
-    mbar_init(bar_free, 4);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(bar_s + t, 1);
+      mbar_init(bar_p + t, 4);
+      mbar_init(bar_o + t, 1);
+    }
     fence_barrier_init();
   }
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmKV);
@@ -114,87 +123,96 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ===================== control warp: TMA + MMA issue =====================
     const int row0 = b * N;  // first token row of this image in the [B*N, 3*h*64] qkv matrix
     if (lane == 0) {
-      mbar_expect_tx(bar_load, Q_BYTES + 2 * C::KV_BYTES);
+      mbar_expect_tx(bar_load, 2 * TILE_BYTES + 2 * C::KV_BYTES);
       tma_load_2d(smem, &tmQ, bar_load, head * HD, row0);
-      tma_load_2d(smem + BLOCK_Q * 128, &tmQ, bar_load, head * HD, row0 + BLOCK_Q);
+      tma_load_2d(smem + TILE_BYTES, &tmQ, bar_load, head * HD, row0 + BLOCK_Q);
       tma_load_2d(smem + C::OFF_K, &tmKV, bar_load, (h + head) * HD, row0);
       tma_load_2d(smem + C::OFF_V, &tmKV, bar_load, (2 * h + head) * HD, row0);
     }
     __syncwarp();
     mbar_wait(bar_load, 0);
     const uint32_t s0 = smem_u32(smem);
-    const uint64_t dq = smem_desc(s0, 16, 1024);                    // A of S: Q tile, K-major
-    const uint64_t dk = smem_desc(s0 + C::OFF_K, 16, 1024);         // B of S: K rows, K-major (N = keys)
-    const uint64_t dp = smem_desc(s0 + C::OFF_P, 16, 1024);         // A of O: P tile, K-major (K = keys)
-    const uint64_t dv = smem_desc(s0 + C::OFF_V, 64 * 128, 1024);   // B of O: V rows, MN-major (N = head dim)
-    const uint32_t idesc_s = instr_desc(BLOCK_Q, C::NKV, 0);
-    const uint32_t idesc_o = instr_desc(BLOCK_Q, HD, 1);
-    for (int t = 0; t < n_tiles; ++t) {
-      const uint32_t ph = t & 1;
-      if (t > 0) {
-        mbar_wait(bar_free, ph ^ 1);  // workers drained tile t-1's S and O
-        tc_fence_after();
-      }
-      if (elect_one_sync()) {
+    const uint64_t dk = smem_desc(s0 + C::OFF_K, 16, 1024);        // B of S: K rows, K-major (N = keys)
+    const uint64_t dv = smem_desc(s0 + C::OFF_V, 64 * 128, 1024);  // B of O: V rows, MN-major (N = head dim)
+    const uint32_t idesc_s = instr_desc(BLOCK_Q, C::NKV, 0, 0);
+    const uint32_t idesc_o = instr_desc(BLOCK_Q, HD, 0, 1);
+    if (elect_one_sync()) {
+      for (int t = 0; t < n_tiles; ++t) {
+        const uint64_t dq = smem_desc(s0 + t * TILE_BYTES, 16, 1024);  // A of S: Q tile, K-major
 #pragma unroll
         for (int ks = 0; ks < HD / 16; ++ks)
-          umma_f16(tmem_base + C::TM_S, dq + (uint64_t)((t * BLOCK_Q * 128 + ks * 32) >> 4), dk + (uint64_t)((ks * 32) >> 4),
-                   idesc_s, ks > 0 ? 1u : 0u);
-        umma_commit(bar_s);
+          umma_f16(tmem_base + t * 256, dq + (uint64_t)((ks * 32) >> 4), dk + (uint64_t)((ks * 32) >> 4), idesc_s, ks > 0 ? 1u : 0u);
+        umma_commit(bar_s + t);
       }
-      __syncwarp();
-      mbar_wait(bar_p, ph);  // P tile complete in smem (workers fenced the generic->async proxy before arriving)
+    }
+    __syncwarp();
+    for (int t = 0; t < n_tiles; ++t) {
+      mbar_wait(bar_p + t, 0);  // P_t complete in smem (workers fenced generic->async proxy before arriving)
       tc_fence_after();
       if (elect_one_sync()) {
+        const uint64_t dp = smem_desc(s0 + C::OFF_P + t * C::P_BYTES, 16, 1024);  // A of O: P tile, K-major (K = keys)
 #pragma unroll 1
         for (int ks = 0; ks < NKV16; ++ks)
-          umma_f16(tmem_base + C::TM_O, dp + (uint64_t)(((ks >> 2) * P_SLAB + (ks & 3) * 32) >> 4),
+          umma_f16(tmem_base + t * 256, dp + (uint64_t)(((ks >> 2) * TILE_BYTES + (ks & 3) * 32) >> 4),
                    dv + (uint64_t)((ks * 16 * 128) >> 4), idesc_o, ks > 0 ? 1u : 0u);
-        umma_commit(bar_o);
+        umma_commit(bar_o + t);
       }
       __syncwarp();
     }
-  } else {
-    // ===================== worker warps: one query row per thread =====================
-    const int q = warp;                 // TMEM lane quarter == warp index (warps 0-3)
-    const int r = q * 32 + lane;        // row inside the 128-row tile
-    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    const float sl2 = scale * 1.4426950408889634f;
-    uint8_t* sP = smem + C::OFF_P;
-    for (int t = 0; t < n_tiles; ++t) {
-      const uint32_t ph = t & 1;
-      const int m = t * BLOCK_Q + r;    // query token index inside the image
-      mbar_wait(bar_s, ph);
-      tc_fence_after();
-      // pass 1: row max of the bf16-rounded scores over the valid keys
-      float mx = -INFINITY;
+  } else if ((warp >> 2) < n_tiles) {
+    // ===================== worker warps: tile t = warp / 4, one query row per thread =====================
+    const int t = warp >> 2, q = warp & 3;
+    const int r = q * 32 + lane;        // row inside the 128-row tile == TMEM lane
+    const int m = t * BLOCK_Q + r;      // query token index inside the image
+    const uint32_t tS = tmem_base + ((uint32_t)(q * 32) << 16) + t * 256;
+    const float sl2 = scale * kLog2e;
+    uint8_t* sP = smem + C::OFF_P + t * C::P_BYTES;
+    mbar_wait(bar_s + t, 0);
+    tc_fence_after();
+    // pass 1: row max of the bf16-rounded scores over the valid keys
+    float mx = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < NKV16; ++c) {
-        uint32_t v[16];
-        tmem_ld_32x16(lane_base + C::TM_S + c * 16, v);
-        tmem_ld_wait();
+    for (int c = 0; c < NKV16; ++c) {
+      uint32_t v[16];
+      tmem_ld_32x16(tS + c * 16, v);
+      tmem_ld_wait();
+      if (c * 16 + 16 <= N) {
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
-          float a = __uint_as_float(v[i]), bq = __uint_as_float(v[i + 1]);
-          const uint32_t pk = pack_bf16x2(a, bq);
-          const float2 rr = unpack_bf16x2(pk);
+          const float2 rr = unpack_bf16x2(pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+          mx = fmaxf(mx, fmaxf(rr.x, rr.y));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          const float2 rr = unpack_bf16x2(pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
           if (c * 16 + i < N) mx = fmaxf(mx, rr.x);
           if (c * 16 + i + 1 < N) mx = fmaxf(mx, rr.y);
         }
       }
-      const float mb = -mx * sl2;
-      // pass 2: p = 2^(s*sl2 - m*sl2), row sum in fp32, P (unnormalised, bf16) -> swizzled smem A tile
-      float l = 0.f;
+    }
+    const float mb = -mx * sl2;
+    // pass 2: p = 2^(s*sl2 - m*sl2), row sum in fp32, P (unnormalised, bf16) -> swizzled smem A tile
+    float l = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < NKV16; ++c) {
-        uint32_t v[16];
-        tmem_ld_32x16(lane_base + C::TM_S + c * 16, v);
-        tmem_ld_wait();
-        uint32_t pw[8];
+    for (int c = 0; c < NKV16; ++c) {
+      uint32_t v[16];
+      tmem_ld_32x16(tS + c * 16, v);
+      tmem_ld_wait();
+      uint32_t pw[8];
+      if (c * 16 + 16 <= N) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          const float2 rr = unpack_bf16x2(pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+          const float p0 = ex2_ftz(fmaf(rr.x, sl2, mb)), p1 = ex2_ftz(fmaf(rr.y, sl2, mb));
+          l += p0 + p1;
+          pw[i >> 1] = pack_bf16x2(p0, p1);
+        }
+      } else {
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
           const float2 rr = unpack_bf16x2(pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
@@ -203,44 +221,359 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           l += p0 + p1;
           pw[i >> 1] = pack_bf16x2(p0, p1);
         }
-        // keys [c*16, c*16+16) = 16-byte chunks (c*2) and (c*2+1) of slab c/4; 128B swizzle: chunk ^ (row & 7)
-        uint8_t* slab = sP + (c >> 2) * P_SLAB + r * 128;
-        const int ch = (c & 3) * 2;
-        *reinterpret_cast<uint4*>(slab + (((ch) ^ (r & 7)) << 4)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
-        *reinterpret_cast<uint4*>(slab + (((ch + 1) ^ (r & 7)) << 4)) = make_uint4(pw[4], pw[5], pw[6], pw[7]);
       }
-      fence_proxy_async();  // the MMA (async proxy) reads what this thread just wrote through the generic proxy
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_p);
-      if (lse && m < N) lse[(size_t)bh * N + m] = mx * scale + __logf(l);
-      // O row: scale by 1/l, round to bf16, 128 contiguous bytes per row
-      mbar_wait(bar_o, ph);
-      tc_fence_after();
-      const float inv = 1.f / l;
-      __nv_bfloat16* orow = out + ((size_t)b * N + m) * ld_out + head * HD;
+      // keys [c*16, c*16+16) = 16-byte chunks (c&3)*2, +1 of slab c/4
+      uint8_t* slab = sP + (c >> 2) * TILE_BYTES;
+      const int ch = (c & 3) * 2;
+      *reinterpret_cast<uint4*>(slab + swz(r, ch)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+      *reinterpret_cast<uint4*>(slab + swz(r, ch + 1)) = make_uint4(pw[4], pw[5], pw[6], pw[7]);
+    }
+    fence_proxy_async();  // the MMA (async proxy) reads what this thread just wrote through the generic proxy
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_p + t);
+    if (lse && m < N) lse[(size_t)bh * N + m] = mx * scale + __logf(l);
+    // O row: scale by 1/l, round to bf16, 128 contiguous bytes per row
+    mbar_wait(bar_o + t, 0);
+    tc_fence_after();
+    const float inv = 1.f / l;
+    __nv_bfloat16* orow = out + ((size_t)b * N + m) * ld_out + head * HD;
 #pragma unroll
-      for (int c = 0; c < HD / 16; ++c) {
-        uint32_t v[16];
-        tmem_ld_32x16(lane_base + C::TM_O + c * 16, v);
-        tmem_ld_wait();
-        if (m < N) {
-          uint32_t ow[8];
+    for (int c = 0; c < HD / 16; ++c) {
+      uint32_t v[16];
+      tmem_ld_32x16(tS + c * 16, v);
+      tmem_ld_wait();
+      if (m < N) {
+        uint32_t ow[8];
 #pragma unroll
-          for (int i = 0; i < 16; i += 2) ow[i >> 1] = pack_bf16x2(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
-          *reinterpret_cast<uint4*>(orow + c * 16) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-          *reinterpret_cast<uint4*>(orow + c * 16 + 8) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
-        }
+        for (int i = 0; i < 16; i += 2) ow[i >> 1] = pack_bf16x2(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
+        *reinterpret_cast<uint4*>(orow + c * 16) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        *reinterpret_cast<uint4*>(orow + c * 16 + 8) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_free);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ====================================================================================================================
+// backward
+// ====================================================================================================================
+template <int NKV16>
+struct BwdCfg {
+  static constexpr int NKV = NKV16 * 16;                   // padded key count, <= 208
+  static constexpr int KV_BYTES = NKV * 128;
+  static constexpr int OFF_Q = 0;                          // two query tiles
+  static constexpr int OFF_DO = 2 * TILE_BYTES;            // two dO tiles
+  static constexpr int OFF_K = 4 * TILE_BYTES;
+  static constexpr int OFF_V = OFF_K + KV_BYTES;
+  static constexpr int OFF_P = (OFF_V + KV_BYTES + 1023) / 1024 * 1024;   // P / dS tile: 4 slabs of 64 keys
+  static constexpr int OFF_F = OFF_P + 4 * TILE_BYTES;     // floats: L[256], D[256], colsum[192]
+  static constexpr int OFF_BAR = OFF_F + (256 + 256 + 192) * 4;
+  static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
+  static constexpr int THREADS = 9 * 32;
+  // TMEM columns: S / dP / dQ share [0, NKV); dK [256, 384): M tile 0 | 1; dV [384, 512)
+  static constexpr int TM_SDP = 0, TM_DK = 256, TM_DV = 384;
+  static constexpr int HALF16 = (NKV16 + 1) / 2;           // 16-key chunks owned by worker group 0
+  static_assert(NKV <= 256, "S / dP tile");
+  static_assert(SMEM_BYTES <= 232448, "shared memory");
+};
+
+// column sums over the 32 rows held by a warp (one row per lane, 32 consecutive columns in v): butterfly transpose-
+// reduce, 31 shuffles instead of 160; on return lane j holds the sum of column j.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float mine = upper ? v[i + half] : v[i];
+      const float give = upper ? v[i] : v[i + half];
+      v[i] = mine + __shfl_xor_sync(0xffffffffu, give, half);
+    }
+  }
+  return v[0];
+}
+
+// Drain one [128 x 64] fp32 accumulator tile (one row per thread, 4 warps): out = bf16(acc * mul) -> global row (when
+// `valid`), and this warp's column sums of the bf16-rounded values -> smem atomics on cs[0..64).
+__device__ __forceinline__ void drain_tile(uint32_t taddr, float mul, bool valid, __nv_bfloat16* grow, float* cs, int lane) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32(taddr + c * 32, v);
+    tmem_ld_wait();
+    float f[32];
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      w[i >> 1] = pack_bf16x2(__uint_as_float(v[i]) * mul, __uint_as_float(v[i + 1]) * mul);
+      const float2 rr = unpack_bf16x2(w[i >> 1]);
+      f[i] = valid ? rr.x : 0.f;
+      f[i + 1] = valid ? rr.y : 0.f;
+    }
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<uint4*>(grow + c * 32 + i * 8) = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+    }
+    if (cs) {
+      const float s = warp_colsum32(f, lane);
+      atomicAdd(cs + c * 32 + lane, s);
+    }
+  }
+}
+
+template <int NKV16>
+__global__ void __launch_bounds__(BwdCfg<NKV16>::THREADS, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                   const __grid_constant__ CUtensorMap tmDO, const __nv_bfloat16* __restrict__ outp,
+                   const __nv_bfloat16* __restrict__ dout, long long ld_out, const float* __restrict__ lse, int N, int h,
+                   float scale, __nv_bfloat16* __restrict__ dqkv, long long ld_dtok, float* __restrict__ colsum) {
+  using C = BwdCfg<NKV16>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* sL = reinterpret_cast<float*>(smem + C::OFF_F);  // base-2 log-sum-exp per query row (256)
+  float* sD = sL + 256;                                   // D_i = sum_d dO O
+  float* sC = sD + 256;                                   // column sums of dq | dk | dv
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* bar_load = bars + 0;
+  uint64_t* bar_s = bars + 1;     // S of the current tile in TMEM
+  uint64_t* bar_p = bars + 2;     // P in smem (8 worker warps)
+  uint64_t* bar_dp = bars + 3;    // dP in TMEM (and dV MMAs of this tile retired: P may be overwritten)
+  uint64_t* bar_ds = bars + 4;    // dS in smem (8 worker warps)
+  uint64_t* bar_dq = bars + 5;    // dQ in TMEM (and dK MMAs retired)
+  uint64_t* bar_free = bars + 6;  // dQ drained (4 worker warps): the shared TMEM columns may be overwritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.x, b = bh / h, head = bh % h;
+  const int n_tiles = (N + BLOCK_Q - 1) / BLOCK_Q;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_load, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 8);
+    mbar_init(bar_dp, 1);
+    mbar_init(bar_ds, 8);
+    mbar_init(bar_dq, 1);
+    mbar_init(bar_free, 4);
+    fence_barrier_init();
+  }
+  if (warp == 8) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmKV);
+      tma_prefetch_desc(&tmDO);
+    }
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const size_t row0 = (size_t)b * N;
+
+  if (warp == 8) {
+    // ===================== control warp =====================
+    if (lane == 0) {
+      mbar_expect_tx(bar_load, 4 * TILE_BYTES + 2 * C::KV_BYTES);
+      tma_load_2d(smem + C::OFF_Q, &tmQ, bar_load, head * HD, (int)row0);
+      tma_load_2d(smem + C::OFF_Q + TILE_BYTES, &tmQ, bar_load, head * HD, (int)row0 + BLOCK_Q);
+      tma_load_2d(smem + C::OFF_DO, &tmDO, bar_load, head * HD, (int)row0);
+      tma_load_2d(smem + C::OFF_DO + TILE_BYTES, &tmDO, bar_load, head * HD, (int)row0 + BLOCK_Q);
+      tma_load_2d(smem + C::OFF_K, &tmKV, bar_load, (h + head) * HD, (int)row0);
+      tma_load_2d(smem + C::OFF_V, &tmKV, bar_load, (2 * h + head) * HD, (int)row0);
+    }
+    __syncwarp();
+    mbar_wait(bar_load, 0);
+    const uint32_t s0 = smem_u32(smem);
+    const uint64_t dK_kmaj = smem_desc(s0 + C::OFF_K, 16, 1024);         // B of S: [keys x d], K-major (N = keys, K = d)
+    const uint64_t dV_kmaj = smem_desc(s0 + C::OFF_V, 16, 1024);         // B of dP
+    const uint64_t dK_mn = smem_desc(s0 + C::OFF_K, 64 * 128, 1024);     // B of dQ: (K = keys, N = d), MN-major
+    const uint64_t dP_kmaj = smem_desc(s0 + C::OFF_P, 16, 1024);         // A of dQ: dS [q x keys], K-major, 64-key slabs
+    const uint64_t dP_mn = smem_desc(s0 + C::OFF_P, TILE_BYTES, 1024);   // A of dV / dK: P^T / dS^T, MN-major (M = keys), LBO = slab
+    const uint32_t id_s = instr_desc(BLOCK_Q, C::NKV, 0, 0);             // S, dP
+    const uint32_t id_kv = instr_desc(BLOCK_Q, HD, 1, 1);                // dV, dK: A MN-major, B MN-major
+    const uint32_t id_dq = instr_desc(BLOCK_Q, HD, 0, 1);                // dQ
+    for (int t = 0; t < n_tiles; ++t) {
+      const uint32_t ph = t & 1;
+      const uint64_t dQt_k = smem_desc(s0 + C::OFF_Q + t * TILE_BYTES, 16, 1024);        // A of S
+      const uint64_t dQt_mn = smem_desc(s0 + C::OFF_Q + t * TILE_BYTES, 64 * 128, 1024);  // B of dK (K = q rows, N = d)
+      const uint64_t dOt_k = smem_desc(s0 + C::OFF_DO + t * TILE_BYTES, 16, 1024);       // A of dP
+      const uint64_t dOt_mn = smem_desc(s0 + C::OFF_DO + t * TILE_BYTES, 64 * 128, 1024);  // B of dV
+      if (t > 0) {
+        mbar_wait(bar_free, ph ^ 1);  // dQ of tile t-1 drained
+        tc_fence_after();
+      }
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_f16(tmem_base + C::TM_SDP, dQt_k + (uint64_t)(ks * 2), dK_kmaj + (uint64_t)(ks * 2), id_s, ks > 0 ? 1u : 0u);
+        umma_commit(bar_s);
+      }
+      __syncwarp();
+      mbar_wait(bar_p, ph);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        // dV[mt] (+)= P^T dO_t : M = 128 keys of M tile mt (slabs 2mt, 2mt+1), K = 128 query rows in 8 steps of 16
+#pragma unroll 1
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll 1
+          for (int ks = 0; ks < 8; ++ks)
+            umma_f16(tmem_base + C::TM_DV + mt * 64, dP_mn + (uint64_t)((mt * 2 * TILE_BYTES + ks * 2048) >> 4),
+                     dOt_mn + (uint64_t)((ks * 2048) >> 4), id_kv, (t > 0 || ks > 0) ? 1u : 0u);
+        // dP = dO_t V^T into the columns S occupied (every worker has consumed S: bar_p)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_f16(tmem_base + C::TM_SDP, dOt_k + (uint64_t)(ks * 2), dV_kmaj + (uint64_t)(ks * 2), id_s, ks > 0 ? 1u : 0u);
+        umma_commit(bar_dp);
+      }
+      __syncwarp();
+      mbar_wait(bar_ds, ph);
+      tc_fence_after();
+      if (elect_one_sync()) {
+#pragma unroll 1
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll 1
+          for (int ks = 0; ks < 8; ++ks)
+            umma_f16(tmem_base + C::TM_DK + mt * 64, dP_mn + (uint64_t)((mt * 2 * TILE_BYTES + ks * 2048) >> 4),
+                     dQt_mn + (uint64_t)((ks * 2048) >> 4), id_kv, (t > 0 || ks > 0) ? 1u : 0u);
+        // dQ_t = dS K : K = keys in NKV16 steps of 16
+#pragma unroll 1
+        for (int ks = 0; ks < NKV16; ++ks)
+          umma_f16(tmem_base + C::TM_SDP, dP_kmaj + (uint64_t)(((ks >> 2) * TILE_BYTES + (ks & 3) * 32) >> 4),
+                   dK_mn + (uint64_t)((ks * 2048) >> 4), id_dq, ks > 0 ? 1u : 0u);
+        umma_commit(bar_dq);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== worker warps =====================
+    const int g = warp >> 2, q = warp & 3;   // g: key-column half (and, for the drains, which tile this group owns)
+    const int r = q * 32 + lane;             // row inside a 128-row tile == TMEM lane
+    const uint32_t tL = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float sl2 = scale * kLog2e;
+    uint8_t* sP = smem + C::OFF_P;
+    // per-row constants: base-2 LSE and D_i = sum_d dO O straight from global (one 128-byte row per thread and tensor)
+    {
+      const int m = g * BLOCK_Q + r;  // this thread prepares row m of the image (rows 0..255)
+      float L = 0.f, D = 0.f;
+      if (m < N) {
+        L = lse[(size_t)bh * N + m] * kLog2e;
+        const uint4* po = reinterpret_cast<const uint4*>(outp + (row0 + m) * ld_out + head * HD);
+        const uint4* pd = reinterpret_cast<const uint4*>(dout + (row0 + m) * ld_out + head * HD);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 a = __ldg(po + i), c = __ldg(pd + i);
+          const uint32_t aa[4] = {a.x, a.y, a.z, a.w}, cc[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 x = unpack_bf16x2(aa[j]), y = unpack_bf16x2(cc[j]);
+            D = fmaf(x.x, y.x, D);
+            D = fmaf(x.y, y.y, D);
+          }
+        }
+      }
+      sL[m] = L;
+      sD[m] = D;
+      if (threadIdx.x < 192) sC[threadIdx.x] = 0.f;
+    }
+    named_bar_sync(1, 256);
+    const int c_lo = g == 0 ? 0 : C::HALF16, c_hi = g == 0 ? C::HALF16 : NKV16;
+    for (int t = 0; t < n_tiles; ++t) {
+      const uint32_t ph = t & 1;
+      const int m = t * BLOCK_Q + r;
+      const bool row_ok = m < N;
+      const float L = sL[m], D = sD[m];
+      // ---- P = 2^(s*sl2 - L) for my key columns (0 for padded rows / keys) -> smem
+      mbar_wait(bar_s, ph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = c_lo; c < c_hi; ++c) {
+        uint32_t v[16];
+        tmem_ld_32x16(tL + C::TM_SDP + c * 16, v);
+        tmem_ld_wait();
+        uint32_t pw[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          const float2 rr = unpack_bf16x2(pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+          const float p0 = (row_ok && c * 16 + i < N) ? ex2_ftz(fmaf(rr.x, sl2, -L)) : 0.f;
+          const float p1 = (row_ok && c * 16 + i + 1 < N) ? ex2_ftz(fmaf(rr.y, sl2, -L)) : 0.f;
+          pw[i >> 1] = pack_bf16x2(p0, p1);
+        }
+        uint8_t* slab = sP + (c >> 2) * TILE_BYTES;
+        const int ch = (c & 3) * 2;
+        *reinterpret_cast<uint4*>(slab + swz(r, ch)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+        *reinterpret_cast<uint4*>(slab + swz(r, ch + 1)) = make_uint4(pw[4], pw[5], pw[6], pw[7]);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
+      // ---- dS = P (dP - D), bf16, in place of P
+      mbar_wait(bar_dp, ph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = c_lo; c < c_hi; ++c) {
+        uint32_t v[16];
+        tmem_ld_32x16(tL + C::TM_SDP + c * 16, v);
+        uint8_t* slab = sP + (c >> 2) * TILE_BYTES;
+        const int ch = (c & 3) * 2;
+        const uint4 pa = *reinterpret_cast<const uint4*>(slab + swz(r, ch));
+        const uint4 pb = *reinterpret_cast<const uint4*>(slab + swz(r, ch + 1));
+        tmem_ld_wait();
+        const uint32_t pin[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+        uint32_t dw[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          const float2 dp = unpack_bf16x2(pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));  // bf16 dP
+          const float2 pp = unpack_bf16x2(pin[i >> 1]);  // p = 0 on masked rows / keys: dS = 0 there whatever dP holds
+          dw[i >> 1] = pack_bf16x2(pp.x * (dp.x - D), pp.y * (dp.y - D));
+        }
+        *reinterpret_cast<uint4*>(slab + swz(r, ch)) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+        *reinterpret_cast<uint4*>(slab + swz(r, ch + 1)) = make_uint4(dw[4], dw[5], dw[6], dw[7]);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_ds);
+      // ---- dQ_t: group 0 drains it (group 1 runs ahead to the next tile's waits)
+      if (g == 0) {
+        mbar_wait(bar_dq, ph);
+        tc_fence_after();
+        drain_tile(tL + C::TM_SDP, scale, row_ok, dqkv + (row0 + m) * ld_dtok + head * HD, colsum ? sC : nullptr, lane);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_free);
+      }
+    }
+    // ---- dK / dV: group g drains M tile g (keys g*128 + r); the last bar_dq completion covers every MMA issued
+    mbar_wait(bar_dq, (n_tiles - 1) & 1);
+    tc_fence_after();
+    {
+      const int key = g * BLOCK_Q + r;
+      const bool ok = key < N;
+      __nv_bfloat16* base = dqkv + (row0 + key) * ld_dtok + head * HD;
+      drain_tile(tL + C::TM_DK + g * 64, scale, ok, base + (size_t)h * HD, colsum ? sC + 64 : nullptr, lane);
+      drain_tile(tL + C::TM_DV + g * 64, 1.f, ok, base + (size_t)2 * h * HD, colsum ? sC + 128 : nullptr, lane);
+    }
+    named_bar_sync(1, 256);
+    if (colsum && threadIdx.x < 192) {
+      const int part = threadIdx.x >> 6, d = threadIdx.x & 63;
+      atomicAdd(colsum + (size_t)part * h * HD + head * HD + d, sC[threadIdx.x]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -273,9 +606,9 @@ static int tmap_rows(CUtensorMap* tm, const void* base, long long rows, long lon
 }
 
 template <int NKV16>
-static int launch(const void* qkv, long long ld_tok, int B, int N, int h, float scale, void* out, long long ld_out, float* lse,
-                  cudaStream_t s) {
-  using C = Cfg<NKV16>;
+static int launch_fwd(const void* qkv, long long ld_tok, int B, int N, int h, float scale, void* out, long long ld_out, float* lse,
+                      cudaStream_t s) {
+  using C = FwdCfg<NKV16>;
   CUtensorMap tmQ, tmKV;
   int rc = tmap_rows(&tmQ, qkv, (long long)B * N, 3LL * h * HD, ld_tok, BLOCK_Q);
   if (rc) return rc;
@@ -287,7 +620,31 @@ static int launch(const void* qkv, long long ld_tok, int B, int N, int h, float 
       return B200_ERR_CUDA;
     attr = true;
   }
-  attn_fwd_tc_kernel<NKV16><<<B * h, THREADS, C::SMEM_BYTES, s>>>(tmQ, tmKV, N, h, scale, (__nv_bfloat16*)out, ld_out, lse);
+  attn_fwd_tc_kernel<NKV16><<<B * h, C::THREADS, C::SMEM_BYTES, s>>>(tmQ, tmKV, N, h, scale, (__nv_bfloat16*)out, ld_out, lse);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+template <int NKV16>
+static int launch_bwd(const void* qkv, long long ld_tok, const void* out, const void* dout, long long ld_out, const float* lse, int B,
+                      int N, int h, float scale, void* dqkv, long long ld_dtok, float* colsum, cudaStream_t s) {
+  using C = BwdCfg<NKV16>;
+  CUtensorMap tmQ, tmKV, tmDO;
+  int rc = tmap_rows(&tmQ, qkv, (long long)B * N, 3LL * h * HD, ld_tok, BLOCK_Q);
+  if (rc) return rc;
+  rc = tmap_rows(&tmKV, qkv, (long long)B * N, 3LL * h * HD, ld_tok, C::NKV);
+  if (rc) return rc;
+  rc = tmap_rows(&tmDO, dout, (long long)B * N, (long long)h * HD, ld_out, BLOCK_Q);
+  if (rc) return rc;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(attn_bwd_tc_kernel<NKV16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
+      return B200_ERR_CUDA;
+    attr = true;
+  }
+  attn_bwd_tc_kernel<NKV16><<<B * h, C::THREADS, C::SMEM_BYTES, s>>>(tmQ, tmKV, tmDO, (const __nv_bfloat16*)out,
+                                                                      (const __nv_bfloat16*)dout, ld_out, lse, N, h, scale,
+                                                                      (__nv_bfloat16*)dqkv, ld_dtok, colsum);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -295,15 +652,31 @@ static int launch(const void* qkv, long long ld_tok, int B, int N, int h, float 
 }  // namespace attn_tc
 }  // namespace b200
 
+// Forward on tcgen05.  128 < N <= 256 (shorter sequences: b200_attention_fwd routes them to the warp-level kernel).
 extern "C" int b200_attention_fwd_tc(const void* qkv, long long ld_tok, int B, int N, int h, int head_dim, float scale, void* out,
                                      long long ld_out, float* lse, void* stream) {
   using namespace b200::attn_tc;
   if (!qkv || !out || B <= 0 || N <= 0 || h <= 0 || !(scale > 0.f)) return B200_ERR_INVALID_ARG;
   if (head_dim != HD || (ld_tok % 8) || (ld_out % 8) || ((uintptr_t)qkv & 15) || ((uintptr_t)out & 15)) return B200_ERR_UNSUPPORTED;
-  if (N > 256) return B200_ERR_UNSUPPORTED;  // two 128-row query tiles, one MMA N <= 256 of keys
+  if (N > 256) return B200_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
   const int nb = (N + 15) / 16;
-  if (nb <= 3) return launch<3>(qkv, ld_tok, B, N, h, scale, out, ld_out, lse, s);
-  if (nb <= 13) return launch<13>(qkv, ld_tok, B, N, h, scale, out, ld_out, lse, s);
-  return launch<16>(qkv, ld_tok, B, N, h, scale, out, ld_out, lse, s);
+  if (nb <= 4) return launch_fwd<4>(qkv, ld_tok, B, N, h, scale, out, ld_out, lse, s);
+  if (nb <= 13) return launch_fwd<13>(qkv, ld_tok, B, N, h, scale, out, ld_out, lse, s);
+  return launch_fwd<16>(qkv, ld_tok, B, N, h, scale, out, ld_out, lse, s);
+}
+
+// Backward on tcgen05.  N <= 208.
+extern "C" int b200_attention_bwd_tc(const void* qkv, long long ld_tok, const void* out, const void* dout, long long ld_out,
+                                     const float* lse, int B, int N, int h, int head_dim, float scale, void* dqkv,
+                                     long long ld_dtok, float* dqkv_colsum, void* stream) {
+  using namespace b200::attn_tc;
+  if (!qkv || !out || !dout || !lse || !dqkv || B <= 0 || N <= 0 || h <= 0 || !(scale > 0.f)) return B200_ERR_INVALID_ARG;
+  if (head_dim != HD || (ld_tok % 8) || (ld_out % 8) || (ld_dtok % 8)) return B200_ERR_UNSUPPORTED;
+  if (((uintptr_t)qkv & 15) || ((uintptr_t)out & 15) || ((uintptr_t)dout & 15) || ((uintptr_t)dqkv & 15)) return B200_ERR_UNSUPPORTED;
+  if (N > 208) return B200_ERR_UNSUPPORTED;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nb = (N + 15) / 16;
+  if (nb <= 4) return launch_bwd<4>(qkv, ld_tok, out, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, dqkv_colsum, s);
+  return launch_bwd<13>(qkv, ld_tok, out, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, dqkv_colsum, s);
 }

@@ -110,16 +110,24 @@ def _L():
     return _lib.lib()
 
 
+# Sequence lengths the tcgen05 attention kernels take (global crops: N = 197 / 201 / ...); the rest stay on the
+# warp-level kernels.  Module switches so that tests / A-B timing can pin either implementation.
+TC_ATTENTION_FWD = True
+TC_ATTENTION_BWD = True
+
+
 def attention_fwd(qkv: torch.Tensor, B: int, N: int, h: int, out: torch.Tensor, lse: torch.Tensor | None,
                   scale: float) -> None:
     """qkv bf16 [B*N, 3*h*64]; out bf16 [B*N, h*64]; lse f32 [B*h, N]."""
     _req_cuda(qkv, out, lse)
+    if TC_ATTENTION_FWD and 128 < N <= 256:
+        return attention_fwd_tc(qkv, B, N, h, out, lse, scale)
     check(_L().b200_attention_fwd(qkv.data_ptr(), qkv.stride(0), B, N, h, 64, scale, out.data_ptr(), out.stride(0),
                                   _ptr(lse), _stream()), "b200_attention_fwd")
 
 
 def attention_fwd_tc(qkv, B: int, N: int, h: int, out, lse, scale: float) -> None:
-    """tcgen05 forward (bring-up, not used by the model: csrc/attention_tc.cu); same contract as attention_fwd, N <= 256."""
+    """tcgen05 / TMEM / TMA forward (csrc/attention_tc.cu); same contract as attention_fwd, N <= 256."""
     _req_cuda(qkv, out)
     check(_L().b200_attention_fwd_tc(qkv.data_ptr(), qkv.stride(0), B, N, h, 64, scale, out.data_ptr(), out.stride(0),
                                      _ptr(lse), _stream()), "b200_attention_fwd_tc")
@@ -129,9 +137,20 @@ def attention_bwd(qkv, out, dout, lse, B: int, N: int, h: int, dqkv, scale: floa
     """colsum (optional f32 [3*h*64]): += column sums of dqkv, i.e. the gradient of the qkv projection's bias."""
     _req_cuda(qkv, out, dout, lse, dqkv)
     assert out.stride(0) == dout.stride(0)
+    if TC_ATTENTION_BWD and 128 < N <= 208:
+        return attention_bwd_tc(qkv, out, dout, lse, B, N, h, dqkv, scale, colsum)
     check(_L().b200_attention_bwd(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), dout.data_ptr(), dout.stride(0),
                                   lse.data_ptr(), B, N, h, 64, scale, dqkv.data_ptr(), dqkv.stride(0), _ptr(colsum),
                                   _stream()), "b200_attention_bwd")
+
+
+def attention_bwd_tc(qkv, out, dout, lse, B: int, N: int, h: int, dqkv, scale: float, colsum=None) -> None:
+    """tcgen05 / TMEM / TMA backward (csrc/attention_tc.cu); same contract as attention_bwd, N <= 208."""
+    _req_cuda(qkv, out, dout, lse, dqkv)
+    assert out.stride(0) == dout.stride(0)
+    check(_L().b200_attention_bwd_tc(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), dout.data_ptr(), dout.stride(0),
+                                     lse.data_ptr(), B, N, h, 64, scale, dqkv.data_ptr(), dqkv.stride(0), _ptr(colsum),
+                                     _stream()), "b200_attention_bwd_tc")
 
 
 def layernorm_fwd(x, w, b, eps: float, y, mean=None, rstd=None) -> None:

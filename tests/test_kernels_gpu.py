@@ -142,18 +142,20 @@ def test_attention_fwd_bwd(B, N, h):
     torch.testing.assert_close(cs, ref, rtol=1e-4, atol=1e-3 * max(1.0, float(ref.abs().max())))
 
 
-@pytest.mark.skipif(__import__("os").environ.get("B200_TEST_TC_ATTENTION") != "1",
-                    reason="tcgen05 attention forward is a bring-up kernel (csrc/attention_tc.cu): opt in with B200_TEST_TC_ATTENTION=1")
-@pytest.mark.parametrize("B,N,h", [(3, 197, 6), (5, 37, 2), (2, 256, 3), (2, 130, 2), (1, 16, 1)])
+@pytest.mark.parametrize("B,N,h", [(3, 197, 6), (2, 201, 3), (5, 37, 2), (2, 256, 3), (2, 130, 2), (1, 16, 1)])
 def test_attention_fwd_tcgen05(B, N, h):
-    """Gate for switching the product path to the tcgen05 forward: same checks as the mma.sync kernel, plus agreement
-    with it (P is rounded before normalisation here, so the two differ by bf16 rounding only)."""
+    """tcgen05 / TMEM / TMA forward (the product path for 128 < N <= 256) against the fp32 torch statement and against
+    the warp-level kernel (P is rounded before normalisation here, so the two differ by bf16 rounding only)."""
     D = h * 64
     qkv = rnd(B * N, 3 * D, dtype=torch.bfloat16, scale=1.0, seed=10)
     out, ref = (torch.empty(B * N, D, device=dev, dtype=torch.bfloat16) for _ in range(2))
     lse, lse_ref = (torch.empty(B * h, N, device=dev) for _ in range(2))
     ops.attention_fwd_tc(qkv, B, N, h, out, lse, 0.125)
-    ops.attention_fwd(qkv, B, N, h, ref, lse_ref, 0.125)
+    ops.TC_ATTENTION_FWD = False
+    try:
+        ops.attention_fwd(qkv, B, N, h, ref, lse_ref, 0.125)
+    finally:
+        ops.TC_ATTENTION_FWD = True
     q5 = qkv.float().view(B, N, 3, h, 64).permute(2, 0, 3, 1, 4)
     s = (q5[0] * 0.125) @ q5[1].transpose(-1, -2)
     o = (s.softmax(-1) @ q5[2]).transpose(1, 2).reshape(B * N, D)
@@ -161,6 +163,38 @@ def test_attention_fwd_tcgen05(B, N, h):
     torch.testing.assert_close(lse.view(B, h, N), torch.logsumexp(s, -1), rtol=1e-2, atol=3e-2)
     torch.testing.assert_close(out.float(), ref.float(), rtol=2e-2, atol=2e-2)
     torch.testing.assert_close(lse, lse_ref, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("B,N,h", [(3, 197, 6), (2, 201, 3), (5, 37, 2), (2, 208, 1), (2, 130, 2)])
+def test_attention_bwd_tcgen05(B, N, h):
+    """tcgen05 backward (the product path for 128 < N <= 208): dq | dk | dv against torch autograd (fp32) and against the
+    warp-level kernel, and the fused qkv-bias gradient against the column sums of the bf16 dqkv it wrote."""
+    D = h * 64
+    qkv = rnd(B * N, 3 * D, dtype=torch.bfloat16, scale=1.0, seed=10)
+    do = rnd(B * N, D, dtype=torch.bfloat16, scale=1.0, seed=11)
+    out = torch.empty(B * N, D, device=dev, dtype=torch.bfloat16)
+    lse = torch.empty(B * h, N, device=dev)
+    ops.attention_fwd(qkv, B, N, h, out, lse, 0.125)
+    q5 = qkv.float().view(B, N, 3, h, 64).permute(2, 0, 3, 1, 4).clone().requires_grad_(True)
+    o = (((q5[0] * 0.125) @ q5[1].transpose(-1, -2)).softmax(-1) @ q5[2]).transpose(1, 2).reshape(B * N, D)
+    o.backward(do.float())
+    want = q5.grad.permute(1, 3, 0, 2, 4).reshape(B * N, 3 * D)
+    dq_t, dq_w = torch.full_like(qkv, 7.0), torch.empty_like(qkv)
+    cs = torch.ones(3 * D, device=dev)
+    ops.attention_bwd_tc(qkv, out, do, lse, B, N, h, dq_t, 0.125, colsum=cs)
+    ops.TC_ATTENTION_BWD = False
+    try:
+        ops.attention_bwd(qkv, out, do, lse, B, N, h, dq_w, 0.125)
+    finally:
+        ops.TC_ATTENTION_BWD = True
+    assert torch.isfinite(dq_t.float()).all()
+    for sl in (slice(0, D), slice(D, 2 * D), slice(2 * D, 3 * D)):
+        a, w, t = dq_t[:, sl].float(), dq_w[:, sl].float(), want[:, sl]
+        assert ((a - t).norm() / t.norm()).item() < 2e-2
+        assert (a - t).abs().max().item() < 0.05 * max(1.0, t.abs().max().item())
+        assert ((a - w).norm() / w.norm()).item() < 1e-2
+    ref = dq_t.float().sum(0) + 1
+    torch.testing.assert_close(cs, ref, rtol=1e-4, atol=1e-3 * max(1.0, float(ref.abs().max())))
 
 
 @pytest.mark.parametrize("T,D", [(1000, 384), (77, 128), (300, 1024), (64, 192)])
