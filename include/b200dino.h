@@ -81,6 +81,21 @@ int b200_attention_bwd_tc(const void* qkv, long long ld_tok, const void* out, co
                           const float* lse, int B, int N, int h, int head_dim, float scale, void* dqkv,
                           long long ld_dtok, float* dqkv_colsum, void* stream);
 /* ------------------------------------------------------------------------------------------------
+ * Distillation path (BASELINE cfg4): DINOv3 teacher RoPE and the DistillationV3 KL terms.
+ *
+ * b200_rope_apply: axial RoPE on q and k of the patch tokens (tokens >= prefix of every image), in place in the bf16
+ *   qkv buffer [B*N, 3*h*64]; sin/cos: f32 [N - prefix, 64].  out = x*cos + rotate_half(x)*sin in fp32, cast to bf16.
+ *   Replaces SelfAttention.apply_rope, LT/_models/dinov3/dinov3_src/layers/attention.py:21-33,79-100.
+ * b200_kl_rows: rows of KLDivLoss(reduction="batchmean")(log_softmax(s*inv_temp), softmax(t*inv_temp)):
+ *   loss_rows[r] = sum_k p_t (log p_t - log p_s); ds (optional) = gscale * d loss_rows[r] / d s[r, :].
+ *   Replaces the softmax / log_softmax / KLDivLoss chains of DistillationV3Loss.forward,
+ *   LT/_methods/distillationv3/distillationv3_loss.py:60-84 (queue logits) and :86-115 (token-token logits). */
+int b200_rope_apply(void* qkv, long long ld, int B, int N, int prefix, int h, int head_dim, const float* sin_tab,
+                    const float* cos_tab, void* stream);
+int b200_kl_rows(const float* s, long long lds, const float* t, long long ldt, int R, int K, float inv_temp, float gscale,
+                 float* loss_rows, float* ds, long long ldds, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Attention core for short sequences (head_dim 64), forward and backward.
  * Replaces LT/_models/dinov2_vit/dinov2_vit_src/layers/attention.py:55-63 (q*scale @ k^T, softmax, @ v) and
  * its autograd backward.  qkv: bf16 [B, N, 3, h, 64] with token pitch ld_tok; out/dout: bf16 [B, N, h*64]

@@ -112,8 +112,8 @@ def _L():
 
 # Sequence lengths the tcgen05 attention kernels take (global crops: N = 197 / 201 / ...); the rest stay on the
 # warp-level kernels.  Module switches so that tests / A-B timing can pin either implementation.
-TC_ATTENTION_FWD = True
-TC_ATTENTION_BWD = True
+TC_ATTENTION_FWD = False  # flipped to True once validated on hardware (tools/attn_check.py, tests/test_kernels_gpu.py)
+TC_ATTENTION_BWD = False
 
 
 def attention_fwd(qkv: torch.Tensor, B: int, N: int, h: int, out: torch.Tensor, lse: torch.Tensor | None,
@@ -328,3 +328,21 @@ def sumsq(x, out) -> None:
 def adamw_ema(args: AdamWArgs) -> None:
     nb = float(args.n) * ((20.0 + 20.0) if args.t else (16.0 + 14.0))
     _timed("adamw_ema", nb, lambda: check(_L().b200_adamw_ema(C.byref(args), _stream()), "b200_adamw_ema"))
+
+
+def rope_apply(qkv, B: int, N: int, prefix: int, h: int, sin_tab, cos_tab) -> None:
+    """In-place axial RoPE on q, k of the patch tokens; qkv bf16 [B*N, 3*h*64]; sin/cos f32 [N - prefix, 64]."""
+    _req_cuda(qkv, sin_tab, cos_tab)
+    assert sin_tab.dtype == cos_tab.dtype == torch.float32 and sin_tab.is_contiguous() and cos_tab.is_contiguous()
+    assert sin_tab.shape == (N - prefix, 64) == cos_tab.shape
+    check(_L().b200_rope_apply(qkv.data_ptr(), qkv.stride(0), B, N, prefix, h, 64, sin_tab.data_ptr(), cos_tab.data_ptr(),
+                               _stream()), "b200_rope_apply")
+
+
+def kl_rows(s, t, inv_temp: float, loss_rows, ds=None, gscale: float = 1.0) -> None:
+    """loss_rows[r] = KL(softmax(t[r] * inv_temp) || softmax(s[r] * inv_temp)); ds = gscale * d loss_rows / d s.  f32 2-D."""
+    _req_cuda(s, t, loss_rows, ds)
+    R, K = s.shape
+    assert s.dtype == t.dtype == torch.float32 and s.stride(1) == 1 and t.stride(1) == 1 and t.shape == s.shape
+    check(_L().b200_kl_rows(s.data_ptr(), s.stride(0), t.data_ptr(), t.stride(0), R, K, inv_temp, gscale, loss_rows.data_ptr(),
+                            _ptr(ds), ds.stride(0) if ds is not None else 0, _stream()), "b200_kl_rows")

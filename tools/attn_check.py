@@ -38,7 +38,6 @@ def check_fwd():
         torch.cuda.synchronize()
         ops.TC_ATTENTION_FWD = False
         ops.attention_fwd(qkv, B, N, h, ref, lse_ref, 0.125)
-        ops.TC_ATTENTION_FWD = True
         o, l, _ = ref_fwd_bwd(qkv, torch.zeros(B * N, D, device=dev), B, N, h)
         print(f"fwd B={B} N={N} h={h}: |out-torch| {(out.float() - o).abs().max().item():.4f}  |out-warp| "
               f"{(out.float() - ref.float()).abs().max().item():.4f}  |lse-torch| {(lse.view(B, h, N) - l).abs().max().item():.4f}  "
