@@ -466,8 +466,7 @@ class DINOv2(nn.Module):
         else:
             raise ValueError(f"Unknown centering method: {a.center_method}")
         ops.row_lse(t_logits[:n_crops], colterm_d, t_scale, t_rowterm[:n_crops], scale_dev=t_scale_dev)
-        if M:
-            ops.row_lse(t_logits[n_crops:], colterm_i, t_scale, t_rowterm[n_crops:], scale_dev=t_scale_dev)
+        # (the masked-patch rows' teacher log-sum-exp is computed inside the CE kernel: one HBM read of those logits)
 
         # ---------------- student forward (dinov2.py:474-519)
         sg = s_vit._fwd(gv, masks_u8, save=True, drop_path=True)
@@ -513,7 +512,7 @@ class DINOv2(nn.Module):
         ops.dino_ce(s_logits[:nd], t_logits[:n_crops], colterm_d, t_rowterm[:n_crops], idx0[:nd], idx1[:nd], wrow[:nd],
                     s_scale, t_scale, loss_rows[:nd], ds[:nd], gscale=a.dino_loss_weight, t_scale_dev=t_scale_dev)
         if M:
-            ops.dino_ce(s_logits[nd:], t_logits[n_crops:], colterm_i, t_rowterm[n_crops:], idx0[nd:], None, wrow[nd:],
+            ops.dino_ce(s_logits[nd:], t_logits[n_crops:], colterm_i, None, idx0[nd:], None, wrow[nd:],
                         s_scale, t_scale, loss_rows[nd:], ds[nd:], gscale=a.ibot_loss_weight, t_scale_dev=t_scale_dev)
         seg = self._segments(n_crops, nd, Rs)
         loss_terms = torch.zeros(3, device=dev, dtype=f32)

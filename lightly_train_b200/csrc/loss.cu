@@ -167,72 +167,151 @@ __global__ void vec_op_kernel(float* __restrict__ y, const float* __restrict__ x
 //   n_t   = number of paired teacher rows (1 or 2)
 //   loss  = w * ( n_t * LSE_s - s_scale * sum_k p_t[k] * s[k] )
 //   dS[k] = w * s_scale * ( n_t * softmax_s[k] - p_t[k] ) * gscale     (bf16, optional)
-// Pass 1 streams the student row (HBM) for (max,sum); pass 2 re-reads it (L2-resident: 128 KB/row),
-// streams the teacher row(s) once and writes the gradient row once.
-__global__ void __launch_bounds__(LOSS_THREADS)
+// Pass 1 streams the student row (HBM) for its log-sum-exp -- and, when t_rowterm is NULL (single-teacher rows: the iBOT
+// term), the paired teacher row for ITS log-sum-exp, so that the teacher logits are read from HBM once per step instead
+// of once by row_lse and once here.  Pass 2 re-reads the row(s) (L2-resident: 128 KB each), and writes the gradient row.
+// All exponentials are raw ex2 with log2(e) folded into the scales (MUFU time ~ HBM time for this kernel: 4.25 ex2 per
+// element against 6 bytes); two 16-byte loads per tensor are in flight per thread and iteration.
+struct MaxSum2 {  // running (max, sum 2^(v - max)) in the base-2 domain
+  float m, s;
+};
+__device__ __forceinline__ void ms2_add8(MaxSum2& a, const float (&z)[8]) {
+  float cm = fmaxf(fmaxf(fmaxf(z[0], z[1]), fmaxf(z[2], z[3])), fmaxf(fmaxf(z[4], z[5]), fmaxf(z[6], z[7])));
+  const float mn = fmaxf(a.m, cm);
+  float sum = a.s * ex2_ftz(a.m - mn);  // a.m = -inf on the first chunk: 2^-inf = 0
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum += ex2_ftz(z[i] - mn);
+  a.m = mn;
+  a.s = sum;
+}
+__device__ __forceinline__ MaxSum2 ms2_merge(MaxSum2 a, MaxSum2 b) {
+  const float m = fmaxf(a.m, b.m);
+  if (m == -INFINITY) return {m, 0.f};
+  return {m, a.s * ex2_ftz(a.m - m) + b.s * ex2_ftz(b.m - m)};
+}
+__device__ __forceinline__ MaxSum2 block_maxsum2(MaxSum2 v, MaxSum2* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    MaxSum2 w{__shfl_xor_sync(0xffffffffu, v.m, o), __shfl_xor_sync(0xffffffffu, v.s, o)};
+    v = ms2_merge(v, w);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  MaxSum2 r = (lane < nw) ? red[lane] : MaxSum2{-INFINITY, 0.f};
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    MaxSum2 w{__shfl_xor_sync(0xffffffffu, r.m, o), __shfl_xor_sync(0xffffffffu, r.s, o)};
+    r = ms2_merge(r, w);
+  }
+  return r;
+}
+
+// 256 threads, 4 CTAs per SM (64 registers): four rows in flight per SM hide each other's block barriers.
+static constexpr int CE_THREADS = 256;
+template <bool FUSE_T_LSE>
+__global__ void __launch_bounds__(CE_THREADS, 4)
 dino_ce_kernel(const __nv_bfloat16* __restrict__ s, long long lds, int Rs, int K, const __nv_bfloat16* __restrict__ t,
                long long ldt, const float* __restrict__ colterm, const float* __restrict__ t_rowterm,
                const int* __restrict__ t_idx0, const int* __restrict__ t_idx1, const float* __restrict__ weight,
                float s_scale, float t_scale, const float* __restrict__ t_scale_dev, float gscale,
                float* __restrict__ loss_rows, __nv_bfloat16* __restrict__ ds, long long ldds) {
-  __shared__ MaxSum red[32];
+  __shared__ MaxSum2 red[32];
+  __shared__ MaxSum2 red_t[32];
   __shared__ float redf[32];
+  constexpr float kL2e = 1.4426950408889634f;
   if (t_scale_dev) t_scale = __ldg(t_scale_dev);
   const int r = blockIdx.x;
   const float w = weight ? __ldg(weight + r) : 1.f;
   const int i0 = t_idx0[r];
-  const int i1 = t_idx1 ? t_idx1[r] : -1;
+  const int i1 = (!FUSE_T_LSE && t_idx1) ? t_idx1[r] : -1;
   const float n_t = (i1 >= 0) ? 2.f : 1.f;
   const __nv_bfloat16* sr = s + (size_t)r * lds;
   const __nv_bfloat16* t0 = t + (size_t)i0 * ldt;
   const __nv_bfloat16* t1 = (i1 >= 0) ? t + (size_t)i1 * ldt : nullptr;
-  const float rt0 = __ldg(t_rowterm + i0);
-  const float rt1 = (i1 >= 0) ? __ldg(t_rowterm + i1) : 0.f;
+  const float ss2 = s_scale * kL2e, ts2 = t_scale * kL2e;
+  const int step = blockDim.x * 8;
 
-  // pass 1: student log-sum-exp
-  MaxSum acc{-INFINITY, 0.f};
-  for (int k = threadIdx.x * 8; k < K; k += blockDim.x * 8) {
-    float v[8];
-    load8(sr + k, v);
-    float m = -INFINITY;
+  // pass 1: log-sum-exp of the student row (base 2), and of the teacher row when fused
+  MaxSum2 acc{-INFINITY, 0.f}, acc_t{-INFINITY, 0.f};
+  for (int k = threadIdx.x * 8; k < K; k += 2 * step) {
+    const bool two = k + step < K;
+    float v0[8], v1[8], u0[8], u1[8], c0[8], c1[8];
+    load8(sr + k, v0);
+    if (two) load8(sr + k + step, v1);
+    if (FUSE_T_LSE) {
+      load8(t0 + k, u0);
+      if (two) load8(t0 + k + step, u1);
+      if (colterm) {
+        load8f(colterm + k, c0);
+        if (two) load8f(colterm + k + step, c1);
+      }
+    }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { v[i] *= s_scale; m = fmaxf(m, v[i]); }
-    float sum = 0.f;
+    for (int i = 0; i < 8; ++i) v0[i] *= ss2;
+    ms2_add8(acc, v0);
+    if (two) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) sum += __expf(v[i] - m);
-    acc = ms_merge(acc, MaxSum{m, sum});
+      for (int i = 0; i < 8; ++i) v1[i] *= ss2;
+      ms2_add8(acc, v1);
+    }
+    if (FUSE_T_LSE) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) u0[i] = fmaf(u0[i], ts2, colterm ? c0[i] * kL2e : 0.f);
+      ms2_add8(acc_t, u0);
+      if (two) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) u1[i] = fmaf(u1[i], ts2, colterm ? c1[i] * kL2e : 0.f);
+        ms2_add8(acc_t, u1);
+      }
+    }
   }
-  MaxSum st = block_maxsum(acc, red);
-  const float lse = st.m + __logf(st.s);
+  const MaxSum2 st = block_maxsum2(acc, red);
+  const float lse2 = st.m + __log2f(st.s);           // base-2 LSE of s * s_scale
+  const float lse = lse2 * 0.6931471805599453f;
+  float rt0, rt1 = 0.f;                               // base-2 row terms: p = 2^(t*ts2 + c*log2e + rt)
+  if (FUSE_T_LSE) {
+    const MaxSum2 tt = block_maxsum2(acc_t, red_t);
+    rt0 = -(tt.m + __log2f(tt.s));
+  } else {
+    rt0 = __ldg(t_rowterm + i0) * kL2e;
+    if (i1 >= 0) rt1 = __ldg(t_rowterm + i1) * kL2e;
+  }
 
   // pass 2: dot(p_t, s) and gradient
   float dot = 0.f;
   const float gw = w * s_scale * gscale;
-  for (int k = threadIdx.x * 8; k < K; k += blockDim.x * 8) {
-    float sv[8], tv[8], c[8], p[8];
-    load8(sr + k, sv);
-    load8(t0 + k, tv);
-    if (colterm) load8f(colterm + k, c);
+  for (int k0 = threadIdx.x * 8; k0 < K; k0 += 2 * step) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (!colterm) c[i] = 0.f;
-      p[i] = __expf(tv[i] * t_scale + c[i] + rt0);
-    }
-    if (t1) {
-      load8(t1 + k, tv);
+    for (int u = 0; u < 2; ++u) {
+      const int k = k0 + u * step;
+      if (k >= K) break;
+      float sv[8], tv[8], c[8], p[8];
+      load8(sr + k, sv);
+      load8(t0 + k, tv);
+      if (colterm) load8f(colterm + k, c);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) p[i] += __expf(tv[i] * t_scale + c[i] + rt1);
-    }
+      for (int i = 0; i < 8; ++i) {
+        c[i] = colterm ? c[i] * kL2e : 0.f;
+        p[i] = ex2_ftz(fmaf(tv[i], ts2, c[i] + rt0));
+      }
+      if (t1) {
+        load8(t1 + k, tv);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) dot += p[i] * sv[i];
-    if (ds) {
-      float g[8];
+        for (int i = 0; i < 8; ++i) p[i] += ex2_ftz(fmaf(tv[i], ts2, c[i] + rt1));
+      }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) g[i] = gw * (n_t * __expf(sv[i] * s_scale - lse) - p[i]);
-      uint4 o;
-      o.x = pack_bf16x2(g[0], g[1]); o.y = pack_bf16x2(g[2], g[3]);
-      o.z = pack_bf16x2(g[4], g[5]); o.w = pack_bf16x2(g[6], g[7]);
-      *reinterpret_cast<uint4*>(ds + (size_t)r * ldds + k) = o;
+      for (int i = 0; i < 8; ++i) dot = fmaf(p[i], sv[i], dot);
+      if (ds) {
+        float g[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = gw * (n_t * ex2_ftz(fmaf(sv[i], ss2, -lse2)) - p[i]);
+        uint4 o;
+        o.x = pack_bf16x2(g[0], g[1]); o.y = pack_bf16x2(g[2], g[3]);
+        o.z = pack_bf16x2(g[4], g[5]); o.w = pack_bf16x2(g[6], g[7]);
+        *reinterpret_cast<uint4*>(ds + (size_t)r * ldds + k) = o;
+      }
     }
   }
   dot = block_sum(dot, redf);
@@ -401,12 +480,19 @@ extern "C" int b200_dino_ce(const void* s, long long lds, int Rs, int K, const v
                             const float* colterm, const float* t_rowterm, const int* t_idx0, const int* t_idx1,
                             const float* weight, float s_scale, float t_scale, const float* t_scale_dev, float gscale,
                             float* loss_rows, void* ds, long long ldds, void* stream) {
-  if (!s || !t || !t_rowterm || !t_idx0 || !loss_rows || Rs <= 0 || K <= 0) return B200_ERR_INVALID_ARG;
+  if (!s || !t || !t_idx0 || !loss_rows || Rs <= 0 || K <= 0) return B200_ERR_INVALID_ARG;
+  if (!t_rowterm && t_idx1) return B200_ERR_INVALID_ARG;  // the fused teacher LSE covers single-teacher rows only
   if ((K % 8) || (lds % 8) || (ldt % 8) || (ds && (ldds % 8))) return B200_ERR_INVALID_ARG;
-  dino_ce_kernel<<<Rs, LOSS_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)s, lds, Rs, K,
-                                                                 (const __nv_bfloat16*)t, ldt, colterm, t_rowterm, t_idx0,
-                                                                 t_idx1, weight, s_scale, t_scale, t_scale_dev, gscale,
-                                                                 loss_rows, (__nv_bfloat16*)ds, ldds);
+  if (t_rowterm)
+    dino_ce_kernel<false><<<Rs, CE_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)s, lds, Rs, K,
+                                                                          (const __nv_bfloat16*)t, ldt, colterm, t_rowterm, t_idx0,
+                                                                          t_idx1, weight, s_scale, t_scale, t_scale_dev, gscale,
+                                                                          loss_rows, (__nv_bfloat16*)ds, ldds);
+  else
+    dino_ce_kernel<true><<<Rs, CE_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)s, lds, Rs, K,
+                                                                         (const __nv_bfloat16*)t, ldt, colterm, nullptr, t_idx0,
+                                                                         nullptr, weight, s_scale, t_scale, t_scale_dev, gscale,
+                                                                         loss_rows, (__nv_bfloat16*)ds, ldds);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

@@ -296,10 +296,13 @@ def vec_op(y, x, a: float, b: float, op: int, a_dev=None) -> None:
 
 def dino_ce(s, t, colterm, t_rowterm, t_idx0, t_idx1, weight, s_scale: float, t_scale: float, loss_rows, ds=None,
             gscale: float = 1.0, t_scale_dev=None) -> None:
+    """t_rowterm=None (single-teacher rows only): the kernel computes the teacher rows' log-sum-exp itself in its first
+    pass (the teacher logits are then read from HBM once per step instead of twice)."""
     Rs, K = s.shape
-    _timed("dino_ce", (4.0 if ds is not None else 2.0) * Rs * K, lambda: check(
+    nbytes = ((4.0 if ds is not None else 2.0) + (2.0 if t_rowterm is None else 0.0)) * Rs * K
+    _timed("dino_ce", nbytes, lambda: check(
         _L().b200_dino_ce(s.data_ptr(), s.stride(0), Rs, K, t.data_ptr(), t.stride(0), _ptr(colterm),
-                          t_rowterm.data_ptr(), t_idx0.data_ptr(), _ptr(t_idx1), _ptr(weight), s_scale, t_scale, _ptr(t_scale_dev), gscale,
+                          _ptr(t_rowterm), t_idx0.data_ptr(), _ptr(t_idx1), _ptr(weight), s_scale, t_scale, _ptr(t_scale_dev), gscale,
                           loss_rows.data_ptr(), _ptr(ds), ds.stride(0) if ds is not None else 0, _stream()), "b200_dino_ce"))
 
 

@@ -400,6 +400,18 @@ def test_loss_kernels(K):
     (ref_rows.sum() * 2.0).backward()
     err = (ds.float() - sf.grad).abs().max().item()
     assert err <= 1e-2 * sf.grad.abs().max().item() + 1e-8, err
+    # single-teacher rows with the teacher log-sum-exp fused into the CE kernel (t_rowterm=None: the iBOT term)
+    loss2, ds2 = torch.empty(Rs, device=dev), torch.empty(Rs, K, device=dev, dtype=torch.bfloat16)
+    ops.dino_ce(s, t, colterm, None, i0, None, w, s_scale, t_scale, loss2, ds2, gscale=2.0)
+    sf2 = s.float().requires_grad_(True)
+    ref2 = -(probs[i0.long()] * F.log_softmax(sf2 * s_scale, -1)).sum(-1) * w
+    torch.testing.assert_close(loss2, ref2, rtol=1e-4, atol=1e-4)
+    (ref2.sum() * 2.0).backward()
+    assert (ds2.float() - sf2.grad).abs().max().item() <= 1e-2 * sf2.grad.abs().max().item() + 1e-8
+    loss3 = torch.empty(Rs, device=dev)
+    ops.dino_ce(s, t, None, None, i0, None, None, s_scale, t_scale, loss3)  # no colterm / weights / gradient
+    ref3 = -(torch.softmax(t.float() * t_scale, -1)[i0.long()] * F.log_softmax(s.float() * s_scale, -1)).sum(-1)
+    torch.testing.assert_close(loss3, ref3, rtol=1e-4, atol=1e-4)
     # column reductions
     cs = torch.zeros(K, device=dev)
     ops.col_reduce(t, cs)
