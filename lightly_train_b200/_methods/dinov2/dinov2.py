@@ -331,7 +331,9 @@ class DINOv2(nn.Module):
         self._side_stream = torch.cuda.Stream(device=self.device_) if self.device_.type == "cuda" else None
         self._comm_stream = torch.cuda.Stream(device=self.device_) if self.device_.type == "cuda" else None
         self._head_ready = torch.cuda.Event() if self.device_.type == "cuda" else None
+        self._mid_ready = torch.cuda.Event() if self.device_.type == "cuda" else None
         self._head_work = None
+        self._mid_work = None
         self._head_off = self.s_arena.offsets["dino_head.mlp.0.weight"][0]  # arena order: backbone.*, then the heads
 
     # ------------------------------------------------------------------ the step
@@ -346,6 +348,24 @@ class DINOv2(nn.Module):
         self._comm_stream.wait_event(self._head_ready)
         with torch.cuda.stream(self._comm_stream):
             self._head_work = dist.all_reduce(self.s_arena.grad[self._head_off:], async_op=True)
+
+    def _backbone_split(self) -> int:
+        """Block index at which the backbone backward is cut for the second overlapped all-reduce (0: no cut)."""
+        nb = self.s_vit.n_blocks
+        return nb // 2 if nb >= 4 else 0
+
+    def _allreduce_upper_backbone_async(self, split_at: int) -> None:
+        """Data-parallel runs: all-reduce the gradients of blocks >= split_at and of `norm` (contiguous in the arena, final
+        after `_core_b(split_at=...)`) on the communication stream while `_core_b2` runs."""
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        lo = self.s_arena.offsets[f"backbone.blocks.{split_at}.norm1.weight"][0]
+        hi = self.s_arena.offsets["backbone.mask_token"][0]  # arena order: ..., blocks.*, norm.*, mask_token, heads
+        main = torch.cuda.current_stream()
+        self._mid_ready.record(main)
+        self._comm_stream.wait_event(self._mid_ready)
+        with torch.cuda.stream(self._comm_stream):
+            self._mid_work = (dist.all_reduce(self.s_arena.grad[lo:hi], async_op=True), lo, hi)
 
     def _masks(self, n_crops: int, h: int, w: int):
         a = self.method_args
@@ -376,7 +396,11 @@ class DINOv2(nn.Module):
             self.ibot_loss.apply_center_update()
         st = self._core_a(gv, lv, collated.to(torch.uint8), mask_idx, masks_weight, 1.0 / teacher_temp, None, None, None)
         self._allreduce_head_grads_async()
-        out = self._core_b(st)
+        split_at = self._backbone_split()
+        out = self._core_b(st, split_at)
+        if split_at > 0:
+            self._allreduce_upper_backbone_async(split_at)
+            out = self._core_b2(st)
         if a.center_method == "softmax":
             self.dino_loss._launch_reduce(out["dino_center_sum"], gv.shape[0])
             if mask_idx.shape[0]:
@@ -535,8 +559,9 @@ class DINOv2(nn.Module):
         return dict(out=out, loss_terms=loss_terms, sg=sg, sl=sl, dx_d=dx_d, dxn_g=dxn_g, n_crops=n_crops, B=B, Ng=Ng,
                     lcls_rows=lcls_rows)
 
-    def _core_b(self, st: Dict[str, Any]) -> Dict[str, Tensor]:
-        """Second half: KoLeo and the backbone backward (local crops, then global crops)."""
+    def _core_b(self, st: Dict[str, Any], split_at: int = 0) -> Dict[str, Tensor]:
+        """Second half: KoLeo and the backbone backward (local crops, then global crops).  split_at > 0 stops the
+        global-crop backward before block `split_at - 1` (continued by `_core_b2`)."""
         a = self.method_args
         dev = self.device_
         f32 = torch.float32
@@ -567,9 +592,22 @@ class DINOv2(nn.Module):
             del sl, dxn_l
         if side is not None:
             main.wait_stream(side)
-        s_vit._bwd(sg, dxn_g)
         out["loss_terms"], out["koleo"] = loss_terms, koleo
+        if split_at <= 0:
+            s_vit._bwd(sg, dxn_g)
+            return out
+        # first segment of the global-crop backward: final LayerNorm + blocks nb-1 .. split_at.  When it returns, the
+        # gradients of those blocks and of `norm` are final (the local-crop pass above already added its share): their
+        # all-reduce overlaps `_core_b2`
+        st["bwd_state"] = s_vit._bwd(sg, dxn_g, stop_before=split_at)
+        st["sg"], st["out"] = sg, out
         return out
+
+    def _core_b2(self, st: Dict[str, Any]) -> Dict[str, Tensor]:
+        """Last segment: global-crop backward of blocks split-1 .. 0 and the embeddings."""
+        sg, state = st.pop("sg"), st.pop("bwd_state")
+        self.s_vit._bwd(sg, None, state=state)
+        return st.pop("out")
 
     def _segments(self, n_crops: int, nd: int, Rs: int) -> Tensor:
         key = (n_crops, nd, Rs)
@@ -634,27 +672,41 @@ class DINOv2(nn.Module):
             return self._core_a(st["gv"], st["lv"], st["masks_u8"], st["idx"][:cap], st["mw"][:cap], 0.0, st["t_scale"],
                                 st["iw"][:cap], st["m_valid"])
 
+        split_at = self._backbone_split()
         entry = st["graphs"].get(cap)
         if entry is None:
-            self._core_b(run_a())  # eager warm-up at this shape (no collective: ranks reach new shapes at different steps)
+            warm = run_a()  # eager warm-up at this shape (no collective: ranks reach new shapes at different steps)
+            self._core_b(warm, split_at)
+            if split_at > 0:
+                self._core_b2(warm)
+            del warm
             torch.cuda.synchronize()
-            # two graphs sharing one memory pool: [teacher, student fwd, losses, head bwd] and [backbone bwd]; the head
-            # gradients' all-reduce is issued between the two replays and overlaps the second
-            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            # three graphs sharing one memory pool: [teacher, student fwd, losses, head bwd] | [local-crop backward, upper
+            # half of the global-crop backward] | [lower half + embeddings]; the all-reduce of the gradients that are final
+            # after each graph is issued between the replays and overlaps the next one
+            g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             n0 = _lib.LAUNCHES
             with torch.cuda.graph(g1, pool=st["pool"], capture_error_mode="thread_local"):  # NCCL watchdog thread may touch CUDA
                 mid = run_a()
             if st["pool"] is None:
                 st["pool"] = g1.pool()
             with torch.cuda.graph(g2, pool=st["pool"], capture_error_mode="thread_local"):
-                outs = self._core_b(mid)
+                outs = self._core_b(mid, split_at)
+            if split_at > 0:
+                with torch.cuda.graph(g3, pool=st["pool"], capture_error_mode="thread_local"):
+                    outs = self._core_b2(mid)
+            else:
+                g3 = None
             n_captured = _lib.LAUNCHES - n0
             _lib.LAUNCHES = n0  # captured, not executed; every replay executes all of them
-            entry = st["graphs"][cap] = (g1, g2, outs, n_captured)
-        g1, g2, outs, n_captured = entry
+            entry = st["graphs"][cap] = (g1, g2, g3, outs, n_captured)
+        g1, g2, g3, outs, n_captured = entry
         g1.replay()
         self._allreduce_head_grads_async()
         g2.replay()
+        if g3 is not None:
+            self._allreduce_upper_backbone_async(split_at)
+            g3.replay()
         _lib.LAUNCHES += n_captured
         self.dino_loss._launch_reduce(outs["dino_center_sum"], 2 * B)
         self.ibot_loss._launch_reduce(outs["ibot_center_sum"], 1)
@@ -741,19 +793,32 @@ class DINOv2(nn.Module):
         self.trainer.global_step += 1
         self.on_train_batch_end(None, None, 0)
 
+    def _finish_grad_allreduce(self) -> None:
+        """DDP gradient all-reduce (sum; the mean is folded into the sweep's grad_scale): reduce whatever part of the arena
+        is not already in flight and make the current stream wait for the parts that are (the host never blocks)."""
+        if self._head_work is not None:
+            # the head part (and, when the backward was cut, blocks >= split and `norm`) are already in flight
+            if self._mid_work is not None:
+                work, lo, hi = self._mid_work
+                dist.all_reduce(self.s_arena.grad[:lo])
+                dist.all_reduce(self.s_arena.grad[hi:self._head_off])  # mask_token
+                work.wait()
+                self._mid_work = None
+            else:
+                dist.all_reduce(self.s_arena.grad[:self._head_off])
+            self._head_work.wait()
+            self._head_work = None
+        else:
+            dist.all_reduce(self.s_arena.grad)
+
     def _fused_sweep(self, opt: "FusedAdamWEMA", lr: float, fuse_ema: bool = True) -> None:
         """all-reduce(grad) -> deterministic sum of squares -> ONE sweep: clip + AdamW (per-chunk lr/wd, freezes) + EMA
         teacher + bf16 shadows of student and teacher."""
         a = self.method_args
         max_steps = self.trainer.estimated_stepping_batches
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        if world > 1:  # DDP gradient all-reduce (sum); mean applied via grad_scale
-            if self._head_work is not None:
-                dist.all_reduce(self.s_arena.grad[:self._head_off])  # backbone part; the head part is already in flight
-                self._head_work.wait()                               # (stream-side wait, the host does not block)
-                self._head_work = None
-            else:
-                dist.all_reduce(self.s_arena.grad)
+        if world > 1:
+            self._finish_grad_allreduce()
         ops.fill_f32(self.gradnorm_sq, 0.0)
         ops.sumsq(self.s_arena.grad, self.gradnorm_sq)
         # on_train_batch_end runs after Lightning has incremented global_step: the momentum index is step + 1

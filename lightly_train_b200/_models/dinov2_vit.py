@@ -320,8 +320,14 @@ class DinoVisionTransformer(nn.Module):
         return ctx
 
     # ------------------------------------------------------------------ backward
-    def _bwd(self, ctx: VitCtx, d_xnorm: Tensor, wgrad_splits: int = 0) -> None:
-        """d_xnorm: f32 [T, D] gradient wrt the final-LayerNorm output. Accumulates into the gradient arena."""
+    def _bwd(self, ctx: VitCtx, d_xnorm: Optional[Tensor], wgrad_splits: int = 0, stop_before: int = 0,
+             state: Optional[dict] = None) -> Optional[dict]:
+        """d_xnorm: f32 [T, D] gradient wrt the final-LayerNorm output. Accumulates into the gradient arena.
+
+        The schedule can be cut between blocks: `stop_before=k` (k > 0) runs the final LayerNorm and blocks nb-1 .. k and
+        returns a state; a second call with `state=` runs blocks k-1 .. 0 and the embeddings.  After the first segment of
+        the LAST backward pass of a step the gradients of blocks >= k and of `norm` are final, so their all-reduce can
+        overlap the second segment (DINOv2._core_b1 / _core_b2)."""
         Bc, Np, R, N, T, H, Wimg = ctx.dims
         D, Hd, h = self.embed_dim, self.hidden_dim, self.num_heads
         dev = d_xnorm.device
@@ -338,7 +344,8 @@ class DinoVisionTransformer(nn.Module):
 
         ls = self.layerscale
         nb = self.n_blocks
-        dx = E(T, D, dt=f32)
+        resume = state is not None
+        dx = state["dx"] if resume else E(T, D, dt=f32)
         # final LayerNorm backward, fused with the LayerScale backward of the last block's MLP branch
         def materialise(j: int) -> dict:
             """Recompute the activations of a checkpointed block from its saved input (same DropPath scales)."""
@@ -349,14 +356,19 @@ class DinoVisionTransformer(nn.Module):
                 ctx.blocks[j] = blk
             return blk
 
-        last = materialise(nb - 1)
-        bl = f"blocks.{nb - 1}."
-        do2 = E(T, D)
-        ops.layernorm_bwd_ls(d_xnorm, ctx.x_prenorm, self._P("norm.weight"), ctx.meanf, ctx.rstdf, dx, False,
-                             self._G("norm.weight"), self._G("norm.bias"), last["o2"],
-                             self._P(bl + "ls2.gamma") if ls else None, last["rs2"], N, do2,
-                             self._G(bl + "ls2.gamma") if ls else None, self._G(bl + self._ffn_out + "bias"))
-        for i in reversed(range(nb)):
+        if resume:
+            do2 = state["do2"]
+            hi = state["next"]
+        else:
+            last = materialise(nb - 1)
+            bl = f"blocks.{nb - 1}."
+            do2 = E(T, D)
+            ops.layernorm_bwd_ls(d_xnorm, ctx.x_prenorm, self._P("norm.weight"), ctx.meanf, ctx.rstdf, dx, False,
+                                 self._G("norm.weight"), self._G("norm.bias"), last["o2"],
+                                 self._P(bl + "ls2.gamma") if ls else None, last["rs2"], N, do2,
+                                 self._G(bl + "ls2.gamma") if ls else None, self._G(bl + self._ffn_out + "bias"))
+            hi = nb - 1
+        for i in range(hi, stop_before - 1, -1):
             b = f"blocks.{i}."
             sv = ctx.blocks[i]
             # ---- MLP branch (do2 = gradient of the fc2 output, produced by the fused kernel above / below)
@@ -403,6 +415,8 @@ class DinoVisionTransformer(nn.Module):
                 ops.layernorm_bwd(dxn, sv["x_in"], self._P(b + "norm1.weight"), sv["mean1"], sv["rstd1"], dx, True,
                                   self._G(b + "norm1.weight"), self._G(b + "norm1.bias"))
             ctx.blocks[i] = None  # free activations early
+        if stop_before > 0:
+            return {"dx": dx, "do2": do2, "next": stop_before - 1}
         # ---- embeddings
         dtok = E(Bc * Np, D)
         gpos = self._G("pos_embed")[0]

@@ -64,12 +64,8 @@ for center_method in ("softmax", "sinkhorn_knopp"):
     w = O.masks_weight_from_masks(masks)
     res = m.training_step_impl({"views": [v.to(dev) for v in views],
                                 "masks": {"collated_masks": masks, "mask_indices_list": idx, "masks_weight": w}}, 0)
+    m._finish_grad_allreduce()  # the product's own bucketed reduction (head | upper backbone | rest)
     torch.cuda.synchronize()
-    if m._head_work is not None:
-        m._head_work.wait(); m._head_work = None
-        dist.all_reduce(m.s_arena.grad[:m._head_off])
-    else:
-        dist.all_reduce(m.s_arena.grad)
     loss = res.loss.detach().clone()
     dist.all_reduce(loss)
     loss /= world
