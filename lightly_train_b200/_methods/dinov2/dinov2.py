@@ -421,7 +421,7 @@ class DINOv2(nn.Module):
 
     def _core_a(self, gv: Tensor, lv: Optional[Tensor], masks_u8: Tensor, mask_idx: Tensor, masks_weight: Tensor,
                 t_scale: float, t_scale_dev: Optional[Tensor], ibot_rowvec: Optional[Tensor],
-                m_valid_dev: Optional[Tensor]) -> Dict[str, Any]:
+                m_valid_dev: Optional[Tensor], pad_mask: Optional[Tensor] = None) -> Dict[str, Any]:
         """First half of the device schedule of one step: teacher, student forward, losses, HEAD backward.  When it
         returns, the gradients of the projection heads (the tail of the flat arena, half of all parameters) are final,
         so their all-reduce can overlap `_core_b` (the backbone backward).  Shapes depend only on the arguments' shapes, every per-step scalar is
@@ -482,11 +482,11 @@ class DINOv2(nn.Module):
                 rv = ibot_rowvec if ibot_rowvec is not None else torch.full((M,), 1.0 / M, device=dev, dtype=f32)
                 ops.col_reduce(t_logits[n_crops:], out["ibot_center_sum"], rowvec=rv)
         elif a.center_method == "sinkhorn_knopp":
-            if t_scale_dev is not None:
-                raise NotImplementedError("Sinkhorn-Knopp centering runs on the eager schedule (needs mid-step all-reduce)")
-            colterm_d = sinkhorn_colterm(t_logits[:n_crops], t_scale)
+            # (graph replay: single-rank only -- with several ranks the prototype sums are all-reduced in the middle of
+            # this schedule, which stays on the eager launch path; `train_step` routes accordingly)
+            colterm_d = sinkhorn_colterm(t_logits[:n_crops], t_scale, scale_dev=t_scale_dev)
             if M:
-                colterm_i = sinkhorn_colterm(t_logits[n_crops:], t_scale)
+                colterm_i = sinkhorn_colterm(t_logits[n_crops:], t_scale, scale_dev=t_scale_dev, row_mask=pad_mask)
         else:
             raise ValueError(f"Unknown centering method: {a.center_method}")
         ops.row_lse(t_logits[:n_crops], colterm_d, t_scale, t_rowterm[:n_crops], scale_dev=t_scale_dev)
@@ -637,6 +637,7 @@ class DINOv2(nn.Module):
                 "idx": torch.zeros(cap_max, device=dev, dtype=torch.int64),
                 "mw": torch.zeros(cap_max, device=dev, dtype=torch.float32),
                 "iw": torch.zeros(cap_max, device=dev, dtype=torch.float32),
+                "pad": torch.zeros(cap_max, device=dev, dtype=torch.float32),
                 "m_valid": torch.zeros(1, device=dev, dtype=torch.int32),
                 "t_scale": torch.zeros(1, device=dev, dtype=torch.float32),
                 "graphs": {}, "pool": None,
@@ -660,17 +661,20 @@ class DINOv2(nn.Module):
         st["idx"][:cap].copy_(idx_h, non_blocking=True)
         st["mw"][:cap].copy_(mw_h, non_blocking=True)
         st["iw"][:cap].copy_(iw_h, non_blocking=True)
+        pad_h = torch.full((cap,), -1e30, dtype=torch.float32); pad_h[:M] = 0.0
+        st["pad"][:cap].copy_(pad_h, non_blocking=True)
         st["m_valid"].fill_(M)
         st["t_scale"].fill_(1.0 / teacher_temp)
         for arena in (self.s_arena, self.t_arena):
             if not arena.bf16_valid:
                 arena.refresh_bf16()
-        self.dino_loss.apply_center_update()
-        self.ibot_loss.apply_center_update()
+        if a.center_method == "softmax":
+            self.dino_loss.apply_center_update()
+            self.ibot_loss.apply_center_update()
 
         def run_a() -> Dict[str, Any]:
             return self._core_a(st["gv"], st["lv"], st["masks_u8"], st["idx"][:cap], st["mw"][:cap], 0.0, st["t_scale"],
-                                st["iw"][:cap], st["m_valid"])
+                                st["iw"][:cap], st["m_valid"], st["pad"][:cap])
 
         split_at = self._backbone_split()
         entry = st["graphs"].get(cap)
@@ -708,15 +712,16 @@ class DINOv2(nn.Module):
             self._allreduce_upper_backbone_async(split_at)
             g3.replay()
         _lib.LAUNCHES += n_captured
-        self.dino_loss._launch_reduce(outs["dino_center_sum"], 2 * B)
-        self.ibot_loss._launch_reduce(outs["ibot_center_sum"], 1)
+        if a.center_method == "softmax":
+            self.dino_loss._launch_reduce(outs["dino_center_sum"], 2 * B)
+            self.ibot_loss._launch_reduce(outs["ibot_center_sum"], 1)
         return self._result(outs)
 
     # ------------------------------------------------------------------ Method surface (LT/_methods/method.py:131-148)
     def training_step(self, batch: Dict[str, Any], batch_idx: int = 0) -> Tensor:
         """Method.training_step: run the step, log `train_loss` + the log_dict with sync_dist=True semantics (cross-rank
         mean; ONE tiny all-reduce for all five scalars), return the loss."""
-        if self.use_cuda_graph and self.method_args.center_method == "softmax":
+        if self._graph_ok():
             res = self._graphed_step(batch)
         else:
             res = self.training_step_impl(batch, batch_idx)
@@ -870,9 +875,18 @@ class DINOv2(nn.Module):
         make `backward()` a no-op instead of an error ('autograd bridge')."""
         return result.loss.detach().requires_grad_(True)
 
+    def _graph_ok(self) -> bool:
+        """CUDA-graph replay of the step: always for softmax centering; for Sinkhorn-Knopp only on a single rank (its
+        per-iteration all-reduce sits in the middle of the captured schedule)."""
+        if not self.use_cuda_graph:
+            return False
+        if self.method_args.center_method == "softmax":
+            return True
+        return not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
+
     def train_step(self, batch: Dict[str, Any]) -> TrainingStepResult:
         """One full optimisation step: what Lightning's fit loop does around training_step."""
-        if self.use_cuda_graph and self.method_args.center_method == "softmax":
+        if self._graph_ok():
             res = self._graphed_step(batch)
         else:
             res = self.training_step_impl(batch, 0)

@@ -51,26 +51,31 @@ def _as_bf16_2d(x: Tensor) -> Tensor:
     return x.contiguous()
 
 
-def sinkhorn_colterm(logits: Tensor, t_scale: float, n_iterations: int = 3) -> Tensor:
+def sinkhorn_colterm(logits: Tensor, t_scale: float, n_iterations: int = 3, scale_dev: Optional[Tensor] = None,
+                     row_mask: Optional[Tensor] = None) -> Tensor:
     """log u of the Sinkhorn-Knopp diagonal scaling Q = diag(u) exp(t/T)^T diag(v)  (dinov2_loss.py:84-115).
 
     Each iteration = one weighted column reduction (prototype sums, all-reduced over ranks) + one row LSE.
     Scalar normalisations of the reference (sum_Q, /K, /B, *B) cancel in the final column normalisation, which
     the caller performs as rowterm = -LSE_k(t/T + log u).
+    scale_dev: 1/T read from device memory (CUDA-graph replay).  row_mask (f32 [R], 0 for real rows, -1e30 for the padding
+    rows of a static-shape replay): added to log v so that padding rows carry no mass in the prototype sums.
     """
     R, K = logits.shape
     dev = logits.device
-    logv = torch.zeros(R, device=dev, dtype=torch.float32)
+    logv = torch.zeros(R, device=dev, dtype=torch.float32) if row_mask is None else row_mask.clone()
     logu = torch.empty(K, device=dev, dtype=torch.float32)
     sums = torch.empty(K, device=dev, dtype=torch.float32)
     for it in range(n_iterations):
         ops.fill_f32(sums, 0.0)
-        ops.col_reduce(logits, sums, rowvec=logv, scale=t_scale, mode=1)
+        ops.col_reduce(logits, sums, rowvec=logv, scale=t_scale, mode=1, scale_dev=scale_dev)
         if _world() > 1:
             dist.all_reduce(sums)
         ops.vec_op(logu, sums, 0.0, 0.0, 2)  # logu = -log(sums)
         if it + 1 < n_iterations:
-            ops.row_lse(logits, logu, t_scale, logv)  # log v = -LSE_k(t/T + log u)
+            ops.row_lse(logits, logu, t_scale, logv, scale_dev=scale_dev)  # log v = -LSE_k(t/T + log u)
+            if row_mask is not None:
+                logv.add_(row_mask)
     return logu
 
 

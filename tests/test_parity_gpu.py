@@ -191,11 +191,13 @@ def test_two_steps_run_and_loss_is_finite():
     assert torch.isfinite(res.loss).item()
 
 
-def test_cuda_graph_replay_matches_eager_schedule():
+@pytest.mark.parametrize("center_method,separate", [("softmax", False), ("sinkhorn_knopp", True)])
+def test_cuda_graph_replay_matches_eager_schedule(center_method, separate):
     """The padded, static-shape CUDA-graph replay of the step must reproduce the eager launch schedule: same loss
     terms, same gradients (fp32 atomics reorder sums: 1e-5), same center sums -- including the masked-token
-    padding rows (M is padded to a multiple of 512) being inert."""
-    cfg = R.step_config("softmax", False)
+    padding rows (M is padded to a multiple of 512) being inert (for Sinkhorn-Knopp: carrying no mass in the
+    prototype sums)."""
+    cfg = R.step_config(center_method, separate)
     st = R.det_step_state(cfg, seed=41)
     views, masks, idx, w = R.step_case_inputs(cfg)
     batch = {"views": [v.to(dev) for v in views],
