@@ -57,6 +57,12 @@ CONFIGS = {
         metric="images/sec ViT-L/16 DINOv2 training step (2g+10l crops, bs16/GPU, activation checkpointing)",
         workload="cfg5: ViT-L/16 DINOv2, 2x224^2 + 10x96^2 crops, bs=%d/GPU, K=65536 shared head, softmax centering, "
                  "drop_path 0.3 uniform (batch-subset form), activation checkpointing on, full step incl. clip+AdamW+EMA"),
+    "cfg4": dict(
+        batch=128,
+        metric="images/sec DistillationV3 step (DINOv3 ViT-B/16 teacher -> ResNet-50 student, 224^2, bs128/GPU)",
+        workload="cfg4: distillation, DINOv3 ViT-B/16 teacher (RoPE, 4 storage tokens; this repo's sm_100a kernels, forward only) -> "
+                 "torchvision ResNet-50 student (cuDNN via torch.autograd, channels-last bf16 autocast), one 224^2 view, bs=%d/GPU, "
+                 "queue 8192, fused KL kernels, full step incl. student backward + AdamW"),
 }
 
 
@@ -236,6 +242,9 @@ def run_reference_arm(args) -> None:
     if rank != 0:
         return
     cfg = CONFIGS[args.config]
+    if "vit" not in cfg:
+        print(json.dumps({"impl": "reference", "unavailable": f"no host reference arm for {args.config} (only the DINOv2 configs)"}), flush=True)
+        return
     value, desc = cpu_reference(cfg, args.steps, args.warmup, sweep=True)
     batch = desc["batch"]
     line = {
@@ -298,6 +307,126 @@ def bench_parity(method, cfg: dict, views_dev, dev) -> dict:
             "logit_rows": int(dt.shape[0] + ds.shape[0])}
 
 
+# --------------------------------------------------------------------------------------------- cfg4: distillation
+def run_distill(args) -> None:
+    """BASELINE.json configs[3].  The teacher forward (the ViT-B FLOPs) and the loss run on this repo's kernels; the
+    convolutional student, its backward and its AdamW are torch / cuDNN (library code, stated in the workload string)."""
+    import torch.distributed as dist
+    import torchvision
+
+    from lightly_train_b200 import _lib, ops
+    from lightly_train_b200._methods.distillationv3.distillationv3 import DistillationV3, DistillationV3Args
+    from lightly_train_b200._models.dinov3_vit import DinoV3VisionTransformer, DINOv3ViTModelWrapper
+    from lightly_train_b200._models.torchvision_resnet import EmbeddingModel, ResNetModelWrapper
+
+    cfg = CONFIGS["cfg4"]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
+    W, K, B = max(args.warmup, 3), args.steps, args.batch or cfg["batch"]
+    torch.manual_seed(0)
+    teacher = DinoV3VisionTransformer(img_size=224, patch_size=16, embed_dim=768, depth=12, num_heads=12, ffn_ratio=4.0,
+                                      layerscale_init=1e-5, norm_layer="layernormbf16", n_storage_tokens=4, mask_k_bias=True,
+                                      pos_embed_rope_dtype="fp32", device=str(dev))
+    student = EmbeddingModel(ResNetModelWrapper(torchvision.models.resnet50())).to(dev).to(memory_format=torch.channels_last)
+    method = DistillationV3(DistillationV3Args(), None, student, B * world, 3,
+                            teacher_embedding_model=DINOv3ViTModelWrapper(teacher)).to(dev)
+    params = [p for p in method.parameters() if p.requires_grad]
+    if world > 1:
+        for p in params:
+            dist.broadcast(p.data, 0)
+    opt = torch.optim.AdamW(params, lr=5e-4, weight_decay=0.04, fused=True)
+    g = torch.Generator().manual_seed(1000 + rank)
+    batches = [torch.randn(B, 3, 224, 224, generator=g).to(dev).contiguous(memory_format=torch.channels_last) for _ in range(2)]
+
+    def step(x):
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            res = method.training_step_impl({"views": [x]}, 0)
+        res.loss.backward()
+        if world > 1:
+            for p in params:
+                dist.all_reduce(p.grad)
+                p.grad.div_(world)
+        opt.step()
+        return res
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        step(batches[i % 2])
+    barrier()
+    l0 = _lib.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        e0.record()
+        for i in range(K):
+            res = step(batches[i % 2])
+        e1.record()
+        barrier()
+    launches = _lib.LAUNCHES - l0
+    t = torch.tensor([e0.elapsed_time(e1) / K], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    # e2e: pinned host images -> device every step, loss read back every step
+    host = [torch.randn(B, 3, 224, 224, generator=g).pin_memory() for _ in range(2)]
+    dbuf = [torch.empty(B, 3, 224, 224, device=dev).contiguous(memory_format=torch.channels_last) for _ in range(2)]
+    lh = torch.zeros(1).pin_memory()
+
+    def e2e_run(n):
+        for i in range(n):
+            dbuf[i % 2].copy_(host[i % 2], non_blocking=True)
+            r = step(dbuf[i % 2])
+            lh.copy_(r.loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_run(2)
+    barrier()
+    e0.record(); e2e_run(K); e1.record()
+    barrier()
+    t2 = torch.tensor([e0.elapsed_time(e1) / K], device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    # roofline: the teacher's tcgen05 GEMMs of one step, CUDA events per launch
+    ops.GEMM_PROFILE = []
+    step(batches[0])
+    torch.cuda.synchronize()
+    prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
+    peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+    if rank == 0:
+        flops = sum(f for f, _, _ in prof)
+        gms = sum(a.elapsed_time(b) for _, a, b in prof)
+        peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        line = {"metric": cfg["metric"], "value": B * world / (ms / 1e3), "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": cfg["workload"] % B, "global_batch": B * world, "parallelism": f"dp{world}",
+                           "l2_policy": "2 alternating 77 MB input batches; activations exceed the 126 MB L2"},
+                "clocks": clk.summary(),
+                "e2e": {"value": B * world / (float(t2[0]) / 1e3), "unit": "images/s", "h2d_bytes_per_step": B * 3 * 224 * 224 * 4,
+                        "d2h_bytes_per_step": 4},
+                "gpu_launches": launches, "gpu_launches_scope": "library (libb200dino.so) kernel launches of rank 0: teacher + loss; the student's cuDNN / ATen launches are not counted",
+                "loss": float(res.loss),
+                "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (teacher forward, all launches of one step)",
+                             "achieved": flops / (gms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": flops / (gms * 1e-3) / 1e12 / peak,
+                             "traffic": None, "gemm_launches": len(prof), "gemm_ms_per_step": gms,
+                             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained"},
+                "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 # --------------------------------------------------------------------------------------------- B200 arm
 def main() -> None:
     ap = argparse.ArgumentParser()
@@ -316,6 +445,9 @@ def main() -> None:
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+        return
+    if args.config == "cfg4":
+        run_distill(args)
         return
 
     import torch.distributed as dist
