@@ -146,6 +146,11 @@ int b200_layerscale_bwd(const float* dx, long long lddx, const void* o, long lon
 int b200_swiglu_fwd(const void* x12, long long ld12, int T, int H, void* hidden, long long ldh, void* stream);
 int b200_swiglu_bwd(const void* x12, long long ld12, const void* dhidden, long long lddh, int T, int H, void* dx12,
                     long long lddx12, void* stream);
+/* Batch-subset stochastic depth (drop_add_residual_stochastic_depth, LT/_models/dinov2_vit/dinov2_vit_src/layers/block.py:118-141):
+ * sample-granular copies of the fp32 residual stream, rows of row_elems floats (% 4 == 0).
+ * scatter = 0: dst[j, :] = src[idx[j], :] (x[brange]);  scatter = 1: dst[idx[j], :] = src[j, :] (the index_add target rows). */
+int b200_copy_samples(const float* src, float* dst, const long long* idx, int n_idx, long long row_elems, int scatter,
+                      void* stream);
 /* torch.index_select of token rows (dinov2.py:427-431,496-500) and its backward (scatter).
  * Row index = Np>0 ? (idx/Np)*N + off + idx%Np : idx. */
 int b200_gather_rows(const float* src, long long lds, const long long* idx, int M, int D, int Np, int N, int off,

@@ -127,6 +127,9 @@ class DinoVisionTransformer(nn.Module):
         # configured post-instantiation, like DINOv2ViTModelWrapper.set_activation_checkpointing (dinov2_vit.py:55-59)
         self._activation_checkpointing = False
         self._activation_checkpointing_every_n_blocks = 1
+        # batch-subset stochastic depth: run the residual branches on the kept samples only (True) or on all samples with the
+        # dropped ones scaled by zero (False: the dense statement of the same arithmetic)
+        self.subset_skips_compute = True
         self.init_weights(init_values)
 
     # ------------------------------------------------------------------ init (vision_transformer.py:244-249,574+)
@@ -231,6 +234,135 @@ class DinoVisionTransformer(nn.Module):
                       mean2=mean2, rstd2=rstd2, xn2=xn2, u=u, h=hh, o2=o2, rs1=rs1, rs2=rs2)
         return sv
 
+    # ------------------------------------------------------------------ batch-subset stochastic depth (block.py:118-141)
+    def _branch_fwd(self, i: int, which: int, xs: Tensor, bsub: int, N: int, scale_vec: Tensor, save: bool) -> dict:
+        """One residual branch of block i on a COMPACT subset [bsub*N, D] of the residual stream:
+        which=0: LN1 -> qkv -> attention -> proj ; which=1: LN2 -> FFN.  Returns xo = xs + (b/b') * LayerScale(branch)."""
+        dev = xs.device
+        D, Hd, h = self.embed_dim, self.hidden_dim, self.num_heads
+        Ts = xs.shape[0]
+        bf, f32 = torch.bfloat16, torch.float32
+        E = lambda *s, dt=bf: torch.empty(*s, device=dev, dtype=dt)  # noqa: E731
+        b = f"blocks.{i}."
+        mean, rstd = (E(Ts, dt=f32), E(Ts, dt=f32)) if save else (None, None)
+        xn = E(Ts, D)
+        o = E(Ts, D) if save else None
+        xo = E(Ts, D, dt=f32)
+        if which == 0:
+            ops.layernorm_fwd(xs, self._P(b + "norm1.weight"), self._P(b + "norm1.bias"), self.ln_eps, xn, mean, rstd)
+            qkv = E(Ts, 3 * D)
+            ops.gemm(xn, self._W(b + "attn.qkv.weight"), qkv, bias=self._P(b + "attn.qkv.bias"))
+            att = E(Ts, D)
+            lse = E(bsub * h, N, dt=f32) if save else None
+            ops.attention_fwd(qkv, bsub, N, h, att, lse, 64 ** -0.5)
+            ops.gemm(att, self._W(b + "attn.proj.weight"), xo, epi=ops.EPI_RESIDUAL, bias=self._P(b + "attn.proj.bias"), out2=o,
+                     aux=xs, gamma=self._P(b + "ls1.gamma") if self.layerscale else None, rowscale=scale_vec, rows_per_scale=N)
+            sv = dict(xs=xs, mean=mean, rstd=rstd, xn=xn, qkv=qkv, att=att, lse=lse, o=o) if save else {}
+        else:
+            ops.layernorm_fwd(xs, self._P(b + "norm2.weight"), self._P(b + "norm2.bias"), self.ln_eps, xn, mean, rstd)
+            hh = E(Ts, Hd)
+            if self.swiglu:
+                u = E(Ts, 2 * Hd)
+                ops.gemm(xn, self._W(b + "mlp.w12.weight"), u, bias=self._P(b + "mlp.w12.bias"))
+                ops.swiglu_fwd(u, hh)
+            else:
+                u = E(Ts, Hd) if save else None
+                ops.gemm(xn, self._W(b + "mlp.fc1.weight"), hh, epi=ops.EPI_BIAS_GELU_DG if save else ops.EPI_BIAS_GELU,
+                         bias=self._P(b + "mlp.fc1.bias"), out2=u)
+            ops.gemm(hh, self._W(b + self._ffn_out + "weight"), xo, epi=ops.EPI_RESIDUAL, bias=self._P(b + self._ffn_out + "bias"),
+                     out2=o, aux=xs, gamma=self._P(b + "ls2.gamma") if self.layerscale else None, rowscale=scale_vec, rows_per_scale=N)
+            sv = dict(xs=xs, mean=mean, rstd=rstd, xn=xn, u=u, h=hh, o=o) if save else {}
+        sv["xo"] = xo
+        return sv
+
+    def _block_fwd_subset(self, i: int, xcur: Tensor, Bc: int, N: int, idx1: Tensor, idx2: Tensor, save: bool, ckpt: bool) -> dict:
+        """Block i with both residual branches evaluated on random subsets of b' = max(int(b (1 - r)), 1) samples and added
+        back with alpha = b / b' (drop_add_residual_stochastic_depth): the dropped samples' branch is NOT computed.
+        The residual stream `xcur` [Bc*N, D] is updated IN PLACE (only the subset rows change); what the backward needs of
+        the old values are the compact copies made here."""
+        D = self.embed_dim
+        dev = xcur.device
+        f32 = torch.float32
+        x3 = xcur.view(Bc, N, D)
+        out = {"subset": True, "idx": (idx1, idx2), "branches": [None, None]}
+        for which, idx in ((0, idx1), (1, idx2)):
+            bsub = idx.numel()
+            xs = torch.empty(bsub * N, D, device=dev, dtype=f32)
+            ops.gather_samples(x3, idx, xs.view(bsub, N, D))
+            scale_vec = torch.full((bsub,), Bc / bsub, device=dev, dtype=f32)
+            if save and ckpt:  # keep only the compact branch input; the branch is recomputed in the backward
+                br = self._branch_fwd(i, which, xs, bsub, N, scale_vec, False)
+                out["branches"][which] = {"ckpt": True, "xs": xs, "scale_vec": scale_vec}
+            else:
+                br = self._branch_fwd(i, which, xs, bsub, N, scale_vec, save)
+                if save:
+                    br["scale_vec"] = scale_vec
+                    out["branches"][which] = br
+            ops.scatter_samples(br.pop("xo").view(bsub, N, D), idx, x3)
+        # dense per-sample scales (introspection / tests): b/b' on the subset, 0 elsewhere
+        if save:
+            out["rs1"] = torch.zeros(Bc, device=dev, dtype=f32).index_fill_(0, idx1, Bc / idx1.numel())
+            out["rs2"] = torch.zeros(Bc, device=dev, dtype=f32).index_fill_(0, idx2, Bc / idx2.numel())
+        return out
+
+    def _block_bwd_subset(self, i: int, sv: dict, dx: Tensor, Bc: int, N: int, wgrad) -> None:
+        """Backward of a subset block: dx [Bc*N, D] (gradient wrt the block output) becomes the gradient wrt the block input,
+        in place: for each branch (MLP first) the subset rows of dx are copied out, the compact branch backward adds the
+        branch's input gradient to the copy (identity path + branch path), and the rows are written back."""
+        D, Hd, h = self.embed_dim, self.hidden_dim, self.num_heads
+        dev = dx.device
+        bf, f32 = torch.bfloat16, torch.float32
+        E = lambda *s, dt=bf: torch.empty(*s, device=dev, dtype=dt)  # noqa: E731
+        ls = self.layerscale
+        b = f"blocks.{i}."
+        dx3 = dx.view(Bc, N, D)
+        for which in (1, 0):
+            idx = sv["idx"][which]
+            bsub = idx.numel()
+            br = sv["branches"][which]
+            if br.get("ckpt"):
+                sc = br["scale_vec"]
+                br = self._branch_fwd(i, which, br["xs"], bsub, N, sc, True)
+                br["scale_vec"] = sc
+                br.pop("xo")
+            Ts = bsub * N
+            ddx = torch.empty(Ts, D, device=dev, dtype=f32)
+            ops.gather_samples(dx3, idx, ddx.view(bsub, N, D))
+            do = E(Ts, D)
+            if which == 1:
+                ops.layerscale_bwd(ddx, br["o"], self._P(b + "ls2.gamma") if ls else None, br["scale_vec"], N, do,
+                                   self._G(b + "ls2.gamma") if ls else None, self._G(b + self._ffn_out + "bias"))
+                if self.swiglu:
+                    dH = E(Ts, Hd)
+                    ops.gemm(do, self._W(b + "mlp.w3.weight"), dH, b_mn=True)
+                    dU = E(Ts, 2 * Hd)
+                    ops.swiglu_bwd(br["u"], dH, dU)
+                else:
+                    dU = E(Ts, Hd)
+                    ops.gemm(do, self._W(b + "mlp.fc2.weight"), dU, b_mn=True, epi=ops.EPI_MUL_AUX, aux=br["u"])
+                wgrad(do, br["h"], b + self._ffn_out + "weight")
+                ops.col_reduce(dU, self._G(b + self._ffn_in + "bias"))
+                wgrad(dU, br["xn"], b + self._ffn_in + "weight")
+                dxn = E(Ts, D)
+                ops.gemm(dU, self._W(b + self._ffn_in + "weight"), dxn, b_mn=True)
+                ops.layernorm_bwd(dxn, br["xs"], self._P(b + "norm2.weight"), br["mean"], br["rstd"], ddx, True,
+                                  self._G(b + "norm2.weight"), self._G(b + "norm2.bias"))
+            else:
+                ops.layerscale_bwd(ddx, br["o"], self._P(b + "ls1.gamma") if ls else None, br["scale_vec"], N, do,
+                                   self._G(b + "ls1.gamma") if ls else None, self._G(b + "attn.proj.bias"))
+                datt = E(Ts, D)
+                ops.gemm(do, self._W(b + "attn.proj.weight"), datt, b_mn=True)
+                wgrad(do, br["att"], b + "attn.proj.weight")
+                dqkv = E(Ts, 3 * D)
+                ops.attention_bwd(br["qkv"], br["att"], datt, br["lse"], bsub, N, h, dqkv, 64 ** -0.5,
+                                  colsum=self._G(b + "attn.qkv.bias").view(-1))
+                wgrad(dqkv, br["xn"], b + "attn.qkv.weight")
+                dxn = E(Ts, D)
+                ops.gemm(dqkv, self._W(b + "attn.qkv.weight"), dxn, b_mn=True)
+                ops.layernorm_bwd(dxn, br["xs"], self._P(b + "norm1.weight"), br["mean"], br["rstd"], ddx, True,
+                                  self._G(b + "norm1.weight"), self._G(b + "norm1.bias"))
+            ops.scatter_samples(ddx.view(bsub, N, D), idx, dx3)
+
     # ------------------------------------------------------------------ forward
     def _fwd(self, x: Tensor, masks: Optional[Tensor], save: bool, drop_path: bool = False,
              keep_scales: Optional[List[Tensor]] = None) -> VitCtx:
@@ -291,14 +423,22 @@ class DinoVisionTransformer(nn.Module):
                 rs1, rs2 = bern_scales[2 * j], bern_scales[2 * j + 1]
             elif drop_path and self.dpr[i] > 0.1:
                 # drop_add_residual_stochastic_depth (layers/block.py:118-141): the branch runs on a random subset of
-                # b' = max(int(b*(1-r)), 1) samples and is added back with alpha = b/b'.  Same arithmetic as a per-sample
-                # scale of b/b' on the subset and 0 elsewhere (the dropped samples' branch output is computed, then unused).
+                # b' = max(int(b*(1-r)), 1) samples and is added back with alpha = b/b'.
                 bsub = max(int(Bc * (1.0 - self.dpr[i])), 1)
                 # (random subset = the bsub smallest of Bc uniform draws: graph-capturable, unlike randperm/index_put)
-                rs1 = torch.zeros(Bc, device=dev, dtype=f32)
-                rs1.index_fill_(0, torch.rand(Bc, device=dev).argsort()[:bsub], Bc / bsub)
-                rs2 = torch.zeros(Bc, device=dev, dtype=f32)
-                rs2.index_fill_(0, torch.rand(Bc, device=dev).argsort()[:bsub], Bc / bsub)
+                idx1 = torch.rand(Bc, device=dev).argsort()[:bsub]
+                idx2 = torch.rand(Bc, device=dev).argsort()[:bsub]
+                if self.subset_skips_compute:
+                    # compact schedule: only the subset's rows go through the branch (20-30 % of the block FLOPs saved)
+                    ckpt = save and self._activation_checkpointing and (i % self._activation_checkpointing_every_n_blocks == 0)
+                    sv = self._block_fwd_subset(i, xcur, Bc, N, idx1, idx2, save, ckpt)
+                    if save:
+                        ctx.blocks.append(sv)
+                    continue
+                # dense statement of the same arithmetic: per-sample scale b/b' on the subset, 0 elsewhere (every sample's
+                # branch output is computed, the dropped ones are then multiplied by zero)
+                rs1 = torch.zeros(Bc, device=dev, dtype=f32).index_fill_(0, idx1, Bc / bsub)
+                rs2 = torch.zeros(Bc, device=dev, dtype=f32).index_fill_(0, idx2, Bc / bsub)
             elif drop_path and self.dpr[i] > 0.0:
                 keep = 1.0 - self.dpr[i]
                 rs1 = torch.empty(Bc, device=dev, dtype=f32).bernoulli_(keep).div_(keep)  # drop_path.py:23-27
@@ -356,9 +496,18 @@ class DinoVisionTransformer(nn.Module):
                 ctx.blocks[j] = blk
             return blk
 
+        def is_subset(j: int) -> bool:
+            return bool(ctx.blocks[j].get("subset"))
+
         if resume:
             do2 = state["do2"]
             hi = state["next"]
+        elif is_subset(nb - 1):
+            # batch-subset block: its branches run on compact row subsets, so nothing fuses across the block boundary
+            ops.layernorm_bwd(d_xnorm, ctx.x_prenorm, self._P("norm.weight"), ctx.meanf, ctx.rstdf, dx, False,
+                              self._G("norm.weight"), self._G("norm.bias"))
+            do2 = None
+            hi = nb - 1
         else:
             last = materialise(nb - 1)
             bl = f"blocks.{nb - 1}."
@@ -371,6 +520,17 @@ class DinoVisionTransformer(nn.Module):
         for i in range(hi, stop_before - 1, -1):
             b = f"blocks.{i}."
             sv = ctx.blocks[i]
+            if sv.get("subset"):
+                self._block_bwd_subset(i, sv, dx, Bc, N, wgrad)
+                do2 = None
+                ctx.blocks[i] = None
+                continue
+            if do2 is None:
+                # the block after this one (or the final LayerNorm) could not fuse this block's LayerScale backward
+                sv = materialise(i)
+                do2 = E(T, D)
+                ops.layerscale_bwd(dx, sv["o2"], self._P(b + "ls2.gamma") if ls else None, sv["rs2"], N, do2,
+                                   self._G(b + "ls2.gamma") if ls else None, self._G(b + self._ffn_out + "bias"))
             # ---- MLP branch (do2 = gradient of the fc2 output, produced by the fused kernel above / below)
             if self.swiglu:
                 dH = E(T, Hd)
@@ -402,7 +562,7 @@ class DinoVisionTransformer(nn.Module):
             wgrad(dqkv, sv["xn"], b + "attn.qkv.weight")
             dxn = E(T, D)
             ops.gemm(dqkv, self._W(b + "attn.qkv.weight"), dxn, b_mn=True)
-            if i > 0:
+            if i > 0 and not is_subset(i - 1):
                 # LN1 backward fused with the LayerScale backward of the PREVIOUS block's MLP branch
                 pv = materialise(i - 1)
                 bp = f"blocks.{i - 1}."
@@ -414,6 +574,7 @@ class DinoVisionTransformer(nn.Module):
             else:
                 ops.layernorm_bwd(dxn, sv["x_in"], self._P(b + "norm1.weight"), sv["mean1"], sv["rstd1"], dx, True,
                                   self._G(b + "norm1.weight"), self._G(b + "norm1.bias"))
+                do2 = None
             ctx.blocks[i] = None  # free activations early
         if stop_before > 0:
             return {"dx": dx, "do2": do2, "next": stop_before - 1}

@@ -773,6 +773,28 @@ extern "C" int b200_layerscale_bwd(const float* dx, long long lddx, const void* 
   return B200_OK;
 }
 
+// Sample-granular copies for batch-subset stochastic depth (layers/block.py:118-141): rows of `row_elems` floats.
+//   gather : dst[j, :] = src[idx[j], :]      scatter: dst[idx[j], :] = src[j, :]
+__global__ void copy_samples_kernel(const float* __restrict__ src, float* __restrict__ dst, const long long* __restrict__ idx,
+                                    long long row_elems, int scatter) {
+  const long long s = idx[blockIdx.y];
+  const float4* in = reinterpret_cast<const float4*>(src + (scatter ? (long long)blockIdx.y : s) * row_elems);
+  float4* out = reinterpret_cast<float4*>(dst + (scatter ? s : (long long)blockIdx.y) * row_elems);
+  const long long nv = row_elems >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) out[i] = in[i];
+}
+
+extern "C" int b200_copy_samples(const float* src, float* dst, const long long* idx, int n_idx, long long row_elems, int scatter,
+                                 void* stream) {
+  if (!src || !dst || !idx || n_idx <= 0 || row_elems <= 0 || (row_elems % 4)) return B200_ERR_INVALID_ARG;
+  if (((uintptr_t)src & 15) || ((uintptr_t)dst & 15)) return B200_ERR_UNSUPPORTED;
+  long long per = (row_elems / 4 + 255) / 256;
+  int gx = (int)(per < 64 ? per : 64);
+  copy_samples_kernel<<<dim3(gx, n_idx), 256, 0, (cudaStream_t)stream>>>(src, dst, idx, row_elems, scatter);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
 extern "C" int b200_swiglu_fwd(const void* x12, long long ld12, int T, int H, void* hidden, long long ldh, void* stream) {
   if (!x12 || !hidden || T <= 0 || H <= 0) return B200_ERR_INVALID_ARG;
   if ((H % 8) || (ld12 % 8) || (ldh % 8) || ((uintptr_t)x12 & 15) || ((uintptr_t)hidden & 15)) return B200_ERR_UNSUPPORTED;

@@ -349,3 +349,19 @@ def kl_rows(s, t, inv_temp: float, loss_rows, ds=None, gscale: float = 1.0) -> N
     assert s.dtype == t.dtype == torch.float32 and s.stride(1) == 1 and t.stride(1) == 1 and t.shape == s.shape
     check(_L().b200_kl_rows(s.data_ptr(), s.stride(0), t.data_ptr(), t.stride(0), R, K, inv_temp, gscale, loss_rows.data_ptr(),
                             _ptr(ds), ds.stride(0) if ds is not None else 0, _stream()), "b200_kl_rows")
+
+
+def gather_samples(src, idx, dst) -> None:
+    """dst[j] = src[idx[j]] for fp32 [*, N, D] sample blocks (batch-subset stochastic depth)."""
+    _req_cuda(src, idx, dst)
+    assert src.dtype == dst.dtype == torch.float32 and idx.dtype == torch.int64 and src.is_contiguous() and dst.is_contiguous()
+    row = src[0].numel()
+    check(_L().b200_copy_samples(src.data_ptr(), dst.data_ptr(), idx.data_ptr(), idx.numel(), row, 0, _stream()), "b200_copy_samples")
+
+
+def scatter_samples(src, idx, dst) -> None:
+    """dst[idx[j]] = src[j] (overwrite) for fp32 [*, N, D] sample blocks."""
+    _req_cuda(src, idx, dst)
+    assert src.dtype == dst.dtype == torch.float32 and idx.dtype == torch.int64 and src.is_contiguous() and dst.is_contiguous()
+    row = dst[0].numel()
+    check(_L().b200_copy_samples(src.data_ptr(), dst.data_ptr(), idx.data_ptr(), idx.numel(), row, 1, _stream()), "b200_copy_samples")

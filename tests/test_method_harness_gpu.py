@@ -200,3 +200,34 @@ def test_stochastic_depth_rng_paths():
     torch.cuda.synchronize()
     assert g0.abs().max().item() == 0.0, "dropped sample leaked gradient into its dropped MLP branch"
     assert m.arena.g("blocks.0.mlp.fc2.weight").abs().max().item() > 0.0
+
+
+@pytest.mark.parametrize("ckpt", [False, True])
+def test_subset_stochastic_depth_compact_equals_dense(ckpt):
+    """Batch-subset stochastic depth (layers/block.py:118-141): the compact schedule (only the kept samples go through the
+    branch: gather -> branch -> scaled write-back) must reproduce the dense statement (every sample computed, dropped ones
+    multiplied by zero) for the same random subsets -- forward features and every parameter gradient."""
+    Bc = 16
+    x = torch.randn(Bc, 3, 64, 64, device=dev)
+
+    def run(compact: bool):
+        torch.manual_seed(5)
+        m = DinoVisionTransformer(img_size=64, patch_size=16, embed_dim=128, depth=3, num_heads=2, init_values=0.7,
+                                  drop_path_rate=0.3, drop_path_uniform=True, requires_grad=True)
+        m.subset_skips_compute = compact
+        m._activation_checkpointing = ckpt
+        m.arena.zero_grad()
+        torch.manual_seed(11)  # same subset draws in both schedules
+        ctx = m._fwd(x, None, save=True, drop_path=True)
+        out = ctx.xnorm.clone()
+        kept = [int((blk["rs1"] > 0).sum()) for blk in ctx.blocks] if compact else None
+        cot = torch.randn(out.shape, generator=torch.Generator().manual_seed(9)).to(dev)
+        m._bwd(ctx, cot)
+        torch.cuda.synchronize()
+        return out, m.arena.grad.clone(), kept
+
+    o_d, g_d, _ = run(False)
+    o_c, g_c, kept = run(True)
+    assert kept == [max(int(Bc * 0.7), 1)] * 3
+    assert (o_d - o_c).abs().max().item() < 2e-2 and (o_d - o_c).abs().mean().item() < 1e-3  # same math, bf16 tiles regrouped
+    assert ((g_d - g_c).norm() / g_d.norm()).item() < 2e-2
