@@ -49,6 +49,7 @@ class DINOv2ProjectionHead(nn.Module):
         attach_params(self, arena, prefix, [prefix + k for k in shapes], requires_grad)
         self.w_eff = torch.empty(out_dim, bottleneck_dim, device=arena.device, dtype=torch.bfloat16)
         self.init_weights()
+        self.register_load_state_dict_post_hook(lambda mod, incompatible: setattr(mod.arena, "bf16_valid", False))
 
     @torch.no_grad()
     def init_weights(self) -> None:

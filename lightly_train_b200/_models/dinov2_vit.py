@@ -71,6 +71,17 @@ def attach_params(root: nn.Module, arena: Arena, prefix: str, names, requires_gr
         mod.register_parameter(parts[-1], param)
 
 
+def _unchunk_block_names(state_dict, prefix, *args) -> None:
+    """load_state_dict pre-hook: `blocks.{chunk}.{i}.x` -> `blocks.{i}.x` (vision_transformer.py:215-226 keeps the global
+    block index inside each chunk, so dropping the chunk index is the whole mapping)."""
+    for k in list(state_dict.keys()):
+        if not k.startswith(prefix + "blocks."):
+            continue
+        parts = k[len(prefix):].split(".")
+        if len(parts) > 3 and parts[1].isdigit() and parts[2].isdigit():
+            state_dict[prefix + ".".join(parts[:1] + parts[2:])] = state_dict.pop(k)
+
+
 class VitCtx:
     """Saved activations of one forward pass (everything the explicit backward needs)."""
 
@@ -131,6 +142,10 @@ class DinoVisionTransformer(nn.Module):
         # dropped ones scaled by zero (False: the dense statement of the same arithmetic)
         self.subset_skips_compute = True
         self.init_weights(init_values)
+        # checkpoints written with block_chunks > 0 (zoo ViT-L/g configs) name blocks `blocks.{chunk}.{i}.*`
+        self._register_load_state_dict_pre_hook(_unchunk_block_names)
+        # weights land in the fp32 arena: the bf16 GEMM shadow is stale after any load
+        self.register_load_state_dict_post_hook(lambda mod, incompatible: setattr(mod.arena, "bf16_valid", False))
 
     # ------------------------------------------------------------------ init (vision_transformer.py:244-249,574+)
     @torch.no_grad()
