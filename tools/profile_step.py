@@ -12,7 +12,7 @@ from lightly_train_b200._methods.dinov2.dinov2 import DINOv2, DINOv2AdamWViTArgs
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 random.seed(0)
 torch.manual_seed(0)
-m = DINOv2(DINOv2Args(), DINOv2AdamWViTArgs(), bench.VIT_S16, global_batch_size=B, device="cuda:0")
+m = DINOv2(DINOv2Args(), DINOv2AdamWViTArgs(), dict(bench.CONFIGS["cfg2"]["vit"]), global_batch_size=B, device="cuda:0")
 batch = {"views": bench.make_views(B, 8, 0, torch.device("cuda:0"))}
 for _ in range(2):
     m.train_step(batch)
