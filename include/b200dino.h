@@ -94,6 +94,9 @@ int b200_rope_apply(void* qkv, long long ld, int B, int N, int prefix, int h, in
                     const float* cos_tab, void* stream);
 int b200_kl_rows(const float* s, long long lds, const float* t, long long ldt, int R, int K, float inv_temp, float gscale,
                  float* loss_rows, float* ds, long long ldds, void* stream);
+/* out[0] += mean((teacher - student)^2); ds (optional) = d/d student.  DistillationV2Loss.forward,
+ * LT/_methods/distillationv2/distillationv2_loss.py:27-44 (MSELoss, reduction "mean") + its autograd backward. */
+int b200_mse(const float* teacher, const float* student, long long n, float* out, float* ds, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Attention core for short sequences (head_dim 64), forward and backward.

@@ -90,9 +90,33 @@ __global__ void __launch_bounds__(256) kl_rows_kernel(const float* __restrict__ 
   }
 }
 
+// out[0] += mean((t - s)^2) ; ds = 2 (s - t) / n   (MSELoss(reduction="mean") and its gradient wrt s, one pass)
+__global__ void __launch_bounds__(256) mse_kernel(const float* __restrict__ t, const float* __restrict__ s, long long n,
+                                                  float* __restrict__ out, float* __restrict__ ds) {
+  __shared__ float red[32];
+  const float inv_n = 1.f / (float)n;
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float d = s[i] - t[i];
+    acc = fmaf(d, d, acc);
+    if (ds) ds[i] = 2.f * d * inv_n;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(out, acc * inv_n);
+}
+
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" int b200_mse(const float* teacher, const float* student, long long n, float* out, float* ds, void* stream) {
+  if (!teacher || !student || !out || n <= 0) return B200_ERR_INVALID_ARG;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  mse_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(teacher, student, n, out, ds);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
 
 extern "C" int b200_rope_apply(void* qkv, long long ld, int B, int N, int prefix, int h, int head_dim, const float* sin_tab,
                                const float* cos_tab, void* stream) {

@@ -365,3 +365,9 @@ def scatter_samples(src, idx, dst) -> None:
     assert src.dtype == dst.dtype == torch.float32 and idx.dtype == torch.int64 and src.is_contiguous() and dst.is_contiguous()
     row = dst[0].numel()
     check(_L().b200_copy_samples(src.data_ptr(), dst.data_ptr(), idx.data_ptr(), idx.numel(), row, 1, _stream()), "b200_copy_samples")
+
+
+def mse(teacher, student, out, ds=None) -> None:
+    """out[0] += mean((teacher - student)^2); ds = gradient wrt student.  Flat contiguous f32 tensors."""
+    _req_cuda(teacher, student, out, ds)
+    check(_L().b200_mse(teacher.data_ptr(), student.data_ptr(), student.numel(), out.data_ptr(), _ptr(ds), _stream()), "b200_mse")

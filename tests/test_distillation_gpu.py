@@ -145,3 +145,27 @@ def test_distillation_step_matches_reference_method():
     ga = mm.student_embedding_model.wrapped_model.get_model().conv1.weight.grad.float().cpu()
     gb = rm.student_embedding_model.wrapped_model.get_model().conv1.weight.grad
     assert ((ga - gb).norm() / gb.norm()).item() < 0.25  # through 18 bf16 BatchNorm/conv layers
+
+
+def test_sibling_distillation_losses():
+    """Distillation v1 (queue KL, LT/_methods/distillation/distillation_loss.py) and v2 (MSE, distillationv2_loss.py) on the
+    fused kernels against the torch statement of the reference modules' forward, values and student gradients."""
+    from lightly_train_b200._methods.distillation.distillation_loss import DistillationLoss
+    from lightly_train_b200._methods.distillationv2.distillationv2_loss import DistillationV2Loss
+    tg, tl, sg, sl, q = (t.to(dev) for t in R.distill_case_inputs())
+    s1 = sg.clone().requires_grad_(True)
+    l1 = DistillationLoss(0.07)(tg, s1, q)
+    l1.backward()
+    s2 = sg.clone().requires_grad_(True)
+    want = F.kl_div(F.log_softmax(s2 @ q.t() / 0.07, -1), F.softmax(tg @ q.t() / 0.07, -1), reduction="batchmean")
+    want.backward()
+    assert abs(float(l1) - float(want)) < 1e-5
+    torch.testing.assert_close(s1.grad, s2.grad, rtol=1e-4, atol=1e-6)
+    a = sl.clone().requires_grad_(True)
+    l2 = DistillationV2Loss()(tl, a)
+    l2.backward()
+    b = sl.clone().requires_grad_(True)
+    w2 = F.mse_loss(tl, b)
+    w2.backward()
+    assert abs(float(l2) - float(w2)) < 1e-6
+    torch.testing.assert_close(a.grad, b.grad, rtol=1e-5, atol=1e-8)
