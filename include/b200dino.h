@@ -149,6 +149,17 @@ int b200_layerscale_bwd(const float* dx, long long lddx, const void* o, long lon
 int b200_swiglu_fwd(const void* x12, long long ld12, int T, int H, void* hidden, long long ldh, void* stream);
 int b200_swiglu_bwd(const void* x12, long long ld12, const void* dhidden, long long lddh, int T, int H, void* dx12,
                     long long lddx12, void* stream);
+/* Device-side block-wise mask generation (the input side of the step).  Same algorithm and
+ * distribution as MaskingGenerator.__call__ / _mask (LT/_methods/dinov2/utils.py:41-113) and the collation of
+ * create_collated_masks (:116-152), counter-based device RNG instead of python's `random` (statistical, not bit, parity).
+ * b200_block_masks: targets int32 [B] (per-crop mask counts, 0 = unmasked crop) -> masks u8 [B, H*W]; one RNG stream per
+ *   (seed, *step_dev, crop).
+ * b200_collate_masks: masks -> idx int64 [cap] (mask_indices_list), weight f32 [cap] (masks_weight), row_w (1/M), pad
+ *   (0 | -1e30 for rows >= M), m_valid int32 [1]; rows >= M are inert (idx 0, weight 0). */
+int b200_block_masks(const int* targets, int B, int H, int W, int min_patches, int max_patches, float min_aspect,
+                     float max_aspect, long long seed, const int* step_dev, unsigned char* masks, void* stream);
+int b200_collate_masks(const unsigned char* masks, int B, int Np, int cap, long long* idx, float* weight, float* row_w,
+                       float* pad, int* m_valid, void* stream);
 /* Batch-subset stochastic depth (drop_add_residual_stochastic_depth, LT/_models/dinov2_vit/dinov2_vit_src/layers/block.py:118-141):
  * sample-granular copies of the fp32 residual stream, rows of row_elems floats (% 4 == 0).
  * scatter = 0: dst[j, :] = src[idx[j], :] (x[brange]);  scatter = 1: dst[idx[j], :] = src[j, :] (the index_add target rows). */

@@ -277,6 +277,10 @@ class DINOv2(nn.Module):
         self._optimizer: Optional["FusedAdamWEMA"] = None
         self._scheduler: Optional["CosineWarmupFactor"] = None
         self._ema_done = False
+        # iBOT masks: "host" = the reference's python-`random` generator (bit-exact stream, default); "device" = csrc/masks.cu
+        self.mask_source = "host"
+        self.mask_seed = 0
+        self._mask_step_dev: Optional[Tensor] = None
         self.debug_taps: Optional[Dict[str, Any]] = None
         self.logged: Dict[str, Any] = {}
         self._last_result: Optional[TrainingStepResult] = None
@@ -372,6 +376,41 @@ class DINOv2(nn.Module):
         gen = MaskingGenerator(input_size=(h, w), max_num_patches=int(0.5 * h * w))
         return create_collated_masks(a.mask_ratio_min, a.mask_ratio_max, int(n_crops * a.mask_probability), n_crops, gen)
 
+    def _mask_targets(self, n_crops: int, n_tokens: int) -> List[int]:
+        """Per-crop mask counts exactly as create_collated_masks draws them (utils.py:116-133): one uniform draw per masked
+        crop inside its ratio bucket, zero for the others, then the shuffle -- a few dozen python-`random` draws per step."""
+        import random
+
+        import numpy as np
+
+        a = self.method_args
+        n_masked = int(n_crops * a.mask_probability)
+        edges = np.linspace(a.mask_ratio_min, a.mask_ratio_max, n_masked + 1)
+        t = [int(n_tokens * random.uniform(edges[i], edges[i + 1])) for i in range(n_masked)] + [0] * (n_crops - n_masked)
+        random.shuffle(t)
+        return t
+
+    def _device_masks(self, n_crops: int, h: int, w: int, bufs: Optional[Dict[str, Tensor]] = None) -> Dict[str, Any]:
+        """Block-wise masks generated ON THE DEVICE (csrc/masks.cu): only the per-crop target counts come from the host.
+        Returns padded, static-shape tensors (capacity = the targets' sum rounded up to 512): rows >= M are inert."""
+        dev = self.device_
+        targets = self._mask_targets(n_crops, h * w)
+        cap = max(512, -(-sum(targets) // 512) * 512)
+        if bufs is None:
+            bufs = {"targets": torch.empty(n_crops, device=dev, dtype=torch.int32),
+                    "masks_u8": torch.empty(n_crops, h * w, device=dev, dtype=torch.uint8),
+                    "idx": torch.empty(cap, device=dev, dtype=torch.int64), "mw": torch.empty(cap, device=dev),
+                    "iw": torch.empty(cap, device=dev), "pad": torch.empty(cap, device=dev),
+                    "m_valid": torch.empty(1, device=dev, dtype=torch.int32)}
+        if self._mask_step_dev is None:
+            self._mask_step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+        bufs["targets"].copy_(torch.tensor(targets, dtype=torch.int32), non_blocking=True)
+        ops.block_masks(bufs["targets"], h, w, int(0.5 * h * w), self.mask_seed, bufs["masks_u8"], step_dev=self._mask_step_dev)
+        ops.collate_masks(bufs["masks_u8"], cap, bufs["idx"], bufs["mw"], bufs["iw"], bufs["pad"], bufs["m_valid"])
+        self._mask_step_dev.add_(1)
+        return {"device": True, "cap": cap, "collated_masks_u8": bufs["masks_u8"], "mask_indices_list": bufs["idx"][:cap],
+                "masks_weight": bufs["mw"][:cap], "row_w": bufs["iw"][:cap], "pad": bufs["pad"][:cap], "m_valid": bufs["m_valid"]}
+
     def training_step_impl(self, batch: Dict[str, Any], batch_idx: int = 0) -> TrainingStepResult:
         """Loss evaluation + explicit backward (gradients land in the arena / `param.grad`). Eager launch schedule."""
         a = self.method_args
@@ -384,17 +423,25 @@ class DINOv2(nn.Module):
         p = self._patch_size
         masks = batch.get("masks")
         if masks is None:
-            masks = self._masks(gv.shape[0], gv.shape[2] // p, gv.shape[3] // p)  # host python RNG, reference stream
-        collated = masks["collated_masks"].to(dev, non_blocking=True)
-        mask_idx = masks["mask_indices_list"].to(dev, non_blocking=True)
-        masks_weight = masks["masks_weight"].to(dev, torch.float32, non_blocking=True)
+            if self.mask_source == "device":
+                masks = self._device_masks(gv.shape[0], gv.shape[2] // p, gv.shape[3] // p)
+            else:
+                masks = self._masks(gv.shape[0], gv.shape[2] // p, gv.shape[3] // p)  # host python RNG, reference stream
         for arena in (self.s_arena, self.t_arena):
             if not arena.bf16_valid:
                 arena.refresh_bf16()
         if a.center_method == "softmax":
             self.dino_loss.apply_center_update()
             self.ibot_loss.apply_center_update()
-        st = self._core_a(gv, lv, collated.to(torch.uint8), mask_idx, masks_weight, 1.0 / teacher_temp, None, None, None)
+        if masks.get("device"):  # padded static-shape mask tensors produced on the device: rows >= M are inert
+            mask_idx = masks["mask_indices_list"]
+            st = self._core_a(gv, lv, masks["collated_masks_u8"], mask_idx, masks["masks_weight"], 1.0 / teacher_temp, None,
+                              masks["row_w"], masks["m_valid"], masks["pad"])
+        else:
+            collated = masks["collated_masks"].to(dev, non_blocking=True)
+            mask_idx = masks["mask_indices_list"].to(dev, non_blocking=True)
+            masks_weight = masks["masks_weight"].to(dev, torch.float32, non_blocking=True)
+            st = self._core_a(gv, lv, collated.to(torch.uint8), mask_idx, masks_weight, 1.0 / teacher_temp, None, None, None)
         self._allreduce_head_grads_async()
         split_at = self._backbone_split()
         out = self._core_b(st, split_at)
@@ -645,25 +692,31 @@ class DINOv2(nn.Module):
         teacher_temp = linear_warmup_schedule(self.trainer.global_step, a.teacher_temp_warmup_steps,
                                               a.teacher_temp_start, a.teacher_temp_end)
         masks = batch.get("masks")
-        if masks is None:
-            masks = self._masks(2 * B, hh, ww)
-        M = int(masks["mask_indices_list"].shape[0])
-        cap = max(512, -(-M // 512) * 512)
         # stage the step's inputs into the static buffers (device copies for resident views, H2D otherwise)
         for i in range(2):
             st["gv"][i * B:(i + 1) * B].copy_(views[i], non_blocking=True)
         for i in range(n_local):
             st["lv"][i * B:(i + 1) * B].copy_(views[2 + i], non_blocking=True)
-        st["masks_u8"].copy_(masks["collated_masks"].to(torch.uint8), non_blocking=True)
-        idx_h = torch.zeros(cap, dtype=torch.int64); idx_h[:M] = masks["mask_indices_list"]
-        mw_h = torch.zeros(cap, dtype=torch.float32); mw_h[:M] = masks["masks_weight"]
-        iw_h = torch.zeros(cap, dtype=torch.float32); iw_h[:M] = 1.0 / max(M, 1)
-        st["idx"][:cap].copy_(idx_h, non_blocking=True)
-        st["mw"][:cap].copy_(mw_h, non_blocking=True)
-        st["iw"][:cap].copy_(iw_h, non_blocking=True)
-        pad_h = torch.full((cap,), -1e30, dtype=torch.float32); pad_h[:M] = 0.0
-        st["pad"][:cap].copy_(pad_h, non_blocking=True)
-        st["m_valid"].fill_(M)
+        if masks is None and self.mask_source == "device":
+            # masks, index list, weights and padding masks are written straight into the static buffers by two kernels
+            if "targets" not in st:
+                st["targets"] = torch.empty(2 * B, device=dev, dtype=torch.int32)
+            cap = self._device_masks(2 * B, hh, ww, bufs=st)["cap"]
+        else:
+            if masks is None:
+                masks = self._masks(2 * B, hh, ww)
+            M = int(masks["mask_indices_list"].shape[0])
+            cap = max(512, -(-M // 512) * 512)
+            st["masks_u8"].copy_(masks["collated_masks"].to(torch.uint8), non_blocking=True)
+            idx_h = torch.zeros(cap, dtype=torch.int64); idx_h[:M] = masks["mask_indices_list"]
+            mw_h = torch.zeros(cap, dtype=torch.float32); mw_h[:M] = masks["masks_weight"]
+            iw_h = torch.zeros(cap, dtype=torch.float32); iw_h[:M] = 1.0 / max(M, 1)
+            st["idx"][:cap].copy_(idx_h, non_blocking=True)
+            st["mw"][:cap].copy_(mw_h, non_blocking=True)
+            st["iw"][:cap].copy_(iw_h, non_blocking=True)
+            pad_h = torch.full((cap,), -1e30, dtype=torch.float32); pad_h[:M] = 0.0
+            st["pad"][:cap].copy_(pad_h, non_blocking=True)
+            st["m_valid"].fill_(M)
         st["t_scale"].fill_(1.0 / teacher_temp)
         for arena in (self.s_arena, self.t_arena):
             if not arena.bf16_valid:

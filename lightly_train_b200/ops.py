@@ -371,3 +371,19 @@ def mse(teacher, student, out, ds=None) -> None:
     """out[0] += mean((teacher - student)^2); ds = gradient wrt student.  Flat contiguous f32 tensors."""
     _req_cuda(teacher, student, out, ds)
     check(_L().b200_mse(teacher.data_ptr(), student.data_ptr(), student.numel(), out.data_ptr(), _ptr(ds), _stream()), "b200_mse")
+
+
+def block_masks(targets_i32, H: int, W: int, max_patches: int, seed: int, masks_u8, step_dev=None, min_patches: int = 4,
+                min_aspect: float = 0.3, max_aspect: float = 1 / 0.3) -> None:
+    """Device block-wise masks: targets int32 [B] -> masks_u8 [B, H*W]."""
+    _req_cuda(targets_i32, masks_u8, step_dev)
+    B = targets_i32.numel()
+    check(_L().b200_block_masks(targets_i32.data_ptr(), B, H, W, min_patches, max_patches, min_aspect, max_aspect, seed,
+                                _ptr(step_dev), masks_u8.data_ptr(), _stream()), "b200_block_masks")
+
+
+def collate_masks(masks_u8, cap: int, idx_i64, weight, row_w, pad, m_valid) -> None:
+    _req_cuda(masks_u8, idx_i64, weight, row_w, pad, m_valid)
+    B, Np = masks_u8.shape
+    check(_L().b200_collate_masks(masks_u8.data_ptr(), B, Np, cap, idx_i64.data_ptr(), weight.data_ptr(), row_w.data_ptr(),
+                                  pad.data_ptr(), m_valid.data_ptr(), _stream()), "b200_collate_masks")
