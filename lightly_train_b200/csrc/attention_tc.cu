@@ -8,10 +8,12 @@
 // rounded to bf16 before P V (here BEFORE the 1/l normalisation, flash-style: same relative rounding error), dP and dS
 // are rounded to bf16 (autocast matmul outputs / operands), dq dk dv are written in bf16.
 //
-// One CTA per (image, head).  qkv: bf16 [B*N, 3*h*64] (row pitch ld_tok); out / dout: bf16 [B*N, h*64].
-// Rows past an image's N tokens inside a TMA box belong to the next image (or are zero-filled past the tensor): finite
-// data that is always MASKED (keys >= N get probability 0, query rows >= N are zeroed before they are contracted over
-// and never stored).
+// One CTA per (image, head) -- or, for N <= 128, per (G = 128 / N consecutive images, head): the G sequences share one
+// 128-row MMA tile and a block-diagonal mask keeps every query on its own image's keys (local crops: 3 x 37 tokens).
+// qkv: bf16 [B*N, 3*h*64] (row pitch ld_tok); out / dout: bf16 [B*N, h*64].
+// Rows past the group's tokens inside a TMA box belong to the next image (or are zero-filled past the tensor): finite
+// data that is always MASKED (keys outside a query's own image get probability 0, query rows past the group are zeroed
+// before they are contracted over and never stored).
 //
 // FORWARD  (9 warps): warp 8 = control (TMA loads, all tcgen05.mma issues); warps 0-3 / 4-7 = the two 128-row query
 //   tiles, one query row per thread (TMEM lane = row, so row max / row sum are thread-local: no shuffles).
@@ -85,7 +87,7 @@ struct FwdCfg {
 
 template <int NKV16>
 __global__ void __launch_bounds__(FwdCfg<NKV16>::THREADS, 1)
-attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, int N, int h,
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, int B, int N, int G, int h,
                    float scale, __nv_bfloat16* __restrict__ out, long long ld_out, float* __restrict__ lse) {
   using C = FwdCfg<NKV16>;
   extern __shared__ uint8_t smem_raw[];
@@ -98,8 +100,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int bh = blockIdx.x, b = bh / h, head = bh % h;
-  const int n_tiles = (N + BLOCK_Q - 1) / BLOCK_Q;  // 1 or 2 query tiles
+  // one CTA = G consecutive images x one head (G > 1: short sequences packed into one 128-row tile, block-diagonal mask)
+  const int bg = blockIdx.x / h, head = blockIdx.x % h;
+  const int b0 = bg * G, n_img = min(G, B - b0);
+  const int rows_valid = n_img * N;
+  const int n_tiles = (rows_valid + BLOCK_Q - 1) / BLOCK_Q;  // 1 or 2 query tiles
 
   if (threadIdx.x == 0) {
     mbar_init(bar_load, 1);
@@ -125,7 +130,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   if (warp == 8) {
     // ===================== control warp: TMA + MMA issue =====================
-    const int row0 = b * N;  // first token row of this image in the [B*N, 3*h*64] qkv matrix
+    const int row0 = b0 * N;  // first token row of this group in the [B*N, 3*h*64] qkv matrix
     if (lane == 0) {
       mbar_expect_tx(bar_load, 2 * TILE_BYTES + 2 * C::KV_BYTES);
       tma_load_2d(smem, &tmQ, bar_load, head * HD, row0);
@@ -167,7 +172,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // ===================== worker warps: tile t = warp / 4, one query row per thread =====================
     const int t = warp >> 2, q = warp & 3;
     const int r = q * 32 + lane;        // row inside the 128-row tile == TMEM lane
-    const int m = t * BLOCK_Q + r;      // query token index inside the image
+    const int m = t * BLOCK_Q + r;      // query row inside the group
+    const int img = min(m / N, n_img - 1);
+    const int klo = img * N, khi = klo + N;  // this row's keys: its own image's tokens
     const uint32_t tS = tmem_base + ((uint32_t)(q * 32) << 16) + t * 256;
     const float sl2 = scale * kLog2e;
     uint8_t* sP = smem + C::OFF_P + t * C::P_BYTES;
@@ -180,7 +187,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       uint32_t v[16];
       tmem_ld_32x16(tS + c * 16, v);
       tmem_ld_wait();
-      if (c * 16 + 16 <= N) {
+      if (c * 16 >= klo && c * 16 + 16 <= khi) {
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
           const float2 rr = unpack_bf16x2(pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
@@ -190,8 +197,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
           const float2 rr = unpack_bf16x2(pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-          if (c * 16 + i < N) mx = fmaxf(mx, rr.x);
-          if (c * 16 + i + 1 < N) mx = fmaxf(mx, rr.y);
+          const int k = c * 16 + i;
+          if (k >= klo && k < khi) mx = fmaxf(mx, rr.x);
+          if (k + 1 >= klo && k + 1 < khi) mx = fmaxf(mx, rr.y);
         }
       }
     }
@@ -204,7 +212,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tmem_ld_32x16(tS + c * 16, v);
       tmem_ld_wait();
       uint32_t pw[8];
-      if (c * 16 + 16 <= N) {
+      if (c * 16 >= klo && c * 16 + 16 <= khi) {
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
           const float2 rr = unpack_bf16x2(pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
@@ -216,8 +224,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
           const float2 rr = unpack_bf16x2(pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-          const float p0 = (c * 16 + i < N) ? ex2_ftz(fmaf(rr.x, sl2, mb)) : 0.f;
-          const float p1 = (c * 16 + i + 1 < N) ? ex2_ftz(fmaf(rr.y, sl2, mb)) : 0.f;
+          const int k = c * 16 + i;
+          const float p0 = (k >= klo && k < khi) ? ex2_ftz(fmaf(rr.x, sl2, mb)) : 0.f;
+          const float p1 = (k + 1 >= klo && k + 1 < khi) ? ex2_ftz(fmaf(rr.y, sl2, mb)) : 0.f;
           l += p0 + p1;
           pw[i >> 1] = pack_bf16x2(p0, p1);
         }
@@ -232,18 +241,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_p + t);
-    if (lse && m < N) lse[(size_t)bh * N + m] = mx * scale + __logf(l);
+    if (lse && m < rows_valid) lse[((size_t)(b0 + img) * h + head) * N + (m - klo)] = mx * scale + __logf(l);
     // O row: scale by 1/l, round to bf16, 128 contiguous bytes per row
     mbar_wait(bar_o + t, 0);
     tc_fence_after();
     const float inv = 1.f / l;
-    __nv_bfloat16* orow = out + ((size_t)b * N + m) * ld_out + head * HD;
+    __nv_bfloat16* orow = out + ((size_t)b0 * N + m) * ld_out + head * HD;
 #pragma unroll
     for (int c = 0; c < HD / 16; ++c) {
       uint32_t v[16];
       tmem_ld_32x16(tS + c * 16, v);
       tmem_ld_wait();
-      if (m < N) {
+      if (m < rows_valid) {
         uint32_t ow[8];
 #pragma unroll
         for (int i = 0; i < 16; i += 2) ow[i >> 1] = pack_bf16x2(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
@@ -333,8 +342,8 @@ template <int NKV16>
 __global__ void __launch_bounds__(BwdCfg<NKV16>::THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                    const __grid_constant__ CUtensorMap tmDO, const __nv_bfloat16* __restrict__ outp,
-                   const __nv_bfloat16* __restrict__ dout, long long ld_out, const float* __restrict__ lse, int N, int h,
-                   float scale, __nv_bfloat16* __restrict__ dqkv, long long ld_dtok, float* __restrict__ colsum) {
+                   const __nv_bfloat16* __restrict__ dout, long long ld_out, const float* __restrict__ lse, int B, int N, int G,
+                   int h, float scale, __nv_bfloat16* __restrict__ dqkv, long long ld_dtok, float* __restrict__ colsum) {
   using C = BwdCfg<NKV16>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -352,8 +361,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int bh = blockIdx.x, b = bh / h, head = bh % h;
-  const int n_tiles = (N + BLOCK_Q - 1) / BLOCK_Q;
+  const int bg = blockIdx.x / h, head = blockIdx.x % h;  // G consecutive images x one head (see the forward kernel)
+  const int b0 = bg * G, n_img = min(G, B - b0);
+  const int rows_valid = n_img * N;
+  const int n_tiles = (rows_valid + BLOCK_Q - 1) / BLOCK_Q;
 
   if (threadIdx.x == 0) {
     mbar_init(bar_load, 1);
@@ -378,7 +389,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const size_t row0 = (size_t)b * N;
+  const size_t row0 = (size_t)b0 * N;
 
   if (warp == 8) {
     // ===================== control warp =====================
@@ -463,10 +474,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     uint8_t* sP = smem + C::OFF_P;
     // per-row constants: base-2 LSE and D_i = sum_d dO O straight from global (one 128-byte row per thread and tensor)
     {
-      const int m = g * BLOCK_Q + r;  // this thread prepares row m of the image (rows 0..255)
+      const int m = g * BLOCK_Q + r;  // this thread prepares row m of the group (rows 0..255)
       float L = 0.f, D = 0.f;
-      if (m < N) {
-        L = lse[(size_t)bh * N + m] * kLog2e;
+      if (m < rows_valid) {
+        const int im = m / N;
+        L = lse[((size_t)(b0 + im) * h + head) * N + (m - im * N)] * kLog2e;
         const uint4* po = reinterpret_cast<const uint4*>(outp + (row0 + m) * ld_out + head * HD);
         const uint4* pd = reinterpret_cast<const uint4*>(dout + (row0 + m) * ld_out + head * HD);
 #pragma unroll
@@ -490,7 +502,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     for (int t = 0; t < n_tiles; ++t) {
       const uint32_t ph = t & 1;
       const int m = t * BLOCK_Q + r;
-      const bool row_ok = m < N;
+      const bool row_ok = m < rows_valid;
+      const int klo = min(m / N, n_img - 1) * N, khi = klo + N;  // this row's keys: its own image's tokens
       const float L = sL[m], D = sD[m];
       // ---- P = 2^(s*sl2 - L) for my key columns (0 for padded rows / keys) -> smem
       mbar_wait(bar_s, ph);
@@ -504,8 +517,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
           const float2 rr = unpack_bf16x2(pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-          const float p0 = (row_ok && c * 16 + i < N) ? ex2_ftz(fmaf(rr.x, sl2, -L)) : 0.f;
-          const float p1 = (row_ok && c * 16 + i + 1 < N) ? ex2_ftz(fmaf(rr.y, sl2, -L)) : 0.f;
+          const int k = c * 16 + i;
+          const float p0 = (row_ok && k >= klo && k < khi) ? ex2_ftz(fmaf(rr.x, sl2, -L)) : 0.f;
+          const float p1 = (row_ok && k + 1 >= klo && k + 1 < khi) ? ex2_ftz(fmaf(rr.y, sl2, -L)) : 0.f;
           pw[i >> 1] = pack_bf16x2(p0, p1);
         }
         uint8_t* slab = sP + (c >> 2) * TILE_BYTES;
@@ -559,7 +573,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tc_fence_after();
     {
       const int key = g * BLOCK_Q + r;
-      const bool ok = key < N;
+      const bool ok = key < rows_valid;
       __nv_bfloat16* base = dqkv + (row0 + key) * ld_dtok + head * HD;
       drain_tile(tL + C::TM_DK + g * 64, scale, ok, base + (size_t)h * HD, colsum ? sC + 64 : nullptr, lane);
       drain_tile(tL + C::TM_DV + g * 64, 1.f, ok, base + (size_t)2 * h * HD, colsum ? sC + 128 : nullptr, lane);
@@ -606,8 +620,8 @@ static int tmap_rows(CUtensorMap* tm, const void* base, long long rows, long lon
 }
 
 template <int NKV16>
-static int launch_fwd(const void* qkv, long long ld_tok, int B, int N, int h, float scale, void* out, long long ld_out, float* lse,
-                      cudaStream_t s) {
+static int launch_fwd(const void* qkv, long long ld_tok, int B, int N, int G, int h, float scale, void* out, long long ld_out,
+                      float* lse, cudaStream_t s) {
   using C = FwdCfg<NKV16>;
   CUtensorMap tmQ, tmKV;
   int rc = tmap_rows(&tmQ, qkv, (long long)B * N, 3LL * h * HD, ld_tok, BLOCK_Q);
@@ -620,14 +634,15 @@ static int launch_fwd(const void* qkv, long long ld_tok, int B, int N, int h, fl
       return B200_ERR_CUDA;
     attr = true;
   }
-  attn_fwd_tc_kernel<NKV16><<<B * h, C::THREADS, C::SMEM_BYTES, s>>>(tmQ, tmKV, N, h, scale, (__nv_bfloat16*)out, ld_out, lse);
+  attn_fwd_tc_kernel<NKV16><<<((B + G - 1) / G) * h, C::THREADS, C::SMEM_BYTES, s>>>(tmQ, tmKV, B, N, G, h, scale, (__nv_bfloat16*)out,
+                                                                                  ld_out, lse);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
 
 template <int NKV16>
 static int launch_bwd(const void* qkv, long long ld_tok, const void* out, const void* dout, long long ld_out, const float* lse, int B,
-                      int N, int h, float scale, void* dqkv, long long ld_dtok, float* colsum, cudaStream_t s) {
+                      int N, int G, int h, float scale, void* dqkv, long long ld_dtok, float* colsum, cudaStream_t s) {
   using C = BwdCfg<NKV16>;
   CUtensorMap tmQ, tmKV, tmDO;
   int rc = tmap_rows(&tmQ, qkv, (long long)B * N, 3LL * h * HD, ld_tok, BLOCK_Q);
@@ -642,9 +657,9 @@ static int launch_bwd(const void* qkv, long long ld_tok, const void* out, const 
       return B200_ERR_CUDA;
     attr = true;
   }
-  attn_bwd_tc_kernel<NKV16><<<B * h, C::THREADS, C::SMEM_BYTES, s>>>(tmQ, tmKV, tmDO, (const __nv_bfloat16*)out,
-                                                                      (const __nv_bfloat16*)dout, ld_out, lse, N, h, scale,
-                                                                      (__nv_bfloat16*)dqkv, ld_dtok, colsum);
+  attn_bwd_tc_kernel<NKV16><<<((B + G - 1) / G) * h, C::THREADS, C::SMEM_BYTES, s>>>(tmQ, tmKV, tmDO, (const __nv_bfloat16*)out,
+                                                                                  (const __nv_bfloat16*)dout, ld_out, lse, B, N, G, h,
+                                                                                  scale, (__nv_bfloat16*)dqkv, ld_dtok, colsum);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -660,10 +675,10 @@ extern "C" int b200_attention_fwd_tc(const void* qkv, long long ld_tok, int B, i
   if (head_dim != HD || (ld_tok % 8) || (ld_out % 8) || ((uintptr_t)qkv & 15) || ((uintptr_t)out & 15)) return B200_ERR_UNSUPPORTED;
   if (N > 256) return B200_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
-  const int nb = (N + 15) / 16;
-  if (nb <= 4) return launch_fwd<4>(qkv, ld_tok, B, N, h, scale, out, ld_out, lse, s);
-  if (nb <= 13) return launch_fwd<13>(qkv, ld_tok, B, N, h, scale, out, ld_out, lse, s);
-  return launch_fwd<16>(qkv, ld_tok, B, N, h, scale, out, ld_out, lse, s);
+  // N <= 128: as many whole images as fit one 128-row tile share a CTA (local crops: 3 x 37 tokens), keys padded to 128
+  if (N <= 128) return launch_fwd<8>(qkv, ld_tok, B, N, 128 / N, h, scale, out, ld_out, lse, s);
+  if (N <= 208) return launch_fwd<13>(qkv, ld_tok, B, N, 1, h, scale, out, ld_out, lse, s);
+  return launch_fwd<16>(qkv, ld_tok, B, N, 1, h, scale, out, ld_out, lse, s);
 }
 
 // Backward on tcgen05.  N <= 208.
@@ -676,7 +691,6 @@ extern "C" int b200_attention_bwd_tc(const void* qkv, long long ld_tok, const vo
   if (((uintptr_t)qkv & 15) || ((uintptr_t)out & 15) || ((uintptr_t)dout & 15) || ((uintptr_t)dqkv & 15)) return B200_ERR_UNSUPPORTED;
   if (N > 208) return B200_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
-  const int nb = (N + 15) / 16;
-  if (nb <= 4) return launch_bwd<4>(qkv, ld_tok, out, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, dqkv_colsum, s);
-  return launch_bwd<13>(qkv, ld_tok, out, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, dqkv_colsum, s);
+  if (N <= 128) return launch_bwd<8>(qkv, ld_tok, out, dout, ld_out, lse, B, N, 128 / N, h, scale, dqkv, ld_dtok, dqkv_colsum, s);
+  return launch_bwd<13>(qkv, ld_tok, out, dout, ld_out, lse, B, N, 1, h, scale, dqkv, ld_dtok, dqkv_colsum, s);
 }

@@ -114,13 +114,14 @@ def _L():
 # warp-level kernels.  Module switches so that tests / A-B timing can pin either implementation.
 TC_ATTENTION_FWD = False  # flipped to True once validated on hardware (tools/attn_check.py, tests/test_kernels_gpu.py)
 TC_ATTENTION_BWD = False
+TC_ATTENTION_PACKED = False  # N <= 128 (local crops): several images of one head share a CTA on the tcgen05 kernels
 
 
 def attention_fwd(qkv: torch.Tensor, B: int, N: int, h: int, out: torch.Tensor, lse: torch.Tensor | None,
                   scale: float) -> None:
     """qkv bf16 [B*N, 3*h*64]; out bf16 [B*N, h*64]; lse f32 [B*h, N]."""
     _req_cuda(qkv, out, lse)
-    if TC_ATTENTION_FWD and 128 < N <= 256:
+    if (TC_ATTENTION_FWD and 128 < N <= 256) or (TC_ATTENTION_PACKED and N <= 128):
         return attention_fwd_tc(qkv, B, N, h, out, lse, scale)
     check(_L().b200_attention_fwd(qkv.data_ptr(), qkv.stride(0), B, N, h, 64, scale, out.data_ptr(), out.stride(0),
                                   _ptr(lse), _stream()), "b200_attention_fwd")
@@ -137,7 +138,7 @@ def attention_bwd(qkv, out, dout, lse, B: int, N: int, h: int, dqkv, scale: floa
     """colsum (optional f32 [3*h*64]): += column sums of dqkv, i.e. the gradient of the qkv projection's bias."""
     _req_cuda(qkv, out, dout, lse, dqkv)
     assert out.stride(0) == dout.stride(0)
-    if TC_ATTENTION_BWD and 128 < N <= 208:
+    if (TC_ATTENTION_BWD and 128 < N <= 208) or (TC_ATTENTION_PACKED and N <= 128):
         return attention_bwd_tc(qkv, out, dout, lse, B, N, h, dqkv, scale, colsum)
     check(_L().b200_attention_bwd(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), dout.data_ptr(), dout.stride(0),
                                   lse.data_ptr(), B, N, h, 64, scale, dqkv.data_ptr(), dqkv.stride(0), _ptr(colsum),

@@ -29,7 +29,7 @@ def ref_fwd_bwd(qkv, do, B, N, h):
 
 
 def check_fwd():
-    for (B, N, h) in [(3, 197, 6), (2, 201, 3), (2, 256, 3), (2, 130, 2), (5, 37, 2), (1, 16, 1), (64, 197, 6)]:
+    for (B, N, h) in [(3, 197, 6), (2, 201, 3), (2, 256, 3), (2, 130, 2), (5, 37, 2), (7, 54, 3), (1, 16, 1), (64, 197, 6)]:
         D = h * 64
         qkv = rnd(B * N, 3 * D, dtype=torch.bfloat16, seed=10)
         out, ref = (torch.zeros(B * N, D, device=dev, dtype=torch.bfloat16) for _ in range(2))
@@ -45,13 +45,13 @@ def check_fwd():
 
 
 def check_bwd():
-    for (B, N, h) in [(3, 197, 6), (2, 201, 3), (2, 130, 2), (5, 37, 2), (2, 208, 1), (64, 197, 6)]:
+    for (B, N, h) in [(3, 197, 6), (2, 201, 3), (2, 130, 2), (5, 37, 2), (7, 54, 3), (2, 208, 1), (64, 197, 6)]:
         D = h * 64
         qkv = rnd(B * N, 3 * D, dtype=torch.bfloat16, seed=10)
         do = rnd(B * N, D, dtype=torch.bfloat16, seed=11)
         out = torch.zeros(B * N, D, device=dev, dtype=torch.bfloat16)
         lse = torch.zeros(B * h, N, device=dev)
-        ops.TC_ATTENTION_FWD = ops.TC_ATTENTION_BWD = False
+        ops.TC_ATTENTION_FWD = ops.TC_ATTENTION_BWD = ops.TC_ATTENTION_PACKED = False
         ops.attention_fwd(qkv, B, N, h, out, lse, 0.125)
         dq_w = torch.zeros_like(qkv)
         cs_w = torch.zeros(3 * D, device=dev)
@@ -86,7 +86,7 @@ def timeit(fn, n=20):
 
 
 def bench():
-    for (B, N, h) in [(128, 197, 6), (64, 197, 12), (32, 197, 16)]:
+    for (B, N, h) in [(128, 197, 6), (512, 37, 6), (64, 197, 12), (32, 197, 16)]:
         D = h * 64
         qkv = rnd(B * N, 3 * D, dtype=torch.bfloat16, seed=10)
         do = rnd(B * N, D, dtype=torch.bfloat16, seed=11)
@@ -96,7 +96,7 @@ def bench():
         cs = torch.zeros(3 * D, device=dev)
         res = {}
         for tc in (False, True):
-            ops.TC_ATTENTION_FWD = ops.TC_ATTENTION_BWD = tc
+            ops.TC_ATTENTION_FWD = ops.TC_ATTENTION_BWD = ops.TC_ATTENTION_PACKED = tc
             res[("fwd", tc)] = timeit(lambda: ops.attention_fwd(qkv, B, N, h, out, lse, 0.125))
             res[("bwd", tc)] = timeit(lambda: ops.attention_bwd(qkv, out, do, lse, B, N, h, dq, 0.125, colsum=cs))
         fl = 4.0 * N * N * 64 * B * h
