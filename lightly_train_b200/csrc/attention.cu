@@ -117,6 +117,7 @@ template <int NKV16, int WARPS, bool EXACT>
 __global__ void __launch_bounds__(WARPS * 32)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, int N, int h, float scale,
                 __nv_bfloat16* __restrict__ out, long long ld_out, float* __restrict__ lse) {
+  B200_PDL_SYNC();
   constexpr int NP = NKV16 * 16;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sQ = smem_u32(smem), sK = sQ + NP * 128, sV = sK + NP * 128;
@@ -249,6 +250,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 4 ? 4 : 1))
 attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_tok, const __nv_bfloat16* __restrict__ outp,
                 const __nv_bfloat16* __restrict__ dout, long long ld_out, const float* __restrict__ lse, int N, int h,
                 float scale, __nv_bfloat16* __restrict__ dqkv, long long ld_dtok, float* __restrict__ colsum) {
+  B200_PDL_SYNC();
   constexpr int NP = NKV16 * 16;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sQ = smem_u32(smem), sK = sQ + NP * 128, sV = sK + NP * 128, sDO = sV + NP * 128;
@@ -464,7 +466,7 @@ static int launch_fwd(const void* qkv, long long ld_tok, int B, int N, int h, fl
       return B200_ERR_CUDA;
     attr = true;
   }
-  attn_fwd_kernel<NKV16, WARPS, EXACT><<<B * h, WARPS * 32, smem, s>>>((const __nv_bfloat16*)qkv, ld_tok, N, h, scale,
+  launch_kernel(attn_fwd_kernel<NKV16, WARPS, EXACT>, B * h, WARPS * 32, smem, s, (const __nv_bfloat16*)qkv, ld_tok, N, h, scale,
                                                           (__nv_bfloat16*)out, ld_out, lse);
   B200_CHECK_LAUNCH();
   return B200_OK;
@@ -480,7 +482,7 @@ static int launch_bwd(const void* qkv, long long ld_tok, const void* outp, const
       return B200_ERR_CUDA;
     attr = true;
   }
-  attn_bwd_kernel<NKV16, WARPS><<<B * h, WARPS * 32, smem, s>>>((const __nv_bfloat16*)qkv, ld_tok, (const __nv_bfloat16*)outp,
+  launch_kernel(attn_bwd_kernel<NKV16, WARPS>, B * h, WARPS * 32, smem, s, (const __nv_bfloat16*)qkv, ld_tok, (const __nv_bfloat16*)outp,
                                                                  (const __nv_bfloat16*)dout, ld_out, lse, N, h, scale,
                                                           (__nv_bfloat16*)dqkv, ld_dtok, colsum);
   B200_CHECK_LAUNCH();

@@ -89,6 +89,7 @@ template <int NKV16>
 __global__ void __launch_bounds__(FwdCfg<NKV16>::THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, int B, int N, int G, int h,
                    float scale, __nv_bfloat16* __restrict__ out, long long ld_out, float* __restrict__ lse) {
+  pdl_launch_dependents();  // the wait follows the barrier / TMEM set-up below
   using C = FwdCfg<NKV16>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -126,6 +127,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 8) {
@@ -344,6 +346,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    const __grid_constant__ CUtensorMap tmDO, const __nv_bfloat16* __restrict__ outp,
                    const __nv_bfloat16* __restrict__ dout, long long ld_out, const float* __restrict__ lse, int B, int N, int G,
                    int h, float scale, __nv_bfloat16* __restrict__ dqkv, long long ld_dtok, float* __restrict__ colsum) {
+  pdl_launch_dependents();  // the wait follows the barrier / TMEM set-up below
   using C = BwdCfg<NKV16>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -388,6 +391,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
   const size_t row0 = (size_t)b0 * N;
 
@@ -634,7 +638,7 @@ static int launch_fwd(const void* qkv, long long ld_tok, int B, int N, int G, in
       return B200_ERR_CUDA;
     attr = true;
   }
-  attn_fwd_tc_kernel<NKV16><<<((B + G - 1) / G) * h, C::THREADS, C::SMEM_BYTES, s>>>(tmQ, tmKV, B, N, G, h, scale, (__nv_bfloat16*)out,
+  launch_kernel(attn_fwd_tc_kernel<NKV16>, ((B + G - 1) / G) * h, C::THREADS, C::SMEM_BYTES, s, tmQ, tmKV, B, N, G, h, scale, (__nv_bfloat16*)out,
                                                                                   ld_out, lse);
   B200_CHECK_LAUNCH();
   return B200_OK;
@@ -657,7 +661,7 @@ static int launch_bwd(const void* qkv, long long ld_tok, const void* out, const 
       return B200_ERR_CUDA;
     attr = true;
   }
-  attn_bwd_tc_kernel<NKV16><<<((B + G - 1) / G) * h, C::THREADS, C::SMEM_BYTES, s>>>(tmQ, tmKV, tmDO, (const __nv_bfloat16*)out,
+  launch_kernel(attn_bwd_tc_kernel<NKV16>, ((B + G - 1) / G) * h, C::THREADS, C::SMEM_BYTES, s, tmQ, tmKV, tmDO, (const __nv_bfloat16*)out,
                                                                                   (const __nv_bfloat16*)dout, ld_out, lse, B, N, G, h,
                                                                                   scale, (__nv_bfloat16*)dqkv, ld_dtok, colsum);
   B200_CHECK_LAUNCH();

@@ -17,7 +17,50 @@
     if (e__ != cudaSuccess) return B200_ERR_CUDA - (int)e__ * 16; \
   } while (0)
 
+#include <cstdlib>
+#include <utility>
+
 namespace b200 {
+
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Every kernel of the library starts with B200_PDL_SYNC(): `griddepcontrol.launch_dependents` (the NEXT kernel in the
+// stream may be scheduled as soon as every CTA of this grid is running) then `griddepcontrol.wait` (block until the
+// PREVIOUS grid has completed and its memory is visible).  With launches carrying the programmatic-stream-serialization
+// attribute (B200_PDL=1) the launch latency and the prologue of kernel i+1 overlap the tail of kernel i -- ~640 dependent
+// launches per step; without the attribute both instructions are no-ops.  The tcgen05 kernels issue the wait only after
+// their barrier / TMEM / descriptor set-up, which touches no global memory.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#define B200_PDL_SYNC()                \
+  do {                                 \
+    b200::pdl_launch_dependents();     \
+    b200::pdl_wait();                  \
+  } while (0)
+
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("B200_PDL");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+// kernel<<<grid, block, smem, stream>>>(args...) with the PDL launch attribute when enabled
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);  // errors surface in cudaGetLastError
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);

@@ -18,6 +18,7 @@ namespace b200 {
 // together with its rotate-half partner chunk (dims j and j +- 32), i.e. one thread per pair of 16-byte chunks.
 __global__ void rope_apply_kernel(__nv_bfloat16* __restrict__ qkv, long long ld, int B, int N, int prefix, int h,
                                   const float* __restrict__ sn, const float* __restrict__ cs) {
+  B200_PDL_SYNC();
   const int P = N - prefix;
   const long long total = (long long)B * P * 2 * h * 4;  // 4 chunk pairs (8 dims each, first half) per head vector
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -53,6 +54,7 @@ template <bool WARP_ROWS>
 __global__ void __launch_bounds__(256) kl_rows_kernel(const float* __restrict__ s, long long lds, const float* __restrict__ t,
                                                       long long ldt, int R, int K, float inv_temp, float gscale,
                                                       float* __restrict__ loss_rows, float* __restrict__ ds, long long ldds) {
+  B200_PDL_SYNC();
   __shared__ float red[32];
   const int lane = threadIdx.x & 31;
   const int row = WARP_ROWS ? blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5) : blockIdx.x;
@@ -93,6 +95,7 @@ __global__ void __launch_bounds__(256) kl_rows_kernel(const float* __restrict__ 
 // out[0] += mean((t - s)^2) ; ds = 2 (s - t) / n   (MSELoss(reduction="mean") and its gradient wrt s, one pass)
 __global__ void __launch_bounds__(256) mse_kernel(const float* __restrict__ t, const float* __restrict__ s, long long n,
                                                   float* __restrict__ out, float* __restrict__ ds) {
+  B200_PDL_SYNC();
   __shared__ float red[32];
   const float inv_n = 1.f / (float)n;
   float acc = 0.f;
@@ -113,7 +116,7 @@ extern "C" int b200_mse(const float* teacher, const float* student, long long n,
   if (!teacher || !student || !out || n <= 0) return B200_ERR_INVALID_ARG;
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  mse_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(teacher, student, n, out, ds);
+  launch_kernel(mse_kernel, (int)blocks, 256, 0, (cudaStream_t)stream, teacher, student, n, out, ds);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -125,7 +128,7 @@ extern "C" int b200_rope_apply(void* qkv, long long ld, int B, int N, int prefix
   if (prefix == N) return B200_OK;
   const long long total = (long long)B * (N - prefix) * 2 * h * 4;
   const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  rope_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)qkv, ld, B, N, prefix, h, sin_tab, cos_tab);
+  launch_kernel(rope_apply_kernel, grid, 256, 0, (cudaStream_t)stream, (__nv_bfloat16*)qkv, ld, B, N, prefix, h, sin_tab, cos_tab);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -134,9 +137,9 @@ extern "C" int b200_kl_rows(const float* s, long long lds, const float* t, long 
                             float gscale, float* loss_rows, float* ds, long long ldds, void* stream) {
   if (!s || !t || !loss_rows || R <= 0 || K <= 0 || !(inv_temp > 0.f)) return B200_ERR_INVALID_ARG;
   if (K <= 1024)
-    kl_rows_kernel<true><<<(R + 7) / 8, 256, 0, (cudaStream_t)stream>>>(s, lds, t, ldt, R, K, inv_temp, gscale, loss_rows, ds, ldds);
+    launch_kernel(kl_rows_kernel<true>, (R + 7) / 8, 256, 0, (cudaStream_t)stream, s, lds, t, ldt, R, K, inv_temp, gscale, loss_rows, ds, ldds);
   else
-    kl_rows_kernel<false><<<R, 256, 0, (cudaStream_t)stream>>>(s, lds, t, ldt, R, K, inv_temp, gscale, loss_rows, ds, ldds);
+    launch_kernel(kl_rows_kernel<false>, R, 256, 0, (cudaStream_t)stream, s, lds, t, ldt, R, K, inv_temp, gscale, loss_rows, ds, ldds);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

@@ -335,6 +335,7 @@ template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(EpiCfg<BLOCK_N>::THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmDev p) {
+  pdl_launch_dependents();  // the wait follows the barrier / TMEM set-up below (no global memory touched before it)
   using Cfg = GemmCfg<BLOCK_N>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -379,6 +380,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_base_slot;
 
   if (warp == 0) {
@@ -503,6 +505,7 @@ template <int BLOCK_N, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<BLOCK_N>::THREADS, 1)
 gemm_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                         const GemmDev p) {
+  pdl_launch_dependents();  // the wait follows the barrier / TMEM set-up below (no global memory touched before it)
   using Cfg = Gemm2Cfg<BLOCK_N>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -548,6 +551,7 @@ gemm_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   tc_fence_before();
   cluster_sync_all();  // barrier inits and TMEM allocations of both CTAs are visible before any remote signal
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_base_slot;
 
   if (warp == 0) {
@@ -666,6 +670,7 @@ template <int BLOCK_N, int KB_MAX, int EPI>
 __global__ void __launch_bounds__(EpiCfg<BLOCK_N>::THREADS, 1)
 gemm_tcgen05_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const GemmDev p) {
+  pdl_launch_dependents();  // the wait follows the barrier / TMEM set-up below (no global memory touched before it)
   using Cfg = GemmWsCfg<BLOCK_N, KB_MAX>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -703,6 +708,7 @@ gemm_tcgen05_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_base_slot;
 
   if (warp == 0) {
@@ -874,7 +880,7 @@ static int launch_gemm_epi(const b200_gemm_args* a, cudaStream_t stream) {
   long long work = (long long)tiles * splits;
   int grid = (int)(work < g_num_sms ? work : g_num_sms);
   if (grid < 1) grid = 1;
-  gemm_tcgen05_kernel<BLOCK_N, EPI><<<grid, EpiCfg<BLOCK_N>::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  launch_kernel(gemm_tcgen05_kernel<BLOCK_N, EPI>, grid, EpiCfg<BLOCK_N>::THREADS, Cfg::SMEM_BYTES, stream, tmA, tmB, p);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -919,7 +925,7 @@ static int launch_gemm_ws_epi(const b200_gemm_args* a, cudaStream_t stream) {
   // even out the contiguous runs: ceil(tiles/grid) tiles per CTA, drop CTAs that would get nothing
   const long long per = (tiles + grid - 1) / grid;
   grid = (int)((tiles + per - 1) / per);
-  gemm_tcgen05_ws_kernel<BLOCK_N, KB_MAX, EPI><<<grid, EpiCfg<BLOCK_N>::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  launch_kernel(gemm_tcgen05_ws_kernel<BLOCK_N, KB_MAX, EPI>, grid, EpiCfg<BLOCK_N>::THREADS, Cfg::SMEM_BYTES, stream, tmA, tmB, p);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -966,7 +972,7 @@ static int launch_gemm_2sm_epi(const b200_gemm_args* a, cudaStream_t stream) {
   const int max_pairs = g_num_sms / 2;
   int pairs = (int)(work < max_pairs ? work : max_pairs);
   if (pairs < 1) pairs = 1;
-  gemm_tcgen05_2sm_kernel<BLOCK_N, EPI><<<2 * pairs, EpiCfg<BLOCK_N>::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  launch_kernel(gemm_tcgen05_2sm_kernel<BLOCK_N, EPI>, 2 * pairs, EpiCfg<BLOCK_N>::THREADS, Cfg::SMEM_BYTES, stream, tmA, tmB, p);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

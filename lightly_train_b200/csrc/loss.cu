@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) row_lse_kernel(const __nv_bfloat
                                                                 int R, int K, const float* __restrict__ colterm,
                                                                 float scale, const float* __restrict__ scale_dev,
                                                                 float* __restrict__ rowterm) {
+  B200_PDL_SYNC();
   __shared__ MaxSum red[32];
   if (scale_dev) scale = __ldg(scale_dev);
   const int r = blockIdx.x;
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(CR_THREADS) col_reduce_kernel(const __nv_bfloa
                                                                 int cg, int rows_per_cta, const float* __restrict__ rowvec,
                                                                 float scale, const float* __restrict__ scale_dev, int mode,
                                                                 float* __restrict__ out) {
+  B200_PDL_SYNC();
   extern __shared__ float cr_sm[];  // [lanes][cg*8]
   if (scale_dev) scale = __ldg(scale_dev);
   const int lanes = CR_THREADS / cg;
@@ -154,6 +156,7 @@ __global__ void __launch_bounds__(CR_THREADS) col_reduce_kernel(const __nv_bfloa
 // op 2: y = -log(x) - a        (Sinkhorn: log u = -log(sum) - log K)
 __global__ void vec_op_kernel(float* __restrict__ y, const float* __restrict__ x, int n, float a, float b, int op,
                               const float* __restrict__ a_dev) {
+  B200_PDL_SYNC();
   if (a_dev) a = __ldg(a_dev);
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -217,6 +220,7 @@ dino_ce_kernel(const __nv_bfloat16* __restrict__ s, long long lds, int Rs, int K
                const int* __restrict__ t_idx0, const int* __restrict__ t_idx1, const float* __restrict__ weight,
                float s_scale, float t_scale, const float* __restrict__ t_scale_dev, float gscale,
                float* __restrict__ loss_rows, __nv_bfloat16* __restrict__ ds, long long ldds) {
+  B200_PDL_SYNC();
   __shared__ MaxSum2 red[32];
   __shared__ MaxSum2 red_t[32];
   __shared__ float redf[32];
@@ -323,6 +327,7 @@ dino_ce_kernel(const __nv_bfloat16* __restrict__ s, long long lds, int Rs, int K
 // fixed summation order (deterministic).
 __global__ void __launch_bounds__(256) segment_sum_kernel(const float* __restrict__ x, const int* __restrict__ offsets,
                                                           float* __restrict__ out, const float* __restrict__ scale) {
+  B200_PDL_SYNC();
   __shared__ float red[32];
   const int j = blockIdx.x;
   const int a = offsets[j], b = offsets[j + 1];
@@ -341,6 +346,7 @@ template <int DL>
 __global__ void __launch_bounds__(256) koleo_kernel(const float* __restrict__ x, long long ldx, int n, int D, float eps,
                                                     int bf16_sim, float gscale, float* __restrict__ loss_out,
                                                     float* __restrict__ dx, long long lddx, int* __restrict__ nn_out) {
+  B200_PDL_SYNC();
   extern __shared__ float sm[];
   float* xn = sm;                        // [n, D]
   float* gxn = xn + (size_t)n * D;       // [n, D] grad wrt xn
@@ -444,7 +450,7 @@ using namespace b200;
 extern "C" int b200_row_lse(const void* x, long long ld, int R, int K, const float* colterm, float scale,
                             const float* scale_dev, float* rowterm, void* stream) {
   if (!x || !rowterm || R <= 0 || K <= 0 || (K % 8) || (ld % 8)) return B200_ERR_INVALID_ARG;
-  row_lse_kernel<<<R, LOSS_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ld, R, K, colterm, scale, scale_dev, rowterm);
+  launch_kernel(row_lse_kernel, R, LOSS_THREADS, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, ld, R, K, colterm, scale, scale_dev, rowterm);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -463,7 +469,7 @@ extern "C" int b200_col_reduce(const void* x, long long ld, int R, int K, const 
   const int rows_per_cta = (R + gy - 1) / gy;
   gy = (R + rows_per_cta - 1) / rows_per_cta;
   const size_t smem = (size_t)lanes * cg * 8 * sizeof(float);
-  col_reduce_kernel<<<dim3(gx, gy), CR_THREADS, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ld, R, K, cg, rows_per_cta,
+  launch_kernel(col_reduce_kernel, dim3(gx, gy), CR_THREADS, smem, (cudaStream_t)stream, (const __nv_bfloat16*)x, ld, R, K, cg, rows_per_cta,
                                                                                 rowvec, scale, scale_dev, mode, out);
   B200_CHECK_LAUNCH();
   return B200_OK;
@@ -471,7 +477,7 @@ extern "C" int b200_col_reduce(const void* x, long long ld, int R, int K, const 
 
 extern "C" int b200_vec_op(float* y, const float* x, int n, float a, float b, int op, const float* a_dev, void* stream) {
   if (!y || !x || n <= 0 || op < 0 || op > 2) return B200_ERR_INVALID_ARG;
-  vec_op_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(y, x, n, a, b, op, a_dev);
+  launch_kernel(vec_op_kernel, (n + 255) / 256, 256, 0, (cudaStream_t)stream, y, x, n, a, b, op, a_dev);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -484,12 +490,12 @@ extern "C" int b200_dino_ce(const void* s, long long lds, int Rs, int K, const v
   if (!t_rowterm && t_idx1) return B200_ERR_INVALID_ARG;  // the fused teacher LSE covers single-teacher rows only
   if ((K % 8) || (lds % 8) || (ldt % 8) || (ds && (ldds % 8))) return B200_ERR_INVALID_ARG;
   if (t_rowterm)
-    dino_ce_kernel<false><<<Rs, CE_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)s, lds, Rs, K,
+    launch_kernel(dino_ce_kernel<false>, Rs, CE_THREADS, 0, (cudaStream_t)stream, (const __nv_bfloat16*)s, lds, Rs, K,
                                                                           (const __nv_bfloat16*)t, ldt, colterm, t_rowterm, t_idx0,
                                                                           t_idx1, weight, s_scale, t_scale, t_scale_dev, gscale,
                                                                           loss_rows, (__nv_bfloat16*)ds, ldds);
   else
-    dino_ce_kernel<true><<<Rs, CE_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)s, lds, Rs, K,
+    launch_kernel(dino_ce_kernel<true>, Rs, CE_THREADS, 0, (cudaStream_t)stream, (const __nv_bfloat16*)s, lds, Rs, K,
                                                                          (const __nv_bfloat16*)t, ldt, colterm, nullptr, t_idx0,
                                                                          nullptr, weight, s_scale, t_scale, t_scale_dev, gscale,
                                                                          loss_rows, (__nv_bfloat16*)ds, ldds);
@@ -500,7 +506,7 @@ extern "C" int b200_dino_ce(const void* s, long long lds, int Rs, int K, const v
 extern "C" int b200_segment_sum(const float* x, const int* offsets, int n_segments, const float* scale, float* out,
                                 void* stream) {
   if (!x || !offsets || !out || n_segments <= 0) return B200_ERR_INVALID_ARG;
-  segment_sum_kernel<<<n_segments, 256, 0, (cudaStream_t)stream>>>(x, offsets, out, scale);
+  launch_kernel(segment_sum_kernel, n_segments, 256, 0, (cudaStream_t)stream, x, offsets, out, scale);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -518,7 +524,7 @@ extern "C" int b200_koleo(const float* x, long long ldx, int groups, int n, int 
         return B200_ERR_CUDA;                                                                                        \
       attr = true;                                                                                                   \
     }                                                                                                                \
-    koleo_kernel<DLV><<<groups, 256, smem, (cudaStream_t)stream>>>(x, ldx, n, D, eps, bf16_sim, gscale, loss_out, dx, lddx, nn_out); \
+    launch_kernel(koleo_kernel<DLV>, groups, 256, smem, (cudaStream_t)stream, x, ldx, n, D, eps, bf16_sim, gscale, loss_out, dx, lddx, nn_out); \
   } while (0)
   switch (D / 32) {
     case 4: B200_KOLEO(4); break;

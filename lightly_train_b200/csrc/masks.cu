@@ -36,6 +36,7 @@ static constexpr int MASK_WARPS = 4;
 __global__ void __launch_bounds__(MASK_WARPS * 32)
 block_masks_kernel(const int* __restrict__ targets, int B, int H, int W, int min_patches, int max_patches, float log_ar_lo,
                    float log_ar_hi, unsigned long long seed, const int* __restrict__ step_dev, unsigned char* __restrict__ masks) {
+  B200_PDL_SYNC();
   extern __shared__ unsigned char sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int crop = blockIdx.x * MASK_WARPS + warp;
@@ -91,6 +92,7 @@ block_masks_kernel(const int* __restrict__ targets, int B, int H, int W, int min
 __global__ void __launch_bounds__(1024)
 collate_masks_kernel(const unsigned char* __restrict__ masks, int B, int Np, int cap, long long* __restrict__ idx,
                      float* __restrict__ weight, float* __restrict__ row_w, float* __restrict__ pad, int* __restrict__ m_valid) {
+  B200_PDL_SYNC();
   __shared__ int warp_tot[32];
   __shared__ int base;
   extern __shared__ int crop_count[];  // [B]
@@ -155,7 +157,7 @@ extern "C" int b200_block_masks(const int* targets, int B, int H, int W, int min
   if (!(min_aspect > 0.f) || !(max_aspect >= min_aspect)) return B200_ERR_INVALID_ARG;
   const size_t per_warp = ((size_t)H * W + 15) / 16 * 16;
   if (per_warp * MASK_WARPS > 48 * 1024) return B200_ERR_UNSUPPORTED;
-  block_masks_kernel<<<(B + MASK_WARPS - 1) / MASK_WARPS, MASK_WARPS * 32, per_warp * MASK_WARPS, (cudaStream_t)stream>>>(
+  launch_kernel(block_masks_kernel, (B + MASK_WARPS - 1) / MASK_WARPS, MASK_WARPS * 32, per_warp * MASK_WARPS, (cudaStream_t)stream, 
       targets, B, H, W, min_patches, max_patches, logf(min_aspect), logf(max_aspect), (unsigned long long)seed, step_dev, masks);
   B200_CHECK_LAUNCH();
   return B200_OK;
@@ -165,7 +167,7 @@ extern "C" int b200_collate_masks(const unsigned char* masks, int B, int Np, int
                                   float* pad, int* m_valid, void* stream) {
   if (!masks || !idx || !weight || !row_w || !pad || !m_valid || B <= 0 || Np <= 0 || cap <= 0) return B200_ERR_INVALID_ARG;
   if ((size_t)B * sizeof(int) > 40 * 1024) return B200_ERR_UNSUPPORTED;
-  collate_masks_kernel<<<1, 1024, (size_t)B * sizeof(int), (cudaStream_t)stream>>>(masks, B, Np, cap, idx, weight, row_w, pad, m_valid);
+  launch_kernel(collate_masks_kernel, 1, 1024, (size_t)B * sizeof(int), (cudaStream_t)stream, masks, B, Np, cap, idx, weight, row_w, pad, m_valid);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

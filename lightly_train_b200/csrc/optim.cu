@@ -13,6 +13,7 @@ namespace b200 {
 
 __global__ void __launch_bounds__(256) ema_kernel(float* __restrict__ t, const float* __restrict__ s, long long n, float m,
                                                   __nv_bfloat16* __restrict__ t_bf16) {
+  B200_PDL_SYNC();
   const long long stride = (long long)gridDim.x * blockDim.x * 4;
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
     if (i + 3 < n) {
@@ -46,6 +47,7 @@ __device__ float g_sumsq_partials[SUMSQ_MAX_BLOCKS];
 __device__ unsigned int g_sumsq_ticket = 0;
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  B200_PDL_SYNC();
   __shared__ float red[32];
   __shared__ bool last;
   float acc = 0.f;
@@ -88,6 +90,7 @@ struct AdamDev {
 };
 
 __global__ void __launch_bounds__(256) adamw_ema_kernel(AdamDev a) {
+  B200_PDL_SYNC();
   if (a.dyn) {  // per-step scalars from device memory (CUDA-graph replay): see b200_adamw_args.dyn
     a.lr = a.dyn[0]; a.wd = a.dyn[1]; a.bc1 = a.dyn[2]; a.bc2_sqrt = a.dyn[3]; a.ema_m = a.dyn[4];
     a.freeze_last_layer = a.dyn[5] != 0.f; a.freeze_backbone = a.dyn[6] != 0.f;
@@ -141,6 +144,7 @@ __global__ void __launch_bounds__(256) adamw_ema_kernel(AdamDev a) {
 }
 
 __global__ void fill_kernel(float* __restrict__ x, long long n, float v) {
+  B200_PDL_SYNC();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = v;
 }
@@ -159,7 +163,7 @@ static inline int sweep_grid(long long n) {
 extern "C" int b200_ema(float* teacher, const float* student, long long n, float m, void* teacher_bf16, void* stream) {
   if (!teacher || !student || n <= 0) return B200_ERR_INVALID_ARG;
   if (((uintptr_t)teacher & 15) || ((uintptr_t)student & 15)) return B200_ERR_UNSUPPORTED;
-  ema_kernel<<<sweep_grid(n), 256, 0, (cudaStream_t)stream>>>(teacher, student, n, m, (__nv_bfloat16*)teacher_bf16);
+  launch_kernel(ema_kernel, sweep_grid(n), 256, 0, (cudaStream_t)stream, teacher, student, n, m, (__nv_bfloat16*)teacher_bf16);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -168,7 +172,7 @@ extern "C" int b200_sumsq(const float* x, long long n, float* out, void* stream)
   if (!x || !out || n <= 0 || ((uintptr_t)x & 15)) return B200_ERR_INVALID_ARG;
   int grid = sweep_grid(n);
   if (grid > SUMSQ_MAX_BLOCKS) grid = SUMSQ_MAX_BLOCKS;
-  sumsq_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, out);
+  launch_kernel(sumsq_kernel, grid, 256, 0, (cudaStream_t)stream, x, n, out);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -188,7 +192,7 @@ extern "C" int b200_adamw_ema(const b200_adamw_args* a, void* stream) {
   d.gradnorm_sq = a->gradnorm_sq;
   d.dyn = a->dyn;
   d.freeze_last_layer = a->freeze_last_layer; d.freeze_backbone = a->freeze_backbone;
-  adamw_ema_kernel<<<sweep_grid(a->n), 256, 0, (cudaStream_t)stream>>>(d);
+  launch_kernel(adamw_ema_kernel, sweep_grid(a->n), 256, 0, (cudaStream_t)stream, d);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -197,7 +201,7 @@ extern "C" int b200_fill_f32(float* x, long long n, float v, void* stream) {
   if (!x || n <= 0) return B200_ERR_INVALID_ARG;
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  fill_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, v);
+  launch_kernel(fill_kernel, (int)blocks, 256, 0, (cudaStream_t)stream, x, n, v);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

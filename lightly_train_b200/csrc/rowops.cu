@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_fwd_kernel(const float* __rest
                                                              const float* __restrict__ w, const float* __restrict__ b,
                                                              float eps, void* __restrict__ y, long long ldy,
                                                              float* __restrict__ mean, float* __restrict__ rstd) {
+  B200_PDL_SYNC();
   const int row = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
   if (row >= T) return;
   const int lane = threadIdx.x & 31;
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_bwd_kernel(const void* __restr
                                                              const float* __restrict__ rstd, float* __restrict__ dx,
                                                              long long lddx, int accumulate, float* __restrict__ dw,
                                                              float* __restrict__ db) {
+  B200_PDL_SYNC();
   extern __shared__ float sm[];  // [2][D]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = D >> 2;
@@ -166,6 +168,7 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_bwd_ls_kernel(
     long long lddx, int accumulate, float* __restrict__ dw, float* __restrict__ db, const __nv_bfloat16* __restrict__ o,
     long long ldo, const float* __restrict__ gamma, const float* __restrict__ rowscale, int rows_per_scale,
     __nv_bfloat16* __restrict__ dout, long long lddo, float* __restrict__ dgamma, float* __restrict__ dbias) {
+  B200_PDL_SYNC();
   extern __shared__ float sm[];  // [4][D]: dw, db, dgamma, dbias
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = D >> 2;
@@ -259,6 +262,7 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_bwd_ls_kernel(
 // im2col for Conv2d(k=s=p): x f32 [B,C,H,W] -> cols bf16 [B*Np, C*p*p], column order (c, ky, kx).
 __global__ void im2col_kernel(const float* __restrict__ x, int B, int C, int H, int W, int p,
                               __nv_bfloat16* __restrict__ cols, long long ldc) {
+  B200_PDL_SYNC();
   const int gw = W / p, gh = H / p;
   const long long total = (long long)B * gh * gw * C * p;  // one work item = p contiguous pixels
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -293,6 +297,7 @@ __global__ void __launch_bounds__(ROW_THREADS) assemble_tokens_kernel(const __nv
                                                                       const float* __restrict__ reg,
                                                                       const float* __restrict__ pos, int B, int Np, int R,
                                                                       int D, float* __restrict__ x) {
+  B200_PDL_SYNC();
   const int N = 1 + R + Np;
   const long long row = (long long)blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
   if (row >= (long long)B * N) return;
@@ -332,6 +337,7 @@ __global__ void assemble_tokens_bwd_kernel(const float* __restrict__ dx, const u
                                            int Np, int R, int D, __nv_bfloat16* __restrict__ dtok, long long lddt,
                                            float* __restrict__ dpos, float* __restrict__ dcls, float* __restrict__ dreg,
                                            float* __restrict__ dmask_token) {
+  B200_PDL_SYNC();
   const int N = 1 + R + Np;
   const int nd4 = D >> 2;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -381,6 +387,7 @@ __global__ void __launch_bounds__(ROW_THREADS) layerscale_bwd_kernel(const float
                                                                      int T, int D, __nv_bfloat16* __restrict__ dout,
                                                                      long long lddo, float* __restrict__ dgamma,
                                                                      float* __restrict__ dbias) {
+  B200_PDL_SYNC();
   extern __shared__ float sm[];  // [2][D]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = D >> 2;
@@ -424,6 +431,7 @@ __device__ __forceinline__ float sigmoid_fast(float x) { return rcp_ftz(1.0f + e
 
 __global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ x12, long long ld12, int T, int H,
                                   __nv_bfloat16* __restrict__ hid, long long ldh) {
+  B200_PDL_SYNC();
   const int hv = H >> 3;
   const long long total = (long long)T * hv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -445,6 +453,7 @@ __global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ x12, long lo
 
 __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ x12, long long ld12, const __nv_bfloat16* __restrict__ dh,
                                   long long lddh, int T, int H, __nv_bfloat16* __restrict__ dx12, long long lddx) {
+  B200_PDL_SYNC();
   const int hv = H >> 3;
   const long long total = (long long)T * hv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -478,6 +487,7 @@ template <bool OUT_BF16>
 __global__ void __launch_bounds__(ROW_THREADS) gather_rows_kernel(const float* __restrict__ src, long long lds,
                                                                   const long long* __restrict__ idx, int M, int D, int Np,
                                                                   int N, int off, void* __restrict__ out, long long ldo) {
+  B200_PDL_SYNC();
   const int m = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
   if (m >= M) return;
   const int lane = threadIdx.x & 31;
@@ -498,6 +508,7 @@ __global__ void __launch_bounds__(ROW_THREADS) scatter_rows_kernel(const void* _
                                                                    const long long* __restrict__ idx, int M, int D, int Np,
                                                                    int N, int off, float* __restrict__ dst, long long ldd,
                                                                    int accumulate, const int* __restrict__ count_dev) {
+  B200_PDL_SYNC();
   const int m = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
   if (m >= M) return;
   if (count_dev && m >= __ldg(count_dev)) return;  // padded rows of a static-shape (CUDA graph) step
@@ -525,6 +536,7 @@ __global__ void __launch_bounds__(ROW_THREADS) scatter_rows_kernel(const void* _
 __global__ void __launch_bounds__(ROW_THREADS) l2norm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int R,
                                                                  int D, float eps, __nv_bfloat16* __restrict__ y,
                                                                  long long ldy, float* __restrict__ nrm) {
+  B200_PDL_SYNC();
   const int row = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
   if (row >= R) return;
   const int lane = threadIdx.x & 31;
@@ -545,6 +557,7 @@ __global__ void __launch_bounds__(ROW_THREADS) l2norm_bwd_kernel(const __nv_bflo
                                                                  const __nv_bfloat16* __restrict__ x, long long ldx,
                                                                  const float* __restrict__ nrm, int R, int D,
                                                                  __nv_bfloat16* __restrict__ dx, long long lddx) {
+  B200_PDL_SYNC();
   const int row = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
   if (row >= R) return;
   const int lane = threadIdx.x & 31;
@@ -568,6 +581,7 @@ __global__ void __launch_bounds__(ROW_THREADS) l2norm_bwd_kernel(const __nv_bflo
 __global__ void __launch_bounds__(ROW_THREADS) weightnorm_fwd_kernel(const float* __restrict__ g, const float* __restrict__ v,
                                                                      int O, int I, __nv_bfloat16* __restrict__ w,
                                                                      float* __restrict__ vnorm) {
+  B200_PDL_SYNC();
   const int row = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
   if (row >= O) return;
   const int lane = threadIdx.x & 31;
@@ -589,6 +603,7 @@ __global__ void __launch_bounds__(ROW_THREADS) weightnorm_fwd_kernel(const float
 __global__ void __launch_bounds__(ROW_THREADS) weightnorm_bwd_kernel(const float* __restrict__ dW, const float* __restrict__ g,
                                                                      const float* __restrict__ v, int O, int I,
                                                                      float* __restrict__ dg, float* __restrict__ dv) {
+  B200_PDL_SYNC();
   const int row = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
   if (row >= O) return;
   const int lane = threadIdx.x & 31;
@@ -619,6 +634,7 @@ __global__ void __launch_bounds__(ROW_THREADS) weightnorm_bwd_kernel(const float
 // resampling (a fixed [36,196] bicubic operator applied to pos_embed and its transpose in the backward).
 __global__ void small_matmul_kernel(const float* __restrict__ A, long long lda, int a_trans, const float* __restrict__ B,
                                     long long ldb, int M, int N, int K, float* __restrict__ Cm, long long ldc, int accumulate) {
+  B200_PDL_SYNC();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int m = blockIdx.y;
   if (n >= N || m >= M) return;
@@ -633,6 +649,7 @@ __global__ void small_matmul_kernel(const float* __restrict__ A, long long lda, 
 
 // f32 -> bf16 cast of a flat buffer (weights for the GEMMs)
 __global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  B200_PDL_SYNC();
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     float4 v = *reinterpret_cast<const float4*>(x + i);
@@ -656,8 +673,8 @@ extern "C" int b200_layernorm_fwd(const float* x, long long ldx, int T, int D, c
   cudaStream_t st = (cudaStream_t)stream;
 #define B200_LN_FWD(V)                                                                                      \
   do {                                                                                                      \
-    if (out_bf16) ln_fwd_kernel<true, V><<<grid, ROW_THREADS, 0, st>>>(x, ldx, T, D, w, b, eps, y, ldy, mean, rstd); \
-    else ln_fwd_kernel<false, V><<<grid, ROW_THREADS, 0, st>>>(x, ldx, T, D, w, b, eps, y, ldy, mean, rstd);         \
+    if (out_bf16) launch_kernel(ln_fwd_kernel<true, V>, grid, ROW_THREADS, 0, st, x, ldx, T, D, w, b, eps, y, ldy, mean, rstd); \
+    else launch_kernel(ln_fwd_kernel<false, V>, grid, ROW_THREADS, 0, st, x, ldx, T, D, w, b, eps, y, ldy, mean, rstd);         \
   } while (0)
   if (D <= 384) B200_LN_FWD(3); else if (D <= 768) B200_LN_FWD(6); else B200_LN_FWD(8);
 #undef B200_LN_FWD
@@ -676,8 +693,8 @@ extern "C" int b200_layernorm_bwd(const void* dy, long long lddy, int dy_bf16, c
   cudaStream_t st = (cudaStream_t)stream;
 #define B200_LN_BWD(V)                                                                                                           \
   do {                                                                                                                           \
-    if (dy_bf16) ln_bwd_kernel<true, V><<<grid, ROW_THREADS, smem, st>>>(dy, lddy, x, ldx, T, D, w, mean, rstd, dx, lddx, accumulate, dw, db); \
-    else ln_bwd_kernel<false, V><<<grid, ROW_THREADS, smem, st>>>(dy, lddy, x, ldx, T, D, w, mean, rstd, dx, lddx, accumulate, dw, db);        \
+    if (dy_bf16) launch_kernel(ln_bwd_kernel<true, V>, grid, ROW_THREADS, smem, st, dy, lddy, x, ldx, T, D, w, mean, rstd, dx, lddx, accumulate, dw, db); \
+    else launch_kernel(ln_bwd_kernel<false, V>, grid, ROW_THREADS, smem, st, dy, lddy, x, ldx, T, D, w, mean, rstd, dx, lddx, accumulate, dw, db);        \
   } while (0)
   if (D <= 384) B200_LN_BWD(3); else if (D <= 768) B200_LN_BWD(6); else B200_LN_BWD(8);
 #undef B200_LN_BWD
@@ -701,11 +718,11 @@ extern "C" int b200_layernorm_bwd_ls(const void* dy, long long lddy, int dy_bf16
 #define B200_LN_BWD_LS_(V, E)                                                                                               \
   do {                                                                                                                      \
     if (dy_bf16)                                                                                                            \
-      ln_bwd_ls_kernel<true, V, E><<<grid, ROW_THREADS, smem, st>>>(dy, lddy, x, ldx, T, D, w, mean, rstd, dx, lddx, accumulate, dw, db, \
+      launch_kernel(ln_bwd_ls_kernel<true, V, E>, grid, ROW_THREADS, smem, st, dy, lddy, x, ldx, T, D, w, mean, rstd, dx, lddx, accumulate, dw, db, \
                                                                     (const __nv_bfloat16*)o, ldo, gamma, rowscale, rps,    \
                                                                     (__nv_bfloat16*)dout, lddo, dgamma, dbias);            \
     else                                                                                                                    \
-      ln_bwd_ls_kernel<false, V, false><<<grid, ROW_THREADS, smem, st>>>(dy, lddy, x, ldx, T, D, w, mean, rstd, dx, lddx, accumulate, dw, db, \
+      launch_kernel(ln_bwd_ls_kernel<false, V, false>, grid, ROW_THREADS, smem, st, dy, lddy, x, ldx, T, D, w, mean, rstd, dx, lddx, accumulate, dw, db, \
                                                                   (const __nv_bfloat16*)o, ldo, gamma, rowscale, rps,      \
                                                                   (__nv_bfloat16*)dout, lddo, dgamma, dbias);              \
   } while (0)
@@ -725,7 +742,7 @@ extern "C" int b200_im2col(const float* x, int B, int C, int H, int W, int p, vo
   if (!x || !cols || B <= 0 || C <= 0 || p <= 0 || (H % p) || (W % p)) return B200_ERR_INVALID_ARG;
   long long total = (long long)B * (H / p) * (W / p) * C * p;
   int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  im2col_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, B, C, H, W, p, (__nv_bfloat16*)cols, ldc);
+  launch_kernel(im2col_kernel, grid, 256, 0, (cudaStream_t)stream, x, B, C, H, W, p, (__nv_bfloat16*)cols, ldc);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -736,7 +753,7 @@ extern "C" int b200_assemble_tokens(const void* tok, long long ldt, const unsign
   if (!tok || !cls || !pos || !x || B <= 0 || Np <= 0 || R < 0 || (D % 4) || (ldt % 4)) return B200_ERR_INVALID_ARG;
   if ((masks && !mask_token) || (R > 0 && !reg)) return B200_ERR_INVALID_ARG;
   long long rows = (long long)B * (1 + R + Np);
-  assemble_tokens_kernel<<<(unsigned)((rows + 7) / 8), ROW_THREADS, 0, (cudaStream_t)stream>>>(
+  launch_kernel(assemble_tokens_kernel, (unsigned)((rows + 7) / 8), ROW_THREADS, 0, (cudaStream_t)stream, 
       (const __nv_bfloat16*)tok, ldt, masks, mask_token, cls, reg, pos, B, Np, R, D, x);
   B200_CHECK_LAUNCH();
   return B200_OK;
@@ -749,7 +766,7 @@ extern "C" int b200_assemble_tokens_bwd(const float* dx, const unsigned char* ma
   if ((masks && !dmask_token) || (R > 0 && !dreg)) return B200_ERR_INVALID_ARG;
   long long n = (long long)(1 + R + Np) * (D / 4);
   const int ysplit = B >= 64 ? 8 : (B >= 8 ? 4 : 1);
-  assemble_tokens_bwd_kernel<<<dim3((unsigned)((n + 127) / 128), ysplit), 128, 0, (cudaStream_t)stream>>>(
+  launch_kernel(assemble_tokens_bwd_kernel, dim3((unsigned)((n + 127) / 128), ysplit), 128, 0, (cudaStream_t)stream, 
       dx, masks, B, Np, R, D, (__nv_bfloat16*)dtok, lddt, dpos, dcls, dreg, dmask_token);
   B200_CHECK_LAUNCH();
   return B200_OK;
@@ -764,7 +781,7 @@ extern "C" int b200_layerscale_bwd(const float* dx, long long lddx, const void* 
   cudaStream_t st = (cudaStream_t)stream;
   const int rps = rows_per_scale > 0 ? rows_per_scale : 1;
 #define B200_LS_BWD(V)                                                                                          \
-  layerscale_bwd_kernel<V><<<grid, ROW_THREADS, 2 * D * sizeof(float), st>>>(dx, lddx, (const __nv_bfloat16*)o, ldo, gamma, \
+  launch_kernel(layerscale_bwd_kernel<V>, grid, ROW_THREADS, 2 * D * sizeof(float), st, dx, lddx, (const __nv_bfloat16*)o, ldo, gamma, \
                                                                             rowscale, rps, T, D, (__nv_bfloat16*)dout, lddo, \
                                                                             dgamma, dbias)
   if (D <= 384) B200_LS_BWD(3); else if (D <= 768) B200_LS_BWD(6); else B200_LS_BWD(8);
@@ -777,6 +794,7 @@ extern "C" int b200_layerscale_bwd(const float* dx, long long lddx, const void* 
 //   gather : dst[j, :] = src[idx[j], :]      scatter: dst[idx[j], :] = src[j, :]
 __global__ void copy_samples_kernel(const float* __restrict__ src, float* __restrict__ dst, const long long* __restrict__ idx,
                                     long long row_elems, int scatter) {
+  B200_PDL_SYNC();
   const long long s = idx[blockIdx.y];
   const float4* in = reinterpret_cast<const float4*>(src + (scatter ? (long long)blockIdx.y : s) * row_elems);
   float4* out = reinterpret_cast<float4*>(dst + (scatter ? s : (long long)blockIdx.y) * row_elems);
@@ -790,7 +808,7 @@ extern "C" int b200_copy_samples(const float* src, float* dst, const long long* 
   if (((uintptr_t)src & 15) || ((uintptr_t)dst & 15)) return B200_ERR_UNSUPPORTED;
   long long per = (row_elems / 4 + 255) / 256;
   int gx = (int)(per < 64 ? per : 64);
-  copy_samples_kernel<<<dim3(gx, n_idx), 256, 0, (cudaStream_t)stream>>>(src, dst, idx, row_elems, scatter);
+  launch_kernel(copy_samples_kernel, dim3(gx, n_idx), 256, 0, (cudaStream_t)stream, src, dst, idx, row_elems, scatter);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -800,7 +818,7 @@ extern "C" int b200_swiglu_fwd(const void* x12, long long ld12, int T, int H, vo
   if ((H % 8) || (ld12 % 8) || (ldh % 8) || ((uintptr_t)x12 & 15) || ((uintptr_t)hidden & 15)) return B200_ERR_UNSUPPORTED;
   const long long total = (long long)T * (H / 8);
   const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  swiglu_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x12, ld12, T, H, (__nv_bfloat16*)hidden, ldh);
+  launch_kernel(swiglu_fwd_kernel, grid, 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x12, ld12, T, H, (__nv_bfloat16*)hidden, ldh);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -813,7 +831,7 @@ extern "C" int b200_swiglu_bwd(const void* x12, long long ld12, const void* dhid
     return B200_ERR_UNSUPPORTED;
   const long long total = (long long)T * (H / 8);
   const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  swiglu_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x12, ld12, (const __nv_bfloat16*)dhidden, lddh, T, H,
+  launch_kernel(swiglu_bwd_kernel, grid, 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x12, ld12, (const __nv_bfloat16*)dhidden, lddh, T, H,
                                                             (__nv_bfloat16*)dx12, lddx12);
   B200_CHECK_LAUNCH();
   return B200_OK;
@@ -824,8 +842,8 @@ extern "C" int b200_gather_rows(const float* src, long long lds, const long long
   if (!src || !idx || !out || M < 0 || (D % 4) || (lds % 4) || (ldo % 4)) return B200_ERR_INVALID_ARG;
   if (M == 0) return B200_OK;
   dim3 grid((M + 7) / 8);
-  if (out_bf16) gather_rows_kernel<true><<<grid, ROW_THREADS, 0, (cudaStream_t)stream>>>(src, lds, idx, M, D, Np, N, off, out, ldo);
-  else gather_rows_kernel<false><<<grid, ROW_THREADS, 0, (cudaStream_t)stream>>>(src, lds, idx, M, D, Np, N, off, out, ldo);
+  if (out_bf16) launch_kernel(gather_rows_kernel<true>, grid, ROW_THREADS, 0, (cudaStream_t)stream, src, lds, idx, M, D, Np, N, off, out, ldo);
+  else launch_kernel(gather_rows_kernel<false>, grid, ROW_THREADS, 0, (cudaStream_t)stream, src, lds, idx, M, D, Np, N, off, out, ldo);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -835,8 +853,8 @@ extern "C" int b200_scatter_rows(const void* in, long long ldi, int in_bf16, con
   if (!in || !dst || M < 0 || (D % 4) || (ldi % 4) || (ldd % 4)) return B200_ERR_INVALID_ARG;
   if (M == 0) return B200_OK;
   dim3 grid((M + 7) / 8);
-  if (in_bf16) scatter_rows_kernel<true><<<grid, ROW_THREADS, 0, (cudaStream_t)stream>>>(in, ldi, idx, M, D, Np, N, off, dst, ldd, accumulate, count_dev);
-  else scatter_rows_kernel<false><<<grid, ROW_THREADS, 0, (cudaStream_t)stream>>>(in, ldi, idx, M, D, Np, N, off, dst, ldd, accumulate, count_dev);
+  if (in_bf16) launch_kernel(scatter_rows_kernel<true>, grid, ROW_THREADS, 0, (cudaStream_t)stream, in, ldi, idx, M, D, Np, N, off, dst, ldd, accumulate, count_dev);
+  else launch_kernel(scatter_rows_kernel<false>, grid, ROW_THREADS, 0, (cudaStream_t)stream, in, ldi, idx, M, D, Np, N, off, dst, ldd, accumulate, count_dev);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -844,7 +862,7 @@ extern "C" int b200_scatter_rows(const void* in, long long ldi, int in_bf16, con
 extern "C" int b200_l2norm_fwd(const void* x, long long ldx, int R, int D, float eps, void* y, long long ldy, float* nrm,
                                void* stream) {
   if (!x || !y || !nrm || R <= 0 || (D % 2) || (ldx % 2) || (ldy % 2)) return B200_ERR_INVALID_ARG;
-  l2norm_fwd_kernel<<<(R + 7) / 8, ROW_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ldx, R, D, eps,
+  launch_kernel(l2norm_fwd_kernel, (R + 7) / 8, ROW_THREADS, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, ldx, R, D, eps,
                                                                            (__nv_bfloat16*)y, ldy, nrm);
   B200_CHECK_LAUNCH();
   return B200_OK;
@@ -853,7 +871,7 @@ extern "C" int b200_l2norm_fwd(const void* x, long long ldx, int R, int D, float
 extern "C" int b200_l2norm_bwd(const void* dy, long long lddy, const void* x, long long ldx, const float* nrm, int R, int D,
                                void* dx, long long lddx, void* stream) {
   if (!dy || !x || !nrm || !dx || R <= 0 || (D % 2) || (ldx % 2) || (lddy % 2) || (lddx % 2)) return B200_ERR_INVALID_ARG;
-  l2norm_bwd_kernel<<<(R + 7) / 8, ROW_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, lddy,
+  launch_kernel(l2norm_bwd_kernel, (R + 7) / 8, ROW_THREADS, 0, (cudaStream_t)stream, (const __nv_bfloat16*)dy, lddy,
                                                                            (const __nv_bfloat16*)x, ldx, nrm, R, D,
                                                                            (__nv_bfloat16*)dx, lddx);
   B200_CHECK_LAUNCH();
@@ -862,7 +880,7 @@ extern "C" int b200_l2norm_bwd(const void* dy, long long lddy, const void* x, lo
 
 extern "C" int b200_weightnorm_fwd(const float* g, const float* v, int O, int I, void* w, float* vnorm, void* stream) {
   if (!g || !v || !w || O <= 0 || (I % 4)) return B200_ERR_INVALID_ARG;
-  weightnorm_fwd_kernel<<<(O + 7) / 8, ROW_THREADS, 0, (cudaStream_t)stream>>>(g, v, O, I, (__nv_bfloat16*)w, vnorm);
+  launch_kernel(weightnorm_fwd_kernel, (O + 7) / 8, ROW_THREADS, 0, (cudaStream_t)stream, g, v, O, I, (__nv_bfloat16*)w, vnorm);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -870,7 +888,7 @@ extern "C" int b200_weightnorm_fwd(const float* g, const float* v, int O, int I,
 extern "C" int b200_weightnorm_bwd(const float* dW, const float* g, const float* v, int O, int I, float* dg, float* dv,
                                    void* stream) {
   if (!dW || !g || !v || !dg || !dv || O <= 0 || (I % 4)) return B200_ERR_INVALID_ARG;
-  weightnorm_bwd_kernel<<<(O + 7) / 8, ROW_THREADS, 0, (cudaStream_t)stream>>>(dW, g, v, O, I, dg, dv);
+  launch_kernel(weightnorm_bwd_kernel, (O + 7) / 8, ROW_THREADS, 0, (cudaStream_t)stream, dW, g, v, O, I, dg, dv);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -879,7 +897,7 @@ extern "C" int b200_small_matmul(const float* A, long long lda, int a_trans, con
                                  float* C, long long ldc, int accumulate, void* stream) {
   if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0) return B200_ERR_INVALID_ARG;
   dim3 grid((N + 127) / 128, M);
-  small_matmul_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(A, lda, a_trans, B, ldb, M, N, K, C, ldc, accumulate);
+  launch_kernel(small_matmul_kernel, grid, 128, 0, (cudaStream_t)stream, A, lda, a_trans, B, ldb, M, N, K, C, ldc, accumulate);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -887,7 +905,7 @@ extern "C" int b200_small_matmul(const float* A, long long lda, int a_trans, con
 extern "C" int b200_cast_bf16(const float* x, void* y, long long n, void* stream) {
   if (!x || !y || n <= 0) return B200_ERR_INVALID_ARG;
   long long threads = (n + 3) / 4;
-  cast_bf16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, n);
+  launch_kernel(cast_bf16_kernel, (unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream, x, (__nv_bfloat16*)y, n);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
