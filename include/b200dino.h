@@ -214,9 +214,11 @@ int b200_dino_ce(const void* s, long long lds, int Rs, int K, const void* t, lon
 int b200_segment_sum(const float* x, const int* offsets, int n_segments, const float* scale, float* out,
                      void* stream);
 /* KoLeoLoss forward+backward (lightly.loss.KoLeoLoss; call site dinov2.py:377-380), `groups` independent
- * sets of n rows. dx += gscale * dloss/dx. */
+ * sets of n rows. dx += gscale * dloss/dx.  Groups whose 2*n*D fp32 values exceed one CTA's shared memory (or n > 256)
+ * run tiled over rows and need `scratch` (>= groups*n*(2*D + 1) floats); smaller groups ignore it (may be NULL). */
 int b200_koleo(const float* x, long long ldx, int groups, int n, int D, float eps, int bf16_sim, float gscale,
-               float* loss_out, float* dx, long long lddx, int* nn_out, void* stream);
+               float* loss_out, float* dx, long long lddx, int* nn_out, float* scratch, long long scratch_elems,
+               void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Parameter sweeps over flat fp32 arenas.

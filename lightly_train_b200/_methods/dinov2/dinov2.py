@@ -620,9 +620,8 @@ class DINOv2(nn.Module):
         n_crops, B, Ng, lcls_rows = st["n_crops"], st["B"], st["Ng"], st["lcls_rows"]
         # KoLeo on the pre-head global cls tokens (:377-380): forward value + gradient (+=) into dxn_g
         koleo = torch.zeros(2, device=dev, dtype=f32)
-        if B > self._koleo_max_batch or B < 2:
-            raise _lib.B200Error(f"KoLeo kernel: per-GPU batch {B} outside [2, {self._koleo_max_batch}] for embed_dim {D} "
-                                 "(one CTA per crop group keeps the group's features in shared memory; csrc/loss.cu)")
+        if B < 2:
+            raise _lib.B200Error("KoLeo needs at least 2 images per GPU (nearest neighbour inside the crop group)")
         # two CTAs of pure latency (~160 us): forked onto a side stream (a parallel branch of the captured graph) so it
         # overlaps the local-crop backward; its += into dxn_g is only needed by the global-crop backward below
         main = torch.cuda.current_stream()

@@ -443,6 +443,112 @@ __global__ void __launch_bounds__(256) koleo_kernel(const float* __restrict__ x,
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// KoLeo for groups that do not fit one CTA's shared memory (n * D * 8 B > 220 KB: e.g. ViT-B at 64 images per GPU):
+// the same arithmetic as koleo_kernel, tiled over rows, with the normalised rows / gradient accumulator / per-row
+// results in a global scratch (a few hundred KB: L2-resident).  Three launches:
+//   koleo_prep   : xn = x / max(||x||, eps) ; G = 0 ; loss = 0
+//   koleo_search : 32 query rows per CTA against all n candidates -> nn, d, loss += -log(d + eps)/n, and the two
+//                  gradient contributions of row i (to itself and to its neighbour) with fp32 atomics on G
+//   koleo_apply  : dx += gscale * (G - xn <xn, G>) / ||x||
+__global__ void __launch_bounds__(256) koleo_prep_kernel(const float* __restrict__ x, long long ldx, int rows, int n, int D, float eps,
+                                                         float* __restrict__ xn, float* __restrict__ G, float* __restrict__ nrm,
+                                                         float* __restrict__ loss_out) {
+  B200_PDL_SYNC();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + warp;
+  if (r >= rows) return;
+  float ss = 0.f;
+  for (int d = lane; d < D; d += 32) { const float v = x[(size_t)r * ldx + d]; ss += v * v; }
+  ss = warp_sum(ss);
+  const float nr = fmaxf(sqrtf(ss), eps);
+  for (int d = lane; d < D; d += 32) { xn[(size_t)r * D + d] = x[(size_t)r * ldx + d] / nr; G[(size_t)r * D + d] = 0.f; }
+  if (lane == 0) {
+    nrm[r] = nr;
+    if (r % n == 0) loss_out[r / n] = 0.f;
+  }
+}
+
+template <int DL>
+__global__ void __launch_bounds__(256) koleo_search_kernel(const float* __restrict__ xn, int n, int D, float eps, int bf16_sim,
+                                                           float* __restrict__ G, float* __restrict__ loss_out,
+                                                           int* __restrict__ nn_out, bool want_grad) {
+  B200_PDL_SYNC();
+  constexpr int KR = 4;
+  const int g = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* xg = xn + (size_t)g * n * D;
+  float* Gg = G + (size_t)g * n * D;
+  const int i0 = blockIdx.x * 32 + warp * KR;
+  if (i0 >= n) return;
+  float r[KR][DL];
+#pragma unroll
+  for (int q = 0; q < KR; ++q)
+#pragma unroll
+    for (int e = 0; e < DL; ++e) {
+      const float v = (i0 + q < n) ? xg[(size_t)(i0 + q) * D + lane + 32 * e] : 0.f;
+      r[q][e] = bf16_sim ? bf16_round(v) : v;
+    }
+  float best[KR]; int bi[KR];
+#pragma unroll
+  for (int q = 0; q < KR; ++q) { best[q] = -INFINITY; bi[q] = 0; }
+  for (int k = 0; k < n; ++k) {
+    float dot[KR];
+#pragma unroll
+    for (int q = 0; q < KR; ++q) dot[q] = 0.f;
+#pragma unroll
+    for (int e = 0; e < DL; ++e) {
+      float xk = xg[(size_t)k * D + lane + 32 * e];
+      if (bf16_sim) xk = bf16_round(xk);
+#pragma unroll
+      for (int q = 0; q < KR; ++q) dot[q] = fmaf(r[q][e], xk, dot[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < KR; ++q) {
+      float dsum = warp_sum(dot[q]);
+      if (bf16_sim) dsum = bf16_round(dsum);
+      if (k == i0 + q) dsum = -2.f;
+      if (dsum > best[q]) { best[q] = dsum; bi[q] = k; }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < KR; ++q) {
+    const int i = i0 + q;
+    if (i >= n) continue;
+    const int j = bi[q];
+    float ss = 0.f;
+    for (int d = lane; d < D; d += 32) { const float df = xg[(size_t)i * D + d] - xg[(size_t)j * D + d] + eps; ss += df * df; }
+    ss = warp_sum(ss);
+    const float di = sqrtf(ss);
+    if (lane == 0) {
+      atomicAdd(loss_out + g, -__logf(di + eps) / n);
+      if (nn_out) nn_out[g * n + i] = j;
+    }
+    if (want_grad) {
+      const float c = -(1.f / n) / (di + eps) / fmaxf(di, 1e-30f);
+      for (int d = lane; d < D; d += 32) {
+        const float v = c * (xg[(size_t)i * D + d] - xg[(size_t)j * D + d] + eps);
+        atomicAdd(Gg + (size_t)i * D + d, v);
+        atomicAdd(Gg + (size_t)j * D + d, -v);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) koleo_apply_kernel(const float* __restrict__ xn, const float* __restrict__ G,
+                                                          const float* __restrict__ nrm, int rows, int D, float gscale,
+                                                          float* __restrict__ dx, long long lddx) {
+  B200_PDL_SYNC();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + warp;
+  if (r >= rows) return;
+  float dot = 0.f;
+  for (int d = lane; d < D; d += 32) dot += xn[(size_t)r * D + d] * G[(size_t)r * D + d];
+  dot = warp_sum(dot);
+  const float inv = gscale / nrm[r];
+  for (int d = lane; d < D; d += 32) dx[(size_t)r * lddx + d] += inv * (G[(size_t)r * D + d] - xn[(size_t)r * D + d] * dot);
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -512,10 +618,35 @@ extern "C" int b200_segment_sum(const float* x, const int* offsets, int n_segmen
 }
 
 extern "C" int b200_koleo(const float* x, long long ldx, int groups, int n, int D, float eps, int bf16_sim, float gscale,
-                          float* loss_out, float* dx, long long lddx, int* nn_out, void* stream) {
-  if (!x || !loss_out || groups <= 0 || n <= 1 || n > 256 || D <= 0 || (D % 32) || D > 1024) return B200_ERR_INVALID_ARG;
-  size_t smem = (size_t)(2 * n * D + 3 * n) * sizeof(float);
-  if (smem > 220 * 1024) return B200_ERR_UNSUPPORTED;
+                          float* loss_out, float* dx, long long lddx, int* nn_out, float* scratch, long long scratch_elems,
+                          void* stream) {
+  if (!x || !loss_out || groups <= 0 || n <= 1 || D <= 0 || (D % 32) || D > 1024) return B200_ERR_INVALID_ARG;
+  const size_t smem = (size_t)(2 * n * D + 3 * n) * sizeof(float);
+  const bool tiled = smem > 220 * 1024 || n > 256;
+  if (tiled) {
+    // rows tiled over CTAs, state in the caller's scratch: xn [R, D] | G [R, D] | nrm [R]   (R = groups * n)
+    const long long R = (long long)groups * n;
+    if (!scratch || scratch_elems < 2 * R * D + R) return B200_ERR_INVALID_ARG;
+    float* xn = scratch;
+    float* G = xn + R * D;
+    float* nrm = G + R * D;
+    cudaStream_t st = (cudaStream_t)stream;
+    launch_kernel(koleo_prep_kernel, (int)((R + 7) / 8), 256, 0, st, x, ldx, (int)R, n, D, eps, xn, G, nrm, loss_out);
+#define B200_KOLEO_T(DLV) \
+    launch_kernel(koleo_search_kernel<DLV>, dim3((n + 31) / 32, groups), 256, 0, st, (const float*)xn, n, D, eps, bf16_sim, G, loss_out, nn_out, dx != nullptr)
+    switch (D / 32) {
+      case 4: B200_KOLEO_T(4); break;
+      case 6: B200_KOLEO_T(6); break;
+      case 12: B200_KOLEO_T(12); break;
+      case 24: B200_KOLEO_T(24); break;
+      case 32: B200_KOLEO_T(32); break;
+      default: return B200_ERR_UNSUPPORTED;
+    }
+#undef B200_KOLEO_T
+    if (dx) launch_kernel(koleo_apply_kernel, (int)((R + 7) / 8), 256, 0, st, (const float*)xn, (const float*)G, (const float*)nrm, (int)R, D, gscale, dx, lddx);
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+  }
 #define B200_KOLEO(DLV)                                                                                              \
   do {                                                                                                               \
     static bool attr = false;                                                                                        \

@@ -315,8 +315,12 @@ def segment_sum(x, offsets_i32, out, scale=None) -> None:
 def koleo(x, groups: int, n: int, loss_out, dx=None, gscale: float = 1.0, eps: float = 1e-8, bf16_sim: bool = True,
           nn_out=None) -> None:
     D = x.shape[1]
+    scratch = None
+    if (2 * n * D + 3 * n) * 4 > 220 * 1024 or n > 256:  # row-tiled path: normalised rows / gradient accumulator in a scratch
+        scratch = torch.empty(groups * n * (2 * D + 1), device=x.device, dtype=torch.float32)
     check(_L().b200_koleo(x.data_ptr(), x.stride(0), groups, n, D, eps, int(bf16_sim), gscale, loss_out.data_ptr(),
-                          _ptr(dx), dx.stride(0) if dx is not None else 0, _ptr(nn_out), _stream()), "b200_koleo")
+                          _ptr(dx), dx.stride(0) if dx is not None else 0, _ptr(nn_out), _ptr(scratch),
+                          scratch.numel() if scratch is not None else 0, _stream()), "b200_koleo")
 
 
 def ema(teacher_flat, student_flat, m: float, teacher_bf16=None) -> None:

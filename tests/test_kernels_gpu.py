@@ -426,8 +426,11 @@ def test_loss_kernels(K):
     torch.testing.assert_close(out, torch.stack([loss_rows[:10].sum(), loss_rows[10:30].sum(), loss_rows[30:].sum()]))
 
 
-def test_koleo():
-    n, D, groups = 64, 384, 2
+@pytest.mark.parametrize("n,D", [(64, 384), (128, 384), (128, 768), (40, 1024), (300, 128)])
+def test_koleo(n, D):
+    """(64, 384): one CTA per group with the features in shared memory; the other sizes exceed 220 KB of shared memory (or
+    256 rows) and take the row-tiled path (ViT-B / ViT-L at large per-GPU batches)."""
+    groups = 2
     x = rnd(groups * n, D, seed=40).requires_grad_(True)
     loss = torch.empty(groups, device=dev)
     dx = torch.zeros(groups * n, D, device=dev)
