@@ -485,7 +485,7 @@ class DinoVisionTransformer(nn.Module):
         overlap the second segment (DINOv2._core_b1 / _core_b2)."""
         Bc, Np, R, N, T, H, Wimg = ctx.dims
         D, Hd, h = self.embed_dim, self.hidden_dim, self.num_heads
-        dev = d_xnorm.device
+        dev = (d_xnorm if d_xnorm is not None else state["dx"]).device
         bf, f32 = torch.bfloat16, torch.float32
         E = lambda *s, dt=bf: torch.empty(*s, device=dev, dtype=dt)  # noqa: E731
         if wgrad_splits < 0:
