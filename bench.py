@@ -636,13 +636,20 @@ def main() -> None:
 
     parity = None
     if rank == 0 and world == 1 and not args.no_parity:
-        parity = bench_parity(method, cfg, batches[0]["views"], dev)
+        try:
+            parity = bench_parity(method, cfg, batches[0]["views"], dev)
+        except Exception as e:  # a checker problem must not take the measured line down
+            parity = {"error": repr(e)[:300]}
+        torch.cuda.empty_cache()
 
     cpu_baseline = None
     gpu_torch_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:  # reported at N=1 only (the other ranks would idle)
-        v, desc = cpu_reference(cfg, 1, 1, sweep=False)
-        cpu_baseline = {"value": v, "unit": "images/s", **desc}
+        try:
+            v, desc = cpu_reference(cfg, 1, 1, sweep=False)
+            cpu_baseline = {"value": v, "unit": "images/s", **desc}
+        except Exception as e:
+            cpu_baseline = {"error": repr(e)[:300]}
     if rank == 0 and world == 1 and not args.no_gpu_baseline:
         from oracle import ref_full
         if ref_full.available():
