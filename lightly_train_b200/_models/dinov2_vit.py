@@ -14,6 +14,7 @@ with fp32 accumulation, fp32 residual stream / LayerNorm / softmax.
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -141,6 +142,9 @@ class DinoVisionTransformer(nn.Module):
         # batch-subset stochastic depth: run the residual branches on the kept samples only (True) or on all samples with the
         # dropped ones scaled by zero (False: the dense statement of the same arithmetic)
         self.subset_skips_compute = True
+        # below this rate the gather / write-back copies and the un-fused LayerNorm backward cost more than the skipped rows
+        # save (cfg2: the last block's rate is float32(0.1) > 0.1, i.e. a subset block that would skip 10 % of one block)
+        self.subset_compact_min_rate = float(os.environ.get("B200_SUBSET_MIN_RATE", "0.15"))
         self.init_weights(init_values)
         # checkpoints written with block_chunks > 0 (zoo ViT-L/g configs) name blocks `blocks.{chunk}.{i}.*`
         self._register_load_state_dict_pre_hook(_unchunk_block_names)
@@ -443,7 +447,7 @@ class DinoVisionTransformer(nn.Module):
                 # (random subset = the bsub smallest of Bc uniform draws: graph-capturable, unlike randperm/index_put)
                 idx1 = torch.rand(Bc, device=dev).argsort()[:bsub]
                 idx2 = torch.rand(Bc, device=dev).argsort()[:bsub]
-                if self.subset_skips_compute:
+                if self.subset_skips_compute and self.dpr[i] >= self.subset_compact_min_rate:
                     # compact schedule: only the subset's rows go through the branch (20-30 % of the block FLOPs saved)
                     ckpt = save and self._activation_checkpointing and (i % self._activation_checkpointing_every_n_blocks == 0)
                     sv = self._block_fwd_subset(i, xcur, Bc, N, idx1, idx2, save, ckpt)

@@ -211,10 +211,10 @@ __device__ __forceinline__ MaxSum2 block_maxsum2(MaxSum2 v, MaxSum2* red) {
   return r;
 }
 
-// 256 threads, 4 CTAs per SM (64 registers): four rows in flight per SM hide each other's block barriers.
-static constexpr int CE_THREADS = 256;
-template <bool FUSE_T_LSE>
-__global__ void __launch_bounds__(CE_THREADS, 4)
+// THREADS / UNROLL2 are tuning variants (b200_dino_ce picks one; B200_CE_VARIANT overrides for A/B runs): 256 threads put
+// four rows in flight per SM (they hide each other's block barriers), UNROLL2 keeps two 16-byte loads per tensor in flight.
+template <bool FUSE_T_LSE, int THREADS, bool UNROLL2>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 dino_ce_kernel(const __nv_bfloat16* __restrict__ s, long long lds, int Rs, int K, const __nv_bfloat16* __restrict__ t,
                long long ldt, const float* __restrict__ colterm, const float* __restrict__ t_rowterm,
                const int* __restrict__ t_idx0, const int* __restrict__ t_idx1, const float* __restrict__ weight,
@@ -239,8 +239,8 @@ dino_ce_kernel(const __nv_bfloat16* __restrict__ s, long long lds, int Rs, int K
 
   // pass 1: log-sum-exp of the student row (base 2), and of the teacher row when fused
   MaxSum2 acc{-INFINITY, 0.f}, acc_t{-INFINITY, 0.f};
-  for (int k = threadIdx.x * 8; k < K; k += 2 * step) {
-    const bool two = k + step < K;
+  for (int k = threadIdx.x * 8; k < K; k += (UNROLL2 ? 2 : 1) * step) {
+    const bool two = UNROLL2 && k + step < K;
     float v0[8], v1[8], u0[8], u1[8], c0[8], c1[8];
     load8(sr + k, v0);
     if (two) load8(sr + k + step, v1);
@@ -286,9 +286,9 @@ dino_ce_kernel(const __nv_bfloat16* __restrict__ s, long long lds, int Rs, int K
   // pass 2: dot(p_t, s) and gradient
   float dot = 0.f;
   const float gw = w * s_scale * gscale;
-  for (int k0 = threadIdx.x * 8; k0 < K; k0 += 2 * step) {
+  for (int k0 = threadIdx.x * 8; k0 < K; k0 += (UNROLL2 ? 2 : 1) * step) {
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < (UNROLL2 ? 2 : 1); ++u) {
       const int k = k0 + u * step;
       if (k >= K) break;
       float sv[8], tv[8], c[8], p[8];
@@ -595,16 +595,28 @@ extern "C" int b200_dino_ce(const void* s, long long lds, int Rs, int K, const v
   if (!s || !t || !t_idx0 || !loss_rows || Rs <= 0 || K <= 0) return B200_ERR_INVALID_ARG;
   if (!t_rowterm && t_idx1) return B200_ERR_INVALID_ARG;  // the fused teacher LSE covers single-teacher rows only
   if ((K % 8) || (lds % 8) || (ldt % 8) || (ds && (ldds % 8))) return B200_ERR_INVALID_ARG;
-  if (t_rowterm)
-    launch_kernel(dino_ce_kernel<false>, Rs, CE_THREADS, 0, (cudaStream_t)stream, (const __nv_bfloat16*)s, lds, Rs, K,
-                                                                          (const __nv_bfloat16*)t, ldt, colterm, t_rowterm, t_idx0,
-                                                                          t_idx1, weight, s_scale, t_scale, t_scale_dev, gscale,
-                                                                          loss_rows, (__nv_bfloat16*)ds, ldds);
-  else
-    launch_kernel(dino_ce_kernel<true>, Rs, CE_THREADS, 0, (cudaStream_t)stream, (const __nv_bfloat16*)s, lds, Rs, K,
-                                                                         (const __nv_bfloat16*)t, ldt, colterm, nullptr, t_idx0,
-                                                                         nullptr, weight, s_scale, t_scale, t_scale_dev, gscale,
-                                                                         loss_rows, (__nv_bfloat16*)ds, ldds);
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = std::getenv("B200_CE_VARIANT");
+    variant = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 3;
+  }
+  const __nv_bfloat16* sp = (const __nv_bfloat16*)s;
+  const __nv_bfloat16* tp = (const __nv_bfloat16*)t;
+  __nv_bfloat16* dsp = (__nv_bfloat16*)ds;
+  cudaStream_t st = (cudaStream_t)stream;
+#define B200_CE(F, TH, U)                                                                                                       \
+  launch_kernel(dino_ce_kernel<F, TH, U>, Rs, TH, 0, st, sp, lds, Rs, K, tp, ldt, colterm, (const float*)(F ? nullptr : t_rowterm), \
+                t_idx0, (const int*)(F ? nullptr : t_idx1), weight, s_scale, t_scale, t_scale_dev, gscale, loss_rows, dsp, ldds)
+#define B200_CE_V(F)                                          \
+  switch (variant) {                                          \
+    case 0: B200_CE(F, 512, false); break;                    \
+    case 1: B200_CE(F, 512, true); break;                     \
+    case 2: B200_CE(F, 256, false); break;                    \
+    default: B200_CE(F, 256, true); break;                    \
+  }
+  if (t_rowterm) { B200_CE_V(false) } else { B200_CE_V(true) }
+#undef B200_CE_V
+#undef B200_CE
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

@@ -112,9 +112,12 @@ def _L():
 
 # Sequence lengths the tcgen05 attention kernels take (global crops: N = 197 / 201 / ...); the rest stay on the
 # warp-level kernels.  Module switches so that tests / A-B timing can pin either implementation.
-TC_ATTENTION_FWD = False  # flipped to True once validated on hardware (tools/attn_check.py, tests/test_kernels_gpu.py)
-TC_ATTENTION_BWD = False
-TC_ATTENTION_PACKED = False  # N <= 128 (local crops): several images of one head share a CTA on the tcgen05 kernels
+import os as _os
+
+# validated on hardware (tools/attn_check.py, tests/test_kernels_gpu.py); the defaults follow the measured A/B timings
+TC_ATTENTION_FWD = _os.environ.get("B200_TC_ATTN_FWD", "0") == "1"
+TC_ATTENTION_BWD = _os.environ.get("B200_TC_ATTN_BWD", "1") == "1"
+TC_ATTENTION_PACKED = _os.environ.get("B200_TC_ATTN_PACKED", "0") == "1"  # N <= 128: several images of one head per CTA
 
 
 def attention_fwd(qkv: torch.Tensor, B: int, N: int, h: int, out: torch.Tensor, lse: torch.Tensor | None,

@@ -7,9 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(__import__("os").environ.get("B200_TEST_UNVALIDATED") != "1",
-                                 reason="mask kernels not yet validated on hardware this round: B200_TEST_UNVALIDATED=1")]
+pytestmark = pytest.mark.gpu
 
 if not torch.cuda.is_available():
     pytest.skip("needs CUDA", allow_module_level=True)
@@ -43,7 +41,8 @@ def test_device_masks_statistics_match_host_generator():
     assert abs(cnt_d.sum() / cnt_h.sum() - 1) < 0.01
     # per-cell masking probability map (centre cells are masked more often than corners: rectangles must fit)
     pd, ph = dm[tg > 0].mean(0), hm[tg > 0].mean(0)
-    assert np.abs(pd - ph).max() < 0.04, np.abs(pd - ph).max()
+    assert np.abs(pd - ph).max() < 0.07, np.abs(pd - ph).max()  # 2 x 2048 crops: the max over 196 cells of a difference with sigma 0.016
+    assert np.abs(pd - ph).mean() < 0.015
     # blockiness: fraction of horizontally adjacent cell pairs that differ (random dots would give ~2p(1-p) = 0.4)
     def edges(m):
         g = m.reshape(-1, H, W)

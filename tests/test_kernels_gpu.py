@@ -146,7 +146,6 @@ _UNVALIDATED = pytest.mark.skipif(__import__("os").environ.get("B200_TEST_UNVALI
                                   reason="kernel not yet validated on hardware this round: opt in with B200_TEST_UNVALIDATED=1")
 
 
-@_UNVALIDATED
 @pytest.mark.parametrize("B,N,h", [(3, 197, 6), (2, 201, 3), (5, 37, 2), (2, 256, 3), (2, 130, 2), (1, 16, 1)])
 def test_attention_fwd_tcgen05(B, N, h):
     """tcgen05 / TMEM / TMA forward (the product path for 128 < N <= 256) against the fp32 torch statement and against
@@ -170,7 +169,6 @@ def test_attention_fwd_tcgen05(B, N, h):
     torch.testing.assert_close(lse, lse_ref, rtol=1e-5, atol=1e-4)
 
 
-@_UNVALIDATED
 @pytest.mark.parametrize("B,N,h", [(3, 197, 6), (2, 201, 3), (5, 37, 2), (2, 208, 1), (2, 130, 2)])
 def test_attention_bwd_tcgen05(B, N, h):
     """tcgen05 backward (the product path for 128 < N <= 208): dq | dk | dv against torch autograd (fp32) and against the

@@ -65,9 +65,11 @@ def test_lightning_shaped_loop_equals_train_step():
     lb = [float(b.train_step(batch).loss) for _ in range(3)]
     torch.cuda.synchronize()
     assert la == pytest.approx(lb, rel=1e-5)
-    # fp32 split-K atomics reorder the wgrad sums run to run: weights agree to a few ulps of the lr-sized updates
-    assert (a.s_arena.fp32 - b.s_arena.fp32).abs().max().item() < 1e-5
-    assert (a.t_arena.fp32 - b.t_arena.fp32).abs().max().item() < 1e-6
+    # fp32 split-K atomics reorder the wgrad sums run to run and Adam's first steps are lr * g/|g|: elements whose gradient
+    # sits at rounding-noise level can move by up to ~lr (here 2e-3) differently in two runs; everything else agrees tightly
+    d = (a.s_arena.fp32 - b.s_arena.fp32).abs()
+    assert d.max().item() < 3 * a.base_lr and d.mean().item() < 1e-6 and (d > 1e-5).float().mean().item() < 1e-3
+    assert (a.t_arena.fp32 - b.t_arena.fp32).abs().max().item() < 1e-4
     assert a.trainer.global_step == b.trainer.global_step == 3
     for k in ("train_loss", "train_loss/dino_global_loss", "train_loss/dino_local_loss", "train_loss/ibot_loss", "train_loss/koleo_loss"):
         assert k in a.logged and torch.isfinite(a.logged[k]).item()
@@ -180,16 +182,23 @@ def test_stochastic_depth_rng_paths():
     ctx = m._fwd(x, None, save=True, drop_path=True)
     blocks = ctx.blocks
     assert blocks[0]["rs1"] is None and blocks[0]["rs2"] is None            # rate 0: no scaling
-    rs = blocks[1]["rs1"]                                                   # rate 0.1: bernoulli(0.9) / 0.9
-    vals = set(round(v, 4) for v in rs.tolist())
-    assert vals <= {0.0, round(1 / 0.9, 4)} and len(vals) >= 1
-    for i, rate in ((2, 0.2), (3, 0.3)):                                   # subset form: b' = max(int(b(1-r)),1) kept at b/b'
+    # torch.linspace is float32: the second rate is 0.10000000149 > 0.1, so -- exactly like the reference's
+    # `sample_drop_ratio > 0.1` test (block.py:104) -- block 1 already takes the batch-subset form
+    assert m.dpr[1] > 0.1
+    for i, rate in ((1, 0.1), (2, 0.2), (3, 0.3)):                         # subset form: b' = max(int(b(1-r)),1) kept at b/b'
         for key in ("rs1", "rs2"):
             r = blocks[i][key]
             bsub = max(int(Bc * (1.0 - m.dpr[i])), 1)
             assert int((r > 0).sum()) == bsub
             assert torch.allclose(r[r > 0], torch.full((bsub,), Bc / bsub, device=dev))
     assert not torch.equal(blocks[3]["rs1"], blocks[3]["rs2"])             # independent draws per branch
+    # per-sample DropPath (rates <= 0.1): scales are bernoulli(keep) / keep
+    m2 = DinoVisionTransformer(img_size=32, patch_size=16, embed_dim=128, depth=3, num_heads=2, init_values=1.0,
+                               drop_path_rate=0.08, requires_grad=True)
+    c2 = m2._fwd(x, None, save=True, drop_path=True)
+    for i in (1, 2):
+        vals = set(round(v, 4) for v in c2.blocks[i]["rs1"].tolist())
+        assert vals <= {0.0, round(1 / (1 - m2.dpr[i]), 4)} and len(vals) >= 1
     # gradient isolation: cotangent only on sample j's tokens; a block-3 branch dropped for sample j must not see it
     N = ctx.dims[3]
     j = int((blocks[3]["rs2"] == 0).nonzero()[0])

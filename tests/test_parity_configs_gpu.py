@@ -77,11 +77,14 @@ def test_step_parity_at_baseline_dims(case):
     got = {"loss": float(res.loss)}
     got.update({k.split("/")[1]: float(v) for k, v in res.log_dict.items()})
 
-    # ---- autocast oracle on the host cores
+    # ---- autocast oracle on the host cores (with its own autograd backward: the bf16-noise yardstick for the gradients)
     taps = {}
-    with torch.no_grad():
-        out = O.training_step(cfg, student, teacher, centers, views, mk["collated_masks"], mk["mask_indices_list"],
-                              mk["masks_weight"], teacher_temp=0.05, autocast=True, taps=taps)
+    ostudent = {k: v.clone().requires_grad_(True) for k, v in student.items()}
+    out = O.training_step(cfg, ostudent, teacher, centers, views, mk["collated_masks"], mk["mask_indices_list"],
+                          mk["masks_weight"], teacher_temp=0.05, autocast=True, taps=taps)
+    out["loss"].backward()
+    out = {k: v.detach() for k, v in out.items()}
+    taps = {k: (v.detach() if torch.is_tensor(v) else v) for k, v in taps.items()}
     rec = {"case": case.name, "cuda": got, "oracle_autocast": {k: float(out[k]) for k in got}}
     nc = 2 * case.batch
     t_log = m.debug_taps["t_logits"].float().cpu()
@@ -107,19 +110,26 @@ def test_step_parity_at_baseline_dims(case):
         for k in got:
             tol = 5e-2 if k == "koleo_loss" else 5e-3
             assert abs(got[k] - terms[k]) < tol * max(1.0, abs(terms[k])), (k, got[k], terms[k])
-        worst = ("", 0.0)
-        errs = []
+        # Gradients vs the reference's fp32 autograd, norm-wise per tensor.  How far a CORRECT bf16-autocast step is from fp32
+        # depends on the configuration (at ViT-T / ViT-S width with this initialisation the cancellation-dominated
+        # patch-embedding gradient moves by 40-70 % under bf16 rounding alone), so the yardstick is the autocast-emulating
+        # oracle's own distance from the same fp32 gradients: the CUDA path may not be further away than that (x1.5 + 0.03).
+        worst = ("", 0.0, 0.0)
+        errs, oerrs = [], []
         for k in student:
             name = ("student_embedding_model.wrapped_model._model." + k[len("backbone."):]) if k.startswith("backbone.") else "student_head." + k
             gref = grads.get(name)
             if gref is None or gref.norm().item() < 1e-9:
                 continue
             e = (m.s_arena.g(k).float().cpu() - gref).norm().item() / gref.norm().item()
-            errs.append(e)
-            if e > worst[1]:
-                worst = (k, e)
-        rec["grad_rel_err"] = {"worst": worst, "median": sorted(errs)[len(errs) // 2]}
-        assert worst[1] < 8e-2, worst
+            eo = (ostudent[k].grad - gref).norm().item() / gref.norm().item()
+            errs.append(e); oerrs.append(eo)
+            if e - 1.5 * eo > worst[1] - 1.5 * worst[2]:
+                worst = (k, e, eo)
+        rec["grad_rel_err"] = {"worst_excess": worst, "median": sorted(errs)[len(errs) // 2], "max": max(errs),
+                               "autocast_oracle_median": sorted(oerrs)[len(oerrs) // 2], "autocast_oracle_max": max(oerrs)}
+        assert worst[1] < 1.5 * worst[2] + 0.03, (worst, rec["grad_rel_err"])
+        assert rec["grad_rel_err"]["median"] < 1.5 * rec["grad_rel_err"]["autocast_oracle_median"] + 0.01, rec["grad_rel_err"]
     print("PARITY", rec)
     RESULTS[case.name] = rec
 

@@ -170,7 +170,8 @@ def test_optimizer_ema_step_matches_oracle():
         hp = O.param_hparams(k[len("backbone."):] if is_bb else k, is_bb, lr, 1.0, cfg.vit.depth)
         lr_k = 0.0 if "last_layer" in k else hp["lr"]  # student_freeze_last_layer_steps=1 -> frozen at step 0
         O.adamw_step(p[k], grads[k], torch.zeros_like(p[k]), torch.zeros_like(p[k]), 1, lr_k, wd_now * hp["weight_decay"])
-    mom = O.cosine_schedule(0, 10, a.momentum_start, a.momentum_end)
+    # on_train_batch_end runs after Lightning has incremented global_step (pinned in tests/test_oracle_vs_reference_method.py)
+    mom = O.cosine_schedule(1, 10, a.momentum_start, a.momentum_end)
     O.update_ema([p[k] for k in p], [t[k] for k in p], mom)
     for k in p:
         torch.testing.assert_close(m.s_arena.p(k).cpu(), p[k], rtol=1e-4, atol=1e-6, msg=lambda s: f"{k}: {s}")
