@@ -273,6 +273,252 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 // ====================================================================================================================
+// forward, schedule 3: one 128-row query tile per CTA, two CTAs per SM
+// ====================================================================================================================
+// The first schedule keeps both query tiles of a pair in one CTA (213 KB of smem: one CTA per SM) and every thread walks
+// its score row twice through `tcgen05.ld` + `tcgen05.wait::ld` pairs: 61 us per 768-pair launch, no better than the
+// warp-level kernel -- the CTA is a serial chain (TMEM alloc, 85 KB of TMA, MMA, 26 exposed TMEM-load latencies per thread,
+// MMA, store) with nothing to overlap it.  Here:
+//   * a CTA owns ONE query tile: smem = Q 16 KB + K + V + a 2-slab P buffer (32 KB) = 100 KB at NKV = 208, TMEM = 256
+//     columns, so TWO CTAs are resident per SM and one's loads / MMAs hide behind the other's softmax;
+//   * the score row is read from TMEM ONCE, with 16-column loads software-pipelined one chunk ahead, and kept in registers as
+//     packed bf16 pairs (it is rounded to bf16 anyway: NKV/2 registers); keys outside the query's image become -inf there, so
+//     the exponential pass has no masks;
+//   * with the row in registers S is dead after pass 1, so O = P V reuses its first 64 TMEM columns, and P goes through the
+//     2-slab buffer in two halves (keys [0,128) then [128, NKV)) with the second half's exponentials computed while the first
+//     half's MMAs run.
+template <int NKV16>
+struct Fwd3Cfg {
+  static constexpr int NKV = NKV16 * 16;
+  static constexpr int KV_BYTES = NKV * 128;
+  static constexpr int OFF_K = TILE_BYTES;
+  static constexpr int OFF_V = OFF_K + KV_BYTES;
+  static constexpr int OFF_P = (OFF_V + KV_BYTES + 1023) / 1024 * 1024;
+  static constexpr int P_SLABS = NKV > 64 ? 2 : 1;
+  static constexpr int OFF_BAR = OFF_P + P_SLABS * TILE_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
+  static constexpr int THREADS = 5 * 32;
+  static constexpr int KS0 = NKV16 < 8 ? NKV16 : 8;        // 16-key MMA steps of the first / second P half
+  static constexpr int KS1 = NKV16 - KS0;
+  static constexpr int TMEM_COLS = NKV <= 128 ? 128 : 256;
+  static_assert(NKV <= 256 && SMEM_BYTES <= 232448, "shared memory (two CTAs per SM up to NKV = 208)");
+};
+
+template <int NKV16>
+__global__ void __launch_bounds__(Fwd3Cfg<NKV16>::THREADS, 2)
+attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, int B, int N, int G, int h,
+                    int tiles_per_group, float scale, __nv_bfloat16* __restrict__ out, long long ld_out, float* __restrict__ lse) {
+  pdl_launch_dependents();
+  using C = Fwd3Cfg<NKV16>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* bar_load = bars + 0;
+  uint64_t* bar_s = bars + 1;     // S in TMEM
+  uint64_t* bar_p0 = bars + 2;    // first P half in smem AND every thread has its S row in registers (4 warps)
+  uint64_t* bar_pv0 = bars + 3;   // first-half MMAs retired: the P buffer may be overwritten
+  uint64_t* bar_p1 = bars + 4;    // second P half in smem (4 warps)
+  uint64_t* bar_o = bars + 5;     // O complete in TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x % tiles_per_group;
+  const int grp = blockIdx.x / tiles_per_group;
+  const int bg = grp / h, head = grp % h;
+  const int b0 = bg * G, n_img = min(G, B - b0);
+  const int rows_valid = n_img * N;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_load, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p0, 4);
+    mbar_init(bar_pv0, 1);
+    mbar_init(bar_p1, 4);
+    mbar_init(bar_o, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmKV);
+    }
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ===================== control warp =====================
+    const int row0 = b0 * N;
+    if (lane == 0) {
+      mbar_expect_tx(bar_load, TILE_BYTES + 2 * C::KV_BYTES);
+      tma_load_2d(smem, &tmQ, bar_load, head * HD, row0 + t * BLOCK_Q);
+      tma_load_2d(smem + C::OFF_K, &tmKV, bar_load, (h + head) * HD, row0);
+      tma_load_2d(smem + C::OFF_V, &tmKV, bar_load, (2 * h + head) * HD, row0);
+    }
+    __syncwarp();
+    mbar_wait(bar_load, 0);
+    const uint32_t s0 = smem_u32(smem);
+    const uint64_t dq = smem_desc(s0, 16, 1024);
+    const uint64_t dk = smem_desc(s0 + C::OFF_K, 16, 1024);
+    const uint64_t dv = smem_desc(s0 + C::OFF_V, 64 * 128, 1024);
+    const uint64_t dp = smem_desc(s0 + C::OFF_P, 16, 1024);
+    const uint32_t idesc_s = instr_desc(BLOCK_Q, C::NKV, 0, 0);
+    const uint32_t idesc_o = instr_desc(BLOCK_Q, HD, 0, 1);
+    if (elect_one_sync()) {
+#pragma unroll
+      for (int ks = 0; ks < HD / 16; ++ks)
+        umma_f16(tmem_base, dq + (uint64_t)(ks * 2), dk + (uint64_t)(ks * 2), idesc_s, ks > 0 ? 1u : 0u);
+      umma_commit(bar_s);
+    }
+    __syncwarp();
+    mbar_wait(bar_p0, 0);
+    tc_fence_after();
+    if (elect_one_sync()) {
+#pragma unroll 1
+      for (int ks = 0; ks < C::KS0; ++ks)
+        umma_f16(tmem_base, dp + (uint64_t)(((ks >> 2) * TILE_BYTES + (ks & 3) * 32) >> 4), dv + (uint64_t)((ks * 2048) >> 4),
+                 idesc_o, ks > 0 ? 1u : 0u);
+      umma_commit(C::KS1 > 0 ? bar_pv0 : bar_o);
+    }
+    __syncwarp();
+    if (C::KS1 > 0) {
+      mbar_wait(bar_p1, 0);
+      tc_fence_after();
+      if (elect_one_sync()) {
+#pragma unroll 1
+        for (int ks = 0; ks < C::KS1; ++ks)
+          umma_f16(tmem_base, dp + (uint64_t)(((ks >> 2) * TILE_BYTES + (ks & 3) * 32) >> 4),
+                   dv + (uint64_t)(((C::KS0 + ks) * 2048) >> 4), idesc_o, 1u);
+        umma_commit(bar_o);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== worker warps: one query row per thread =====================
+    const int q = warp;
+    const int r = q * 32 + lane;
+    const int m = t * BLOCK_Q + r;
+    const int img = min(m / N, n_img - 1);
+    const int klo = img * N, khi = klo + N;
+    const uint32_t tS = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float sl2 = scale * kLog2e;
+    uint8_t* sP = smem + C::OFF_P;
+    uint32_t srow[C::KS0 * 8];                      // keys [0, 16 KS0) of the score row as packed bf16 pairs (masked = -inf)
+    uint32_t buf[2][16];                            // 16-column TMEM loads, issued one chunk ahead of their use
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+    // masked bf16 pair of columns (k, k + 1) of chunk registers a, b
+    auto pack_masked = [&](uint32_t a, uint32_t b, int k, bool inside) -> uint32_t {
+      uint32_t pk = pack_bf16x2(__uint_as_float(a), __uint_as_float(b));
+      if (!inside) {
+        if (!(k >= klo && k < khi)) pk = (pk & 0xFFFF0000u) | 0x0000FF80u;          // bf16 -inf in the low half
+        if (!(k + 1 >= klo && k + 1 < khi)) pk = (pk & 0x0000FFFFu) | 0xFF800000u;  // and in the high half
+      }
+      return pk;
+    };
+    // pass 1: row max over all keys; the first half of the row stays in registers (the second half is re-read from TMEM
+    // columns [128, NKV) later: O only overwrites columns [0, 64))
+    float mx = -INFINITY;
+    tmem_ld_32x16(tS, buf[0]);
+#pragma unroll
+    for (int c = 0; c < NKV16; ++c) {
+      tmem_ld_wait();
+      if (c + 1 < NKV16) tmem_ld_32x16(tS + (c + 1) * 16, buf[(c + 1) & 1]);
+      const bool inside = c * 16 >= klo && c * 16 + 16 <= khi;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t pk = pack_masked(buf[c & 1][2 * i], buf[c & 1][2 * i + 1], c * 16 + 2 * i, inside);
+        if (c < C::KS0) srow[c * 8 + i] = pk;
+        const float2 rr = unpack_bf16x2(pk);
+        mx = fmaxf(mx, fmaxf(rr.x, rr.y));
+      }
+    }
+    const float mb = -mx * sl2;
+    float l = 0.f;
+    if (C::KS1 > 0) tmem_ld_32x16(tS + C::KS0 * 16, buf[0]);  // second half, first chunk: in flight during the first half's math
+    // first half: keys [0, 16 * KS0) -> slabs 0 (keys 0..63) and 1 (keys 64..127)
+#pragma unroll
+    for (int c8 = 0; c8 < C::KS0 * 2; ++c8) {       // c8: group of 8 keys = 4 packed registers = one 16-byte chunk
+      uint32_t pw[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 rr = unpack_bf16x2(srow[c8 * 4 + j]);
+        const float p0 = ex2_ftz(fmaf(rr.x, sl2, mb)), p1 = ex2_ftz(fmaf(rr.y, sl2, mb));
+        l += p0 + p1;
+        pw[j] = pack_bf16x2(p0, p1);
+      }
+      *reinterpret_cast<uint4*>(sP + (c8 >> 3) * TILE_BYTES + swz(r, c8 & 7)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+    }
+    // S columns [0, 64) -- the ones O will overwrite -- were read and waited for in pass 1; the second half's in-flight loads
+    // touch columns >= 128 only
+    tc_fence_before();
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_p0);
+    if (C::KS1 > 0) {
+      // second half: exponentials of keys [16 KS0, NKV) into the (now free) row registers while the first half's MMAs run
+#pragma unroll
+      for (int c = 0; c < C::KS1; ++c) {
+        tmem_ld_wait();
+        if (c + 1 < C::KS1) tmem_ld_32x16(tS + (C::KS0 + c + 1) * 16, buf[(c + 1) & 1]);
+        const int kc = (C::KS0 + c) * 16;
+        const bool inside = kc >= klo && kc + 16 <= khi;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 rr = unpack_bf16x2(pack_masked(buf[c & 1][2 * i], buf[c & 1][2 * i + 1], kc + 2 * i, inside));
+          const float p0 = ex2_ftz(fmaf(rr.x, sl2, mb)), p1 = ex2_ftz(fmaf(rr.y, sl2, mb));
+          l += p0 + p1;
+          srow[c * 8 + i] = pack_bf16x2(p0, p1);
+        }
+      }
+    }
+    if (C::KS1 > 0) {
+      mbar_wait(bar_pv0, 0);  // the first half's MMAs have retired: the P buffer is free
+#pragma unroll
+      for (int c8 = 0; c8 < C::KS1 * 2; ++c8)
+        *reinterpret_cast<uint4*>(sP + (c8 >> 3) * TILE_BYTES + swz(r, c8 & 7)) =
+            make_uint4(srow[c8 * 4], srow[c8 * 4 + 1], srow[c8 * 4 + 2], srow[c8 * 4 + 3]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p1);
+    }
+    if (lse && m < rows_valid) lse[((size_t)(b0 + img) * h + head) * N + (m - klo)] = mx * scale + __logf(l);
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    const float inv = 1.f / l;
+    __nv_bfloat16* orow = out + ((size_t)b0 * N + m) * ld_out + head * HD;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(tS + c * 32, v);
+      tmem_ld_wait();
+      if (m < rows_valid) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint32_t ow[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            ow[j] = pack_bf16x2(__uint_as_float(v[i * 8 + 2 * j]) * inv, __uint_as_float(v[i * 8 + 2 * j + 1]) * inv);
+          *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ====================================================================================================================
 // backward
 // ====================================================================================================================
 template <int NKV16>
@@ -337,6 +583,59 @@ __device__ __forceinline__ void drain_tile(uint32_t taddr, float mul, bool valid
       const float s = warp_colsum32(f, lane);
       atomicAdd(cs + c * 32 + lane, s);
     }
+  }
+}
+
+// Backward worker passes over the 16-key chunks [C0, C1) of one row, TMEM loads issued one chunk ahead of their use.
+//   P pass : p = 2^(s*sl2 - L) (0 on padded rows / keys outside [klo, khi)) -> bf16 -> swizzled smem row
+//   dS pass: dS = p * (dP - D), bf16, written in place of p
+template <int C0, int C1>
+__device__ __forceinline__ void bwd_p_pass(uint32_t tcol, uint8_t* sP, int r, bool row_ok, int klo, int khi, float sl2, float L) {
+  uint32_t buf[2][16];
+  tmem_ld_32x16(tcol + C0 * 16, buf[0]);
+#pragma unroll
+  for (int c = C0; c < C1; ++c) {
+    tmem_ld_wait();
+    if (c + 1 < C1) tmem_ld_32x16(tcol + (c + 1) * 16, buf[(c + 1 - C0) & 1]);
+    const uint32_t (&v)[16] = buf[(c - C0) & 1];
+    uint32_t pw[8];
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+      const float2 rr = unpack_bf16x2(pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+      const int k = c * 16 + i;
+      const float p0 = (row_ok && k >= klo && k < khi) ? ex2_ftz(fmaf(rr.x, sl2, -L)) : 0.f;
+      const float p1 = (row_ok && k + 1 >= klo && k + 1 < khi) ? ex2_ftz(fmaf(rr.y, sl2, -L)) : 0.f;
+      pw[i >> 1] = pack_bf16x2(p0, p1);
+    }
+    uint8_t* slab = sP + (c >> 2) * TILE_BYTES;
+    const int ch = (c & 3) * 2;
+    *reinterpret_cast<uint4*>(slab + swz(r, ch)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+    *reinterpret_cast<uint4*>(slab + swz(r, ch + 1)) = make_uint4(pw[4], pw[5], pw[6], pw[7]);
+  }
+}
+template <int C0, int C1>
+__device__ __forceinline__ void bwd_ds_pass(uint32_t tcol, uint8_t* sP, int r, float D) {
+  uint32_t buf[2][16];
+  tmem_ld_32x16(tcol + C0 * 16, buf[0]);
+#pragma unroll
+  for (int c = C0; c < C1; ++c) {
+    uint8_t* slab = sP + (c >> 2) * TILE_BYTES;
+    const int ch = (c & 3) * 2;
+    const uint4 pa = *reinterpret_cast<const uint4*>(slab + swz(r, ch));
+    const uint4 pb = *reinterpret_cast<const uint4*>(slab + swz(r, ch + 1));
+    tmem_ld_wait();
+    if (c + 1 < C1) tmem_ld_32x16(tcol + (c + 1) * 16, buf[(c + 1 - C0) & 1]);
+    const uint32_t (&v)[16] = buf[(c - C0) & 1];
+    const uint32_t pin[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+    uint32_t dw[8];
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+      const float2 dp = unpack_bf16x2(pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));  // bf16 dP
+      const float2 pp = unpack_bf16x2(pin[i >> 1]);  // p = 0 on masked rows / keys: dS = 0 there whatever dP holds
+      dw[i >> 1] = pack_bf16x2(pp.x * (dp.x - D), pp.y * (dp.y - D));
+    }
+    *reinterpret_cast<uint4*>(slab + swz(r, ch)) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+    *reinterpret_cast<uint4*>(slab + swz(r, ch + 1)) = make_uint4(dw[4], dw[5], dw[6], dw[7]);
   }
 }
 
@@ -502,7 +801,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (threadIdx.x < 192) sC[threadIdx.x] = 0.f;
     }
     named_bar_sync(1, 256);
-    const int c_lo = g == 0 ? 0 : C::HALF16, c_hi = g == 0 ? C::HALF16 : NKV16;
     for (int t = 0; t < n_tiles; ++t) {
       const uint32_t ph = t & 1;
       const int m = t * BLOCK_Q + r;
@@ -512,25 +810,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // ---- P = 2^(s*sl2 - L) for my key columns (0 for padded rows / keys) -> smem
       mbar_wait(bar_s, ph);
       tc_fence_after();
-#pragma unroll 1
-      for (int c = c_lo; c < c_hi; ++c) {
-        uint32_t v[16];
-        tmem_ld_32x16(tL + C::TM_SDP + c * 16, v);
-        tmem_ld_wait();
-        uint32_t pw[8];
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          const float2 rr = unpack_bf16x2(pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-          const int k = c * 16 + i;
-          const float p0 = (row_ok && k >= klo && k < khi) ? ex2_ftz(fmaf(rr.x, sl2, -L)) : 0.f;
-          const float p1 = (row_ok && k + 1 >= klo && k + 1 < khi) ? ex2_ftz(fmaf(rr.y, sl2, -L)) : 0.f;
-          pw[i >> 1] = pack_bf16x2(p0, p1);
-        }
-        uint8_t* slab = sP + (c >> 2) * TILE_BYTES;
-        const int ch = (c & 3) * 2;
-        *reinterpret_cast<uint4*>(slab + swz(r, ch)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
-        *reinterpret_cast<uint4*>(slab + swz(r, ch + 1)) = make_uint4(pw[4], pw[5], pw[6], pw[7]);
-      }
+      if (g == 0) bwd_p_pass<0, C::HALF16>(tL + C::TM_SDP, sP, r, row_ok, klo, khi, sl2, L);
+      else bwd_p_pass<C::HALF16, NKV16>(tL + C::TM_SDP, sP, r, row_ok, klo, khi, sl2, L);
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
@@ -538,26 +819,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // ---- dS = P (dP - D), bf16, in place of P
       mbar_wait(bar_dp, ph);
       tc_fence_after();
-#pragma unroll 1
-      for (int c = c_lo; c < c_hi; ++c) {
-        uint32_t v[16];
-        tmem_ld_32x16(tL + C::TM_SDP + c * 16, v);
-        uint8_t* slab = sP + (c >> 2) * TILE_BYTES;
-        const int ch = (c & 3) * 2;
-        const uint4 pa = *reinterpret_cast<const uint4*>(slab + swz(r, ch));
-        const uint4 pb = *reinterpret_cast<const uint4*>(slab + swz(r, ch + 1));
-        tmem_ld_wait();
-        const uint32_t pin[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
-        uint32_t dw[8];
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          const float2 dp = unpack_bf16x2(pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));  // bf16 dP
-          const float2 pp = unpack_bf16x2(pin[i >> 1]);  // p = 0 on masked rows / keys: dS = 0 there whatever dP holds
-          dw[i >> 1] = pack_bf16x2(pp.x * (dp.x - D), pp.y * (dp.y - D));
-        }
-        *reinterpret_cast<uint4*>(slab + swz(r, ch)) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
-        *reinterpret_cast<uint4*>(slab + swz(r, ch + 1)) = make_uint4(dw[4], dw[5], dw[6], dw[7]);
-      }
+      if (g == 0) bwd_ds_pass<0, C::HALF16>(tL + C::TM_SDP, sP, r, D);
+      else bwd_ds_pass<C::HALF16, NKV16>(tL + C::TM_SDP, sP, r, D);
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
@@ -645,6 +908,28 @@ static int launch_fwd(const void* qkv, long long ld_tok, int B, int N, int G, in
 }
 
 template <int NKV16>
+static int launch_fwd3(const void* qkv, long long ld_tok, int B, int N, int G, int h, float scale, void* out, long long ld_out,
+                       float* lse, cudaStream_t s) {
+  using C = Fwd3Cfg<NKV16>;
+  CUtensorMap tmQ, tmKV;
+  int rc = tmap_rows(&tmQ, qkv, (long long)B * N, 3LL * h * HD, ld_tok, BLOCK_Q);
+  if (rc) return rc;
+  rc = tmap_rows(&tmKV, qkv, (long long)B * N, 3LL * h * HD, ld_tok, C::NKV);
+  if (rc) return rc;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(attn_fwd_tc3_kernel<NKV16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
+      return B200_ERR_CUDA;
+    attr = true;
+  }
+  const int tiles = (G * N + BLOCK_Q - 1) / BLOCK_Q;  // query tiles per (image group, head): 1 or 2
+  launch_kernel(attn_fwd_tc3_kernel<NKV16>, ((B + G - 1) / G) * h * tiles, C::THREADS, C::SMEM_BYTES, s, tmQ, tmKV, B, N, G, h, tiles,
+                scale, (__nv_bfloat16*)out, ld_out, lse);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+template <int NKV16>
 static int launch_bwd(const void* qkv, long long ld_tok, const void* out, const void* dout, long long ld_out, const float* lse, int B,
                       int N, int G, int h, float scale, void* dqkv, long long ld_dtok, float* colsum, cudaStream_t s) {
   using C = BwdCfg<NKV16>;
@@ -679,6 +964,16 @@ extern "C" int b200_attention_fwd_tc(const void* qkv, long long ld_tok, int B, i
   if (head_dim != HD || (ld_tok % 8) || (ld_out % 8) || ((uintptr_t)qkv & 15) || ((uintptr_t)out & 15)) return B200_ERR_UNSUPPORTED;
   if (N > 256) return B200_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
+  static int sched = -1;  // B200_ATTN_FWD_SCHEDULE=1: both query tiles in one CTA; default 3: one tile per CTA, two CTAs per SM
+  if (sched < 0) {
+    const char* e = std::getenv("B200_ATTN_FWD_SCHEDULE");
+    sched = (e && e[0] == '1') ? 1 : 3;
+  }
+  if (sched == 3) {
+    if (N <= 128) return launch_fwd3<8>(qkv, ld_tok, B, N, 128 / N, h, scale, out, ld_out, lse, s);
+    if (N <= 208) return launch_fwd3<13>(qkv, ld_tok, B, N, 1, h, scale, out, ld_out, lse, s);
+    return launch_fwd3<16>(qkv, ld_tok, B, N, 1, h, scale, out, ld_out, lse, s);
+  }
   // N <= 128: as many whole images as fit one 128-row tile share a CTA (local crops: 3 x 37 tokens), keys padded to 128
   if (N <= 128) return launch_fwd<8>(qkv, ld_tok, B, N, 128 / N, h, scale, out, ld_out, lse, s);
   if (N <= 208) return launch_fwd<13>(qkv, ld_tok, B, N, 1, h, scale, out, ld_out, lse, s);
