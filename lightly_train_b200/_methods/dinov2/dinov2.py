@@ -338,6 +338,7 @@ class DINOv2(nn.Module):
         self._mid_ready = torch.cuda.Event() if self.device_.type == "cuda" else None
         self._head_work = None
         self._mid_work = None
+        self.force_backbone_split: Optional[int] = None  # tests: cut the backbone backward at this block on a single rank
         self._head_off = self.s_arena.offsets["dino_head.mlp.0.weight"][0]  # arena order: backbone.*, then the heads
 
     # ------------------------------------------------------------------ the step
@@ -356,7 +357,10 @@ class DINOv2(nn.Module):
     def _backbone_split(self) -> int:
         """Block index at which the backbone backward is cut for the second overlapped all-reduce (0: no cut)."""
         nb = self.s_vit.n_blocks
-        return nb // 2 if nb >= 4 else 0
+        if self.force_backbone_split is not None:
+            return self.force_backbone_split
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        return nb // 2 if (nb >= 4 and multi) else 0  # a single rank has nothing to overlap: no cut, one graph fewer
 
     def _allreduce_upper_backbone_async(self, split_at: int) -> None:
         """Data-parallel runs: all-reduce the gradients of blocks >= split_at and of `norm` (contiguous in the arena, final

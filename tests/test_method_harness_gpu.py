@@ -240,3 +240,31 @@ def test_subset_stochastic_depth_compact_equals_dense(ckpt):
     assert kept == [max(int(Bc * 0.7), 1)] * 3
     assert (o_d - o_c).abs().max().item() < 2e-2 and (o_d - o_c).abs().mean().item() < 1e-3  # same math, bf16 tiles regrouped
     assert ((g_d - g_c).norm() / g_d.norm()).item() < 2e-2
+
+
+def test_cut_backbone_backward_equals_uncut():
+    """The backbone backward cut between blocks (the second all-reduce bucket boundary of multi-GPU runs) must produce the same
+    gradients as the uncut schedule -- eager and graph replay."""
+    from tests.golden import recipes as Rr
+    import oracle.dinov2_oracle as Oo
+    vit = Oo.ViTConfig(embed_dim=128, depth=4, num_heads=2, patch_size=16, img_size=224, init_values=1e-5)
+    cfg = Oo.StepConfig(vit=vit, head=Rr.HEAD_TINY)
+    st = Rr.det_step_state(cfg, seed=43)
+    views, masks, idx, w = Rr.step_case_inputs(cfg)
+    batch = {"views": [v.to(dev) for v in views], "masks": {"collated_masks": masks, "mask_indices_list": idx, "masks_weight": w}}
+
+    def run(split, graph):
+        margs = DINOv2Args(hidden_dim=cfg.head.hidden_dim, dino_bottleneck_dim=cfg.head.bottleneck_dim, output_dim=cfg.head.out_dim)
+        mk = dict(img_size=224, patch_size=16, embed_dim=128, depth=4, num_heads=2, init_values=1e-5, drop_path_rate=0.0)
+        m = DINOv2(margs, DINOv2AdamWViTArgs(), mk, 1024, 3, max_steps=10, device=dev)
+        m.s_arena.load_from(st["student"]); m.t_arena.load_from(st["teacher"])
+        m.force_backbone_split = split
+        res = m._graphed_step(batch) if graph else m.training_step_impl(batch, 0)
+        torch.cuda.synchronize()
+        return float(res.loss), m.s_arena.grad.clone()
+
+    l0, g0 = run(0, False)
+    for split, graph in ((2, False), (2, True), (1, True)):
+        l1, g1 = run(split, graph)
+        assert abs(l0 - l1) < 1e-5 * abs(l0)
+        assert (g0 - g1).abs().max().item() < 2e-4 * g0.abs().max().item(), (split, graph)

@@ -69,6 +69,7 @@ def _method(depth, dpr, uniform=False, ckpt=False, center="softmax", sep=False, 
         m.student_embedding_model.wrapped_model.set_activation_checkpointing(True)
     m.mask_source = mask_source
     m.use_cuda_graph = graph
+    m.force_backbone_split = depth // 2 if depth >= 4 else None  # exercise the cut backward on one rank too
     return m
 
 
