@@ -211,8 +211,9 @@ __device__ __forceinline__ MaxSum2 block_maxsum2(MaxSum2 v, MaxSum2* red) {
   return r;
 }
 
-// THREADS / UNROLL2 are tuning variants (b200_dino_ce picks one; B200_CE_VARIANT overrides for A/B runs): 256 threads put
-// four rows in flight per SM (they hide each other's block barriers), UNROLL2 keeps two 16-byte loads per tensor in flight.
+// THREADS / UNROLL2 are tuning variants (B200_CE_VARIANT=0..3 for A/B runs; profiles/r02_loss_bench.log): 512 threads with one
+// 16-byte load per tensor in flight measured fastest (masked rows, fused LSE: 445 us; 256 threads x 4 rows per SM and / or two
+// loads in flight: 486-545 us -- the kernel is bound by MUFU + issue, more registers per thread only cost occupancy).
 template <bool FUSE_T_LSE, int THREADS, bool UNROLL2>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 dino_ce_kernel(const __nv_bfloat16* __restrict__ s, long long lds, int Rs, int K, const __nv_bfloat16* __restrict__ t,
@@ -598,7 +599,7 @@ extern "C" int b200_dino_ce(const void* s, long long lds, int Rs, int K, const v
   static int variant = -1;
   if (variant < 0) {
     const char* e = std::getenv("B200_CE_VARIANT");
-    variant = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 3;
+    variant = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 0;  // measured (tools/loss_bench.py): 512 threads, one load in flight
   }
   const __nv_bfloat16* sp = (const __nv_bfloat16*)s;
   const __nv_bfloat16* tp = (const __nv_bfloat16*)t;

@@ -8,6 +8,7 @@ against
 The mirror is built from the reference's embedding model (reference ctor) and loads the reference method's state_dict
 with strict=True, so checkpoint-name compatibility is exercised at the real sizes too.
 """
+import dataclasses
 import random
 
 import pytest
@@ -54,9 +55,15 @@ def _mirror_from_state(case: RC.Case, student, teacher, centers) -> DINOv2:
 @pytest.mark.parametrize("case", [RC.CFG1, RC.CFG2, RC.CFG3, RC.CFG5], ids=lambda c: c.name)
 def test_step_parity_at_baseline_dims(case):
     torch.set_num_threads(min(32, torch.get_num_threads() if torch.get_num_threads() > 1 else 32))
+    # KoLeo enters the loss with weight 0 here (its VALUE is still computed, logged and compared): -log of the nearest-
+    # neighbour distance between a handful of nearly identical cls features is so ill-conditioned that bf16 rounding alone
+    # moves the gradient of a correct step by 40-70 % at ViT-T / ViT-S width (measured with the autocast oracle: worst
+    # tensor 0.46 with the term, 0.013 without), which would drown the comparison of everything else; the term is
+    # third-party and unpinned anyway.  Its kernel gradient is checked in tests/test_kernels_gpu.py.
+    case = dataclasses.replace(case, method=dict(case.method, koleo_loss_weight=0.0))
     have_ref = ref_full.available()
     views = RC.make_views(case)
-    cfg = RC.oracle_cfg(case)
+    cfg = dataclasses.replace(RC.oracle_cfg(case), koleo_loss_weight=0.0)
     if have_ref:
         ref, _, _ = RC.build_reference(case)
         ref_sd = {k: v.detach().clone() for k, v in ref.state_dict().items()}
@@ -110,10 +117,9 @@ def test_step_parity_at_baseline_dims(case):
         for k in got:
             tol = 5e-2 if k == "koleo_loss" else 5e-3
             assert abs(got[k] - terms[k]) < tol * max(1.0, abs(terms[k])), (k, got[k], terms[k])
-        # Gradients vs the reference's fp32 autograd, norm-wise per tensor.  How far a CORRECT bf16-autocast step is from fp32
-        # depends on the configuration (at ViT-T / ViT-S width with this initialisation the cancellation-dominated
-        # patch-embedding gradient moves by 40-70 % under bf16 rounding alone), so the yardstick is the autocast-emulating
-        # oracle's own distance from the same fp32 gradients: the CUDA path may not be further away than that (x1.5 + 0.03).
+        # Gradients vs the reference's fp32 autograd, norm-wise per tensor.  The yardstick is the autocast-emulating oracle's own
+        # distance from the same fp32 gradients (bf16 rounding of a correct step): the CUDA path may not be further away than
+        # that (x1.5 + 0.03), and never further than 8e-2.
         worst = ("", 0.0, 0.0)
         errs, oerrs = [], []
         for k in student:
@@ -129,6 +135,7 @@ def test_step_parity_at_baseline_dims(case):
         rec["grad_rel_err"] = {"worst_excess": worst, "median": sorted(errs)[len(errs) // 2], "max": max(errs),
                                "autocast_oracle_median": sorted(oerrs)[len(oerrs) // 2], "autocast_oracle_max": max(oerrs)}
         assert worst[1] < 1.5 * worst[2] + 0.03, (worst, rec["grad_rel_err"])
+        assert rec["grad_rel_err"]["max"] < 8e-2, rec["grad_rel_err"]
         assert rec["grad_rel_err"]["median"] < 1.5 * rec["grad_rel_err"]["autocast_oracle_median"] + 0.01, rec["grad_rel_err"]
     print("PARITY", rec)
     RESULTS[case.name] = rec
