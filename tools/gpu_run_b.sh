@@ -6,7 +6,7 @@ mkdir -p $O
 timeout 1500 python -m pytest tests -m gpu -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log
 for mode in fwd bwd time; do timeout 240 python tools/attn_check.py $mode > $O/attn3_$mode.log 2>&1; echo "rc=$?" >> $O/attn3_$mode.log; done
 B200_ATTN_FWD_SCHEDULE=1 timeout 240 python tools/attn_check.py time > $O/attn1_time.log 2>&1
-for v in 0 1 2 3; do B200_CE_VARIANT=$v timeout 200 python tools/loss_bench.py >> $O/loss_bench.log 2>&1; done
+for v in 0 4; do B200_CE_VARIANT=$v timeout 200 python tools/loss_bench.py >> $O/loss_bench.log 2>&1; done
 timeout 600 python bench.py --steps 20 --warmup 5 > $O/bench_cfg2.json 2> $O/bench_cfg2.err; echo "rc=$?" >> $O/bench_cfg2.err
 Q="--steps 20 --warmup 5 --no-cpu-baseline --no-gpu-baseline --no-parity --no-e2e"
 B200_TC_ATTN_FWD=1 timeout 300 python bench.py $Q > $O/bench_tcfwd.json 2>> $O/bench_ab.err
