@@ -519,6 +519,307 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 }
 
 // ====================================================================================================================
+// forward, schedule 4: persistent CTAs, TMA prefetch of the next pair, both query tiles in flight
+// ====================================================================================================================
+// Schedules 1 and 3 pay ~10 us of serial latency per CTA (TMEM alloc, descriptor fetch, an 85 KB TMA round trip, exposed
+// TMEM-load latencies) for ~1.5 us of tensor + MUFU work: 60-68 us per 768-pair launch however the work is cut.  Here a CTA
+// stays on its SM and loops over (image, head) pairs:
+//   * the set-up (barriers, TMEM, descriptors) is paid once per CTA, not once per pair;
+//   * K / V of pair i+1 are TMA-loaded into the second shared-memory stage while pair i is being processed, Q as soon as
+//     pair i's two S MMAs have retired (Q is only read by them);
+//   * the two 128-row query tiles of a pair run concurrently on the two worker warpgroups (warps 0-3 / 4-7), each with its
+//     own 256 TMEM columns (O aliases S) and its own 2-slab P buffer; the control warp (8) services them in turn;
+//   * workers use the register-cached score row and pipelined TMEM loads of schedule 3.
+// Shared memory: Q 32 KB + 2 x (K + V) + 2 x 32 KB P = 202 KB at NKV = 208.
+template <int NKV16>
+struct Fwd4Cfg {
+  static constexpr int NKV = NKV16 * 16;
+  static constexpr int KV_BYTES = NKV * 128;
+  static constexpr int OFF_KV = 2 * TILE_BYTES;                       // stage s: K at OFF_KV + s * 2 * KV_BYTES, V after it
+  static constexpr int OFF_P = (OFF_KV + 4 * KV_BYTES + 1023) / 1024 * 1024;
+  static constexpr int P_SLABS = NKV > 64 ? 2 : 1;
+  static constexpr int P_BYTES = P_SLABS * TILE_BYTES;                // per query tile
+  static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int THREADS = 9 * 32;
+  static constexpr int KS0 = NKV16 < 8 ? NKV16 : 8;
+  static constexpr int KS1 = NKV16 - KS0;
+  static_assert(NKV <= 256 && SMEM_BYTES <= 232448, "shared memory");
+};
+
+template <int NKV16>
+__global__ void __launch_bounds__(Fwd4Cfg<NKV16>::THREADS, 1)
+attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, int B, int N, int G, int h,
+                    int n_groups, float scale, __nv_bfloat16* __restrict__ out, long long ld_out, float* __restrict__ lse) {
+  pdl_launch_dependents();
+  using C = Fwd4Cfg<NKV16>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* bar_q = bars + 0;        // Q of the current pair landed                         (once per pair)
+  uint64_t* bar_kv = bars + 1;       // [2] K, V landed in stage s                           (once per two pairs)
+  uint64_t* bar_s = bars + 3;        // [2] S_t in TMEM                                      (once per pair)
+  uint64_t* bar_smma = bars + 5;     // both S MMAs retired: Q smem may be overwritten       (once per pair)
+  uint64_t* bar_p0 = bars + 6;       // [2] first P half of tile t in smem (4 warps)
+  uint64_t* bar_pv0 = bars + 8;      // [2] first-half MMAs of tile t retired
+  uint64_t* bar_p1 = bars + 10;      // [2] second P half in smem (4 warps)
+  uint64_t* bar_o = bars + 12;       // [2] O_t complete in TMEM
+  uint64_t* bar_tfree = bars + 14;   // [2] tile t's TMEM region drained (4 warps)
+  uint64_t* bar_kvfree = bars + 16;  // [2] every MMA that reads stage s has retired          (once per two pairs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool two_tiles = G * N > BLOCK_Q;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_q, 1);
+    mbar_init(bar_smma, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_kv + i, 1);
+      mbar_init(bar_s + i, 1);
+      mbar_init(bar_p0 + i, 4);
+      mbar_init(bar_pv0 + i, 1);
+      mbar_init(bar_p1 + i, 4);
+      mbar_init(bar_o + i, 1);
+      mbar_init(bar_tfree + i, 4);
+      mbar_init(bar_kvfree + i, 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 8) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmKV);
+    }
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_mine = (n_groups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // groups blockIdx.x, + gridDim.x, ...
+
+  if (warp == 8) {
+    // ===================== control warp =====================
+    const uint32_t s0 = smem_u32(smem);
+    const uint32_t idesc_s = instr_desc(BLOCK_Q, C::NKV, 0, 0);
+    const uint32_t idesc_o = instr_desc(BLOCK_Q, HD, 0, 1);
+    const uint32_t q_bytes = (two_tiles ? 2 : 1) * TILE_BYTES;
+    auto group_rows = [&](int it, int& head, int& row0) {
+      const int grp = blockIdx.x + it * gridDim.x;
+      head = grp % h;
+      row0 = (grp / h) * G * N;
+    };
+    if (lane == 0 && n_mine > 0) {  // prologue: pair 0
+      int head, row0;
+      group_rows(0, head, row0);
+      mbar_expect_tx(bar_q, q_bytes);
+      tma_load_2d(smem, &tmQ, bar_q, head * HD, row0);
+      if (two_tiles) tma_load_2d(smem + TILE_BYTES, &tmQ, bar_q, head * HD, row0 + BLOCK_Q);
+      mbar_expect_tx(bar_kv, 2 * C::KV_BYTES);
+      tma_load_2d(smem + C::OFF_KV, &tmKV, bar_kv, (h + head) * HD, row0);
+      tma_load_2d(smem + C::OFF_KV + C::KV_BYTES, &tmKV, bar_kv, (2 * h + head) * HD, row0);
+    }
+    __syncwarp();
+    for (int it = 0; it < n_mine; ++it) {
+      const int st = it & 1;
+      const uint32_t ph = it & 1, ph2 = (it >> 1) & 1;
+      const uint32_t sK = s0 + C::OFF_KV + st * 2 * C::KV_BYTES, sV = sK + C::KV_BYTES;
+      mbar_wait(bar_q, ph);
+      mbar_wait(bar_kv + st, ph2);
+      if (it > 0) {  // the TMEM regions still hold the previous pair's O until the workers have drained them
+        mbar_wait(bar_tfree + 0, ph ^ 1);
+        if (two_tiles) mbar_wait(bar_tfree + 1, ph ^ 1);
+      }
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint64_t dk = smem_desc(sK, 16, 1024);
+        for (int t = 0; t < (two_tiles ? 2 : 1); ++t) {
+          const uint64_t dq = smem_desc(s0 + t * TILE_BYTES, 16, 1024);
+#pragma unroll
+          for (int ks = 0; ks < HD / 16; ++ks)
+            umma_f16(tmem_base + t * 256, dq + (uint64_t)(ks * 2), dk + (uint64_t)(ks * 2), idesc_s, ks > 0 ? 1u : 0u);
+          umma_commit(bar_s + t);
+        }
+        umma_commit(bar_smma);
+      }
+      __syncwarp();
+      // prefetch pair it + 1: Q once this pair's S MMAs have retired, K / V into the other stage once the MMAs of pair it - 1
+      // (its last user) have retired
+      if (it + 1 < n_mine) {
+        mbar_wait(bar_smma, ph);
+        if (it >= 1) mbar_wait(bar_kvfree + (st ^ 1), ((it - 1) >> 1) & 1);
+        if (lane == 0) {
+          int head, row0;
+          group_rows(it + 1, head, row0);
+          mbar_expect_tx(bar_q, q_bytes);
+          tma_load_2d(smem, &tmQ, bar_q, head * HD, row0);
+          if (two_tiles) tma_load_2d(smem + TILE_BYTES, &tmQ, bar_q, head * HD, row0 + BLOCK_Q);
+          const uint32_t off = C::OFF_KV + (st ^ 1) * 2 * C::KV_BYTES;
+          mbar_expect_tx(bar_kv + (st ^ 1), 2 * C::KV_BYTES);
+          tma_load_2d(smem + off, &tmKV, bar_kv + (st ^ 1), (h + head) * HD, row0);
+          tma_load_2d(smem + off + C::KV_BYTES, &tmKV, bar_kv + (st ^ 1), (2 * h + head) * HD, row0);
+        }
+        __syncwarp();
+      }
+      const uint64_t dv = smem_desc(sV, 64 * 128, 1024);
+      const int nt = two_tiles ? 2 : 1;
+      for (int t = 0; t < nt; ++t) {  // first P halves
+        mbar_wait(bar_p0 + t, ph);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint64_t dp = smem_desc(s0 + C::OFF_P + t * C::P_BYTES, 16, 1024);
+#pragma unroll 1
+          for (int ks = 0; ks < C::KS0; ++ks)
+            umma_f16(tmem_base + t * 256, dp + (uint64_t)(((ks >> 2) * TILE_BYTES + (ks & 3) * 32) >> 4),
+                     dv + (uint64_t)((ks * 2048) >> 4), idesc_o, ks > 0 ? 1u : 0u);
+          umma_commit(C::KS1 > 0 ? bar_pv0 + t : bar_o + t);
+          if (C::KS1 == 0 && t == nt - 1) umma_commit(bar_kvfree + st);
+        }
+        __syncwarp();
+      }
+      if (C::KS1 > 0) {
+        for (int t = 0; t < nt; ++t) {  // second P halves
+          mbar_wait(bar_p1 + t, ph);
+          tc_fence_after();
+          if (elect_one_sync()) {
+            const uint64_t dp = smem_desc(s0 + C::OFF_P + t * C::P_BYTES, 16, 1024);
+#pragma unroll 1
+            for (int ks = 0; ks < C::KS1; ++ks)
+              umma_f16(tmem_base + t * 256, dp + (uint64_t)(((ks >> 2) * TILE_BYTES + (ks & 3) * 32) >> 4),
+                       dv + (uint64_t)(((C::KS0 + ks) * 2048) >> 4), idesc_o, 1u);
+            umma_commit(bar_o + t);
+            if (t == nt - 1) umma_commit(bar_kvfree + st);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp < 4 || two_tiles) {
+    // ===================== worker warpgroup t: query tile t of every pair =====================
+    const int t = warp >> 2, q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t tS = tmem_base + ((uint32_t)(q * 32) << 16) + t * 256;
+    const float sl2 = scale * kLog2e;
+    uint8_t* sP = smem + C::OFF_P + t * C::P_BYTES;
+    for (int it = 0; it < n_mine; ++it) {
+      const uint32_t ph = it & 1;
+      const int grp = blockIdx.x + it * gridDim.x;
+      const int head = grp % h, b0 = (grp / h) * G;
+      const int n_img = min(G, B - b0);
+      const int rows_valid = n_img * N;
+      const int m = t * BLOCK_Q + r;
+      const int img = min(m / N, n_img - 1);
+      const int klo = img * N, khi = klo + N;
+      uint32_t srow[C::KS0 * 8];
+      uint32_t buf[2][16];
+      auto pack_masked = [&](uint32_t a, uint32_t b, int k, bool inside) -> uint32_t {
+        uint32_t pk = pack_bf16x2(__uint_as_float(a), __uint_as_float(b));
+        if (!inside) {
+          if (!(k >= klo && k < khi)) pk = (pk & 0xFFFF0000u) | 0x0000FF80u;
+          if (!(k + 1 >= klo && k + 1 < khi)) pk = (pk & 0x0000FFFFu) | 0xFF800000u;
+        }
+        return pk;
+      };
+      mbar_wait(bar_s + t, ph);
+      tc_fence_after();
+      float mx = -INFINITY;
+      tmem_ld_32x16(tS, buf[0]);
+#pragma unroll
+      for (int c = 0; c < NKV16; ++c) {
+        tmem_ld_wait();
+        if (c + 1 < NKV16) tmem_ld_32x16(tS + (c + 1) * 16, buf[(c + 1) & 1]);
+        const bool inside = c * 16 >= klo && c * 16 + 16 <= khi;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t pk = pack_masked(buf[c & 1][2 * i], buf[c & 1][2 * i + 1], c * 16 + 2 * i, inside);
+          if (c < C::KS0) srow[c * 8 + i] = pk;
+          const float2 rr = unpack_bf16x2(pk);
+          mx = fmaxf(mx, fmaxf(rr.x, rr.y));
+        }
+      }
+      const float mb = -mx * sl2;
+      float l = 0.f;
+      if (C::KS1 > 0) tmem_ld_32x16(tS + C::KS0 * 16, buf[0]);
+#pragma unroll
+      for (int c8 = 0; c8 < C::KS0 * 2; ++c8) {
+        uint32_t pw[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 rr = unpack_bf16x2(srow[c8 * 4 + j]);
+          const float p0 = ex2_ftz(fmaf(rr.x, sl2, mb)), p1 = ex2_ftz(fmaf(rr.y, sl2, mb));
+          l += p0 + p1;
+          pw[j] = pack_bf16x2(p0, p1);
+        }
+        *reinterpret_cast<uint4*>(sP + (c8 >> 3) * TILE_BYTES + swz(r, c8 & 7)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p0 + t);
+      if (C::KS1 > 0) {
+#pragma unroll
+        for (int c = 0; c < C::KS1; ++c) {
+          tmem_ld_wait();
+          if (c + 1 < C::KS1) tmem_ld_32x16(tS + (C::KS0 + c + 1) * 16, buf[(c + 1) & 1]);
+          const int kc = (C::KS0 + c) * 16;
+          const bool inside = kc >= klo && kc + 16 <= khi;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float2 rr = unpack_bf16x2(pack_masked(buf[c & 1][2 * i], buf[c & 1][2 * i + 1], kc + 2 * i, inside));
+            const float p0 = ex2_ftz(fmaf(rr.x, sl2, mb)), p1 = ex2_ftz(fmaf(rr.y, sl2, mb));
+            l += p0 + p1;
+            srow[c * 8 + i] = pack_bf16x2(p0, p1);
+          }
+        }
+        mbar_wait(bar_pv0 + t, ph);
+#pragma unroll
+        for (int c8 = 0; c8 < C::KS1 * 2; ++c8)
+          *reinterpret_cast<uint4*>(sP + (c8 >> 3) * TILE_BYTES + swz(r, c8 & 7)) =
+              make_uint4(srow[c8 * 4], srow[c8 * 4 + 1], srow[c8 * 4 + 2], srow[c8 * 4 + 3]);
+        tc_fence_before();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_p1 + t);
+      }
+      if (lse && m < rows_valid) lse[((size_t)(b0 + img) * h + head) * N + (m - klo)] = mx * scale + __logf(l);
+      mbar_wait(bar_o + t, ph);
+      tc_fence_after();
+      const float inv = 1.f / l;
+      uint32_t ov[2][32];
+      tmem_ld_32x32(tS, ov[0]);
+      tmem_ld_32x32(tS + 32, ov[1]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tfree + t);  // the next pair's S may overwrite this TMEM region
+      if (m < rows_valid) {
+        __nv_bfloat16* orow = out + ((size_t)b0 * N + m) * ld_out + head * HD;
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint32_t ow[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              ow[j] = pack_bf16x2(__uint_as_float(ov[c][i * 8 + 2 * j]) * inv, __uint_as_float(ov[c][i * 8 + 2 * j + 1]) * inv);
+            *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ====================================================================================================================
 // backward
 // ====================================================================================================================
 template <int NKV16>
@@ -930,6 +1231,33 @@ static int launch_fwd3(const void* qkv, long long ld_tok, int B, int N, int G, i
 }
 
 template <int NKV16>
+static int launch_fwd4(const void* qkv, long long ld_tok, int B, int N, int G, int h, float scale, void* out, long long ld_out,
+                       float* lse, cudaStream_t s) {
+  using C = Fwd4Cfg<NKV16>;
+  CUtensorMap tmQ, tmKV;
+  int rc = tmap_rows(&tmQ, qkv, (long long)B * N, 3LL * h * HD, ld_tok, BLOCK_Q);
+  if (rc) return rc;
+  rc = tmap_rows(&tmKV, qkv, (long long)B * N, 3LL * h * HD, ld_tok, C::NKV);
+  if (rc) return rc;
+  static bool attr = false;
+  static int num_sms = 0;
+  if (!attr) {
+    if (cudaFuncSetAttribute(attn_fwd_tc4_kernel<NKV16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
+      return B200_ERR_CUDA;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    attr = true;
+  }
+  const int n_groups = ((B + G - 1) / G) * h;
+  const int grid = n_groups < num_sms ? n_groups : num_sms;
+  launch_kernel(attn_fwd_tc4_kernel<NKV16>, grid, C::THREADS, C::SMEM_BYTES, s, tmQ, tmKV, B, N, G, h, n_groups, scale,
+                (__nv_bfloat16*)out, ld_out, lse);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+template <int NKV16>
 static int launch_bwd(const void* qkv, long long ld_tok, const void* out, const void* dout, long long ld_out, const float* lse, int B,
                       int N, int G, int h, float scale, void* dqkv, long long ld_dtok, float* colsum, cudaStream_t s) {
   using C = BwdCfg<NKV16>;
@@ -967,7 +1295,12 @@ extern "C" int b200_attention_fwd_tc(const void* qkv, long long ld_tok, int B, i
   static int sched = -1;  // B200_ATTN_FWD_SCHEDULE=1: both query tiles in one CTA; default 3: one tile per CTA, two CTAs per SM
   if (sched < 0) {
     const char* e = std::getenv("B200_ATTN_FWD_SCHEDULE");
-    sched = (e && e[0] == '1') ? 1 : 3;
+    sched = (e && e[0] >= '1' && e[0] <= '4') ? e[0] - '0' : 3;
+  }
+  if (sched == 4) {
+    if (N <= 128) return launch_fwd4<8>(qkv, ld_tok, B, N, 128 / N, h, scale, out, ld_out, lse, s);
+    if (N <= 208) return launch_fwd4<13>(qkv, ld_tok, B, N, 1, h, scale, out, ld_out, lse, s);
+    return launch_fwd<16>(qkv, ld_tok, B, N, 1, h, scale, out, ld_out, lse, s);  // NKV = 256 does not fit two K/V stages
   }
   if (sched == 3) {
     if (N <= 128) return launch_fwd3<8>(qkv, ld_tok, B, N, 128 / N, h, scale, out, ld_out, lse, s);
