@@ -18,6 +18,7 @@ torch.autograd bridge for trainers that insist on calling `loss.backward()` (INT
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Literal, Optional, Tuple
 
@@ -34,6 +35,13 @@ from .scheduler import cosine_schedule, cosine_warmup_factor, linear_warmup_sche
 from ..._torch_helpers import update_momentum
 from ... import _lib
 from .utils import MaskingGenerator, create_collated_masks, param_group_settings
+
+# Sinkhorn-Knopp on several ranks: capture the per-iteration [K] all-reduces into the step's CUDA graph (opt-in)
+GRAPH_NCCL = os.environ.get("B200_GRAPH_NCCL", "0") == "1"
+
+
+def _world_size() -> int:
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
 
 @dataclass
@@ -690,7 +698,7 @@ class DINOv2(nn.Module):
                 "pad": torch.zeros(cap_max, device=dev, dtype=torch.float32),
                 "m_valid": torch.zeros(1, device=dev, dtype=torch.int32),
                 "t_scale": torch.zeros(1, device=dev, dtype=torch.float32),
-                "graphs": {}, "pool": None,
+                "graphs": {}, "pool": None, "cap_max": cap_max,
             }
         teacher_temp = linear_warmup_schedule(self.trainer.global_step, a.teacher_temp_warmup_steps,
                                               a.teacher_temp_start, a.teacher_temp_end)
@@ -710,6 +718,10 @@ class DINOv2(nn.Module):
                 masks = self._masks(2 * B, hh, ww)
             M = int(masks["mask_indices_list"].shape[0])
             cap = max(512, -(-M // 512) * 512)
+            if a.center_method != "softmax" and _world_size() > 1:
+                # the captured Sinkhorn all-reduces must be replayed by every rank every step: one shape for all ranks and
+                # steps (the masked-token count differs per rank), i.e. the guaranteed upper bound
+                cap = max(cap, st["cap_max"])
             st["masks_u8"].copy_(masks["collated_masks"].to(torch.uint8), non_blocking=True)
             idx_h = torch.zeros(cap, dtype=torch.int64); idx_h[:M] = masks["mask_indices_list"]
             mw_h = torch.zeros(cap, dtype=torch.float32); mw_h[:M] = masks["masks_weight"]
@@ -932,13 +944,14 @@ class DINOv2(nn.Module):
         return result.loss.detach().requires_grad_(True)
 
     def _graph_ok(self) -> bool:
-        """CUDA-graph replay of the step: always for softmax centering; for Sinkhorn-Knopp only on a single rank (its
-        per-iteration all-reduce sits in the middle of the captured schedule)."""
+        """CUDA-graph replay of the step: always for softmax centering and for Sinkhorn-Knopp on a single rank.  With
+        Sinkhorn-Knopp on several ranks the per-iteration [K] all-reduces sit in the middle of the captured schedule: they
+        are captured into the graph (NCCL kernels are capturable) when B200_GRAPH_NCCL=1, otherwise the step runs eagerly."""
         if not self.use_cuda_graph:
             return False
-        if self.method_args.center_method == "softmax":
+        if self.method_args.center_method == "softmax" or _world_size() == 1:
             return True
-        return not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
+        return GRAPH_NCCL
 
     def train_step(self, batch: Dict[str, Any]) -> TrainingStepResult:
         """One full optimisation step: what Lightning's fit loop does around training_step."""

@@ -117,6 +117,31 @@ dist.all_reduce(flags, op=dist.ReduceOp.MIN)
 result["replicas_bit_identical_after_5_steps"] = bool(flags.item())
 result["per_tensor_rank%d" % rank] = same
 assert flags.item() == 1, same
+# ---- Sinkhorn-Knopp with the [K] all-reduces captured into the step graph (B200_GRAPH_NCCL=1): graph replay == eager
+from lightly_train_b200._methods.dinov2 import dinov2 as _dm  # noqa: E402
+if _dm.GRAPH_NCCL:
+    losses = {}
+    for graphed in (False, True):
+        m, cfg, st = build("sinkhorn_knopp", koleo_w=0.1, drop_path=0.0)
+        m.use_cuda_graph = graphed
+        assert m._graph_ok() == graphed
+        random.seed(11 + rank)
+        torch.manual_seed(5 + rank)
+        ls = []
+        for i in range(4):
+            ls.append(float(m.train_step({"views": vd}).loss))
+        torch.cuda.synchronize()
+        losses[graphed] = ls
+        if graphed:
+            ref = m.s_arena.fp32.clone()
+            dist.broadcast(ref, 0)
+            ok = torch.tensor([int(torch.equal(ref, m.s_arena.fp32))], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            result["sinkhorn_graph_nccl_replicas_identical"] = bool(ok.item())
+            assert ok.item() == 1
+    result["sinkhorn_graph_nccl_losses_rank%d" % rank] = losses
+    for a, b in zip(losses[False], losses[True]):
+        assert abs(a - b) < 2e-3 * max(1.0, abs(a)), losses
 if rank == 0:
     print("DDP_CHECK", json.dumps(result), flush=True)
     if out_path:
