@@ -421,6 +421,8 @@ def run_distill(args) -> None:
                              "traffic": None, "gemm_launches": len(prof), "gemm_ms_per_step": gms,
                              "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained"},
                 "cpu_baseline": None}
+        if diag:
+            line["diagnostic"] = "gradient all-reduce DISABLED (B200_BENCH_DIAG_NO_ALLREDUCE=1): not a training step, not a bench value"
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -477,6 +479,11 @@ def main() -> None:
     if cfg["ckpt"]:
         method.student_embedding_model.wrapped_model.set_activation_checkpointing(True)
     method.use_cuda_graph = not args.eager
+    diag = os.environ.get("B200_BENCH_DIAG_NO_ALLREDUCE", "0") == "1"
+    if diag:  # DIAGNOSTIC ONLY (line is flagged): the step without its gradient all-reduce = the ceiling of overlap tuning
+        method._allreduce_head_grads_async = lambda: None
+        method._allreduce_upper_backbone_async = lambda split_at: None
+        method._finish_grad_allreduce = lambda: None
     if world > 1:  # identical initial weights on every rank
         dist.broadcast(method.s_arena.fp32, 0)
         dist.broadcast(method.t_arena.fp32, 0)
@@ -676,6 +683,8 @@ def main() -> None:
             "host_ms_per_step": round(host_ms, 3), "loss": loss_val, "parity": parity,
             "roofline": roofline, "rooflines_hbm": rooflines_hbm, "cpu_baseline": cpu_baseline, "gpu_torch_baseline": gpu_torch_baseline,
         }
+        if diag:
+            line["diagnostic"] = "gradient all-reduce DISABLED (B200_BENCH_DIAG_NO_ALLREDUCE=1): not a training step, not a bench value"
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

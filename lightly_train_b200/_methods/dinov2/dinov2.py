@@ -40,6 +40,10 @@ from .utils import MaskingGenerator, create_collated_masks, param_group_settings
 GRAPH_NCCL = os.environ.get("B200_GRAPH_NCCL", "0") == "1"
 
 
+# where the backbone backward is cut for the middle all-reduce bucket: blocks >= FRAC * depth go out after graph 2
+DDP_SPLIT_FRAC = float(os.environ.get("B200_DDP_SPLIT_FRAC", "0.5"))
+
+
 def _world_size() -> int:
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
@@ -368,7 +372,8 @@ class DINOv2(nn.Module):
         if self.force_backbone_split is not None:
             return self.force_backbone_split
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        return nb // 2 if (nb >= 4 and multi) else 0  # a single rank has nothing to overlap: no cut, one graph fewer
+        # a single rank has nothing to overlap: no cut, one graph fewer
+        return max(1, int(nb * DDP_SPLIT_FRAC)) if (nb >= 4 and multi) else 0
 
     def _allreduce_upper_backbone_async(self, split_at: int) -> None:
         """Data-parallel runs: all-reduce the gradients of blocks >= split_at and of `norm` (contiguous in the arena, final
