@@ -64,7 +64,12 @@ def test_lightning_shaped_loop_equals_train_step():
     la = _lightning_like_fit(a, [batch], 3)
     lb = [float(b.train_step(batch).loss) for _ in range(3)]
     torch.cuda.synchronize()
-    assert la == pytest.approx(lb, rel=1e-5)
+    # steps 0 and 1 see identical weights (the warm-up lr of step 0 is 0); step 2 sees the first real Adam update, which is
+    # lr * g/|g|: run-to-run reordering of the fp32 split-K atomics flips it for noise-level gradients (observed 7e-4 on the
+    # loss between two identical runs), so only steps 0-1 are compared tightly.  The update rule itself is pinned by
+    # test_optimizer_ema_step_matches_oracle and the hook order by test_ema_hook_order_and_unfused_update_momentum.
+    assert la[:2] == pytest.approx(lb[:2], rel=1e-5)
+    assert la[2] == pytest.approx(lb[2], rel=3e-3)
     # fp32 split-K atomics reorder the wgrad sums run to run and Adam's first steps are lr * g/|g|: elements whose gradient
     # sits at rounding-noise level can move by up to ~lr (here 2e-3) differently in two runs; everything else agrees tightly
     d = (a.s_arena.fp32 - b.s_arena.fp32).abs()
