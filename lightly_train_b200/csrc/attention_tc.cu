@@ -820,9 +820,230 @@ attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 }
 
 // ====================================================================================================================
+// forward, schedule 5: schedule 1's CTA (both query tiles of a pair, one CTA per SM) with SIXTEEN worker warps
+// ====================================================================================================================
+// ncu on schedules 1 / 3 / 4 (profiles/r02_ncu_attn_tc.txt): 8 worker warps per SM, issue slots 27 % busy, tensor pipe 8 % --
+// the softmax of a pair is a latency chain of ~3.4 k dependent instructions per warp and there are only two warps per
+// scheduler to hide it; making the CTA persistent (schedule 4) or splitting it (schedule 3) leaves the per-SM warp count
+// unchanged, and the time too (62 - 72 us).  Here every query row is shared by TWO threads (warps w and w + 8 address the
+// same TMEM lane quarter): each owns half of the key columns (two passes over them with software-pipelined TMEM
+// loads; 17 warps leave 96 registers per thread, too few to keep the half row), and the pair exchanges its half-row maximum and half-row sum through shared memory + a 64-thread named barrier.
+// P V is issued per half as soon as that half's four warps have written their P columns; each thread drains 32 of the 64
+// O columns.
+template <int NKV16>
+struct Fwd5Cfg {
+  static constexpr int NKV = NKV16 * 16;
+  static constexpr int KV_BYTES = NKV * 128;
+  static constexpr int P_SLABS = (NKV + 63) / 64;
+  static constexpr int OFF_K = 2 * TILE_BYTES;
+  static constexpr int OFF_V = OFF_K + KV_BYTES;
+  static constexpr int OFF_P = (OFF_V + KV_BYTES + 1023) / 1024 * 1024;
+  static constexpr int P_BYTES = P_SLABS * TILE_BYTES;
+  static constexpr int OFF_X = OFF_P + 2 * P_BYTES;          // floats: half-row max [2][256], half-row sum [2][256]
+  static constexpr int OFF_BAR = OFF_X + 4 * 256 * 4;
+  static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
+  static constexpr int THREADS = 17 * 32;
+  static constexpr int HA = (NKV16 + 1) / 2;                 // 16-key chunks of the first / second column half
+  static constexpr int HB = NKV16 - HA;
+  static_assert(NKV <= 256 && SMEM_BYTES <= 232448, "shared memory");
+};
+
+template <int NKV16>
+__global__ void __launch_bounds__(Fwd5Cfg<NKV16>::THREADS, 1)
+attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, int B, int N, int G, int h,
+                    float scale, __nv_bfloat16* __restrict__ out, long long ld_out, float* __restrict__ lse) {
+  pdl_launch_dependents();
+  using C = Fwd5Cfg<NKV16>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* bar_load = bars + 0;
+  uint64_t* bar_s = bars + 1;     // [2] S_t in TMEM
+  uint64_t* bar_p = bars + 3;     // [2 tiles][2 halves] P columns of that half in smem (4 warps each)
+  uint64_t* bar_o = bars + 7;     // [2] O_t in TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  float* xmax = reinterpret_cast<float*>(smem + C::OFF_X);   // [half][256]
+  float* xsum = xmax + 512;                                  // [half][256]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bg = blockIdx.x / h, head = blockIdx.x % h;
+  const int b0 = bg * G, n_img = min(G, B - b0);
+  const int rows_valid = n_img * N;
+  const int n_tiles = (rows_valid + BLOCK_Q - 1) / BLOCK_Q;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_load, 1);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(bar_s + t, 1);
+      mbar_init(bar_p + 2 * t, 4);
+      mbar_init(bar_p + 2 * t + 1, 4);
+      mbar_init(bar_o + t, 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 16) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmKV);
+    }
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 16) {
+    // ===================== control warp: TMA + MMA issue =====================
+    const int row0 = b0 * N;
+    if (lane == 0) {
+      mbar_expect_tx(bar_load, 2 * TILE_BYTES + 2 * C::KV_BYTES);
+      tma_load_2d(smem, &tmQ, bar_load, head * HD, row0);
+      tma_load_2d(smem + TILE_BYTES, &tmQ, bar_load, head * HD, row0 + BLOCK_Q);
+      tma_load_2d(smem + C::OFF_K, &tmKV, bar_load, (h + head) * HD, row0);
+      tma_load_2d(smem + C::OFF_V, &tmKV, bar_load, (2 * h + head) * HD, row0);
+    }
+    __syncwarp();
+    mbar_wait(bar_load, 0);
+    const uint32_t s0 = smem_u32(smem);
+    const uint64_t dk = smem_desc(s0 + C::OFF_K, 16, 1024);
+    const uint64_t dv = smem_desc(s0 + C::OFF_V, 64 * 128, 1024);
+    const uint32_t idesc_s = instr_desc(BLOCK_Q, C::NKV, 0, 0);
+    const uint32_t idesc_o = instr_desc(BLOCK_Q, HD, 0, 1);
+    if (elect_one_sync()) {
+      for (int t = 0; t < n_tiles; ++t) {
+        const uint64_t dq = smem_desc(s0 + t * TILE_BYTES, 16, 1024);
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks)
+          umma_f16(tmem_base + t * 256, dq + (uint64_t)((ks * 32) >> 4), dk + (uint64_t)((ks * 32) >> 4), idesc_s, ks > 0 ? 1u : 0u);
+        umma_commit(bar_s + t);
+      }
+    }
+    __syncwarp();
+    for (int t = 0; t < n_tiles; ++t) {
+      const uint64_t dp = smem_desc(s0 + C::OFF_P + t * C::P_BYTES, 16, 1024);
+      for (int half = 0; half < (C::HB > 0 ? 2 : 1); ++half) {
+        mbar_wait(bar_p + 2 * t + half, 0);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const int k0 = half ? C::HA : 0, k1 = half ? NKV16 : C::HA;
+#pragma unroll 1
+          for (int ks = k0; ks < k1; ++ks)
+            umma_f16(tmem_base + t * 256, dp + (uint64_t)(((ks >> 2) * TILE_BYTES + (ks & 3) * 32) >> 4),
+                     dv + (uint64_t)((ks * 16 * 128) >> 4), idesc_o, ks > 0 ? 1u : 0u);
+          if (half == (C::HB > 0 ? 1 : 0)) umma_commit(bar_o + t);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (((warp & 7) >> 2) < n_tiles) {
+    // ===================== worker warps: tile t, lane quarter q, column half =====================
+    const int half = warp >> 3, t = (warp & 7) >> 2, q = warp & 3;
+    const int r = q * 32 + lane;
+    const int m = t * BLOCK_Q + r;
+    const int img = min(m / N, n_img - 1);
+    const int klo = img * N, khi = klo + N;
+    const int c0 = half ? C::HA : 0, nc = half ? C::HB : C::HA;
+    const uint32_t tS = tmem_base + ((uint32_t)(q * 32) << 16) + t * 256;
+    const float sl2 = scale * kLog2e;
+    uint8_t* sP = smem + C::OFF_P + t * C::P_BYTES;
+    const int pair_bar = 1 + (warp & 7);                     // named barrier shared by warps w and w + 8
+    uint32_t buf[16];
+    // packed bf16 scores of one 16-key chunk, keys outside the row's image -> -inf; the next chunk's TMEM load is issued as
+    // soon as `buf` has been packed so that it is in flight during the arithmetic on this chunk
+    auto take_chunk = [&](int c, uint32_t (&pk)[8]) {
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(__uint_as_float(buf[2 * i]), __uint_as_float(buf[2 * i + 1]));
+      if (c + 1 < nc) tmem_ld_32x16(tS + (c0 + c + 1) * 16, buf);
+      const int kc = (c0 + c) * 16;
+      if (!(kc >= klo && kc + 16 <= khi)) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int k = kc + 2 * i;
+          if (!(k >= klo && k < khi)) pk[i] = (pk[i] & 0xFFFF0000u) | 0x0000FF80u;          // -inf
+          if (!(k + 1 >= klo && k + 1 < khi)) pk[i] = (pk[i] & 0x0000FFFFu) | 0xFF800000u;
+        }
+      }
+    };
+    mbar_wait(bar_s + t, 0);
+    tc_fence_after();
+    float mx = -INFINITY;
+    if (nc > 0) tmem_ld_32x16(tS + c0 * 16, buf);
+#pragma unroll 1
+    for (int c = 0; c < nc; ++c) {
+      uint32_t pk[8];
+      take_chunk(c, pk);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 rr = unpack_bf16x2(pk[i]);
+        mx = fmaxf(mx, fmaxf(rr.x, rr.y));
+      }
+    }
+    if (nc > 0) tmem_ld_32x16(tS + c0 * 16, buf);            // first chunk of pass 2: in flight across the exchange
+    xmax[half * 256 + m] = mx;
+    named_bar_sync(pair_bar, 64);
+    mx = fmaxf(mx, xmax[(half ^ 1) * 256 + m]);
+    const float mb = -mx * sl2;
+    float l = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < nc; ++c) {
+      uint32_t pk[8], pw[8];
+      take_chunk(c, pk);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 rr = unpack_bf16x2(pk[i]);
+        const float p0 = ex2_ftz(fmaf(rr.x, sl2, mb)), p1 = ex2_ftz(fmaf(rr.y, sl2, mb));
+        l += p0 + p1;
+        pw[i] = pack_bf16x2(p0, p1);
+      }
+      const int cc = c0 + c;
+      uint8_t* slab = sP + (cc >> 2) * TILE_BYTES;
+      const int ch = (cc & 3) * 2;
+      *reinterpret_cast<uint4*>(slab + swz(r, ch)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+      *reinterpret_cast<uint4*>(slab + swz(r, ch + 1)) = make_uint4(pw[4], pw[5], pw[6], pw[7]);
+    }
+    xsum[half * 256 + m] = l;
+    fence_proxy_async();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_p + 2 * t + half);
+    named_bar_sync(pair_bar, 64);
+    l += xsum[(half ^ 1) * 256 + m];
+    if (half == 0 && lse && m < rows_valid) lse[((size_t)(b0 + img) * h + head) * N + (m - klo)] = mx * scale + __logf(l);
+    mbar_wait(bar_o + t, 0);
+    tc_fence_after();
+    const float inv = 1.f / l;
+    uint32_t ov[32];
+    tmem_ld_32x32(tS + half * 32, ov);
+    tmem_ld_wait();
+    if (m < rows_valid) {
+      __nv_bfloat16* orow = out + ((size_t)b0 * N + m) * ld_out + head * HD + half * 32;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t ow[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          ow[j] = pack_bf16x2(__uint_as_float(ov[i * 8 + 2 * j]) * inv, __uint_as_float(ov[i * 8 + 2 * j + 1]) * inv);
+        *reinterpret_cast<uint4*>(orow + i * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ====================================================================================================================
 // backward
 // ====================================================================================================================
-template <int NKV16>
+template <int NKV16, int NG = 2>
 struct BwdCfg {
   static constexpr int NKV = NKV16 * 16;                   // padded key count, <= 208
   static constexpr int KV_BYTES = NKV * 128;
@@ -834,10 +1055,11 @@ struct BwdCfg {
   static constexpr int OFF_F = OFF_P + 4 * TILE_BYTES;     // floats: L[256], D[256], colsum[192]
   static constexpr int OFF_BAR = OFF_F + (256 + 256 + 192) * 4;
   static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
-  static constexpr int THREADS = 9 * 32;
+  static constexpr int WORKERS = 4 * NG;                   // worker warps: NG column groups x 4 lane quarters
+  static constexpr int THREADS = (WORKERS + 1) * 32;       // + the control warp (the last one)
   // TMEM columns: S / dP / dQ share [0, NKV); dK [256, 384): M tile 0 | 1; dV [384, 512)
   static constexpr int TM_SDP = 0, TM_DK = 256, TM_DV = 384;
-  static constexpr int HALF16 = (NKV16 + 1) / 2;           // 16-key chunks owned by worker group 0
+  __host__ __device__ static constexpr int qb(int g) { return (NKV16 * g + NG - 1) / NG; }   // column group g owns the 16-key chunks [qb(g), qb(g+1))
   static_assert(NKV <= 256, "S / dP tile");
   static_assert(SMEM_BYTES <= 232448, "shared memory");
 };
@@ -860,31 +1082,33 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 
 // Drain one [128 x 64] fp32 accumulator tile (one row per thread, 4 warps): out = bf16(acc * mul) -> global row (when
 // `valid`), and this warp's column sums of the bf16-rounded values -> smem atomics on cs[0..64).
-__device__ __forceinline__ void drain_tile(uint32_t taddr, float mul, bool valid, __nv_bfloat16* grow, float* cs, int lane) {
+// 32 columns [c*32, c*32+32) of the tile
+__device__ __forceinline__ void drain_cols32(uint32_t taddr, int c, float mul, bool valid, __nv_bfloat16* grow, float* cs, int lane) {
+  uint32_t v[32];
+  tmem_ld_32x32(taddr + c * 32, v);
+  tmem_ld_wait();
+  float f[32];
+  uint32_t w[16];
 #pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    uint32_t v[32];
-    tmem_ld_32x32(taddr + c * 32, v);
-    tmem_ld_wait();
-    float f[32];
-    uint32_t w[16];
-#pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      w[i >> 1] = pack_bf16x2(__uint_as_float(v[i]) * mul, __uint_as_float(v[i + 1]) * mul);
-      const float2 rr = unpack_bf16x2(w[i >> 1]);
-      f[i] = valid ? rr.x : 0.f;
-      f[i + 1] = valid ? rr.y : 0.f;
-    }
-    if (valid) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        *reinterpret_cast<uint4*>(grow + c * 32 + i * 8) = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
-    }
-    if (cs) {
-      const float s = warp_colsum32(f, lane);
-      atomicAdd(cs + c * 32 + lane, s);
-    }
+  for (int i = 0; i < 32; i += 2) {
+    w[i >> 1] = pack_bf16x2(__uint_as_float(v[i]) * mul, __uint_as_float(v[i + 1]) * mul);
+    const float2 rr = unpack_bf16x2(w[i >> 1]);
+    f[i] = valid ? rr.x : 0.f;
+    f[i + 1] = valid ? rr.y : 0.f;
   }
+  if (valid) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<uint4*>(grow + c * 32 + i * 8) = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+  }
+  if (cs) {
+    const float s = warp_colsum32(f, lane);
+    atomicAdd(cs + c * 32 + lane, s);
+  }
+}
+__device__ __forceinline__ void drain_tile(uint32_t taddr, float mul, bool valid, __nv_bfloat16* grow, float* cs, int lane) {
+  drain_cols32(taddr, 0, mul, valid, grow, cs, lane);
+  drain_cols32(taddr, 1, mul, valid, grow, cs, lane);
 }
 
 // Backward worker passes over the 16-key chunks [C0, C1) of one row, TMEM loads issued one chunk ahead of their use.
@@ -940,14 +1164,15 @@ __device__ __forceinline__ void bwd_ds_pass(uint32_t tcol, uint8_t* sP, int r, f
   }
 }
 
-template <int NKV16>
-__global__ void __launch_bounds__(BwdCfg<NKV16>::THREADS, 1)
+template <int NKV16, int NG>
+__global__ void __launch_bounds__(BwdCfg<NKV16, NG>::THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                    const __grid_constant__ CUtensorMap tmDO, const __nv_bfloat16* __restrict__ outp,
                    const __nv_bfloat16* __restrict__ dout, long long ld_out, const float* __restrict__ lse, int B, int N, int G,
                    int h, float scale, __nv_bfloat16* __restrict__ dqkv, long long ld_dtok, float* __restrict__ colsum) {
   pdl_launch_dependents();  // the wait follows the barrier / TMEM set-up below
-  using C = BwdCfg<NKV16>;
+  using C = BwdCfg<NKV16, NG>;
+  constexpr int CTRL = C::WORKERS;  // control warp index
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* sL = reinterpret_cast<float*>(smem + C::OFF_F);  // base-2 log-sum-exp per query row (256)
@@ -956,11 +1181,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
   uint64_t* bar_load = bars + 0;
   uint64_t* bar_s = bars + 1;     // S of the current tile in TMEM
-  uint64_t* bar_p = bars + 2;     // P in smem (8 worker warps)
+  uint64_t* bar_p = bars + 2;     // P in smem (all worker warps)
   uint64_t* bar_dp = bars + 3;    // dP in TMEM (and dV MMAs of this tile retired: P may be overwritten)
-  uint64_t* bar_ds = bars + 4;    // dS in smem (8 worker warps)
+  uint64_t* bar_ds = bars + 4;    // dS in smem (all worker warps)
   uint64_t* bar_dq = bars + 5;    // dQ in TMEM (and dK MMAs retired)
-  uint64_t* bar_free = bars + 6;  // dQ drained (4 worker warps): the shared TMEM columns may be overwritten
+  uint64_t* bar_free = bars + 6;  // dQ drained (4 warps, or 8 with NG = 4): the shared TMEM columns may be overwritten
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -972,14 +1197,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (threadIdx.x == 0) {
     mbar_init(bar_load, 1);
     mbar_init(bar_s, 1);
-    mbar_init(bar_p, 8);
+    mbar_init(bar_p, C::WORKERS);
     mbar_init(bar_dp, 1);
-    mbar_init(bar_ds, 8);
+    mbar_init(bar_ds, C::WORKERS);
     mbar_init(bar_dq, 1);
-    mbar_init(bar_free, 4);
+    mbar_init(bar_free, NG == 2 ? 4 : 8);
     fence_barrier_init();
   }
-  if (warp == 8) {
+  if (warp == CTRL) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmKV);
@@ -995,7 +1220,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
   const size_t row0 = (size_t)b0 * N;
 
-  if (warp == 8) {
+  if (warp == CTRL) {
     // ===================== control warp =====================
     if (lane == 0) {
       mbar_expect_tx(bar_load, 4 * TILE_BYTES + 2 * C::KV_BYTES);
@@ -1071,13 +1296,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else {
     // ===================== worker warps =====================
-    const int g = warp >> 2, q = warp & 3;   // g: key-column half (and, for the drains, which tile this group owns)
+    const int g = warp >> 2, q = warp & 3;   // g: key-column group (and which accumulator / columns this group drains)
     const int r = q * 32 + lane;             // row inside a 128-row tile == TMEM lane
     const uint32_t tL = tmem_base + ((uint32_t)(q * 32) << 16);
     const float sl2 = scale * kLog2e;
     uint8_t* sP = smem + C::OFF_P;
     // per-row constants: base-2 LSE and D_i = sum_d dO O straight from global (one 128-byte row per thread and tensor)
-    {
+    if (g < 2) {
       const int m = g * BLOCK_Q + r;  // this thread prepares row m of the group (rows 0..255)
       float L = 0.f, D = 0.f;
       if (m < rows_valid) {
@@ -1101,7 +1326,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       sD[m] = D;
       if (threadIdx.x < 192) sC[threadIdx.x] = 0.f;
     }
-    named_bar_sync(1, 256);
+    named_bar_sync(1, C::WORKERS * 32);
     for (int t = 0; t < n_tiles; ++t) {
       const uint32_t ph = t & 1;
       const int m = t * BLOCK_Q + r;
@@ -1111,8 +1336,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // ---- P = 2^(s*sl2 - L) for my key columns (0 for padded rows / keys) -> smem
       mbar_wait(bar_s, ph);
       tc_fence_after();
-      if (g == 0) bwd_p_pass<0, C::HALF16>(tL + C::TM_SDP, sP, r, row_ok, klo, khi, sl2, L);
-      else bwd_p_pass<C::HALF16, NKV16>(tL + C::TM_SDP, sP, r, row_ok, klo, khi, sl2, L);
+      if (g == 0) bwd_p_pass<C::qb(0), C::qb(1)>(tL + C::TM_SDP, sP, r, row_ok, klo, khi, sl2, L);
+      else if (g == 1) bwd_p_pass<C::qb(1), C::qb(2)>(tL + C::TM_SDP, sP, r, row_ok, klo, khi, sl2, L);
+      else if (NG == 4 && g == 2) bwd_p_pass<C::qb(NG == 4 ? 2 : 0), C::qb(NG == 4 ? 3 : 1)>(tL + C::TM_SDP, sP, r, row_ok, klo, khi, sl2, L);
+      else if (NG == 4) bwd_p_pass<C::qb(NG == 4 ? 3 : 0), C::qb(NG == 4 ? 4 : 1)>(tL + C::TM_SDP, sP, r, row_ok, klo, khi, sl2, L);
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
@@ -1120,33 +1347,43 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // ---- dS = P (dP - D), bf16, in place of P
       mbar_wait(bar_dp, ph);
       tc_fence_after();
-      if (g == 0) bwd_ds_pass<0, C::HALF16>(tL + C::TM_SDP, sP, r, D);
-      else bwd_ds_pass<C::HALF16, NKV16>(tL + C::TM_SDP, sP, r, D);
+      if (g == 0) bwd_ds_pass<C::qb(0), C::qb(1)>(tL + C::TM_SDP, sP, r, D);
+      else if (g == 1) bwd_ds_pass<C::qb(1), C::qb(2)>(tL + C::TM_SDP, sP, r, D);
+      else if (NG == 4 && g == 2) bwd_ds_pass<C::qb(NG == 4 ? 2 : 0), C::qb(NG == 4 ? 3 : 1)>(tL + C::TM_SDP, sP, r, D);
+      else if (NG == 4) bwd_ds_pass<C::qb(NG == 4 ? 3 : 0), C::qb(NG == 4 ? 4 : 1)>(tL + C::TM_SDP, sP, r, D);
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_ds);
-      // ---- dQ_t: group 0 drains it (group 1 runs ahead to the next tile's waits)
-      if (g == 0) {
+      // ---- dQ_t: group 0 drains it (NG = 4: groups 0 / 1 take 32 columns each); the others run ahead to the next tile's waits
+      if (g == 0 || (NG == 4 && g == 1)) {
         mbar_wait(bar_dq, ph);
         tc_fence_after();
-        drain_tile(tL + C::TM_SDP, scale, row_ok, dqkv + (row0 + m) * ld_dtok + head * HD, colsum ? sC : nullptr, lane);
+        __nv_bfloat16* grow = dqkv + (row0 + m) * ld_dtok + head * HD;
+        if (NG == 2) drain_tile(tL + C::TM_SDP, scale, row_ok, grow, colsum ? sC : nullptr, lane);
+        else drain_cols32(tL + C::TM_SDP, g, scale, row_ok, grow, colsum ? sC : nullptr, lane);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_free);
       }
     }
-    // ---- dK / dV: group g drains M tile g (keys g*128 + r); the last bar_dq completion covers every MMA issued
+    // ---- dK / dV: keys on the lanes, two 128-key M tiles each; the last bar_dq completion covers every MMA issued
     mbar_wait(bar_dq, (n_tiles - 1) & 1);
     tc_fence_after();
-    {
+    if (NG == 2) {  // group g drains M tile g of both
       const int key = g * BLOCK_Q + r;
       const bool ok = key < rows_valid;
       __nv_bfloat16* base = dqkv + (row0 + key) * ld_dtok + head * HD;
       drain_tile(tL + C::TM_DK + g * 64, scale, ok, base + (size_t)h * HD, colsum ? sC + 64 : nullptr, lane);
       drain_tile(tL + C::TM_DV + g * 64, 1.f, ok, base + (size_t)2 * h * HD, colsum ? sC + 128 : nullptr, lane);
+    } else {        // groups 0 / 1: dK tiles 0 / 1; groups 2 / 3: dV tiles 0 / 1
+      const int mt = g & 1, is_v = g >> 1;
+      const int key = mt * BLOCK_Q + r;
+      const bool ok = key < rows_valid;
+      __nv_bfloat16* base = dqkv + (row0 + key) * ld_dtok + head * HD + (size_t)(1 + is_v) * h * HD;
+      drain_tile(tL + (is_v ? C::TM_DV : C::TM_DK) + mt * 64, is_v ? 1.f : scale, ok, base, colsum ? sC + 64 + 64 * is_v : nullptr, lane);
     }
-    named_bar_sync(1, 256);
+    named_bar_sync(1, C::WORKERS * 32);
     if (colsum && threadIdx.x < 192) {
       const int part = threadIdx.x >> 6, d = threadIdx.x & 63;
       atomicAdd(colsum + (size_t)part * h * HD + head * HD + d, sC[threadIdx.x]);
@@ -1155,7 +1392,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == CTRL) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -1258,9 +1495,30 @@ static int launch_fwd4(const void* qkv, long long ld_tok, int B, int N, int G, i
 }
 
 template <int NKV16>
+static int launch_fwd5(const void* qkv, long long ld_tok, int B, int N, int G, int h, float scale, void* out, long long ld_out,
+                       float* lse, cudaStream_t s) {
+  using C = Fwd5Cfg<NKV16>;
+  CUtensorMap tmQ, tmKV;
+  int rc = tmap_rows(&tmQ, qkv, (long long)B * N, 3LL * h * HD, ld_tok, BLOCK_Q);
+  if (rc) return rc;
+  rc = tmap_rows(&tmKV, qkv, (long long)B * N, 3LL * h * HD, ld_tok, C::NKV);
+  if (rc) return rc;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(attn_fwd_tc5_kernel<NKV16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
+      return B200_ERR_CUDA;
+    attr = true;
+  }
+  launch_kernel(attn_fwd_tc5_kernel<NKV16>, ((B + G - 1) / G) * h, C::THREADS, C::SMEM_BYTES, s, tmQ, tmKV, B, N, G, h, scale,
+                (__nv_bfloat16*)out, ld_out, lse);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+template <int NKV16, int NG>
 static int launch_bwd(const void* qkv, long long ld_tok, const void* out, const void* dout, long long ld_out, const float* lse, int B,
                       int N, int G, int h, float scale, void* dqkv, long long ld_dtok, float* colsum, cudaStream_t s) {
-  using C = BwdCfg<NKV16>;
+  using C = BwdCfg<NKV16, NG>;
   CUtensorMap tmQ, tmKV, tmDO;
   int rc = tmap_rows(&tmQ, qkv, (long long)B * N, 3LL * h * HD, ld_tok, BLOCK_Q);
   if (rc) return rc;
@@ -1270,11 +1528,11 @@ static int launch_bwd(const void* qkv, long long ld_tok, const void* out, const 
   if (rc) return rc;
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(attn_bwd_tc_kernel<NKV16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(attn_bwd_tc_kernel<NKV16, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
       return B200_ERR_CUDA;
     attr = true;
   }
-  launch_kernel(attn_bwd_tc_kernel<NKV16>, ((B + G - 1) / G) * h, C::THREADS, C::SMEM_BYTES, s, tmQ, tmKV, tmDO, (const __nv_bfloat16*)out,
+  launch_kernel(attn_bwd_tc_kernel<NKV16, NG>, ((B + G - 1) / G) * h, C::THREADS, C::SMEM_BYTES, s, tmQ, tmKV, tmDO, (const __nv_bfloat16*)out,
                                                                                   (const __nv_bfloat16*)dout, ld_out, lse, B, N, G, h,
                                                                                   scale, (__nv_bfloat16*)dqkv, ld_dtok, colsum);
   B200_CHECK_LAUNCH();
@@ -1295,7 +1553,12 @@ extern "C" int b200_attention_fwd_tc(const void* qkv, long long ld_tok, int B, i
   static int sched = -1;  // B200_ATTN_FWD_SCHEDULE=1: both query tiles in one CTA; default 3: one tile per CTA, two CTAs per SM
   if (sched < 0) {
     const char* e = std::getenv("B200_ATTN_FWD_SCHEDULE");
-    sched = (e && e[0] >= '1' && e[0] <= '4') ? e[0] - '0' : 3;
+    sched = (e && e[0] >= '1' && e[0] <= '5') ? e[0] - '0' : 3;
+  }
+  if (sched == 5) {
+    if (N <= 128) return launch_fwd5<8>(qkv, ld_tok, B, N, 128 / N, h, scale, out, ld_out, lse, s);
+    if (N <= 208) return launch_fwd5<13>(qkv, ld_tok, B, N, 1, h, scale, out, ld_out, lse, s);
+    return launch_fwd<16>(qkv, ld_tok, B, N, 1, h, scale, out, ld_out, lse, s);  // NKV = 256: P tiles + exchange buffers exceed smem
   }
   if (sched == 4) {
     if (N <= 128) return launch_fwd4<8>(qkv, ld_tok, B, N, 128 / N, h, scale, out, ld_out, lse, s);
@@ -1323,6 +1586,15 @@ extern "C" int b200_attention_bwd_tc(const void* qkv, long long ld_tok, const vo
   if (((uintptr_t)qkv & 15) || ((uintptr_t)out & 15) || ((uintptr_t)dout & 15) || ((uintptr_t)dqkv & 15)) return B200_ERR_UNSUPPORTED;
   if (N > 208) return B200_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
-  if (N <= 128) return launch_bwd<8>(qkv, ld_tok, out, dout, ld_out, lse, B, N, 128 / N, h, scale, dqkv, ld_dtok, dqkv_colsum, s);
-  return launch_bwd<13>(qkv, ld_tok, out, dout, ld_out, lse, B, N, 1, h, scale, dqkv, ld_dtok, dqkv_colsum, s);
+  static int groups = -1;  // B200_ATTN_BWD_GROUPS = 2 (8 worker warps, default) | 4 (16 worker warps: each row's keys split four ways)
+  if (groups < 0) {
+    const char* e = std::getenv("B200_ATTN_BWD_GROUPS");
+    groups = (e && e[0] == '4') ? 4 : 2;
+  }
+  if (groups == 4) {
+    if (N <= 128) return launch_bwd<8, 4>(qkv, ld_tok, out, dout, ld_out, lse, B, N, 128 / N, h, scale, dqkv, ld_dtok, dqkv_colsum, s);
+    return launch_bwd<13, 4>(qkv, ld_tok, out, dout, ld_out, lse, B, N, 1, h, scale, dqkv, ld_dtok, dqkv_colsum, s);
+  }
+  if (N <= 128) return launch_bwd<8, 2>(qkv, ld_tok, out, dout, ld_out, lse, B, N, 128 / N, h, scale, dqkv, ld_dtok, dqkv_colsum, s);
+  return launch_bwd<13, 2>(qkv, ld_tok, out, dout, ld_out, lse, B, N, 1, h, scale, dqkv, ld_dtok, dqkv_colsum, s);
 }
