@@ -425,6 +425,8 @@ def run_distill(args) -> None:
             line["diagnostic"] = "gradient all-reduce DISABLED (B200_BENCH_DIAG_NO_ALLREDUCE=1): not a training step, not a bench value"
         print(json.dumps(line), flush=True)
     if world > 1:
+        torch.cuda.synchronize()
+        method.release_graphs()  # captured NCCL kernels (B200_GRAPH_NCCL=1) must be gone before the communicator is
         dist.barrier()
         dist.destroy_process_group()
 
@@ -687,6 +689,8 @@ def main() -> None:
             line["diagnostic"] = "gradient all-reduce DISABLED (B200_BENCH_DIAG_NO_ALLREDUCE=1): not a training step, not a bench value"
         print(json.dumps(line), flush=True)
     if world > 1:
+        torch.cuda.synchronize()
+        method.release_graphs()  # captured NCCL kernels (B200_GRAPH_NCCL=1) must be gone before the communicator is
         dist.barrier()
         dist.destroy_process_group()
 

@@ -948,6 +948,19 @@ class DINOv2(nn.Module):
         make `backward()` a no-op instead of an error ('autograd bridge')."""
         return result.loss.detach().requires_grad_(True)
 
+    def release_graphs(self) -> None:
+        """Drop the captured step graphs (and their memory pool).  Call before `dist.destroy_process_group()` when the graphs
+        hold captured NCCL kernels (B200_GRAPH_NCCL=1): the communicator cannot be torn down while a graph references it."""
+        st = self._static
+        if st is not None:
+            for entry in st["graphs"].values():
+                for g in entry[:3]:
+                    if g is not None:
+                        g.reset()
+            st["graphs"].clear()
+            st["pool"] = None
+        self._static = None
+
     def _graph_ok(self) -> bool:
         """CUDA-graph replay of the step: always for softmax centering and for Sinkhorn-Knopp on a single rank.  With
         Sinkhorn-Knopp on several ranks the per-iteration [K] all-reduces sit in the middle of the captured schedule: they

@@ -139,6 +139,8 @@ if _dm.GRAPH_NCCL:
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             result["sinkhorn_graph_nccl_replicas_identical"] = bool(ok.item())
             assert ok.item() == 1
+            torch.cuda.synchronize()
+            m.release_graphs()  # the communicator cannot be destroyed while a graph holds captured NCCL kernels
     result["sinkhorn_graph_nccl_losses_rank%d" % rank] = losses
     for a, b in zip(losses[False], losses[True]):
         assert abs(a - b) < 2e-3 * max(1.0, abs(a)), losses
