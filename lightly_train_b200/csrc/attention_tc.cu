@@ -951,52 +951,68 @@ attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint8_t* sP = smem + C::OFF_P + t * C::P_BYTES;
     const int pair_bar = 1 + (warp & 7);                     // named barrier shared by warps w and w + 8
     uint32_t buf[16];
-    // packed bf16 scores of one 16-key chunk, keys outside the row's image -> -inf; the next chunk's TMEM load is issued as
-    // soon as `buf` has been packed so that it is in flight during the arithmetic on this chunk
+    // Leading chunks of my range whose 16 keys are valid for EVERY row of the CTA run a mask-free body (with one image per
+    // CTA that is all but the last chunk; packed short sequences take the masked body throughout).  ncu on the first
+    // version: the per-element key tests were if-converted into ~3 predicate / select instructions per element on every
+    // chunk, 18 instructions per score element in total.
+    const int nfull = (G == 1) ? max(0, min(nc, N / 16 - c0)) : 0;
+    // packed bf16 scores of one 16-key chunk; the next chunk's TMEM load is issued as soon as `buf` has been packed so that it
+    // is in flight during the arithmetic on this chunk
     auto take_chunk = [&](int c, uint32_t (&pk)[8]) {
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(__uint_as_float(buf[2 * i]), __uint_as_float(buf[2 * i + 1]));
       if (c + 1 < nc) tmem_ld_32x16(tS + (c0 + c + 1) * 16, buf);
+    };
+    auto mask_chunk = [&](int c, uint32_t (&pk)[8]) {  // keys outside the row's image -> -inf
       const int kc = (c0 + c) * 16;
-      if (!(kc >= klo && kc + 16 <= khi)) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int k = kc + 2 * i;
-          if (!(k >= klo && k < khi)) pk[i] = (pk[i] & 0xFFFF0000u) | 0x0000FF80u;          // -inf
-          if (!(k + 1 >= klo && k + 1 < khi)) pk[i] = (pk[i] & 0x0000FFFFu) | 0xFF800000u;
-        }
+      for (int i = 0; i < 8; ++i) {
+        const int k = kc + 2 * i;
+        if (!(k >= klo && k < khi)) pk[i] = (pk[i] & 0xFFFF0000u) | 0x0000FF80u;
+        if (!(k + 1 >= klo && k + 1 < khi)) pk[i] = (pk[i] & 0x0000FFFFu) | 0xFF800000u;
       }
     };
     mbar_wait(bar_s + t, 0);
     tc_fence_after();
-    float mx = -INFINITY;
+    // pass 1: row max of the bf16-rounded scores, on packed pairs (max.bf16x2)
+    uint32_t mx2 = 0xFF80FF80u;
     if (nc > 0) tmem_ld_32x16(tS + c0 * 16, buf);
 #pragma unroll 1
-    for (int c = 0; c < nc; ++c) {
+    for (int c = 0; c < nfull; ++c) {
       uint32_t pk[8];
       take_chunk(c, pk);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float2 rr = unpack_bf16x2(pk[i]);
-        mx = fmaxf(mx, fmaxf(rr.x, rr.y));
-      }
+      for (int i = 0; i < 8; i += 2) mx2 = bf16x2_max(mx2, bf16x2_max(pk[i], pk[i + 1]));
+    }
+#pragma unroll 1
+    for (int c = nfull; c < nc; ++c) {
+      uint32_t pk[8];
+      take_chunk(c, pk);
+      mask_chunk(c, pk);
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) mx2 = bf16x2_max(mx2, bf16x2_max(pk[i], pk[i + 1]));
     }
     if (nc > 0) tmem_ld_32x16(tS + c0 * 16, buf);            // first chunk of pass 2: in flight across the exchange
+    float mx;
+    {
+      const float2 mm = unpack_bf16x2(mx2);
+      mx = fmaxf(mm.x, mm.y);
+    }
     xmax[half * 256 + m] = mx;
     named_bar_sync(pair_bar, 64);
     mx = fmaxf(mx, xmax[(half ^ 1) * 256 + m]);
     const float mb = -mx * sl2;
-    float l = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < nc; ++c) {
-      uint32_t pk[8], pw[8];
-      take_chunk(c, pk);
+    // pass 2: p = 2^(s*sl2 - m*sl2) -> bf16 -> swizzled smem A tile; row sum in fp32 (two accumulators)
+    float l0 = 0.f, l1 = 0.f;
+    auto exp_store = [&](int c, const uint32_t (&pk)[8]) {
+      uint32_t pw[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float2 rr = unpack_bf16x2(pk[i]);
         const float p0 = ex2_ftz(fmaf(rr.x, sl2, mb)), p1 = ex2_ftz(fmaf(rr.y, sl2, mb));
-        l += p0 + p1;
+        l0 += p0;
+        l1 += p1;
         pw[i] = pack_bf16x2(p0, p1);
       }
       const int cc = c0 + c;
@@ -1004,7 +1020,21 @@ attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int ch = (cc & 3) * 2;
       *reinterpret_cast<uint4*>(slab + swz(r, ch)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
       *reinterpret_cast<uint4*>(slab + swz(r, ch + 1)) = make_uint4(pw[4], pw[5], pw[6], pw[7]);
+    };
+#pragma unroll 1
+    for (int c = 0; c < nfull; ++c) {
+      uint32_t pk[8];
+      take_chunk(c, pk);
+      exp_store(c, pk);
     }
+#pragma unroll 1
+    for (int c = nfull; c < nc; ++c) {
+      uint32_t pk[8];
+      take_chunk(c, pk);
+      mask_chunk(c, pk);
+      exp_store(c, pk);
+    }
+    float l = l0 + l1;
     xsum[half * 256 + m] = l;
     fence_proxy_async();
     tc_fence_before();
@@ -1111,53 +1141,80 @@ __device__ __forceinline__ void drain_tile(uint32_t taddr, float mul, bool valid
   drain_cols32(taddr, 1, mul, valid, grow, cs, lane);
 }
 
-// Backward worker passes over the 16-key chunks [C0, C1) of one row, TMEM loads issued one chunk ahead of their use.
-//   P pass : p = 2^(s*sl2 - L) (0 on padded rows / keys outside [klo, khi)) -> bf16 -> swizzled smem row
+// Backward worker passes over the 16-key chunks [C0, C1) of one row.  The next chunk's TMEM load is issued as soon as the
+// current one has been packed to bf16 pairs, so it is in flight during the arithmetic.
+//   P pass : p = 2^(s*sl2 - L) (0 on padded rows / keys outside [klo, khi)) -> bf16 -> swizzled smem row.  Chunks below
+//            `nfull` hold only valid keys for every row of the CTA and run a mask-free body (padded ROWS carry L = +inf there,
+//            which makes their p exactly 0 without a test); the rest test every key.
 //   dS pass: dS = p * (dP - D), bf16, written in place of p
 template <int C0, int C1>
-__device__ __forceinline__ void bwd_p_pass(uint32_t tcol, uint8_t* sP, int r, bool row_ok, int klo, int khi, float sl2, float L) {
-  uint32_t buf[2][16];
-  tmem_ld_32x16(tcol + C0 * 16, buf[0]);
-#pragma unroll
-  for (int c = C0; c < C1; ++c) {
+__device__ __forceinline__ void bwd_p_pass(uint32_t tcol, uint8_t* sP, int r, bool row_ok, int klo, int khi, int nfull, float sl2,
+                                           float L) {
+  uint32_t buf[16];
+  const float Linf = row_ok ? L : INFINITY;
+  tmem_ld_32x16(tcol + C0 * 16, buf);
+  auto take = [&](int c, uint32_t (&pk)[8]) {
     tmem_ld_wait();
-    if (c + 1 < C1) tmem_ld_32x16(tcol + (c + 1) * 16, buf[(c + 1 - C0) & 1]);
-    const uint32_t (&v)[16] = buf[(c - C0) & 1];
-    uint32_t pw[8];
 #pragma unroll
-    for (int i = 0; i < 16; i += 2) {
-      const float2 rr = unpack_bf16x2(pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-      const int k = c * 16 + i;
-      const float p0 = (row_ok && k >= klo && k < khi) ? ex2_ftz(fmaf(rr.x, sl2, -L)) : 0.f;
-      const float p1 = (row_ok && k + 1 >= klo && k + 1 < khi) ? ex2_ftz(fmaf(rr.y, sl2, -L)) : 0.f;
-      pw[i >> 1] = pack_bf16x2(p0, p1);
-    }
+    for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(__uint_as_float(buf[2 * i]), __uint_as_float(buf[2 * i + 1]));
+    if (c + 1 < C1) tmem_ld_32x16(tcol + (c + 1) * 16, buf);
+  };
+  auto store = [&](int c, const uint32_t (&pw)[8]) {
     uint8_t* slab = sP + (c >> 2) * TILE_BYTES;
     const int ch = (c & 3) * 2;
     *reinterpret_cast<uint4*>(slab + swz(r, ch)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
     *reinterpret_cast<uint4*>(slab + swz(r, ch + 1)) = make_uint4(pw[4], pw[5], pw[6], pw[7]);
+  };
+  int c = C0;
+  const int cf = min(C1, nfull);
+#pragma unroll 1
+  for (; c < cf; ++c) {
+    uint32_t pk[8], pw[8];
+    take(c, pk);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 rr = unpack_bf16x2(pk[i]);
+      pw[i] = pack_bf16x2(ex2_ftz(fmaf(rr.x, sl2, -Linf)), ex2_ftz(fmaf(rr.y, sl2, -Linf)));
+    }
+    store(c, pw);
+  }
+#pragma unroll 1
+  for (; c < C1; ++c) {
+    uint32_t pk[8], pw[8];
+    take(c, pk);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 rr = unpack_bf16x2(pk[i]);
+      const int k = c * 16 + 2 * i;
+      const float p0 = (row_ok && k >= klo && k < khi) ? ex2_ftz(fmaf(rr.x, sl2, -L)) : 0.f;
+      const float p1 = (row_ok && k + 1 >= klo && k + 1 < khi) ? ex2_ftz(fmaf(rr.y, sl2, -L)) : 0.f;
+      pw[i] = pack_bf16x2(p0, p1);
+    }
+    store(c, pw);
   }
 }
 template <int C0, int C1>
 __device__ __forceinline__ void bwd_ds_pass(uint32_t tcol, uint8_t* sP, int r, float D) {
-  uint32_t buf[2][16];
-  tmem_ld_32x16(tcol + C0 * 16, buf[0]);
-#pragma unroll
+  uint32_t buf[16];
+  tmem_ld_32x16(tcol + C0 * 16, buf);
+#pragma unroll 1
   for (int c = C0; c < C1; ++c) {
     uint8_t* slab = sP + (c >> 2) * TILE_BYTES;
     const int ch = (c & 3) * 2;
     const uint4 pa = *reinterpret_cast<const uint4*>(slab + swz(r, ch));
     const uint4 pb = *reinterpret_cast<const uint4*>(slab + swz(r, ch + 1));
     tmem_ld_wait();
-    if (c + 1 < C1) tmem_ld_32x16(tcol + (c + 1) * 16, buf[(c + 1 - C0) & 1]);
-    const uint32_t (&v)[16] = buf[(c - C0) & 1];
+    uint32_t dpk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dpk[i] = pack_bf16x2(__uint_as_float(buf[2 * i]), __uint_as_float(buf[2 * i + 1]));  // bf16 dP
+    if (c + 1 < C1) tmem_ld_32x16(tcol + (c + 1) * 16, buf);
     const uint32_t pin[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
     uint32_t dw[8];
 #pragma unroll
-    for (int i = 0; i < 16; i += 2) {
-      const float2 dp = unpack_bf16x2(pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));  // bf16 dP
-      const float2 pp = unpack_bf16x2(pin[i >> 1]);  // p = 0 on masked rows / keys: dS = 0 there whatever dP holds
-      dw[i >> 1] = pack_bf16x2(pp.x * (dp.x - D), pp.y * (dp.y - D));
+    for (int i = 0; i < 8; ++i) {
+      const float2 dp = unpack_bf16x2(dpk[i]);
+      const float2 pp = unpack_bf16x2(pin[i]);  // p = 0 on masked rows / keys: dS = 0 there whatever dP holds
+      dw[i] = pack_bf16x2(pp.x * (dp.x - D), pp.y * (dp.y - D));
     }
     *reinterpret_cast<uint4*>(slab + swz(r, ch)) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
     *reinterpret_cast<uint4*>(slab + swz(r, ch + 1)) = make_uint4(dw[4], dw[5], dw[6], dw[7]);
@@ -1333,13 +1390,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const bool row_ok = m < rows_valid;
       const int klo = min(m / N, n_img - 1) * N, khi = klo + N;  // this row's keys: its own image's tokens
       const float L = sL[m], D = sD[m];
+      const int nfull = (G == 1) ? N / 16 : 0;  // chunks whose 16 keys are valid for every row (one image per CTA)
       // ---- P = 2^(s*sl2 - L) for my key columns (0 for padded rows / keys) -> smem
       mbar_wait(bar_s, ph);
       tc_fence_after();
-      if (g == 0) bwd_p_pass<C::qb(0), C::qb(1)>(tL + C::TM_SDP, sP, r, row_ok, klo, khi, sl2, L);
-      else if (g == 1) bwd_p_pass<C::qb(1), C::qb(2)>(tL + C::TM_SDP, sP, r, row_ok, klo, khi, sl2, L);
-      else if (NG == 4 && g == 2) bwd_p_pass<C::qb(NG == 4 ? 2 : 0), C::qb(NG == 4 ? 3 : 1)>(tL + C::TM_SDP, sP, r, row_ok, klo, khi, sl2, L);
-      else if (NG == 4) bwd_p_pass<C::qb(NG == 4 ? 3 : 0), C::qb(NG == 4 ? 4 : 1)>(tL + C::TM_SDP, sP, r, row_ok, klo, khi, sl2, L);
+      if (g == 0) bwd_p_pass<C::qb(0), C::qb(1)>(tL + C::TM_SDP, sP, r, row_ok, klo, khi, nfull, sl2, L);
+      else if (g == 1) bwd_p_pass<C::qb(1), C::qb(2)>(tL + C::TM_SDP, sP, r, row_ok, klo, khi, nfull, sl2, L);
+      else if (NG == 4 && g == 2) bwd_p_pass<C::qb(NG == 4 ? 2 : 0), C::qb(NG == 4 ? 3 : 1)>(tL + C::TM_SDP, sP, r, row_ok, klo, khi, nfull, sl2, L);
+      else if (NG == 4) bwd_p_pass<C::qb(NG == 4 ? 3 : 0), C::qb(NG == 4 ? 4 : 1)>(tL + C::TM_SDP, sP, r, row_ok, klo, khi, nfull, sl2, L);
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();

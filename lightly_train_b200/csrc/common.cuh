@@ -265,6 +265,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// element-wise maximum of two packed bf16 pairs (one HMNMX2 instead of two unpacks + two FMNMX)
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
 // two bit operations (the __bfloat1622float2 intrinsic compiles to two PRMT + two shifts per pair)
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));

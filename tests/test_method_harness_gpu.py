@@ -73,7 +73,8 @@ def test_lightning_shaped_loop_equals_train_step():
     # fp32 split-K atomics reorder the wgrad sums run to run and Adam's first steps are lr * g/|g|: elements whose gradient
     # sits at rounding-noise level can move by up to ~lr (here 2e-3) differently in two runs; everything else agrees tightly
     d = (a.s_arena.fp32 - b.s_arena.fp32).abs()
-    assert d.max().item() < 3 * a.base_lr and d.mean().item() < 1e-6 and (d > 1e-5).float().mean().item() < 1e-3
+    # (a systematic difference -- a wrong lr / weight-decay / momentum index -- moves EVERY element by ~lr: mean ~1e-3)
+    assert d.max().item() < 3 * a.base_lr and d.mean().item() < 2e-5 and (d > 1e-5).float().mean().item() < 5e-3
     assert (a.t_arena.fp32 - b.t_arena.fp32).abs().max().item() < 1e-4
     assert a.trainer.global_step == b.trainer.global_step == 3
     for k in ("train_loss", "train_loss/dino_global_loss", "train_loss/dino_local_loss", "train_loss/ibot_loss", "train_loss/koleo_loss"):
@@ -104,10 +105,14 @@ def test_ema_hook_order_and_unfused_update_momentum():
     assert torch.equal(b.t_arena.fp32, t_before)  # teacher untouched so far
     b.on_train_batch_end(None, batch, 0)
     torch.cuda.synchronize()
-    assert (a.t_arena.fp32 - b.t_arena.fp32).abs().max().item() < 1e-6
+    # each run against ITS OWN student (the two students differ by run-to-run atomics noise through Adam's first step, which
+    # the EMA passes on scaled by 1 - m): exact identity; across the runs only the noise bound
     m = O.cosine_schedule(1, 10, a.method_args.momentum_start, a.method_args.momentum_end)
     want = t_before * m + a.s_arena.fp32 * (1 - m)
     assert (a.t_arena.fp32 - want).abs().max().item() < 1e-6
+    want_b = t_before * m + b.s_arena.fp32 * (1 - m)
+    assert (b.t_arena.fp32 - want_b).abs().max().item() < 1e-6
+    assert (a.t_arena.fp32 - b.t_arena.fp32).abs().max().item() < 3 * a.base_lr * (1 - m) + 1e-6
     # reference signature on arbitrary arena-backed modules (LT/_torch_helpers.py:89-96)
     t2 = b.t_arena.fp32.clone()
     update_momentum(b.student_head, b.teacher_head, 0.5)
@@ -136,7 +141,10 @@ def test_checkpoint_resume_is_exact():
     ra, rb = a.train_step(batch), b.train_step(batch)
     torch.cuda.synchronize()
     assert abs(float(ra.loss) - float(rb.loss)) < 1e-5 * abs(float(ra.loss))
-    assert (a.s_arena.fp32 - b.s_arena.fp32).abs().max().item() < 1e-5
+    # identical state going in; the step itself reorders fp32 atomics run to run (see the Lightning-loop test): elements with
+    # noise-level gradients may differ by ~lr, everything else agrees tightly
+    d = (a.s_arena.fp32 - b.s_arena.fp32).abs()
+    assert d.max().item() < 3 * a.base_lr and d.mean().item() < 2e-5 and (d > 1e-5).float().mean().item() < 5e-3
 
 
 @pytest.mark.skipif(not ref_full.available(), reason="reference copy (baseline/_ref) not on this box")
