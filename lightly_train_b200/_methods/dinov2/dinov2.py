@@ -17,9 +17,11 @@ torch.autograd bridge for trainers that insist on calling `loss.backward()` (INT
 """
 from __future__ import annotations
 
+import atexit
 import contextlib
 import math
 import os
+import weakref
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Literal, Optional, Tuple
 
@@ -37,8 +39,39 @@ from ..._torch_helpers import update_momentum
 from ... import _lib
 from .utils import MaskingGenerator, create_collated_masks, param_group_settings
 
-# Sinkhorn-Knopp on several ranks: capture the per-iteration [K] all-reduces into the step's CUDA graph (opt-in)
-GRAPH_NCCL = os.environ.get("B200_GRAPH_NCCL", "0") == "1"
+# Sinkhorn-Knopp on several ranks: capture the per-iteration [K] all-reduces into the step's CUDA graph (NCCL kernels are
+# capturable; 2 x B200 at cfg3: 36.4 ms against 45.7 ms launched eagerly).  B200_GRAPH_NCCL=0 keeps that step eager.
+GRAPH_NCCL = os.environ.get("B200_GRAPH_NCCL", "1") == "1"
+
+# A communicator cannot be torn down while a live CUDA graph holds captured NCCL kernels (destroy_process_group blocks for
+# ever): methods that captured collectives are tracked here and their graphs are dropped before the process group goes.
+_NCCL_GRAPH_HOLDERS: "weakref.WeakSet[DINOv2]" = weakref.WeakSet()
+_teardown_hooked = False
+
+
+def _release_all_nccl_graphs() -> None:
+    for m in list(_NCCL_GRAPH_HOLDERS):
+        try:
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+            m.release_graphs()
+        except Exception:  # interpreter shutdown: nothing left to protect
+            pass
+
+
+def _hook_process_group_teardown() -> None:
+    global _teardown_hooked
+    if _teardown_hooked:
+        return
+    _teardown_hooked = True
+    original = dist.destroy_process_group
+
+    def destroy_process_group(*args: Any, **kwargs: Any) -> Any:
+        _release_all_nccl_graphs()
+        return original(*args, **kwargs)
+
+    dist.destroy_process_group = destroy_process_group
+    atexit.register(_release_all_nccl_graphs)
 
 
 # where the backbone backward is cut for the middle all-reduce bucket: blocks >= FRAC * depth go out after graph 2
@@ -775,6 +808,9 @@ class DINOv2(nn.Module):
             # half of the global-crop backward] | [lower half + embeddings]; the all-reduce of the gradients that are final
             # after each graph is issued between the replays and overlaps the next one
             g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            if a.center_method != "softmax" and _world_size() > 1:  # graph 1 will hold captured all-reduces
+                _NCCL_GRAPH_HOLDERS.add(self)
+                _hook_process_group_teardown()
             n0 = _lib.LAUNCHES
             with torch.cuda.graph(g1, pool=st["pool"], capture_error_mode="thread_local"):  # NCCL watchdog thread may touch CUDA
                 mid = run_a()
@@ -975,9 +1011,9 @@ class DINOv2(nn.Module):
         self._static = None
 
     def _graph_ok(self) -> bool:
-        """CUDA-graph replay of the step: always for softmax centering and for Sinkhorn-Knopp on a single rank.  With
-        Sinkhorn-Knopp on several ranks the per-iteration [K] all-reduces sit in the middle of the captured schedule: they
-        are captured into the graph (NCCL kernels are capturable) when B200_GRAPH_NCCL=1, otherwise the step runs eagerly."""
+        """CUDA-graph replay of the step.  With Sinkhorn-Knopp on several ranks the per-iteration [K] all-reduces sit in the
+        middle of the captured schedule: they are captured into the graph (every rank then replays ONE padded shape every
+        step, see `_graphed_step`), unless B200_GRAPH_NCCL=0, in which case that step runs eagerly."""
         if not self.use_cuda_graph:
             return False
         if self.method_args.center_method == "softmax" or _world_size() == 1:
