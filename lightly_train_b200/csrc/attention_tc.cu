@@ -63,6 +63,15 @@ __device__ __forceinline__ uint32_t instr_desc(int m, int n, int a_mn, int b_mn)
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// 64-thread barrier of warp pair q (0..3) with a compile-time id each, so that ptxas reserves 5 barriers, not all 16
+__device__ __forceinline__ void pair_bar_sync4(int q) {
+  switch (q) {
+    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+  }
+}
 // 16-byte chunk `chunk` (8 bf16) of row `row` of a [rows][64] bf16 tile with 128-byte rows, 128B swizzle
 __device__ __forceinline__ uint32_t swz(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
 
@@ -1071,6 +1080,231 @@ attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 }
 
 // ====================================================================================================================
+// forward, schedule 7: P stays in TENSOR MEMORY (A operand of P V read from TMEM); one query tile per CTA, two CTAs per SM
+// ====================================================================================================================
+// ncu on schedule 5 (profiles/r02_ncu_attn_tc16.txt): per (image, head) pair the softmax warps spend 23 % of the CTA's life
+// waiting for its 85 KB of TMA loads (every CTA of a wave loads at the same time, then computes while HBM idles), 9 % on
+// P V, 5 % in the exit tail; and the 2 x 64 KB of swizzled shared memory that carry P to the second MMA are what keeps a
+// second CTA (or a second K / V stage) off the SM.  Here the probabilities never leave tensor memory:
+//   * S = Q K^T lands in TMEM columns [0, NKV); every row is shared by two threads (warps w / w + 4, the same TMEM lane
+//     quarter) that read their half of the row ONCE, keep it in registers as packed bf16 pairs (keys outside the query's
+//     image = -inf) and exchange the half-row maximum / sum through shared memory + a 64-thread named barrier;
+//   * P = 2^((s - m) scale log2e) is written back with tcgen05.st as packed bf16 pairs into columns [0, NKV / 2) -- over S,
+//     which is dead once both halves hold their rows -- and O = P V is issued with the A operand in TMEM (tcgen05.mma
+//     [d], [a], b-desc), per half as soon as that half's four warps have stored their columns; O accumulates in columns
+//     [128, 192) (also over dead S);
+//   * shared memory is only Q (16 KB) + K + V: 69 KB at NKV = 208, TMEM 256 columns, so two CTAs share an SM and one's loads,
+//     set-up and tail hide behind the other's softmax.
+template <int NKV16>
+struct Fwd7Cfg {
+  static constexpr int NKV = NKV16 * 16;
+  static constexpr int KV_BYTES = NKV * 128;
+  static constexpr int OFF_K = TILE_BYTES;
+  static constexpr int OFF_V = OFF_K + KV_BYTES;
+  static constexpr int OFF_X = (OFF_V + KV_BYTES + 1023) / 1024 * 1024;  // floats: half-row max [2][128], half-row sum [2][128]
+  static constexpr int OFF_BAR = OFF_X + 4 * 128 * 4;
+  static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
+  static constexpr int THREADS = 9 * 32;
+  static constexpr int HA = (NKV16 + 1) / 2;                // 16-key chunks of the first / second column half
+  static constexpr int HB = NKV16 - HA;
+  static constexpr int TM_O = 128;                          // O accumulator columns [128, 192)
+  static constexpr int TMEM_COLS = 256;
+  static_assert(NKV <= 256 && HB >= 1 && 2 * SMEM_BYTES <= 232448, "two CTAs per SM");
+};
+
+// one half of one query row: HALF 0 = key chunks [0, HA), HALF 1 = [HA, NKV16)
+template <int NKV16, int HALF>
+__device__ __forceinline__ void fwd7_worker(uint32_t tS, float* xmax, float* xsum, uint64_t* bar_s, uint64_t* bar_p, uint64_t* bar_o,
+                                            int r, int q, int lane, int klo, int khi, bool all_inside, float sl2, float scale,
+                                            float* lse_row, __nv_bfloat16* orow) {
+  using C = Fwd7Cfg<NKV16>;
+  constexpr int C0 = HALF ? C::HA : 0, NC = HALF ? C::HB : C::HA;
+  uint32_t srow[NC * 8];
+  uint32_t buf[16];
+  mbar_wait(bar_s, 0);
+  tc_fence_after();
+  // pass 1 (the only read of S): packed bf16 row half -> registers, row max on packed pairs
+  uint32_t mx2 = 0xFF80FF80u;
+  tmem_ld_32x16(tS + C0 * 16, buf);
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) srow[c * 8 + i] = pack_bf16x2(__uint_as_float(buf[2 * i]), __uint_as_float(buf[2 * i + 1]));
+    if (c + 1 < NC) tmem_ld_32x16(tS + (C0 + c + 1) * 16, buf);
+    const int kc = (C0 + c) * 16;
+    if (!(all_inside && kc + 16 <= khi)) {  // warp-uniform when one image per CTA: only the last chunk takes this path
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = kc + 2 * i;
+        if (!(k >= klo && k < khi)) srow[c * 8 + i] = (srow[c * 8 + i] & 0xFFFF0000u) | 0x0000FF80u;  // -inf
+        if (!(k + 1 >= klo && k + 1 < khi)) srow[c * 8 + i] = (srow[c * 8 + i] & 0x0000FFFFu) | 0xFF800000u;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) mx2 = bf16x2_max(mx2, bf16x2_max(srow[c * 8 + i], srow[c * 8 + i + 1]));
+  }
+  float mx;
+  {
+    const float2 mm = unpack_bf16x2(mx2);
+    mx = fmaxf(mm.x, mm.y);
+  }
+  xmax[HALF * 128 + r] = mx;
+  tc_fence_before();              // my S reads are complete before the partner (after the barrier) overwrites those columns
+  pair_bar_sync4(q);
+  tc_fence_after();
+  mx = fmaxf(mx, xmax[(HALF ^ 1) * 128 + r]);
+  const float mb = -mx * sl2;
+  // pass 2 from registers: p -> bf16 pairs -> TMEM columns [(C0 + c) * 8, + 8) (over the dead S)
+  float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    uint32_t pw[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 rr = unpack_bf16x2(srow[c * 8 + i]);
+      const float p0 = ex2_ftz(fmaf(rr.x, sl2, mb)), p1 = ex2_ftz(fmaf(rr.y, sl2, mb));
+      l0 += p0;
+      l1 += p1;
+      pw[i] = pack_bf16x2(p0, p1);
+    }
+    tmem_st_32x8(tS + (C0 + c) * 8, pw);
+  }
+  float l = l0 + l1;
+  xsum[HALF * 128 + r] = l;
+  tmem_st_wait();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar_p + HALF);
+  pair_bar_sync4(q);
+  l += xsum[(HALF ^ 1) * 128 + r];
+  if (HALF == 0 && lse_row) *lse_row = mx * scale + __logf(l);
+  mbar_wait(bar_o, 0);
+  tc_fence_after();
+  const float inv = 1.f / l;
+  uint32_t ov[32];
+  tmem_ld_32x32(tS + C::TM_O + HALF * 32, ov);
+  tmem_ld_wait();
+  if (orow) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t ow[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        ow[j] = pack_bf16x2(__uint_as_float(ov[i * 8 + 2 * j]) * inv, __uint_as_float(ov[i * 8 + 2 * j + 1]) * inv);
+      *reinterpret_cast<uint4*>(orow + HALF * 32 + i * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+  }
+}
+
+template <int NKV16>
+__global__ void __launch_bounds__(Fwd7Cfg<NKV16>::THREADS, 2)
+attn_fwd_tc7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, int B, int N, int G, int h,
+                    int tiles_per_group, float scale, __nv_bfloat16* __restrict__ out, long long ld_out, float* __restrict__ lse) {
+  pdl_launch_dependents();
+  using C = Fwd7Cfg<NKV16>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* bar_load = bars + 0;
+  uint64_t* bar_s = bars + 1;     // S in TMEM
+  uint64_t* bar_p = bars + 2;     // [2 halves] P columns of that half stored to TMEM (4 warps each)
+  uint64_t* bar_o = bars + 4;     // O complete in TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  float* xmax = reinterpret_cast<float*>(smem + C::OFF_X);   // [half][128]
+  float* xsum = xmax + 256;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x % tiles_per_group;
+  const int grp = blockIdx.x / tiles_per_group;
+  const int bg = grp / h, head = grp % h;
+  const int b0 = bg * G, n_img = min(G, B - b0);
+  const int rows_valid = n_img * N;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_load, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 4);
+    mbar_init(bar_p + 1, 4);
+    mbar_init(bar_o, 1);
+    fence_barrier_init();
+  }
+  if (warp == 8) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmKV);
+    }
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ===================== control warp: TMA + MMA issue =====================
+    const int row0 = b0 * N;
+    if (lane == 0) {
+      mbar_expect_tx(bar_load, TILE_BYTES + 2 * C::KV_BYTES);
+      tma_load_2d(smem, &tmQ, bar_load, head * HD, row0 + t * BLOCK_Q);
+      tma_load_2d(smem + C::OFF_K, &tmKV, bar_load, (h + head) * HD, row0);
+      tma_load_2d(smem + C::OFF_V, &tmKV, bar_load, (2 * h + head) * HD, row0);
+    }
+    __syncwarp();
+    mbar_wait(bar_load, 0);
+    const uint32_t s0 = smem_u32(smem);
+    const uint64_t dq = smem_desc(s0, 16, 1024);
+    const uint64_t dk = smem_desc(s0 + C::OFF_K, 16, 1024);
+    const uint64_t dv = smem_desc(s0 + C::OFF_V, 64 * 128, 1024);  // B of O: V rows, MN-major (N = head dim)
+    const uint32_t idesc_s = instr_desc(BLOCK_Q, C::NKV, 0, 0);
+    const uint32_t idesc_o = instr_desc(BLOCK_Q, HD, 0, 1);
+    if (elect_one_sync()) {
+#pragma unroll
+      for (int ks = 0; ks < HD / 16; ++ks)
+        umma_f16(tmem_base, dq + (uint64_t)(ks * 2), dk + (uint64_t)(ks * 2), idesc_s, ks > 0 ? 1u : 0u);
+      umma_commit(bar_s);
+    }
+    __syncwarp();
+    for (int half = 0; half < 2; ++half) {
+      mbar_wait(bar_p + half, 0);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const int k0 = half ? C::HA : 0, k1 = half ? NKV16 : C::HA;
+#pragma unroll 1
+        for (int ks = k0; ks < k1; ++ks)  // A: 16 keys = 8 packed columns of every lane; B: 16 V rows
+          umma_f16_ts(tmem_base + C::TM_O, tmem_base + ks * 8, dv + (uint64_t)((ks * 16 * 128) >> 4), idesc_o, ks > 0 ? 1u : 0u);
+        if (half == 1) umma_commit(bar_o);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== worker warps: lane quarter q, column half =====================
+    const int half = warp >> 2, q = warp & 3;
+    const int r = q * 32 + lane;
+    const int m = t * BLOCK_Q + r;
+    const int img = min(m / N, n_img - 1);
+    const int klo = img * N, khi = klo + N;
+    const uint32_t tS = tmem_base + ((uint32_t)(q * 32) << 16);
+    const bool valid = m < rows_valid;
+    float* lse_row = (lse && valid) ? lse + ((size_t)(b0 + img) * h + head) * N + (m - klo) : nullptr;
+    __nv_bfloat16* orow = valid ? out + ((size_t)b0 * N + m) * ld_out + head * HD : nullptr;
+    if (half == 0)
+      fwd7_worker<NKV16, 0>(tS, xmax, xsum, bar_s, bar_p, bar_o, r, q, lane, klo, khi, G == 1, scale * kLog2e, scale, lse_row, orow);
+    else
+      fwd7_worker<NKV16, 1>(tS, xmax, xsum, bar_s, bar_p, bar_o, r, q, lane, klo, khi, G == 1, scale * kLog2e, scale, lse_row, orow);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ====================================================================================================================
 // backward
 // ====================================================================================================================
 template <int NKV16, int NG = 2>
@@ -1573,6 +1807,28 @@ static int launch_fwd5(const void* qkv, long long ld_tok, int B, int N, int G, i
   return B200_OK;
 }
 
+template <int NKV16>
+static int launch_fwd7(const void* qkv, long long ld_tok, int B, int N, int G, int h, float scale, void* out, long long ld_out,
+                       float* lse, cudaStream_t s) {
+  using C = Fwd7Cfg<NKV16>;
+  CUtensorMap tmQ, tmKV;
+  int rc = tmap_rows(&tmQ, qkv, (long long)B * N, 3LL * h * HD, ld_tok, BLOCK_Q);
+  if (rc) return rc;
+  rc = tmap_rows(&tmKV, qkv, (long long)B * N, 3LL * h * HD, ld_tok, C::NKV);
+  if (rc) return rc;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(attn_fwd_tc7_kernel<NKV16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
+      return B200_ERR_CUDA;
+    attr = true;
+  }
+  const int tiles = (G * N + BLOCK_Q - 1) / BLOCK_Q;  // query tiles per (image group, head): 1 or 2
+  launch_kernel(attn_fwd_tc7_kernel<NKV16>, ((B + G - 1) / G) * h * tiles, C::THREADS, C::SMEM_BYTES, s, tmQ, tmKV, B, N, G, h, tiles,
+                scale, (__nv_bfloat16*)out, ld_out, lse);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
 template <int NKV16, int NG>
 static int launch_bwd(const void* qkv, long long ld_tok, const void* out, const void* dout, long long ld_out, const float* lse, int B,
                       int N, int G, int h, float scale, void* dqkv, long long ld_dtok, float* colsum, cudaStream_t s) {
@@ -1611,7 +1867,12 @@ extern "C" int b200_attention_fwd_tc(const void* qkv, long long ld_tok, int B, i
   static int sched = -1;  // B200_ATTN_FWD_SCHEDULE=1: both query tiles in one CTA; default 3: one tile per CTA, two CTAs per SM
   if (sched < 0) {
     const char* e = std::getenv("B200_ATTN_FWD_SCHEDULE");
-    sched = (e && e[0] >= '1' && e[0] <= '5') ? e[0] - '0' : 3;
+    sched = (e && e[0] >= '1' && e[0] <= '7') ? e[0] - '0' : 3;
+  }
+  if (sched == 7) {
+    if (N <= 128) return launch_fwd7<8>(qkv, ld_tok, B, N, 128 / N, h, scale, out, ld_out, lse, s);
+    if (N <= 208) return launch_fwd7<13>(qkv, ld_tok, B, N, 1, h, scale, out, ld_out, lse, s);
+    return launch_fwd7<16>(qkv, ld_tok, B, N, 1, h, scale, out, ld_out, lse, s);
   }
   if (sched == 5) {
     if (N <= 128) return launch_fwd5<8>(qkv, ld_tok, B, N, 128 / N, h, scale, out, ld_out, lse, s);
