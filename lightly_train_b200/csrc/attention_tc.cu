@@ -1864,10 +1864,13 @@ extern "C" int b200_attention_fwd_tc(const void* qkv, long long ld_tok, int B, i
   if (head_dim != HD || (ld_tok % 8) || (ld_out % 8) || ((uintptr_t)qkv & 15) || ((uintptr_t)out & 15)) return B200_ERR_UNSUPPORTED;
   if (N > 256) return B200_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
-  static int sched = -1;  // B200_ATTN_FWD_SCHEDULE=1: both query tiles in one CTA; default 3: one tile per CTA, two CTAs per SM
+  // B200_ATTN_FWD_SCHEDULE: 7 (default) P in tensor memory, one tile per CTA, two CTAs per SM: 46 us at 768 pairs x 197 tokens;
+  // 1 both tiles per CTA, P through shared memory (62 us); 3 one tile per CTA through shared memory (68 us); 4 persistent
+  // (72 us); 5 sixteen softmax warps (57 us) -- kept for A/B timing, all numerically identical (tools/attn_check.py)
+  static int sched = -1;
   if (sched < 0) {
     const char* e = std::getenv("B200_ATTN_FWD_SCHEDULE");
-    sched = (e && e[0] >= '1' && e[0] <= '7') ? e[0] - '0' : 3;
+    sched = (e && e[0] >= '1' && e[0] <= '7') ? e[0] - '0' : 7;
   }
   if (sched == 7) {
     if (N <= 128) return launch_fwd7<8>(qkv, ld_tok, B, N, 128 / N, h, scale, out, ld_out, lse, s);
@@ -1905,10 +1908,10 @@ extern "C" int b200_attention_bwd_tc(const void* qkv, long long ld_tok, const vo
   if (((uintptr_t)qkv & 15) || ((uintptr_t)out & 15) || ((uintptr_t)dout & 15) || ((uintptr_t)dqkv & 15)) return B200_ERR_UNSUPPORTED;
   if (N > 208) return B200_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
-  static int groups = -1;  // B200_ATTN_BWD_GROUPS = 2 (8 worker warps, default) | 4 (16 worker warps: each row's keys split four ways)
+  static int groups = -1;  // B200_ATTN_BWD_GROUPS = 4 (default; 16 worker warps: each row's keys split four ways) | 2 (8 worker warps)
   if (groups < 0) {
     const char* e = std::getenv("B200_ATTN_BWD_GROUPS");
-    groups = (e && e[0] == '4') ? 4 : 2;
+    groups = (e && e[0] == '2') ? 2 : 4;
   }
   if (groups == 4) {
     if (N <= 128) return launch_bwd<8, 4>(qkv, ld_tok, out, dout, ld_out, lse, B, N, 128 / N, h, scale, dqkv, ld_dtok, dqkv_colsum, s);

@@ -115,7 +115,7 @@ def _L():
 import os as _os
 
 # validated on hardware (tools/attn_check.py, tests/test_kernels_gpu.py); the defaults follow the measured A/B timings
-TC_ATTENTION_FWD = _os.environ.get("B200_TC_ATTN_FWD", "0") == "1"
+TC_ATTENTION_FWD = _os.environ.get("B200_TC_ATTN_FWD", "1") == "1"
 TC_ATTENTION_BWD = _os.environ.get("B200_TC_ATTN_BWD", "1") == "1"
 TC_ATTENTION_PACKED = _os.environ.get("B200_TC_ATTN_PACKED", "0") == "1"  # N <= 128: several images of one head per CTA
 
