@@ -1116,12 +1116,12 @@ struct Fwd7Cfg {
 template <int NKV16, int HALF>
 __device__ __forceinline__ void fwd7_worker(uint32_t tS, float* xmax, float* xsum, uint64_t* bar_s, uint64_t* bar_p, uint64_t* bar_o,
                                             int r, int q, int lane, int klo, int khi, bool all_inside, float sl2, float scale,
-                                            float* lse_row, __nv_bfloat16* orow) {
+                                            float* lse_row, __nv_bfloat16* orow, uint32_t ph = 0, uint64_t* bar_tfree = nullptr) {
   using C = Fwd7Cfg<NKV16>;
   constexpr int C0 = HALF ? C::HA : 0, NC = HALF ? C::HB : C::HA;
   uint32_t srow[NC * 8];
   uint32_t buf[16];
-  mbar_wait(bar_s, 0);
+  mbar_wait(bar_s, ph);
   tc_fence_after();
   // pass 1 (the only read of S): packed bf16 row half -> registers, row max on packed pairs
   uint32_t mx2 = 0xFF80FF80u;
@@ -1179,12 +1179,17 @@ __device__ __forceinline__ void fwd7_worker(uint32_t tS, float* xmax, float* xsu
   pair_bar_sync4(q);
   l += xsum[(HALF ^ 1) * 128 + r];
   if (HALF == 0 && lse_row) *lse_row = mx * scale + __logf(l);
-  mbar_wait(bar_o, 0);
+  mbar_wait(bar_o, ph);
   tc_fence_after();
   const float inv = 1.f / l;
   uint32_t ov[32];
   tmem_ld_32x32(tS + C::TM_O + HALF * 32, ov);
   tmem_ld_wait();
+  if (bar_tfree) {  // persistent schedule: the next tile's S may overwrite this TMEM region
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_tfree);
+  }
   if (orow) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -1294,6 +1299,162 @@ attn_fwd_tc7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       fwd7_worker<NKV16, 0>(tS, xmax, xsum, bar_s, bar_p, bar_o, r, q, lane, klo, khi, G == 1, scale * kLog2e, scale, lse_row, orow);
     else
       fwd7_worker<NKV16, 1>(tS, xmax, xsum, bar_s, bar_p, bar_o, r, q, lane, klo, khi, G == 1, scale * kLog2e, scale, lse_row, orow);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ====================================================================================================================
+// forward, schedule 8: schedule 7 in persistent CTAs (two per SM) with the next tile's Q / K and V prefetched
+// ====================================================================================================================
+// ncu on schedule 7 (profiles/r02_ncu_attn_tc7.txt): 24 % of the softmax warps' time is still the wait for the tile's TMA
+// loads + S (the two CTAs of an SM start together and stay in lock-step), 4 % the initial set-up barrier.  Q and K are dead
+// as soon as the S MMAs have retired -- early in a tile -- so the NEXT tile's Q and K are loaded right then into the same
+// buffers; V is dead once P V has retired, and the next V then has the whole softmax phase of the next tile to land.  Shared
+// memory stays at schedule 7's 69 KB; barriers, TMEM and tensor maps are set up once per CTA.
+template <int NKV16>
+__global__ void __launch_bounds__(Fwd7Cfg<NKV16>::THREADS, 2)
+attn_fwd_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, int B, int N, int G, int h,
+                    int tiles_per_group, int n_tiles_total, float scale, __nv_bfloat16* __restrict__ out, long long ld_out,
+                    float* __restrict__ lse) {
+  pdl_launch_dependents();
+  using C = Fwd7Cfg<NKV16>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* bar_qk = bars + 0;     // Q tile + K landed
+  uint64_t* bar_v = bars + 1;      // V landed
+  uint64_t* bar_s = bars + 2;      // S in TMEM (= the S MMAs have retired: Q / K buffers free)
+  uint64_t* bar_p = bars + 3;      // [2 halves] P columns stored (4 warps each)
+  uint64_t* bar_o = bars + 5;      // O complete (= P V retired: V buffer free)
+  uint64_t* bar_tfree = bars + 6;  // O drained by all 8 worker warps: the TMEM region may be overwritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* xmax = reinterpret_cast<float*>(smem + C::OFF_X);
+  float* xsum = xmax + 256;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(bar_qk, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 4);
+    mbar_init(bar_p + 1, 4);
+    mbar_init(bar_o, 1);
+    mbar_init(bar_tfree, 8);
+    fence_barrier_init();
+  }
+  if (warp == 8) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmKV);
+    }
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_mine = (n_tiles_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles blockIdx.x, + gridDim.x, ...
+  auto tile_coords = [&](int it, int& t, int& head, int& b0) {
+    const int w = blockIdx.x + it * gridDim.x;
+    t = w % tiles_per_group;
+    const int grp = w / tiles_per_group;
+    head = grp % h;
+    b0 = (grp / h) * G;
+  };
+
+  if (warp == 8) {
+    // ===================== control warp =====================
+    const uint32_t s0 = smem_u32(smem);
+    const uint64_t dq = smem_desc(s0, 16, 1024);
+    const uint64_t dk = smem_desc(s0 + C::OFF_K, 16, 1024);
+    const uint64_t dv = smem_desc(s0 + C::OFF_V, 64 * 128, 1024);
+    const uint32_t idesc_s = instr_desc(BLOCK_Q, C::NKV, 0, 0);
+    const uint32_t idesc_o = instr_desc(BLOCK_Q, HD, 0, 1);
+    auto load_qk = [&](int it) {
+      int t, head, b0;
+      tile_coords(it, t, head, b0);
+      mbar_expect_tx(bar_qk, TILE_BYTES + C::KV_BYTES);
+      tma_load_2d(smem, &tmQ, bar_qk, head * HD, b0 * N + t * BLOCK_Q);
+      tma_load_2d(smem + C::OFF_K, &tmKV, bar_qk, (h + head) * HD, b0 * N);
+    };
+    auto load_v = [&](int it) {
+      int t, head, b0;
+      tile_coords(it, t, head, b0);
+      mbar_expect_tx(bar_v, C::KV_BYTES);
+      tma_load_2d(smem + C::OFF_V, &tmKV, bar_v, (2 * h + head) * HD, b0 * N);
+    };
+    if (lane == 0 && n_mine > 0) {
+      load_qk(0);
+      load_v(0);
+    }
+    __syncwarp();
+    for (int it = 0; it < n_mine; ++it) {
+      const uint32_t ph = it & 1;
+      mbar_wait(bar_qk, ph);
+      if (it > 0) mbar_wait(bar_tfree, ph ^ 1);  // the previous tile's O has been read out of TMEM
+      tc_fence_after();
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks)
+          umma_f16(tmem_base, dq + (uint64_t)(ks * 2), dk + (uint64_t)(ks * 2), idesc_s, ks > 0 ? 1u : 0u);
+        umma_commit(bar_s);
+      }
+      __syncwarp();
+      if (it + 1 < n_mine) {  // Q / K of the next tile as soon as this tile's S MMAs have read the buffers
+        mbar_wait(bar_s, ph);
+        if (lane == 0) load_qk(it + 1);
+        __syncwarp();
+      }
+      mbar_wait(bar_v, ph);
+      for (int half = 0; half < 2; ++half) {
+        mbar_wait(bar_p + half, ph);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const int k0 = half ? C::HA : 0, k1 = half ? NKV16 : C::HA;
+#pragma unroll 1
+          for (int ks = k0; ks < k1; ++ks)
+            umma_f16_ts(tmem_base + C::TM_O, tmem_base + ks * 8, dv + (uint64_t)((ks * 16 * 128) >> 4), idesc_o, ks > 0 ? 1u : 0u);
+          if (half == 1) umma_commit(bar_o);
+        }
+        __syncwarp();
+      }
+      if (it + 1 < n_mine) {  // V of the next tile once P V has retired
+        mbar_wait(bar_o, ph);
+        if (lane == 0) load_v(it + 1);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== worker warps: lane quarter q, column half =====================
+    const int half = warp >> 2, q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t tS = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int it = 0; it < n_mine; ++it) {
+      int t, head, b0;
+      tile_coords(it, t, head, b0);
+      const int n_img = min(G, B - b0);
+      const int rows_valid = n_img * N;
+      const int m = t * BLOCK_Q + r;
+      const int img = min(m / N, n_img - 1);
+      const int klo = img * N, khi = klo + N;
+      const bool valid = m < rows_valid;
+      float* lse_row = (lse && valid) ? lse + ((size_t)(b0 + img) * h + head) * N + (m - klo) : nullptr;
+      __nv_bfloat16* orow = valid ? out + ((size_t)b0 * N + m) * ld_out + head * HD : nullptr;
+      if (half == 0)
+        fwd7_worker<NKV16, 0>(tS, xmax, xsum, bar_s, bar_p, bar_o, r, q, lane, klo, khi, G == 1, scale * kLog2e, scale, lse_row, orow,
+                              it & 1, bar_tfree);
+      else
+        fwd7_worker<NKV16, 1>(tS, xmax, xsum, bar_s, bar_p, bar_o, r, q, lane, klo, khi, G == 1, scale * kLog2e, scale, lse_row, orow,
+                              it & 1, bar_tfree);
+    }
   }
 
   tc_fence_before();
@@ -1829,6 +1990,34 @@ static int launch_fwd7(const void* qkv, long long ld_tok, int B, int N, int G, i
   return B200_OK;
 }
 
+template <int NKV16>
+static int launch_fwd8(const void* qkv, long long ld_tok, int B, int N, int G, int h, float scale, void* out, long long ld_out,
+                       float* lse, cudaStream_t s) {
+  using C = Fwd7Cfg<NKV16>;
+  CUtensorMap tmQ, tmKV;
+  int rc = tmap_rows(&tmQ, qkv, (long long)B * N, 3LL * h * HD, ld_tok, BLOCK_Q);
+  if (rc) return rc;
+  rc = tmap_rows(&tmKV, qkv, (long long)B * N, 3LL * h * HD, ld_tok, C::NKV);
+  if (rc) return rc;
+  static bool attr = false;
+  static int num_sms = 0;
+  if (!attr) {
+    if (cudaFuncSetAttribute(attn_fwd_tc8_kernel<NKV16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
+      return B200_ERR_CUDA;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    attr = true;
+  }
+  const int tiles = (G * N + BLOCK_Q - 1) / BLOCK_Q;
+  const int total = ((B + G - 1) / G) * h * tiles;
+  const int grid = total < 2 * num_sms ? total : 2 * num_sms;
+  launch_kernel(attn_fwd_tc8_kernel<NKV16>, grid, C::THREADS, C::SMEM_BYTES, s, tmQ, tmKV, B, N, G, h, tiles, total, scale,
+                (__nv_bfloat16*)out, ld_out, lse);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
 template <int NKV16, int NG>
 static int launch_bwd(const void* qkv, long long ld_tok, const void* out, const void* dout, long long ld_out, const float* lse, int B,
                       int N, int G, int h, float scale, void* dqkv, long long ld_dtok, float* colsum, cudaStream_t s) {
@@ -1870,7 +2059,12 @@ extern "C" int b200_attention_fwd_tc(const void* qkv, long long ld_tok, int B, i
   static int sched = -1;
   if (sched < 0) {
     const char* e = std::getenv("B200_ATTN_FWD_SCHEDULE");
-    sched = (e && e[0] >= '1' && e[0] <= '7') ? e[0] - '0' : 7;
+    sched = (e && e[0] >= '1' && e[0] <= '8') ? e[0] - '0' : 7;
+  }
+  if (sched == 8) {
+    if (N <= 128) return launch_fwd8<8>(qkv, ld_tok, B, N, 128 / N, h, scale, out, ld_out, lse, s);
+    if (N <= 208) return launch_fwd8<13>(qkv, ld_tok, B, N, 1, h, scale, out, ld_out, lse, s);
+    return launch_fwd8<16>(qkv, ld_tok, B, N, 1, h, scale, out, ld_out, lse, s);
   }
   if (sched == 7) {
     if (N <= 128) return launch_fwd7<8>(qkv, ld_tok, B, N, 128 / N, h, scale, out, ld_out, lse, s);
