@@ -160,6 +160,11 @@ int b200_block_masks(const int* targets, int B, int H, int W, int min_patches, i
                      float max_aspect, long long seed, const int* step_dev, unsigned char* masks, void* stream);
 int b200_collate_masks(const unsigned char* masks, int B, int Np, int cap, long long* idx, float* weight, float* row_w,
                        float* pad, int* m_valid, void* stream);
+/* Random batch subset of stochastic depth (drop_add_residual_stochastic_depth, LT/_models/dinov2_vit/dinov2_vit_src/
+ * layers/block.py:118-141: `torch.randperm(b)[:sample_subset_size]`): idx_out int64 [k] = a uniformly random k-subset of
+ * {0..n-1} in random order (the k smallest of n counter-based random keys; statistical parity, not torch's stream).
+ * *counter_dev (int64 in device memory) is read and incremented by the launch: graph replays draw fresh subsets.  n <= 2048. */
+int b200_random_subset(int n, int k, long long seed, long long* counter_dev, long long* idx_out, void* stream);
 /* Batch-subset stochastic depth (drop_add_residual_stochastic_depth, LT/_models/dinov2_vit/dinov2_vit_src/layers/block.py:118-141):
  * sample-granular copies of the fp32 residual stream, rows of row_elems floats (% 4 == 0).
  * scatter = 0: dst[j, :] = src[idx[j], :] (x[brange]);  scatter = 1: dst[idx[j], :] = src[j, :] (the index_add target rows). */

@@ -127,6 +127,7 @@ class DinoVisionTransformer(nn.Module):
         else:
             self.dpr = [x.item() for x in torch.linspace(0, drop_path_rate, depth)]  # vision_transformer.py:161-166
         self._dp_keep: dict = {}
+        self._subset_rng: dict = {}  # device -> (seed, launch counter int64[1] on the device): batch-subset stochastic depth
         self.prefix = prefix
         shapes = vit_param_shapes(embed_dim, depth, patch_size, in_chans, self.num_patches, self.hidden_dim,
                                   num_register_tokens, self.layerscale, self.swiglu)
@@ -444,9 +445,9 @@ class DinoVisionTransformer(nn.Module):
                 # drop_add_residual_stochastic_depth (layers/block.py:118-141): the branch runs on a random subset of
                 # b' = max(int(b*(1-r)), 1) samples and is added back with alpha = b/b'.
                 bsub = max(int(Bc * (1.0 - self.dpr[i])), 1)
-                # (random subset = the bsub smallest of Bc uniform draws: graph-capturable, unlike randperm/index_put)
-                idx1 = torch.rand(Bc, device=dev).argsort()[:bsub]
-                idx2 = torch.rand(Bc, device=dev).argsort()[:bsub]
+                # (random subset = the bsub smallest of Bc random keys: one small launch, graph-capturable -- the device-side
+                # counter advances on every replay -- unlike randperm / index_put)
+                idx1, idx2 = self._random_subset(Bc, bsub, dev), self._random_subset(Bc, bsub, dev)
                 if self.subset_skips_compute and self.dpr[i] >= self.subset_compact_min_rate:
                     # compact schedule: only the subset's rows go through the branch (20-30 % of the block FLOPs saved)
                     ckpt = save and self._activation_checkpointing and (i % self._activation_checkpointing_every_n_blocks == 0)
@@ -477,6 +478,24 @@ class DinoVisionTransformer(nn.Module):
         if save:
             ctx.meanf, ctx.rstdf = meanf, rstdf
         return ctx
+
+    def _random_subset(self, n: int, k: int, dev: torch.device) -> Tensor:
+        """int64 [k]: a uniformly random k-subset of range(n) (torch.randperm(n)[:k] of layers/block.py:125-127).  The RNG
+        state (seed drawn once from torch's CPU generator, so torch.manual_seed reproduces it; a launch counter in device
+        memory) is created on first use, which must not be inside a CUDA-graph capture (the step's eager warm-up comes first)."""
+        if n > 2048:
+            return torch.rand(n, device=dev).argsort()[:k]
+        key = str(dev)
+        st = self._subset_rng.get(key)
+        if st is None:
+            if dev.type == "cuda" and torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("stochastic-depth RNG state must be created before CUDA-graph capture (run one eager step first)")
+            rank = torch.distributed.get_rank() if (torch.distributed.is_available() and torch.distributed.is_initialized()) else 0
+            seed = (int(torch.randint(0, 2 ** 62, (1,)).item()) ^ (rank * 0x9E3779B97F4A7C15)) & ((1 << 62) - 1)
+            st = self._subset_rng[key] = (seed, torch.zeros(1, device=dev, dtype=torch.int64))
+        idx = torch.empty(k, device=dev, dtype=torch.int64)
+        ops.random_subset(n, k, st[0], st[1], idx)
+        return idx
 
     # ------------------------------------------------------------------ backward
     def _bwd(self, ctx: VitCtx, d_xnorm: Optional[Tensor], wgrad_splits: int = 0, stop_before: int = 0,

@@ -147,9 +147,46 @@ collate_masks_kernel(const unsigned char* __restrict__ masks, int B, int Np, int
   if (threadIdx.x == 0) *m_valid = M;
 }
 
+// Uniformly random k-subset of {0..n-1} in random order: the k smallest of n counter-based pseudo-random keys, ranked by
+// counting in one CTA (n <= 2048: at most 4 M comparisons).  Replaces `torch.randperm(b)[:k]` of
+// drop_add_residual_stochastic_depth (LT/_models/dinov2_vit/dinov2_vit_src/layers/block.py:125-127) -- a radix sort plus
+// three small launches (17 us) per residual branch -- with one ~2 us launch; *counter advances by one per launch, so CUDA-graph
+// replays draw fresh subsets.
+__global__ void __launch_bounds__(1024)
+random_subset_kernel(int n, int k, unsigned long long seed, long long* __restrict__ counter, long long* __restrict__ idx_out) {
+  B200_PDL_SYNC();
+  extern __shared__ unsigned long long keys[];
+  const unsigned long long ctr = (unsigned long long)*counter;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    Rng rng{seed * 0xD1B54A32D192ED03ull + ctr * 0x9E3779B97F4A7C15ull + (unsigned long long)i * 0xBF58476D1CE4E5B9ull};
+    keys[i] = rng.next();
+  }
+  __syncthreads();  // every thread has read *counter
+  if (threadIdx.x == 0) *counter = (long long)(ctr + 1);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const unsigned long long ki = keys[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const unsigned long long kj = keys[j];
+      rank += (kj < ki || (kj == ki && j < i)) ? 1 : 0;
+    }
+    if (rank < k) idx_out[rank] = i;
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" int b200_random_subset(int n, int k, long long seed, long long* counter_dev, long long* idx_out, void* stream) {
+  if (!counter_dev || !idx_out || n <= 0 || k <= 0 || k > n) return B200_ERR_INVALID_ARG;
+  if (n > 2048) return B200_ERR_UNSUPPORTED;
+  const int threads = n >= 1024 ? 1024 : ((n + 31) / 32) * 32;
+  launch_kernel(random_subset_kernel, 1, threads, (size_t)n * sizeof(unsigned long long), (cudaStream_t)stream, n, k,
+                (unsigned long long)seed, counter_dev, idx_out);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
 
 extern "C" int b200_block_masks(const int* targets, int B, int H, int W, int min_patches, int max_patches, float min_aspect,
                                 float max_aspect, long long seed, const int* step_dev, unsigned char* masks, void* stream) {

@@ -390,6 +390,12 @@ def block_masks(targets_i32, H: int, W: int, max_patches: int, seed: int, masks_
                                 _ptr(step_dev), masks_u8.data_ptr(), _stream()), "b200_block_masks")
 
 
+def random_subset(n: int, k: int, seed: int, counter, idx_i64) -> None:
+    """idx_i64[:k] = uniformly random k-subset of range(n) in random order; counter (int64 [1], device) += 1."""
+    _req_cuda(counter, idx_i64)
+    check(_L().b200_random_subset(n, k, seed, counter.data_ptr(), idx_i64.data_ptr(), _stream()), "b200_random_subset")
+
+
 def collate_masks(masks_u8, cap: int, idx_i64, weight, row_w, pad, m_valid) -> None:
     _req_cuda(masks_u8, idx_i64, weight, row_w, pad, m_valid)
     B, Np = masks_u8.shape

@@ -510,3 +510,35 @@ def test_swiglu_gate_fwd_bwd(T, H):
     torch.testing.assert_close(dx.float(), xr.grad.float(), rtol=2.4e-2, atol=2e-3)
     rel = (dx.float() - xr.grad.float()).norm() / xr.grad.float().norm()
     assert rel < 5e-3, rel
+
+
+@pytest.mark.parametrize("n,k", [(64, 51), (128, 89), (512, 358), (2048, 1433), (5, 1)])
+def test_random_subset(n, k):
+    """b200_random_subset vs the definition it replaces (torch.randperm(n)[:k], block.py:125-127): k distinct indices in
+    range, a fresh draw per launch (device-side counter), every element included with probability k / n."""
+    counter = torch.zeros(1, device=dev, dtype=torch.int64)
+    hits = torch.zeros(n, device=dev)
+    first = torch.zeros(n, device=dev)
+    prev = None
+    reps = 400
+    for i in range(reps):
+        idx = torch.empty(k, device=dev, dtype=torch.int64)
+        ops.random_subset(n, k, 1234, counter, idx)
+        assert int(idx.min()) >= 0 and int(idx.max()) < n and idx.unique().numel() == k
+        if prev is not None and k < n and n > 8:
+            assert not torch.equal(prev, idx)
+        prev = idx
+        hits[idx] += 1
+        first[idx[0]] += 1
+    assert int(counter) == reps
+    p = k / n
+    tol = 5 * (p * (1 - p) / reps) ** 0.5 + 1e-9
+    assert (hits / reps - p).abs().max().item() < tol                      # inclusion probability
+    if n >= 64:
+        assert first.max().item() < reps * (1.0 / n) + 6 * (reps / n) ** 0.5 + 2  # the leading element is uniform too
+    # same seed + same counter -> same subset (reproducibility under torch.manual_seed in the model)
+    c2 = torch.zeros(1, device=dev, dtype=torch.int64)
+    a = torch.empty(k, device=dev, dtype=torch.int64); ops.random_subset(n, k, 99, c2, a)
+    c3 = torch.zeros(1, device=dev, dtype=torch.int64)
+    b = torch.empty(k, device=dev, dtype=torch.int64); ops.random_subset(n, k, 99, c3, b)
+    assert torch.equal(a, b)

@@ -48,6 +48,8 @@ def stubbed(monkeypatch):
     monkeypatch.setattr(ops, "_L", lambda: fake)
     monkeypatch.setattr(ops, "_req_cuda", lambda *a: None)
     monkeypatch.setattr(ops, "_stream", lambda: 0)
+    # the one stubbed call whose OUTPUT steers host-side indexing: keep its indices in range
+    monkeypatch.setattr(ops, "random_subset", lambda n, k, seed, counter, idx: idx.copy_(torch.arange(k)))
     monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: _S())
     monkeypatch.setattr(torch.cuda, "Stream", lambda *a, **k: _S())
     monkeypatch.setattr(torch.cuda, "Event", lambda *a, **k: _E())
