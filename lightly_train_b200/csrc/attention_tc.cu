@@ -2053,13 +2053,14 @@ extern "C" int b200_attention_fwd_tc(const void* qkv, long long ld_tok, int B, i
   if (head_dim != HD || (ld_tok % 8) || (ld_out % 8) || ((uintptr_t)qkv & 15) || ((uintptr_t)out & 15)) return B200_ERR_UNSUPPORTED;
   if (N > 256) return B200_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
-  // B200_ATTN_FWD_SCHEDULE: 7 (default) P in tensor memory, one tile per CTA, two CTAs per SM: 46 us at 768 pairs x 197 tokens;
-  // 1 both tiles per CTA, P through shared memory (62 us); 3 one tile per CTA through shared memory (68 us); 4 persistent
-  // (72 us); 5 sixteen softmax warps (57 us) -- kept for A/B timing, all numerically identical (tools/attn_check.py)
+  // B200_ATTN_FWD_SCHEDULE: 8 (default) P in tensor memory, persistent CTAs (two per SM) with the next tile's Q / K / V
+  // prefetched: 41 us at 768 pairs x 197 tokens; 7 the same without persistence (45 us); 1 both tiles per CTA, P through shared
+  // memory (62 us); 3 one tile per CTA through shared memory (68 us); 4 persistent, P through shared memory (72 us); 5 sixteen
+  // softmax warps (57 us) -- kept for A/B timing, all numerically identical (tools/attn_check.py)
   static int sched = -1;
   if (sched < 0) {
     const char* e = std::getenv("B200_ATTN_FWD_SCHEDULE");
-    sched = (e && e[0] >= '1' && e[0] <= '8') ? e[0] - '0' : 7;
+    sched = (e && e[0] >= '1' && e[0] <= '8') ? e[0] - '0' : 8;
   }
   if (sched == 8) {
     if (N <= 128) return launch_fwd8<8>(qkv, ld_tok, B, N, 128 / N, h, scale, out, ld_out, lse, s);
