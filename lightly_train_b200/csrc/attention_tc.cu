@@ -1851,6 +1851,283 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
+// ====================================================================================================================
+// backward, schedule 2: key-tile-outer blocks, S and dP side by side in TMEM, ONE fused pass per block
+// ====================================================================================================================
+// The first backward walks the two query tiles of a pair one after the other through a single TMEM region that is S, then dP,
+// then dQ: five dependent phases per tile (MMA, softmax pass, MMA, dS pass, MMA) plus the dQ drain, 25 us per pair whatever the
+// number of softmax warps (129 us per 768-pair launch with 8 or 16 of them).  Here the pair is cut into key tiles (112 + the
+// rest) x query tiles:
+//   TMEM   S [0,112) | dP [112,224) | dK_j [224,288) | dV_j [288,352) | dQ_0 [352,416) | dQ_1 [416,480)
+//   block (i, j):  S = Q_i K_j^T and dP = dO_i V_j^T are issued TOGETHER (dP does not depend on P); one fused pass reads both,
+//                  p = 2^(s*sl2 - L), dS = p (dP - D), and writes P and dS (two smem tiles); then dV_j += P^T dO_i,
+//                  dK_j += dS^T Q_i, dQ_i += dS K_j are issued together.
+// Three dependent phases per block instead of six per tile, and the S / dP MMAs of block b+1 are issued as soon as the pass of
+// block b has read TMEM, i.e. they run under block b's second MMA group.  dK_j / dV_j are drained after the last query tile of
+// key tile j, dQ_0 / dQ_1 (accumulated over the key tiles in TMEM) at the end.  16 worker warps: 4 lane quarters x 4 column
+// groups (8-key units); one control warp.
+template <int NKV16>
+struct Bwd2Cfg {
+  static constexpr int NKV = NKV16 * 16;
+  static constexpr int NJ0 = 112, NJ1 = NKV - NJ0;          // keys per key tile
+  static constexpr int KV_BYTES = NKV * 128;
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_DO = 2 * TILE_BYTES;
+  static constexpr int OFF_K = 4 * TILE_BYTES;
+  static constexpr int OFF_V = OFF_K + KV_BYTES;
+  static constexpr int OFF_P = (OFF_V + KV_BYTES + 1023) / 1024 * 1024;   // P tile: 2 slabs of 64 keys
+  static constexpr int OFF_DS = OFF_P + 2 * TILE_BYTES;                    // dS tile: 2 slabs
+  static constexpr int OFF_F = OFF_DS + 2 * TILE_BYTES;                    // floats: L[256], D[256], colsum[192]
+  static constexpr int OFF_BAR = OFF_F + (256 + 256 + 192) * 4;
+  static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
+  static constexpr int THREADS = 17 * 32;
+  static constexpr int TM_S = 0, TM_DP = 112, TM_DK = 224, TM_DV = 288, TM_DQ = 352;
+  static_assert(NKV > 128 && NKV <= 224 && NJ1 % 16 == 0 && NJ1 >= 16, "two key tiles: 112 + (16 .. 112)");
+  static_assert(SMEM_BYTES <= 232448, "shared memory");
+};
+
+template <int NKV16>
+__global__ void __launch_bounds__(Bwd2Cfg<NKV16>::THREADS, 1)
+attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                    const __grid_constant__ CUtensorMap tmDO, const __nv_bfloat16* __restrict__ outp,
+                    const __nv_bfloat16* __restrict__ dout, long long ld_out, const float* __restrict__ lse, int B, int N, int h,
+                    float scale, __nv_bfloat16* __restrict__ dqkv, long long ld_dtok, float* __restrict__ colsum) {
+  pdl_launch_dependents();
+  using C = Bwd2Cfg<NKV16>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* sL = reinterpret_cast<float*>(smem + C::OFF_F);  // base-2 log-sum-exp per query row (+inf on padded rows)
+  float* sD = sL + 256;                                   // D_i = sum_d dO O
+  float* sC = sD + 256;                                   // column sums of dq | dk | dv
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* bar_load = bars + 0;
+  uint64_t* bar_sdp = bars + 1;      // S and dP of the current block in TMEM
+  uint64_t* bar_sfree = bars + 2;    // every worker warp has read them (16)
+  uint64_t* bar_pds = bars + 3;      // P and dS of the current block in smem (16)
+  uint64_t* bar_mma2 = bars + 4;     // dV / dK / dQ MMAs of the current block retired
+  uint64_t* bar_dkvfree = bars + 5;  // dK_j / dV_j drained (16): the accumulators may be overwritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x / h, head = blockIdx.x % h;  // one image x one head
+  const int n_tiles = (N + BLOCK_Q - 1) / BLOCK_Q;      // 2 (N > 128)
+  const int nb = 2 * n_tiles;                           // blocks: key tile j = blk / n_tiles, query tile i = blk % n_tiles
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_load, 1);
+    mbar_init(bar_sdp, 1);
+    mbar_init(bar_sfree, 16);
+    mbar_init(bar_pds, 16);
+    mbar_init(bar_mma2, 1);
+    mbar_init(bar_dkvfree, 16);
+    fence_barrier_init();
+  }
+  if (warp == 16) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmKV);
+      tma_prefetch_desc(&tmDO);
+    }
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem_base = *tmem_slot;
+  const size_t row0 = (size_t)b * N;
+
+  if (warp == 16) {
+    // ===================== control warp =====================
+    if (lane == 0) {
+      mbar_expect_tx(bar_load, 4 * TILE_BYTES + 2 * C::KV_BYTES);
+      tma_load_2d(smem + C::OFF_Q, &tmQ, bar_load, head * HD, (int)row0);
+      tma_load_2d(smem + C::OFF_Q + TILE_BYTES, &tmQ, bar_load, head * HD, (int)row0 + BLOCK_Q);
+      tma_load_2d(smem + C::OFF_DO, &tmDO, bar_load, head * HD, (int)row0);
+      tma_load_2d(smem + C::OFF_DO + TILE_BYTES, &tmDO, bar_load, head * HD, (int)row0 + BLOCK_Q);
+      tma_load_2d(smem + C::OFF_K, &tmKV, bar_load, (h + head) * HD, (int)row0);
+      tma_load_2d(smem + C::OFF_V, &tmKV, bar_load, (2 * h + head) * HD, (int)row0);
+    }
+    __syncwarp();
+    mbar_wait(bar_load, 0);
+    const uint32_t s0 = smem_u32(smem);
+    const uint64_t dP_mn = smem_desc(s0 + C::OFF_P, TILE_BYTES, 1024);    // A of dV: P^T, MN-major (M = keys), LBO = slab
+    const uint64_t dS_mn = smem_desc(s0 + C::OFF_DS, TILE_BYTES, 1024);   // A of dK: dS^T
+    const uint64_t dS_k = smem_desc(s0 + C::OFF_DS, 16, 1024);            // A of dQ: dS [q x keys], K-major, 64-key slabs
+    const uint32_t id_kv = instr_desc(BLOCK_Q, HD, 1, 1);                 // dV, dK: A MN-major, B MN-major
+    const uint32_t id_dq = instr_desc(BLOCK_Q, HD, 0, 1);                 // dQ
+    for (int blk = 0; blk < nb; ++blk) {
+      const uint32_t ph = blk & 1;
+      const int j = blk / n_tiles, i = blk % n_tiles;
+      const int nj = j ? C::NJ1 : C::NJ0;
+      const uint32_t koff = (uint32_t)(j * C::NJ0 * 128);                 // byte offset of key tile j's rows in K / V
+      const uint64_t dK_k = smem_desc(s0 + C::OFF_K + koff, 16, 1024);    // B of S: [keys x d], K-major
+      const uint64_t dV_k = smem_desc(s0 + C::OFF_V + koff, 16, 1024);    // B of dP
+      const uint64_t dK_mn = smem_desc(s0 + C::OFF_K + koff, 64 * 128, 1024);  // B of dQ: (K = keys, N = d), MN-major
+      const uint64_t dQi_k = smem_desc(s0 + C::OFF_Q + i * TILE_BYTES, 16, 1024);         // A of S
+      const uint64_t dQi_mn = smem_desc(s0 + C::OFF_Q + i * TILE_BYTES, 64 * 128, 1024);  // B of dK (K = q rows, N = d)
+      const uint64_t dOi_k = smem_desc(s0 + C::OFF_DO + i * TILE_BYTES, 16, 1024);        // A of dP
+      const uint64_t dOi_mn = smem_desc(s0 + C::OFF_DO + i * TILE_BYTES, 64 * 128, 1024); // B of dV
+      const uint32_t id_s = instr_desc(BLOCK_Q, nj, 0, 0);
+      if (blk > 0) {
+        mbar_wait(bar_sfree, ph ^ 1);  // the previous block's S / dP have been read
+        tc_fence_after();
+      }
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_f16(tmem_base + C::TM_S, dQi_k + (uint64_t)(ks * 2), dK_k + (uint64_t)(ks * 2), id_s, ks > 0 ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_f16(tmem_base + C::TM_DP, dOi_k + (uint64_t)(ks * 2), dV_k + (uint64_t)(ks * 2), id_s, ks > 0 ? 1u : 0u);
+        umma_commit(bar_sdp);
+      }
+      __syncwarp();
+      mbar_wait(bar_pds, ph);
+      if (i == 0 && j > 0) mbar_wait(bar_dkvfree, (j - 1) & 1);  // dK / dV of the previous key tile have been drained
+      tc_fence_after();
+      if (elect_one_sync()) {
+        // dV_j (+)= P^T dO_i, dK_j (+)= dS^T Q_i : M = 128 key lanes (lanes >= nj carry zeros / unused), K = 128 query rows
+#pragma unroll 1
+        for (int ks = 0; ks < 8; ++ks)
+          umma_f16(tmem_base + C::TM_DV, dP_mn + (uint64_t)((ks * 2048) >> 4), dOi_mn + (uint64_t)((ks * 2048) >> 4), id_kv,
+                   (i > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll 1
+        for (int ks = 0; ks < 8; ++ks)
+          umma_f16(tmem_base + C::TM_DK, dS_mn + (uint64_t)((ks * 2048) >> 4), dQi_mn + (uint64_t)((ks * 2048) >> 4), id_kv,
+                   (i > 0 || ks > 0) ? 1u : 0u);
+        // dQ_i (+)= dS K_j : K = nj keys in steps of 16
+#pragma unroll 1
+        for (int ks = 0; ks < nj / 16; ++ks)
+          umma_f16(tmem_base + C::TM_DQ + i * 64, dS_k + (uint64_t)(((ks >> 2) * TILE_BYTES + (ks & 3) * 32) >> 4),
+                   dK_mn + (uint64_t)((ks * 2048) >> 4), id_dq, (j > 0 || ks > 0) ? 1u : 0u);
+        umma_commit(bar_mma2);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== worker warps =====================
+    const int g = warp >> 2, q = warp & 3;   // g: column group of the fused pass / which accumulator columns this group drains
+    const int r = q * 32 + lane;             // row inside a 128-row tile == TMEM lane
+    const uint32_t tL = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float sl2 = scale * kLog2e;
+    uint8_t* sP = smem + C::OFF_P;
+    uint8_t* sS = smem + C::OFF_DS;
+    if (g < 2) {  // per-row constants of rows 0..255: base-2 LSE (+inf on rows past the sequence: p = 0 there) and D
+      const int m = g * BLOCK_Q + r;
+      float L = INFINITY, D = 0.f;
+      if (m < N) {
+        L = lse[((size_t)b * h + head) * N + m] * kLog2e;
+        const uint4* po = reinterpret_cast<const uint4*>(outp + (row0 + m) * ld_out + head * HD);
+        const uint4* pd = reinterpret_cast<const uint4*>(dout + (row0 + m) * ld_out + head * HD);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const uint4 a = __ldg(po + e), c = __ldg(pd + e);
+          const uint32_t aa[4] = {a.x, a.y, a.z, a.w}, cc[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const float2 x = unpack_bf16x2(aa[w]), y = unpack_bf16x2(cc[w]);
+            D = fmaf(x.x, y.x, D);
+            D = fmaf(x.y, y.y, D);
+          }
+        }
+      }
+      sL[m] = L;
+      sD[m] = D;
+      if (threadIdx.x < 192) sC[threadIdx.x] = 0.f;
+    }
+    named_bar_sync(1, 512);
+    for (int blk = 0; blk < nb; ++blk) {
+      const uint32_t ph = blk & 1;
+      const int j = blk / n_tiles, i = blk % n_tiles;
+      const int nu = (j ? C::NJ1 : C::NJ0) / 8;             // 8-key units of this key tile
+      const int u0 = (nu * g + 3) / 4, u1 = (nu * (g + 1) + 3) / 4;  // my units (at most 4)
+      const int key0 = j * C::NJ0;
+      const float L = sL[i * BLOCK_Q + r], D = sD[i * BLOCK_Q + r];
+      uint32_t pw[4][4], dw[4][4];
+      mbar_wait(bar_sdp, ph);
+      tc_fence_after();
+#pragma unroll
+      for (int uu = 0; uu < 4; ++uu) {
+        const int u = u0 + uu;
+        if (u < u1) {
+          uint32_t sv[8], dv[8];
+          tmem_ld_32x8(tL + C::TM_S + u * 8, sv);
+          tmem_ld_32x8(tL + C::TM_DP + u * 8, dv);
+          tmem_ld_wait();
+          const int kb = key0 + u * 8;
+          const bool full = kb + 8 <= N;                     // warp-uniform: only the last units of key tile 1 hold padded keys
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 s2 = unpack_bf16x2(pack_bf16x2(__uint_as_float(sv[2 * e]), __uint_as_float(sv[2 * e + 1])));
+            const float2 d2 = unpack_bf16x2(pack_bf16x2(__uint_as_float(dv[2 * e]), __uint_as_float(dv[2 * e + 1])));
+            float p0 = ex2_ftz(fmaf(s2.x, sl2, -L)), p1 = ex2_ftz(fmaf(s2.y, sl2, -L));
+            if (!full) {
+              if (kb + 2 * e >= N) p0 = 0.f;
+              if (kb + 2 * e + 1 >= N) p1 = 0.f;
+            }
+            const uint32_t pk = pack_bf16x2(p0, p1);
+            const float2 pr = unpack_bf16x2(pk);             // the bf16-rounded probability is what multiplies (autocast operand)
+            pw[uu][e] = pk;
+            dw[uu][e] = pack_bf16x2(pr.x * (d2.x - D), pr.y * (d2.y - D));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_sfree);
+      if (blk > 0) mbar_wait(bar_mma2, ph ^ 1);              // the previous block's MMAs have read the P / dS tiles
+#pragma unroll
+      for (int uu = 0; uu < 4; ++uu) {
+        const int u = u0 + uu;
+        if (u < u1) {
+          const uint32_t off = (uint32_t)((u >> 3) * TILE_BYTES) + swz(r, u & 7);
+          *reinterpret_cast<uint4*>(sP + off) = make_uint4(pw[uu][0], pw[uu][1], pw[uu][2], pw[uu][3]);
+          *reinterpret_cast<uint4*>(sS + off) = make_uint4(dw[uu][0], dw[uu][1], dw[uu][2], dw[uu][3]);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_pds);
+      if (i == n_tiles - 1) {
+        // ---- dK_j / dV_j complete: groups 0 / 1 drain dK columns [0,32) / [32,64), groups 2 / 3 dV (key row = TMEM lane)
+        mbar_wait(bar_mma2, ph);
+        tc_fence_after();
+        const int key = key0 + r;
+        const bool ok = r < (j ? C::NJ1 : C::NJ0) && key < N;
+        const int is_v = g >> 1, c = g & 1;
+        __nv_bfloat16* base = dqkv + (row0 + key) * ld_dtok + head * HD + (size_t)(1 + is_v) * h * HD;
+        drain_cols32(tL + (is_v ? C::TM_DV : C::TM_DK), c, is_v ? 1.f : scale, ok, base, colsum ? sC + 64 + 64 * is_v : nullptr, lane);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_dkvfree);
+      }
+    }
+    // ---- dQ_0 / dQ_1 (accumulated over the key tiles): groups 0 / 1 drain dQ_0 columns [0,32) / [32,64), groups 2 / 3 dQ_1
+    {
+      const int i = g >> 1, c = g & 1;
+      if (i < n_tiles) {
+        const int m = i * BLOCK_Q + r;
+        drain_cols32(tL + C::TM_DQ + i * 64, c, scale, m < N, dqkv + (row0 + m) * ld_dtok + head * HD, colsum ? sC : nullptr, lane);
+      }
+    }
+    named_bar_sync(1, 512);
+    if (colsum && threadIdx.x < 192) {
+      const int part = threadIdx.x >> 6, d = threadIdx.x & 63;
+      atomicAdd(colsum + (size_t)part * h * HD + head * HD + d, sC[threadIdx.x]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ---- host side (driver entry point resolved at run time, as in gemm_tcgen05.cu) --------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -2042,6 +2319,29 @@ static int launch_bwd(const void* qkv, long long ld_tok, const void* out, const 
   return B200_OK;
 }
 
+template <int NKV16>
+static int launch_bwd2(const void* qkv, long long ld_tok, const void* out, const void* dout, long long ld_out, const float* lse, int B,
+                       int N, int h, float scale, void* dqkv, long long ld_dtok, float* colsum, cudaStream_t s) {
+  using C = Bwd2Cfg<NKV16>;
+  CUtensorMap tmQ, tmKV, tmDO;
+  int rc = tmap_rows(&tmQ, qkv, (long long)B * N, 3LL * h * HD, ld_tok, BLOCK_Q);
+  if (rc) return rc;
+  rc = tmap_rows(&tmKV, qkv, (long long)B * N, 3LL * h * HD, ld_tok, C::NKV);
+  if (rc) return rc;
+  rc = tmap_rows(&tmDO, dout, (long long)B * N, (long long)h * HD, ld_out, BLOCK_Q);
+  if (rc) return rc;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(attn_bwd_tc2_kernel<NKV16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
+      return B200_ERR_CUDA;
+    attr = true;
+  }
+  launch_kernel(attn_bwd_tc2_kernel<NKV16>, B * h, C::THREADS, C::SMEM_BYTES, s, tmQ, tmKV, tmDO, (const __nv_bfloat16*)out,
+                (const __nv_bfloat16*)dout, ld_out, lse, B, N, h, scale, (__nv_bfloat16*)dqkv, ld_dtok, colsum);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
 }  // namespace attn_tc
 }  // namespace b200
 
@@ -2103,6 +2403,12 @@ extern "C" int b200_attention_bwd_tc(const void* qkv, long long ld_tok, const vo
   if (((uintptr_t)qkv & 15) || ((uintptr_t)out & 15) || ((uintptr_t)dout & 15) || ((uintptr_t)dqkv & 15)) return B200_ERR_UNSUPPORTED;
   if (N > 208) return B200_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
+  static int bsched = -1;  // B200_ATTN_BWD_SCHEDULE = 2: key-tile-outer blocks with one fused pass (N > 128); 1 (default): query-tile chain
+  if (bsched < 0) {
+    const char* e = std::getenv("B200_ATTN_BWD_SCHEDULE");
+    bsched = (e && e[0] == '2') ? 2 : 1;
+  }
+  if (bsched == 2 && N > 128) return launch_bwd2<13>(qkv, ld_tok, out, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, dqkv_colsum, s);
   static int groups = -1;  // B200_ATTN_BWD_GROUPS = 4 (default; 16 worker warps: each row's keys split four ways) | 2 (8 worker warps)
   if (groups < 0) {
     const char* e = std::getenv("B200_ATTN_BWD_GROUPS");
