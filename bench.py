@@ -421,12 +421,10 @@ def run_distill(args) -> None:
                              "traffic": None, "gemm_launches": len(prof), "gemm_ms_per_step": gms,
                              "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained"},
                 "cpu_baseline": None}
-        if diag:
+        if os.environ.get("B200_BENCH_DIAG_NO_ALLREDUCE", "0") == "1":
             line["diagnostic"] = "gradient all-reduce DISABLED (B200_BENCH_DIAG_NO_ALLREDUCE=1): not a training step, not a bench value"
         print(json.dumps(line), flush=True)
     if world > 1:
-        torch.cuda.synchronize()
-        method.release_graphs()  # captured NCCL kernels (B200_GRAPH_NCCL=1) must be gone before the communicator is
         dist.barrier()
         dist.destroy_process_group()
 
@@ -609,7 +607,7 @@ def main() -> None:
         ach = flops / (gemm_ms * 1e-3) / 1e12
         traffic = None
         tf = ROOT / "profiles" / "r02_gemm_traffic.json"  # dram bytes per launch from this round's `ncu --set full` capture
-        if tf.exists():
+        if tf.exists() and args.config == "cfg2" and B == cfg["batch"]:  # the capture is of this workload only
             traffic = json.loads(tf.read_text()).get("mean_dram_bytes_per_launch")
         roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all launches of one step)", "achieved": ach,
                     "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
@@ -685,7 +683,7 @@ def main() -> None:
             "host_ms_per_step": round(host_ms, 3), "loss": loss_val, "parity": parity,
             "roofline": roofline, "rooflines_hbm": rooflines_hbm, "cpu_baseline": cpu_baseline, "gpu_torch_baseline": gpu_torch_baseline,
         }
-        if diag:
+        if os.environ.get("B200_BENCH_DIAG_NO_ALLREDUCE", "0") == "1":
             line["diagnostic"] = "gradient all-reduce DISABLED (B200_BENCH_DIAG_NO_ALLREDUCE=1): not a training step, not a bench value"
         print(json.dumps(line), flush=True)
     if world > 1:
