@@ -1471,22 +1471,30 @@ attn_fwd_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 template <int NKV16, int NG = 2>
 struct BwdCfg {
   static constexpr int NKV = NKV16 * 16;                   // padded key count, <= 208
+  // NKV <= 128 (short sequences packed into ONE 128-row tile): one query tile, one key M-tile, half the P tile -- 99 KB of
+  // shared memory and 256 TMEM columns, so two CTAs share an SM (with NG = 2: 9 warps each)
+  static constexpr bool SMALL = NKV <= 128;
+  static constexpr int QT = SMALL ? 1 : 2;                 // query tiles held in smem
+  static constexpr int MT = SMALL ? 1 : 2;                 // 128-key M tiles of the dK / dV accumulators
+  static constexpr int P_SLABS = SMALL ? 2 : 4;            // 64-key slabs of the P / dS tile
   static constexpr int KV_BYTES = NKV * 128;
-  static constexpr int OFF_Q = 0;                          // two query tiles
-  static constexpr int OFF_DO = 2 * TILE_BYTES;            // two dO tiles
-  static constexpr int OFF_K = 4 * TILE_BYTES;
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_DO = QT * TILE_BYTES;
+  static constexpr int OFF_K = 2 * QT * TILE_BYTES;
   static constexpr int OFF_V = OFF_K + KV_BYTES;
-  static constexpr int OFF_P = (OFF_V + KV_BYTES + 1023) / 1024 * 1024;   // P / dS tile: 4 slabs of 64 keys
-  static constexpr int OFF_F = OFF_P + 4 * TILE_BYTES;     // floats: L[256], D[256], colsum[192]
+  static constexpr int OFF_P = (OFF_V + KV_BYTES + 1023) / 1024 * 1024;
+  static constexpr int OFF_F = OFF_P + P_SLABS * TILE_BYTES;   // floats: L[256], D[256], colsum[192]
   static constexpr int OFF_BAR = OFF_F + (256 + 256 + 192) * 4;
   static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
   static constexpr int WORKERS = 4 * NG;                   // worker warps: NG column groups x 4 lane quarters
   static constexpr int THREADS = (WORKERS + 1) * 32;       // + the control warp (the last one)
-  // TMEM columns: S / dP / dQ share [0, NKV); dK [256, 384): M tile 0 | 1; dV [384, 512)
-  static constexpr int TM_SDP = 0, TM_DK = 256, TM_DV = 384;
+  static constexpr int CTAS_PER_SM = (SMALL && NG == 2) ? 2 : 1;
+  // TMEM columns: S / dP / dQ share [0, NKV); dK: M tile 0 | 1; dV likewise
+  static constexpr int TM_SDP = 0, TM_DK = SMALL ? 128 : 256, TM_DV = SMALL ? 192 : 384;
+  static constexpr int TMEM_COLS = SMALL ? 256 : 512;
   __host__ __device__ static constexpr int qb(int g) { return (NKV16 * g + NG - 1) / NG; }   // column group g owns the 16-key chunks [qb(g), qb(g+1))
   static_assert(NKV <= 256, "S / dP tile");
-  static_assert(SMEM_BYTES <= 232448, "shared memory");
+  static_assert(CTAS_PER_SM * SMEM_BYTES <= 232448, "shared memory");
 };
 
 // column sums over the 32 rows held by a warp (one row per lane, 32 consecutive columns in v): butterfly transpose-
@@ -1617,7 +1625,7 @@ __device__ __forceinline__ void bwd_ds_pass(uint32_t tcol, uint8_t* sP, int r, f
 }
 
 template <int NKV16, int NG>
-__global__ void __launch_bounds__(BwdCfg<NKV16, NG>::THREADS, 1)
+__global__ void __launch_bounds__(BwdCfg<NKV16, NG>::THREADS, BwdCfg<NKV16, NG>::CTAS_PER_SM)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                    const __grid_constant__ CUtensorMap tmDO, const __nv_bfloat16* __restrict__ outp,
                    const __nv_bfloat16* __restrict__ dout, long long ld_out, const float* __restrict__ lse, int B, int N, int G,
@@ -1662,7 +1670,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tma_prefetch_desc(&tmKV);
       tma_prefetch_desc(&tmDO);
     }
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -1675,11 +1683,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == CTRL) {
     // ===================== control warp =====================
     if (lane == 0) {
-      mbar_expect_tx(bar_load, 4 * TILE_BYTES + 2 * C::KV_BYTES);
+      mbar_expect_tx(bar_load, 2 * C::QT * TILE_BYTES + 2 * C::KV_BYTES);
       tma_load_2d(smem + C::OFF_Q, &tmQ, bar_load, head * HD, (int)row0);
-      tma_load_2d(smem + C::OFF_Q + TILE_BYTES, &tmQ, bar_load, head * HD, (int)row0 + BLOCK_Q);
       tma_load_2d(smem + C::OFF_DO, &tmDO, bar_load, head * HD, (int)row0);
-      tma_load_2d(smem + C::OFF_DO + TILE_BYTES, &tmDO, bar_load, head * HD, (int)row0 + BLOCK_Q);
+      if (C::QT == 2) {
+        tma_load_2d(smem + C::OFF_Q + TILE_BYTES, &tmQ, bar_load, head * HD, (int)row0 + BLOCK_Q);
+        tma_load_2d(smem + C::OFF_DO + TILE_BYTES, &tmDO, bar_load, head * HD, (int)row0 + BLOCK_Q);
+      }
       tma_load_2d(smem + C::OFF_K, &tmKV, bar_load, (h + head) * HD, (int)row0);
       tma_load_2d(smem + C::OFF_V, &tmKV, bar_load, (2 * h + head) * HD, (int)row0);
     }
@@ -1716,7 +1726,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (elect_one_sync()) {
         // dV[mt] (+)= P^T dO_t : M = 128 keys of M tile mt (slabs 2mt, 2mt+1), K = 128 query rows in 8 steps of 16
 #pragma unroll 1
-        for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < C::MT; ++mt)
 #pragma unroll 1
           for (int ks = 0; ks < 8; ++ks)
             umma_f16(tmem_base + C::TM_DV + mt * 64, dP_mn + (uint64_t)((mt * 2 * TILE_BYTES + ks * 2048) >> 4),
@@ -1732,7 +1742,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_after();
       if (elect_one_sync()) {
 #pragma unroll 1
-        for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < C::MT; ++mt)
 #pragma unroll 1
           for (int ks = 0; ks < 8; ++ks)
             umma_f16(tmem_base + C::TM_DK + mt * 64, dP_mn + (uint64_t)((mt * 2 * TILE_BYTES + ks * 2048) >> 4),
@@ -1754,7 +1764,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const float sl2 = scale * kLog2e;
     uint8_t* sP = smem + C::OFF_P;
     // per-row constants: base-2 LSE and D_i = sum_d dO O straight from global (one 128-byte row per thread and tensor)
-    if (g < 2) {
+    if (g < C::QT) {
       const int m = g * BLOCK_Q + r;  // this thread prepares row m of the group (rows 0..255)
       float L = 0.f, D = 0.f;
       if (m < rows_valid) {
@@ -1776,8 +1786,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       sL[m] = L;
       sD[m] = D;
-      if (threadIdx.x < 192) sC[threadIdx.x] = 0.f;
     }
+    if (threadIdx.x < 192) sC[threadIdx.x] = 0.f;
     named_bar_sync(1, C::WORKERS * 32);
     for (int t = 0; t < n_tiles; ++t) {
       const uint32_t ph = t & 1;
@@ -1823,7 +1833,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // ---- dK / dV: keys on the lanes, two 128-key M tiles each; the last bar_dq completion covers every MMA issued
     mbar_wait(bar_dq, (n_tiles - 1) & 1);
     tc_fence_after();
-    if (NG == 2) {  // group g drains M tile g of both
+    if (NG == 2 && C::MT == 1) {  // one key M-tile: group 0 drains dK, group 1 dV
+      const bool ok = r < rows_valid;
+      __nv_bfloat16* base = dqkv + (row0 + r) * ld_dtok + head * HD + (size_t)(1 + g) * h * HD;
+      drain_tile(tL + (g ? C::TM_DV : C::TM_DK), g ? 1.f : scale, ok, base, colsum ? sC + 64 + 64 * g : nullptr, lane);
+    } else if (NG == 2) {  // group g drains M tile g of both
       const int key = g * BLOCK_Q + r;
       const bool ok = key < rows_valid;
       __nv_bfloat16* base = dqkv + (row0 + key) * ld_dtok + head * HD;
@@ -1847,7 +1861,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   if (warp == CTRL) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -2414,10 +2428,10 @@ extern "C" int b200_attention_bwd_tc(const void* qkv, long long ld_tok, const vo
     const char* e = std::getenv("B200_ATTN_BWD_GROUPS");
     groups = (e && e[0] == '2') ? 2 : 4;
   }
+  // N <= 128 (packed short sequences): one tile per CTA, 9 warps, two CTAs per SM
+  if (N <= 128) return launch_bwd<8, 2>(qkv, ld_tok, out, dout, ld_out, lse, B, N, 128 / N, h, scale, dqkv, ld_dtok, dqkv_colsum, s);
   if (groups == 4) {
-    if (N <= 128) return launch_bwd<8, 4>(qkv, ld_tok, out, dout, ld_out, lse, B, N, 128 / N, h, scale, dqkv, ld_dtok, dqkv_colsum, s);
     return launch_bwd<13, 4>(qkv, ld_tok, out, dout, ld_out, lse, B, N, 1, h, scale, dqkv, ld_dtok, dqkv_colsum, s);
   }
-  if (N <= 128) return launch_bwd<8, 2>(qkv, ld_tok, out, dout, ld_out, lse, B, N, 128 / N, h, scale, dqkv, ld_dtok, dqkv_colsum, s);
   return launch_bwd<13, 2>(qkv, ld_tok, out, dout, ld_out, lse, B, N, 1, h, scale, dqkv, ld_dtok, dqkv_colsum, s);
 }
