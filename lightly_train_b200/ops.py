@@ -117,7 +117,7 @@ import os as _os
 # validated on hardware (tools/attn_check.py, tests/test_kernels_gpu.py); the defaults follow the measured A/B timings
 TC_ATTENTION_FWD = _os.environ.get("B200_TC_ATTN_FWD", "1") == "1"
 TC_ATTENTION_BWD = _os.environ.get("B200_TC_ATTN_BWD", "1") == "1"
-TC_ATTENTION_PACKED = _os.environ.get("B200_TC_ATTN_PACKED", "0") == "1"  # N <= 128: several images of one head per CTA
+TC_ATTENTION_PACKED = _os.environ.get("B200_TC_ATTN_PACKED", "1") == "1"  # N <= 128: several images of one head per CTA
 
 
 def attention_fwd(qkv: torch.Tensor, B: int, N: int, h: int, out: torch.Tensor, lse: torch.Tensor | None,
