@@ -146,7 +146,8 @@ _UNVALIDATED = pytest.mark.skipif(__import__("os").environ.get("B200_TEST_UNVALI
                                   reason="kernel not yet validated on hardware this round: opt in with B200_TEST_UNVALIDATED=1")
 
 
-@pytest.mark.parametrize("B,N,h", [(3, 197, 6), (2, 201, 3), (5, 37, 2), (2, 256, 3), (2, 130, 2), (1, 16, 1)])
+@pytest.mark.parametrize("B,N,h", [(3, 197, 6), (2, 201, 3), (5, 37, 2), (2, 256, 3), (2, 130, 2), (1, 16, 1), (3, 128, 2), (4, 100, 1),
+                                   (7, 54, 3), (40, 197, 16)])
 def test_attention_fwd_tcgen05(B, N, h):
     """tcgen05 / TMEM / TMA forward (the product path for 128 < N <= 256) against the fp32 torch statement and against
     the warp-level kernel (P is rounded before normalisation here, so the two differ by bf16 rounding only)."""
@@ -155,11 +156,12 @@ def test_attention_fwd_tcgen05(B, N, h):
     out, ref = (torch.empty(B * N, D, device=dev, dtype=torch.bfloat16) for _ in range(2))
     lse, lse_ref = (torch.empty(B * h, N, device=dev) for _ in range(2))
     ops.attention_fwd_tc(qkv, B, N, h, out, lse, 0.125)
-    saved, ops.TC_ATTENTION_FWD = ops.TC_ATTENTION_FWD, False
+    saved = (ops.TC_ATTENTION_FWD, ops.TC_ATTENTION_PACKED)
+    ops.TC_ATTENTION_FWD = ops.TC_ATTENTION_PACKED = False  # the warp-level (mma.sync) kernel for every length
     try:
         ops.attention_fwd(qkv, B, N, h, ref, lse_ref, 0.125)
     finally:
-        ops.TC_ATTENTION_FWD = saved
+        ops.TC_ATTENTION_FWD, ops.TC_ATTENTION_PACKED = saved
     q5 = qkv.float().view(B, N, 3, h, 64).permute(2, 0, 3, 1, 4)
     s = (q5[0] * 0.125) @ q5[1].transpose(-1, -2)
     o = (s.softmax(-1) @ q5[2]).transpose(1, 2).reshape(B * N, D)
@@ -169,7 +171,8 @@ def test_attention_fwd_tcgen05(B, N, h):
     torch.testing.assert_close(lse, lse_ref, rtol=1e-5, atol=1e-4)
 
 
-@pytest.mark.parametrize("B,N,h", [(3, 197, 6), (2, 201, 3), (5, 37, 2), (2, 208, 1), (2, 130, 2)])
+@pytest.mark.parametrize("B,N,h", [(3, 197, 6), (2, 201, 3), (5, 37, 2), (2, 208, 1), (2, 130, 2), (3, 128, 2), (4, 100, 1), (7, 54, 3),
+                                   (1, 16, 1), (40, 197, 16)])
 def test_attention_bwd_tcgen05(B, N, h):
     """tcgen05 backward (the product path for 128 < N <= 208): dq | dk | dv against torch autograd (fp32) and against the
     warp-level kernel, and the fused qkv-bias gradient against the column sums of the bf16 dqkv it wrote."""
@@ -186,11 +189,12 @@ def test_attention_bwd_tcgen05(B, N, h):
     dq_t, dq_w = torch.full_like(qkv, 7.0), torch.empty_like(qkv)
     cs = torch.ones(3 * D, device=dev)
     ops.attention_bwd_tc(qkv, out, do, lse, B, N, h, dq_t, 0.125, colsum=cs)
-    saved, ops.TC_ATTENTION_BWD = ops.TC_ATTENTION_BWD, False
+    saved = (ops.TC_ATTENTION_BWD, ops.TC_ATTENTION_PACKED)
+    ops.TC_ATTENTION_BWD = ops.TC_ATTENTION_PACKED = False  # the warp-level (mma.sync) kernel for every length
     try:
         ops.attention_bwd(qkv, out, do, lse, B, N, h, dq_w, 0.125)
     finally:
-        ops.TC_ATTENTION_BWD = saved
+        ops.TC_ATTENTION_BWD, ops.TC_ATTENTION_PACKED = saved
     assert torch.isfinite(dq_t.float()).all()
     for sl in (slice(0, D), slice(D, 2 * D), slice(2 * D, 3 * D)):
         a, w, t = dq_t[:, sl].float(), dq_w[:, sl].float(), want[:, sl]

@@ -36,7 +36,7 @@ def check_fwd():
         lse, lse_ref = (torch.zeros(B * h, N, device=dev) for _ in range(2))
         ops.attention_fwd_tc(qkv, B, N, h, out, lse, 0.125)
         torch.cuda.synchronize()
-        ops.TC_ATTENTION_FWD = False
+        ops.TC_ATTENTION_FWD = ops.TC_ATTENTION_PACKED = False  # reference: the warp-level kernel for every length
         ops.attention_fwd(qkv, B, N, h, ref, lse_ref, 0.125)
         o, l, _ = ref_fwd_bwd(qkv, torch.zeros(B * N, D, device=dev), B, N, h)
         print(f"fwd B={B} N={N} h={h}: |out-torch| {(out.float() - o).abs().max().item():.4f}  |out-warp| "
