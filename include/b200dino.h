@@ -70,6 +70,22 @@ typedef struct b200_gemm_args {
 
 int b200_gemm(const b200_gemm_args* args, void* stream);
 
+/* LayerNorm as the A-operand prologue of a GEMM (north_star: "LayerNorm fused into the adjacent GEMM"):
+ *   C = epilogue( LayerNorm(x) @ B^T )   replaces  norm1 -> attn.qkv  and  norm2 -> mlp.fc1  of Block.forward,
+ *   LT/_models/dinov2_vit/dinov2_vit_src/layers/block.py:60-78,90-115 (nn.LayerNorm + nn.Linear under bf16 autocast).
+ * x: f32 [M, K] row pitch ldx (the residual stream); weight / bias: f32 [K]; the normalised rows are rounded to bf16 (what
+ * autocast feeds the Linear) and written straight into the swizzled shared-memory tiles the MMA reads.  Optional outputs:
+ * xn_out bf16 [M, K] (the wgrad GEMM of the backward reads it), mean / rstd f32 [M] (LayerNorm backward).
+ * args->A is ignored; K % 64 == 0 and K <= 384 (ViT-T / ViT-S); epi in {B200_EPI_BF16, B200_EPI_BIAS_GELU,
+ * B200_EPI_BIAS_GELU_DG}; b_mn = 0; block_n 0 (auto) | 128 | 192. */
+typedef struct b200_ln_args {
+  const float* x; long long ldx;
+  const float* weight; const float* bias; float eps;
+  void* xn_out; long long ld_xn;
+  float* mean; float* rstd;
+} b200_ln_args;
+int b200_ln_gemm(const b200_gemm_args* args, const b200_ln_args* ln, void* stream);
+
 /* Attention on the 5th-generation tensor cores (tcgen05.mma, fp32 accumulators in TMEM, TMA-staged operands):
  * same contracts as b200_attention_fwd / b200_attention_bwd below, for the global-crop sequence lengths
  * (forward N <= 256, backward N <= 208; lightly_train_b200/csrc/attention_tc.cu).  Replaces

@@ -36,6 +36,16 @@ class GemmArgs(C.Structure):
     ]
 
 
+class LnArgs(C.Structure):
+    """b200_ln_args (include/b200dino.h)."""
+    _fields_ = [
+        ("x", C.c_void_p), ("ldx", C.c_longlong),
+        ("weight", C.c_void_p), ("bias", C.c_void_p), ("eps", C.c_float),
+        ("xn_out", C.c_void_p), ("ld_xn", C.c_longlong),
+        ("mean", C.c_void_p), ("rstd", C.c_void_p),
+    ]
+
+
 class B200Error(RuntimeError):
     pass
 

@@ -24,6 +24,9 @@ from .. import ops
 from .._arena import Arena
 from .pos_embed import pos_embed_operator
 
+# LayerNorm as the A-operand prologue of the following GEMM (b200_ln_gemm; embed_dim <= 384): opt-in
+LN_GEMM = os.environ.get("B200_LN_GEMM", "0") == "1"
+
 
 def vit_param_shapes(embed_dim: int, depth: int, patch_size: int, in_chans: int, num_patches: int, hidden: int,
                      num_register_tokens: int, layerscale: bool, swiglu: bool = False) -> Dict[str, Tuple[int, ...]]:
@@ -208,6 +211,27 @@ class DinoVisionTransformer(nn.Module):
         return out, True
 
     # ------------------------------------------------------------------ one block forward (Block.forward, block.py:90-115)
+    def _ln_linear(self, x: Tensor, norm: str, wname: str, bname: str, out: Tensor, save: bool, epi: int = ops.EPI_BF16,
+                   out2: Optional[Tensor] = None):
+        """out = epi(Linear(LayerNorm(x))) -- norm1 -> attn.qkv and norm2 -> mlp.fc1 / w12 of Block.forward (block.py:90-115).
+        With B200_LN_GEMM=1 and embed_dim <= 384 the LayerNorm runs as the GEMM's A-operand prologue (b200_ln_gemm): the
+        normalised rows go straight into the MMA's shared-memory tiles; the bf16 copy + mean / rstd the backward needs are
+        side outputs (only when `save`).  Returns (xn | None, mean | None, rstd | None)."""
+        T, D = x.shape
+        dev = x.device
+        mean, rstd = (torch.empty(T, device=dev, dtype=torch.float32), torch.empty(T, device=dev, dtype=torch.float32)) if save \
+            else (None, None)
+        w, b = self._P(norm + "weight"), self._P(norm + "bias")
+        if LN_GEMM and D % 64 == 0 and D <= ops.LN_GEMM_MAX_K:
+            xn = torch.empty(T, D, device=dev, dtype=torch.bfloat16) if save else None
+            ops.ln_gemm(x, w, b, self.ln_eps, self._W(wname), out, epi=epi, bias=self._P(bname), out2=out2, xn_out=xn, mean=mean,
+                        rstd=rstd)
+            return xn, mean, rstd
+        xn = torch.empty(T, D, device=dev, dtype=torch.bfloat16)
+        ops.layernorm_fwd(x, w, b, self.ln_eps, xn, mean, rstd)
+        ops.gemm(xn, self._W(wname), out, epi=epi, bias=self._P(bname), out2=out2)
+        return xn, mean, rstd
+
     def _block_fwd(self, i: int, xcur: Tensor, Bc: int, N: int, rs1: Optional[Tensor], rs2: Optional[Tensor], save: bool) -> dict:
         dev = xcur.device
         D, Hd, h = self.embed_dim, self.hidden_dim, self.num_heads
@@ -216,11 +240,8 @@ class DinoVisionTransformer(nn.Module):
         E = lambda *s, dt=bf: torch.empty(*s, device=dev, dtype=dt)  # noqa: E731
         b = f"blocks.{i}."
         scale = 64 ** -0.5
-        mean1, rstd1 = (E(T, dt=f32), E(T, dt=f32)) if save else (None, None)
-        xn = E(T, D)
-        ops.layernorm_fwd(xcur, self._P(b + "norm1.weight"), self._P(b + "norm1.bias"), self.ln_eps, xn, mean1, rstd1)
         qkv = E(T, 3 * D)
-        ops.gemm(xn, self._W(b + "attn.qkv.weight"), qkv, bias=self._P(b + "attn.qkv.bias"))
+        xn, mean1, rstd1 = self._ln_linear(xcur, b + "norm1.", b + "attn.qkv.weight", b + "attn.qkv.bias", qkv, save)
         att = E(T, D)
         lse = E(Bc * h, N, dt=f32) if save else None
         ops.attention_fwd(qkv, Bc, N, h, att, lse, scale)
@@ -229,20 +250,17 @@ class DinoVisionTransformer(nn.Module):
         ops.gemm(att, self._W(b + "attn.proj.weight"), xmid, epi=ops.EPI_RESIDUAL, bias=self._P(b + "attn.proj.bias"),
                  out2=o1, aux=xcur, gamma=self._P(b + "ls1.gamma") if self.layerscale else None,
                  rowscale=rs1, rows_per_scale=N)
-        mean2, rstd2 = (E(T, dt=f32), E(T, dt=f32)) if save else (None, None)
-        xn2 = E(T, D)
-        ops.layernorm_fwd(xmid, self._P(b + "norm2.weight"), self._P(b + "norm2.bias"), self.ln_eps, xn2, mean2, rstd2)
         hh = E(T, Hd)
         if self.swiglu:
             u = E(T, 2 * Hd)  # x12 = w12(x): kept for the backward when saving
-            ops.gemm(xn2, self._W(b + "mlp.w12.weight"), u, bias=self._P(b + "mlp.w12.bias"))
+            xn2, mean2, rstd2 = self._ln_linear(xmid, b + "norm2.", b + "mlp.w12.weight", b + "mlp.w12.bias", u, save)
             ops.swiglu_fwd(u, hh)
             if not save:
                 u = None
         else:
-            u = E(T, Hd) if save else None
-            ops.gemm(xn2, self._W(b + "mlp.fc1.weight"), hh, epi=ops.EPI_BIAS_GELU_DG if save else ops.EPI_BIAS_GELU,
-                     bias=self._P(b + "mlp.fc1.bias"), out2=u)  # u holds gelu'(fc1 out) for the backward
+            u = E(T, Hd) if save else None  # u holds gelu'(fc1 out) for the backward
+            xn2, mean2, rstd2 = self._ln_linear(xmid, b + "norm2.", b + "mlp.fc1.weight", b + "mlp.fc1.bias", hh, save,
+                                                epi=ops.EPI_BIAS_GELU_DG if save else ops.EPI_BIAS_GELU, out2=u)
         o2 = E(T, D) if save else None
         xout = E(T, D, dt=f32)
         ops.gemm(hh, self._W(b + self._ffn_out + "weight"), xout, epi=ops.EPI_RESIDUAL, bias=self._P(b + self._ffn_out + "bias"),

@@ -186,6 +186,12 @@ __device__ __forceinline__ void load_aux_chunk(float4 (&aux4)[8], const char* au
 struct EpiSched {
   int w_begin, w_end, w_step, n_splits, tiles_m, tiles_n;  // tiles_n > 0: n-fastest tile order (generic kernel)
   int m_stride = BLOCK_M, m_off = 0;                       // CTA-pair kernel: 256-row tiles, this CTA's half at m_off
+  // LayerNorm-prologue kernel: the CTA walks whole units (row panels) of `unit_tiles` consecutive tiles; its k-th unit is
+  // unit_first + k * unit_stride and w counts the CTA's own tiles 0, 1, 2, ...
+  int unit_tiles = 0, unit_first = 0, unit_stride = 0;
+  __device__ __forceinline__ int tile_of(int w) const {
+    return unit_tiles > 0 ? (unit_first + (w / unit_tiles) * unit_stride) * unit_tiles + (w % unit_tiles) : w / n_splits;
+  }
 };
 
 template <int BLOCK_N, int EPI, bool TWO_SM = false>
@@ -215,7 +221,7 @@ __device__ __forceinline__ void epilogue_role(const GemmDev& p, const EpiSched& 
   int acc = 0;
   uint32_t acc_phase = 0;
   for (int w = sc.w_begin; w < sc.w_end; w += sc.w_step) {
-    const int tile = w / sc.n_splits;
+    const int tile = sc.tile_of(w);
     const int m0 = (sc.tiles_n > 0 ? tile / sc.tiles_n : tile % sc.tiles_m) * sc.m_stride + sc.m_off;
     const int n0 = (sc.tiles_n > 0 ? tile % sc.tiles_n : tile / sc.tiles_m) * BLOCK_N;
     const int row_first = m0 + quarter * 32 + sub_row;
@@ -241,7 +247,7 @@ __device__ __forceinline__ void epilogue_role(const GemmDev& p, const EpiSched& 
       // one chunk per warp in flight the fp32 residual stream was latency-bound (profiles/r01_gemm_stalls.md)
       const int wn = w + sc.w_step;
       if (wn < sc.w_end) {
-        const int tn = wn / sc.n_splits;
+        const int tn = sc.tile_of(wn);
         const int m0n = (sc.tiles_n > 0 ? tn / sc.tiles_n : tn % sc.tiles_m) * sc.m_stride + sc.m_off + quarter * 32;
         const int n0n = (sc.tiles_n > 0 ? tn % sc.tiles_n : tn / sc.tiles_m) * BLOCK_N + half * COLS_PER_WARP;
         constexpr int LINES = COLS_PER_WARP * AUX_ESIZE / 128;  // 128-byte lines per row slice (>= 1)
@@ -804,6 +810,226 @@ gemm_tcgen05_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------
+// LayerNorm as the GEMM's A-operand prologue (north_star: "LayerNorm fused into the adjacent GEMM").
+//   y = epilogue( LN(x) @ B^T ),  x fp32 [M, K] (the residual stream), K = embed dim <= 384 (ViT-S / ViT-T)
+// A-stationary: a CTA owns whole 128-row panels.  Four dedicated warps normalise the panel's fp32 rows (same arithmetic,
+// in the same order, as ln_fwd_kernel: two-pass mean / variance, rsqrt, affine, bf16 rounding) and write them straight
+// into the 128B-swizzled K-major tiles the MMA reads (one [128 x 64] tile per k-block, exactly the layout TMA would have
+// produced) -- the normalised activations never make a round trip through HBM on their way to the GEMM.  Optionally the
+// bf16 rows (student: the wgrad GEMM reads them later) and mean / rstd (LayerNorm backward) are also stored.  The B
+// operand (weights, [N, K] K-major) streams through a TMA ring; the MMA warp walks the panel's n-tiles; accumulators are
+// double-buffered in TMEM and drained by the shared epilogue role.  The panel is single-buffered (96 KB at K = 384), so the
+// normalisation of a CTA's next panel waits for the MMAs of the current one.
+template <int BLOCK_N>
+struct GemmLnCfg {
+  static constexpr int KB_MAX = 6;                             // K <= 384
+  static constexpr int A_TILE = BLOCK_M * BLOCK_K * 2;         // one k-block of the panel: 16 KB
+  static constexpr int PANEL_BYTES = KB_MAX * A_TILE;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int EPI_STAGING_BYTES = EpiCfg<BLOCK_N>::STAGING_BYTES;
+  static constexpr int BUDGET = 232448 - 1024 - 256 - PANEL_BYTES - EPI_STAGING_BYTES;
+  static constexpr int STAGES = BUDGET / B_BYTES > 6 ? 6 : BUDGET / B_BYTES;
+  static constexpr int LN_WARPS = 4;
+  static constexpr int THREADS = EpiCfg<BLOCK_N>::THREADS + LN_WARPS * 32;
+  static constexpr int ACC_STRIDE = 256;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int SMEM_BYTES = PANEL_BYTES + STAGES * B_BYTES + EPI_STAGING_BYTES + 1024 + 256;
+  static_assert(STAGES >= 2, "no room for the B ring next to the panel");
+};
+
+struct LnDev {
+  const float* x;
+  long long ldx;
+  const float* w;
+  const float* b;
+  float eps;
+  __nv_bfloat16* xn;   // optional bf16 copy of LN(x) [M, K]
+  long long ldxn;
+  float* mean;         // optional [M]
+  float* rstd;
+};
+
+template <int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(GemmLnCfg<BLOCK_N>::THREADS, 1)
+gemm_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const GemmDev p, const LnDev ln) {
+  pdl_launch_dependents();
+  using Cfg = GemmLnCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int EPW = EpiCfg<BLOCK_N>::WARPS;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* panel = smem;
+  uint8_t* ring = smem + Cfg::PANEL_BYTES;
+  float* epi_staging = reinterpret_cast<float*>(ring + STAGES * Cfg::B_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + STAGES * Cfg::B_BYTES + Cfg::EPI_STAGING_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* a_full = tmem_empty + 2;    // the panel holds LN(x) of the current unit (LN_WARPS arrivals)
+  uint64_t* a_empty = a_full + 1;       // every MMA that reads the panel has retired
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(a_empty + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int kb_total = p.K / BLOCK_K;                       // K % 64 == 0, <= KB_MAX (checked on the host)
+  const int n_units = (tiles_m - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // panels blockIdx.x, + gridDim.x, ...
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPW); }
+    mbar_init(a_full, Cfg::LN_WARPS);
+    mbar_init(a_empty, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmB);
+  if (warp == 1) { tmem_alloc(tmem_base_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer: B tiles of every (unit, n-tile, k-block) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int u = 0; u < n_units; ++u) {
+      for (int nt = 0; nt < tiles_n; ++nt) {
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (lane == 0) {
+            mbar_expect_tx(&full_bar[stage], Cfg::B_BYTES);
+            tma_load_2d(ring + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, nt * BLOCK_N);
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc(BLOCK_N, 0, 0);
+    const uint64_t adesc_base = make_smem_desc(smem_u32(panel), 16, 1024);
+    const uint64_t bdesc_base = make_smem_desc(smem_u32(ring), 16, 1024);
+    constexpr uint32_t kstep = (UMMA_K * 2) >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int u = 0; u < n_units; ++u) {
+      mbar_wait(a_full, u & 1);
+      tc_fence_after();
+      for (int nt = 0; nt < tiles_n; ++nt) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * Cfg::ACC_STRIDE;
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t ad = adesc_base + (uint64_t)((kb * Cfg::A_TILE) >> 4);
+          const uint64_t bd = bdesc_base + (uint64_t)((stage * Cfg::B_BYTES) >> 4);
+          if (elect_one_sync()) {
+            umma_f16(tmem_d, ad, bd, idesc, (kb > 0) ? 1u : 0u);
+            umma_f16(tmem_d, ad + kstep, bd + kstep, idesc, 1u);
+            umma_f16(tmem_d, ad + 2 * kstep, bd + 2 * kstep, idesc, 1u);
+            umma_f16(tmem_d, ad + 3 * kstep, bd + 3 * kstep, idesc, 1u);
+            umma_commit(&empty_bar[stage]);
+            if (kb == kb_total - 1) {
+              umma_commit(&tmem_full[acc]);
+              if (nt == tiles_n - 1) umma_commit(a_empty);
+            }
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if ((acc ^= 1) == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp < 2 + EPW) {
+    // ===================== epilogue warps =====================
+    const int ew = warp - 2;
+    EpiSched sc{0, n_units * tiles_n, 1, 1, tiles_m, tiles_n};
+    sc.unit_tiles = tiles_n;
+    sc.unit_first = (int)blockIdx.x;
+    sc.unit_stride = (int)gridDim.x;
+    epilogue_role<BLOCK_N, EPI>(p, sc, tmem_base, tmem_full, tmem_empty, warp & 3, ew >> 2, lane, epi_staging + ew * (32 * 32));
+  } else {
+    // ===================== LayerNorm warps: rows lw*32 .. lw*32+31 of every panel =====================
+    const int lw = warp - 2 - EPW;
+    const int D = p.K, nv = D >> 2;
+    float4 gw[3], gb[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int c = lane + 32 * j;
+      gw[j] = c < nv ? __ldg(reinterpret_cast<const float4*>(ln.w) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      gb[j] = c < nv ? __ldg(reinterpret_cast<const float4*>(ln.b) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int u = 0; u < n_units; ++u) {
+      const int m0 = ((int)blockIdx.x + u * (int)gridDim.x) * BLOCK_M;
+      if (u > 0) mbar_wait(a_empty, (u - 1) & 1);  // the previous panel's MMAs have retired
+#pragma unroll 2
+      for (int rr = 0; rr < 32; ++rr) {
+        const int r = lw * 32 + rr;                // row inside the panel
+        const int row = m0 + r;
+        float4 v[3];
+        float s = 0.f;
+        if (row < p.M) {
+          const float4* xr = reinterpret_cast<const float4*>(ln.x + (size_t)row * ln.ldx);
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const int c = lane + 32 * j;
+            if (c < nv) { v[j] = xr[c]; s += v[j].x + v[j].y + v[j].z + v[j].w; }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const float mu = warp_sum(s) / D;
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int c = lane + 32 * j;
+          if (c < nv) {
+            const float a = v[j].x - mu, bb = v[j].y - mu, cc = v[j].z - mu, d = v[j].w - mu;
+            q += a * a + bb * bb + cc * cc + d * d;
+          }
+        }
+        const float rs = rsqrtf(warp_sum(q) / D + ln.eps);
+        if (lane == 0 && row < p.M) {
+          if (ln.mean) ln.mean[row] = mu;
+          if (ln.rstd) ln.rstd[row] = rs;
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int c = lane + 32 * j;             // float4 index: columns 4c .. 4c+3
+          if (c < nv) {
+            uint2 pk;
+            if (row < p.M) {
+              pk.x = pack_bf16x2((v[j].x - mu) * rs * gw[j].x + gb[j].x, (v[j].y - mu) * rs * gw[j].y + gb[j].y);
+              pk.y = pack_bf16x2((v[j].z - mu) * rs * gw[j].z + gb[j].z, (v[j].w - mu) * rs * gw[j].w + gb[j].w);
+              if (ln.xn) reinterpret_cast<uint2*>(ln.xn + (size_t)row * ln.ldxn)[c] = pk;
+            } else {
+              pk = make_uint2(0u, 0u);             // rows past M: zeros (their outputs are never stored)
+            }
+            // column 4c -> k-block (4c)/64 = c/16, 16-byte chunk ((4c)%64)/8 = (c%16)/2, 8-byte half c&1
+            const int kb = c >> 4, chunk = (c & 15) >> 1;
+            *reinterpret_cast<uint2*>(panel + kb * Cfg::A_TILE + r * 128 + ((chunk ^ (r & 7)) << 4) + (c & 1) * 8) = pk;
+          }
+        }
+      }
+      fence_proxy_async();  // the MMAs (async proxy) read what these threads wrote through the generic proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
+// ---------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                     CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -1010,7 +1236,72 @@ static int launch_gemm_2sm(const b200_gemm_args* a, cudaStream_t stream) {
 #undef B200_CALL
 }
 
+template <int BLOCK_N, int EPI>
+static int launch_gemm_ln_epi(const b200_gemm_args* a, const b200_ln_args* l, cudaStream_t stream) {
+  using Cfg = GemmLnCfg<BLOCK_N>;
+  CUtensorMap tmB;
+  int rc = make_tmap(&tmB, a->B, a->N, a->K, a->ldb, BLOCK_K, BLOCK_N);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_ln_tcgen05_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=
+        cudaSuccess)
+      return B200_ERR_CUDA;
+    attr_set = true;
+  }
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  GemmDev p;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.a_mn = 0; p.b_mn = 0;
+  p.splits = 1;
+  p.epi = a->epi;
+  p.alpha = a->alpha;
+  p.C = a->C; p.ldc = a->ldc;
+  p.C2 = a->C2; p.ldc2 = a->ldc2;
+  p.aux = nullptr; p.ldaux = 0;
+  p.bias = a->bias; p.gamma = nullptr;
+  p.rowscale = nullptr; p.rows_per_scale = 1;
+  LnDev ln;
+  ln.x = l->x; ln.ldx = l->ldx; ln.w = l->weight; ln.b = l->bias; ln.eps = l->eps;
+  ln.xn = (__nv_bfloat16*)l->xn_out; ln.ldxn = l->ld_xn; ln.mean = l->mean; ln.rstd = l->rstd;
+  const int tiles_m = (a->M + BLOCK_M - 1) / BLOCK_M;
+  const int grid = tiles_m < g_num_sms ? tiles_m : g_num_sms;
+  launch_kernel(gemm_ln_tcgen05_kernel<BLOCK_N, EPI>, grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream, tmB, p, ln);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+
 }  // namespace b200
+
+// y = epilogue(LayerNorm(x) @ B^T): LayerNorm as the A-operand prologue of the GEMM (K = embed dim, K % 64 == 0, K <= 384).
+extern "C" int b200_ln_gemm(const b200_gemm_args* a, const b200_ln_args* l, void* stream) {
+  using namespace b200;
+  if (!a || !l || !a->B || !a->C || !l->x || !l->weight || !l->bias) return B200_ERR_INVALID_ARG;
+  if (a->M <= 0 || a->N <= 0 || a->K <= 0) return B200_ERR_INVALID_ARG;
+  if ((a->K % BLOCK_K) || a->K > GemmLnCfg<128>::KB_MAX * BLOCK_K) return B200_ERR_UNSUPPORTED;
+  if (a->a_mn || a->b_mn || a->splits > 1) return B200_ERR_UNSUPPORTED;
+  if ((a->ldb % 8) || (a->N % 8) || (a->ldc % 8) || (l->ldx % 4) || (a->C2 && (a->ldc2 % 8)) || (l->xn_out && (l->ld_xn % 4)))
+    return B200_ERR_UNSUPPORTED;
+  if (((uintptr_t)a->B & 15) || ((uintptr_t)a->C & 15) || ((uintptr_t)l->x & 15)) return B200_ERR_UNSUPPORTED;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int bn = a->block_n ? a->block_n : (a->epi == B200_EPI_BF16 ? 128 : 192);
+  switch (a->epi) {
+    case B200_EPI_BF16:
+      return bn == 192 ? launch_gemm_ln_epi<192, B200_EPI_BF16>(a, l, s) : launch_gemm_ln_epi<128, B200_EPI_BF16>(a, l, s);
+    case B200_EPI_BIAS_GELU:
+      return bn == 192 ? launch_gemm_ln_epi<192, B200_EPI_BIAS_GELU>(a, l, s) : launch_gemm_ln_epi<128, B200_EPI_BIAS_GELU>(a, l, s);
+    case B200_EPI_BIAS_GELU_DG:
+      return bn == 192 ? launch_gemm_ln_epi<192, B200_EPI_BIAS_GELU_DG>(a, l, s)
+                       : launch_gemm_ln_epi<128, B200_EPI_BIAS_GELU_DG>(a, l, s);
+    default:
+      return B200_ERR_UNSUPPORTED;
+  }
+}
 
 extern "C" int b200_gemm(const b200_gemm_args* a, void* stream) {
   using namespace b200;

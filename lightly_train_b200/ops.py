@@ -93,6 +93,48 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn: bool = Fa
     return out
 
 
+LN_GEMM_MAX_K = 384  # b200_ln_gemm: K % 64 == 0 and K <= 384 (the 128 x K bf16 panel stays resident in shared memory)
+
+
+def ln_gemm(x: torch.Tensor, ln_w: torch.Tensor, ln_b: torch.Tensor, eps: float, b: torch.Tensor, out: torch.Tensor, *,
+            epi: int = EPI_BF16, bias: torch.Tensor | None = None, out2: torch.Tensor | None = None,
+            xn_out: torch.Tensor | None = None, mean: torch.Tensor | None = None, rstd: torch.Tensor | None = None,
+            block_n: int = 0) -> torch.Tensor:
+    """out[M,N] = epi(LayerNorm(x)[M,K] @ B[N,K]^T): the LayerNorm is the GEMM's A-operand prologue (x f32, B bf16).
+    xn_out (bf16 [M,K]) / mean / rstd (f32 [M]): optional side outputs for the backward."""
+    _req_cuda(x, ln_w, ln_b, b, out, bias, out2, xn_out, mean, rstd)
+    assert x.dtype == torch.float32 and b.dtype == torch.bfloat16 and x.dim() == 2 and b.dim() == 2
+    assert x.stride(1) == 1 and b.stride(1) == 1 and out.stride(-1) == 1
+    M, K = x.shape
+    N, Kb = b.shape
+    assert K == Kb and out.shape[0] == M and out.shape[1] == N
+    g = GemmArgs()
+    g.A, g.lda, g.a_mn = None, 0, 0
+    g.B, g.ldb, g.b_mn = b.data_ptr(), b.stride(0), 0
+    g.M, g.N, g.K = M, N, K
+    g.splits, g.epi, g.block_n, g.alpha, g.ws_mode = 1, epi, block_n, 1.0, 0
+    g.C, g.ldc = out.data_ptr(), out.stride(0)
+    if out2 is not None:
+        g.C2, g.ldc2 = out2.data_ptr(), out2.stride(0)
+    g.bias = _ptr(bias)
+    ln = _lib.LnArgs()
+    ln.x, ln.ldx = x.data_ptr(), x.stride(0)
+    ln.weight, ln.bias, ln.eps = ln_w.data_ptr(), ln_b.data_ptr(), eps
+    if xn_out is not None:
+        ln.xn_out, ln.ld_xn = xn_out.data_ptr(), xn_out.stride(0)
+    ln.mean, ln.rstd = _ptr(mean), _ptr(rstd)
+    if GEMM_PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(_lib.lib().b200_ln_gemm(C.byref(g), C.byref(ln), _stream()), "b200_ln_gemm")
+        e1.record()
+        GEMM_PROFILE.append((2.0 * M * N * K, e0, e1))
+        GEMM_PROFILE_KEYS.append((M, N, K, 0, 0, epi, -1))
+        return out
+    check(_lib.lib().b200_ln_gemm(C.byref(g), C.byref(ln), _stream()), "b200_ln_gemm")
+    return out
+
+
 class AdamWArgs(C.Structure):
     _fields_ = [
         ("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("t", C.c_void_p),

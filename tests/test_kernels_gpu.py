@@ -546,3 +546,44 @@ def test_random_subset(n, k):
     c3 = torch.zeros(1, device=dev, dtype=torch.int64)
     b = torch.empty(k, device=dev, dtype=torch.int64); ops.random_subset(n, k, 99, c3, b)
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("M,K,N,epi,bn", [(1000, 384, 1152, "bf16", 0), (1000, 384, 1152, "bf16", 192), (300, 192, 576, "bf16", 0),
+                                          (1000, 384, 1536, "gelu", 0), (1000, 384, 1536, "gelu_dg", 0), (129, 384, 1536, "gelu_dg", 128),
+                                          (18944, 384, 1152, "bf16", 0)])
+def test_ln_gemm_prologue(M, K, N, epi, bn):
+    """b200_ln_gemm (LayerNorm as the GEMM's A-operand prologue) against the two-kernel path it replaces (b200_layernorm_fwd
+    -> b200_gemm) and against torch: same normalised rows (bit-exact side outputs), same GEMM result up to accumulation order."""
+    x = rnd(M, K, scale=2.0, seed=40) + 0.3
+    lw, lb = 1.0 + rnd(K, scale=0.2, seed=41), rnd(K, scale=0.1, seed=42)
+    w = rnd(N, K, dtype=torch.bfloat16, scale=0.05, seed=43)
+    bias = rnd(N, scale=0.1, seed=44)
+    code = {"bf16": ops.EPI_BF16, "gelu": ops.EPI_BIAS_GELU, "gelu_dg": ops.EPI_BIAS_GELU_DG}[epi]
+    # two-kernel reference
+    xn_ref = torch.empty(M, K, device=dev, dtype=torch.bfloat16)
+    mean_ref, rstd_ref = torch.empty(M, device=dev), torch.empty(M, device=dev)
+    ops.layernorm_fwd(x, lw, lb, 1e-6, xn_ref, mean_ref, rstd_ref)
+    out_ref = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    out2_ref = torch.empty(M, N, device=dev, dtype=torch.bfloat16) if epi == "gelu_dg" else None
+    ops.gemm(xn_ref, w, out_ref, epi=code, bias=bias, out2=out2_ref)
+    # fused
+    xn = torch.full((M, K), 7.0, device=dev, dtype=torch.bfloat16)
+    mean, rstd = torch.empty(M, device=dev), torch.empty(M, device=dev)
+    out = torch.full((M, N), 7.0, device=dev, dtype=torch.bfloat16)
+    out2 = torch.full((M, N), 7.0, device=dev, dtype=torch.bfloat16) if epi == "gelu_dg" else None
+    ops.ln_gemm(x, lw, lb, 1e-6, w, out, epi=code, bias=bias, out2=out2, xn_out=xn, mean=mean, rstd=rstd, block_n=bn)
+    torch.cuda.synchronize()
+    assert torch.equal(xn, xn_ref) and torch.equal(mean, mean_ref) and torch.equal(rstd, rstd_ref)
+    torch.testing.assert_close(out.float(), out_ref.float(), rtol=1.6e-2, atol=2e-3)  # <= 2 bf16 ulp
+    assert (out.float() - out_ref.float()).abs().mean().item() < 1e-4
+    if out2 is not None:
+        torch.testing.assert_close(out2.float(), out2_ref.float(), rtol=1.6e-2, atol=2e-3)
+    # without the side outputs (teacher / recompute): same product
+    out_b = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    ops.ln_gemm(x, lw, lb, 1e-6, w, out_b, epi=code, bias=bias, block_n=bn)
+    assert torch.equal(out_b, out)
+    # torch statement (fp32 LayerNorm, bf16-rounded activations and weights, fp32 accumulate)
+    y = torch.nn.functional.layer_norm(x, (K,), lw, lb, 1e-6).bfloat16().float() @ w.float().t() + bias
+    if epi != "bf16":
+        y = torch.nn.functional.gelu(y.bfloat16().float())
+    torch.testing.assert_close(out.float(), y, rtol=2e-2, atol=2e-2)
