@@ -24,8 +24,22 @@ from .. import ops
 from .._arena import Arena
 from .pos_embed import pos_embed_operator
 
-# LayerNorm as the A-operand prologue of the following GEMM (b200_ln_gemm; embed_dim <= 384): opt-in
-LN_GEMM = os.environ.get("B200_LN_GEMM", "0") == "1"
+# LayerNorm as the A-operand prologue of the following GEMM (b200_ln_gemm; embed_dim <= 384):
+#   "0" never | "1" whenever supported | "auto" only when every CTA gets at most one 128-row panel (a second panel's
+#   normalisation cannot overlap the first one's MMAs: the panel is single-buffered)
+LN_GEMM = os.environ.get("B200_LN_GEMM", "0")
+_NUM_SMS: Dict[str, int] = {}
+
+
+def _ln_gemm_wanted(T: int, D: int, dev: torch.device) -> bool:
+    if LN_GEMM == "0" or D % 64 != 0 or D > ops.LN_GEMM_MAX_K or dev.type != "cuda":
+        return False
+    if LN_GEMM == "1":
+        return True
+    key = str(dev)
+    if key not in _NUM_SMS:
+        _NUM_SMS[key] = torch.cuda.get_device_properties(dev).multi_processor_count
+    return (T + 127) // 128 <= _NUM_SMS[key]
 
 
 def vit_param_shapes(embed_dim: int, depth: int, patch_size: int, in_chans: int, num_patches: int, hidden: int,
@@ -222,7 +236,7 @@ class DinoVisionTransformer(nn.Module):
         mean, rstd = (torch.empty(T, device=dev, dtype=torch.float32), torch.empty(T, device=dev, dtype=torch.float32)) if save \
             else (None, None)
         w, b = self._P(norm + "weight"), self._P(norm + "bias")
-        if LN_GEMM and D % 64 == 0 and D <= ops.LN_GEMM_MAX_K:
+        if _ln_gemm_wanted(T, D, dev):
             xn = torch.empty(T, D, device=dev, dtype=torch.bfloat16) if save else None
             ops.ln_gemm(x, w, b, self.ln_eps, self._W(wname), out, epi=epi, bias=self._P(bname), out2=out2, xn_out=xn, mean=mean,
                         rstd=rstd)

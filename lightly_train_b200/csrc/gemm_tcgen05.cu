@@ -957,71 +957,83 @@ gemm_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const GemmDev p,
     epilogue_role<BLOCK_N, EPI>(p, sc, tmem_base, tmem_full, tmem_empty, warp & 3, ew >> 2, lane, epi_staging + ew * (32 * 32));
   } else {
     // ===================== LayerNorm warps: rows lw*32 .. lw*32+31 of every panel =====================
+    // The panel's fp32 rows (196 KB at K = 384) are latency-bound if read row by row (first version: 40 us per panel).  Each
+    // warp first asks L2 for ALL of its 32 rows (prefetch.global.L2: no registers held), then walks them four rows at a
+    // time (12 float4 loads per lane in flight); the next panel's rows are requested as soon as this one is written.
     const int lw = warp - 2 - EPW;
     const int D = p.K, nv = D >> 2;
-    float4 gw[3], gb[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const int c = lane + 32 * j;
-      gw[j] = c < nv ? __ldg(reinterpret_cast<const float4*>(ln.w) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      gb[j] = c < nv ? __ldg(reinterpret_cast<const float4*>(ln.b) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    const int row_lines = (D * 4 + 127) / 128;   // 128-byte lines per row
+    auto prefetch_rows = [&](int m0) {
+      for (int i = lane; i < 32 * row_lines; i += 32) {
+        const int row = m0 + lw * 32 + i / row_lines;
+        if (row < p.M) prefetch_l2(reinterpret_cast<const char*>(ln.x + (size_t)row * ln.ldx) + (i % row_lines) * 128);
+      }
+    };
+    if (n_units > 0) prefetch_rows((int)blockIdx.x * BLOCK_M);
+    const float4* w4 = reinterpret_cast<const float4*>(ln.w);
+    const float4* b4 = reinterpret_cast<const float4*>(ln.b);
     for (int u = 0; u < n_units; ++u) {
       const int m0 = ((int)blockIdx.x + u * (int)gridDim.x) * BLOCK_M;
       if (u > 0) mbar_wait(a_empty, (u - 1) & 1);  // the previous panel's MMAs have retired
-#pragma unroll 2
-      for (int rr = 0; rr < 32; ++rr) {
-        const int r = lw * 32 + rr;                // row inside the panel
-        const int row = m0 + r;
-        float4 v[3];
-        float s = 0.f;
-        if (row < p.M) {
+#pragma unroll 1
+      for (int r0 = 0; r0 < 32; r0 += 4) {
+        float4 v[4][3];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int row = m0 + lw * 32 + r0 + t;
           const float4* xr = reinterpret_cast<const float4*>(ln.x + (size_t)row * ln.ldx);
 #pragma unroll
           for (int j = 0; j < 3; ++j) {
             const int c = lane + 32 * j;
-            if (c < nv) { v[j] = xr[c]; s += v[j].x + v[j].y + v[j].z + v[j].w; }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 3; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        const float mu = warp_sum(s) / D;
-        float q = 0.f;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const int c = lane + 32 * j;
-          if (c < nv) {
-            const float a = v[j].x - mu, bb = v[j].y - mu, cc = v[j].z - mu, d = v[j].w - mu;
-            q += a * a + bb * bb + cc * cc + d * d;
+            v[t][j] = (row < p.M && c < nv) ? xr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
-        const float rs = rsqrtf(warp_sum(q) / D + ln.eps);
-        if (lane == 0 && row < p.M) {
-          if (ln.mean) ln.mean[row] = mu;
-          if (ln.rstd) ln.rstd[row] = rs;
-        }
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const int c = lane + 32 * j;             // float4 index: columns 4c .. 4c+3
-          if (c < nv) {
-            uint2 pk;
-            if (row < p.M) {
-              pk.x = pack_bf16x2((v[j].x - mu) * rs * gw[j].x + gb[j].x, (v[j].y - mu) * rs * gw[j].y + gb[j].y);
-              pk.y = pack_bf16x2((v[j].z - mu) * rs * gw[j].z + gb[j].z, (v[j].w - mu) * rs * gw[j].w + gb[j].w);
-              if (ln.xn) reinterpret_cast<uint2*>(ln.xn + (size_t)row * ln.ldxn)[c] = pk;
-            } else {
-              pk = make_uint2(0u, 0u);             // rows past M: zeros (their outputs are never stored)
+        for (int t = 0; t < 4; ++t) {
+          const int r = lw * 32 + r0 + t;            // row inside the panel
+          const int row = m0 + r;
+          float s = 0.f;
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+            if (lane + 32 * j < nv) s += v[t][j].x + v[t][j].y + v[t][j].z + v[t][j].w;
+          const float mu = warp_sum(s) / D;
+          float q = 0.f;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            if (lane + 32 * j < nv) {
+              const float a = v[t][j].x - mu, bb = v[t][j].y - mu, cc = v[t][j].z - mu, d = v[t][j].w - mu;
+              q += a * a + bb * bb + cc * cc + d * d;
             }
-            // column 4c -> k-block (4c)/64 = c/16, 16-byte chunk ((4c)%64)/8 = (c%16)/2, 8-byte half c&1
-            const int kb = c >> 4, chunk = (c & 15) >> 1;
-            *reinterpret_cast<uint2*>(panel + kb * Cfg::A_TILE + r * 128 + ((chunk ^ (r & 7)) << 4) + (c & 1) * 8) = pk;
+          }
+          const float rs = rsqrtf(warp_sum(q) / D + ln.eps);
+          if (lane == 0 && row < p.M) {
+            if (ln.mean) ln.mean[row] = mu;
+            if (ln.rstd) ln.rstd[row] = rs;
+          }
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const int c = lane + 32 * j;             // float4 index: columns 4c .. 4c+3
+            if (c < nv) {
+              uint2 pk;
+              if (row < p.M) {
+                const float4 gw = __ldg(w4 + c), gb = __ldg(b4 + c);
+                pk.x = pack_bf16x2((v[t][j].x - mu) * rs * gw.x + gb.x, (v[t][j].y - mu) * rs * gw.y + gb.y);
+                pk.y = pack_bf16x2((v[t][j].z - mu) * rs * gw.z + gb.z, (v[t][j].w - mu) * rs * gw.w + gb.w);
+                if (ln.xn) reinterpret_cast<uint2*>(ln.xn + (size_t)row * ln.ldxn)[c] = pk;
+              } else {
+                pk = make_uint2(0u, 0u);             // rows past M: zeros (their outputs are never stored)
+              }
+              // column 4c -> k-block (4c)/64 = c/16, 16-byte chunk ((4c)%64)/8 = (c%16)/2, 8-byte half c&1
+              const int kb = c >> 4, chunk = (c & 15) >> 1;
+              *reinterpret_cast<uint2*>(panel + kb * Cfg::A_TILE + r * 128 + ((chunk ^ (r & 7)) << 4) + (c & 1) * 8) = pk;
+            }
           }
         }
       }
       fence_proxy_async();  // the MMAs (async proxy) read what these threads wrote through the generic proxy
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full);
+      if (u + 1 < n_units) prefetch_rows(((int)blockIdx.x + (u + 1) * (int)gridDim.x) * BLOCK_M);
     }
   }
   tc_fence_before();

@@ -1,0 +1,13 @@
+# GPU session R (round 2): LayerNorm-prologue GEMM, second version (L2 prefetch of the panel rows, four rows in flight per warp).
+set -x
+O=gpurun_out/r2r
+mkdir -p $O
+timeout 300 python -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k "ln_gemm" > $O/pytest_ln_gemm.log 2>&1; echo "pytest rc=$?" >> $O/pytest_ln_gemm.log
+timeout 300 python tools/ln_gemm_bench.py > $O/ln_gemm_bench.log 2>&1; echo "rc=$?" >> $O/ln_gemm_bench.log
+Q="--steps 20 --warmup 5 --no-cpu-baseline --no-gpu-baseline --no-e2e"
+timeout 300 python bench.py $Q > $O/bench_default.json 2>> $O/bench_ab.err
+B200_LN_GEMM=auto timeout 300 python bench.py $Q > $O/bench_lngemm_auto.json 2>> $O/bench_ab.err
+B200_LN_GEMM=1 timeout 300 python bench.py $Q > $O/bench_lngemm_all.json 2>> $O/bench_ab.err
+B200_LN_GEMM=auto timeout 600 python -m pytest tests/test_parity_gpu.py tests/test_parity_configs_gpu.py -m gpu -q -x > $O/pytest_parity_lngemm.log 2>&1; echo "pytest rc=$?" >> $O/pytest_parity_lngemm.log
+cat $O/ln_gemm_bench.log; tail -n 4 $O/pytest_ln_gemm.log; tail -n 3 $O/pytest_parity_lngemm.log
+for f in $O/bench_*.json; do python -c "import json; d=json.loads(open('$f').read().strip().splitlines()[-1]); print('$f', d['ms_per_step'], d['loss'], d['parity'] and d['parity']['loss_delta_vs_oracle'])"; done
