@@ -975,6 +975,64 @@ gemm_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const GemmDev p,
     for (int u = 0; u < n_units; ++u) {
       const int m0 = ((int)blockIdx.x + u * (int)gridDim.x) * BLOCK_M;
       if (u > 0) mbar_wait(a_empty, (u - 1) & 1);  // the previous panel's MMAs have retired
+      if (nv == 96 && m0 + BLOCK_M <= p.M) {
+        // fast path (K = 384, full panel): no bounds predicates, gamma / beta in registers, swizzle offsets hoisted.
+        // (ncu on the generic path below: 325 SASS instructions per row and ~36 us per panel on these four warps)
+        float4 gw[3], gb[3];
+        uint32_t poff[3];                            // row-independent part of the panel offset of this lane's 8-byte pieces
+        int chunk[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int c = lane + 32 * j;
+          gw[j] = __ldg(w4 + c);
+          gb[j] = __ldg(b4 + c);
+          poff[j] = (uint32_t)((c >> 4) * Cfg::A_TILE + (c & 1) * 8);
+          chunk[j] = (c & 15) >> 1;
+        }
+        const float inv_d = 1.0f / 384.0f;
+        const float* xbase = ln.x + (size_t)(m0 + lw * 32) * ln.ldx;
+        __nv_bfloat16* xnbase = ln.xn ? ln.xn + (size_t)(m0 + lw * 32) * ln.ldxn : nullptr;
+#pragma unroll 1
+        for (int r0 = 0; r0 < 32; r0 += 4) {
+          float4 v[4][3];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float4* xr = reinterpret_cast<const float4*>(xbase + (size_t)(r0 + t) * ln.ldx);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) v[t][j] = xr[lane + 32 * j];
+          }
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int r = lw * 32 + r0 + t;
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) s += v[t][j].x + v[t][j].y + v[t][j].z + v[t][j].w;
+            const float mu = warp_sum(s) / 384.0f;
+            float q = 0.f;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              const float a = v[t][j].x - mu, bb = v[t][j].y - mu, cc = v[t][j].z - mu, d = v[t][j].w - mu;
+              q += a * a + bb * bb + cc * cc + d * d;
+            }
+            const float rs = rsqrtf(warp_sum(q) / 384.0f + ln.eps);
+            if (lane == 0) {
+              if (ln.mean) ln.mean[m0 + r] = mu;
+              if (ln.rstd) ln.rstd[m0 + r] = rs;
+            }
+            uint8_t* prow = panel + r * 128;
+            const int rx = r & 7;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              uint2 pk;
+              pk.x = pack_bf16x2((v[t][j].x - mu) * rs * gw[j].x + gb[j].x, (v[t][j].y - mu) * rs * gw[j].y + gb[j].y);
+              pk.y = pack_bf16x2((v[t][j].z - mu) * rs * gw[j].z + gb[j].z, (v[t][j].w - mu) * rs * gw[j].w + gb[j].w);
+              if (xnbase) reinterpret_cast<uint2*>(xnbase + (size_t)(r0 + t) * ln.ldxn)[lane + 32 * j] = pk;
+              *reinterpret_cast<uint2*>(prow + poff[j] + ((chunk[j] ^ rx) << 4)) = pk;
+            }
+          }
+        }
+        (void)inv_d;
+      } else {
 #pragma unroll 1
       for (int r0 = 0; r0 < 32; r0 += 4) {
         float4 v[4][3];
@@ -1029,6 +1087,7 @@ gemm_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const GemmDev p,
             }
           }
         }
+      }
       }
       fence_proxy_async();  // the MMAs (async proxy) read what these threads wrote through the generic proxy
       __syncwarp();

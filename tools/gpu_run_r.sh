@@ -1,6 +1,6 @@
-# GPU session R (round 2): LayerNorm-prologue GEMM, second version (L2 prefetch of the panel rows, four rows in flight per warp).
+# GPU session R / T (round 2): LayerNorm-prologue GEMM, later versions (L2 prefetch, four rows in flight; T: predicate-free fast path).
 set -x
-O=gpurun_out/r2r
+O=gpurun_out/r2t
 mkdir -p $O
 timeout 300 python -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k "ln_gemm" > $O/pytest_ln_gemm.log 2>&1; echo "pytest rc=$?" >> $O/pytest_ln_gemm.log
 timeout 300 python tools/ln_gemm_bench.py > $O/ln_gemm_bench.log 2>&1; echo "rc=$?" >> $O/ln_gemm_bench.log
