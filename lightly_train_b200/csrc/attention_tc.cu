@@ -282,807 +282,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 // ====================================================================================================================
-// forward, schedule 3: one 128-row query tile per CTA, two CTAs per SM
-// ====================================================================================================================
-// The first schedule keeps both query tiles of a pair in one CTA (213 KB of smem: one CTA per SM) and every thread walks
-// its score row twice through `tcgen05.ld` + `tcgen05.wait::ld` pairs: 61 us per 768-pair launch, no better than the
-// warp-level kernel -- the CTA is a serial chain (TMEM alloc, 85 KB of TMA, MMA, 26 exposed TMEM-load latencies per thread,
-// MMA, store) with nothing to overlap it.  Here:
-//   * a CTA owns ONE query tile: smem = Q 16 KB + K + V + a 2-slab P buffer (32 KB) = 100 KB at NKV = 208, TMEM = 256
-//     columns, so TWO CTAs are resident per SM and one's loads / MMAs hide behind the other's softmax;
-//   * the score row is read from TMEM ONCE, with 16-column loads software-pipelined one chunk ahead, and kept in registers as
-//     packed bf16 pairs (it is rounded to bf16 anyway: NKV/2 registers); keys outside the query's image become -inf there, so
-//     the exponential pass has no masks;
-//   * with the row in registers S is dead after pass 1, so O = P V reuses its first 64 TMEM columns, and P goes through the
-//     2-slab buffer in two halves (keys [0,128) then [128, NKV)) with the second half's exponentials computed while the first
-//     half's MMAs run.
-template <int NKV16>
-struct Fwd3Cfg {
-  static constexpr int NKV = NKV16 * 16;
-  static constexpr int KV_BYTES = NKV * 128;
-  static constexpr int OFF_K = TILE_BYTES;
-  static constexpr int OFF_V = OFF_K + KV_BYTES;
-  static constexpr int OFF_P = (OFF_V + KV_BYTES + 1023) / 1024 * 1024;
-  static constexpr int P_SLABS = NKV > 64 ? 2 : 1;
-  static constexpr int OFF_BAR = OFF_P + P_SLABS * TILE_BYTES;
-  static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
-  static constexpr int THREADS = 5 * 32;
-  static constexpr int KS0 = NKV16 < 8 ? NKV16 : 8;        // 16-key MMA steps of the first / second P half
-  static constexpr int KS1 = NKV16 - KS0;
-  static constexpr int TMEM_COLS = NKV <= 128 ? 128 : 256;
-  static_assert(NKV <= 256 && SMEM_BYTES <= 232448, "shared memory (two CTAs per SM up to NKV = 208)");
-};
-
-template <int NKV16>
-__global__ void __launch_bounds__(Fwd3Cfg<NKV16>::THREADS, 2)
-attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, int B, int N, int G, int h,
-                    int tiles_per_group, float scale, __nv_bfloat16* __restrict__ out, long long ld_out, float* __restrict__ lse) {
-  pdl_launch_dependents();
-  using C = Fwd3Cfg<NKV16>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
-  uint64_t* bar_load = bars + 0;
-  uint64_t* bar_s = bars + 1;     // S in TMEM
-  uint64_t* bar_p0 = bars + 2;    // first P half in smem AND every thread has its S row in registers (4 warps)
-  uint64_t* bar_pv0 = bars + 3;   // first-half MMAs retired: the P buffer may be overwritten
-  uint64_t* bar_p1 = bars + 4;    // second P half in smem (4 warps)
-  uint64_t* bar_o = bars + 5;     // O complete in TMEM
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t = blockIdx.x % tiles_per_group;
-  const int grp = blockIdx.x / tiles_per_group;
-  const int bg = grp / h, head = grp % h;
-  const int b0 = bg * G, n_img = min(G, B - b0);
-  const int rows_valid = n_img * N;
-
-  if (threadIdx.x == 0) {
-    mbar_init(bar_load, 1);
-    mbar_init(bar_s, 1);
-    mbar_init(bar_p0, 4);
-    mbar_init(bar_pv0, 1);
-    mbar_init(bar_p1, 4);
-    mbar_init(bar_o, 1);
-    fence_barrier_init();
-  }
-  if (warp == 4) {
-    if (lane == 0) {
-      tma_prefetch_desc(&tmQ);
-      tma_prefetch_desc(&tmKV);
-    }
-    tmem_alloc(tmem_slot, C::TMEM_COLS);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  pdl_wait();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 4) {
-    // ===================== control warp =====================
-    const int row0 = b0 * N;
-    if (lane == 0) {
-      mbar_expect_tx(bar_load, TILE_BYTES + 2 * C::KV_BYTES);
-      tma_load_2d(smem, &tmQ, bar_load, head * HD, row0 + t * BLOCK_Q);
-      tma_load_2d(smem + C::OFF_K, &tmKV, bar_load, (h + head) * HD, row0);
-      tma_load_2d(smem + C::OFF_V, &tmKV, bar_load, (2 * h + head) * HD, row0);
-    }
-    __syncwarp();
-    mbar_wait(bar_load, 0);
-    const uint32_t s0 = smem_u32(smem);
-    const uint64_t dq = smem_desc(s0, 16, 1024);
-    const uint64_t dk = smem_desc(s0 + C::OFF_K, 16, 1024);
-    const uint64_t dv = smem_desc(s0 + C::OFF_V, 64 * 128, 1024);
-    const uint64_t dp = smem_desc(s0 + C::OFF_P, 16, 1024);
-    const uint32_t idesc_s = instr_desc(BLOCK_Q, C::NKV, 0, 0);
-    const uint32_t idesc_o = instr_desc(BLOCK_Q, HD, 0, 1);
-    if (elect_one_sync()) {
-#pragma unroll
-      for (int ks = 0; ks < HD / 16; ++ks)
-        umma_f16(tmem_base, dq + (uint64_t)(ks * 2), dk + (uint64_t)(ks * 2), idesc_s, ks > 0 ? 1u : 0u);
-      umma_commit(bar_s);
-    }
-    __syncwarp();
-    mbar_wait(bar_p0, 0);
-    tc_fence_after();
-    if (elect_one_sync()) {
-#pragma unroll 1
-      for (int ks = 0; ks < C::KS0; ++ks)
-        umma_f16(tmem_base, dp + (uint64_t)(((ks >> 2) * TILE_BYTES + (ks & 3) * 32) >> 4), dv + (uint64_t)((ks * 2048) >> 4),
-                 idesc_o, ks > 0 ? 1u : 0u);
-      umma_commit(C::KS1 > 0 ? bar_pv0 : bar_o);
-    }
-    __syncwarp();
-    if (C::KS1 > 0) {
-      mbar_wait(bar_p1, 0);
-      tc_fence_after();
-      if (elect_one_sync()) {
-#pragma unroll 1
-        for (int ks = 0; ks < C::KS1; ++ks)
-          umma_f16(tmem_base, dp + (uint64_t)(((ks >> 2) * TILE_BYTES + (ks & 3) * 32) >> 4),
-                   dv + (uint64_t)(((C::KS0 + ks) * 2048) >> 4), idesc_o, 1u);
-        umma_commit(bar_o);
-      }
-      __syncwarp();
-    }
-  } else {
-    // ===================== worker warps: one query row per thread =====================
-    const int q = warp;
-    const int r = q * 32 + lane;
-    const int m = t * BLOCK_Q + r;
-    const int img = min(m / N, n_img - 1);
-    const int klo = img * N, khi = klo + N;
-    const uint32_t tS = tmem_base + ((uint32_t)(q * 32) << 16);
-    const float sl2 = scale * kLog2e;
-    uint8_t* sP = smem + C::OFF_P;
-    uint32_t srow[C::KS0 * 8];                      // keys [0, 16 KS0) of the score row as packed bf16 pairs (masked = -inf)
-    uint32_t buf[2][16];                            // 16-column TMEM loads, issued one chunk ahead of their use
-    mbar_wait(bar_s, 0);
-    tc_fence_after();
-    // masked bf16 pair of columns (k, k + 1) of chunk registers a, b
-    auto pack_masked = [&](uint32_t a, uint32_t b, int k, bool inside) -> uint32_t {
-      uint32_t pk = pack_bf16x2(__uint_as_float(a), __uint_as_float(b));
-      if (!inside) {
-        if (!(k >= klo && k < khi)) pk = (pk & 0xFFFF0000u) | 0x0000FF80u;          // bf16 -inf in the low half
-        if (!(k + 1 >= klo && k + 1 < khi)) pk = (pk & 0x0000FFFFu) | 0xFF800000u;  // and in the high half
-      }
-      return pk;
-    };
-    // pass 1: row max over all keys; the first half of the row stays in registers (the second half is re-read from TMEM
-    // columns [128, NKV) later: O only overwrites columns [0, 64))
-    float mx = -INFINITY;
-    tmem_ld_32x16(tS, buf[0]);
-#pragma unroll
-    for (int c = 0; c < NKV16; ++c) {
-      tmem_ld_wait();
-      if (c + 1 < NKV16) tmem_ld_32x16(tS + (c + 1) * 16, buf[(c + 1) & 1]);
-      const bool inside = c * 16 >= klo && c * 16 + 16 <= khi;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint32_t pk = pack_masked(buf[c & 1][2 * i], buf[c & 1][2 * i + 1], c * 16 + 2 * i, inside);
-        if (c < C::KS0) srow[c * 8 + i] = pk;
-        const float2 rr = unpack_bf16x2(pk);
-        mx = fmaxf(mx, fmaxf(rr.x, rr.y));
-      }
-    }
-    const float mb = -mx * sl2;
-    float l = 0.f;
-    if (C::KS1 > 0) tmem_ld_32x16(tS + C::KS0 * 16, buf[0]);  // second half, first chunk: in flight during the first half's math
-    // first half: keys [0, 16 * KS0) -> slabs 0 (keys 0..63) and 1 (keys 64..127)
-#pragma unroll
-    for (int c8 = 0; c8 < C::KS0 * 2; ++c8) {       // c8: group of 8 keys = 4 packed registers = one 16-byte chunk
-      uint32_t pw[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 rr = unpack_bf16x2(srow[c8 * 4 + j]);
-        const float p0 = ex2_ftz(fmaf(rr.x, sl2, mb)), p1 = ex2_ftz(fmaf(rr.y, sl2, mb));
-        l += p0 + p1;
-        pw[j] = pack_bf16x2(p0, p1);
-      }
-      *reinterpret_cast<uint4*>(sP + (c8 >> 3) * TILE_BYTES + swz(r, c8 & 7)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
-    }
-    // S columns [0, 64) -- the ones O will overwrite -- were read and waited for in pass 1; the second half's in-flight loads
-    // touch columns >= 128 only
-    tc_fence_before();
-    fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar_p0);
-    if (C::KS1 > 0) {
-      // second half: exponentials of keys [16 KS0, NKV) into the (now free) row registers while the first half's MMAs run
-#pragma unroll
-      for (int c = 0; c < C::KS1; ++c) {
-        tmem_ld_wait();
-        if (c + 1 < C::KS1) tmem_ld_32x16(tS + (C::KS0 + c + 1) * 16, buf[(c + 1) & 1]);
-        const int kc = (C::KS0 + c) * 16;
-        const bool inside = kc >= klo && kc + 16 <= khi;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float2 rr = unpack_bf16x2(pack_masked(buf[c & 1][2 * i], buf[c & 1][2 * i + 1], kc + 2 * i, inside));
-          const float p0 = ex2_ftz(fmaf(rr.x, sl2, mb)), p1 = ex2_ftz(fmaf(rr.y, sl2, mb));
-          l += p0 + p1;
-          srow[c * 8 + i] = pack_bf16x2(p0, p1);
-        }
-      }
-    }
-    if (C::KS1 > 0) {
-      mbar_wait(bar_pv0, 0);  // the first half's MMAs have retired: the P buffer is free
-#pragma unroll
-      for (int c8 = 0; c8 < C::KS1 * 2; ++c8)
-        *reinterpret_cast<uint4*>(sP + (c8 >> 3) * TILE_BYTES + swz(r, c8 & 7)) =
-            make_uint4(srow[c8 * 4], srow[c8 * 4 + 1], srow[c8 * 4 + 2], srow[c8 * 4 + 3]);
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_p1);
-    }
-    if (lse && m < rows_valid) lse[((size_t)(b0 + img) * h + head) * N + (m - klo)] = mx * scale + __logf(l);
-    mbar_wait(bar_o, 0);
-    tc_fence_after();
-    const float inv = 1.f / l;
-    __nv_bfloat16* orow = out + ((size_t)b0 * N + m) * ld_out + head * HD;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(tS + c * 32, v);
-      tmem_ld_wait();
-      if (m < rows_valid) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint32_t ow[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            ow[j] = pack_bf16x2(__uint_as_float(v[i * 8 + 2 * j]) * inv, __uint_as_float(v[i * 8 + 2 * j + 1]) * inv);
-          *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 4) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
-  }
-}
-
-// ====================================================================================================================
-// forward, schedule 4: persistent CTAs, TMA prefetch of the next pair, both query tiles in flight
-// ====================================================================================================================
-// Schedules 1 and 3 pay ~10 us of serial latency per CTA (TMEM alloc, descriptor fetch, an 85 KB TMA round trip, exposed
-// TMEM-load latencies) for ~1.5 us of tensor + MUFU work: 60-68 us per 768-pair launch however the work is cut.  Here a CTA
-// stays on its SM and loops over (image, head) pairs:
-//   * the set-up (barriers, TMEM, descriptors) is paid once per CTA, not once per pair;
-//   * K / V of pair i+1 are TMA-loaded into the second shared-memory stage while pair i is being processed, Q as soon as
-//     pair i's two S MMAs have retired (Q is only read by them);
-//   * the two 128-row query tiles of a pair run concurrently on the two worker warpgroups (warps 0-3 / 4-7), each with its
-//     own 256 TMEM columns (O aliases S) and its own 2-slab P buffer; the control warp (8) services them in turn;
-//   * workers use the register-cached score row and pipelined TMEM loads of schedule 3.
-// Shared memory: Q 32 KB + 2 x (K + V) + 2 x 32 KB P = 202 KB at NKV = 208.
-template <int NKV16>
-struct Fwd4Cfg {
-  static constexpr int NKV = NKV16 * 16;
-  static constexpr int KV_BYTES = NKV * 128;
-  static constexpr int OFF_KV = 2 * TILE_BYTES;                       // stage s: K at OFF_KV + s * 2 * KV_BYTES, V after it
-  static constexpr int OFF_P = (OFF_KV + 4 * KV_BYTES + 1023) / 1024 * 1024;
-  static constexpr int P_SLABS = NKV > 64 ? 2 : 1;
-  static constexpr int P_BYTES = P_SLABS * TILE_BYTES;                // per query tile
-  static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
-  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
-  static constexpr int THREADS = 9 * 32;
-  static constexpr int KS0 = NKV16 < 8 ? NKV16 : 8;
-  static constexpr int KS1 = NKV16 - KS0;
-  static_assert(NKV <= 256 && SMEM_BYTES <= 232448, "shared memory");
-};
-
-template <int NKV16>
-__global__ void __launch_bounds__(Fwd4Cfg<NKV16>::THREADS, 1)
-attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, int B, int N, int G, int h,
-                    int n_groups, float scale, __nv_bfloat16* __restrict__ out, long long ld_out, float* __restrict__ lse) {
-  pdl_launch_dependents();
-  using C = Fwd4Cfg<NKV16>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
-  uint64_t* bar_q = bars + 0;        // Q of the current pair landed                         (once per pair)
-  uint64_t* bar_kv = bars + 1;       // [2] K, V landed in stage s                           (once per two pairs)
-  uint64_t* bar_s = bars + 3;        // [2] S_t in TMEM                                      (once per pair)
-  uint64_t* bar_smma = bars + 5;     // both S MMAs retired: Q smem may be overwritten       (once per pair)
-  uint64_t* bar_p0 = bars + 6;       // [2] first P half of tile t in smem (4 warps)
-  uint64_t* bar_pv0 = bars + 8;      // [2] first-half MMAs of tile t retired
-  uint64_t* bar_p1 = bars + 10;      // [2] second P half in smem (4 warps)
-  uint64_t* bar_o = bars + 12;       // [2] O_t complete in TMEM
-  uint64_t* bar_tfree = bars + 14;   // [2] tile t's TMEM region drained (4 warps)
-  uint64_t* bar_kvfree = bars + 16;  // [2] every MMA that reads stage s has retired          (once per two pairs)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool two_tiles = G * N > BLOCK_Q;
-
-  if (threadIdx.x == 0) {
-    mbar_init(bar_q, 1);
-    mbar_init(bar_smma, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(bar_kv + i, 1);
-      mbar_init(bar_s + i, 1);
-      mbar_init(bar_p0 + i, 4);
-      mbar_init(bar_pv0 + i, 1);
-      mbar_init(bar_p1 + i, 4);
-      mbar_init(bar_o + i, 1);
-      mbar_init(bar_tfree + i, 4);
-      mbar_init(bar_kvfree + i, 1);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 8) {
-    if (lane == 0) {
-      tma_prefetch_desc(&tmQ);
-      tma_prefetch_desc(&tmKV);
-    }
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  pdl_wait();
-  const uint32_t tmem_base = *tmem_slot;
-  const int n_mine = (n_groups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // groups blockIdx.x, + gridDim.x, ...
-
-  if (warp == 8) {
-    // ===================== control warp =====================
-    const uint32_t s0 = smem_u32(smem);
-    const uint32_t idesc_s = instr_desc(BLOCK_Q, C::NKV, 0, 0);
-    const uint32_t idesc_o = instr_desc(BLOCK_Q, HD, 0, 1);
-    const uint32_t q_bytes = (two_tiles ? 2 : 1) * TILE_BYTES;
-    auto group_rows = [&](int it, int& head, int& row0) {
-      const int grp = blockIdx.x + it * gridDim.x;
-      head = grp % h;
-      row0 = (grp / h) * G * N;
-    };
-    if (lane == 0 && n_mine > 0) {  // prologue: pair 0
-      int head, row0;
-      group_rows(0, head, row0);
-      mbar_expect_tx(bar_q, q_bytes);
-      tma_load_2d(smem, &tmQ, bar_q, head * HD, row0);
-      if (two_tiles) tma_load_2d(smem + TILE_BYTES, &tmQ, bar_q, head * HD, row0 + BLOCK_Q);
-      mbar_expect_tx(bar_kv, 2 * C::KV_BYTES);
-      tma_load_2d(smem + C::OFF_KV, &tmKV, bar_kv, (h + head) * HD, row0);
-      tma_load_2d(smem + C::OFF_KV + C::KV_BYTES, &tmKV, bar_kv, (2 * h + head) * HD, row0);
-    }
-    __syncwarp();
-    for (int it = 0; it < n_mine; ++it) {
-      const int st = it & 1;
-      const uint32_t ph = it & 1, ph2 = (it >> 1) & 1;
-      const uint32_t sK = s0 + C::OFF_KV + st * 2 * C::KV_BYTES, sV = sK + C::KV_BYTES;
-      mbar_wait(bar_q, ph);
-      mbar_wait(bar_kv + st, ph2);
-      if (it > 0) {  // the TMEM regions still hold the previous pair's O until the workers have drained them
-        mbar_wait(bar_tfree + 0, ph ^ 1);
-        if (two_tiles) mbar_wait(bar_tfree + 1, ph ^ 1);
-      }
-      tc_fence_after();
-      if (elect_one_sync()) {
-        const uint64_t dk = smem_desc(sK, 16, 1024);
-        for (int t = 0; t < (two_tiles ? 2 : 1); ++t) {
-          const uint64_t dq = smem_desc(s0 + t * TILE_BYTES, 16, 1024);
-#pragma unroll
-          for (int ks = 0; ks < HD / 16; ++ks)
-            umma_f16(tmem_base + t * 256, dq + (uint64_t)(ks * 2), dk + (uint64_t)(ks * 2), idesc_s, ks > 0 ? 1u : 0u);
-          umma_commit(bar_s + t);
-        }
-        umma_commit(bar_smma);
-      }
-      __syncwarp();
-      // prefetch pair it + 1: Q once this pair's S MMAs have retired, K / V into the other stage once the MMAs of pair it - 1
-      // (its last user) have retired
-      if (it + 1 < n_mine) {
-        mbar_wait(bar_smma, ph);
-        if (it >= 1) mbar_wait(bar_kvfree + (st ^ 1), ((it - 1) >> 1) & 1);
-        if (lane == 0) {
-          int head, row0;
-          group_rows(it + 1, head, row0);
-          mbar_expect_tx(bar_q, q_bytes);
-          tma_load_2d(smem, &tmQ, bar_q, head * HD, row0);
-          if (two_tiles) tma_load_2d(smem + TILE_BYTES, &tmQ, bar_q, head * HD, row0 + BLOCK_Q);
-          const uint32_t off = C::OFF_KV + (st ^ 1) * 2 * C::KV_BYTES;
-          mbar_expect_tx(bar_kv + (st ^ 1), 2 * C::KV_BYTES);
-          tma_load_2d(smem + off, &tmKV, bar_kv + (st ^ 1), (h + head) * HD, row0);
-          tma_load_2d(smem + off + C::KV_BYTES, &tmKV, bar_kv + (st ^ 1), (2 * h + head) * HD, row0);
-        }
-        __syncwarp();
-      }
-      const uint64_t dv = smem_desc(sV, 64 * 128, 1024);
-      const int nt = two_tiles ? 2 : 1;
-      for (int t = 0; t < nt; ++t) {  // first P halves
-        mbar_wait(bar_p0 + t, ph);
-        tc_fence_after();
-        if (elect_one_sync()) {
-          const uint64_t dp = smem_desc(s0 + C::OFF_P + t * C::P_BYTES, 16, 1024);
-#pragma unroll 1
-          for (int ks = 0; ks < C::KS0; ++ks)
-            umma_f16(tmem_base + t * 256, dp + (uint64_t)(((ks >> 2) * TILE_BYTES + (ks & 3) * 32) >> 4),
-                     dv + (uint64_t)((ks * 2048) >> 4), idesc_o, ks > 0 ? 1u : 0u);
-          umma_commit(C::KS1 > 0 ? bar_pv0 + t : bar_o + t);
-          if (C::KS1 == 0 && t == nt - 1) umma_commit(bar_kvfree + st);
-        }
-        __syncwarp();
-      }
-      if (C::KS1 > 0) {
-        for (int t = 0; t < nt; ++t) {  // second P halves
-          mbar_wait(bar_p1 + t, ph);
-          tc_fence_after();
-          if (elect_one_sync()) {
-            const uint64_t dp = smem_desc(s0 + C::OFF_P + t * C::P_BYTES, 16, 1024);
-#pragma unroll 1
-            for (int ks = 0; ks < C::KS1; ++ks)
-              umma_f16(tmem_base + t * 256, dp + (uint64_t)(((ks >> 2) * TILE_BYTES + (ks & 3) * 32) >> 4),
-                       dv + (uint64_t)(((C::KS0 + ks) * 2048) >> 4), idesc_o, 1u);
-            umma_commit(bar_o + t);
-            if (t == nt - 1) umma_commit(bar_kvfree + st);
-          }
-          __syncwarp();
-        }
-      }
-    }
-  } else if (warp < 4 || two_tiles) {
-    // ===================== worker warpgroup t: query tile t of every pair =====================
-    const int t = warp >> 2, q = warp & 3;
-    const int r = q * 32 + lane;
-    const uint32_t tS = tmem_base + ((uint32_t)(q * 32) << 16) + t * 256;
-    const float sl2 = scale * kLog2e;
-    uint8_t* sP = smem + C::OFF_P + t * C::P_BYTES;
-    for (int it = 0; it < n_mine; ++it) {
-      const uint32_t ph = it & 1;
-      const int grp = blockIdx.x + it * gridDim.x;
-      const int head = grp % h, b0 = (grp / h) * G;
-      const int n_img = min(G, B - b0);
-      const int rows_valid = n_img * N;
-      const int m = t * BLOCK_Q + r;
-      const int img = min(m / N, n_img - 1);
-      const int klo = img * N, khi = klo + N;
-      uint32_t srow[C::KS0 * 8];
-      uint32_t buf[2][16];
-      auto pack_masked = [&](uint32_t a, uint32_t b, int k, bool inside) -> uint32_t {
-        uint32_t pk = pack_bf16x2(__uint_as_float(a), __uint_as_float(b));
-        if (!inside) {
-          if (!(k >= klo && k < khi)) pk = (pk & 0xFFFF0000u) | 0x0000FF80u;
-          if (!(k + 1 >= klo && k + 1 < khi)) pk = (pk & 0x0000FFFFu) | 0xFF800000u;
-        }
-        return pk;
-      };
-      mbar_wait(bar_s + t, ph);
-      tc_fence_after();
-      float mx = -INFINITY;
-      tmem_ld_32x16(tS, buf[0]);
-#pragma unroll
-      for (int c = 0; c < NKV16; ++c) {
-        tmem_ld_wait();
-        if (c + 1 < NKV16) tmem_ld_32x16(tS + (c + 1) * 16, buf[(c + 1) & 1]);
-        const bool inside = c * 16 >= klo && c * 16 + 16 <= khi;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint32_t pk = pack_masked(buf[c & 1][2 * i], buf[c & 1][2 * i + 1], c * 16 + 2 * i, inside);
-          if (c < C::KS0) srow[c * 8 + i] = pk;
-          const float2 rr = unpack_bf16x2(pk);
-          mx = fmaxf(mx, fmaxf(rr.x, rr.y));
-        }
-      }
-      const float mb = -mx * sl2;
-      float l = 0.f;
-      if (C::KS1 > 0) tmem_ld_32x16(tS + C::KS0 * 16, buf[0]);
-#pragma unroll
-      for (int c8 = 0; c8 < C::KS0 * 2; ++c8) {
-        uint32_t pw[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 rr = unpack_bf16x2(srow[c8 * 4 + j]);
-          const float p0 = ex2_ftz(fmaf(rr.x, sl2, mb)), p1 = ex2_ftz(fmaf(rr.y, sl2, mb));
-          l += p0 + p1;
-          pw[j] = pack_bf16x2(p0, p1);
-        }
-        *reinterpret_cast<uint4*>(sP + (c8 >> 3) * TILE_BYTES + swz(r, c8 & 7)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
-      }
-      tc_fence_before();
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_p0 + t);
-      if (C::KS1 > 0) {
-#pragma unroll
-        for (int c = 0; c < C::KS1; ++c) {
-          tmem_ld_wait();
-          if (c + 1 < C::KS1) tmem_ld_32x16(tS + (C::KS0 + c + 1) * 16, buf[(c + 1) & 1]);
-          const int kc = (C::KS0 + c) * 16;
-          const bool inside = kc >= klo && kc + 16 <= khi;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float2 rr = unpack_bf16x2(pack_masked(buf[c & 1][2 * i], buf[c & 1][2 * i + 1], kc + 2 * i, inside));
-            const float p0 = ex2_ftz(fmaf(rr.x, sl2, mb)), p1 = ex2_ftz(fmaf(rr.y, sl2, mb));
-            l += p0 + p1;
-            srow[c * 8 + i] = pack_bf16x2(p0, p1);
-          }
-        }
-        mbar_wait(bar_pv0 + t, ph);
-#pragma unroll
-        for (int c8 = 0; c8 < C::KS1 * 2; ++c8)
-          *reinterpret_cast<uint4*>(sP + (c8 >> 3) * TILE_BYTES + swz(r, c8 & 7)) =
-              make_uint4(srow[c8 * 4], srow[c8 * 4 + 1], srow[c8 * 4 + 2], srow[c8 * 4 + 3]);
-        tc_fence_before();
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_p1 + t);
-      }
-      if (lse && m < rows_valid) lse[((size_t)(b0 + img) * h + head) * N + (m - klo)] = mx * scale + __logf(l);
-      mbar_wait(bar_o + t, ph);
-      tc_fence_after();
-      const float inv = 1.f / l;
-      uint32_t ov[2][32];
-      tmem_ld_32x32(tS, ov[0]);
-      tmem_ld_32x32(tS + 32, ov[1]);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tfree + t);  // the next pair's S may overwrite this TMEM region
-      if (m < rows_valid) {
-        __nv_bfloat16* orow = out + ((size_t)b0 * N + m) * ld_out + head * HD;
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint32_t ow[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              ow[j] = pack_bf16x2(__uint_as_float(ov[c][i * 8 + 2 * j]) * inv, __uint_as_float(ov[c][i * 8 + 2 * j + 1]) * inv);
-            *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-          }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 8) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
-// ====================================================================================================================
-// forward, schedule 5: schedule 1's CTA (both query tiles of a pair, one CTA per SM) with SIXTEEN worker warps
-// ====================================================================================================================
-// ncu on schedules 1 / 3 / 4 (profiles/r02_ncu_attn_tc.txt): 8 worker warps per SM, issue slots 27 % busy, tensor pipe 8 % --
-// the softmax of a pair is a latency chain of ~3.4 k dependent instructions per warp and there are only two warps per
-// scheduler to hide it; making the CTA persistent (schedule 4) or splitting it (schedule 3) leaves the per-SM warp count
-// unchanged, and the time too (62 - 72 us).  Here every query row is shared by TWO threads (warps w and w + 8 address the
-// same TMEM lane quarter): each owns half of the key columns (two passes over them with software-pipelined TMEM
-// loads; 17 warps leave 96 registers per thread, too few to keep the half row), and the pair exchanges its half-row maximum and half-row sum through shared memory + a 64-thread named barrier.
-// P V is issued per half as soon as that half's four warps have written their P columns; each thread drains 32 of the 64
-// O columns.
-template <int NKV16>
-struct Fwd5Cfg {
-  static constexpr int NKV = NKV16 * 16;
-  static constexpr int KV_BYTES = NKV * 128;
-  static constexpr int P_SLABS = (NKV + 63) / 64;
-  static constexpr int OFF_K = 2 * TILE_BYTES;
-  static constexpr int OFF_V = OFF_K + KV_BYTES;
-  static constexpr int OFF_P = (OFF_V + KV_BYTES + 1023) / 1024 * 1024;
-  static constexpr int P_BYTES = P_SLABS * TILE_BYTES;
-  static constexpr int OFF_X = OFF_P + 2 * P_BYTES;          // floats: half-row max [2][256], half-row sum [2][256]
-  static constexpr int OFF_BAR = OFF_X + 4 * 256 * 4;
-  static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
-  static constexpr int THREADS = 17 * 32;
-  static constexpr int HA = (NKV16 + 1) / 2;                 // 16-key chunks of the first / second column half
-  static constexpr int HB = NKV16 - HA;
-  static_assert(NKV <= 256 && SMEM_BYTES <= 232448, "shared memory");
-};
-
-template <int NKV16>
-__global__ void __launch_bounds__(Fwd5Cfg<NKV16>::THREADS, 1)
-attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, int B, int N, int G, int h,
-                    float scale, __nv_bfloat16* __restrict__ out, long long ld_out, float* __restrict__ lse) {
-  pdl_launch_dependents();
-  using C = Fwd5Cfg<NKV16>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
-  uint64_t* bar_load = bars + 0;
-  uint64_t* bar_s = bars + 1;     // [2] S_t in TMEM
-  uint64_t* bar_p = bars + 3;     // [2 tiles][2 halves] P columns of that half in smem (4 warps each)
-  uint64_t* bar_o = bars + 7;     // [2] O_t in TMEM
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
-  float* xmax = reinterpret_cast<float*>(smem + C::OFF_X);   // [half][256]
-  float* xsum = xmax + 512;                                  // [half][256]
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int bg = blockIdx.x / h, head = blockIdx.x % h;
-  const int b0 = bg * G, n_img = min(G, B - b0);
-  const int rows_valid = n_img * N;
-  const int n_tiles = (rows_valid + BLOCK_Q - 1) / BLOCK_Q;
-
-  if (threadIdx.x == 0) {
-    mbar_init(bar_load, 1);
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(bar_s + t, 1);
-      mbar_init(bar_p + 2 * t, 4);
-      mbar_init(bar_p + 2 * t + 1, 4);
-      mbar_init(bar_o + t, 1);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 16) {
-    if (lane == 0) {
-      tma_prefetch_desc(&tmQ);
-      tma_prefetch_desc(&tmKV);
-    }
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  pdl_wait();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 16) {
-    // ===================== control warp: TMA + MMA issue =====================
-    const int row0 = b0 * N;
-    if (lane == 0) {
-      mbar_expect_tx(bar_load, 2 * TILE_BYTES + 2 * C::KV_BYTES);
-      tma_load_2d(smem, &tmQ, bar_load, head * HD, row0);
-      tma_load_2d(smem + TILE_BYTES, &tmQ, bar_load, head * HD, row0 + BLOCK_Q);
-      tma_load_2d(smem + C::OFF_K, &tmKV, bar_load, (h + head) * HD, row0);
-      tma_load_2d(smem + C::OFF_V, &tmKV, bar_load, (2 * h + head) * HD, row0);
-    }
-    __syncwarp();
-    mbar_wait(bar_load, 0);
-    const uint32_t s0 = smem_u32(smem);
-    const uint64_t dk = smem_desc(s0 + C::OFF_K, 16, 1024);
-    const uint64_t dv = smem_desc(s0 + C::OFF_V, 64 * 128, 1024);
-    const uint32_t idesc_s = instr_desc(BLOCK_Q, C::NKV, 0, 0);
-    const uint32_t idesc_o = instr_desc(BLOCK_Q, HD, 0, 1);
-    if (elect_one_sync()) {
-      for (int t = 0; t < n_tiles; ++t) {
-        const uint64_t dq = smem_desc(s0 + t * TILE_BYTES, 16, 1024);
-#pragma unroll
-        for (int ks = 0; ks < HD / 16; ++ks)
-          umma_f16(tmem_base + t * 256, dq + (uint64_t)((ks * 32) >> 4), dk + (uint64_t)((ks * 32) >> 4), idesc_s, ks > 0 ? 1u : 0u);
-        umma_commit(bar_s + t);
-      }
-    }
-    __syncwarp();
-    for (int t = 0; t < n_tiles; ++t) {
-      const uint64_t dp = smem_desc(s0 + C::OFF_P + t * C::P_BYTES, 16, 1024);
-      for (int half = 0; half < (C::HB > 0 ? 2 : 1); ++half) {
-        mbar_wait(bar_p + 2 * t + half, 0);
-        tc_fence_after();
-        if (elect_one_sync()) {
-          const int k0 = half ? C::HA : 0, k1 = half ? NKV16 : C::HA;
-#pragma unroll 1
-          for (int ks = k0; ks < k1; ++ks)
-            umma_f16(tmem_base + t * 256, dp + (uint64_t)(((ks >> 2) * TILE_BYTES + (ks & 3) * 32) >> 4),
-                     dv + (uint64_t)((ks * 16 * 128) >> 4), idesc_o, ks > 0 ? 1u : 0u);
-          if (half == (C::HB > 0 ? 1 : 0)) umma_commit(bar_o + t);
-        }
-        __syncwarp();
-      }
-    }
-  } else if (((warp & 7) >> 2) < n_tiles) {
-    // ===================== worker warps: tile t, lane quarter q, column half =====================
-    const int half = warp >> 3, t = (warp & 7) >> 2, q = warp & 3;
-    const int r = q * 32 + lane;
-    const int m = t * BLOCK_Q + r;
-    const int img = min(m / N, n_img - 1);
-    const int klo = img * N, khi = klo + N;
-    const int c0 = half ? C::HA : 0, nc = half ? C::HB : C::HA;
-    const uint32_t tS = tmem_base + ((uint32_t)(q * 32) << 16) + t * 256;
-    const float sl2 = scale * kLog2e;
-    uint8_t* sP = smem + C::OFF_P + t * C::P_BYTES;
-    const int pair_bar = 1 + (warp & 7);                     // named barrier shared by warps w and w + 8
-    uint32_t buf[16];
-    // Leading chunks of my range whose 16 keys are valid for EVERY row of the CTA run a mask-free body (with one image per
-    // CTA that is all but the last chunk; packed short sequences take the masked body throughout).  ncu on the first
-    // version: the per-element key tests were if-converted into ~3 predicate / select instructions per element on every
-    // chunk, 18 instructions per score element in total.
-    const int nfull = (G == 1) ? max(0, min(nc, N / 16 - c0)) : 0;
-    // packed bf16 scores of one 16-key chunk; the next chunk's TMEM load is issued as soon as `buf` has been packed so that it
-    // is in flight during the arithmetic on this chunk
-    auto take_chunk = [&](int c, uint32_t (&pk)[8]) {
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(__uint_as_float(buf[2 * i]), __uint_as_float(buf[2 * i + 1]));
-      if (c + 1 < nc) tmem_ld_32x16(tS + (c0 + c + 1) * 16, buf);
-    };
-    auto mask_chunk = [&](int c, uint32_t (&pk)[8]) {  // keys outside the row's image -> -inf
-      const int kc = (c0 + c) * 16;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int k = kc + 2 * i;
-        if (!(k >= klo && k < khi)) pk[i] = (pk[i] & 0xFFFF0000u) | 0x0000FF80u;
-        if (!(k + 1 >= klo && k + 1 < khi)) pk[i] = (pk[i] & 0x0000FFFFu) | 0xFF800000u;
-      }
-    };
-    mbar_wait(bar_s + t, 0);
-    tc_fence_after();
-    // pass 1: row max of the bf16-rounded scores, on packed pairs (max.bf16x2)
-    uint32_t mx2 = 0xFF80FF80u;
-    if (nc > 0) tmem_ld_32x16(tS + c0 * 16, buf);
-#pragma unroll 1
-    for (int c = 0; c < nfull; ++c) {
-      uint32_t pk[8];
-      take_chunk(c, pk);
-#pragma unroll
-      for (int i = 0; i < 8; i += 2) mx2 = bf16x2_max(mx2, bf16x2_max(pk[i], pk[i + 1]));
-    }
-#pragma unroll 1
-    for (int c = nfull; c < nc; ++c) {
-      uint32_t pk[8];
-      take_chunk(c, pk);
-      mask_chunk(c, pk);
-#pragma unroll
-      for (int i = 0; i < 8; i += 2) mx2 = bf16x2_max(mx2, bf16x2_max(pk[i], pk[i + 1]));
-    }
-    if (nc > 0) tmem_ld_32x16(tS + c0 * 16, buf);            // first chunk of pass 2: in flight across the exchange
-    float mx;
-    {
-      const float2 mm = unpack_bf16x2(mx2);
-      mx = fmaxf(mm.x, mm.y);
-    }
-    xmax[half * 256 + m] = mx;
-    named_bar_sync(pair_bar, 64);
-    mx = fmaxf(mx, xmax[(half ^ 1) * 256 + m]);
-    const float mb = -mx * sl2;
-    // pass 2: p = 2^(s*sl2 - m*sl2) -> bf16 -> swizzled smem A tile; row sum in fp32 (two accumulators)
-    float l0 = 0.f, l1 = 0.f;
-    auto exp_store = [&](int c, const uint32_t (&pk)[8]) {
-      uint32_t pw[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float2 rr = unpack_bf16x2(pk[i]);
-        const float p0 = ex2_ftz(fmaf(rr.x, sl2, mb)), p1 = ex2_ftz(fmaf(rr.y, sl2, mb));
-        l0 += p0;
-        l1 += p1;
-        pw[i] = pack_bf16x2(p0, p1);
-      }
-      const int cc = c0 + c;
-      uint8_t* slab = sP + (cc >> 2) * TILE_BYTES;
-      const int ch = (cc & 3) * 2;
-      *reinterpret_cast<uint4*>(slab + swz(r, ch)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
-      *reinterpret_cast<uint4*>(slab + swz(r, ch + 1)) = make_uint4(pw[4], pw[5], pw[6], pw[7]);
-    };
-#pragma unroll 1
-    for (int c = 0; c < nfull; ++c) {
-      uint32_t pk[8];
-      take_chunk(c, pk);
-      exp_store(c, pk);
-    }
-#pragma unroll 1
-    for (int c = nfull; c < nc; ++c) {
-      uint32_t pk[8];
-      take_chunk(c, pk);
-      mask_chunk(c, pk);
-      exp_store(c, pk);
-    }
-    float l = l0 + l1;
-    xsum[half * 256 + m] = l;
-    fence_proxy_async();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar_p + 2 * t + half);
-    named_bar_sync(pair_bar, 64);
-    l += xsum[(half ^ 1) * 256 + m];
-    if (half == 0 && lse && m < rows_valid) lse[((size_t)(b0 + img) * h + head) * N + (m - klo)] = mx * scale + __logf(l);
-    mbar_wait(bar_o + t, 0);
-    tc_fence_after();
-    const float inv = 1.f / l;
-    uint32_t ov[32];
-    tmem_ld_32x32(tS + half * 32, ov);
-    tmem_ld_wait();
-    if (m < rows_valid) {
-      __nv_bfloat16* orow = out + ((size_t)b0 * N + m) * ld_out + head * HD + half * 32;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint32_t ow[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          ow[j] = pack_bf16x2(__uint_as_float(ov[i * 8 + 2 * j]) * inv, __uint_as_float(ov[i * 8 + 2 * j + 1]) * inv);
-        *reinterpret_cast<uint4*>(orow + i * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 16) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
-// ====================================================================================================================
 // forward, schedule 7: P stays in TENSOR MEMORY (A operand of P V read from TMEM); one query tile per CTA, two CTAs per SM
 // ====================================================================================================================
-// ncu on schedule 5 (profiles/r02_ncu_attn_tc16.txt): per (image, head) pair the softmax warps spend 23 % of the CTA's life
+// ncu on a sixteen-softmax-warp version of schedule 1 (profiles/r02_ncu_attn_tc16.txt; since removed): per (image, head) pair
+// the softmax warps spend 23 % of the CTA's life
 // waiting for its 85 KB of TMA loads (every CTA of a wave loads at the same time, then computes while HBM idles), 9 % on
 // P V, 5 % in the exit tail; and the 2 x 64 KB of swizzled shared memory that carry P to the second MMA are what keeps a
 // second CTA (or a second K / V stage) off the SM.  Here the probabilities never leave tensor memory:
@@ -1865,283 +1068,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
-// ====================================================================================================================
-// backward, schedule 2: key-tile-outer blocks, S and dP side by side in TMEM, ONE fused pass per block
-// ====================================================================================================================
-// The first backward walks the two query tiles of a pair one after the other through a single TMEM region that is S, then dP,
-// then dQ: five dependent phases per tile (MMA, softmax pass, MMA, dS pass, MMA) plus the dQ drain, 25 us per pair whatever the
-// number of softmax warps (129 us per 768-pair launch with 8 or 16 of them).  Here the pair is cut into key tiles (112 + the
-// rest) x query tiles:
-//   TMEM   S [0,112) | dP [112,224) | dK_j [224,288) | dV_j [288,352) | dQ_0 [352,416) | dQ_1 [416,480)
-//   block (i, j):  S = Q_i K_j^T and dP = dO_i V_j^T are issued TOGETHER (dP does not depend on P); one fused pass reads both,
-//                  p = 2^(s*sl2 - L), dS = p (dP - D), and writes P and dS (two smem tiles); then dV_j += P^T dO_i,
-//                  dK_j += dS^T Q_i, dQ_i += dS K_j are issued together.
-// Three dependent phases per block instead of six per tile, and the S / dP MMAs of block b+1 are issued as soon as the pass of
-// block b has read TMEM, i.e. they run under block b's second MMA group.  dK_j / dV_j are drained after the last query tile of
-// key tile j, dQ_0 / dQ_1 (accumulated over the key tiles in TMEM) at the end.  16 worker warps: 4 lane quarters x 4 column
-// groups (8-key units); one control warp.
-template <int NKV16>
-struct Bwd2Cfg {
-  static constexpr int NKV = NKV16 * 16;
-  static constexpr int NJ0 = 112, NJ1 = NKV - NJ0;          // keys per key tile
-  static constexpr int KV_BYTES = NKV * 128;
-  static constexpr int OFF_Q = 0;
-  static constexpr int OFF_DO = 2 * TILE_BYTES;
-  static constexpr int OFF_K = 4 * TILE_BYTES;
-  static constexpr int OFF_V = OFF_K + KV_BYTES;
-  static constexpr int OFF_P = (OFF_V + KV_BYTES + 1023) / 1024 * 1024;   // P tile: 2 slabs of 64 keys
-  static constexpr int OFF_DS = OFF_P + 2 * TILE_BYTES;                    // dS tile: 2 slabs
-  static constexpr int OFF_F = OFF_DS + 2 * TILE_BYTES;                    // floats: L[256], D[256], colsum[192]
-  static constexpr int OFF_BAR = OFF_F + (256 + 256 + 192) * 4;
-  static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
-  static constexpr int THREADS = 17 * 32;
-  static constexpr int TM_S = 0, TM_DP = 112, TM_DK = 224, TM_DV = 288, TM_DQ = 352;
-  static_assert(NKV > 128 && NKV <= 224 && NJ1 % 16 == 0 && NJ1 >= 16, "two key tiles: 112 + (16 .. 112)");
-  static_assert(SMEM_BYTES <= 232448, "shared memory");
-};
-
-template <int NKV16>
-__global__ void __launch_bounds__(Bwd2Cfg<NKV16>::THREADS, 1)
-attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                    const __grid_constant__ CUtensorMap tmDO, const __nv_bfloat16* __restrict__ outp,
-                    const __nv_bfloat16* __restrict__ dout, long long ld_out, const float* __restrict__ lse, int B, int N, int h,
-                    float scale, __nv_bfloat16* __restrict__ dqkv, long long ld_dtok, float* __restrict__ colsum) {
-  pdl_launch_dependents();
-  using C = Bwd2Cfg<NKV16>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  float* sL = reinterpret_cast<float*>(smem + C::OFF_F);  // base-2 log-sum-exp per query row (+inf on padded rows)
-  float* sD = sL + 256;                                   // D_i = sum_d dO O
-  float* sC = sD + 256;                                   // column sums of dq | dk | dv
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
-  uint64_t* bar_load = bars + 0;
-  uint64_t* bar_sdp = bars + 1;      // S and dP of the current block in TMEM
-  uint64_t* bar_sfree = bars + 2;    // every worker warp has read them (16)
-  uint64_t* bar_pds = bars + 3;      // P and dS of the current block in smem (16)
-  uint64_t* bar_mma2 = bars + 4;     // dV / dK / dQ MMAs of the current block retired
-  uint64_t* bar_dkvfree = bars + 5;  // dK_j / dV_j drained (16): the accumulators may be overwritten
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x / h, head = blockIdx.x % h;  // one image x one head
-  const int n_tiles = (N + BLOCK_Q - 1) / BLOCK_Q;      // 2 (N > 128)
-  const int nb = 2 * n_tiles;                           // blocks: key tile j = blk / n_tiles, query tile i = blk % n_tiles
-
-  if (threadIdx.x == 0) {
-    mbar_init(bar_load, 1);
-    mbar_init(bar_sdp, 1);
-    mbar_init(bar_sfree, 16);
-    mbar_init(bar_pds, 16);
-    mbar_init(bar_mma2, 1);
-    mbar_init(bar_dkvfree, 16);
-    fence_barrier_init();
-  }
-  if (warp == 16) {
-    if (lane == 0) {
-      tma_prefetch_desc(&tmQ);
-      tma_prefetch_desc(&tmKV);
-      tma_prefetch_desc(&tmDO);
-    }
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  pdl_wait();
-  const uint32_t tmem_base = *tmem_slot;
-  const size_t row0 = (size_t)b * N;
-
-  if (warp == 16) {
-    // ===================== control warp =====================
-    if (lane == 0) {
-      mbar_expect_tx(bar_load, 4 * TILE_BYTES + 2 * C::KV_BYTES);
-      tma_load_2d(smem + C::OFF_Q, &tmQ, bar_load, head * HD, (int)row0);
-      tma_load_2d(smem + C::OFF_Q + TILE_BYTES, &tmQ, bar_load, head * HD, (int)row0 + BLOCK_Q);
-      tma_load_2d(smem + C::OFF_DO, &tmDO, bar_load, head * HD, (int)row0);
-      tma_load_2d(smem + C::OFF_DO + TILE_BYTES, &tmDO, bar_load, head * HD, (int)row0 + BLOCK_Q);
-      tma_load_2d(smem + C::OFF_K, &tmKV, bar_load, (h + head) * HD, (int)row0);
-      tma_load_2d(smem + C::OFF_V, &tmKV, bar_load, (2 * h + head) * HD, (int)row0);
-    }
-    __syncwarp();
-    mbar_wait(bar_load, 0);
-    const uint32_t s0 = smem_u32(smem);
-    const uint64_t dP_mn = smem_desc(s0 + C::OFF_P, TILE_BYTES, 1024);    // A of dV: P^T, MN-major (M = keys), LBO = slab
-    const uint64_t dS_mn = smem_desc(s0 + C::OFF_DS, TILE_BYTES, 1024);   // A of dK: dS^T
-    const uint64_t dS_k = smem_desc(s0 + C::OFF_DS, 16, 1024);            // A of dQ: dS [q x keys], K-major, 64-key slabs
-    const uint32_t id_kv = instr_desc(BLOCK_Q, HD, 1, 1);                 // dV, dK: A MN-major, B MN-major
-    const uint32_t id_dq = instr_desc(BLOCK_Q, HD, 0, 1);                 // dQ
-    for (int blk = 0; blk < nb; ++blk) {
-      const uint32_t ph = blk & 1;
-      const int j = blk / n_tiles, i = blk % n_tiles;
-      const int nj = j ? C::NJ1 : C::NJ0;
-      const uint32_t koff = (uint32_t)(j * C::NJ0 * 128);                 // byte offset of key tile j's rows in K / V
-      const uint64_t dK_k = smem_desc(s0 + C::OFF_K + koff, 16, 1024);    // B of S: [keys x d], K-major
-      const uint64_t dV_k = smem_desc(s0 + C::OFF_V + koff, 16, 1024);    // B of dP
-      const uint64_t dK_mn = smem_desc(s0 + C::OFF_K + koff, 64 * 128, 1024);  // B of dQ: (K = keys, N = d), MN-major
-      const uint64_t dQi_k = smem_desc(s0 + C::OFF_Q + i * TILE_BYTES, 16, 1024);         // A of S
-      const uint64_t dQi_mn = smem_desc(s0 + C::OFF_Q + i * TILE_BYTES, 64 * 128, 1024);  // B of dK (K = q rows, N = d)
-      const uint64_t dOi_k = smem_desc(s0 + C::OFF_DO + i * TILE_BYTES, 16, 1024);        // A of dP
-      const uint64_t dOi_mn = smem_desc(s0 + C::OFF_DO + i * TILE_BYTES, 64 * 128, 1024); // B of dV
-      const uint32_t id_s = instr_desc(BLOCK_Q, nj, 0, 0);
-      if (blk > 0) {
-        mbar_wait(bar_sfree, ph ^ 1);  // the previous block's S / dP have been read
-        tc_fence_after();
-      }
-      if (elect_one_sync()) {
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma_f16(tmem_base + C::TM_S, dQi_k + (uint64_t)(ks * 2), dK_k + (uint64_t)(ks * 2), id_s, ks > 0 ? 1u : 0u);
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma_f16(tmem_base + C::TM_DP, dOi_k + (uint64_t)(ks * 2), dV_k + (uint64_t)(ks * 2), id_s, ks > 0 ? 1u : 0u);
-        umma_commit(bar_sdp);
-      }
-      __syncwarp();
-      mbar_wait(bar_pds, ph);
-      if (i == 0 && j > 0) mbar_wait(bar_dkvfree, (j - 1) & 1);  // dK / dV of the previous key tile have been drained
-      tc_fence_after();
-      if (elect_one_sync()) {
-        // dV_j (+)= P^T dO_i, dK_j (+)= dS^T Q_i : M = 128 key lanes (lanes >= nj carry zeros / unused), K = 128 query rows
-#pragma unroll 1
-        for (int ks = 0; ks < 8; ++ks)
-          umma_f16(tmem_base + C::TM_DV, dP_mn + (uint64_t)((ks * 2048) >> 4), dOi_mn + (uint64_t)((ks * 2048) >> 4), id_kv,
-                   (i > 0 || ks > 0) ? 1u : 0u);
-#pragma unroll 1
-        for (int ks = 0; ks < 8; ++ks)
-          umma_f16(tmem_base + C::TM_DK, dS_mn + (uint64_t)((ks * 2048) >> 4), dQi_mn + (uint64_t)((ks * 2048) >> 4), id_kv,
-                   (i > 0 || ks > 0) ? 1u : 0u);
-        // dQ_i (+)= dS K_j : K = nj keys in steps of 16
-#pragma unroll 1
-        for (int ks = 0; ks < nj / 16; ++ks)
-          umma_f16(tmem_base + C::TM_DQ + i * 64, dS_k + (uint64_t)(((ks >> 2) * TILE_BYTES + (ks & 3) * 32) >> 4),
-                   dK_mn + (uint64_t)((ks * 2048) >> 4), id_dq, (j > 0 || ks > 0) ? 1u : 0u);
-        umma_commit(bar_mma2);
-      }
-      __syncwarp();
-    }
-  } else {
-    // ===================== worker warps =====================
-    const int g = warp >> 2, q = warp & 3;   // g: column group of the fused pass / which accumulator columns this group drains
-    const int r = q * 32 + lane;             // row inside a 128-row tile == TMEM lane
-    const uint32_t tL = tmem_base + ((uint32_t)(q * 32) << 16);
-    const float sl2 = scale * kLog2e;
-    uint8_t* sP = smem + C::OFF_P;
-    uint8_t* sS = smem + C::OFF_DS;
-    if (g < 2) {  // per-row constants of rows 0..255: base-2 LSE (+inf on rows past the sequence: p = 0 there) and D
-      const int m = g * BLOCK_Q + r;
-      float L = INFINITY, D = 0.f;
-      if (m < N) {
-        L = lse[((size_t)b * h + head) * N + m] * kLog2e;
-        const uint4* po = reinterpret_cast<const uint4*>(outp + (row0 + m) * ld_out + head * HD);
-        const uint4* pd = reinterpret_cast<const uint4*>(dout + (row0 + m) * ld_out + head * HD);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const uint4 a = __ldg(po + e), c = __ldg(pd + e);
-          const uint32_t aa[4] = {a.x, a.y, a.z, a.w}, cc[4] = {c.x, c.y, c.z, c.w};
-#pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            const float2 x = unpack_bf16x2(aa[w]), y = unpack_bf16x2(cc[w]);
-            D = fmaf(x.x, y.x, D);
-            D = fmaf(x.y, y.y, D);
-          }
-        }
-      }
-      sL[m] = L;
-      sD[m] = D;
-      if (threadIdx.x < 192) sC[threadIdx.x] = 0.f;
-    }
-    named_bar_sync(1, 512);
-    for (int blk = 0; blk < nb; ++blk) {
-      const uint32_t ph = blk & 1;
-      const int j = blk / n_tiles, i = blk % n_tiles;
-      const int nu = (j ? C::NJ1 : C::NJ0) / 8;             // 8-key units of this key tile
-      const int u0 = (nu * g + 3) / 4, u1 = (nu * (g + 1) + 3) / 4;  // my units (at most 4)
-      const int key0 = j * C::NJ0;
-      const float L = sL[i * BLOCK_Q + r], D = sD[i * BLOCK_Q + r];
-      uint32_t pw[4][4], dw[4][4];
-      mbar_wait(bar_sdp, ph);
-      tc_fence_after();
-#pragma unroll
-      for (int uu = 0; uu < 4; ++uu) {
-        const int u = u0 + uu;
-        if (u < u1) {
-          uint32_t sv[8], dv[8];
-          tmem_ld_32x8(tL + C::TM_S + u * 8, sv);
-          tmem_ld_32x8(tL + C::TM_DP + u * 8, dv);
-          tmem_ld_wait();
-          const int kb = key0 + u * 8;
-          const bool full = kb + 8 <= N;                     // warp-uniform: only the last units of key tile 1 hold padded keys
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 s2 = unpack_bf16x2(pack_bf16x2(__uint_as_float(sv[2 * e]), __uint_as_float(sv[2 * e + 1])));
-            const float2 d2 = unpack_bf16x2(pack_bf16x2(__uint_as_float(dv[2 * e]), __uint_as_float(dv[2 * e + 1])));
-            float p0 = ex2_ftz(fmaf(s2.x, sl2, -L)), p1 = ex2_ftz(fmaf(s2.y, sl2, -L));
-            if (!full) {
-              if (kb + 2 * e >= N) p0 = 0.f;
-              if (kb + 2 * e + 1 >= N) p1 = 0.f;
-            }
-            const uint32_t pk = pack_bf16x2(p0, p1);
-            const float2 pr = unpack_bf16x2(pk);             // the bf16-rounded probability is what multiplies (autocast operand)
-            pw[uu][e] = pk;
-            dw[uu][e] = pack_bf16x2(pr.x * (d2.x - D), pr.y * (d2.y - D));
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_sfree);
-      if (blk > 0) mbar_wait(bar_mma2, ph ^ 1);              // the previous block's MMAs have read the P / dS tiles
-#pragma unroll
-      for (int uu = 0; uu < 4; ++uu) {
-        const int u = u0 + uu;
-        if (u < u1) {
-          const uint32_t off = (uint32_t)((u >> 3) * TILE_BYTES) + swz(r, u & 7);
-          *reinterpret_cast<uint4*>(sP + off) = make_uint4(pw[uu][0], pw[uu][1], pw[uu][2], pw[uu][3]);
-          *reinterpret_cast<uint4*>(sS + off) = make_uint4(dw[uu][0], dw[uu][1], dw[uu][2], dw[uu][3]);
-        }
-      }
-      fence_proxy_async();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_pds);
-      if (i == n_tiles - 1) {
-        // ---- dK_j / dV_j complete: groups 0 / 1 drain dK columns [0,32) / [32,64), groups 2 / 3 dV (key row = TMEM lane)
-        mbar_wait(bar_mma2, ph);
-        tc_fence_after();
-        const int key = key0 + r;
-        const bool ok = r < (j ? C::NJ1 : C::NJ0) && key < N;
-        const int is_v = g >> 1, c = g & 1;
-        __nv_bfloat16* base = dqkv + (row0 + key) * ld_dtok + head * HD + (size_t)(1 + is_v) * h * HD;
-        drain_cols32(tL + (is_v ? C::TM_DV : C::TM_DK), c, is_v ? 1.f : scale, ok, base, colsum ? sC + 64 + 64 * is_v : nullptr, lane);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_dkvfree);
-      }
-    }
-    // ---- dQ_0 / dQ_1 (accumulated over the key tiles): groups 0 / 1 drain dQ_0 columns [0,32) / [32,64), groups 2 / 3 dQ_1
-    {
-      const int i = g >> 1, c = g & 1;
-      if (i < n_tiles) {
-        const int m = i * BLOCK_Q + r;
-        drain_cols32(tL + C::TM_DQ + i * 64, c, scale, m < N, dqkv + (row0 + m) * ld_dtok + head * HD, colsum ? sC : nullptr, lane);
-      }
-    }
-    named_bar_sync(1, 512);
-    if (colsum && threadIdx.x < 192) {
-      const int part = threadIdx.x >> 6, d = threadIdx.x & 63;
-      atomicAdd(colsum + (size_t)part * h * HD + head * HD + d, sC[threadIdx.x]);
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 16) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
 // ---- host side (driver entry point resolved at run time, as in gemm_tcgen05.cu) --------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -2185,76 +1111,6 @@ static int launch_fwd(const void* qkv, long long ld_tok, int B, int N, int G, in
   }
   launch_kernel(attn_fwd_tc_kernel<NKV16>, ((B + G - 1) / G) * h, C::THREADS, C::SMEM_BYTES, s, tmQ, tmKV, B, N, G, h, scale, (__nv_bfloat16*)out,
                                                                                   ld_out, lse);
-  B200_CHECK_LAUNCH();
-  return B200_OK;
-}
-
-template <int NKV16>
-static int launch_fwd3(const void* qkv, long long ld_tok, int B, int N, int G, int h, float scale, void* out, long long ld_out,
-                       float* lse, cudaStream_t s) {
-  using C = Fwd3Cfg<NKV16>;
-  CUtensorMap tmQ, tmKV;
-  int rc = tmap_rows(&tmQ, qkv, (long long)B * N, 3LL * h * HD, ld_tok, BLOCK_Q);
-  if (rc) return rc;
-  rc = tmap_rows(&tmKV, qkv, (long long)B * N, 3LL * h * HD, ld_tok, C::NKV);
-  if (rc) return rc;
-  static bool attr = false;
-  if (!attr) {
-    if (cudaFuncSetAttribute(attn_fwd_tc3_kernel<NKV16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
-      return B200_ERR_CUDA;
-    attr = true;
-  }
-  const int tiles = (G * N + BLOCK_Q - 1) / BLOCK_Q;  // query tiles per (image group, head): 1 or 2
-  launch_kernel(attn_fwd_tc3_kernel<NKV16>, ((B + G - 1) / G) * h * tiles, C::THREADS, C::SMEM_BYTES, s, tmQ, tmKV, B, N, G, h, tiles,
-                scale, (__nv_bfloat16*)out, ld_out, lse);
-  B200_CHECK_LAUNCH();
-  return B200_OK;
-}
-
-template <int NKV16>
-static int launch_fwd4(const void* qkv, long long ld_tok, int B, int N, int G, int h, float scale, void* out, long long ld_out,
-                       float* lse, cudaStream_t s) {
-  using C = Fwd4Cfg<NKV16>;
-  CUtensorMap tmQ, tmKV;
-  int rc = tmap_rows(&tmQ, qkv, (long long)B * N, 3LL * h * HD, ld_tok, BLOCK_Q);
-  if (rc) return rc;
-  rc = tmap_rows(&tmKV, qkv, (long long)B * N, 3LL * h * HD, ld_tok, C::NKV);
-  if (rc) return rc;
-  static bool attr = false;
-  static int num_sms = 0;
-  if (!attr) {
-    if (cudaFuncSetAttribute(attn_fwd_tc4_kernel<NKV16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
-      return B200_ERR_CUDA;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    attr = true;
-  }
-  const int n_groups = ((B + G - 1) / G) * h;
-  const int grid = n_groups < num_sms ? n_groups : num_sms;
-  launch_kernel(attn_fwd_tc4_kernel<NKV16>, grid, C::THREADS, C::SMEM_BYTES, s, tmQ, tmKV, B, N, G, h, n_groups, scale,
-                (__nv_bfloat16*)out, ld_out, lse);
-  B200_CHECK_LAUNCH();
-  return B200_OK;
-}
-
-template <int NKV16>
-static int launch_fwd5(const void* qkv, long long ld_tok, int B, int N, int G, int h, float scale, void* out, long long ld_out,
-                       float* lse, cudaStream_t s) {
-  using C = Fwd5Cfg<NKV16>;
-  CUtensorMap tmQ, tmKV;
-  int rc = tmap_rows(&tmQ, qkv, (long long)B * N, 3LL * h * HD, ld_tok, BLOCK_Q);
-  if (rc) return rc;
-  rc = tmap_rows(&tmKV, qkv, (long long)B * N, 3LL * h * HD, ld_tok, C::NKV);
-  if (rc) return rc;
-  static bool attr = false;
-  if (!attr) {
-    if (cudaFuncSetAttribute(attn_fwd_tc5_kernel<NKV16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
-      return B200_ERR_CUDA;
-    attr = true;
-  }
-  launch_kernel(attn_fwd_tc5_kernel<NKV16>, ((B + G - 1) / G) * h, C::THREADS, C::SMEM_BYTES, s, tmQ, tmKV, B, N, G, h, scale,
-                (__nv_bfloat16*)out, ld_out, lse);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -2333,29 +1189,6 @@ static int launch_bwd(const void* qkv, long long ld_tok, const void* out, const 
   return B200_OK;
 }
 
-template <int NKV16>
-static int launch_bwd2(const void* qkv, long long ld_tok, const void* out, const void* dout, long long ld_out, const float* lse, int B,
-                       int N, int h, float scale, void* dqkv, long long ld_dtok, float* colsum, cudaStream_t s) {
-  using C = Bwd2Cfg<NKV16>;
-  CUtensorMap tmQ, tmKV, tmDO;
-  int rc = tmap_rows(&tmQ, qkv, (long long)B * N, 3LL * h * HD, ld_tok, BLOCK_Q);
-  if (rc) return rc;
-  rc = tmap_rows(&tmKV, qkv, (long long)B * N, 3LL * h * HD, ld_tok, C::NKV);
-  if (rc) return rc;
-  rc = tmap_rows(&tmDO, dout, (long long)B * N, (long long)h * HD, ld_out, BLOCK_Q);
-  if (rc) return rc;
-  static bool attr = false;
-  if (!attr) {
-    if (cudaFuncSetAttribute(attn_bwd_tc2_kernel<NKV16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
-      return B200_ERR_CUDA;
-    attr = true;
-  }
-  launch_kernel(attn_bwd_tc2_kernel<NKV16>, B * h, C::THREADS, C::SMEM_BYTES, s, tmQ, tmKV, tmDO, (const __nv_bfloat16*)out,
-                (const __nv_bfloat16*)dout, ld_out, lse, B, N, h, scale, (__nv_bfloat16*)dqkv, ld_dtok, colsum);
-  B200_CHECK_LAUNCH();
-  return B200_OK;
-}
-
 }  // namespace attn_tc
 }  // namespace b200
 
@@ -2368,13 +1201,14 @@ extern "C" int b200_attention_fwd_tc(const void* qkv, long long ld_tok, int B, i
   if (N > 256) return B200_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
   // B200_ATTN_FWD_SCHEDULE: 8 (default) P in tensor memory, persistent CTAs (two per SM) with the next tile's Q / K / V
-  // prefetched: 41 us at 768 pairs x 197 tokens; 7 the same without persistence (45 us); 1 both tiles per CTA, P through shared
-  // memory (62 us); 3 one tile per CTA through shared memory (68 us); 4 persistent, P through shared memory (72 us); 5 sixteen
-  // softmax warps (57 us) -- kept for A/B timing, all numerically identical (tools/attn_check.py)
+  // prefetched: 41 us at 768 pairs x 197 tokens; 7 the same without persistence (45 us); 1 the first tcgen05 version: both tiles
+  // per CTA, P through swizzled shared memory (62 us).  All numerically identical (tools/attn_check.py).  Three more schedules
+  // that carried P through shared memory (one tile per CTA x two CTAs per SM: 68 us; persistent with TMA prefetch: 72 us;
+  // sixteen softmax warps: 57 us) were measured and removed: profiles/r02_attn_*time*.log, DESIGN.md 6.3.
   static int sched = -1;
   if (sched < 0) {
     const char* e = std::getenv("B200_ATTN_FWD_SCHEDULE");
-    sched = (e && e[0] >= '1' && e[0] <= '8') ? e[0] - '0' : 8;
+    sched = (e && (e[0] == '1' || e[0] == '7' || e[0] == '8')) ? e[0] - '0' : 8;
   }
   if (sched == 8) {
     if (N <= 128) return launch_fwd8<8>(qkv, ld_tok, B, N, 128 / N, h, scale, out, ld_out, lse, s);
@@ -2385,21 +1219,6 @@ extern "C" int b200_attention_fwd_tc(const void* qkv, long long ld_tok, int B, i
     if (N <= 128) return launch_fwd7<8>(qkv, ld_tok, B, N, 128 / N, h, scale, out, ld_out, lse, s);
     if (N <= 208) return launch_fwd7<13>(qkv, ld_tok, B, N, 1, h, scale, out, ld_out, lse, s);
     return launch_fwd7<16>(qkv, ld_tok, B, N, 1, h, scale, out, ld_out, lse, s);
-  }
-  if (sched == 5) {
-    if (N <= 128) return launch_fwd5<8>(qkv, ld_tok, B, N, 128 / N, h, scale, out, ld_out, lse, s);
-    if (N <= 208) return launch_fwd5<13>(qkv, ld_tok, B, N, 1, h, scale, out, ld_out, lse, s);
-    return launch_fwd<16>(qkv, ld_tok, B, N, 1, h, scale, out, ld_out, lse, s);  // NKV = 256: P tiles + exchange buffers exceed smem
-  }
-  if (sched == 4) {
-    if (N <= 128) return launch_fwd4<8>(qkv, ld_tok, B, N, 128 / N, h, scale, out, ld_out, lse, s);
-    if (N <= 208) return launch_fwd4<13>(qkv, ld_tok, B, N, 1, h, scale, out, ld_out, lse, s);
-    return launch_fwd<16>(qkv, ld_tok, B, N, 1, h, scale, out, ld_out, lse, s);  // NKV = 256 does not fit two K/V stages
-  }
-  if (sched == 3) {
-    if (N <= 128) return launch_fwd3<8>(qkv, ld_tok, B, N, 128 / N, h, scale, out, ld_out, lse, s);
-    if (N <= 208) return launch_fwd3<13>(qkv, ld_tok, B, N, 1, h, scale, out, ld_out, lse, s);
-    return launch_fwd3<16>(qkv, ld_tok, B, N, 1, h, scale, out, ld_out, lse, s);
   }
   // N <= 128: as many whole images as fit one 128-row tile share a CTA (local crops: 3 x 37 tokens), keys padded to 128
   if (N <= 128) return launch_fwd<8>(qkv, ld_tok, B, N, 128 / N, h, scale, out, ld_out, lse, s);
@@ -2417,12 +1236,6 @@ extern "C" int b200_attention_bwd_tc(const void* qkv, long long ld_tok, const vo
   if (((uintptr_t)qkv & 15) || ((uintptr_t)out & 15) || ((uintptr_t)dout & 15) || ((uintptr_t)dqkv & 15)) return B200_ERR_UNSUPPORTED;
   if (N > 208) return B200_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
-  static int bsched = -1;  // B200_ATTN_BWD_SCHEDULE = 2: key-tile-outer blocks with one fused pass (N > 128); 1 (default): query-tile chain
-  if (bsched < 0) {
-    const char* e = std::getenv("B200_ATTN_BWD_SCHEDULE");
-    bsched = (e && e[0] == '2') ? 2 : 1;
-  }
-  if (bsched == 2 && N > 128) return launch_bwd2<13>(qkv, ld_tok, out, dout, ld_out, lse, B, N, h, scale, dqkv, ld_dtok, dqkv_colsum, s);
   static int groups = -1;  // B200_ATTN_BWD_GROUPS = 4 (default; 16 worker warps: each row's keys split four ways) | 2 (8 worker warps)
   if (groups < 0) {
     const char* e = std::getenv("B200_ATTN_BWD_GROUPS");
