@@ -211,7 +211,7 @@ __device__ __forceinline__ MaxSum2 block_maxsum2(MaxSum2 v, MaxSum2* red) {
   return r;
 }
 
-// THREADS / UNROLL2 are tuning variants (B200_CE_VARIANT=0..3 for A/B runs; profiles/r02_loss_bench.log): 512 threads with one
+// THREADS / UNROLL2 were tuning parameters (profiles/r02_loss_bench.log; only <512, false> is instantiated): 512 threads with one
 // 16-byte load per tensor in flight measured fastest (masked rows, fused LSE: 445 us; 256 threads x 4 rows per SM and / or two
 // loads in flight: 486-545 us -- the kernel is bound by MUFU + issue, more registers per thread only cost occupancy).
 template <bool FUSE_T_LSE, int THREADS, bool UNROLL2>
@@ -321,126 +321,6 @@ dino_ce_kernel(const __nv_bfloat16* __restrict__ s, long long lds, int Rs, int K
   }
   dot = block_sum(dot, redf);
   if (threadIdx.x == 0) loss_rows[r] = w * (n_t * lse - s_scale * dot);
-}
-
-// ------------------------------------------------------------------------------------------------
-// CE with the student row staged in shared memory (K * 2 B <= 160 KB: K = 65536 -> 128 KB).
-// ncu of the kernel above at cfg2 (profiles/r02_ncu_loss_optim.txt): 1.90 GB of DRAM reads for 0.98 GB of algorithmic reads --
-// with 2-4 rows in flight per SM the "L2-resident" second pass over the 128 KB student and teacher rows misses L2 (up to 150 MB
-// of rows in flight against 126 MB of L2).  Here one 1024-thread CTA per SM owns one row at a time: pass 1 streams the student
-// row from HBM into shared memory (four 16-byte loads in flight per thread) while accumulating its log-sum-exp (and
-// the teacher row's, when fused); pass 2 reads the student row from shared memory and the teacher row(s) from L2 (148 rows x
-// 128 KB in flight: resident), so DRAM traffic equals the algorithmic bytes.
-static constexpr int CE_SM_THREADS = 1024;
-template <bool FUSE_T_LSE>
-__global__ void __launch_bounds__(CE_SM_THREADS, 1)
-dino_ce_smem_kernel(const __nv_bfloat16* __restrict__ s, long long lds, int Rs, int K, const __nv_bfloat16* __restrict__ t,
-                    long long ldt, const float* __restrict__ colterm, const float* __restrict__ t_rowterm,
-                    const int* __restrict__ t_idx0, const int* __restrict__ t_idx1, const float* __restrict__ weight,
-                    float s_scale, float t_scale, const float* __restrict__ t_scale_dev, float gscale,
-                    float* __restrict__ loss_rows, __nv_bfloat16* __restrict__ ds, long long ldds) {
-  B200_PDL_SYNC();
-  extern __shared__ uint4 srow[];  // the student row, K / 8 chunks of 8 bf16
-  __shared__ MaxSum2 red[32];
-  __shared__ MaxSum2 red_t[32];
-  __shared__ float redf[32];
-  constexpr float kL2e = 1.4426950408889634f;
-  if (t_scale_dev) t_scale = __ldg(t_scale_dev);
-  const float ss2 = s_scale * kL2e, ts2 = t_scale * kL2e;
-  const int nchunk = K >> 3;
-  for (int r = blockIdx.x; r < Rs; r += gridDim.x) {
-    const float w = weight ? __ldg(weight + r) : 1.f;
-    const int i0 = t_idx0[r];
-    const int i1 = (!FUSE_T_LSE && t_idx1) ? t_idx1[r] : -1;
-    const float n_t = (i1 >= 0) ? 2.f : 1.f;
-    const uint4* sr = reinterpret_cast<const uint4*>(s + (size_t)r * lds);
-    const uint4* t0 = reinterpret_cast<const uint4*>(t + (size_t)i0 * ldt);
-    const uint4* t1 = (i1 >= 0) ? reinterpret_cast<const uint4*>(t + (size_t)i1 * ldt) : nullptr;
-    __syncthreads();  // the previous row's pass 2 has finished reading srow
-    // ---- pass 1: HBM -> smem, log-sum-exp of the student row (and of the teacher row when fused), base 2
-    MaxSum2 acc{-INFINITY, 0.f}, acc_t{-INFINITY, 0.f};
-    constexpr int NB = FUSE_T_LSE ? 2 : 4;  // 16-byte loads in flight per thread and tensor (64 registers at 1024 threads)
-    for (int c0 = threadIdx.x; c0 < nchunk; c0 += NB * CE_SM_THREADS) {
-      uint4 sv[NB], tv[NB];
-#pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        const int c = c0 + j * CE_SM_THREADS;
-        if (c < nchunk) {
-          sv[j] = sr[c];
-          if (FUSE_T_LSE) tv[j] = t0[c];
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        const int c = c0 + j * CE_SM_THREADS;
-        if (c < nchunk) {
-          srow[c] = sv[j];
-          float v[8];
-          const float2 a = unpack_bf16x2(sv[j].x), b = unpack_bf16x2(sv[j].y), cc = unpack_bf16x2(sv[j].z), d = unpack_bf16x2(sv[j].w);
-          v[0] = a.x * ss2; v[1] = a.y * ss2; v[2] = b.x * ss2; v[3] = b.y * ss2;
-          v[4] = cc.x * ss2; v[5] = cc.y * ss2; v[6] = d.x * ss2; v[7] = d.y * ss2;
-          ms2_add8(acc, v);
-          if (FUSE_T_LSE) {
-            float ct[8];
-            if (colterm) load8f(colterm + c * 8, ct);
-            const float2 ta = unpack_bf16x2(tv[j].x), tb = unpack_bf16x2(tv[j].y), tc = unpack_bf16x2(tv[j].z), td = unpack_bf16x2(tv[j].w);
-            const float tf[8] = {ta.x, ta.y, tb.x, tb.y, tc.x, tc.y, td.x, td.y};
-            float u[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) u[i] = fmaf(tf[i], ts2, colterm ? ct[i] * kL2e : 0.f);
-            ms2_add8(acc_t, u);
-          }
-        }
-      }
-    }
-    const MaxSum2 st = block_maxsum2(acc, red);  // (its barriers also publish srow to the whole CTA)
-    const float lse2 = st.m + __log2f(st.s);
-    const float lse = lse2 * 0.6931471805599453f;
-    float rt0, rt1 = 0.f;
-    if (FUSE_T_LSE) {
-      const MaxSum2 tt = block_maxsum2(acc_t, red_t);
-      rt0 = -(tt.m + __log2f(tt.s));
-    } else {
-      rt0 = __ldg(t_rowterm + i0) * kL2e;
-      if (i1 >= 0) rt1 = __ldg(t_rowterm + i1) * kL2e;
-    }
-    // ---- pass 2: student from smem, teacher row(s) from L2, gradient row to HBM
-    float dot = 0.f;
-    const float gw = w * s_scale * gscale;
-    uint4* dr = ds ? reinterpret_cast<uint4*>(ds + (size_t)r * ldds) : nullptr;
-    for (int c = threadIdx.x; c < nchunk; c += CE_SM_THREADS) {
-      const uint4 sq = srow[c];
-      const uint4 tq = t0[c];
-      float ct[8], p[8];
-      if (colterm) load8f(colterm + c * 8, ct);
-      const float2 a = unpack_bf16x2(sq.x), b = unpack_bf16x2(sq.y), cc = unpack_bf16x2(sq.z), d = unpack_bf16x2(sq.w);
-      const float sv8[8] = {a.x, a.y, b.x, b.y, cc.x, cc.y, d.x, d.y};
-      const float2 ta = unpack_bf16x2(tq.x), tb = unpack_bf16x2(tq.y), tc = unpack_bf16x2(tq.z), td = unpack_bf16x2(tq.w);
-      const float tf[8] = {ta.x, ta.y, tb.x, tb.y, tc.x, tc.y, td.x, td.y};
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        ct[i] = colterm ? ct[i] * kL2e : 0.f;
-        p[i] = ex2_ftz(fmaf(tf[i], ts2, ct[i] + rt0));
-      }
-      if (t1) {
-        const uint4 uq = t1[c];
-        const float2 ua = unpack_bf16x2(uq.x), ub = unpack_bf16x2(uq.y), uc = unpack_bf16x2(uq.z), ud = unpack_bf16x2(uq.w);
-        const float uf[8] = {ua.x, ua.y, ub.x, ub.y, uc.x, uc.y, ud.x, ud.y};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) p[i] += ex2_ftz(fmaf(uf[i], ts2, ct[i] + rt1));
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) dot = fmaf(p[i], sv8[i], dot);
-      if (dr) {
-        float g[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) g[i] = gw * (n_t * ex2_ftz(fmaf(sv8[i], ss2, -lse2)) - p[i]);
-        dr[c] = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
-      }
-    }
-    dot = block_sum(dot, redf);
-    if (threadIdx.x == 0) loss_rows[r] = w * (n_t * lse - s_scale * dot);
-  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -716,55 +596,18 @@ extern "C" int b200_dino_ce(const void* s, long long lds, int Rs, int K, const v
   if (!s || !t || !t_idx0 || !loss_rows || Rs <= 0 || K <= 0) return B200_ERR_INVALID_ARG;
   if (!t_rowterm && t_idx1) return B200_ERR_INVALID_ARG;  // the fused teacher LSE covers single-teacher rows only
   if ((K % 8) || (lds % 8) || (ldt % 8) || (ds && (ldds % 8))) return B200_ERR_INVALID_ARG;
-  static int variant = -1;
-  static int num_sms = 0;
-  if (variant < 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    // B200_CE_VARIANT: 4 = student row staged in shared memory; 0..3 = streaming kernel tuning variants
-    const char* e = std::getenv("B200_CE_VARIANT");
-    variant = (e && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : 0;  // TODO(validate): default 4 once the smem kernel has run on hardware
-  }
-  if (variant == 4 && (size_t)K * 2 <= 160 * 1024 && ((uintptr_t)s & 15) == 0 && ((uintptr_t)t & 15) == 0) {
-    // student row staged in shared memory, persistent CTAs (one per SM)
-    static bool attr = false;
-    if (!attr) {
-      if (cudaFuncSetAttribute(dino_ce_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess ||
-          cudaFuncSetAttribute(dino_ce_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess)
-        return B200_ERR_CUDA;
-      attr = true;
-    }
-    const int grid = Rs < num_sms ? Rs : num_sms;
-    if (t_rowterm)
-      launch_kernel(dino_ce_smem_kernel<false>, grid, CE_SM_THREADS, (size_t)K * 2, (cudaStream_t)stream, (const __nv_bfloat16*)s, lds, Rs, K,
-                    (const __nv_bfloat16*)t, ldt, colterm, t_rowterm, t_idx0, t_idx1, weight, s_scale, t_scale, t_scale_dev, gscale,
-                    loss_rows, (__nv_bfloat16*)ds, ldds);
-    else
-      launch_kernel(dino_ce_smem_kernel<true>, grid, CE_SM_THREADS, (size_t)K * 2, (cudaStream_t)stream, (const __nv_bfloat16*)s, lds, Rs, K,
-                    (const __nv_bfloat16*)t, ldt, colterm, (const float*)nullptr, t_idx0, (const int*)nullptr, weight, s_scale, t_scale,
-                    t_scale_dev, gscale, loss_rows, (__nv_bfloat16*)ds, ldds);
-    B200_CHECK_LAUNCH();
-    return B200_OK;
-  }
-  const int sv = variant == 4 ? 0 : variant;  // rows too long for shared memory: streaming kernel, 512 threads, one load in flight
+  // 512 threads per row, one 16-byte load per tensor in flight: the fastest of the measured launch shapes (256 threads x 4 rows
+  // per SM, two loads in flight, a persistent variant staging the student row in shared memory: profiles/r02_loss_bench*.log)
   const __nv_bfloat16* sp = (const __nv_bfloat16*)s;
   const __nv_bfloat16* tp = (const __nv_bfloat16*)t;
   __nv_bfloat16* dsp = (__nv_bfloat16*)ds;
   cudaStream_t st = (cudaStream_t)stream;
-#define B200_CE(F, TH, U)                                                                                                       \
-  launch_kernel(dino_ce_kernel<F, TH, U>, Rs, TH, 0, st, sp, lds, Rs, K, tp, ldt, colterm, (const float*)(F ? nullptr : t_rowterm), \
-                t_idx0, (const int*)(F ? nullptr : t_idx1), weight, s_scale, t_scale, t_scale_dev, gscale, loss_rows, dsp, ldds)
-#define B200_CE_V(F)                                          \
-  switch (sv) {                                               \
-    case 0: B200_CE(F, 512, false); break;                    \
-    case 1: B200_CE(F, 512, true); break;                     \
-    case 2: B200_CE(F, 256, false); break;                    \
-    default: B200_CE(F, 256, true); break;                    \
-  }
-  if (t_rowterm) { B200_CE_V(false) } else { B200_CE_V(true) }
-#undef B200_CE_V
-#undef B200_CE
+  if (t_rowterm)
+    launch_kernel(dino_ce_kernel<false, 512, false>, Rs, 512, 0, st, sp, lds, Rs, K, tp, ldt, colterm, t_rowterm, t_idx0, t_idx1, weight,
+                  s_scale, t_scale, t_scale_dev, gscale, loss_rows, dsp, ldds);
+  else
+    launch_kernel(dino_ce_kernel<true, 512, false>, Rs, 512, 0, st, sp, lds, Rs, K, tp, ldt, colterm, (const float*)nullptr, t_idx0,
+                  (const int*)nullptr, weight, s_scale, t_scale, t_scale_dev, gscale, loss_rows, dsp, ldds);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

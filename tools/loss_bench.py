@@ -1,6 +1,7 @@
 """Microbench of the loss-path kernels at the cfg2 shapes (K = 65536): fused-LSE CE over the masked-patch rows, two-teacher CE
-over the cls rows, row_lse, and the optimizer sweep, timed with CUDA events between L2 flushes.  B200_CE_VARIANT=0..3 selects
-the CE tuning variant (read once per process): python tools/loss_bench.py"""
+over the cls rows, row_lse, and the optimizer sweep, timed with CUDA events between L2 flushes: python tools/loss_bench.py
+(the `[variant N]` tag in profiles/r02_loss_bench*.log names the CE launch shapes that were A/B-timed with this tool; only the
+fastest, variant 0 = 512 threads / one load in flight, is left in csrc/loss.cu)"""
 import os
 import sys
 from pathlib import Path
@@ -41,7 +42,7 @@ nd = n_crops + LB
 idx0 = torch.cat([torch.arange(n_crops), torch.arange(LB) % 64, torch.arange(M)]).to(dev, torch.int32)
 idx1 = torch.cat([torch.full((n_crops,), -1), torch.arange(LB) % 64 + 64, torch.full((M,), -1)]).to(dev, torch.int32)
 w = torch.rand(s_logits.shape[0], device=dev)
-var = os.environ.get("B200_CE_VARIANT", "default(3)")
+var = os.environ.get("B200_CE_VARIANT", "0")
 
 us = timeit(lambda: ops.row_lse(t_logits[:n_crops], colterm, 25.0, rowterm[:n_crops]))
 print(f"[variant {var}] row_lse {n_crops} rows: {us:.1f} us  {2 * n_crops * K / us / 1e3:.0f} GB/s")
