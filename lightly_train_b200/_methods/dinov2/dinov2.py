@@ -18,7 +18,6 @@ torch.autograd bridge for trainers that insist on calling `loss.backward()` (INT
 from __future__ import annotations
 
 import atexit
-import contextlib
 import math
 import os
 import weakref
@@ -76,10 +75,6 @@ def _hook_process_group_teardown() -> None:
 
 # where the backbone backward is cut for the middle all-reduce bucket: blocks >= FRAC * depth go out after graph 2
 DDP_SPLIT_FRAC = float(os.environ.get("B200_DDP_SPLIT_FRAC", "0.5"))
-
-
-# run the teacher forward (ViT + heads + centering) on a second stream, concurrently with the student forward (opt-in)
-TEACHER_STREAM = os.environ.get("B200_TEACHER_STREAM", "0") == "1"
 
 
 def _world_size() -> int:
@@ -554,51 +549,45 @@ class DINOv2(nn.Module):
         self.s_arena.zero_grad()
         out: Dict[str, Tensor] = {}
 
-        # ---------------- teacher (dinov2.py:399-472), optionally on a second stream: it only meets the student at the
-        # cross-entropy, and two independent kernel sequences fill each other's wave tails and launch gaps
-        main_stream = torch.cuda.current_stream() if dev.type == "cuda" else None
-        t_stream = self._side_stream if (TEACHER_STREAM and main_stream is not None) else None
-        if t_stream is not None:
-            t_stream.wait_stream(main_stream)
-        with torch.cuda.stream(t_stream) if t_stream is not None else contextlib.nullcontext():
-            tctx = t_vit._fwd(gv, None, save=False)
-            Ng = tctx.dims[3]
-            cls_rows = torch.arange(n_crops, device=dev, dtype=torch.int64) * Ng
-            cls_rows_swapped = torch.cat([cls_rows[B:], cls_rows[:B]])  # A<->B swap (:415-417)
-            t_in = torch.empty(n_crops + M, D, device=dev, dtype=bf)
-            ops.gather_rows(tctx.xnorm, cls_rows_swapped, t_in[:n_crops])
-            ops.gather_rows(tctx.xnorm, mask_idx, t_in[n_crops:], Np=hh * ww, N=Ng, off=1 + R)
-            t_logits = torch.empty(n_crops + M, K, device=dev, dtype=bf)
-            if separate:
-                t_dino._fwd(t_in[:n_crops], save=False, logits=t_logits[:n_crops])
-                if M:
-                    t_ibot._fwd(t_in[n_crops:], save=False, logits=t_logits[n_crops:])
-            else:
-                t_dino._fwd(t_in, save=False, logits=t_logits)
-            del tctx
-            t_rowterm = torch.empty(n_crops + M, device=dev, dtype=f32)
-            colterm_d = torch.empty(K, device=dev, dtype=f32)
-            colterm_i = torch.empty(K, device=dev, dtype=f32)
-            if a.center_method == "softmax":
-                ops.vec_op(colterm_d, self.dino_loss.center.view(-1), t_scale, 0.0, 1, a_dev=t_scale_dev)
-                ops.vec_op(colterm_i, self.ibot_loss.center.view(-1), t_scale, 0.0, 1, a_dev=t_scale_dev)
-                # per-rank center batch sums (reduce_center_update, dinov2_loss.py:139-145 / :274-282)
-                out["dino_center_sum"] = torch.zeros(K, device=dev, dtype=f32)
-                ops.col_reduce(t_logits[:n_crops], out["dino_center_sum"])
-                out["ibot_center_sum"] = torch.zeros(K, device=dev, dtype=f32)
-                if M:
-                    rv = ibot_rowvec if ibot_rowvec is not None else torch.full((M,), 1.0 / M, device=dev, dtype=f32)
-                    ops.col_reduce(t_logits[n_crops:], out["ibot_center_sum"], rowvec=rv)
-            elif a.center_method == "sinkhorn_knopp":
-                # (graph replay: single-rank only -- with several ranks the prototype sums are all-reduced in the middle of
-                # this schedule, which stays on the eager launch path; `train_step` routes accordingly)
-                colterm_d = sinkhorn_colterm(t_logits[:n_crops], t_scale, scale_dev=t_scale_dev)
-                if M:
-                    colterm_i = sinkhorn_colterm(t_logits[n_crops:], t_scale, scale_dev=t_scale_dev, row_mask=pad_mask)
-            else:
-                raise ValueError(f"Unknown centering method: {a.center_method}")
-            ops.row_lse(t_logits[:n_crops], colterm_d, t_scale, t_rowterm[:n_crops], scale_dev=t_scale_dev)
-            # (the masked-patch rows' teacher log-sum-exp is computed inside the CE kernel: one HBM read of those logits)
+        # ---------------- teacher (dinov2.py:399-472)
+        tctx = t_vit._fwd(gv, None, save=False)
+        Ng = tctx.dims[3]
+        cls_rows = torch.arange(n_crops, device=dev, dtype=torch.int64) * Ng
+        cls_rows_swapped = torch.cat([cls_rows[B:], cls_rows[:B]])  # A<->B swap (:415-417)
+        t_in = torch.empty(n_crops + M, D, device=dev, dtype=bf)
+        ops.gather_rows(tctx.xnorm, cls_rows_swapped, t_in[:n_crops])
+        ops.gather_rows(tctx.xnorm, mask_idx, t_in[n_crops:], Np=hh * ww, N=Ng, off=1 + R)
+        t_logits = torch.empty(n_crops + M, K, device=dev, dtype=bf)
+        if separate:
+            t_dino._fwd(t_in[:n_crops], save=False, logits=t_logits[:n_crops])
+            if M:
+                t_ibot._fwd(t_in[n_crops:], save=False, logits=t_logits[n_crops:])
+        else:
+            t_dino._fwd(t_in, save=False, logits=t_logits)
+        del tctx
+        t_rowterm = torch.empty(n_crops + M, device=dev, dtype=f32)
+        colterm_d = torch.empty(K, device=dev, dtype=f32)
+        colterm_i = torch.empty(K, device=dev, dtype=f32)
+        if a.center_method == "softmax":
+            ops.vec_op(colterm_d, self.dino_loss.center.view(-1), t_scale, 0.0, 1, a_dev=t_scale_dev)
+            ops.vec_op(colterm_i, self.ibot_loss.center.view(-1), t_scale, 0.0, 1, a_dev=t_scale_dev)
+            # per-rank center batch sums (reduce_center_update, dinov2_loss.py:139-145 / :274-282)
+            out["dino_center_sum"] = torch.zeros(K, device=dev, dtype=f32)
+            ops.col_reduce(t_logits[:n_crops], out["dino_center_sum"])
+            out["ibot_center_sum"] = torch.zeros(K, device=dev, dtype=f32)
+            if M:
+                rv = ibot_rowvec if ibot_rowvec is not None else torch.full((M,), 1.0 / M, device=dev, dtype=f32)
+                ops.col_reduce(t_logits[n_crops:], out["ibot_center_sum"], rowvec=rv)
+        elif a.center_method == "sinkhorn_knopp":
+            # (with several ranks the prototype sums are all-reduced inside sinkhorn_colterm; under graph capture those NCCL
+            # kernels become part of the step graph, see `_graph_ok`)
+            colterm_d = sinkhorn_colterm(t_logits[:n_crops], t_scale, scale_dev=t_scale_dev)
+            if M:
+                colterm_i = sinkhorn_colterm(t_logits[n_crops:], t_scale, scale_dev=t_scale_dev, row_mask=pad_mask)
+        else:
+            raise ValueError(f"Unknown centering method: {a.center_method}")
+        ops.row_lse(t_logits[:n_crops], colterm_d, t_scale, t_rowterm[:n_crops], scale_dev=t_scale_dev)
+        # (the masked-patch rows' teacher log-sum-exp is computed inside the CE kernel: one HBM read of those logits)
 
         # ---------------- student forward (dinov2.py:474-519)
         sg = s_vit._fwd(gv, masks_u8, save=True, drop_path=True)
@@ -641,8 +630,6 @@ class DINOv2(nn.Module):
         loss_rows = torch.empty(Rs, device=dev, dtype=f32)
         ds = torch.empty(Rs, K, device=dev, dtype=bf)
         s_scale = 1.0 / a.student_temp
-        if t_stream is not None:
-            main_stream.wait_stream(t_stream)  # teacher logits / column terms / row terms are ready
         ops.dino_ce(s_logits[:nd], t_logits[:n_crops], colterm_d, t_rowterm[:n_crops], idx0[:nd], idx1[:nd], wrow[:nd],
                     s_scale, t_scale, loss_rows[:nd], ds[:nd], gscale=a.dino_loss_weight, t_scale_dev=t_scale_dev)
         if M:
