@@ -36,6 +36,8 @@ class _E:
 class _G:
     def replay(self): pass
 
+    def reset(self): pass
+
     def pool(self): return 0
 
 
@@ -108,6 +110,37 @@ def test_step_schedules_run(stubbed, kw):
         assert stubbed.get("b200_block_masks", 0) == 3 and stubbed.get("b200_collate_masks", 0) == 3
     if kw.get("depth", 0) >= 4 and not kw.get("graph"):
         pass  # split backward exercised (depth >= 4 cuts at depth / 2)
+
+
+def test_layernorm_prologue_gemm_route(stubbed, monkeypatch):
+    """B200_LN_GEMM=1: norm1 -> qkv and norm2 -> fc1 go through b200_ln_gemm (embed dim 128 <= 384, multiple of 64) in the
+    teacher and the dense student blocks; the policy helper refuses unsupported widths and the "auto" multi-wave case."""
+    from lightly_train_b200._models import dinov2_vit as V
+    monkeypatch.setattr(V, "LN_GEMM", "1")
+    monkeypatch.setattr(V, "_ln_gemm_wanted", lambda T, D, dev: V.LN_GEMM != "0" and D % 64 == 0 and D <= 384)  # cpu tensors here
+    m = _method(depth=2, dpr=0.0)
+    views = [torch.randn(4, 3, 64, 64) for _ in range(2)] + [torch.randn(4, 3, 32, 32) for _ in range(2)]
+    random.seed(0)
+    m.train_step({"views": views})
+    # per block 2 fused launches; teacher (global) + student global + student local = 3 passes x 2 blocks
+    assert stubbed.get("b200_ln_gemm", 0) == 3 * 2 * 2
+    monkeypatch.undo()
+    assert V._ln_gemm_wanted(1000, 768, torch.device("cpu")) is False
+
+
+def test_release_graphs_and_teardown_hook(stubbed, monkeypatch):
+    """release_graphs() drops the captured graphs; the process-group teardown hook releases every registered holder first."""
+    from lightly_train_b200._methods.dinov2 import dinov2 as Dm
+    m = _method(depth=2, dpr=0.0, graph=True)
+    views = [torch.randn(4, 3, 64, 64) for _ in range(2)] + [torch.randn(4, 3, 32, 32) for _ in range(2)]
+    random.seed(0)
+    m.train_step({"views": views})
+    assert m._static is not None and len(m._static["graphs"]) == 1
+    Dm._NCCL_GRAPH_HOLDERS.add(m)
+    Dm._release_all_nccl_graphs()
+    assert m._static is None
+    m.train_step({"views": views})  # re-captures on demand
+    assert m._static is not None
 
 
 def test_world_two_allreduce_buckets(stubbed, monkeypatch):
