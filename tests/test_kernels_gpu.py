@@ -142,10 +142,6 @@ def test_attention_fwd_bwd(B, N, h):
     torch.testing.assert_close(cs, ref, rtol=1e-4, atol=1e-3 * max(1.0, float(ref.abs().max())))
 
 
-_UNVALIDATED = pytest.mark.skipif(__import__("os").environ.get("B200_TEST_UNVALIDATED") != "1",
-                                  reason="kernel not yet validated on hardware this round: opt in with B200_TEST_UNVALIDATED=1")
-
-
 @pytest.mark.parametrize("B,N,h", [(3, 197, 6), (2, 201, 3), (5, 37, 2), (2, 256, 3), (2, 130, 2), (1, 16, 1), (3, 128, 2), (4, 100, 1),
                                    (7, 54, 3), (40, 197, 16)])
 def test_attention_fwd_tcgen05(B, N, h):
