@@ -77,6 +77,26 @@ def make_views(batch: int, n_local: int, seed: int, device, pin: bool = False, l
     return views
 
 
+def _bind_to_gpu_cores(local_rank: int):
+    """Restrict this process to the CPU cores NVML reports as local to GPU `local_rank`; returns the previous affinity (or
+    None when the topology cannot be read: nothing is changed then)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n + 63) // 64)
+        cpus = {i for i in range(n) if (words[i // 64] >> (i % 64)) & 1}
+        old = os.sched_getaffinity(0)
+        cpus &= old
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return old
+    except Exception:
+        return None
+
+
 # --------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
     def __init__(self, index: int) -> None:
@@ -522,7 +542,13 @@ def main() -> None:
     # ---- e2e: host (pinned) crops -> device every step on a copy stream, loss read back every step
     e2e = None
     if not args.no_e2e:
+        # the pinned staging buffers are allocated (first-touched) from the CPU cores that are local to this rank's GPU, as a
+        # launcher would with numactl: with several ranks per host every rank otherwise pins its buffers wherever it happens
+        # to run (B200_BENCH_NUMA_BIND=0 disables; the previous affinity is restored right after the allocation)
+        old_aff = _bind_to_gpu_cores(local_rank) if os.environ.get("B200_BENCH_NUMA_BIND", "0") == "1" else None
         host = [make_views(B, NL, 2000 * rank + i, None, pin=True, local=LS) for i in range(2)]
+        if old_aff is not None:
+            os.sched_setaffinity(0, old_aff)
         h2d_bytes = sum(v.numel() * 4 for v in host[0])
         copy_stream = torch.cuda.Stream(device=dev)
         dev_bufs = [[torch.empty_like(v, device=dev) for v in host[0]] for _ in range(2)]
